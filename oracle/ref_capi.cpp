@@ -1,0 +1,442 @@
+/*
+ * oracle/ref_capi.cpp — C-ABI driver around the UNMODIFIED reference sources.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (osmo_trx_b200/, include/)
+ * may include, link or call this file; only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs load the resulting
+ * oracle/_ref/libref_osmotrx.so.
+ *
+ * The reference's hot path has no FFI of its own (statically linked C++,
+ * SURVEY.md §8(b)), so this file is the thinnest possible batch loop over its
+ * per-burst API.  It #includes sigProcLib.cpp so that the file-static tables
+ * (sigProcLib.cpp:52-135) can be dumped for bit-for-bit table checks.
+ * No reference source is copied: the TUs are compiled where they lie under
+ * /root/reference (see oracle/Makefile).
+ */
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <complex>
+#include <algorithm>
+
+#include "sigProcLib.cpp" /* reference TU, pulled in for its statics */
+
+#include "Channelizer.h"
+#include "Synthesis.h"
+#include "grgsm_vitac/grgsm_vitac.h"
+#include "grgsm_vitac/viterbi_detector.h"
+
+extern "C" {
+#include "convert.h"
+}
+
+int gVectorDebug = 0; /* declared CommonLibs/Vector.h:45, defined nowhere in the tree */
+
+static void noop_free(void *) {}
+
+namespace {
+
+/* Non-owning view of caller memory as a signalVector. */
+struct BurstView {
+	signalVector v;
+	BurstView(const float *p, size_t n) : v((complex *)p, 0, n, NULL, noop_free) {}
+};
+
+template <class F> void parallel_for(int n, int nthreads, F f)
+{
+	if (nthreads <= 1 || n < 2 * nthreads) {
+		for (int i = 0; i < n; i++)
+			f(i);
+		return;
+	}
+	std::vector<std::thread> th;
+	int per = (n + nthreads - 1) / nthreads;
+	for (int t = 0; t < nthreads; t++) {
+		int lo = t * per, hi = std::min(n, lo + per);
+		if (lo >= hi)
+			break;
+		th.emplace_back([=]() {
+			for (int i = lo; i < hi; i++)
+				f(i);
+		});
+	}
+	for (auto &t : th)
+		t.join();
+}
+
+void fill_bits(BitVector &bv, const uint8_t *bits, int n)
+{
+	for (int i = 0; i < n; i++)
+		bv[i] = bits[i];
+}
+
+int copy_sv(const signalVector *sv, float *out, int max_cf)
+{
+	if (!sv)
+		return -1;
+	int n = (int)sv->size();
+	if (n > max_cf)
+		n = max_cf;
+	memcpy(out, sv->begin(), sizeof(float) * 2 * n);
+	return (int)sv->size();
+}
+
+bool g_setup_done = false;
+
+} // namespace
+
+extern "C" {
+
+/* osmo-trx.cpp:648-649 + Transceiver.cpp:207,212 */
+int ref_setup(void)
+{
+	if (g_setup_done)
+		return 0;
+	convolve_init();
+	convert_init();
+	if (!sigProcLibSetup())
+		return -1;
+	initvita();
+	g_setup_done = true;
+	return 0;
+}
+
+/* ---- table dumps (sigProcLib.cpp:52-135 statics) ---- */
+int ref_get_table(const char *name, int idx, float *out, int max_floats)
+{
+	const float *src = NULL;
+	int n = 0;
+	float tmp[8];
+	std::string s(name);
+	auto sv = [&](const signalVector *v) { src = (const float *)v->begin(); n = 2 * (int)v->size(); };
+	auto cs = [&](const CorrelationSequence *c, bool meta) {
+		if (!meta) {
+			sv(c->sequence);
+		} else {
+			tmp[0] = c->gain.real(); tmp[1] = c->gain.imag(); tmp[2] = c->toa;
+			src = tmp; n = 3;
+		}
+	};
+	if (s == "sinc") { src = sincTable; n = TABLESIZE + 1; }
+	else if (s == "rot4") sv(GMSKRotation4);
+	else if (s == "rrot4") sv(GMSKReverseRotation4);
+	else if (s == "rot1") sv(GMSKRotation1);
+	else if (s == "rrot1") sv(GMSKReverseRotation1);
+	else if (s == "delay") { if (idx < 0 || idx >= DELAYFILTS) return -1; sv(delayFilters[idx]); }
+	else if (s == "pulse4_c0") sv(GSMPulse4->c0);
+	else if (s == "pulse4_c1") sv(GSMPulse4->c1);
+	else if (s == "pulse4_c0inv") sv(GSMPulse4->c0_inv);
+	else if (s == "pulse1_c0") sv(GSMPulse1->c0);
+	else if (s == "midamble" || s == "midamble_meta") { if (idx < 0 || idx > 7) return -1; cs(gMidambles[idx], s == "midamble_meta"); }
+	else if (s == "edge_midamble" || s == "edge_midamble_meta") { if (idx < 0 || idx > 7) return -1; cs(gEdgeMidambles[idx], s == "edge_midamble_meta"); }
+	else if (s == "rach" || s == "rach_meta") { if (idx < 0 || idx > 2) return -1; cs(gRACHSequences[idx], s == "rach_meta"); }
+	else if (s == "sch" || s == "sch_meta") cs(gSCHSequence, s == "sch_meta");
+	else if (s == "dummy" || s == "dummy_meta") cs(gDummySequence, s == "dummy_meta");
+	else if (s == "psk8") { src = (const float *)psk8_table; n = 16; }
+	else return -1;
+	if (n > max_floats)
+		return -n;
+	memcpy(out, src, sizeof(float) * n);
+	return n;
+}
+
+/* vitac tables (grgsm_vitac.cpp:46-48): which = 0 norm[idx], 1 access, 2 sch */
+extern gr_complex d_acc_training_seq[N_ACCESS_BITS];
+extern gr_complex d_sch_training_seq[N_SYNC_BITS];
+extern gr_complex d_norm_training_seq[TRAIN_SEQ_NUM][N_TRAIN_BITS];
+int ref_get_vitac_table(int which, int idx, float *out)
+{
+	const gr_complex *p; int n;
+	if (which == 0) { p = d_norm_training_seq[idx]; n = N_TRAIN_BITS; }
+	else if (which == 1) { p = d_acc_training_seq; n = N_ACCESS_BITS; }
+	else { p = d_sch_training_seq; n = N_SYNC_BITS; }
+	memcpy(out, p, sizeof(float) * 2 * n);
+	return n;
+}
+
+/* ---- modulators ---- */
+/* modulateBurst(bits, guard, sps, empty) sigProcLib.cpp:970-979; out has room for max_cf complex */
+int ref_modulate_burst(const uint8_t *bits, int nbits, int guard, int sps, int empty, float *out, int max_cf)
+{
+	BitVector bv(nbits);
+	fill_bits(bv, bits, nbits);
+	signalVector *sv = modulateBurst(bv, guard, sps, empty != 0);
+	int rc = copy_sv(sv, out, max_cf);
+	delete sv;
+	return rc;
+}
+
+int ref_modulate_gmsk_batch(const uint8_t *bits, int nbits, int n, float *out, int nthreads)
+{
+	parallel_for(n, nthreads, [&](int b) {
+		BitVector bv(nbits);
+		fill_bits(bv, bits + (size_t)b * nbits, nbits);
+		signalVector *sv = modulateBurst(bv, 8, 4, false);
+		copy_sv(sv, out + (size_t)b * 1250, 625);
+		delete sv;
+	});
+	return n;
+}
+
+/* modulateEdgeBurst(bits, sps, empty) sigProcLib.cpp:917-936 */
+int ref_modulate_edge(const uint8_t *bits, int nbits, int sps, int empty, float *out, int max_cf)
+{
+	BitVector bv(nbits);
+	fill_bits(bv, bits, nbits);
+	signalVector *sv = modulateEdgeBurst(bv, sps, empty != 0);
+	int rc = copy_sv(sv, out, max_cf);
+	delete sv;
+	return rc;
+}
+
+int ref_modulate_edge_batch(const uint8_t *bits, int nbits, int n, float *out, int nthreads)
+{
+	parallel_for(n, nthreads, [&](int b) {
+		BitVector bv(nbits);
+		fill_bits(bv, bits + (size_t)b * nbits, nbits);
+		signalVector *sv = modulateEdgeBurst(bv, 4, false);
+		copy_sv(sv, out + (size_t)b * 1250, 625);
+		delete sv;
+	});
+	return n;
+}
+
+/* ---- detection / demodulation ---- */
+/* detectAnyBurst sigProcLib.cpp:1926-1957.  bursts: [n][stride] complex, burst length `blen` (625). */
+int ref_detect_batch(const float *bursts, int stride, int blen, int n, const uint8_t *type, const uint8_t *tsc,
+		     const uint16_t *max_toa, float thresh, int sps, int32_t *rc, float *amp, float *toa,
+		     uint8_t *tsc_out, float *ci, int nthreads)
+{
+	parallel_for(n, nthreads, [&](int b) {
+		BurstView bv(bursts + (size_t)b * stride * 2, blen);
+		struct estim_burst_params ebp;
+		ebp.amp = 0.0f; ebp.toa = 0.0f; ebp.tsc = 0; ebp.ci = 0.0f;
+		rc[b] = detectAnyBurst(bv.v, tsc[b], thresh, sps, (CorrType)type[b], max_toa[b], &ebp);
+		amp[2 * b] = ebp.amp.real(); amp[2 * b + 1] = ebp.amp.imag();
+		toa[b] = ebp.toa; tsc_out[b] = ebp.tsc; ci[b] = ebp.ci;
+	});
+	return n;
+}
+
+/* demodAnyBurst sigProcLib.cpp:2130-2137 for bursts with rc > 0; soft: [n][soft_stride] floats
+ * (156 GMSK / 444 EDGE written; rest untouched); nsoft[b] = returned SoftVector size (0 if skipped). */
+int ref_demod_batch(const float *bursts, int stride, int blen, int n, const int32_t *rc, const float *amp,
+		    const float *toa, float *ci, int sps, float *soft, int soft_stride, int32_t *nsoft, int nthreads)
+{
+	parallel_for(n, nthreads, [&](int b) {
+		nsoft[b] = 0;
+		if (rc[b] <= 0)
+			return;
+		BurstView bv(bursts + (size_t)b * stride * 2, blen);
+		struct estim_burst_params ebp;
+		ebp.amp = complex(amp[2 * b], amp[2 * b + 1]);
+		ebp.toa = toa[b]; ebp.tsc = 0; ebp.ci = ci[b];
+		SoftVector *sv = demodAnyBurst(bv.v, (CorrType)rc[b], sps, &ebp);
+		if (!sv)
+			return;
+		int ns = std::min((int)sv->size(), soft_stride);
+		memcpy(soft + (size_t)b * soft_stride, sv->begin(), sizeof(float) * ns);
+		nsoft[b] = (int)sv->size();
+		ci[b] = ebp.ci;
+		delete sv;
+	});
+	return n;
+}
+
+/* detect + demod the way Transceiver::pullRadioVector does (Transceiver.cpp:768,786) */
+int ref_detect_demod_batch(const float *bursts, int stride, int blen, int n, const uint8_t *type, const uint8_t *tsc,
+			   const uint16_t *max_toa, float thresh, int sps, int32_t *rc, float *amp, float *toa,
+			   uint8_t *tsc_out, float *ci, float *soft, int soft_stride, int32_t *nsoft, int nthreads)
+{
+	parallel_for(n, nthreads, [&](int b) {
+		BurstView bv(bursts + (size_t)b * stride * 2, blen);
+		struct estim_burst_params ebp;
+		ebp.amp = 0.0f; ebp.toa = 0.0f; ebp.tsc = 0; ebp.ci = 0.0f;
+		nsoft[b] = 0;
+		int r = detectAnyBurst(bv.v, tsc[b], thresh, sps, (CorrType)type[b], max_toa[b], &ebp);
+		rc[b] = r;
+		if (r > 0) {
+			SoftVector *sv = demodAnyBurst(bv.v, (CorrType)r, sps, &ebp);
+			if (sv) {
+				int ns = std::min((int)sv->size(), soft_stride);
+				memcpy(soft + (size_t)b * soft_stride, sv->begin(), sizeof(float) * ns);
+				nsoft[b] = (int)sv->size();
+				delete sv;
+			}
+		}
+		amp[2 * b] = ebp.amp.real(); amp[2 * b + 1] = ebp.amp.imag();
+		toa[b] = ebp.toa; tsc_out[b] = ebp.tsc; ci[b] = ebp.ci;
+	});
+	return n;
+}
+
+/* helpers exposed for unit parity */
+float ref_energy_detect(const float *burst, int blen, unsigned window)
+{
+	BurstView bv(burst, blen);
+	return energyDetect(bv.v, window);
+}
+
+int ref_delay_vector(const float *in, int len, float delay, float *out)
+{
+	BurstView bv(in, len);
+	signalVector *sv = delayVector(&bv.v, NULL, delay);
+	int rc = copy_sv(sv, out, len);
+	delete sv;
+	return rc;
+}
+
+void ref_vector_slicer(float *dst, const float *src, size_t len) { vectorSlicer(dst, src, len); }
+
+int ref_downsample_burst(const float *in, int blen, float *out)
+{
+	BurstView bv(in, blen);
+	signalVector *sv = downsampleBurst(bv.v);
+	int rc = copy_sv(sv, out, 156);
+	delete sv;
+	return rc;
+}
+
+/* generic static convolve() wrapper (sigProcLib.cpp:297-398) for span-mode parity:
+ * h_real/h_aligned select the 4 dispatch cases. span: 0 START_ONLY 1 NO_DELAY 2 CUSTOM */
+int ref_convolve_sv(const float *x, int x_len, const float *h, int h_len, int h_real, int h_aligned, int span,
+		    int start, int len, float *y, int max_cf)
+{
+	signalVector xv(x_len);
+	memcpy(xv.begin(), x, sizeof(float) * 2 * x_len);
+	complex *hd = (complex *)convolve_h_alloc(h_len);
+	memcpy(hd, h, sizeof(float) * 2 * h_len);
+	signalVector hv(hd, 0, h_len, convolve_h_alloc, free);
+	hv.isReal(h_real != 0);
+	hv.setAligned(h_aligned != 0);
+	signalVector *yv = convolve(&xv, &hv, NULL, (ConvType)span, start, len);
+	int rc = copy_sv(yv, y, max_cf);
+	delete yv;
+	return rc;
+}
+
+/* ---- raw C kernels (arch/common/convolve.h:4-26) ---- */
+int ref_convolve_real(const float *x, int x_len, const float *h, int h_len, float *y, int y_len, int start, int len)
+{
+	return convolve_real(x, x_len, h, h_len, y, y_len, start, len);
+}
+int ref_convolve_complex(const float *x, int x_len, const float *h, int h_len, float *y, int y_len, int start, int len)
+{
+	return convolve_complex(x, x_len, h, h_len, y, y_len, start, len);
+}
+int ref_base_convolve_real(const float *x, int x_len, const float *h, int h_len, float *y, int y_len, int start, int len)
+{
+	return base_convolve_real(x, x_len, h, h_len, y, y_len, start, len);
+}
+int ref_base_convolve_complex(const float *x, int x_len, const float *h, int h_len, float *y, int y_len, int start,
+			      int len)
+{
+	return base_convolve_complex(x, x_len, h, h_len, y, y_len, start, len);
+}
+void *ref_convolve_h_alloc(size_t n) { return convolve_h_alloc(n); }
+void ref_free(void *p) { free(p); }
+
+void ref_convert_float_short(short *out, const float *in, float scale, int len) { convert_float_short(out, in, scale, len); }
+void ref_convert_short_float(float *out, const short *in, int len) { convert_short_float(out, in, len); }
+
+/* ---- Resampler (Resampler.h:31-61) ---- */
+void *ref_resampler_create(int p, int q, int filt_len, float bw)
+{
+	Resampler *r = new Resampler(p, q, filt_len);
+	if (!r->init(bw)) {
+		delete r;
+		return NULL;
+	}
+	return r;
+}
+void ref_resampler_destroy(void *r) { delete (Resampler *)r; }
+/* `in` must have filt_len complex samples of history before it (caller supplies in_hist = pointer to start
+ * of a buffer [hist | block]); returns rotate()'s rc */
+int ref_resampler_rotate(void *r, const float *in_with_hist, int hist, int in_len, float *out, int out_len)
+{
+	return ((Resampler *)r)->rotate(in_with_hist + 2 * hist, in_len, out, out_len);
+}
+
+/* ---- Channelizer / Synthesis (Channelizer.h:13-31, Synthesis.h:13-32) ---- */
+void *ref_channelizer_create(int m, int block_len, int h_len)
+{
+	Channelizer *c = new Channelizer(m, block_len, h_len);
+	if (!c->init()) {
+		delete c;
+		return NULL;
+	}
+	return c;
+}
+void ref_channelizer_destroy(void *c) { delete (Channelizer *)c; }
+/* in: [block_len*m] complex; out: [m][block_len] complex */
+int ref_channelizer_rotate(void *c_, const float *in, int m, int block_len, float *out)
+{
+	Channelizer *c = (Channelizer *)c_;
+	if (!c->rotate(in, (size_t)m * block_len))
+		return -1;
+	for (int ch = 0; ch < m; ch++)
+		memcpy(out + (size_t)ch * block_len * 2, c->outputBuffer(ch), sizeof(float) * 2 * block_len);
+	return 0;
+}
+
+void *ref_synthesis_create(int m, int block_len, int h_len)
+{
+	Synthesis *s = new Synthesis(m, block_len, h_len);
+	if (!s->init()) {
+		delete s;
+		return NULL;
+	}
+	return s;
+}
+void ref_synthesis_destroy(void *s) { delete (Synthesis *)s; }
+/* in: [m][block_len] complex; out: [block_len*m] complex */
+int ref_synthesis_rotate(void *s_, const float *in, int m, int block_len, float *out)
+{
+	Synthesis *s = (Synthesis *)s_;
+	for (int ch = 0; ch < m; ch++)
+		memcpy(s->inputBuffer(ch), in + (size_t)ch * block_len * 2, sizeof(float) * 2 * block_len);
+	return s->rotate(out, (size_t)m * block_len) ? 0 : -1;
+}
+
+/* ---- grgsm_vitac (grgsm_vitac.h:65-82) ---- */
+/* bufs: [n][stride] complex, burst begins at sample `offset` inside each row (rows are zero padded so
+ * negative starts are addressable, ms_upper.cpp:164-171). type: 0 NB (tsc per burst), 1 AB. */
+int ref_vitac_batch(const float *bufs, int stride, int offset, int n, int is_ab, const uint8_t *tsc, int max_delay,
+		    int clamp_lo, int clamp_hi, int8_t *bits, int32_t *start_out, float *corr_max, float *cir_out,
+		    int nthreads)
+{
+	const int nbits = is_ab ? 88 : 148;
+	parallel_for(n, nthreads, [&](int b) {
+		const gr_complex *in = (const gr_complex *)(bufs + (size_t)b * stride * 2) + offset;
+		gr_complex cir[CHAN_IMP_RESP_LENGTH * 4];
+		float cmax = 0.0f;
+		int st;
+		if (is_ab)
+			st = get_access_imp_resp(in, cir, &cmax, max_delay);
+		else
+			st = get_norm_chan_imp_resp(in, cir, &cmax, tsc[b]);
+		st = std::max(clamp_lo, std::min(clamp_hi, st));
+		if (is_ab)
+			detect_burst_ab(in, cir, st, (sbit_t *)bits + (size_t)b * nbits);
+		else
+			detect_burst_nb(in, cir, st, (sbit_t *)bits + (size_t)b * nbits);
+		start_out[b] = st;
+		corr_max[b] = cmax;
+		if (cir_out)
+			memcpy(cir_out + (size_t)b * 40, cir, sizeof(float) * 40);
+	});
+	return n;
+}
+
+/* raw viterbi for unit parity: input N complex, rhh 5 complex */
+void ref_viterbi(const float *input, int n, const float *rhh, int start_state, float *out)
+{
+	unsigned int stops[2] = { 4, 12 };
+	gr_complex r[5];
+	memcpy(r, rhh, sizeof(r));
+	viterbi_detector((const gr_complex *)input, n, r, start_state, stops, 2, out);
+}
+
+} /* extern "C" */
