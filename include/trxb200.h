@@ -1,0 +1,185 @@
+/*
+ * trxb200.h — C ABI of the B200-native batched burst-DSP library (libtrxb200.so).
+ *
+ * This is the drop-in boundary for the Transceiver52M burst signal-processing hot path of
+ * osmo-trx.  The reference has no FFI for this path: sigProcLib / Resampler / Channelizer /
+ * Synthesis / grgsm_vitac are statically linked C++ called once per burst
+ * (Transceiver.cpp:392-396,768-786; radioInterfaceMulti.cpp:264-343).  The entry points below are
+ * what a binding for that path has to offer: the same operations, batched over N independent
+ * bursts (ARFCN x timeslot x frame), plain pointers and sizes, no C++ or torch types.
+ * Citations are file:line in the reference tree.  osmo_trx_b200/host/ re-creates the reference's
+ * per-burst C++ API (sigProcLib.h etc.) on top of this ABI; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - complex samples are interleaved float32 (re,im) = `Complex<float>` (Complex.h:29-33);
+ *     `stride` arguments are in complex samples.
+ *   - `*_batch` functions take DEVICE pointers, enqueue on the context's stream and return
+ *     without synchronising; `*_host` functions take HOST pointers and include the copies.
+ *   - return value: 0 (TRXB200_OK) or a negative TRXB200_E* code.  Per-burst results use the
+ *     reference's own conventions (rc > 0 CorrType, 0 no burst, < 0 -SignalError,
+ *     sigProcLib.h:29-45,127-129).
+ *   - there is no CPU fallback: every entry point fails with TRXB200_ENODEV/TRXB200_ECUDA when
+ *     no sm_100 device is usable.
+ */
+#ifndef TRXB200_H
+#define TRXB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRXB200_ABI_VERSION 1
+
+/* error codes */
+#define TRXB200_OK 0
+#define TRXB200_EINVAL (-1)   /* bad argument */
+#define TRXB200_ENODEV (-2)   /* no usable CUDA device */
+#define TRXB200_ECUDA (-3)    /* CUDA runtime error (see trxb200_last_error) */
+#define TRXB200_ENOMEM (-4)
+#define TRXB200_EBOUNDS (-5)  /* convolve bounds_check failure (convolve_base.c:114-131) */
+
+/* CorrType (sigProcLib.h:29-37) and SignalError (sigProcLib.h:39-45) */
+enum trxb200_corr_type { TRXB200_OFF = 0, TRXB200_TSC = 1, TRXB200_EXT_RACH = 2, TRXB200_RACH = 3,
+			 TRXB200_SCH = 4, TRXB200_EDGE = 5, TRXB200_IDLE = 6 };
+enum trxb200_sigerr { TRXB200_SIGERR_NONE = 0, TRXB200_SIGERR_BOUNDS = 1, TRXB200_SIGERR_CLIP = 2,
+		      TRXB200_SIGERR_UNSUPPORTED = 3, TRXB200_SIGERR_INTERNAL = 4 };
+
+/* per-burst edge-case flags (north_star parity rule: such bursts are counted and reported) */
+#define TRXB200_FLAG_THRESH_EDGE 1 /* |peak-to-average - threshold| < 1e-5 */
+#define TRXB200_FLAG_BISECT_TIE 2  /* early/late powers within 4 ulp in some TOA bisection step */
+#define TRXB200_FLAG_CLIP 4	   /* max(|I|,|Q|) > 30000 (sigProcLib.cpp:49,1746) */
+
+#define TRXB200_BURST_LEN 625	/* samples per slot at 4 sps (radioInterface.cpp:257-258) */
+#define TRXB200_GMSK_SOFT 156	/* demodGmskBurst output length (sigProcLib.cpp:2055-2072) */
+#define TRXB200_NB_BITS 148
+#define TRXB200_EDGE_SOFT 444	/* demodEdgeBurst output length (sigProcLib.cpp:1962-2006) */
+
+typedef struct trxb200_ctx trxb200_ctx;
+
+/* ---- life cycle: replaces convolve_init()+convert_init() (osmo-trx.cpp:648-649),
+ *      sigProcLibSetup() (sigProcLib.cpp:2139-2172) and initvita() (grgsm_vitac.cpp:51-80) ---- */
+int trxb200_init(int device, trxb200_ctx **out);
+void trxb200_destroy(trxb200_ctx *ctx); /* sigProcLibDestroy() sigProcLib.cpp:137-176 */
+int trxb200_abi_version(void);
+const char *trxb200_last_error(trxb200_ctx *ctx);
+/* use an existing CUDA stream (cudaStream_t) for all subsequent calls; NULL = the context's own */
+int trxb200_set_stream(trxb200_ctx *ctx, void *cuda_stream);
+void *trxb200_get_stream(trxb200_ctx *ctx);
+int trxb200_sync(trxb200_ctx *ctx);
+int trxb200_device(trxb200_ctx *ctx);
+int trxb200_sm_count(trxb200_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t trxb200_launch_count(trxb200_ctx *ctx);
+/* host copy of a setup table for bit-exact checks against sigProcLib.cpp:52-135 statics.
+ * names: sinc rot4 rrot4 rot1 rrot1 delay pulse4_c0 pulse4_c1 pulse4_c0inv pulse1_c0 dnsamp psk8
+ *        midamble edge_midamble rach sch dummy (+ "_meta" = gain.re, gain.im, toa)
+ *        vitac_norm vitac_access vitac_sch.  Returns the number of floats written or < 0. */
+int trxb200_get_table(trxb200_ctx *ctx, const char *name, int idx, float *out, int max_floats);
+
+/* ---- modulators: modulateBurst(bits, guard, sps=4) -> modulateBurstLaurent (sigProcLib.cpp:595-670,
+ *      970-979) and modulateEdgeBurst(bits, sps=4) (sigProcLib.cpp:713-763,917-936).
+ *      bits: u8[n][bits_stride], one bit per byte, only bit 0 is read (BitVector semantics,
+ *      BitVector.cpp:59-68); out: complex[n][out_stride], 625 samples written per burst. ---- */
+int trxb200_modulate_gmsk_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits, int bits_stride, int n,
+				float *out, int out_stride);
+int trxb200_modulate_edge_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits, int bits_stride, int n,
+				float *out, int out_stride);
+
+/* ---- detection: detectAnyBurst (sigProcLib.cpp:1926-1957) at sps = 4 for every burst b:
+ *      rc[b] = detectAnyBurst(bursts[b], tsc[b], thresh, 4, type[b], max_toa[b], &ebp)
+ *      amp[b] (re,im), toa[b], tsc_out[b], ci[b] = ebp fields (sigProcLib.h:113-118).
+ *      max_toa_bound >= every max_toa[b] (sizes on-chip buffers; larger values give -SIGERR_BOUNDS).
+ *      flags may be NULL. ---- */
+int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, const uint8_t *type,
+			 const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh, int32_t *rc,
+			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags);
+
+/* ---- demodulation: demodAnyBurst (sigProcLib.cpp:2130-2137) for every burst with rc[b] > 0
+ *      (rc[b] is the CorrType returned by detection).  soft: f32[n][soft_stride]; GMSK bursts get
+ *      `n_gmsk_soft` values (148 = what Transceiver.cpp:799-803 consumes, or 156 = the full
+ *      SoftVector), EDGE bursts 444.  ci is updated for EDGE bursts (computeEdgeCI, :2074-2093,2118).
+ *      Bursts with rc[b] <= 0 leave their soft row untouched. ---- */
+int trxb200_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, const int32_t *rc,
+			const float *amp, const float *toa, float *ci, float *soft, int soft_stride,
+			int n_gmsk_soft);
+
+/* ---- fused detect + demod, the Transceiver::pullRadioVector sequence (Transceiver.cpp:768,786) ---- */
+int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, const uint8_t *type,
+			       const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh,
+			       int32_t *rc, float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags,
+			       float *soft, int soft_stride, int n_gmsk_soft);
+
+/* same, HOST buffers: chunks the batch, overlaps H2D / kernels / D2H on internal streams and pinned
+ * staging, returns after everything has landed in the host outputs (this is the e2e path). */
+int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride, int n, const uint8_t *type,
+			      const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh,
+			      int32_t *rc, float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags,
+			      float *soft, int soft_stride, int n_gmsk_soft);
+
+/* ---- small per-burst helpers of sigProcLib.h used around detection ---- */
+/* energyDetect(burst, window) (sigProcLib.cpp:1573-1585): mean |x|^2 of `window` samples at stride 4 */
+int trxb200_energy_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int blen, int n,
+				unsigned window, float *energy);
+/* vectorSlicer (sigProcLib.cpp:546-556) over a flat array */
+int trxb200_vector_slicer(trxb200_ctx *ctx, float *dst, const float *src, size_t len);
+/* delayVector (sigProcLib.cpp:1046-1098): per-burst delay[b] in samples */
+int trxb200_delay_vector_batch(trxb200_ctx *ctx, const float *in, int stride, int len, int n,
+			       const float *delay, float *out, int out_stride);
+
+/* ---- FIR stages: convolve_real / convolve_complex / base_convolve_* (arch/common/convolve.h:4-26),
+ *      y[b][i] = sum_k x[b][i + start - (h_len-1) + k] * h[k], i < len, one shared h for the batch.
+ *      x points at sample 0 of burst 0; samples before it (head-room) are read when start < h_len-1,
+ *      exactly like the reference.  `base` != 0 selects the strictly sequential summation of
+ *      arch/common/convolve_base.c (used for unaligned taps), otherwise the SSE3 summation tree of
+ *      arch/x86/convolve_sse_3.c is reproduced.  Returns TRXB200_EBOUNDS where the reference
+ *      returns -1. ---- */
+int trxb200_convolve_real_batch(trxb200_ctx *ctx, const float *x, int x_len, int x_stride, const float *h,
+				int h_len, float *y, int y_len, int y_stride, int start, int len, int n, int base);
+int trxb200_convolve_complex_batch(trxb200_ctx *ctx, const float *x, int x_len, int x_stride, const float *h,
+				   int h_len, float *y, int y_len, int y_stride, int start, int len, int n,
+				   int base);
+
+/* ---- int16 <-> float (arch/common/convert.h; SSE semantics: round-to-nearest-even + saturation) ---- */
+int trxb200_convert_float_short(trxb200_ctx *ctx, int16_t *out, const float *in, float scale, size_t len);
+int trxb200_convert_short_float(trxb200_ctx *ctx, float *out, const int16_t *in, size_t len);
+
+/* ---- grgsm_vitac MLSE (grgsm_vitac.h:65-82): per burst get_norm_chan_imp_resp / get_access_imp_resp
+ *      -> clamp start to [clamp_lo, clamp_hi] (ms_upper.cpp:224-225 / Transceiver.cpp:631,635) ->
+ *      detect_burst_nb / detect_burst_ab.  bufs: complex[n][stride]; the burst starts `offset`
+ *      samples into each row so that negative starts stay addressable.  bits: i8[n][148 or 88]
+ *      (+-127, pre-flipped, grgsm_vitac.cpp:101-102); cir may be NULL (else complex[n][20]). ---- */
+int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab,
+			const uint8_t *tsc, int max_delay, int clamp_lo, int clamp_hi, int8_t *bits,
+			int32_t *start, float *corr_max, float *cir);
+
+/* ---- Resampler (Resampler.h:31-61): rational p/q polyphase resampler, filt_len taps per path.
+ *      rotate: in points at the first NEW input sample of each stream; `filt_len` samples of history
+ *      precede it in memory (Resampler.cpp:131-150 reads before `in`).  n_streams independent streams
+ *      (channels) are processed per call. ---- */
+typedef struct trxb200_resampler trxb200_resampler;
+int trxb200_resampler_create(trxb200_ctx *ctx, int p, int q, int filt_len, float bw, trxb200_resampler **out);
+void trxb200_resampler_destroy(trxb200_resampler *r);
+int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out,
+			     int out_len, int out_stride, int n_streams);
+int trxb200_resampler_taps(trxb200_resampler *r, int path, float *out_host);
+
+/* ---- Channelizer / Synthesis (Channelizer.h:13-31, Synthesis.h:13-32, ChannelizerBase.cpp):
+ *      M-channel critically sampled polyphase filterbanks; history is carried inside the object
+ *      (ChannelizerBase hist[], Channelizer.cpp:87-88).  n_blocks consecutive blocks per call:
+ *      channelizer in: complex[n_blocks][block_len*m] -> out: complex[m][n_blocks*block_len]
+ *      synthesis   in: complex[m][n_blocks*block_len] -> out: complex[n_blocks][block_len*m] ---- */
+typedef struct trxb200_filterbank trxb200_filterbank;
+int trxb200_channelizer_create(trxb200_ctx *ctx, int m, int block_len, int h_len, trxb200_filterbank **out);
+int trxb200_synthesis_create(trxb200_ctx *ctx, int m, int block_len, int h_len, trxb200_filterbank **out);
+void trxb200_filterbank_destroy(trxb200_filterbank *fb);
+int trxb200_filterbank_reset(trxb200_filterbank *fb);
+int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *out, int n_blocks);
+int trxb200_synthesis_rotate(trxb200_filterbank *fb, const float *in, float *out, int n_blocks);
+int trxb200_filterbank_taps(trxb200_filterbank *fb, int branch, float *out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRXB200_H */

@@ -1,0 +1,265 @@
+"""osmo_trx_b200 — B200-native batched burst DSP behind the sigProcLib / Resampler / Channelizer /
+grgsm_vitac interface of osmo-trx's Transceiver52M.
+
+This package is a thin ctypes binding over ``libtrxb200.so`` (hand-written sm_100a CUDA kernels behind
+the C ABI in ``include/trxb200.h``).  torch is used only for device memory, streams and
+``torch.distributed``.  There is no CPU fallback: constructing :class:`Trx` raises when the shared
+library is missing or no Blackwell GPU is visible.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import buildlib as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtrxb200.so")
+
+OFF, TSC, EXT_RACH, RACH, SCH, EDGE, IDLE = range(7)
+SIGERR_NONE, SIGERR_BOUNDS, SIGERR_CLIP, SIGERR_UNSUPPORTED, SIGERR_INTERNAL = range(5)
+FLAG_THRESH_EDGE, FLAG_BISECT_TIE, FLAG_CLIP = 1, 2, 4
+BURST_LEN = 625
+BURST_THRESH = 4.0  # sigProcLib.h:54
+
+_lib = None
+
+
+class TrxError(RuntimeError):
+    pass
+
+
+def load_library(path=LIB_PATH):
+    """dlopen libtrxb200.so (building it first only if sources are newer and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise TrxError(
+            f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.trxb200_last_error.restype = C.c_char_p
+    lib.trxb200_get_stream.restype = C.c_void_p
+    lib.trxb200_launch_count.restype = C.c_uint64
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _chk_dev(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise TrxError("tensor arguments must be contiguous CUDA tensors")
+
+
+class Trx:
+    """One context per process/GPU (sigProcLibSetup + initvita equivalent)."""
+
+    def __init__(self, device=None):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise TrxError("no CUDA device visible; osmo_trx_b200 has no CPU path")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device)
+        h = C.c_void_p()
+        rc = self.lib.trxb200_init(C.c_int(self.device.index), C.byref(h))
+        if rc != 0:
+            raise TrxError(f"trxb200_init failed with {rc}")
+        self.h = h
+        torch.cuda.set_device(self.device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.trxb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing --
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.trxb200_last_error(self.h)
+            raise TrxError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def use_current_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self.lib.trxb200_set_stream(self.h, C.c_void_p(s))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.trxb200_launch_count(self.h))
+
+    def get_table(self, name, idx=0, max_floats=16384):
+        import numpy as np
+        buf = np.zeros(max_floats, np.float32)
+        n = self.lib.trxb200_get_table(self.h, name.encode(), C.c_int(idx), buf.ctypes.data_as(C.c_void_p),
+                                       C.c_int(max_floats))
+        if n < 0:
+            raise KeyError(name)
+        return buf[:n].copy()
+
+    # -- modulators --
+    def modulate_gmsk(self, bits, out=None):
+        """bits: uint8 [n, nbits] on device -> float32 [n, 625, 2]"""
+        _chk_dev(bits, out)
+        n, nbits = bits.shape
+        if out is None:
+            out = torch.empty((n, BURST_LEN, 2), dtype=torch.float32, device=bits.device)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_modulate_gmsk_batch(self.h, _ptr(bits), C.c_int(nbits), C.c_int(bits.stride(0)),
+                                                         C.c_int(n), _ptr(out), C.c_int(out.stride(0) // 2)),
+                    "modulate_gmsk_batch")
+        return out
+
+    def modulate_edge(self, bits, out=None):
+        _chk_dev(bits, out)
+        n, nbits = bits.shape
+        if out is None:
+            out = torch.empty((n, BURST_LEN, 2), dtype=torch.float32, device=bits.device)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_modulate_edge_batch(self.h, _ptr(bits), C.c_int(nbits), C.c_int(bits.stride(0)),
+                                                         C.c_int(n), _ptr(out), C.c_int(out.stride(0) // 2)),
+                    "modulate_edge_batch")
+        return out
+
+    # -- detection / demod --
+    def alloc_results(self, n, soft_stride=148, device=None):
+        d = device or self.device
+        return dict(rc=torch.zeros(n, dtype=torch.int32, device=d), amp=torch.zeros((n, 2), dtype=torch.float32, device=d),
+                    toa=torch.zeros(n, dtype=torch.float32, device=d), tsc=torch.zeros(n, dtype=torch.uint8, device=d),
+                    ci=torch.zeros(n, dtype=torch.float32, device=d), flags=torch.zeros(n, dtype=torch.uint8, device=d),
+                    soft=torch.zeros((n, soft_stride), dtype=torch.float32, device=d))
+
+    def detect(self, bursts, type_, tsc, max_toa, max_toa_bound, thresh=BURST_THRESH, out=None):
+        """bursts float32 [n, stride>=625, 2]; type_/tsc uint8 [n]; max_toa int16/uint16 [n] (device)."""
+        _chk_dev(bursts, type_, tsc, max_toa)
+        n = bursts.shape[0]
+        r = out or self.alloc_results(n, 1)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_detect_batch(self.h, _ptr(bursts), C.c_int(bursts.stride(0) // 2), C.c_int(n),
+                                                  _ptr(type_), _ptr(tsc), _ptr(max_toa), C.c_int(max_toa_bound),
+                                                  C.c_float(thresh), _ptr(r["rc"]), _ptr(r["amp"]), _ptr(r["toa"]),
+                                                  _ptr(r["tsc"]), _ptr(r["ci"]), _ptr(r["flags"])), "detect_batch")
+        return r
+
+    def demod(self, bursts, rc, amp, toa, ci, soft=None, n_gmsk_soft=148, soft_stride=None):
+        _chk_dev(bursts, rc, amp, toa, ci, soft)
+        n = bursts.shape[0]
+        if soft is None:
+            soft = torch.zeros((n, soft_stride or n_gmsk_soft), dtype=torch.float32, device=bursts.device)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_demod_batch(self.h, _ptr(bursts), C.c_int(bursts.stride(0) // 2), C.c_int(n),
+                                                 _ptr(rc), _ptr(amp), _ptr(toa), _ptr(ci), _ptr(soft),
+                                                 C.c_int(soft.stride(0)), C.c_int(n_gmsk_soft)), "demod_batch")
+        return soft
+
+    def detect_demod(self, bursts, type_, tsc, max_toa, max_toa_bound, thresh=BURST_THRESH, n_gmsk_soft=148,
+                     soft_stride=None, out=None):
+        _chk_dev(bursts, type_, tsc, max_toa)
+        n = bursts.shape[0]
+        r = out or self.alloc_results(n, soft_stride or n_gmsk_soft)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_detect_demod_batch(
+            self.h, _ptr(bursts), C.c_int(bursts.stride(0) // 2), C.c_int(n), _ptr(type_), _ptr(tsc), _ptr(max_toa),
+            C.c_int(max_toa_bound), C.c_float(thresh), _ptr(r["rc"]), _ptr(r["amp"]), _ptr(r["toa"]), _ptr(r["tsc"]),
+            _ptr(r["ci"]), _ptr(r["flags"]), _ptr(r["soft"]), C.c_int(r["soft"].stride(0)), C.c_int(n_gmsk_soft)),
+            "detect_demod_batch")
+        return r
+
+    def detect_demod_host(self, bursts, type_, tsc, max_toa, max_toa_bound, out, thresh=BURST_THRESH, n_gmsk_soft=148):
+        """Same with HOST tensors (ideally pinned); copies are inside the call.  `out` from alloc_results(device='cpu')."""
+        n = bursts.shape[0]
+        self._check(self.lib.trxb200_detect_demod_host(
+            self.h, _ptr(bursts), C.c_int(bursts.stride(0) // 2), C.c_int(n), _ptr(type_), _ptr(tsc), _ptr(max_toa),
+            C.c_int(max_toa_bound), C.c_float(thresh), _ptr(out["rc"]), _ptr(out["amp"]), _ptr(out["toa"]),
+            _ptr(out["tsc"]), _ptr(out["ci"]), _ptr(out["flags"]), _ptr(out["soft"]), C.c_int(out["soft"].stride(0)),
+            C.c_int(n_gmsk_soft)), "detect_demod_host")
+        return out
+
+    # -- helpers --
+    def energy_detect(self, bursts, window, blen=BURST_LEN):
+        _chk_dev(bursts)
+        n = bursts.shape[0]
+        e = torch.empty(n, dtype=torch.float32, device=bursts.device)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_energy_detect_batch(self.h, _ptr(bursts), C.c_int(bursts.stride(0) // 2),
+                                                         C.c_int(blen), C.c_int(n), C.c_uint(window), _ptr(e)),
+                    "energy_detect_batch")
+        return e
+
+    def vector_slicer(self, src):
+        _chk_dev(src)
+        dst = torch.empty_like(src)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_vector_slicer(self.h, _ptr(dst), _ptr(src), C.c_size_t(src.numel())), "vector_slicer")
+        return dst
+
+    def delay_vector(self, x, delay):
+        """x float32 [n, len, 2], delay float32 [n] -> [n, len, 2]"""
+        _chk_dev(x, delay)
+        out = torch.empty_like(x)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_delay_vector_batch(self.h, _ptr(x), C.c_int(x.stride(0) // 2), C.c_int(x.shape[1]),
+                                                        C.c_int(x.shape[0]), _ptr(delay), _ptr(out),
+                                                        C.c_int(out.stride(0) // 2)), "delay_vector_batch")
+        return out
+
+    def convolve(self, x, x_off, x_len, h, start, length, complex_taps, base=False):
+        """x float32 [n, row, 2] where the addressed vector starts x_off samples into each row (head-room)."""
+        _chk_dev(x, h)
+        n = x.shape[0]
+        y = torch.zeros((n, length, 2), dtype=torch.float32, device=x.device)
+        fn = self.lib.trxb200_convolve_complex_batch if complex_taps else self.lib.trxb200_convolve_real_batch
+        self.use_current_stream()
+        rc = fn(self.h, C.c_void_p(x.data_ptr() + 8 * x_off), C.c_int(x_len), C.c_int(x.stride(0) // 2), _ptr(h),
+                C.c_int(h.shape[0]), _ptr(y), C.c_int(length), C.c_int(y.stride(0) // 2), C.c_int(start),
+                C.c_int(length), C.c_int(n), C.c_int(int(base)))
+        return rc, y
+
+    def convert_float_short(self, x, scale):
+        _chk_dev(x)
+        out = torch.empty(x.numel(), dtype=torch.int16, device=x.device)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_convert_float_short(self.h, _ptr(out), _ptr(x), C.c_float(scale),
+                                                         C.c_size_t(x.numel())), "convert_float_short")
+        return out
+
+    def convert_short_float(self, x):
+        _chk_dev(x)
+        out = torch.empty(x.numel(), dtype=torch.float32, device=x.device)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_convert_short_float(self.h, _ptr(out), _ptr(x), C.c_size_t(x.numel())),
+                    "convert_short_float")
+        return out
+
+    # -- vitac --
+    def vitac(self, bufs, offset, tsc, is_ab=False, max_delay=0, clamp=(-39, 39), want_cir=False):
+        _chk_dev(bufs, tsc)
+        n = bufs.shape[0]
+        nb = 88 if is_ab else 148
+        d = bufs.device
+        r = dict(bits=torch.zeros((n, nb), dtype=torch.int8, device=d), start=torch.zeros(n, dtype=torch.int32, device=d),
+                 corr_max=torch.zeros(n, dtype=torch.float32, device=d),
+                 cir=torch.zeros((n, 20, 2), dtype=torch.float32, device=d) if want_cir else None)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_vitac_batch(self.h, _ptr(bufs), C.c_int(bufs.stride(0) // 2), C.c_int(offset),
+                                                 C.c_int(n), C.c_int(int(is_ab)), _ptr(tsc), C.c_int(max_delay),
+                                                 C.c_int(clamp[0]), C.c_int(clamp[1]), _ptr(r["bits"]), _ptr(r["start"]),
+                                                 _ptr(r["corr_max"]), _ptr(r["cir"])), "vitac_batch")
+        return r
+
+
+def build(force=False):
+    """Compile libtrxb200.so in-tree (nvcc, sm_100a)."""
+    return _build.build(force=force)

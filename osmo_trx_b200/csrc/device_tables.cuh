@@ -1,0 +1,60 @@
+// device_tables.cuh — constant-memory tables shared by the kernels, and exact-arithmetic helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace trxb200 {
+
+// sequence ids
+constexpr int SEQ_MIDAMBLE = 0;	 // 0..7
+constexpr int SEQ_EDGE = 8;	 // 8..15
+constexpr int SEQ_RACH = 16;	 // 16..18
+constexpr int SEQ_SCH = 19;
+constexpr int SEQ_DUMMY = 20;
+constexpr int SEQ_COUNT = 21;
+constexpr int SEQ_STORE = 17 * 16 + 3 * 40 + 64;
+
+struct SeqInfo {
+	int off, len;	 // into c_seq
+	float inv_gr, inv_gi; // gain.inv() (Complex.h:144-150): amp = xcorr * inv(gain)  (sigProcLib.cpp:1701)
+	float ci_den;	 // (N-1) * |gain|   (sigProcLib.cpp:1629)
+	float toa;	 // sequence time offset (sigProcLib.cpp:1704)
+};
+
+struct ConstTables {
+	float2 seq[SEQ_STORE];
+	SeqInfo info[SEQ_COUNT];
+	float dnsamp[16];
+	float pulse_c0[16], pulse_c1[8];
+	float c0_inv[5];
+	float2 rrot1[160];
+	float2 rot4[628];
+	float2 psk8[8];
+	float2 edge_mod_rot[156];
+	float2 edge_derot[16];
+	float2 edge_ideal[9];
+	float2 edge_rot1, edge_rot2;
+	float delay[64][20];
+	float2 vitac_norm[9][26];
+	float2 vitac_access[41];
+};
+
+// Pointers to the larger tables kept in global memory (L1/L2 resident).
+struct GlobalTables {
+	const float *interp_w; // [512][21]
+	const float *comp;     // [65][16][36]
+};
+
+// ---- exact float32 helpers: no contraction, reference operation order ----
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+// Complex::norm2() = i*i + r*r  (Complex.h:112)
+__device__ __forceinline__ float norm2(float2 v) { return fa(fm(v.y, v.y), fm(v.x, v.x)); }
+// Complex * Complex (Complex.h:73)
+__device__ __forceinline__ float2 cmul_exact(float2 a, float2 b)
+{
+	return make_float2(fs(fm(a.x, b.x), fm(a.y, b.y)), fa(fm(a.x, b.y), fm(a.y, b.x)));
+}
+
+} // namespace trxb200

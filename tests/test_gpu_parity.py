@@ -1,0 +1,253 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs the CPU checker on identical seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import cpulibs
+import parity
+import synth
+from cpulibs import TSC, EXT_RACH, RACH, EDGE, IDLE
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def run_gpu_dd(trx, rx, typ, tsc, max_toa, bound, n_soft=156, soft_stride=444):
+    n = rx.shape[0]
+    t_type = dev(np.broadcast_to(np.asarray(typ, np.uint8), (n,)).copy())
+    t_tsc = dev(np.broadcast_to(np.asarray(tsc, np.uint8), (n,)).copy())
+    t_toa = dev(np.broadcast_to(np.asarray(max_toa, np.int16), (n,)).copy())
+    r = trx.detect_demod(dev(rx), t_type, t_tsc, t_toa, bound, n_gmsk_soft=n_soft, soft_stride=soft_stride)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in r.items()}
+
+
+def check_dd(trx, checker, rx, typ, tsc, max_toa, what, n_soft=156):
+    bound = int(np.max(max_toa))
+    g = run_gpu_dd(trx, rx, typ, tsc, max_toa, bound, n_soft=n_soft)
+    c = checker.detect_demod(rx, typ, tsc, max_toa)
+    rep = parity.compare_detect(g, c, g["flags"], what)
+    ok = rep["ok_mask"]
+    gmsk = ok & (c["rc"] != EDGE)
+    edge = ok & (c["rc"] == EDGE)
+    rep["ci_max_dB"] = parity.compare_ci(g["ci"], c["ci"], ok, what)
+    rep["gmsk"] = parity.compare_soft(g["soft"], c["soft"], gmsk, n_soft, what + " gmsk")
+    rep["edge"] = parity.compare_soft(g["soft"], c["soft"], edge, 444, what + " edge")
+    rep.pop("ok_mask"); rep.pop("_ga")
+    print(what, rep)
+    return g, c, rep
+
+
+def test_tables_bit_exact(trx, checker):
+    names = [("sinc", 0), ("rot4", 0), ("rrot4", 0), ("rot1", 0), ("rrot1", 0), ("pulse4_c0", 0), ("pulse4_c1", 0),
+             ("pulse4_c0inv", 0), ("pulse1_c0", 0), ("sch", 0), ("sch_meta", 0), ("dummy", 0), ("dummy_meta", 0), ("psk8", 0)]
+    names += [("delay", i) for i in range(64)]
+    for nm in ("midamble", "edge_midamble"):
+        names += [(nm, i) for i in range(8)] + [(nm + "_meta", i) for i in range(8)]
+    names += [("rach", i) for i in range(3)] + [("rach_meta", i) for i in range(3)]
+    for nm, i in names:
+        a, b = trx.get_table(nm, i), checker.get_table(nm, i)
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (nm, i)
+    for t in range(9):
+        assert np.array_equal(trx.get_table("vitac_norm", t).reshape(-1, 2), checker.vitac_table(0, t))
+    assert np.array_equal(trx.get_table("vitac_access").reshape(-1, 2), checker.vitac_table(1))
+    assert np.array_equal(trx.get_table("vitac_sch").reshape(-1, 2), checker.vitac_table(2))
+
+
+def test_modulate_gmsk_exact(trx, checker):
+    rng = np.random.default_rng(11)
+    n = 512
+    bits = synth.nb_bits(n, np.arange(n) % 8, rng)
+    bits[::5] |= 0xA2  # BitVector elements carry garbage above bit 0 (BitVector.cpp:59-68): only &1 counts
+    ref = checker.modulate_gmsk_batch(bits & 1)
+    out = trx.modulate_gmsk(dev(bits)).cpu().numpy()
+    assert np.array_equal(out, ref)  # value-exact (signed zeros compare equal)
+    # ragged: access-burst lengths
+    for nb in (88, 100, 147, 156, 2):
+        b = rng.integers(0, 2, (7, nb)).astype(np.uint8)
+        ref = np.stack([checker.modulate_burst(b[i], 0, 4) for i in range(7)])
+        out = trx.modulate_gmsk(dev(b)).cpu().numpy()
+        assert np.array_equal(out, ref), nb
+
+
+def test_modulate_edge_exact(trx, checker):
+    rng = np.random.default_rng(12)
+    n = 256
+    bits = synth.edge_bits(n, np.arange(n) % 8, rng)
+    ref = checker.modulate_edge_batch(bits)
+    out = trx.modulate_edge(dev(bits)).cpu().numpy()
+    assert np.array_equal(out, ref)
+
+
+def test_nb_detect_demod_cfg1(trx, checker):
+    """BASELINE configs[0]: 10k GMSK normal bursts, TSC 0-7, sps=4, AWGN + random TOA."""
+    rng = np.random.default_rng(1)
+    n = 10000
+    tsc = np.arange(n) % 8
+    bits = synth.nb_bits(n, tsc, rng)
+    w = checker.modulate_gmsk_batch(bits, nthreads=8)
+    snr = np.choose(np.arange(n) % 3, [30.0, 10.0, 6.0])
+    rx, _ = synth.impair(w, rng, snr_db=snr, noise_only_frac=0.05)
+    g, c, rep = check_dd(trx, checker, rx, TSC, tsc, 4, "cfg1-NB")
+    assert rep["detected"] > 0.9 * 0.95 * n
+    det = c["rc"] > 0
+    hard = (g["soft"][det][:, :148] > 0).astype(np.uint8)
+    ber = (hard != bits[det]).mean()
+    print("cfg1 BER", ber)
+    assert ber < 0.02
+    # also with the 148-wide output the transceiver consumes
+    g2 = run_gpu_dd(trx, rx[:512], TSC, tsc[:512], 4, 4, n_soft=148, soft_stride=148)
+    assert np.array_equal(g2["soft"], g["soft"][:512, :148])
+
+
+def test_nb_full_scale_and_clipping(trx, checker):
+    rng = np.random.default_rng(5)
+    n = 1024
+    tsc = np.arange(n) % 8
+    w = checker.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng))
+    rx, _ = synth.impair(w, rng, snr_db=20.0, full_scale=20000.0, noise_only_frac=0.2)
+    rx[::7] *= 3.0  # drive some bursts beyond CLIP_THRESH
+    g, c, rep = check_dd(trx, checker, rx, TSC, tsc, 4, "clip")
+    assert (c["rc"] == -2).any() and (c["rc"] == 1).any()
+    # standalone detect reports clipping too
+    n2 = 256
+    r = trx.detect(dev(rx[:n2]), dev(np.full(n2, TSC, np.uint8)), dev(tsc[:n2].astype(np.uint8)),
+                   dev(np.full(n2, 4, np.int16)), 4)
+    assert np.array_equal(r["rc"].cpu().numpy(), c["rc"][:n2])
+
+
+def test_rach(trx, checker):
+    rng = np.random.default_rng(2)
+    outs = []
+    for seq in range(3):
+        for delay in (0, 7, 33, 59):
+            b = synth.ab_bits(40, delay, rng, seq)
+            outs.append(np.stack([checker.modulate_burst(b[i], 68 - delay, 4) for i in range(40)]))
+    w = np.concatenate(outs)
+    rx, _ = synth.impair(w, rng, snr_db=12.0, shift_lo=-22, shift_hi=-14, noise_only_frac=0.05)
+    for typ in (RACH, EXT_RACH):
+        g, c, rep = check_dd(trx, checker, rx, typ, 0, 63, f"rach-{typ}")
+        assert rep["detected"] > 100
+
+
+def test_edge_and_fallback(trx, checker):
+    rng = np.random.default_rng(3)
+    n = 2000
+    tsc = np.arange(n) % 8
+    w = checker.modulate_edge_batch(synth.edge_bits(n, tsc, rng), nthreads=8)
+    rx, _ = synth.impair(w, rng, snr_db=25.0, noise_only_frac=0.05)
+    wn = checker.modulate_gmsk_batch(synth.nb_bits(300, tsc[:300], rng))
+    rx[:300], _ = synth.impair(wn, rng, snr_db=20.0)
+    g, c, rep = check_dd(trx, checker, rx, EDGE, tsc, 4, "edge")
+    assert (c["rc"] == EDGE).sum() > 1000 and (c["rc"] == TSC).sum() > 200
+
+
+def test_idle_and_mixed_types(trx, checker):
+    rng = np.random.default_rng(4)
+    n = 1500
+    tsc = np.arange(n) % 8
+    w = checker.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng))
+    rx, _ = synth.impair(w, rng, snr_db=15.0)
+    typ = np.choose(np.arange(n) % 6, [TSC, IDLE, EDGE, RACH, 0, 4]).astype(np.uint8)  # incl. OFF and SCH (invalid here)
+    tscv = tsc.copy()
+    tscv[::50] = 9  # unsupported TSC -> -SIGERR_UNSUPPORTED
+    mt = np.choose(np.arange(n) % 4, [0, 4, 17, 63]).astype(np.int16)
+    g, c, rep = check_dd(trx, checker, rx, typ, tscv, mt, "mixed")
+    assert (c["rc"] == -3).any()
+
+
+def test_empty_and_tiny_batches(trx, checker):
+    rng = np.random.default_rng(6)
+    w = checker.modulate_gmsk_batch(synth.nb_bits(3, [0, 1, 2], rng))
+    rx, _ = synth.impair(w, rng, snr_db=30.0)
+    for n in (1, 3):
+        check_dd(trx, checker, rx[:n], TSC, np.arange(n), 4, f"tiny{n}")
+    r = trx.detect_demod(torch.zeros((0, 625, 2), device="cuda"), torch.zeros(0, dtype=torch.uint8, device="cuda"),
+                         torch.zeros(0, dtype=torch.uint8, device="cuda"), torch.zeros(0, dtype=torch.int16, device="cuda"), 4)
+    assert r["rc"].numel() == 0
+    # all-zero bursts: nothing detected, no NaNs
+    z = np.zeros((64, 625, 2), np.float32)
+    g = run_gpu_dd(trx, z, TSC, 0, 4, 4)
+    c = checker.detect_demod(z, TSC, 0, 4)
+    assert np.array_equal(g["rc"], c["rc"]) and (g["rc"] == 0).all()
+
+
+def test_convolve_golden(trx):
+    """The reference's own KAT: tests/Transceiver52M/convolve_test_golden.h (fixture in tests/golden)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "convolve_golden.npz"))
+    x, h = gold["x"], gold["h"]
+    for cplx in (False, True):
+        for hl in (4, 8, 12, 16, 20, 24):
+            ref = gold[f"y_{'complex' if cplx else 'real'}_base_{hl}"].reshape(-1, 2)
+            start, ln = hl - 1, 100 - (hl - 1)
+            for base in (False, True):
+                rc, y = trx.convolve(dev(x.reshape(1, 100, 2)), 0, 100, dev(h.reshape(-1, 2)[:hl]), start, ln, cplx, base)
+                assert rc == 0
+                y = y.cpu().numpy()[0]
+                ok = (np.abs(y - ref) < 1e-5) | (np.abs(1 - y / ref) < 1e-5)  # compare_floats, convolve_test.c:76-96
+                assert ok.all(), (cplx, hl, base)
+
+
+def test_convolve_exact_vs_checker(trx, checker):
+    rng = np.random.default_rng(7)
+    n, xl, head = 5, 300, 70
+    x = rng.standard_normal((n, head + xl, 2)).astype(np.float32)
+    for hl in (1, 4, 5, 8, 12, 16, 20, 24, 40, 64, 7):
+        h = rng.standard_normal((hl, 2)).astype(np.float32)
+        for start, ln in ((hl - 1, xl - hl + 1), (0, xl), (3, 100)):
+            for cplx in (False, True):
+                for base in (False, True):
+                    rc, y = trx.convolve(dev(x), head, xl, dev(h), start, ln, cplx, base)
+                    assert rc == 0
+                    y = y.cpu().numpy()
+                    for b in range(n):
+                        f = {(False, False): checker.convolve_real, (True, False): checker.convolve_complex,
+                             (False, True): checker.base_convolve_real, (True, True): checker.base_convolve_complex}[(cplx, base)]
+                        _, yr = f(x[b], h, start, ln, x_off=head)
+                        assert np.array_equal(y[b], yr), (hl, start, ln, cplx, base)
+    # bounds failure mirrors the reference's -1
+    rc, _ = trx.convolve(dev(x), head, xl, dev(h), 10, xl, False, True)
+    assert rc == -5
+
+
+def test_helpers(trx, checker):
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((16, 625, 2)).astype(np.float32)
+    e = trx.energy_detect(dev(x), 80).cpu().numpy()
+    for b in range(16):
+        assert e[b] == np.float32(checker.energy_detect(x[b], 80))
+    s = (rng.standard_normal(5000) * 1.5).astype(np.float32)
+    assert np.array_equal(trx.vector_slicer(dev(s)).cpu().numpy(), checker.vector_slicer(s))
+    delays = np.array([0.0, 0.005, -0.005, 3.3, -7.71, 12.999, -0.5, 1.0, -40.25, 80.6, 0.011, -0.011, 624.5, -700.0, 2.0, -3.0], np.float32)
+    y = trx.delay_vector(dev(x), dev(delays)).cpu().numpy()
+    for b in range(16):
+        assert np.array_equal(y[b], checker.delay_vector(x[b], float(delays[b]))), delays[b]
+    v = (rng.standard_normal(4096) * 20000).astype(np.float32)
+    v[:6] = [0.5, 1.5, 2.5, -0.5, -1.5, 1e12]
+    assert np.array_equal(trx.convert_float_short(dev(v), 1.7).cpu().numpy(), checker.convert_float_short(v, 1.7))
+    i16 = rng.integers(-32768, 32767, 4096).astype(np.int16)
+    assert np.array_equal(trx.convert_short_float(dev(i16)).cpu().numpy(), checker.convert_short_float(i16))
+
+
+def test_host_pipeline_matches_device_path(trx, checker):
+    rng = np.random.default_rng(9)
+    n = 40000  # > 2 chunks of the host pipeline
+    tsc = (np.arange(n) % 8).astype(np.uint8)
+    w = checker.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng), nthreads=8)
+    rx, _ = synth.impair(w, rng, snr_db=12.0, noise_only_frac=0.1)
+    g = run_gpu_dd(trx, rx, TSC, tsc, 4, 4, n_soft=148, soft_stride=148)
+    out = trx.alloc_results(n, 148, device="cpu")
+    out = {k: v.pin_memory() for k, v in out.items()}
+    trx.detect_demod_host(torch.from_numpy(rx).pin_memory(), torch.full((n,), TSC, dtype=torch.uint8).pin_memory(),
+                          torch.from_numpy(tsc).pin_memory(), torch.full((n,), 4, dtype=torch.int16).pin_memory(), 4, out)
+    for k in ("rc", "amp", "toa", "tsc", "ci", "flags"):
+        assert np.array_equal(out[k].numpy(), g[k]), k
+    det = g["rc"] > 0
+    assert np.array_equal(out["soft"].numpy()[det], g["soft"][det])
