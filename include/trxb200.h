@@ -64,8 +64,11 @@ int trxb200_init(int device, trxb200_ctx **out);
 void trxb200_destroy(trxb200_ctx *ctx); /* sigProcLibDestroy() sigProcLib.cpp:137-176 */
 int trxb200_abi_version(void);
 const char *trxb200_last_error(trxb200_ctx *ctx);
-/* use an existing CUDA stream (cudaStream_t) for all subsequent calls; NULL = the context's own */
+/* A new context launches on its own non-blocking stream.  trxb200_set_stream() makes all subsequent
+ * calls use the given cudaStream_t instead (NULL = the CUDA default stream); trxb200_use_own_stream()
+ * switches back. */
 int trxb200_set_stream(trxb200_ctx *ctx, void *cuda_stream);
+int trxb200_use_own_stream(trxb200_ctx *ctx);
 void *trxb200_get_stream(trxb200_ctx *ctx);
 int trxb200_sync(trxb200_ctx *ctx);
 int trxb200_device(trxb200_ctx *ctx);

@@ -263,3 +263,91 @@ class Trx:
 def build(force=False):
     """Compile libtrxb200.so in-tree (nvcc, sm_100a)."""
     return _build.build(force=force)
+
+
+class Resampler:
+    """Rational p/q polyphase resampler (Resampler.h:31-61) on device streams."""
+
+    def __init__(self, trx, p, q, filt_len=16, bw=1.0):
+        self.trx, self.p, self.q, self.filt_len = trx, p, q, filt_len
+        h = C.c_void_p()
+        trx._check(trx.lib.trxb200_resampler_create(trx.h, C.c_int(p), C.c_int(q), C.c_int(filt_len), C.c_float(bw),
+                                                    C.byref(h)), "resampler_create")
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.trx.lib.trxb200_resampler_destroy(self.h)
+            self.h = None
+
+    def taps(self, path):
+        import numpy as np
+        out = np.zeros(self.filt_len, np.float32)
+        self.trx.lib.trxb200_resampler_taps(self.h, C.c_int(path), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def rotate(self, x, out_len):
+        """x float32 [n_streams, filt_len + in_len, 2]: history then the new block. -> [n_streams, out_len, 2]"""
+        _chk_dev(x)
+        ns, tot = x.shape[0], x.shape[1]
+        out = torch.empty((ns, out_len, 2), dtype=torch.float32, device=x.device)
+        self.trx.use_current_stream()
+        rc = self.trx.lib.trxb200_resampler_rotate(self.h, C.c_void_p(x.data_ptr() + 8 * self.filt_len),
+                                                   C.c_int(tot - self.filt_len), C.c_int(x.stride(0) // 2), _ptr(out),
+                                                   C.c_int(out_len), C.c_int(out.stride(0) // 2), C.c_int(ns))
+        self.trx._check(rc, "resampler_rotate")
+        return out
+
+
+class _Filterbank:
+    def __init__(self, trx, m, block_len, h_len, synth):
+        self.trx, self.m, self.block_len, self.h_len = trx, m, block_len, h_len
+        h = C.c_void_p()
+        fn = trx.lib.trxb200_synthesis_create if synth else trx.lib.trxb200_channelizer_create
+        trx._check(fn(trx.h, C.c_int(m), C.c_int(block_len), C.c_int(h_len), C.byref(h)), "filterbank_create")
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.trx.lib.trxb200_filterbank_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        self.trx.use_current_stream()
+        self.trx._check(self.trx.lib.trxb200_filterbank_reset(self.h), "filterbank_reset")
+
+    def taps(self, branch):
+        import numpy as np
+        out = np.zeros(self.h_len, np.float32)
+        self.trx.lib.trxb200_filterbank_taps(self.h, C.c_int(branch), out.ctypes.data_as(C.c_void_p))
+        return out
+
+
+class Channelizer(_Filterbank):
+    """M-channel analysis filterbank (Channelizer.h:13-31). rotate(): [n_blocks*block_len*m, 2] -> [m, n_blocks*block_len, 2]"""
+
+    def __init__(self, trx, m, block_len, h_len=16):
+        super().__init__(trx, m, block_len, h_len, False)
+
+    def rotate(self, x):
+        _chk_dev(x)
+        nb = x.shape[0] // (self.m * self.block_len)
+        out = torch.empty((self.m, nb * self.block_len, 2), dtype=torch.float32, device=x.device)
+        self.trx.use_current_stream()
+        self.trx._check(self.trx.lib.trxb200_channelizer_rotate(self.h, _ptr(x), _ptr(out), C.c_int(nb)), "channelizer_rotate")
+        return out
+
+
+class Synthesis(_Filterbank):
+    """M-channel synthesis filterbank (Synthesis.h:13-32). rotate(): [m, n_blocks*block_len, 2] -> [n_blocks*block_len*m, 2]"""
+
+    def __init__(self, trx, m, block_len, h_len=16):
+        super().__init__(trx, m, block_len, h_len, True)
+
+    def rotate(self, x):
+        _chk_dev(x)
+        nb = x.shape[1] // self.block_len
+        out = torch.empty((nb * self.block_len * self.m, 2), dtype=torch.float32, device=x.device)
+        self.trx.use_current_stream()
+        self.trx._check(self.trx.lib.trxb200_synthesis_rotate(self.h, _ptr(x), _ptr(out), C.c_int(nb)), "synthesis_rotate")
+        return out

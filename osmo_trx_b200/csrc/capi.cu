@@ -205,7 +205,13 @@ const char *trxb200_last_error(trxb200_ctx *ctx) { return ctx ? ctx->err.c_str()
 int trxb200_set_stream(trxb200_ctx *ctx, void *s)
 {
 	if (!ctx) return TRXB200_EINVAL;
-	ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+	ctx->stream = (cudaStream_t)s; // NULL is the CUDA default stream, exactly as passed
+	return TRXB200_OK;
+}
+int trxb200_use_own_stream(trxb200_ctx *ctx)
+{
+	if (!ctx) return TRXB200_EINVAL;
+	ctx->stream = ctx->own_stream;
 	return TRXB200_OK;
 }
 void *trxb200_get_stream(trxb200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

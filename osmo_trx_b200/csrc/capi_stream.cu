@@ -1,15 +1,190 @@
 // capi_stream.cu — vitac / resampler / filterbank entry points (included by capi.cu)
+
+struct trxb200_resampler {
+	trxb200_ctx *ctx;
+	int p, q, L;
+	std::vector<float> taps;
+	float *d_taps = nullptr;
+};
+
+struct trxb200_filterbank {
+	trxb200_ctx *ctx;
+	int m, block_len, L, synth;
+	std::vector<float> taps;
+	float *d_taps = nullptr;
+	float2 *d_tw = nullptr;
+	float *d_hist[2] = { nullptr, nullptr }; // ping-pong: read by the main kernel, written by the tail kernel
+	int cur = 0;
+};
+
 extern "C" {
-int trxb200_vitac_batch(trxb200_ctx *ctx, const float *, int, int, int, int, const uint8_t *, int, int, int, int8_t *, int32_t *, float *, float *) { return fail(ctx, TRXB200_EINVAL, "vitac: not built yet"); }
-int trxb200_resampler_create(trxb200_ctx *ctx, int, int, int, float, trxb200_resampler **) { return fail(ctx, TRXB200_EINVAL, "resampler: not built yet"); }
-void trxb200_resampler_destroy(trxb200_resampler *) {}
-int trxb200_resampler_rotate(trxb200_resampler *, const float *, int, int, float *, int, int, int) { return TRXB200_EINVAL; }
-int trxb200_resampler_taps(trxb200_resampler *, int, float *) { return TRXB200_EINVAL; }
-int trxb200_channelizer_create(trxb200_ctx *ctx, int, int, int, trxb200_filterbank **) { return fail(ctx, TRXB200_EINVAL, "channelizer: not built yet"); }
-int trxb200_synthesis_create(trxb200_ctx *ctx, int, int, int, trxb200_filterbank **) { return fail(ctx, TRXB200_EINVAL, "synthesis: not built yet"); }
-void trxb200_filterbank_destroy(trxb200_filterbank *) {}
-int trxb200_filterbank_reset(trxb200_filterbank *) { return TRXB200_EINVAL; }
-int trxb200_channelizer_rotate(trxb200_filterbank *, const float *, float *, int) { return TRXB200_EINVAL; }
-int trxb200_synthesis_rotate(trxb200_filterbank *, const float *, float *, int) { return TRXB200_EINVAL; }
-int trxb200_filterbank_taps(trxb200_filterbank *, int, float *) { return TRXB200_EINVAL; }
+
+int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab, const uint8_t *tsc,
+			int max_delay, int clamp_lo, int clamp_hi, int8_t *bits, int32_t *start, float *corr_max, float *cir)
+{
+	if (!ctx) return TRXB200_EINVAL;
+	if (!bufs || !bits || !start || !corr_max || n < 0 || max_delay < 0 || max_delay > 64 || (!is_ab && !tsc))
+		return fail(ctx, TRXB200_EINVAL, "vitac: bad argument");
+	const int N = is_ab ? 88 : 148, center = is_ab ? 13 : 66;
+	const int s0 = (center - 5) * 4 + 1, s1 = (center + 10 + (is_ab ? max_delay : 0)) * 4;
+	// every read must stay inside the row: [offset+clamp_lo, offset+clamp_hi+4N) and the search windows
+	const int tlen = is_ab ? 31 : 16;
+	if (offset + clamp_lo < 0 || offset + clamp_hi + 4 * N > stride || offset + s1 - 1 + 4 * (tlen - 1) >= stride || clamp_lo > clamp_hi)
+		return fail(ctx, TRXB200_EINVAL, "vitac: row too short for the search window / clamp range");
+	if (n == 0) return TRXB200_OK;
+	VitacParams p;
+	p.bufs = bufs; p.stride = stride; p.offset = offset; p.n = n; p.is_ab = is_ab; p.tsc = tsc; p.max_delay = max_delay;
+	p.clamp_lo = clamp_lo; p.clamp_hi = clamp_hi; p.bits = bits; p.start = start; p.corr_max = corr_max; p.cir = cir;
+	p.nwin_max = s1 - s0;
+	const int wpb = 4;
+	const size_t smem = (size_t)wpb * (3 * p.nwin_max + 2 * 160 + 16 + 2 * 160 + 8) * sizeof(float);
+	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int grid = std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
+	if (grid < 1) grid = 1;
+	vitac_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(p);
+	return post_launch(ctx, "vitac_kernel");
 }
+
+/* ---------------- Resampler ---------------- */
+int trxb200_resampler_create(trxb200_ctx *ctx, int p, int q, int filt_len, float bw, trxb200_resampler **out)
+{
+	if (!ctx || !out) return TRXB200_EINVAL;
+	*out = nullptr;
+	if (p <= 0 || q <= 0 || filt_len <= 0 || filt_len > 32) // Resampler::init returns false for zero sizes
+		return fail(ctx, TRXB200_EINVAL, "resampler: bad p/q/filt_len");
+	trxb200_resampler *r = new trxb200_resampler();
+	r->ctx = ctx; r->p = p; r->q = q; r->L = filt_len;
+	build_resampler_taps(p, q, filt_len, bw, r->taps);
+	cudaError_t e = cudaMalloc(&r->d_taps, r->taps.size() * sizeof(float));
+	if (e == cudaSuccess) e = cudaMemcpy(r->d_taps, r->taps.data(), r->taps.size() * sizeof(float), cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) { delete r; return fail(ctx, TRXB200_ECUDA, "resampler_create", e); }
+	*out = r;
+	return TRXB200_OK;
+}
+
+void trxb200_resampler_destroy(trxb200_resampler *r)
+{
+	if (!r) return;
+	cudaFree(r->d_taps);
+	delete r;
+}
+
+int trxb200_resampler_taps(trxb200_resampler *r, int path, float *out_host)
+{
+	if (!r || !out_host || path < 0 || path >= r->p) return TRXB200_EINVAL;
+	std::memcpy(out_host, r->taps.data() + (size_t)path * r->L, sizeof(float) * r->L);
+	return r->L;
+}
+
+int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out, int out_len,
+			     int out_stride, int n_streams)
+{
+	if (!r) return TRXB200_EINVAL;
+	trxb200_ctx *ctx = r->ctx;
+	if (!in || !out || n_streams < 0 || in_len <= 0 || out_len <= 0)
+		return fail(ctx, TRXB200_EINVAL, "resampler_rotate: bad argument");
+	// check_vec_len (Resampler.cpp:98-129) + MAX_OUTPUT_LEN
+	if (in_len % r->q || out_len % r->p || in_len / r->q != out_len / r->p || out_len > 4096 * 4)
+		return fail(ctx, TRXB200_EINVAL, "resampler_rotate: block length mismatch");
+	if (n_streams == 0) return TRXB200_OK;
+	resampler_kernel<<<grid_for(ctx, (long)n_streams * out_len, 256, 8), 256, 0, ctx->stream>>>(
+		in, in_stride, out, out_len, out_stride, n_streams, r->p, r->q, r->L, r->d_taps);
+	return post_launch(ctx, "resampler_kernel");
+}
+
+/* ---------------- Channelizer / Synthesis ---------------- */
+static int fb_create(trxb200_ctx *ctx, int m, int block_len, int h_len, int synth, trxb200_filterbank **out)
+{
+	if (!ctx || !out) return TRXB200_EINVAL;
+	*out = nullptr;
+	if (m < 1 || m > 256 || h_len < 1 || h_len > 32 || block_len < h_len)
+		return fail(ctx, TRXB200_EINVAL, "filterbank: bad m/block_len/h_len");
+	trxb200_filterbank *fb = new trxb200_filterbank();
+	fb->ctx = ctx; fb->m = m; fb->block_len = block_len; fb->L = h_len; fb->synth = synth;
+	build_channelizer_taps(m, h_len, fb->taps);
+	std::vector<float2> tw(m);
+	for (int k = 0; k < m; k++) {
+		const double ph = -2.0 * M_PI * (double)k / (double)m; // forward DFT, both directions (ChannelizerBase.cpp:154)
+		tw[k] = make_float2((float)cos(ph), (float)sin(ph));
+	}
+	cudaError_t e = cudaMalloc(&fb->d_taps, fb->taps.size() * sizeof(float));
+	if (e == cudaSuccess) e = cudaMemcpy(fb->d_taps, fb->taps.data(), fb->taps.size() * sizeof(float), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMalloc(&fb->d_tw, m * sizeof(float2));
+	if (e == cudaSuccess) e = cudaMemcpy(fb->d_tw, tw.data(), m * sizeof(float2), cudaMemcpyHostToDevice);
+	for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+		e = cudaMalloc(&fb->d_hist[k], (size_t)m * h_len * 8);
+		if (e == cudaSuccess) e = cudaMemset(fb->d_hist[k], 0, (size_t)m * h_len * 8);
+	}
+	if (e != cudaSuccess) { trxb200_filterbank_destroy(fb); return fail(ctx, TRXB200_ECUDA, "filterbank_create", e); }
+	*out = fb;
+	return TRXB200_OK;
+}
+
+int trxb200_channelizer_create(trxb200_ctx *ctx, int m, int block_len, int h_len, trxb200_filterbank **out)
+{
+	return fb_create(ctx, m, block_len, h_len, 0, out);
+}
+int trxb200_synthesis_create(trxb200_ctx *ctx, int m, int block_len, int h_len, trxb200_filterbank **out)
+{
+	return fb_create(ctx, m, block_len, h_len, 1, out);
+}
+
+void trxb200_filterbank_destroy(trxb200_filterbank *fb)
+{
+	if (!fb) return;
+	cudaFree(fb->d_taps); cudaFree(fb->d_tw); cudaFree(fb->d_hist[0]); cudaFree(fb->d_hist[1]);
+	delete fb;
+}
+
+int trxb200_filterbank_reset(trxb200_filterbank *fb)
+{
+	if (!fb) return TRXB200_EINVAL;
+	trxb200_ctx *ctx = fb->ctx;
+	for (int k = 0; k < 2; k++) CK(cudaMemsetAsync(fb->d_hist[k], 0, (size_t)fb->m * fb->L * 8, ctx->stream));
+	return TRXB200_OK;
+}
+
+int trxb200_filterbank_taps(trxb200_filterbank *fb, int branch, float *out_host)
+{
+	if (!fb || !out_host || branch < 0 || branch >= fb->m) return TRXB200_EINVAL;
+	std::memcpy(out_host, fb->taps.data() + (size_t)branch * fb->L, sizeof(float) * fb->L);
+	return fb->L;
+}
+
+int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *out, int n_blocks)
+{
+	if (!fb) return TRXB200_EINVAL;
+	trxb200_ctx *ctx = fb->ctx;
+	if (fb->synth || !in || !out || n_blocks < 0) return fail(ctx, TRXB200_EINVAL, "channelizer_rotate: bad argument");
+	if (n_blocks == 0) return TRXB200_OK;
+	const long total_t = (long)n_blocks * fb->block_len;
+	const size_t smem = ((size_t)fb->m * 33 + fb->m) * sizeof(float2);
+	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(channelizer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const int grid = (int)std::min<long>((total_t + 31) / 32, (long)ctx->sm_count * 4);
+	channelizer_kernel<<<grid, 256, smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, fb->m, fb->L, total_t, fb->d_taps, fb->d_tw);
+	int r = post_launch(ctx, "channelizer_kernel");
+	if (r) return r;
+	channelizer_hist_kernel<<<(fb->m * fb->L + 127) / 128, 128, 0, ctx->stream>>>(in, fb->d_hist[fb->cur ^ 1], fb->m, fb->L, total_t);
+	fb->cur ^= 1;
+	return post_launch(ctx, "channelizer_hist_kernel");
+}
+
+int trxb200_synthesis_rotate(trxb200_filterbank *fb, const float *in, float *out, int n_blocks)
+{
+	if (!fb) return TRXB200_EINVAL;
+	trxb200_ctx *ctx = fb->ctx;
+	if (!fb->synth || !in || !out || n_blocks < 0) return fail(ctx, TRXB200_EINVAL, "synthesis_rotate: bad argument");
+	if (n_blocks == 0) return TRXB200_OK;
+	const long total_t = (long)n_blocks * fb->block_len;
+	const size_t smem = ((size_t)fb->m * 65 * 2 + fb->m) * sizeof(float2);
+	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const int grid = (int)std::min<long>((total_t + 31) / 32, (long)ctx->sm_count * 2);
+	synthesis_kernel<<<grid, 256, smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, fb->m, fb->L, total_t, fb->d_taps, fb->d_tw);
+	int r = post_launch(ctx, "synthesis_kernel");
+	if (r) return r;
+	synthesis_tail_kernel<<<(fb->m * fb->L + 127) / 128, 128, 0, ctx->stream>>>(in, fb->d_hist[fb->cur ^ 1], fb->m, fb->L, total_t);
+	fb->cur ^= 1;
+	return post_launch(ctx, "synthesis_tail_kernel");
+}
+
+} // extern "C"
