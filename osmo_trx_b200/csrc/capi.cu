@@ -342,6 +342,7 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 static int check_dd(trxb200_ctx *ctx, const void *bursts, int stride, int n, int bound)
 {
 	if (!ctx) return TRXB200_EINVAL;
+	if (n == 0) return TRXB200_OK; /* empty batch: nothing to validate, nothing to do */
 	if (!bursts || stride < 625 || n < 0 || bound < 0 || bound > 1024)
 		return fail(ctx, TRXB200_EINVAL, "detect/demod: bad argument");
 	return TRXB200_OK;

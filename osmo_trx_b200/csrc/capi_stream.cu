@@ -37,7 +37,7 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 	p.clamp_lo = clamp_lo; p.clamp_hi = clamp_hi; p.bits = bits; p.start = start; p.corr_max = corr_max; p.cir = cir;
 	p.nwin_max = s1 - s0;
 	const int wpb = 4;
-	const size_t smem = (size_t)wpb * (3 * p.nwin_max + 2 * 160 + 16 + 2 * 160 + 8) * sizeof(float);
+	const size_t smem = (size_t)wpb * ((3 * p.nwin_max + 2 * 160 + 16 + 2 * 160 + 8 + 3) & ~3) * sizeof(float);
 	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int grid = std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
 	if (grid < 1) grid = 1;

@@ -3,7 +3,7 @@
 // Same contract as arch/common/convolve.h:4-26: y[i] = sum_k x[i + start - (h_len-1) + k] * h[k].
 // These replace arch/x86/convolve_sse_3.c (SSE3) and arch/arm/convolve_neon.S: one thread per
 // output sample, taps staged in shared memory, burst rows read through the read-only path.  The
-// summation trees of the SSE3 kernels are reproduced (see oracle/ and SURVEY.md Appendix B) so
+// summation trees of the SSE3 kernels are reproduced so
 // decision-bearing callers get bit-identical results; `base` selects the sequential MAC of
 // arch/common/convolve_base.c:27-82.
 #include "device_tables.cuh"

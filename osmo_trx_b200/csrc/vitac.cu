@@ -48,7 +48,7 @@ vitac_kernel(VitacParams p)
 {
 	extern __shared__ __align__(16) float vsm[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-	const int per_warp = 3 * p.nwin_max + 2 * 160 + 16 + 2 * 160 + 8;
+	const int per_warp = (3 * p.nwin_max + 2 * 160 + 16 + 2 * 160 + 8 + 3) & ~3; // keep float2 alignment per warp
 	float *base = vsm + (size_t)warp * per_warp;
 	float2 *cb = reinterpret_cast<float2 *>(base);
 	float *pw = base + 2 * p.nwin_max;

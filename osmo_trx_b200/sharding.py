@@ -1,0 +1,70 @@
+"""Multi-GPU sharding of the burst batch (one process per GPU, torch.distributed).
+
+Bursts (ARFCN x timeslot x frame) are independent and every rank holds its own copy of the tables
+(SURVEY.md §8(e)), so the data path needs no collective: each rank processes a contiguous slice of the
+burst index space.  The only exchange is result collection - per-burst records gathered to one rank and
+counters summed - which maps to NCCL all_gather / all_reduce over NVLink on GPUs and to gloo in the CPU
+tests.  This module is backend-agnostic plumbing; it never touches sample data.
+"""
+import torch
+import torch.distributed as dist
+
+COUNTER_NAMES = ("bursts", "detected", "clipped", "thresh_edge", "bisect_tie", "errors")
+
+
+def shard_range(n, rank, world):
+    """Contiguous [lo, hi) slice of n bursts for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def shard_by_arfcn(n_arfcn, rank, world):
+    """ARFCN-major partition: whole carriers per rank (all 8 timeslots of a carrier stay together)."""
+    return shard_range(n_arfcn, rank, world)
+
+
+def counters(res):
+    """Per-shard statistics tensor (int64[6]) from a result dict (rc int32[n], flags uint8[n])."""
+    rc, fl = res["rc"], res["flags"]
+    vals = [rc.numel(), int((rc > 0).sum()), int((rc == -2).sum()), int(((fl & 1) != 0).sum()),
+            int(((fl & 2) != 0).sum()), int(((rc < 0) & (rc != -2)).sum())]
+    return torch.tensor(vals, dtype=torch.int64, device=rc.device)
+
+
+def counters_device(res):
+    """Same as counters() but without host synchronisation (stays on the device stream)."""
+    rc, fl = res["rc"], res["flags"]
+    return torch.stack([torch.tensor(rc.numel(), device=rc.device), (rc > 0).sum(), (rc == -2).sum(),
+                        ((fl & 1) != 0).sum(), ((fl & 2) != 0).sum(), ((rc < 0) & (rc != -2)).sum()]).to(torch.int64)
+
+
+def reduce_counters(c, group=None):
+    """Sum the statistics over all ranks (ncclAllReduce on GPUs)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+    return c
+
+
+def gather_results(res, n_total, group=None, keys=("rc", "amp", "toa", "tsc", "ci", "flags", "soft")):
+    """All-gather per-burst result records into global burst order.
+
+    `res[k]` is this rank's slice ([n_local, ...]); shards follow shard_range(n_total, rank, world).
+    Returns a dict of tensors of length n_total on every rank.
+    """
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return {k: res[k] for k in keys}
+    world = dist.get_world_size(group)
+    sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+    maxn = max(sizes)
+    out = {}
+    for k in keys:
+        t = res[k]
+        pad_shape = (maxn,) + tuple(t.shape[1:])
+        buf = torch.zeros(pad_shape, dtype=t.dtype, device=t.device)
+        buf[: t.shape[0]] = t
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf, group=group)
+        out[k] = torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+    return out
