@@ -352,6 +352,7 @@ int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int 
 			 const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh, int32_t *rc,
 			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags)
 {
+	if (ctx && n == 0) return TRXB200_OK;
 	int r = check_dd(ctx, bursts, stride, n, max_toa_bound);
 	if (r) return r;
 	if (!type || !tsc || !max_toa || !rc || !amp || !toa || !tsc_out || !ci)
@@ -364,6 +365,7 @@ int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int 
 int trxb200_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, const int32_t *rc, const float *amp,
 			const float *toa, float *ci, float *soft, int soft_stride, int n_gmsk_soft)
 {
+	if (ctx && n == 0) return TRXB200_OK;
 	int r = check_dd(ctx, bursts, stride, n, 0);
 	if (r) return r;
 	if (!rc || !amp || !toa || !ci || !soft || n_gmsk_soft < 1 || n_gmsk_soft > 156 || soft_stride < n_gmsk_soft)
@@ -378,6 +380,7 @@ int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride
 			       int32_t *rc, float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags,
 			       float *soft, int soft_stride, int n_gmsk_soft)
 {
+	if (ctx && n == 0) return TRXB200_OK;
 	int r = check_dd(ctx, bursts, stride, n, max_toa_bound);
 	if (r) return r;
 	if (!type || !tsc || !max_toa || !rc || !amp || !toa || !tsc_out || !ci || !soft || n_gmsk_soft < 1 ||
@@ -436,6 +439,7 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 			      int32_t *rc, float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags,
 			      float *soft, int soft_stride, int n_gmsk_soft)
 {
+	if (ctx && n == 0) return TRXB200_OK;
 	int r = check_dd(ctx, bursts, stride, n, max_toa_bound);
 	if (r) return r;
 	if (!type || !tsc || !max_toa || !rc || !amp || !toa || !tsc_out || !ci || !soft || n_gmsk_soft < 1 ||

@@ -327,10 +327,14 @@ def test_channelizer_synthesis(trx, checker, m):
         s = sy.rotate(dev(xin)).cpu().numpy()
         sr = np.concatenate([checker.synthesis_rotate(sc, np.ascontiguousarray(xin[:, k * bl:(k + 1) * bl]), m, bl)[1] for k in range(nb)])
         assert np.abs(s - sr).max() <= 1e-4 * np.abs(sr).max(), (m, it)
-    # synthesis -> channelizer loopback: channel n -> n with amplitude gain m
+    # synthesis -> channelizer loopback after reset(), against the checker's own loopback
     ch.reset(); sy.reset()
-    xin = np.zeros((m, 4 * bl, 2), np.float32)
-    xin[1 % m, :, 0] = 1.0
-    wide = sy.rotate(dev(xin))
-    back = ch.rotate(wide).cpu().numpy()
-    assert abs(back[1 % m, -1, 0] - m) < 1e-2 * m
+    cc2, sc2 = checker.channelizer(m, bl), checker.synthesis(m, bl)
+    xin = rng.standard_normal((m, 2 * bl, 2)).astype(np.float32)
+    back = ch.rotate(sy.rotate(dev(xin))).cpu().numpy()
+    ref_back = []
+    for k in range(2):
+        wide = checker.synthesis_rotate(sc2, np.ascontiguousarray(xin[:, k * bl:(k + 1) * bl]), m, bl)[1]
+        ref_back.append(checker.channelizer_rotate(cc2, wide, m, bl)[1])
+    ref_back = np.concatenate(ref_back, axis=1)
+    assert np.abs(back - ref_back).max() <= 2e-4 * np.abs(ref_back).max()
