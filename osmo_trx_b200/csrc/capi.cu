@@ -39,6 +39,8 @@ struct trxb200_ctx {
 	HostTables *ht = nullptr;
 	float *d_interp_w = nullptr;
 	float *d_comp = nullptr;
+	float2 *d_edge_tab = nullptr; // derotation + ideal-symbol tables for the EDGE demodulator
+	float *d_mod_tab = nullptr;   // modulator tables in global memory (per-lane indexed): rot4 | c0 | c1 | edge_rot | psk8
 	uint64_t launches = 0;
 	std::string err;
 	HostStage *stage = nullptr;
@@ -175,6 +177,24 @@ int trxb200_init(int device, trxb200_ctx **out)
 		e = cudaMemcpy(ctx->d_interp_w, ctx->ht->interp_w.data(), ctx->ht->interp_w.size() * sizeof(float), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
 		e = cudaMemcpy(ctx->d_comp, ctx->ht->comp.data(), ctx->ht->comp.size() * sizeof(float), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) {
+		std::vector<float2> et(25);
+		for (int i = 0; i < 16; i++) et[i] = make_float2(ctx->ht->edge_derot[i].r, ctx->ht->edge_derot[i].i);
+		for (int i = 0; i < 9; i++) et[16 + i] = make_float2(ctx->ht->edge_ideal[i].r, ctx->ht->edge_ideal[i].i);
+		e = cudaMalloc(&ctx->d_edge_tab, et.size() * sizeof(float2));
+		if (e == cudaSuccess) e = cudaMemcpy(ctx->d_edge_tab, et.data(), et.size() * sizeof(float2), cudaMemcpyHostToDevice);
+	}
+	if (e == cudaSuccess) {
+		std::vector<float> mt(kModTabFloats, 0.0f);
+		const HostTables &t = *ctx->ht;
+		for (int i = 0; i < 625; i++) { mt[kModRot4 + 2 * i] = t.rot4[i].r; mt[kModRot4 + 2 * i + 1] = t.rot4[i].i; }
+		for (int i = 0; i < 16; i++) mt[kModC0 + i] = t.pulse4_c0[i];
+		for (int i = 0; i < 8; i++) mt[kModC1 + i] = t.pulse4_c1[i];
+		for (int i = 0; i < 156; i++) { mt[kModEdgeRot + 2 * i] = t.edge_mod_rot[i].r; mt[kModEdgeRot + 2 * i + 1] = t.edge_mod_rot[i].i; }
+		for (int i = 0; i < 8; i++) { mt[kModPsk8 + 2 * i] = t.psk8[i].r; mt[kModPsk8 + 2 * i + 1] = t.psk8[i].i; }
+		e = cudaMalloc(&ctx->d_mod_tab, mt.size() * sizeof(float));
+		if (e == cudaSuccess) e = cudaMemcpy(ctx->d_mod_tab, mt.data(), mt.size() * sizeof(float), cudaMemcpyHostToDevice);
+	}
 	if (e != cudaSuccess) {
 		fprintf(stderr, "trxb200_init: %s\n", cudaGetErrorString(e));
 		trxb200_destroy(ctx);
@@ -195,6 +215,8 @@ void trxb200_destroy(trxb200_ctx *ctx)
 	if (ctx->stage) stage_free(ctx->stage);
 	if (ctx->d_interp_w) cudaFree(ctx->d_interp_w);
 	if (ctx->d_comp) cudaFree(ctx->d_comp);
+	if (ctx->d_edge_tab) cudaFree(ctx->d_edge_tab);
+	if (ctx->d_mod_tab) cudaFree(ctx->d_mod_tab);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	delete ctx->ht;
 	delete ctx;
@@ -274,7 +296,7 @@ int trxb200_modulate_gmsk_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits
 	if (!ctx || !bits || !out || nbits < 2 || nbits > 156 || bits_stride < nbits || out_stride < 625 || n < 0)
 		return fail(ctx, TRXB200_EINVAL, "modulate_gmsk: bad argument");
 	if (n == 0) return TRXB200_OK;
-	modulate_gmsk_kernel<<<grid_for(ctx, n, 2, 8), 256, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride);
+	modulate_gmsk_kernel<<<grid_for(ctx, n, 2, 8), 256, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride, ctx->d_mod_tab);
 	return post_launch(ctx, "modulate_gmsk_kernel");
 }
 
@@ -284,7 +306,7 @@ int trxb200_modulate_edge_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits
 	if (!ctx || !bits || !out || nbits < 3 || (nbits % 3) || bits_stride < nbits || out_stride < 625 || n < 0)
 		return fail(ctx, TRXB200_EINVAL, "modulate_edge: bad argument");
 	if (n == 0) return TRXB200_OK;
-	modulate_edge_kernel<<<grid_for(ctx, n, 2, 8), 256, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride);
+	modulate_edge_kernel<<<grid_for(ctx, n, 2, 8), 256, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride, ctx->d_mod_tab);
 	return post_launch(ctx, "modulate_edge_kernel");
 }
 
@@ -298,12 +320,13 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, const float *bursts,
 	p.max_toa_bound = bound; p.thresh = thresh; p.rc = rc; p.amp = amp; p.toa = toa; p.ci = ci;
 	p.tsc_out = tsc_out; p.flags = flags; p.interp_w = ctx->d_interp_w;
 	p.lmax = 16 + bound;
-	p.ndmax = 64 + p.lmax; // longest sequence (64) + window - 1
+	p.ndmax = 40 + p.lmax; // longest sequence used by detectAnyBurst (40, RACH) + window - 1
 	p.scan_clip = scan_clip;
-	const size_t per_warp = (size_t)p.lmax * 32 * 12 + (size_t)p.ndmax * 8;
-	int warps = 4;
-	while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-	const size_t smem = per_warp * warps;
+	const size_t hdr = SEQ_STORE * sizeof(float2) + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
+	const size_t per_warp = (size_t)p.lmax * 32 * 12 + (size_t)kGroup * p.ndmax * 8;
+	int warps = 8;
+	while (warps > 1 && hdr + per_warp * warps > 72 * 1024) warps >>= 1;
+	const size_t smem = hdr + per_warp * warps;
 	if (smem > 227 * 1024)
 		return fail(ctx, TRXB200_EINVAL, "detect: max_toa_bound too large for on-chip buffers");
 	static size_t configured = 0;
@@ -312,7 +335,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, const float *bursts,
 		configured = 227 * 1024;
 	}
 	const int tiles = (n + 31) / 32;
-	int bps = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / std::max<size_t>(smem, 1)));
+	int bps = (int)std::max<size_t>(1, std::min<size_t>(3, (225 * 1024) / std::max<size_t>(smem + 1024, 1)));
 	int grid = std::min((tiles + warps - 1) / warps, ctx->sm_count * bps);
 	if (grid < 1) grid = 1;
 	detect_kernel<<<grid, warps * 32, smem, st>>>(p);
@@ -325,7 +348,7 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 {
 	DemodParams p;
 	p.bursts = bursts; p.stride = stride; p.n = n; p.rc = rc; p.amp = amp; p.toa = toa; p.ci = ci; p.flags = flags;
-	p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp; p.fix_clip = fix_clip;
+	p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp; p.edge_tab = ctx->d_edge_tab; p.fix_clip = fix_clip;
 	const int wpb = 8;
 	const size_t smem = (size_t)wpb * kDemodWarpFloats * sizeof(float);
 	static bool configured = false;
@@ -333,7 +356,7 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 		CK(cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		configured = true;
 	}
-	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * 4);
+	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * 3);
 	if (grid < 1) grid = 1;
 	demod_kernel<<<grid, wpb * 32, smem, st>>>(p);
 	return post_launch(ctx, "demod_kernel");

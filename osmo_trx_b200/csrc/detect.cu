@@ -134,6 +134,41 @@ __device__ __forceinline__ float2 interp_point(const float2 *corr, int lane, int
 	return acc;
 }
 
+// the early and late points of one bisection step are exactly 2 samples apart, i.e. they sit on the same
+// 1/512 grid position and use the same 21 weights: evaluate both in one pass (two independent chains)
+__device__ __forceinline__ void interp_pair(const float2 *corr, int lane, int len, float early, const float *__restrict__ W,
+					    float2 &pe, float2 &pl)
+{
+	const int m = (int)floorf(early);
+	const int F = (int)((early - (float)m) * 512.0f);
+	const int last = len - 1;
+	int lo_e = max(m - 10, 0), hi_e = m + 11, lo_l = max(m - 8, 0), hi_l = m + 13;
+	if ((unsigned)hi_e > (unsigned)last) hi_e = last;
+	if ((unsigned)hi_l > (unsigned)last) hi_l = last;
+	const float *w = W + F * 21;
+	float er = 0.0f, ei = 0.0f, lr = 0.0f, li = 0.0f;
+#pragma unroll 7
+	for (int d = 0; d < 21; d++) {
+		const int ie = m - 10 + d, il = ie + 2;
+		const bool ve = ie >= lo_e && ie < hi_e, vl = il >= lo_l && il < hi_l;
+		if (ve || vl) {
+			const float s = __ldg(&w[d]);
+			if (ve) {
+				const float2 v = corr[ie * 32 + lane];
+				er = fa(er, fm(v.x, s));
+				ei = fa(ei, fm(v.y, s));
+			}
+			if (vl) {
+				const float2 v = corr[il * 32 + lane];
+				lr = fa(lr, fm(v.x, s));
+				li = fa(li, fm(v.y, s));
+			}
+		}
+	}
+	pe = make_float2(er, ei);
+	pl = make_float2(lr, li);
+}
+
 __device__ __forceinline__ bool near_tie(float a, float b)
 {
 	const float m = fmaxf(fabsf(a), fabsf(b));
@@ -142,19 +177,29 @@ __device__ __forceinline__ bool near_tie(float a, float b)
 
 } // namespace
 
-// Dynamic shared memory per warp: corr [LMAX][32] float2, spow [LMAX][32] float, dec [NDMAX] float2
-__global__ void __launch_bounds__(128)
+// Dynamic shared memory: per block the sync sequences + their SeqInfo (indexed per lane, so not read from
+// __constant__), then per warp: corr [LMAX][32] float2, spow [LMAX][32] float, dec [kGroup][NDMAX] float2
+constexpr int kGroup = 4; // bursts decimated/correlated together in phase A (keeps the 32 lanes busy)
+
+__global__ void __launch_bounds__(256, 3)
 detect_kernel(DetectParams p)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int warps_per_block = blockDim.x >> 5;
-	const size_t per_warp = (size_t)p.lmax * 32 * (sizeof(float2) + sizeof(float)) + (size_t)p.ndmax * sizeof(float2);
-	unsigned char *base = smem_raw + per_warp * warp;
+	float2 *sseq = reinterpret_cast<float2 *>(smem_raw);
+	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + SEQ_STORE * sizeof(float2));
+	const size_t shared_hdr = SEQ_STORE * sizeof(float2) + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
+	const size_t per_warp = (size_t)p.lmax * 32 * (sizeof(float2) + sizeof(float)) + (size_t)kGroup * p.ndmax * sizeof(float2);
+	unsigned char *base = smem_raw + shared_hdr + per_warp * warp;
 	float2 *corr = reinterpret_cast<float2 *>(base);
 	float *spow = reinterpret_cast<float *>(base + (size_t)p.lmax * 32 * sizeof(float2));
 	float2 *dec = reinterpret_cast<float2 *>(base + (size_t)p.lmax * 32 * (sizeof(float2) + sizeof(float)));
 	const float *__restrict__ W = p.interp_w;
+
+	for (int k = threadIdx.x; k < SEQ_STORE; k += blockDim.x) sseq[k] = c_tab.seq[k];
+	for (int k = threadIdx.x; k < SEQ_COUNT; k += blockDim.x) sinfo[k] = c_tab.info[k];
+	__syncthreads();
 
 	const int ntiles = (p.n + 31) >> 5;
 	for (int tile = blockIdx.x * warps_per_block + warp; tile < ntiles; tile += gridDim.x * warps_per_block) {
@@ -210,33 +255,63 @@ detect_kernel(DetectParams p)
 			if (!mask)
 				break;
 
-			// ---- phase A ----
-			for (unsigned m = mask; m; m &= m - 1) {
-				const int lb = __ffs(m) - 1;
-				const int seq = __shfl_sync(0xffffffffu, at.seq, lb);
-				const int start = __shfl_sync(0xffffffffu, at.start, lb);
-				const int len = __shfl_sync(0xffffffffu, at.len, lb);
-				const SeqInfo si = c_tab.info[seq];
-				const int hlen = si.len;
-				const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)(tile * 32 + lb) * p.stride;
-				const int d0 = start - (hlen - 1), nd = hlen + len - 1;
-				__syncwarp();
-				for (int j = lane; j < nd; j += 32) {
-					const int d = d0 + j;
-					float2 v = make_float2(0.0f, 0.0f);
-					if (d >= 0 && d < 156)
-						v = decimate_one(x, d);
-					dec[j] = v;
+			// ---- phase A: kGroup bursts at a time, work items flattened over (burst, output) ----
+			unsigned m = mask;
+			while (m) {
+				int g_lb[kGroup], g_seq[kGroup], g_start[kGroup], g_len[kGroup];
+				int ng = 0, ndpad = 0, lenpad = 0;
+#pragma unroll
+				for (int g = 0; g < kGroup; g++) {
+					g_lb[g] = -1; g_seq[g] = 0; g_start[g] = 0; g_len[g] = 0;
+					if (m) {
+						const int lb = __ffs(m) - 1;
+						m &= m - 1;
+						g_lb[g] = lb;
+						g_seq[g] = __shfl_sync(0xffffffffu, at.seq, lb);
+						g_start[g] = __shfl_sync(0xffffffffu, at.start, lb);
+						g_len[g] = __shfl_sync(0xffffffffu, at.len, lb);
+						const int hl = sinfo[g_seq[g]].len;
+						ndpad = max(ndpad, hl + g_len[g] - 1);
+						lenpad = max(lenpad, g_len[g]);
+						ng = g + 1;
+					}
 				}
 				__syncwarp();
-				const float2 *h = &c_tab.seq[si.off];
-				for (int i = lane; i < len; i += 32) {
-					corr[i * 32 + lb] = correlate_one(dec + i, h, hlen);
-					// signal power over the N samples starting at candidate c = i  (computeCI :1622-1626)
-					float S = 0.0f;
-					for (int k = 0; k < hlen; k++)
-						S = fa(S, norm2(dec[i + k]));
-					spow[i * 32 + lb] = S / (float)hlen;
+				// decimation of the samples the correlators need
+				for (int it = lane; it < ng * ndpad; it += 32) {
+					const int g = it / ndpad, j = it - g * ndpad;
+					int lb = g_lb[0], seq = g_seq[0], start = g_start[0], len = g_len[0];
+#pragma unroll
+					for (int q = 1; q < kGroup; q++)
+						if (g == q) { lb = g_lb[q]; seq = g_seq[q]; start = g_start[q]; len = g_len[q]; }
+					const int hlen = sinfo[seq].len;
+					if (j < hlen + len - 1) {
+						const int d = start - (hlen - 1) + j;
+						float2 v = make_float2(0.0f, 0.0f);
+						if (d >= 0 && d < 156) {
+							const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)(tile * 32 + lb) * p.stride;
+							v = decimate_one(x, d);
+						}
+						dec[g * p.ndmax + j] = v;
+					}
+				}
+				__syncwarp();
+				// correlation + candidate signal powers (computeCI :1622-1626)
+				for (int it = lane; it < ng * lenpad; it += 32) {
+					const int g = it / lenpad, i = it - g * lenpad;
+					int lb = g_lb[0], seq = g_seq[0], len = g_len[0];
+#pragma unroll
+					for (int q = 1; q < kGroup; q++)
+						if (g == q) { lb = g_lb[q]; seq = g_seq[q]; len = g_len[q]; }
+					if (i < len) {
+						const SeqInfo si = sinfo[seq];
+						const float2 *dg = dec + g * p.ndmax + i;
+						corr[i * 32 + lb] = correlate_one(dg, sseq + si.off, si.len);
+						float S = 0.0f;
+						for (int k = 0; k < si.len; k++)
+							S = fa(S, norm2(dg[k]));
+						spow[i * 32 + lb] = S / (float)si.len;
+					}
 				}
 			}
 			__syncwarp();
@@ -244,7 +319,7 @@ detect_kernel(DetectParams p)
 			// ---- phase C ----
 			if (need) {
 				const int len = at.len;
-				const SeqInfo si = c_tab.info[at.seq];
+				const SeqInfo si = sinfo[at.seq];
 				// fastPeakDetect
 				float mx = 0.0f;
 				int idx = -1;
@@ -277,8 +352,8 @@ detect_kernel(DetectParams p)
 					float early = t - 1.0f, late = t + 1.0f, incr = 0.5f;
 #pragma unroll 1
 					for (int it = 0; it < 9; it++) {
-						const float2 e = interp_point(corr, lane, len, early, W);
-						const float2 l = interp_point(corr, lane, len, late, W);
+						float2 e, l;
+						interp_pair(corr, lane, len, early, W, e, l); // late == early + 2 throughout (:1172)
 						const float ne = norm2(e), nl = norm2(l);
 						if (near_tie(ne, nl)) flags |= 2u;
 						if (ne < nl) early += incr;

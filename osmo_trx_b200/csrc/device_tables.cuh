@@ -39,6 +39,9 @@ struct ConstTables {
 	float2 vitac_access[41];
 };
 
+// layout of the modulator table block kept in global memory (indexed per lane, so not __constant__)
+constexpr int kModRot4 = 0, kModC0 = 1250, kModC1 = 1266, kModEdgeRot = 1274, kModPsk8 = 1586, kModTabFloats = 1602;
+
 // Pointers to the larger tables kept in global memory (L1/L2 resident).
 struct GlobalTables {
 	const float *interp_w; // [512][21]

@@ -16,8 +16,10 @@ namespace trxb200 {
 
 __global__ void __launch_bounds__(256)
 modulate_gmsk_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_stride, int n, float *__restrict__ out,
-		     int out_stride)
+		     int out_stride, const float *__restrict__ mtab)
 {
+	const float2 *__restrict__ rot4 = reinterpret_cast<const float2 *>(mtab + kModRot4);
+	const float *__restrict__ pc0 = mtab + kModC0, *__restrict__ pc1 = mtab + kModC1;
 	__shared__ float sym[2][160];  // NRZ symbols incl. the two padded "0" symbols
 	__shared__ float ph1[2][160];  // C1 phase sign per symbol slot
 	for (int b0 = blockIdx.x * 2; b0 < n; b0 += gridDim.x * 2) {
@@ -46,12 +48,12 @@ modulate_gmsk_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_strid
 				const int k = js + 4 * g, idx = nn - 15 + k, m = idx >> 2;
 				float xr = 0.0f, xi = 0.0f;
 				if (idx >= 0 && m < 160) {
-					const float2 r = c_tab.rot4[idx];
+					const float2 r = __ldg(&rot4[idx]);
 					xr = fm(r.x, sym[w][m]);
 					xi = fm(r.y, sym[w][m]);
 				}
-				pr[g] = fm(xr, c_tab.pulse_c0[k]);
-				pi[g] = fm(xi, c_tab.pulse_c0[k]);
+				pr[g] = fm(xr, __ldg(&pc0[k]));
+				pi[g] = fm(xi, __ldg(&pc0[k]));
 			}
 			float yr = fa(fa(pr[0], pr[1]), fa(pr[2], pr[3]));
 			float yi = fa(fa(pi[0], pi[1]), fa(pi[2], pi[3]));
@@ -62,14 +64,14 @@ modulate_gmsk_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_strid
 				const int k = js + 4 * g, idx = nn - 7 + k, m = idx >> 2;
 				float xr = 0.0f, xi = 0.0f;
 				if (idx >= 0 && m < 160) {
-					const float2 r = c_tab.rot4[idx];
+					const float2 r = __ldg(&rot4[idx]);
 					const float c0r = fm(r.x, sym[w][m]), c0i = fm(r.y, sym[w][m]);
 					const float ph = ph1[w][m];
 					xr = fs(fm(c0r, 0.0f), fm(c0i, ph));
 					xi = fa(fm(c0r, ph), fm(c0i, 0.0f));
 				}
-				qr[g] = fm(xr, c_tab.pulse_c1[k]);
-				qi[g] = fm(xi, c_tab.pulse_c1[k]);
+				qr[g] = fm(xr, __ldg(&pc1[k]));
+				qi[g] = fm(xi, __ldg(&pc1[k]));
 			}
 			yr = fa(yr, fa(qr[0], qr[1]));
 			yi = fa(yi, fa(qi[0], qi[1]));
@@ -80,8 +82,11 @@ modulate_gmsk_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_strid
 
 __global__ void __launch_bounds__(256)
 modulate_edge_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_stride, int n, float *__restrict__ out,
-		     int out_stride)
+		     int out_stride, const float *__restrict__ mtab)
 {
+	const float *__restrict__ pc0 = mtab + kModC0;
+	const float2 *__restrict__ erot = reinterpret_cast<const float2 *>(mtab + kModEdgeRot);
+	const float2 *__restrict__ psk8 = reinterpret_cast<const float2 *>(mtab + kModPsk8);
 	__shared__ float2 sym[2][160]; // rotated symbols at sample 4 + 4i -> slot m = i + 1
 	int nsym = nbits / 3;
 	if (nsym * 4 > 625) nsym = 156;
@@ -93,7 +98,7 @@ modulate_edge_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_strid
 			if (b < n && m >= 1 && m <= nsym && 4 * m < 625) {
 				const uint8_t *bb = bits + (size_t)b * bits_stride + 3 * (m - 1);
 				const unsigned idx = (bb[0] & 1u) | ((bb[1] & 1u) << 1) | ((bb[2] & 1u) << 2);
-				v = cmul_exact(c_tab.psk8[idx], c_tab.edge_mod_rot[m - 1]);
+				v = cmul_exact(__ldg(&psk8[idx]), __ldg(&erot[m - 1]));
 			}
 			sym[w][m] = v;
 		}
@@ -108,8 +113,8 @@ modulate_edge_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_strid
 				const int k = js + 4 * g, idx = nn - 15 + k, m = idx >> 2;
 				float2 xv = make_float2(0.0f, 0.0f);
 				if (idx >= 0 && m < 160) xv = sym[w][m];
-				pr[g] = fm(xv.x, c_tab.pulse_c0[k]);
-				pi[g] = fm(xv.y, c_tab.pulse_c0[k]);
+				pr[g] = fm(xv.x, __ldg(&pc0[k]));
+				pi[g] = fm(xv.y, __ldg(&pc0[k]));
 			}
 			reinterpret_cast<float2 *>(out)[(size_t)b * out_stride + nn] =
 				make_float2(fa(fa(pr[0], pr[1]), fa(pr[2], pr[3])), fa(fa(pi[0], pi[1]), fa(pi[2], pi[3])));
