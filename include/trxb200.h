@@ -99,6 +99,12 @@ int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int 
 			 const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh, int32_t *rc,
 			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags);
 
+/* Sizing hint for the detection kernels' on-chip buffers: the longest sync sequence following batches may
+ * correlate against - 16 when only TSC / EDGE / IDLE bursts are submitted, 40 (default) when RACH / EXT_RACH
+ * may occur (generateRACHSequence uses 40 symbols, sigProcLib.cpp:1420).  A burst that needs more than the
+ * configured size is reported as -SIGERR_BOUNDS, never processed wrongly. */
+int trxb200_detect_config(trxb200_ctx *ctx, int max_seq_len);
+
 /* ---- demodulation: demodAnyBurst (sigProcLib.cpp:2130-2137) for every burst with rc[b] > 0
  *      (rc[b] is the CorrType returned by detection).  soft: f32[n][soft_stride]; GMSK bursts get
  *      `n_gmsk_soft` values (148 = what Transceiver.cpp:799-803 consumes, or 156 = the full

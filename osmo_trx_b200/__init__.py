@@ -109,6 +109,10 @@ class Trx:
             raise KeyError(name)
         return buf[:n].copy()
 
+    def detect_config(self, max_seq_len=40):
+        """16: only TSC/EDGE/IDLE bursts will be submitted (smaller on-chip buffers, higher occupancy); 40: any type."""
+        self._check(self.lib.trxb200_detect_config(self.h, C.c_int(max_seq_len)), "detect_config")
+
     # -- modulators --
     def modulate_gmsk(self, bits, out=None):
         """bits: uint8 [n, nbits] on device -> float32 [n, 625, 2]"""

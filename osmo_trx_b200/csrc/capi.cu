@@ -42,6 +42,7 @@ struct trxb200_ctx {
 	float2 *d_edge_tab = nullptr; // derotation + ideal-symbol tables for the EDGE demodulator
 	float *d_mod_tab = nullptr;   // modulator tables in global memory (per-lane indexed): rot4 | c0 | c1 | edge_rot | psk8
 	uint64_t launches = 0;
+	int max_seq_len = 40; // longest sync sequence detect batches may need (sizes on-chip buffers)
 	std::string err;
 	HostStage *stage = nullptr;
 };
@@ -247,6 +248,14 @@ int trxb200_device(trxb200_ctx *ctx) { return ctx ? ctx->device : -1; }
 int trxb200_sm_count(trxb200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t trxb200_launch_count(trxb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int trxb200_detect_config(trxb200_ctx *ctx, int max_seq_len)
+{
+	if (!ctx) return TRXB200_EINVAL;
+	if (max_seq_len != 16 && max_seq_len != 40) return fail(ctx, TRXB200_EINVAL, "detect_config: max_seq_len must be 16 or 40");
+	ctx->max_seq_len = max_seq_len;
+	return TRXB200_OK;
+}
+
 int trxb200_get_table(trxb200_ctx *ctx, const char *name, int idx, float *out, int max_floats)
 {
 	if (!ctx || !name || !out) return TRXB200_EINVAL;
@@ -320,10 +329,10 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, const float *bursts,
 	p.max_toa_bound = bound; p.thresh = thresh; p.rc = rc; p.amp = amp; p.toa = toa; p.ci = ci;
 	p.tsc_out = tsc_out; p.flags = flags; p.interp_w = ctx->d_interp_w;
 	p.lmax = 16 + bound;
-	p.ndmax = 40 + p.lmax; // longest sequence used by detectAnyBurst (40, RACH) + window - 1
+	p.ndmax = ctx->max_seq_len + p.lmax - 1; // decimated samples a correlation window needs
 	p.scan_clip = scan_clip;
-	const size_t hdr = SEQ_STORE * sizeof(float2) + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
-	const size_t per_warp = (size_t)p.lmax * 32 * 12 + (size_t)kGroup * p.ndmax * 8;
+	const size_t hdr = detect_hdr_bytes();
+	const size_t per_warp = detect_warp_bytes(p.lmax, p.ndmax);
 	int warps = 8;
 	while (warps > 1 && hdr + per_warp * warps > 72 * 1024) warps >>= 1;
 	const size_t smem = hdr + per_warp * warps;

@@ -204,27 +204,52 @@ demod_kernel(DemodParams p)
 			}
 		}
 		// ---- stage s*x into the planar window, zero outside the burst; clip scan rides along ----
+		// All 16-byte loads of the burst are issued before the first use (12 in flight per lane) so the warp
+		// pays the HBM latency once per burst; groups straddling the burst ends are patched afterwards.
 		float mx = 0.0f;
-		for (int q = lane; q < kNQ; q += 32) {
-			const int p0 = off2 + 4 * q;
-			float2 v[4];
-			if (p0 >= 0 && p0 + 3 < 625) {
-				const float4 a = __ldg(reinterpret_cast<const float4 *>(x + p0));
-				const float4 c = __ldg(reinterpret_cast<const float4 *>(x + p0 + 2));
-				v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
-				v[2] = make_float2(c.x, c.y); v[3] = make_float2(c.z, c.w);
-			} else {
+		{
+			float4 ld[6][2];
 #pragma unroll
-				for (int j = 0; j < 4; j++) {
-					const int src = p0 + j;
-					v[j] = (src >= 0 && src < 625) ? __ldg(&x[src]) : make_float2(0.0f, 0.0f);
+			for (int it = 0; it < 6; it++) {
+				const int q = lane + 32 * it;
+				const int p0 = off2 + 4 * q;
+				const bool full = (q < kNQ) && p0 >= 0 && p0 <= 621;
+				ld[it][0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+				ld[it][1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+				if (full) {
+					ld[it][0] = __ldg(reinterpret_cast<const float4 *>(x + p0));
+					ld[it][1] = __ldg(reinterpret_cast<const float4 *>(x + p0 + 2));
 				}
 			}
 #pragma unroll
-			for (int j = 0; j < 4; j++) {
-				mx = fmaxf(mx, fmaxf(fabsf(v[j].x), fabsf(v[j].y)));
-				u[j * kPlane + q] = fmaf(v[j].x, s.x, -v[j].y * s.y);
-				u[kCompWords + j * kPlane + q] = fmaf(v[j].x, s.y, v[j].y * s.x);
+			for (int it = 0; it < 6; it++) {
+				const int q = lane + 32 * it;
+				if (q < kNQ) {
+					const float4 a = ld[it][0], c = ld[it][1];
+					mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+					mx = fmaxf(mx, fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))));
+					float *ur = u + q, *ui = u + kCompWords + q;
+					ur[0 * kPlane] = fmaf(a.x, s.x, -a.y * s.y); ui[0 * kPlane] = fmaf(a.x, s.y, a.y * s.x);
+					ur[1 * kPlane] = fmaf(a.z, s.x, -a.w * s.y); ui[1 * kPlane] = fmaf(a.z, s.y, a.w * s.x);
+					ur[2 * kPlane] = fmaf(c.x, s.x, -c.y * s.y); ui[2 * kPlane] = fmaf(c.x, s.y, c.y * s.x);
+					ur[3 * kPlane] = fmaf(c.z, s.x, -c.w * s.y); ui[3 * kPlane] = fmaf(c.z, s.y, c.w * s.x);
+				}
+			}
+			// partial groups at the two ends of the burst (at most two lanes per burst have one)
+#pragma unroll
+			for (int it = 0; it < 6; it++) {
+				const int q = lane + 32 * it;
+				const int p0 = off2 + 4 * q;
+				if (q < kNQ && ((p0 < 0 && p0 > -4) || (p0 > 621 && p0 < 625))) {
+					for (int j = 0; j < 4; j++) {
+						const int src = p0 + j;
+						float2 v = make_float2(0.0f, 0.0f);
+						if (src >= 0 && src < 625) v = __ldg(&x[src]);
+						mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+						u[j * kPlane + q] = fmaf(v.x, s.x, -v.y * s.y);
+						u[kCompWords + j * kPlane + q] = fmaf(v.x, s.y, v.y * s.x);
+					}
+				}
 			}
 		}
 		if (p.flags && p.fix_clip) {
@@ -296,11 +321,14 @@ demod_kernel(DemodParams p)
 				kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
 				const int kmax = min(15, 639 + whole - 4 * i);
 				if (kmin <= 15 && kmax == 15) {
-					const float *__restrict__ c = p.comp + ((size_t)f * 16 + kmin) * 36;
+					// taps 9*part .. 9*part+8 (36th tap of the row is zero padding)
+					const float *__restrict__ c = p.comp + ((size_t)f * 16 + kmin) * 36 + 9 * part;
 					const float *uc = u + ((i & 1) ? kCompWords : 0);
-					for (int t = part * 9; t < min(35, part * 9 + 9); t++) {
-						const int w = 4 * i + t + e;
-						a = fmaf(uc[(w & 3) * kPlane + (w >> 2)], __ldg(&c[t]), a);
+					const int w0 = 4 * i + e + 9 * part;
+#pragma unroll
+					for (int j = 0; j < 9; j++) {
+						const int w = w0 + j;
+						a = fmaf(uc[(w & 3) * kPlane + (w >> 2)], __ldg(&c[j]), a);
 					}
 				} else if (kmin <= kmax && part == 0) {
 					const float2 d = slow_output(u, 4 * i + e, f, kmin, kmax);

@@ -178,8 +178,21 @@ __device__ __forceinline__ bool near_tie(float a, float b)
 } // namespace
 
 // Dynamic shared memory: per block the sync sequences + their SeqInfo (indexed per lane, so not read from
-// __constant__), then per warp: corr [LMAX][32] float2, spow [LMAX][32] float, dec [kGroup][NDMAX] float2
+// __constant__), then per warp: corr [LMAX][32] float2, pwr [NDMAX][32] float (|dec|^2 of the decimated samples,
+// for computeCI), dec [kGroup][NDMAX] float2, group parameters.
 constexpr int kGroup = 4; // bursts decimated/correlated together in phase A (keeps the 32 lanes busy)
+
+struct GroupSlot { int lb, seq_off, hlen, start, len, pad0, pad1, pad2; };
+
+__host__ __device__ inline size_t detect_warp_bytes(int lmax, int ndmax)
+{
+	return (size_t)lmax * 32 * sizeof(float2) + (size_t)ndmax * 32 * sizeof(float) + (size_t)kGroup * ndmax * sizeof(float2) +
+	       kGroup * sizeof(GroupSlot);
+}
+__host__ __device__ inline size_t detect_hdr_bytes()
+{
+	return SEQ_STORE * sizeof(float2) + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
+}
 
 __global__ void __launch_bounds__(256, 3)
 detect_kernel(DetectParams p)
@@ -189,12 +202,11 @@ detect_kernel(DetectParams p)
 	const int warps_per_block = blockDim.x >> 5;
 	float2 *sseq = reinterpret_cast<float2 *>(smem_raw);
 	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + SEQ_STORE * sizeof(float2));
-	const size_t shared_hdr = SEQ_STORE * sizeof(float2) + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
-	const size_t per_warp = (size_t)p.lmax * 32 * (sizeof(float2) + sizeof(float)) + (size_t)kGroup * p.ndmax * sizeof(float2);
-	unsigned char *base = smem_raw + shared_hdr + per_warp * warp;
+	unsigned char *base = smem_raw + detect_hdr_bytes() + detect_warp_bytes(p.lmax, p.ndmax) * warp;
 	float2 *corr = reinterpret_cast<float2 *>(base);
-	float *spow = reinterpret_cast<float *>(base + (size_t)p.lmax * 32 * sizeof(float2));
-	float2 *dec = reinterpret_cast<float2 *>(base + (size_t)p.lmax * 32 * (sizeof(float2) + sizeof(float)));
+	float *pwr = reinterpret_cast<float *>(base + (size_t)p.lmax * 32 * sizeof(float2));
+	float2 *dec = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(pwr) + (size_t)p.ndmax * 32 * sizeof(float));
+	GroupSlot *slot = reinterpret_cast<GroupSlot *>(dec + (size_t)kGroup * p.ndmax);
 	const float *__restrict__ W = p.interp_w;
 
 	for (int k = threadIdx.x; k < SEQ_STORE; k += blockDim.x) sseq[k] = c_tab.seq[k];
@@ -250,68 +262,64 @@ detect_kernel(DetectParams p)
 
 		for (int attempt = 0; attempt < 3; attempt++) {
 			Attempt at = make_attempt(type, tsc, T, attempt);
+			if (!done && at.seq >= 0 && sinfo[at.seq].len + at.len - 1 > p.ndmax) {
+				rc = -1; done = true; // window larger than trxb200_detect_config() promised: -SIGERR_BOUNDS
+			}
 			const bool need = !done && at.seq >= 0;
 			const unsigned mask = __ballot_sync(0xffffffffu, need);
 			if (!mask)
 				break;
+			const float2 *tile_x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)tile * 32 * p.stride;
 
 			// ---- phase A: kGroup bursts at a time, work items flattened over (burst, output) ----
 			unsigned m = mask;
 			while (m) {
-				int g_lb[kGroup], g_seq[kGroup], g_start[kGroup], g_len[kGroup];
+				// lanes 0..kGroup-1 publish the parameters of the next bursts of the mask
 				int ng = 0, ndpad = 0, lenpad = 0;
+				__syncwarp();
 #pragma unroll
 				for (int g = 0; g < kGroup; g++) {
-					g_lb[g] = -1; g_seq[g] = 0; g_start[g] = 0; g_len[g] = 0;
 					if (m) {
 						const int lb = __ffs(m) - 1;
 						m &= m - 1;
-						g_lb[g] = lb;
-						g_seq[g] = __shfl_sync(0xffffffffu, at.seq, lb);
-						g_start[g] = __shfl_sync(0xffffffffu, at.start, lb);
-						g_len[g] = __shfl_sync(0xffffffffu, at.len, lb);
-						const int hl = sinfo[g_seq[g]].len;
-						ndpad = max(ndpad, hl + g_len[g] - 1);
-						lenpad = max(lenpad, g_len[g]);
+						const int seq = __shfl_sync(0xffffffffu, at.seq, lb);
+						const int start = __shfl_sync(0xffffffffu, at.start, lb);
+						const int len = __shfl_sync(0xffffffffu, at.len, lb);
+						const int hl = sinfo[seq].len;
+						if (lane == 0) {
+							GroupSlot gs;
+							gs.lb = lb; gs.seq_off = sinfo[seq].off; gs.hlen = hl; gs.start = start; gs.len = len;
+							gs.pad0 = gs.pad1 = gs.pad2 = 0;
+							slot[g] = gs;
+						}
+						ndpad = max(ndpad, hl + len - 1);
+						lenpad = max(lenpad, len);
 						ng = g + 1;
 					}
 				}
 				__syncwarp();
-				// decimation of the samples the correlators need
+				// decimation of the samples the correlators need (+ their powers for computeCI)
 				for (int it = lane; it < ng * ndpad; it += 32) {
-					const int g = it / ndpad, j = it - g * ndpad;
-					int lb = g_lb[0], seq = g_seq[0], start = g_start[0], len = g_len[0];
-#pragma unroll
-					for (int q = 1; q < kGroup; q++)
-						if (g == q) { lb = g_lb[q]; seq = g_seq[q]; start = g_start[q]; len = g_len[q]; }
-					const int hlen = sinfo[seq].len;
-					if (j < hlen + len - 1) {
-						const int d = start - (hlen - 1) + j;
+					const int g = (it >= ndpad) + (it >= 2 * ndpad) + (it >= 3 * ndpad);
+					const int j = it - g * ndpad;
+					const GroupSlot gs = slot[g];
+					if (j < gs.hlen + gs.len - 1) {
+						const int d = gs.start - (gs.hlen - 1) + j;
 						float2 v = make_float2(0.0f, 0.0f);
-						if (d >= 0 && d < 156) {
-							const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)(tile * 32 + lb) * p.stride;
-							v = decimate_one(x, d);
-						}
+						if (d >= 0 && d < 156)
+							v = decimate_one(tile_x + (size_t)gs.lb * p.stride, d);
 						dec[g * p.ndmax + j] = v;
+						pwr[j * 32 + gs.lb] = norm2(v);
 					}
 				}
 				__syncwarp();
-				// correlation + candidate signal powers (computeCI :1622-1626)
+				// correlation
 				for (int it = lane; it < ng * lenpad; it += 32) {
-					const int g = it / lenpad, i = it - g * lenpad;
-					int lb = g_lb[0], seq = g_seq[0], len = g_len[0];
-#pragma unroll
-					for (int q = 1; q < kGroup; q++)
-						if (g == q) { lb = g_lb[q]; seq = g_seq[q]; len = g_len[q]; }
-					if (i < len) {
-						const SeqInfo si = sinfo[seq];
-						const float2 *dg = dec + g * p.ndmax + i;
-						corr[i * 32 + lb] = correlate_one(dg, sseq + si.off, si.len);
-						float S = 0.0f;
-						for (int k = 0; k < si.len; k++)
-							S = fa(S, norm2(dg[k]));
-						spow[i * 32 + lb] = S / (float)si.len;
-					}
+					const int g = (it >= lenpad) + (it >= 2 * lenpad) + (it >= 3 * lenpad);
+					const int i = it - g * lenpad;
+					const GroupSlot gs = slot[g];
+					if (i < gs.len)
+						corr[i * 32 + gs.lb] = correlate_one(dec + g * p.ndmax + i, sseq + gs.seq_off, gs.hlen);
 				}
 			}
 			__syncwarp();
@@ -371,7 +379,11 @@ detect_kernel(DetectParams p)
 					if (ps < 0 || ps + N > 156 || rt < 0 || rt >= len) {
 						ci = 0.0f;
 					} else {
-						const float S = spow[rt * 32 + lane];
+						// S = mean |burst[ps..ps+N)|^2, sequential (:1622-1626); pwr index j = dec index - d0 = rt + k
+						float S = 0.0f;
+						for (int k = 0; k < N; k++)
+							S = fa(S, pwr[(rt + k) * 32 + lane]);
+						S = S / (float)N;
 						const float C = norm2(xc) / si.ci_den;
 						ci = fm(3.0103f, log2f(C / fs(S, C)));
 					}

@@ -338,3 +338,23 @@ def test_channelizer_synthesis(trx, checker, m):
         ref_back.append(checker.channelizer_rotate(cc2, wide, m, bl)[1])
     ref_back = np.concatenate(ref_back, axis=1)
     assert np.abs(back - ref_back).max() <= 2e-4 * np.abs(ref_back).max()
+
+
+def test_detect_config_hint(trx, checker):
+    """With the 16-symbol sizing hint TSC/EDGE/IDLE results are unchanged and RACH bursts fail loudly."""
+    rng = np.random.default_rng(31)
+    n = 512
+    tsc = np.arange(n) % 8
+    w = checker.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng))
+    rx, _ = synth.impair(w, rng, snr_db=15.0)
+    typ = np.choose(np.arange(n) % 4, [TSC, EDGE, IDLE, RACH]).astype(np.uint8)
+    try:
+        trx.detect_config(16)
+        g = run_gpu_dd(trx, rx, typ, tsc, 4, 4)
+    finally:
+        trx.detect_config(40)
+    c = checker.detect_demod(rx, typ, tsc, 4)
+    rach = typ == RACH
+    assert (g["rc"][rach] == -1).all()  # -SIGERR_BOUNDS, not a silent wrong answer
+    for k in ("rc", "toa", "amp", "tsc"):
+        assert np.array_equal(g[k][~rach], c[k][~rach]), k
