@@ -125,6 +125,12 @@ void fill_const_tables(const HostTables &t, ConstTables &c)
 	for (int k = 0; k < 9; k++)
 		for (int i = 0; i < 26; i++) c.vitac_norm[k][i] = make_float2(t.vitac_norm[k][i].r, t.vitac_norm[k][i].i);
 	for (int i = 0; i < 41; i++) c.vitac_access[i] = make_float2(t.vitac_access[i].r, t.vitac_access[i].i);
+	for (int f = 0; f < kCompFilts; f++)
+		for (int e = 0; e < 2; e++)
+			for (int u = 0; u < 36; u++) {
+				const int tt = u - e;
+				c.comp0[f][e][u] = (tt >= 0 && tt < kCompTaps) ? t.comp[((size_t)f * 16 + 0) * kCompStride + tt] : 0.0f;
+			}
 }
 
 int grid_for(trxb200_ctx *ctx, long work_items, int per_block, int blocks_per_sm)
@@ -173,11 +179,13 @@ int trxb200_init(int device, trxb200_ctx **out)
 	delete c;
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_interp_w, ctx->ht->interp_w.size() * sizeof(float));
-	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_comp, ctx->ht->comp.size() * sizeof(float));
+	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_comp, (ctx->ht->comp.size() + 16) * sizeof(float)); // + decimator taps
 	if (e == cudaSuccess)
 		e = cudaMemcpy(ctx->d_interp_w, ctx->ht->interp_w.data(), ctx->ht->interp_w.size() * sizeof(float), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
 		e = cudaMemcpy(ctx->d_comp, ctx->ht->comp.data(), ctx->ht->comp.size() * sizeof(float), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess)
+		e = cudaMemcpy(ctx->d_comp + ctx->ht->comp.size(), ctx->ht->dnsamp, 16 * sizeof(float), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) {
 		std::vector<float2> et(25);
 		for (int i = 0; i < 16; i++) et[i] = make_float2(ctx->ht->edge_derot[i].r, ctx->ht->edge_derot[i].i);
@@ -357,7 +365,7 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 {
 	DemodParams p;
 	p.bursts = bursts; p.stride = stride; p.n = n; p.rc = rc; p.amp = amp; p.toa = toa; p.ci = ci; p.flags = flags;
-	p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp; p.edge_tab = ctx->d_edge_tab; p.fix_clip = fix_clip;
+	p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp; p.dnsamp_g = ctx->d_comp + ctx->ht->comp.size(); p.edge_tab = ctx->d_edge_tab; p.fix_clip = fix_clip;
 	const int wpb = 8;
 	const size_t smem = (size_t)wpb * kDemodWarpFloats * sizeof(float);
 	static bool configured = false;

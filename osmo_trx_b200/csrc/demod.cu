@@ -10,70 +10,117 @@
 // burst.  Where the reference's intermediate vectors are truncated (samples shifted in from outside
 // the 625-sample burst are zero, the decimator's history before sample 0 is zero) the affected
 // leading outputs use the composite truncated to the surviving decimator taps (comp[f][kmin]); outputs
-// truncated from above take a generic two-stage path.  The complex gain 1/amp is applied while the
-// burst is staged into shared memory, and because e^{-j*pi*n/2} only selects +-re/+-im (the table
-// entries are exactly +-1 on the selected component; the other has ~1e-16 leakage from the
-// double-precision phase accumulation, far below the 1e-4 soft-bit tolerance) a GMSK output needs
-// one real 35-tap dot product.  This chain feeds no decisions, so FMA is used.
+// truncated from above take a generic two-stage path.  This chain feeds no decisions, so FMA is used.
 //
-// Work mapping, one warp per burst:
-//   stage   16-byte global loads (two samples) of the burst, scaled by 1/amp, into a polyphase-planar
-//           window u[comp][phase][q] (window sample 4q+phase); the window origin is chosen 4-aligned
-//           to the 16-byte grid of the row, the residual shift e is folded into the tap index.
-//   FIR     lane l owns 5 consecutive outputs 5l..5l+4: for each polyphase plane it loads the 13 (+11)
-//           window values its outputs share and the plane's 9 taps (shared-memory broadcast), and
-//           issues 45 FMAs into 5 independent accumulators.  Lane stride 5 words = conflict free.
-//   edges   the few leading outputs whose decimator taps are truncated are recomputed with the
-//           truncated composites, 4 lanes per output + shuffle reduction.
+// The FIR runs on the RAW complex samples with Blackwell's packed FP32 pipe: one FFMA2
+// (fma.rn.f32x2) advances the (re,im) pair of an output by one real tap, so the complex sum costs the
+// same issue slots a real one would, and the staging pass is a pure copy (no arithmetic).  The
+// complex gain 1/amp and the e^{-j*pi*n/2} derotation (which only selects +-re/+-im; the table's
+// ~1e-16 leakage is far below the 1e-4 soft-bit tolerance) are applied once per output.
+//
+// Work mapping, one warp per burst (the kernel is bound by the shared-memory data pipe, so every
+// window sample is written to and read from shared memory exactly once):
+//   stage   16-byte global loads (two samples) -> 16-byte shared stores into a 680-sample window; 16-byte
+//           slot s lives at s ^ ((s/40)&1), which keeps both the staging stores and the per-lane reads
+//           below (lane stride 10 slots) bank-conflict free; the window origin is aligned to the 16-byte
+//           grid of the row, the residual shift e is folded into the tap index.  The next burst of the
+//           warp is prefetched into L2 meanwhile.
+//   FIR     transposed form: lane l owns window samples 20l..20l+19 (10 LDS.128) and scatters each into
+//           the 13 outputs 5l-8..5l+4 it can reach (180 FFMA2 with the tap as scalar-broadcast operand,
+//           taps fetched warp-uniformly from __constant__ comp0[f][e]); the 8 partial sums that belong to
+//           lanes l-1 and l-2 are handed over with shuffles once per burst.
+//   edges   the few leading outputs whose decimator taps are truncated get the dropped terms subtracted:
+//           the (at most 31) delayed samples Y[v] those taps would have read are evaluated one per lane
+//           (20-tap fractional filter from __constant__), then 4 lanes per output sum g[k]*Y[4i+k], k < kmin.
+//   store   outputs are staged in shared memory and written with 16-byte coalesced stores.
 #include "device_tables.cuh"
 #include "kernels.hpp"
 
 namespace trxb200 {
 namespace {
 
-constexpr int kPlane = 168;		 // floats per polyphase plane (q = 0..165 used)
-constexpr int kCompWords = 4 * kPlane;	 // one component
-constexpr int kNQ = 166;		 // staged q range: window samples 0 .. 663
-constexpr int kCoefWords = 40;		 // shifted composite taps ce[0..39]
-constexpr int kDemodWarpFloats = 2 * kCompWords + kCoefWords + 2 * 164; // + coef + complex dec scratch (EDGE)
+constexpr int kPairs = 340;		 // 16-byte sample pairs (slots) in the window: samples 0 .. 679
+constexpr int kScratchFloats = 2 * 164;	 // output staging + Y scratch (GMSK) / complex decimated samples (EDGE)
+constexpr int kDemodWarpFloats = 4 * kPairs + kScratchFloats;
+constexpr int kYOff = 192;		 // float offset of the Y scratch (float2[32]) inside the scratch area
 
-__device__ __forceinline__ float win_get(const float *u, int comp, int w)
+// ---- packed FP32 (sm_100 FFMA2): both halves are IEEE fma.rn ----
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
 {
-	return u[comp * kCompWords + (w & 3) * kPlane + (w >> 2)];
+	unsigned long long ra, rb, rc, rd;
+	ra = *reinterpret_cast<unsigned long long *>(&a);
+	rb = *reinterpret_cast<unsigned long long *>(&b);
+	rc = *reinterpret_cast<unsigned long long *>(&c);
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+	return *reinterpret_cast<float2 *>(&rd);
+}
+
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+	unsigned long long ra, rb, rd;
+	ra = *reinterpret_cast<unsigned long long *>(&a);
+	rb = *reinterpret_cast<unsigned long long *>(&b);
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+	return *reinterpret_cast<float2 *>(&rd);
+}
+
+// physical 16-byte slot of logical slot s (window samples 2s, 2s+1)
+__device__ __forceinline__ int slot_phys(int s) { return s ^ ((s / 40) & 1); }
+
+__device__ __forceinline__ float2 win_get(const float2 *U, int w)
+{
+	return U[2 * slot_phys(w >> 1) + (w & 1)];
 }
 
 // generic two-stage evaluation of one decimated sample restricted to decimator taps [kmin,kmax]
 // (only when the shifted burst runs off the top of the 625-sample vector); w0 = window index of tap 0
-__device__ __noinline__ float2 slow_output(const float *u, int w0, int f, int kmin, int kmax)
+__device__ __noinline__ float2 slow_output(const float2 *U, int w0, int f, int kmin, int kmax)
 {
 	float2 acc = make_float2(0.0f, 0.0f);
 	for (int k = kmin; k <= kmax; k++) {
-		float yr = 0.0f, yi = 0.0f;
+		float2 y = make_float2(0.0f, 0.0f);
 		if (f < 64) {
 			for (int j = 0; j < 20; j++) {
 				const float h = c_tab.delay[f][j];
-				yr = fmaf(win_get(u, 0, w0 + k + j), h, yr);
-				yi = fmaf(win_get(u, 1, w0 + k + j), h, yi);
+				y = ffma2(win_get(U, w0 + k + j), make_float2(h, h), y);
 			}
 		} else {
-			yr = win_get(u, 0, w0 + k + 9);
-			yi = win_get(u, 1, w0 + k + 9);
+			y = win_get(U, w0 + k + 9);
 		}
-		acc.x = fmaf(yr, c_tab.dnsamp[k], acc.x);
-		acc.y = fmaf(yi, c_tab.dnsamp[k], acc.y);
+		const float g = c_tab.dnsamp[k];
+		acc = ffma2(y, make_float2(g, g), acc);
 	}
 	return acc;
 }
 
-// Re(e^{-j*pi*i/2} * d): GMSKReverseRotate(1 sps) + real part (sigProcLib.cpp:262-287,2011-2022)
-__device__ __forceinline__ float derot_real(int i, float dr, float di)
+// (complex)1/amp applied to an unscaled FIR sum
+__device__ __forceinline__ float2 cscale(float2 a, float2 s)
 {
-	const float v = (i & 1) ? di : dr;
+	return make_float2(fmaf(a.x, s.x, -a.y * s.y), fmaf(a.x, s.y, a.y * s.x));
+}
+
+// Re(e^{-j*pi*i/2} * s * a): scale + GMSKReverseRotate(1 sps) + real part (sigProcLib.cpp:262-287,2011-2022)
+__device__ __forceinline__ float soft_out(int i, float2 a, float2 s)
+{
+	const float v = (i & 1) ? fmaf(a.x, s.y, a.y * s.x) : fmaf(a.x, s.x, -a.y * s.y);
 	return (i & 2) ? -v : v;
 }
 
+// one output with a (possibly truncated) composite: kmin..15 decimator taps present, 35 composite taps
+__device__ __forceinline__ float2 comp_output(const DemodParams &p, const float2 *U, int i, int e, int f, int kmin)
+{
+	const float *__restrict__ c = p.comp + ((size_t)f * 16 + kmin) * 36;
+	float2 d = make_float2(0.0f, 0.0f);
+#pragma unroll 5
+	for (int t = 0; t < 35; t++) {
+		const float ct = __ldg(&c[t]);
+		d = ffma2(win_get(U, 4 * i + t + e), make_float2(ct, ct), d);
+	}
+	return d;
+}
+
 // ---- EDGE: demodEdgeBurst :2105-2128 on the staged window (complex outputs) ----
-__device__ __noinline__ void demod_edge_burst(const DemodParams &p, int b, float *u, float2 *decs, const float *ce, int e, int f,
+__device__ __noinline__ void demod_edge_burst(const DemodParams &p, int b, const float2 *U, float2 *decs, float2 s, int e, int f,
 					      int whole, int lane)
 {
 	for (int i = lane; i < 160; i += 32) {
@@ -82,21 +129,12 @@ __device__ __noinline__ void demod_edge_burst(const DemodParams &p, int b, float
 			const int kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
 			const int kmax = min(15, 639 + whole - 4 * i);
 			if (kmin <= kmax) {
-				if (kmax == 15) {
-					const float *__restrict__ c = p.comp + ((size_t)f * 16 + kmin) * 36;
-#pragma unroll 5
-					for (int t = 0; t < 35; t++) {
-						const float ct = __ldg(&c[t]);
-						const int w = 4 * i + t + e;
-						const int q = (w & 3) * kPlane + (w >> 2);
-						d.x = fmaf(u[q], ct, d.x);
-						d.y = fmaf(u[kCompWords + q], ct, d.y);
-					}
-				} else {
-					d = slow_output(u, 4 * i + e, f, kmin, kmax);
-				}
+				if (kmax == 15)
+					d = comp_output(p, U, i, e, f, kmin);
+				else
+					d = slow_output(U, 4 * i + e, f, kmin, kmax);
 			}
-			decs[2 + i] = d;
+			decs[2 + i] = cscale(d, s);
 		}
 	}
 	if (lane < 2) { decs[lane] = make_float2(0.0f, 0.0f); decs[158 + lane] = make_float2(0.0f, 0.0f); }
@@ -140,6 +178,15 @@ __device__ __noinline__ void demod_edge_burst(const DemodParams &p, int b, float
 		p.ci[b] = fm(3.0103f, log2f(140.0f / err));
 }
 
+__device__ __forceinline__ void prefetch_row_l2(const float2 *x, int lane)
+{
+	// 625 samples = 5000 B: one bulk L2 prefetch of the 16-byte aligned span inside the row
+	if (lane == 0) {
+		const uintptr_t a = (reinterpret_cast<uintptr_t>(x) + 15u) & ~(uintptr_t)15u;
+		asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(4976));
+	}
+}
+
 } // namespace
 
 __global__ void __launch_bounds__(256, 3)
@@ -148,14 +195,40 @@ demod_kernel(DemodParams p)
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int wpb = blockDim.x >> 5;
-	float *u = reinterpret_cast<float *>(smem_raw) + (size_t)warp * kDemodWarpFloats;
-	float *ce = u + 2 * kCompWords;
-	float2 *decs = reinterpret_cast<float2 *>(ce + kCoefWords);
+	float2 *U = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * (kDemodWarpFloats / 2);
+	float *ostage = reinterpret_cast<float *>(U + 2 * kPairs);
+	float2 *decs = reinterpret_cast<float2 *>(ostage);
+	float2 *yv = reinterpret_cast<float2 *>(ostage + kYOff);
 	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
+	const int step = gridDim.x * wpb;
+	// decimator taps this lane applies in the leading-output correction (k = 4*(lane&3) + kk)
+	float gk[4];
+#pragma unroll
+	for (int kk = 0; kk < 4; kk++) gk[kk] = p.dnsamp_g[4 * (lane & 3) + kk];
 
-	for (int b = blockIdx.x * wpb + warp; b < p.n; b += gridDim.x * wpb) {
-		const int rc = p.rc[b];
+	int b = blockIdx.x * wpb + warp;
+	// per-burst scalars are fetched one burst ahead
+	int rc_n = 0;
+	float2 amp_n = make_float2(1.0f, 0.0f);
+	float toa_n = 0.0f;
+	if (b < p.n) {
+		rc_n = p.rc[b];
+		amp_n = reinterpret_cast<const float2 *>(p.amp)[b];
+		toa_n = p.toa[b];
+	}
+	for (; b < p.n; b += step) {
+		const int rc = rc_n;
+		const float2 amp = amp_n;
+		const float toa = toa_n;
 		const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
+		const int bn = b + step;
+		if (bn < p.n) {
+			rc_n = p.rc[bn];
+			amp_n = reinterpret_cast<const float2 *>(p.amp)[bn];
+			toa_n = p.toa[bn];
+			if (rc_n > 0)
+				prefetch_row_l2(reinterpret_cast<const float2 *>(p.bursts) + (size_t)bn * p.stride, lane);
+		}
 
 		if (rc <= 0) {
 			// undetected burst: only the deferred clipping report is left to do (sigProcLib.cpp:1746-1764)
@@ -177,10 +250,9 @@ demod_kernel(DemodParams p)
 		}
 
 		// ---- per-burst scalars (demodCommon / delayVector :1046-1060) ----
-		const float2 amp = reinterpret_cast<const float2 *>(p.amp)[b];
 		const float an = norm2(amp);
 		const float2 s = make_float2(amp.x / an, -amp.y / an); // (complex)1.0 / amp
-		const float delay = fm(-p.toa[b], 4.0f);
+		const float delay = fm(-toa, 4.0f);
 		const int whole = (int)floorf(delay);
 		const float frac = fs(delay, (float)whole);
 		int f = 64;
@@ -195,161 +267,171 @@ demod_kernel(DemodParams p)
 		const bool edge = (rc == 5);
 
 		__syncwarp();
-		// shifted composite taps: ce[u] = comp[f][0][u - e]
+		// ---- stage the raw burst into the window, zero outside the burst ----
+		// All 16-byte loads of the burst are issued before the first use (11 in flight per lane) so the warp
+		// pays the memory latency once per burst.  Slot s starts at burst sample p0 = off2 + 2s, 16-byte
+		// aligned by construction; the one slot that straddles an end of the burst is patched below.
 		{
-			const float *__restrict__ c = p.comp + (size_t)f * 16 * 36;
-			for (int k = lane; k < kCoefWords; k += 32) {
-				const int t = k - e;
-				ce[k] = (t >= 0 && t < 35) ? __ldg(&c[t]) : 0.0f;
-			}
-		}
-		// ---- stage s*x into the planar window, zero outside the burst; clip scan rides along ----
-		// All 16-byte loads of the burst are issued before the first use (12 in flight per lane) so the warp
-		// pays the HBM latency once per burst; groups straddling the burst ends are patched afterwards.
-		float mx = 0.0f;
-		{
-			float4 ld[6][2];
+			float4 ld[11];
 #pragma unroll
-			for (int it = 0; it < 6; it++) {
-				const int q = lane + 32 * it;
-				const int p0 = off2 + 4 * q;
-				const bool full = (q < kNQ) && p0 >= 0 && p0 <= 621;
-				ld[it][0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-				ld[it][1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-				if (full) {
-					ld[it][0] = __ldg(reinterpret_cast<const float4 *>(x + p0));
-					ld[it][1] = __ldg(reinterpret_cast<const float4 *>(x + p0 + 2));
+			for (int it = 0; it < 11; it++) {
+				const int sl = lane + 32 * it;
+				const int p0 = off2 + 2 * sl;
+				ld[it] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+				if ((it < 10 || sl < kPairs) && (unsigned)p0 <= 623u)
+					ld[it] = __ldg(reinterpret_cast<const float4 *>(x + p0));
+			}
+			float4 *U4 = reinterpret_cast<float4 *>(U);
+#pragma unroll
+			for (int it = 0; it < 11; it++) {
+				const int sl = lane + 32 * it;
+				if (it < 10 || sl < kPairs)
+					U4[slot_phys(sl)] = ld[it];
+			}
+			// the straddling slot: samples (-1, 0) or (624, 625), one per burst depending on the row parity
+			if (lane == 0) {
+				if (((-1 - off2) & 1) == 0) {
+					const int sl = (-1 - off2) >> 1;
+					if (sl >= 0 && sl < kPairs) U[2 * slot_phys(sl) + 1] = __ldg(&x[0]);
+				} else {
+					const int sl = (624 - off2) >> 1;
+					if (sl >= 0 && sl < kPairs) U[2 * slot_phys(sl)] = __ldg(&x[624]);
 				}
 			}
-#pragma unroll
-			for (int it = 0; it < 6; it++) {
-				const int q = lane + 32 * it;
-				if (q < kNQ) {
-					const float4 a = ld[it][0], c = ld[it][1];
-					mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
-					mx = fmaxf(mx, fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))));
-					float *ur = u + q, *ui = u + kCompWords + q;
-					ur[0 * kPlane] = fmaf(a.x, s.x, -a.y * s.y); ui[0 * kPlane] = fmaf(a.x, s.y, a.y * s.x);
-					ur[1 * kPlane] = fmaf(a.z, s.x, -a.w * s.y); ui[1 * kPlane] = fmaf(a.z, s.y, a.w * s.x);
-					ur[2 * kPlane] = fmaf(c.x, s.x, -c.y * s.y); ui[2 * kPlane] = fmaf(c.x, s.y, c.y * s.x);
-					ur[3 * kPlane] = fmaf(c.z, s.x, -c.w * s.y); ui[3 * kPlane] = fmaf(c.z, s.y, c.w * s.x);
-				}
-			}
-			// partial groups at the two ends of the burst (at most two lanes per burst have one)
-#pragma unroll
-			for (int it = 0; it < 6; it++) {
-				const int q = lane + 32 * it;
-				const int p0 = off2 + 4 * q;
-				if (q < kNQ && ((p0 < 0 && p0 > -4) || (p0 > 621 && p0 < 625))) {
-					for (int j = 0; j < 4; j++) {
-						const int src = p0 + j;
-						float2 v = make_float2(0.0f, 0.0f);
-						if (src >= 0 && src < 625) v = __ldg(&x[src]);
-						mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
-						u[j * kPlane + q] = fmaf(v.x, s.x, -v.y * s.y);
-						u[kCompWords + j * kPlane + q] = fmaf(v.x, s.y, v.y * s.x);
-					}
-				}
-			}
-		}
-		if (p.flags && p.fix_clip) {
-			// samples the window did not cover (only for extreme shifts)
-			if (off2 > 0 || off2 + 4 * kNQ < 625) {
-				for (int i = lane; i < 625; i += 32) {
-					if (i - off2 < 0 || i - off2 >= 4 * kNQ) {
-						const float2 raw = __ldg(&x[i]);
-						mx = fmaxf(mx, fmaxf(fabsf(raw.x), fabsf(raw.y)));
-					}
-				}
-			}
-#pragma unroll
-			for (int o = 16; o; o >>= 1)
-				mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-			if (lane == 0 && mx > 30000.0f) p.flags[b] |= 4;
 		}
 		__syncwarp();
 
 		if (edge) {
-			demod_edge_burst(p, b, u, decs, ce, e, f, whole, lane);
+			demod_edge_burst(p, b, U, decs, s, e, f, whole, lane);
 			continue;
 		}
 
-		// ---- GMSK main pass: lane owns outputs 5*lane .. 5*lane+4 with the untruncated composite ----
+		// ---- GMSK main pass (transposed FIR): lane owns window samples 20*lane .. 20*lane+19 and
+		//      accumulates into outputs i = 5*lane - 8 + m, m = 0..12; sample j meets output m with
+		//      tap u = j + 32 - 4m (0 <= u <= 35), coefficient ce[u] = comp0[f][e][u] ----
 		const int nout = p.n_gmsk_soft;
-		const int i0 = 5 * lane;
-		float acc[5] = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
-		if (i0 < nout) {
-			// outputs 0,2,4 of the lane use one component, 1,3 the other (parity of i0 decides which)
-			const float *uA = u + ((i0 & 1) ? kCompWords : 0) + i0;
-			const float *uB = u + ((i0 & 1) ? 0 : kCompWords) + i0;
+		{
+			float2 acc[13];
 #pragma unroll
-			for (int r = 0; r < 4; r++) {
-				float xa[13], xb[11], c[9];
+			for (int m = 0; m < 13; m++) acc[m] = make_float2(0.0f, 0.0f);
+			const float4 *U4 = reinterpret_cast<const float4 *>(U);
+			const int sw = (lane >> 2) & 1;
+			const float *__restrict__ ce = c_tab.comp0[f][e];
 #pragma unroll
-				for (int k = 0; k < 13; k++) xa[k] = uA[r * kPlane + k];
+			for (int h = 0; h < 2; h++) {
+				// samples j = 4k + 2h and 4k + 2h + 1, k = 0..4
+				float2 xa[5], xb[5];
 #pragma unroll
-				for (int k = 0; k < 11; k++) xb[k] = uB[r * kPlane + 1 + k];
+				for (int k = 0; k < 5; k++) {
+					const float4 v = U4[(10 * lane + 2 * k + h) ^ sw];
+					xa[k] = make_float2(v.x, v.y);
+					xb[k] = make_float2(v.z, v.w);
+				}
 #pragma unroll
-				for (int k = 0; k < 9; k++) c[k] = ce[4 * k + r];
+				for (int g = 0; g < 9; g++) {
+					// taps u = 4g + 2h (for xa) and u + 1 (for xb)
+					const float ca = ce[4 * g + 2 * h], cb = ce[4 * g + 2 * h + 1];
 #pragma unroll
-				for (int k = 0; k < 9; k++) {
-					acc[0] = fmaf(xa[k], c[k], acc[0]);
-					acc[2] = fmaf(xa[k + 2], c[k], acc[2]);
-					acc[4] = fmaf(xa[k + 4], c[k], acc[4]);
-					acc[1] = fmaf(xb[k], c[k], acc[1]);
-					acc[3] = fmaf(xb[k + 2], c[k], acc[3]);
+					for (int k = 0; k < 5; k++) {
+						// j = 4k + 2h, u = 4g + 2h  =>  m = (j + 32 - u) / 4 = k + 8 - g
+						const int m = k + 8 - g;
+						acc[m] = ffma2(xa[k], make_float2(ca, ca), acc[m]);
+						acc[m] = ffma2(xb[k], make_float2(cb, cb), acc[m]);
+					}
+				}
+			}
+			// hand the partial sums of outputs owned by lanes l-1 (m = 3..7) and l-2 (m = 0..2) over
+			float2 fin[5];
+#pragma unroll
+			for (int a = 0; a < 5; a++) {
+				float2 t1;
+				t1.x = __shfl_down_sync(0xffffffffu, acc[3 + a].x, 1);
+				t1.y = __shfl_down_sync(0xffffffffu, acc[3 + a].y, 1);
+				fin[a] = fadd2(acc[8 + a], t1);
+				if (a >= 2) {
+					float2 t2;
+					t2.x = __shfl_down_sync(0xffffffffu, acc[a - 2].x, 2);
+					t2.y = __shfl_down_sync(0xffffffffu, acc[a - 2].y, 2);
+					fin[a] = fadd2(fin[a], t2);
+				}
+			}
+			// soft value = Re(z_i * sum), z_i = (1/amp) * (-j)^i, i = 5*lane + a  (i mod 4 = (lane + a) mod 4);
+			// lanes 30, 31 lack their right-hand neighbours: outputs >= 150 are finished by the generic path
+			if (lane < 30) {
+				float zx = (lane & 1) ? s.y : s.x, zy = (lane & 1) ? -s.x : s.y;
+				if (lane & 2) { zx = -zx; zy = -zy; }
+#pragma unroll
+				for (int a = 0; a < 5; a++) {
+					ostage[5 * lane + a] = fmaf(zx, fin[a].x, -zy * fin[a].y);
+					const float t = zx; // z *= -j
+					zx = zy;
+					zy = -t;
 				}
 			}
 		}
-		float *orow = p.soft + (size_t)b * p.soft_stride;
-		// leading outputs have their decimator taps truncated from below (recomputed next); outputs with
-		// 4i > 624 + whole are truncated from above (generic path at the end)
+		// leading outputs have their decimator taps truncated from below (corrected next); outputs with
+		// 4i > 624 + whole are truncated from above, outputs >= 150 lack window lanes (generic path below)
 		const int nlead = min(nout, (max(15, 15 + whole) + 3) >> 2);
 		const int top = 624 + whole;
+		const int nv = 15 + max(0, whole); // delayed samples Y[v], v < nv, are what the dropped taps would read
+		__syncwarp();
+		if (nv <= 32) {
+			// Y[v] = sum_j win(v + e + j) * delay[f][j]: the delayed sample decimator tap k of output i reads, v = 4i + k
+			float2 y = make_float2(0.0f, 0.0f);
+			if (f < 64) {
 #pragma unroll
-		for (int a = 0; a < 5; a++) {
-			const int i = i0 + a;
-			if (i < nout && i >= nlead && 4 * i <= top)
-				orow[i] = derot_real(i, acc[a], acc[a]);
-		}
-		// ---- leading outputs: truncated composites, 4 lanes per output ----
-		for (int base = 0; base < nlead; base += 8) {
-			const int i = base + (lane >> 2), part = lane & 3;
-			float a = 0.0f;
-			int kmin = 16;
-			if (i < nlead) {
-				kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
-				const int kmax = min(15, 639 + whole - 4 * i);
-				if (kmin <= 15 && kmax == 15) {
-					// taps 9*part .. 9*part+8 (36th tap of the row is zero padding)
-					const float *__restrict__ c = p.comp + ((size_t)f * 16 + kmin) * 36 + 9 * part;
-					const float *uc = u + ((i & 1) ? kCompWords : 0);
-					const int w0 = 4 * i + e + 9 * part;
-#pragma unroll
-					for (int j = 0; j < 9; j++) {
-						const int w = w0 + j;
-						a = fmaf(uc[(w & 3) * kPlane + (w >> 2)], __ldg(&c[j]), a);
-					}
-				} else if (kmin <= kmax && part == 0) {
-					const float2 d = slow_output(u, 4 * i + e, f, kmin, kmax);
-					a = (i & 1) ? d.y : d.x;
+				for (int j = 0; j < 20; j++) {
+					const float hj = c_tab.delay[f][j];
+					y = ffma2(U[lane + e + j], make_float2(hj, hj), y); // w < 80: slot_phys is the identity
 				}
+			} else {
+				y = U[lane + e + 9];
 			}
-			a += __shfl_xor_sync(0xffffffffu, a, 1);
-			a += __shfl_xor_sync(0xffffffffu, a, 2);
-			if (i < nlead && part == 0)
-				orow[i] = derot_real(i, a, a);
+			yv[lane] = y;
+			__syncwarp();
+			for (int base = 0; base < nlead; base += 8) {
+				const int i = base + (lane >> 2), part = lane & 3;
+				const int kmin = min(16, max(0, max(15 - 4 * i, 15 - 4 * i + whole)));
+				float2 d = make_float2(0.0f, 0.0f);
+				if (i < nlead) {
+#pragma unroll
+					for (int kk = 0; kk < 4; kk++) {
+						const int k = 4 * part + kk;
+						if (k < kmin)
+							d = ffma2(yv[4 * i + k], make_float2(gk[kk], gk[kk]), d);
+					}
+				}
+				d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
+				d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
+				d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
+				d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
+				if (i < nlead && part == 0)
+					ostage[i] -= soft_out(i, d, s);
+			}
 		}
-		// ---- outputs truncated from above (shifted burst runs past sample 624): rare, generic path ----
-		if (4 * (nout - 1) > top) {
-			for (int i = nlead + lane; i < nout; i += 32) {
-				if (4 * i <= top) continue; // written by the main pass
+		// ---- generic per-output path (rare): outputs truncated from above (shifted burst runs past sample
+		//      624), outputs beyond the main pass (>= 150), leading outputs of very early bursts (nv > 32) ----
+		if (4 * (nout - 1) > top || nout > 150 || nv > 32) {
+			for (int i = lane; i < nout; i += 32) {
+				if (4 * i <= top && i < 150 && !(nv > 32 && i < nlead)) continue; // main pass result stands
 				const int kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
 				const int kmax = min(15, 639 + whole - 4 * i);
 				float2 d = make_float2(0.0f, 0.0f);
-				if (kmin <= kmax) d = slow_output(u, 4 * i + e, f, kmin, kmax);
-				orow[i] = derot_real(i, d.x, d.y);
+				if (kmin <= kmax)
+					d = (kmax == 15) ? comp_output(p, U, i, e, f, kmin) : slow_output(U, 4 * i + e, f, kmin, kmax);
+				ostage[i] = soft_out(i, d, s);
 			}
+		}
+		__syncwarp();
+		// ---- coalesced store of the soft row ----
+		float *orow = p.soft + (size_t)b * p.soft_stride;
+		if (((reinterpret_cast<uintptr_t>(orow) & 15u) == 0) && (nout & 3) == 0) {
+			const float4 *os4 = reinterpret_cast<const float4 *>(ostage);
+			for (int j = lane; j < (nout >> 2); j += 32)
+				reinterpret_cast<float4 *>(orow)[j] = os4[j];
+		} else {
+			for (int j = lane; j < nout; j += 32)
+				orow[j] = ostage[j];
 		}
 	}
 }

@@ -31,6 +31,7 @@ struct DemodParams {
 	float *soft;
 	int soft_stride, n_gmsk_soft;
 	const float *comp; // [65][16][36]
+	const float *dnsamp_g; // [16] decimator taps in global memory (per-lane indexed)
 	const float2 *edge_tab; // [16] derotation (cosf,-sinf)((i%16)*3pi/8) then [9] ideal 8-PSK points k=-4..4
 	int fix_clip;
 };
