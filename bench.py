@@ -272,7 +272,8 @@ def main():
     n = args.bursts
     rx, typ, tsc, max_toa, bound = make_workload(trx, args.workload, n, seed=1000 + rank, device=device)
     out = trx.alloc_results(n, 148)
-    trx.detect_config(40 if args.workload == "rach" else 16)  # host knows the slot types it submits
+    # the host knows the slot types it submits: sync length 16/40, detection rounds (EDGE falls back to TSC)
+    trx.detect_config(40 if args.workload == "rach" else 16, 2 if args.workload == "edge" else 1)
     launches0 = trx.launch_count
 
     def step():

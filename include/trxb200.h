@@ -49,7 +49,8 @@ enum trxb200_sigerr { TRXB200_SIGERR_NONE = 0, TRXB200_SIGERR_BOUNDS = 1, TRXB20
 /* per-burst edge-case flags (north_star parity rule: such bursts are counted and reported) */
 #define TRXB200_FLAG_THRESH_EDGE 1 /* |peak-to-average - threshold| < 1e-5 */
 #define TRXB200_FLAG_BISECT_TIE 2  /* early/late powers within 4 ulp in some TOA bisection step */
-#define TRXB200_FLAG_CLIP 4	   /* max(|I|,|Q|) > 30000 (sigProcLib.cpp:49,1746) */
+#define TRXB200_FLAG_CLIP 4	   /* undetected burst with max(|I|,|Q|) > 30000, i.e. rc == -SIGERR_CLIP
+				    * (sigProcLib.cpp:49,1746-1764; what Transceiver.cpp:772 counts as rx_clipping) */
 
 #define TRXB200_BURST_LEN 625	/* samples per slot at 4 sps (radioInterface.cpp:257-258) */
 #define TRXB200_GMSK_SOFT 156	/* demodGmskBurst output length (sigProcLib.cpp:2055-2072) */
@@ -99,11 +100,13 @@ int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int 
 			 const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh, int32_t *rc,
 			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags);
 
-/* Sizing hint for the detection kernels' on-chip buffers: the longest sync sequence following batches may
+/* Sizing hints for the detection kernels.  max_seq_len: the longest sync sequence following batches may
  * correlate against - 16 when only TSC / EDGE / IDLE bursts are submitted, 40 (default) when RACH / EXT_RACH
- * may occur (generateRACHSequence uses 40 symbols, sigProcLib.cpp:1420).  A burst that needs more than the
- * configured size is reported as -SIGERR_BOUNDS, never processed wrongly. */
-int trxb200_detect_config(trxb200_ctx *ctx, int max_seq_len);
+ * may occur (generateRACHSequence uses 40 symbols, sigProcLib.cpp:1420).  max_attempts: detection rounds
+ * scheduled per batch - 1 when only TSC / RACH / IDLE bursts are submitted, 2 with EDGE (detectAnyBurst retries
+ * an EDGE miss as TSC, sigProcLib.cpp:1933-1941), 3 (default) with EXT_RACH (three sync sequences, :1793-1800).
+ * A burst that needs more than the configured sizes is reported as -SIGERR_BOUNDS, never processed wrongly. */
+int trxb200_detect_config(trxb200_ctx *ctx, int max_seq_len, int max_attempts);
 
 /* ---- demodulation: demodAnyBurst (sigProcLib.cpp:2130-2137) for every burst with rc[b] > 0
  *      (rc[b] is the CorrType returned by detection).  soft: f32[n][soft_stride]; GMSK bursts get

@@ -109,9 +109,10 @@ class Trx:
             raise KeyError(name)
         return buf[:n].copy()
 
-    def detect_config(self, max_seq_len=40):
-        """16: only TSC/EDGE/IDLE bursts will be submitted (smaller on-chip buffers, higher occupancy); 40: any type."""
-        self._check(self.lib.trxb200_detect_config(self.h, C.c_int(max_seq_len)), "detect_config")
+    def detect_config(self, max_seq_len=40, max_attempts=3):
+        """max_seq_len 16: only TSC/EDGE/IDLE bursts will be submitted (smaller on-chip buffers); 40: any type.
+        max_attempts: detection rounds per batch (1: TSC/RACH/IDLE only, 2: + EDGE, 3: + EXT_RACH)."""
+        self._check(self.lib.trxb200_detect_config(self.h, C.c_int(max_seq_len), C.c_int(max_attempts)), "detect_config")
 
     # -- modulators --
     def modulate_gmsk(self, bits, out=None):

@@ -31,18 +31,27 @@ using namespace trxb200;
 
 struct HostStage; // pinned staging for the *_host entry points
 
+// intermediates of the detection kernels (corr_kernel -> peak_kernel), sized for one chunk of bursts
+struct DetectScratch {
+	float2 *corr = nullptr; // [cap][lmax]
+	float *pwr = nullptr;	// [cap][ndmax]
+	size_t corr_bytes = 0, pwr_bytes = 0;
+};
+
 struct trxb200_ctx {
 	int device = -1;
 	int sm_count = 0;
 	cudaStream_t own_stream = nullptr;
 	cudaStream_t stream = nullptr;
 	HostTables *ht = nullptr;
-	float *d_interp_w = nullptr;
+	float *d_sinc512 = nullptr;
 	float *d_comp = nullptr;
 	float2 *d_edge_tab = nullptr; // derotation + ideal-symbol tables for the EDGE demodulator
 	float *d_mod_tab = nullptr;   // modulator tables in global memory (per-lane indexed): rot4 | c0 | c1 | edge_rot | psk8
 	uint64_t launches = 0;
 	int max_seq_len = 40; // longest sync sequence detect batches may need (sizes on-chip buffers)
+	int max_attempts = 3; // detection rounds scheduled per batch (EXT_RACH needs 3, EDGE 2, others 1)
+	DetectScratch ws;     // used by the *_batch entry points (one stream at a time)
 	std::string err;
 	HostStage *stage = nullptr;
 };
@@ -58,6 +67,7 @@ struct HostStage {
 	uint16_t *d_max_toa[kSlots] = {};
 	int32_t *d_rc[kSlots] = {};
 	float *d_amp[kSlots] = {}, *d_toa[kSlots] = {}, *d_ci[kSlots] = {}, *d_soft[kSlots] = {};
+	DetectScratch ws[kSlots];
 };
 
 namespace {
@@ -178,10 +188,10 @@ int trxb200_init(int device, trxb200_ctx **out)
 	cudaError_t e = cudaMemcpyToSymbol(c_tab, c, sizeof(ConstTables));
 	delete c;
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_interp_w, ctx->ht->interp_w.size() * sizeof(float));
+	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_sinc512, ctx->ht->sinc512.size() * sizeof(float));
 	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_comp, (ctx->ht->comp.size() + 16) * sizeof(float)); // + decimator taps
 	if (e == cudaSuccess)
-		e = cudaMemcpy(ctx->d_interp_w, ctx->ht->interp_w.data(), ctx->ht->interp_w.size() * sizeof(float), cudaMemcpyHostToDevice);
+		e = cudaMemcpy(ctx->d_sinc512, ctx->ht->sinc512.data(), ctx->ht->sinc512.size() * sizeof(float), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
 		e = cudaMemcpy(ctx->d_comp, ctx->ht->comp.data(), ctx->ht->comp.size() * sizeof(float), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
@@ -222,7 +232,9 @@ void trxb200_destroy(trxb200_ctx *ctx)
 		return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stage) stage_free(ctx->stage);
-	if (ctx->d_interp_w) cudaFree(ctx->d_interp_w);
+	if (ctx->d_sinc512) cudaFree(ctx->d_sinc512);
+	cudaFree(ctx->ws.corr);
+	cudaFree(ctx->ws.pwr);
 	if (ctx->d_comp) cudaFree(ctx->d_comp);
 	if (ctx->d_edge_tab) cudaFree(ctx->d_edge_tab);
 	if (ctx->d_mod_tab) cudaFree(ctx->d_mod_tab);
@@ -256,11 +268,13 @@ int trxb200_device(trxb200_ctx *ctx) { return ctx ? ctx->device : -1; }
 int trxb200_sm_count(trxb200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t trxb200_launch_count(trxb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-int trxb200_detect_config(trxb200_ctx *ctx, int max_seq_len)
+int trxb200_detect_config(trxb200_ctx *ctx, int max_seq_len, int max_attempts)
 {
 	if (!ctx) return TRXB200_EINVAL;
 	if (max_seq_len != 16 && max_seq_len != 40) return fail(ctx, TRXB200_EINVAL, "detect_config: max_seq_len must be 16 or 40");
+	if (max_attempts < 1 || max_attempts > 3) return fail(ctx, TRXB200_EINVAL, "detect_config: max_attempts must be 1..3");
 	ctx->max_seq_len = max_seq_len;
+	ctx->max_attempts = max_attempts;
 	return TRXB200_OK;
 }
 
@@ -299,6 +313,7 @@ int trxb200_get_table(trxb200_ctx *ctx, const char *name, int idx, float *out, i
 	else if (base == "vitac_access") cx(t.vitac_access, 41);
 	else if (base == "vitac_sch") cx(t.vitac_sch, 64);
 	else if (base == "interp_w") v = t.interp_w;
+	else if (base == "sinc512") v = t.sinc512;
 	else if (base == "comp") { if (idx < 0 || idx >= kCompFilts * 16) return TRXB200_EINVAL; v.assign(&t.comp[(size_t)idx * kCompStride], &t.comp[(size_t)idx * kCompStride] + kCompStride); }
 	else return TRXB200_EINVAL;
 	if ((int)v.size() > max_floats) return TRXB200_EINVAL;
@@ -328,35 +343,86 @@ int trxb200_modulate_edge_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits
 }
 
 /* ---------------- detection / demodulation ---------------- */
-static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, int stride, int n, const uint8_t *type,
-			 const uint8_t *tsc, const uint16_t *max_toa, int bound, float thresh, int32_t *rc, float *amp,
-			 float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags, int scan_clip)
+static int gcd_i(long a, long b) { while (b) { long t = a % b; a = b; b = t; } return (int)a; }
+
+static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, const float *bursts, int stride, int n,
+			 const uint8_t *type, const uint8_t *tsc, const uint16_t *max_toa, int bound, float thresh, int32_t *rc,
+			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags, int scan_clip)
 {
-	DetectParams p;
-	p.bursts = bursts; p.stride = stride; p.n = n; p.type = type; p.tsc = tsc; p.max_toa = max_toa;
-	p.max_toa_bound = bound; p.thresh = thresh; p.rc = rc; p.amp = amp; p.toa = toa; p.ci = ci;
-	p.tsc_out = tsc_out; p.flags = flags; p.interp_w = ctx->d_interp_w;
-	p.lmax = 16 + bound;
-	p.ndmax = ctx->max_seq_len + p.lmax - 1; // decimated samples a correlation window needs
-	p.scan_clip = scan_clip;
-	const size_t hdr = detect_hdr_bytes();
-	const size_t per_warp = detect_warp_bytes(p.lmax, p.ndmax);
-	int warps = 8;
-	while (warps > 1 && hdr + per_warp * warps > 72 * 1024) warps >>= 1;
-	const size_t smem = hdr + per_warp * warps;
-	if (smem > 227 * 1024)
+	const int lmax = 16 + bound;
+	const int ndmax = ctx->max_seq_len + lmax - 1; // decimated samples a correlation window needs
+	// ---- launch geometry ----
+	int cw = 8; // warps per corr block
+	while (cw > 1 && corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw > 72 * 1024) cw >>= 1;
+	const size_t csmem = corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw;
+	int pw = 16; // warps per peak block
+	while (pw > 1 && peak_hdr_bytes() + peak_warp_bytes(lmax) * pw > 200 * 1024) pw >>= 1;
+	const size_t psmem = peak_hdr_bytes() + peak_warp_bytes(lmax) * pw;
+	if (csmem > 227 * 1024 || psmem > 227 * 1024)
 		return fail(ctx, TRXB200_EINVAL, "detect: max_toa_bound too large for on-chip buffers");
-	static size_t configured = 0;
-	if (smem > 48 * 1024 && smem > configured) {
-		CK(cudaFuncSetAttribute(detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-		configured = 227 * 1024;
+	static bool configured = false;
+	if (!configured) {
+		CK(cudaFuncSetAttribute(corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		CK(cudaFuncSetAttribute(peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		configured = true;
 	}
-	const int tiles = (n + 31) / 32;
-	int bps = (int)std::max<size_t>(1, std::min<size_t>(3, (225 * 1024) / std::max<size_t>(smem + 1024, 1)));
-	int grid = std::min((tiles + warps - 1) / warps, ctx->sm_count * bps);
-	if (grid < 1) grid = 1;
-	detect_kernel<<<grid, warps * 32, smem, st>>>(p);
-	return post_launch(ctx, "detect_kernel");
+	const int cbps = (int)std::max<size_t>(1, std::min<size_t>(3, (225 * 1024) / (csmem + 1024)));
+	const int pbps = (int)std::max<size_t>(1, std::min<size_t>(2, (225 * 1024) / (psmem + 1024)));
+	const long corr_sweep = (long)ctx->sm_count * cbps * cw * kGroup; // bursts one full wave of corr warps covers
+	const long peak_sweep = (long)ctx->sm_count * pbps * pw * 32;
+	// chunk: a whole number of sweeps of both kernels (no tail quantisation), small enough that the
+	// intermediates (lmax*8 + ndmax*4 bytes per burst) stay L2 resident
+	long chunk = corr_sweep / gcd_i(corr_sweep, peak_sweep) * peak_sweep;
+	const long cap = 262144;
+	if (chunk > cap) chunk = std::max<long>(1, cap / peak_sweep) * peak_sweep;
+	else chunk *= std::max<long>(1, cap / chunk);
+	if (chunk > n) chunk = n;
+	// ---- scratch ----
+	const size_t need_c = (size_t)chunk * lmax * sizeof(float2), need_p = (size_t)chunk * ndmax * sizeof(float);
+	if (ws.corr_bytes < need_c) {
+		CK(cudaStreamSynchronize(st));
+		cudaFree(ws.corr);
+		ws.corr = nullptr; ws.corr_bytes = 0;
+		CK(cudaMalloc(&ws.corr, need_c));
+		ws.corr_bytes = need_c;
+	}
+	if (ws.pwr_bytes < need_p) {
+		CK(cudaStreamSynchronize(st));
+		cudaFree(ws.pwr);
+		ws.pwr = nullptr; ws.pwr_bytes = 0;
+		CK(cudaMalloc(&ws.pwr, need_p));
+		ws.pwr_bytes = need_p;
+	}
+	const int rounds = ctx->max_attempts;
+	for (long lo = 0; lo < n; lo += chunk) {
+		const int m = (int)std::min<long>(chunk, n - lo);
+		for (int r = 0; r < rounds; r++) {
+			CorrParams c;
+			c.bursts = bursts + (size_t)lo * stride * 2; c.stride = stride; c.n = m;
+			c.type = type + lo; c.tsc = tsc + lo; c.max_toa = max_toa + lo; c.rc = rc + lo; c.round = r;
+			c.max_toa_bound = bound; c.lmax = lmax; c.ndmax = ndmax; c.corr = ws.corr; c.pwr = ws.pwr; c.negzero = -0.0f;
+			const int ngroups = (m + kGroup - 1) / kGroup;
+			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));
+			corr_kernel<<<cgrid, cw * 32, csmem, st>>>(c);
+			int e = post_launch(ctx, "corr_kernel");
+			if (e) return e;
+			PeakParams q;
+			q.n = m; q.type = type + lo; q.tsc = tsc + lo; q.max_toa = max_toa + lo; q.round = r; q.last_round = (r == rounds - 1);
+			q.max_toa_bound = bound; q.thresh = thresh; q.lmax = lmax; q.ndmax = ndmax; q.corr = ws.corr; q.pwr = ws.pwr;
+			q.sinc512 = ctx->d_sinc512; q.negzero = -0.0f; q.rc = rc + lo; q.amp = amp + (size_t)lo * 2; q.toa = toa + lo; q.ci = ci + lo;
+			q.tsc_out = tsc_out + lo; q.flags = flags ? flags + lo : nullptr;
+			const int ntiles = (m + 31) / 32;
+			const int pgrid = std::max(1, std::min((ntiles + pw - 1) / pw, ctx->sm_count * pbps));
+			peak_kernel<<<pgrid, pw * 32, psmem, st>>>(q);
+			e = post_launch(ctx, "peak_kernel");
+			if (e) return e;
+		}
+	}
+	if (scan_clip) {
+		clip_kernel<<<std::max(1, std::min((n + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(bursts, stride, n, rc, flags);
+		return post_launch(ctx, "clip_kernel");
+	}
+	return TRXB200_OK;
 }
 
 static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, int stride, int n, int32_t *rc,
@@ -398,7 +464,7 @@ int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int 
 	if (!type || !tsc || !max_toa || !rc || !amp || !toa || !tsc_out || !ci)
 		return fail(ctx, TRXB200_EINVAL, "detect: null output");
 	if (n == 0) return TRXB200_OK;
-	return launch_detect(ctx, ctx->stream, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp, toa,
+	return launch_detect(ctx, ctx->stream, ctx->ws, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp, toa,
 			     tsc_out, ci, flags, 1);
 }
 
@@ -427,7 +493,7 @@ int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride
 	    n_gmsk_soft > 156 || soft_stride < n_gmsk_soft)
 		return fail(ctx, TRXB200_EINVAL, "detect_demod: bad argument");
 	if (n == 0) return TRXB200_OK;
-	r = launch_detect(ctx, ctx->stream, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp, toa,
+	r = launch_detect(ctx, ctx->stream, ctx->ws, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp, toa,
 			  tsc_out, ci, flags, 0);
 	if (r) return r;
 	return launch_demod(ctx, ctx->stream, bursts, stride, n, rc, amp, toa, ci, flags, soft, soft_stride, n_gmsk_soft, 1);
@@ -440,6 +506,7 @@ static void stage_free(HostStage *s)
 		cudaFree(s->d_bursts[k]); cudaFree(s->d_type[k]); cudaFree(s->d_tsc[k]); cudaFree(s->d_tsc_out[k]);
 		cudaFree(s->d_flags[k]); cudaFree(s->d_max_toa[k]); cudaFree(s->d_rc[k]); cudaFree(s->d_amp[k]);
 		cudaFree(s->d_toa[k]); cudaFree(s->d_ci[k]); cudaFree(s->d_soft[k]);
+		cudaFree(s->ws[k].corr); cudaFree(s->ws[k].pwr);
 		if (s->streams[k]) cudaStreamDestroy(s->streams[k]);
 		if (s->done[k]) cudaEventDestroy(s->done[k]);
 	}
@@ -501,7 +568,7 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 		CK(cudaMemcpyAsync(s->d_max_toa[slot], max_toa + lo, (size_t)m * 2, cudaMemcpyHostToDevice, st));
 		// rows of undetected bursts are never written by the kernels: define them as zero for host callers
 		CK(cudaMemsetAsync(s->d_soft[slot], 0, (size_t)m * soft_stride * 4, st));
-		r = launch_detect(ctx, st, s->d_bursts[slot], stride, m, s->d_type[slot], s->d_tsc[slot], s->d_max_toa[slot],
+		r = launch_detect(ctx, st, s->ws[slot], s->d_bursts[slot], stride, m, s->d_type[slot], s->d_tsc[slot], s->d_max_toa[slot],
 				  max_toa_bound, thresh, s->d_rc[slot], s->d_amp[slot], s->d_toa[slot], s->d_tsc_out[slot],
 				  s->d_ci[slot], s->d_flags[slot], 0);
 		if (r) return r;

@@ -1,23 +1,27 @@
 // detect.cu — batched burst detection (detectAnyBurst, sigProcLib.cpp:1926-1957) for sm_100a.
 //
-// Work decomposition (one warp owns a tile of 32 bursts, no block-level barriers):
-//   phase A  (warp cooperates on one burst at a time, lanes = output samples)
-//            4 sps -> 1 sps decimation of only the samples the correlator window needs
-//            (downsampleBurst :1587-1601), correlation against the sync sequence (:1674) and the
-//            candidate signal powers computeCI may need (:1622-1626).  Every output is an
-//            independent dot product evaluated in the reference's float32 order, so spreading
-//            outputs over lanes keeps results bit-identical.
-//   phase C  (lanes = bursts) the inherently serial, comparison-driven part: argmax (:1120-1139),
-//            edge gate (:1683), peak-to-average threshold (:1541-1571,1689), the 9-step early/late
-//            TOA bisection over sinc-interpolated points (:1100-1118,1141-1186), C/I (:1608-1639),
-//            amp = xcorr/gain, toa bookkeeping.  One lane per burst keeps all 32 lanes busy on
-//            the long dependent chains; the correlation vectors live in shared memory laid out
-//            [sample][lane] so that same-sample accesses are conflict free.
-// The interpolation weights depend only on the tap distance and the position on the 1/512-symbol
-// bisection grid, so the table-sinc (:990-998, double-precision index math) is folded on the host
-// into interp_w[512][21] (tables.cpp); a weight is a single cached load.
+// Two kernels per detection attempt, joined by a small L2-resident intermediate (per burst the
+// correlation vector and the powers of the decimated samples, 300 B for a normal burst):
+//
+//   corr_kernel  (warp = group of 4 bursts, lanes = output samples)
+//            stages the part of each burst the correlator window needs (152 of 625 samples for a
+//            normal burst) into shared memory with 16-byte loads, decimates 4 sps -> 1 sps
+//            (downsampleBurst :1587-1601) and correlates against the sync sequence (:1674).  Every
+//            output is an independent dot product evaluated in the reference's float32 order (SSE3
+//            summation trees of convolve_sse_3.c, no FMA contraction) on the packed FP32 pipe: one
+//            FMUL2/FADD2 (mul/add.rn.f32x2) handles the (re,im) pair, so results stay bit-identical.
+//   peak_kernel  (warp = tile of 32 bursts, lanes = bursts)
+//            the inherently serial, comparison-driven part: argmax (:1120-1139), edge gate (:1683),
+//            peak-to-average threshold (:1541-1571,1689), the 9-step early/late TOA bisection over
+//            sinc-interpolated points (:1100-1118,1141-1186), C/I (:1608-1639), amp = xcorr/gain,
+//            TOA bookkeeping.  The tile's correlation vectors sit in shared memory [sample][lane]
+//            (conflict free) between zero rows, which makes the 21-tap interpolation branch free:
+//            a tap outside the reference's summation range multiplies a zero sample and adds +0.
+//            The interpolation weight of tap d at grid position F/512 is sinc(pi*|d-10-F/512|), i.e.
+//            one entry of the table-sinc folded onto the 1/512 grid (sinc512, 22 KB in shared
+//            memory): two per-lane base pointers per step, immediate offsets per tap.
 // Multi-attempt types (EDGE -> TSC fall-through :1933-1941, EXT_RACH's three sequences :1793-1800)
-// loop over attempts; only bursts that still need an attempt re-enter phase A.
+// run further rounds of the two kernels; only bursts still undetected take part.
 #include "device_tables.cuh"
 #include "kernels.hpp"
 
@@ -27,53 +31,30 @@ namespace {
 
 constexpr float kClipThresh = 30000.0f; // CLIP_THRESH sigProcLib.cpp:49
 
-// one decimated sample: sum_k x[4d-15+k] * g[k], sse_conv_real16 order (convolve_sse_3.c:188-264)
-__device__ __forceinline__ float2 decimate_one(const float2 *__restrict__ x, int d)
+// ---- packed FP32 (sm_100), exact: both halves are IEEE round-to-nearest and nothing may be contracted.
+// ptxas (12.9) fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 whatever -fmad says (it even folds
+// fma(fma(a,b,-0),1,c)), which would change the rounding of the decision-bearing sums.  The product is
+// therefore written as fma(a, b, nz) with nz = -0.0f passed in at RUN time: a*b + (-0) is the correctly
+// rounded product including the sign of a zero result, and an FFMA2 cannot be merged into the FADD2 that
+// consumes it.  (Checked in SASS: FFMA2 ... UR.F32 followed by FADD2.)
+__device__ __forceinline__ float2 mul2(float2 a, float2 b, float2 nz)
 {
-	float pr[16], pi[16];
-	const int base = 4 * d - 15;
-#pragma unroll
-	for (int k = 0; k < 16; k++) {
-		const int idx = base + k;
-		float2 v = make_float2(0.0f, 0.0f);
-		if (idx >= 0)
-			v = __ldg(&x[idx]);
-		pr[k] = fm(v.x, c_tab.dnsamp[k]);
-		pi[k] = fm(v.y, c_tab.dnsamp[k]);
-	}
-	float Lr[4], Li[4];
-#pragma unroll
-	for (int j = 0; j < 4; j++) {
-		Lr[j] = fa(fa(pr[j], pr[4 + j]), fa(pr[8 + j], pr[12 + j]));
-		Li[j] = fa(fa(pi[j], pi[4 + j]), fa(pi[8 + j], pi[12 + j]));
-	}
-	return make_float2(fa(fa(Lr[0], Lr[1]), fa(Lr[2], Lr[3])), fa(fa(Li[0], Li[1]), fa(Li[2], Li[3])));
+	unsigned long long ra, rb, rc, rd;
+	ra = *reinterpret_cast<unsigned long long *>(&a);
+	rb = *reinterpret_cast<unsigned long long *>(&b);
+	rc = *reinterpret_cast<unsigned long long *>(&nz);
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+	return *reinterpret_cast<float2 *>(&rd);
 }
-
-// one correlator output, sse_conv_cmplx_8n order (convolve_sse_3.c:462-537); hlen is 16, 40 or 64
-__device__ __forceinline__ float2 correlate_one(const float2 *__restrict__ d, const float2 *__restrict__ h, int hlen)
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
 {
-	float Ar[4] = { 0, 0, 0, 0 }, Ai[4] = { 0, 0, 0, 0 }, Br[4] = { 0, 0, 0, 0 }, Bi[4] = { 0, 0, 0, 0 };
-	for (int g = 0; g < hlen; g += 8) {
-#pragma unroll
-		for (int j = 0; j < 4; j++) {
-			float2 xv = d[g + j], hv = h[g + j];
-			Ar[j] = fa(Ar[j], fs(fm(hv.x, xv.x), fm(hv.y, xv.y)));
-			Ai[j] = fa(Ai[j], fa(fm(hv.x, xv.y), fm(hv.y, xv.x)));
-			xv = d[g + 4 + j];
-			hv = h[g + 4 + j];
-			Br[j] = fa(Br[j], fs(fm(hv.x, xv.x), fm(hv.y, xv.y)));
-			Bi[j] = fa(Bi[j], fa(fm(hv.x, xv.y), fm(hv.y, xv.x)));
-		}
-	}
-	float Lr[4], Li[4];
-#pragma unroll
-	for (int j = 0; j < 4; j++) {
-		Lr[j] = fa(Ar[j], Br[j]);
-		Li[j] = fa(Ai[j], Bi[j]);
-	}
-	return make_float2(fa(fa(Lr[0], Lr[1]), fa(Lr[2], Lr[3])), fa(fa(Li[0], Li[1]), fa(Li[2], Li[3])));
+	unsigned long long ra, rb, rd;
+	ra = *reinterpret_cast<unsigned long long *>(&a);
+	rb = *reinterpret_cast<unsigned long long *>(&b);
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+	return *reinterpret_cast<float2 *>(&rd);
 }
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
 
 struct Attempt {
 	int seq;   // sequence id or -1
@@ -111,62 +92,21 @@ __device__ __forceinline__ Attempt make_attempt(int type, int tsc, int T, int at
 	return a;
 }
 
-// interpolatePoint (sigProcLib.cpp:1100-1118) on a correlation vector stored [sample][lane]
-__device__ __forceinline__ float2 interp_point(const float2 *corr, int lane, int len, float ix, const float *__restrict__ W)
-{
-	const int m = (int)floorf(ix);
-	const int F = (int)((ix - (float)m) * 512.0f);
-	int lo = m - 10, hi = m + 11;
-	if (lo < 0) lo = 0;
-	if ((unsigned)hi > (unsigned)(len - 1)) hi = len - 1;
-	const float *w = W + F * 21;
-	float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll 7
-	for (int d = 0; d < 21; d++) {
-		const int i = m - 10 + d;
-		if (i >= lo && i < hi) {
-			const float s = __ldg(&w[d]);
-			const float2 v = corr[i * 32 + lane];
-			acc.x = fa(acc.x, fm(v.x, s));
-			acc.y = fa(acc.y, fm(v.y, s));
-		}
-	}
-	return acc;
-}
+__device__ __forceinline__ bool type_known(int type) { return type == 1 || type == 2 || type == 3 || type == 5 || type == 6; }
 
-// the early and late points of one bisection step are exactly 2 samples apart, i.e. they sit on the same
-// 1/512 grid position and use the same 21 weights: evaluate both in one pass (two independent chains)
-__device__ __forceinline__ void interp_pair(const float2 *corr, int lane, int len, float early, const float *__restrict__ W,
-					    float2 &pe, float2 &pl)
+// Does burst (type, tsc, T) run attempt `round`?  Shared by both kernels so that they agree.
+// seq_len: length of the attempt's sync sequence (from the SeqInfo table the caller holds).
+__device__ __forceinline__ bool attempt_runs(int type, int tsc, int T, int bound, int ndmax, int round, int rc_prev,
+					      const SeqInfo *sinfo, Attempt &at)
 {
-	const int m = (int)floorf(early);
-	const int F = (int)((early - (float)m) * 512.0f);
-	const int last = len - 1;
-	int lo_e = max(m - 10, 0), hi_e = m + 11, lo_l = max(m - 8, 0), hi_l = m + 13;
-	if ((unsigned)hi_e > (unsigned)last) hi_e = last;
-	if ((unsigned)hi_l > (unsigned)last) hi_l = last;
-	const float *w = W + F * 21;
-	float er = 0.0f, ei = 0.0f, lr = 0.0f, li = 0.0f;
-#pragma unroll 7
-	for (int d = 0; d < 21; d++) {
-		const int ie = m - 10 + d, il = ie + 2;
-		const bool ve = ie >= lo_e && ie < hi_e, vl = il >= lo_l && il < hi_l;
-		if (ve || vl) {
-			const float s = __ldg(&w[d]);
-			if (ve) {
-				const float2 v = corr[ie * 32 + lane];
-				er = fa(er, fm(v.x, s));
-				ei = fa(ei, fm(v.y, s));
-			}
-			if (vl) {
-				const float2 v = corr[il * 32 + lane];
-				lr = fa(lr, fm(v.x, s));
-				li = fa(li, fm(v.y, s));
-			}
-		}
-	}
-	pe = make_float2(er, ei);
-	pl = make_float2(lr, li);
+	at = make_attempt(type, tsc, T, round);
+	if (!type_known(type)) return false;
+	if ((type == 1 || type == 5) && tsc > 7) return false;
+	if (T > bound) return false;
+	if (at.seq < 0) return false;
+	if (sinfo[at.seq].len + at.len - 1 > ndmax) return false;
+	if (round > 0 && rc_prev != 0) return false;
+	return true;
 }
 
 __device__ __forceinline__ bool near_tie(float a, float b)
@@ -177,233 +117,450 @@ __device__ __forceinline__ bool near_tie(float a, float b)
 
 } // namespace
 
-// Dynamic shared memory: per block the sync sequences + their SeqInfo (indexed per lane, so not read from
-// __constant__), then per warp: corr [LMAX][32] float2, pwr [NDMAX][32] float (|dec|^2 of the decimated samples,
-// for computeCI), dec [kGroup][NDMAX] float2, group parameters.
-constexpr int kGroup = 4; // bursts decimated/correlated together in phase A (keeps the 32 lanes busy)
+// ---------------------------------------------------------------------------------------------
+// corr_kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int kGroup = 4; // bursts staged / decimated / correlated together by one warp
 
-struct GroupSlot { int lb, seq_off, hlen, start, len, pad0, pad1, pad2; };
+struct GroupSlot { int active, seq_off, hlen, start, len, nd, pad0, pad1; };
 
-__host__ __device__ inline size_t detect_warp_bytes(int lmax, int ndmax)
+// slots (16 B = 2 samples) per polyphase plane of one staged window; = 4 (mod 8) keeps the two planes
+// on disjoint bank groups for the staging stores
+__host__ __device__ inline int corr_plane_slots(int ndmax) { int s = ndmax + 3; while ((s & 7) != 4) s++; return s; }
+__host__ __device__ inline size_t corr_warp_bytes(int ndmax)
 {
-	return (size_t)lmax * 32 * sizeof(float2) + (size_t)ndmax * 32 * sizeof(float) + (size_t)kGroup * ndmax * sizeof(float2) +
-	       kGroup * sizeof(GroupSlot);
+	return (size_t)kGroup * 2 * corr_plane_slots(ndmax) * 16 + (size_t)kGroup * ndmax * 16 + kGroup * sizeof(GroupSlot);
 }
-__host__ __device__ inline size_t detect_hdr_bytes()
+__host__ __device__ inline size_t corr_hdr_bytes()
 {
-	return SEQ_STORE * sizeof(float2) + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
+	return (size_t)SEQ_STORE * 16 + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
 }
 
 __global__ void __launch_bounds__(256, 3)
-detect_kernel(DetectParams p)
+corr_kernel(CorrParams p)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int warps_per_block = blockDim.x >> 5;
-	float2 *sseq = reinterpret_cast<float2 *>(smem_raw);
-	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + SEQ_STORE * sizeof(float2));
-	unsigned char *base = smem_raw + detect_hdr_bytes() + detect_warp_bytes(p.lmax, p.ndmax) * warp;
-	float2 *corr = reinterpret_cast<float2 *>(base);
-	float *pwr = reinterpret_cast<float *>(base + (size_t)p.lmax * 32 * sizeof(float2));
-	float2 *dec = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(pwr) + (size_t)p.ndmax * 32 * sizeof(float));
+	const int wpb = blockDim.x >> 5;
+	// sync sequences as (hr, hr, -hi, hi): one 16-byte load feeds both packed products of a complex tap
+	float4 *hseq = reinterpret_cast<float4 *>(smem_raw);
+	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + (size_t)SEQ_STORE * 16);
+	const int PS = corr_plane_slots(p.ndmax);
+	unsigned char *wbase = smem_raw + corr_hdr_bytes() + corr_warp_bytes(p.ndmax) * warp;
+	float4 *raw = reinterpret_cast<float4 *>(wbase);			       // [kGroup][2][PS]
+	float4 *dec = raw + (size_t)kGroup * 2 * PS;				       // [kGroup][ndmax] (xr, xi, xi, xr)
 	GroupSlot *slot = reinterpret_cast<GroupSlot *>(dec + (size_t)kGroup * p.ndmax);
-	const float *__restrict__ W = p.interp_w;
 
-	for (int k = threadIdx.x; k < SEQ_STORE; k += blockDim.x) sseq[k] = c_tab.seq[k];
+	for (int k = threadIdx.x; k < SEQ_STORE; k += blockDim.x) {
+		const float2 h = c_tab.seq[k];
+		hseq[k] = make_float4(h.x, h.x, -h.y, h.y);
+	}
 	for (int k = threadIdx.x; k < SEQ_COUNT; k += blockDim.x) sinfo[k] = c_tab.info[k];
 	__syncthreads();
 
+	const float2 NZ = bc2(p.negzero);
+	float g16[16]; // decimator taps (Resampler(1,4) partition, reversed)
+#pragma unroll
+	for (int k = 0; k < 16; k++) g16[k] = c_tab.dnsamp[k];
+	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
+
+	const int ngroups = (p.n + kGroup - 1) / kGroup;
+	for (int grp = blockIdx.x * wpb + warp; grp < ngroups; grp += gridDim.x * wpb) {
+		const int b0 = grp * kGroup;
+		__syncwarp();
+		// ---- lanes 0..3 publish the parameters of the group's bursts ----
+		if (lane < kGroup) {
+			GroupSlot gs;
+			gs.active = 0; gs.seq_off = 0; gs.hlen = 0; gs.start = 0; gs.len = 0; gs.nd = 0; gs.pad0 = gs.pad1 = 0;
+			const int b = b0 + lane;
+			if (b < p.n) {
+				const int type = p.type[b], tsc = p.tsc[b], T = p.max_toa[b];
+				const int rc_prev = p.round > 0 ? p.rc[b] : 0;
+				Attempt at;
+				if (attempt_runs(type, tsc, T, p.max_toa_bound, p.ndmax, p.round, rc_prev, sinfo, at)) {
+					gs.active = 1;
+					gs.seq_off = sinfo[at.seq].off;
+					gs.hlen = sinfo[at.seq].len;
+					gs.start = at.start;
+					gs.len = at.len;
+					gs.nd = gs.hlen + gs.len - 1;
+				}
+			}
+			slot[lane] = gs;
+		}
+		__syncwarp();
+		int ndpad = 0, lenpad = 0;
+#pragma unroll
+		for (int g = 0; g < kGroup; g++) {
+			ndpad = max(ndpad, slot[g].nd);
+			lenpad = max(lenpad, slot[g].len);
+		}
+		if (ndpad == 0)
+			continue;
+
+		// ---- stage: window samples s_lo .. s_lo + 4*nd + 11 of each burst; sample s of the window lives in
+		//      16-byte slot s>>1, slot sl goes to plane sl&1 at index sl>>1 (conflict-free 16-byte reads at lane
+		//      stride 2 slots).  Fast path (windows inside the burst, <= 96 aligned pairs): all 16-byte loads of
+		//      the group are issued before the first shared store, so the warp pays the memory latency once. ----
+		bool fast = true;
+#pragma unroll
+		for (int g = 0; g < kGroup; g++) {
+			const GroupSlot gs = slot[g];
+			if (gs.active && (4 * (gs.start - gs.hlen + 1) - 15 < 1 || 2 * gs.nd + 7 > 96)) fast = false;
+		}
+		if (fast) {
+			float4 ld[kGroup][3];
+			int dlt[kGroup], npr[kGroup];
+#pragma unroll
+			for (int g = 0; g < kGroup; g++) {
+				const GroupSlot gs = slot[g];
+				const int b = b0 + g;
+				const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
+				const int s_lo = 4 * (gs.start - gs.hlen + 1) - 15;
+				const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
+				const int delta = (int)(((unsigned)s_lo + row_par) & 1u); // first aligned pair starts delta samples early
+				const int np = gs.active ? 2 * gs.nd + 6 + delta : 0;	    // aligned pairs covering the window
+				dlt[g] = delta;
+				npr[g] = np;
+#pragma unroll
+				for (int it = 0; it < 3; it++) {
+					const int sl = lane + 32 * it;
+					ld[g][it] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+					if (sl < np)
+						ld[g][it] = __ldg(reinterpret_cast<const float4 *>(x + (s_lo - delta + 2 * sl)));
+				}
+			}
+#pragma unroll
+			for (int g = 0; g < kGroup; g++) {
+				float2 *rg2 = reinterpret_cast<float2 *>(raw + (size_t)g * 2 * PS);
+#pragma unroll
+				for (int it = 0; it < 3; it++) {
+					const int sl = lane + 32 * it;
+					// window sample positions of the pair: r, r + 1
+					const int r = 2 * sl - dlt[g];
+					const int r1 = r + 1;
+					if (sl < npr[g]) {
+						if (r >= 0) rg2[(((r >> 1) & 1) * PS + (r >> 2)) * 2 + (r & 1)] = make_float2(ld[g][it].x, ld[g][it].y);
+						rg2[(((r1 >> 1) & 1) * PS + (r1 >> 2)) * 2 + (r1 & 1)] = make_float2(ld[g][it].z, ld[g][it].w);
+					}
+				}
+			}
+		} else {
+#pragma unroll 1
+			for (int g = 0; g < kGroup; g++) {
+				const GroupSlot gs = slot[g];
+				if (!gs.active) continue;
+				const int b = b0 + g;
+				const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
+				const int s_lo = 4 * (gs.start - gs.hlen + 1) - 15;
+				const int ns = 2 * gs.nd + 6;
+				const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
+				const bool aligned = (((unsigned)s_lo + row_par) & 1u) == 0;
+				float4 *rg = raw + (size_t)g * 2 * PS;
+				for (int sl = lane; sl < ns; sl += 32) {
+					const int idx = s_lo + 2 * sl;
+					float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+					if (aligned && idx >= 0 && idx <= 622) {
+						v = __ldg(reinterpret_cast<const float4 *>(x + idx));
+					} else {
+						// downsampleBurst reads samples 0..623 behind 16 zero history samples (:1590-1593)
+						if (idx >= 0 && idx <= 623) { const float2 a = __ldg(&x[idx]); v.x = a.x; v.y = a.y; }
+						if (idx + 1 >= 0 && idx + 1 <= 623) { const float2 a = __ldg(&x[idx + 1]); v.z = a.x; v.w = a.y; }
+					}
+					rg[(sl & 1) * PS + (sl >> 1)] = v;
+				}
+			}
+		}
+		__syncwarp();
+
+		// ---- decimation: one 1-sps sample per work item, sse_conv_real16 order (convolve_sse_3.c:188-264):
+		//      p[k] = x[4d-15+k]*g[k], L_j = (p[j]+p[4+j]) + (p[8+j]+p[12+j]), y = (L0+L1)+(L2+L3) ----
+		for (int it = lane; it < kGroup * ndpad; it += 32) {
+			const int g = (it >= ndpad) + (it >= 2 * ndpad) + (it >= 3 * ndpad);
+			const int j = it - g * ndpad;
+			const GroupSlot gs = slot[g];
+			if (!gs.active || j >= gs.nd) continue;
+			const int d = gs.start - (gs.hlen - 1) + j;
+			float2 y = make_float2(0.0f, 0.0f);
+			if (d >= 0 && d < 156) {
+				const float4 *r0 = raw + (size_t)g * 2 * PS + j; // plane 0: slots 2j, 2j+2, ...
+				const float4 *r1 = r0 + PS;			  // plane 1: slots 2j+1, ...
+				float2 pr[16];
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					const float4 a = r0[q], c = r1[q]; // samples 4q..4q+3 of the 16-sample window
+					pr[4 * q + 0] = mul2(make_float2(a.x, a.y), bc2(g16[4 * q + 0]), NZ);
+					pr[4 * q + 1] = mul2(make_float2(a.z, a.w), bc2(g16[4 * q + 1]), NZ);
+					pr[4 * q + 2] = mul2(make_float2(c.x, c.y), bc2(g16[4 * q + 2]), NZ);
+					pr[4 * q + 3] = mul2(make_float2(c.z, c.w), bc2(g16[4 * q + 3]), NZ);
+				}
+				float2 L[4];
+#pragma unroll
+				for (int q = 0; q < 4; q++)
+					L[q] = add2(add2(pr[q], pr[4 + q]), add2(pr[8 + q], pr[12 + q]));
+				y = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+			}
+			dec[(size_t)g * p.ndmax + j] = make_float4(y.x, y.y, y.y, y.x);
+			p.pwr[(size_t)(b0 + g) * p.ndmax + j] = norm2(y);
+		}
+		__syncwarp();
+
+		// ---- correlation: sse_conv_cmplx_8n order (convolve_sse_3.c:462-537); hlen is 16, 40 or 64 ----
+		for (int it = lane; it < kGroup * lenpad; it += 32) {
+			const int g = (it >= lenpad) + (it >= 2 * lenpad) + (it >= 3 * lenpad);
+			const int i = it - g * lenpad;
+			const GroupSlot gs = slot[g];
+			if (!gs.active || i >= gs.len) continue;
+			const float4 *dx = dec + (size_t)g * p.ndmax + i;
+			const float4 *hh = hseq + gs.seq_off;
+			float2 A[4], B[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) { A[q] = make_float2(0.0f, 0.0f); B[q] = make_float2(0.0f, 0.0f); }
+			for (int t0 = 0; t0 < gs.hlen; t0 += 8) {
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					float4 xv = dx[t0 + q], hv = hh[t0 + q];
+					A[q] = add2(A[q], add2(mul2(make_float2(xv.x, xv.y), make_float2(hv.x, hv.y), NZ),
+							       mul2(make_float2(xv.z, xv.w), make_float2(hv.z, hv.w), NZ)));
+					xv = dx[t0 + 4 + q];
+					hv = hh[t0 + 4 + q];
+					B[q] = add2(B[q], add2(mul2(make_float2(xv.x, xv.y), make_float2(hv.x, hv.y), NZ),
+							       mul2(make_float2(xv.z, xv.w), make_float2(hv.z, hv.w), NZ)));
+				}
+			}
+			float2 L[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) L[q] = add2(A[q], B[q]);
+			p.corr[(size_t)(b0 + g) * p.lmax + i] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// peak_kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int kPadRows = 9;    // zero rows on either side of a correlation vector (interpolation reach)
+constexpr int kRowPitch = 32;  // float2 per row = one per lane: a lane's accesses stay on its own bank pair whatever the row
+constexpr int kSinc512 = 5632; // sinc512[a] = sinc(pi * a/512), a < 11*512
+
+__host__ __device__ inline size_t peak_warp_bytes(int lmax) { return (size_t)(lmax + 2 * kPadRows) * kRowPitch * sizeof(float2); }
+__host__ __device__ inline size_t peak_hdr_bytes()
+{
+	return (size_t)kSinc512 * sizeof(float) + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
+}
+
+__global__ void __launch_bounds__(512, 1)
+peak_kernel(PeakParams p)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int wpb = blockDim.x >> 5;
+	float *stab = reinterpret_cast<float *>(smem_raw);
+	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + (size_t)kSinc512 * sizeof(float));
+	float2 *C = reinterpret_cast<float2 *>(smem_raw + peak_hdr_bytes() + peak_warp_bytes(p.lmax) * warp);
+	const int nrows = p.lmax + 2 * kPadRows;
+	const float2 NZ = bc2(p.negzero);
+
+	for (int k = threadIdx.x; k < kSinc512; k += blockDim.x) stab[k] = p.sinc512[k];
+	for (int k = threadIdx.x; k < SEQ_COUNT; k += blockDim.x) sinfo[k] = c_tab.info[k];
+	for (int k = lane; k < nrows * kRowPitch; k += 32) C[k] = make_float2(0.0f, 0.0f);
+	__syncthreads();
+
 	const int ntiles = (p.n + 31) >> 5;
-	for (int tile = blockIdx.x * warps_per_block + warp; tile < ntiles; tile += gridDim.x * warps_per_block) {
+	for (int tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
 		const int b = tile * 32 + lane;
 		const bool valid = b < p.n;
-		int type = 0, tsc = 0, T = 0;
+		int type = 0, tsc = 0, T = 0, rc = 0;
 		if (valid) {
 			type = p.type[b];
 			tsc = p.tsc[b];
 			T = p.max_toa[b];
+			if (p.round > 0) rc = p.rc[b];
 		}
-		int rc = 0;
-		bool done = !valid;
+		Attempt at;
+		const bool run = valid && attempt_runs(type, tsc, T, p.max_toa_bound, p.ndmax, p.round, rc, sinfo, at);
+
+		// ---- bring the tile's correlation vectors in: global [burst][lmax] -> shared [kPadRows + i][lane];
+		//      each lane copies its own burst's row (16-byte loads at row stride, conflict-free 8-byte stores) ----
+		__syncwarp();
+		if (run) {
+			const float2 *src = p.corr + (size_t)b * p.lmax;
+			float2 *dst = C + kPadRows * kRowPitch + lane;
+			const int len = at.len;
+			if ((p.lmax & 1) == 0) {
+				for (int i = 0; i < len; i += 2) {
+					const float4 v = __ldg(reinterpret_cast<const float4 *>(src + i));
+					dst[i * kRowPitch] = make_float2(v.x, v.y);
+					dst[(i + 1) * kRowPitch] = make_float2(v.z, v.w);
+				}
+			} else {
+				for (int i = 0; i < len; i++) dst[i * kRowPitch] = __ldg(&src[i]);
+			}
+		}
+		__syncwarp();
+
 		unsigned flags = 0;
 		float2 amp = make_float2(0.0f, 0.0f);
 		float toa = 0.0f, ci = 0.0f;
 		int tsc_out = 0;
-		bool clip = false;
+		bool write_all = false; // round 0 defines every output of a valid burst; later rounds only on a hit / error
 
-		if (valid) {
-			if ((type == 1 || type == 5) && tsc > 7) { rc = -3; done = true; tsc_out = 0; } // -SIGERR_UNSUPPORTED
-			else if (type == 1 || type == 5) tsc_out = tsc;
-			if (!done && (type == 1 || type == 2 || type == 3 || type == 5 || type == 6) && T > p.max_toa_bound) {
-				rc = -1; done = true; // -SIGERR_BOUNDS: caller's bound was wrong
+		if (valid && p.round == 0) {
+			write_all = true;
+			if ((type == 1 || type == 5) && tsc > 7) { rc = -3; tsc_out = 0; } // -SIGERR_UNSUPPORTED
+			else {
+				if (type == 1 || type == 5) tsc_out = tsc;
+				if (type_known(type) && T > p.max_toa_bound) rc = -1; // -SIGERR_BOUNDS: caller's bound was wrong
 			}
-			if (!(type == 1 || type == 2 || type == 3 || type == 5 || type == 6)) done = true; // "Invalid correlation type"
+		}
+		if (valid && !run && rc == 0 && type_known(type) && !((type == 1 || type == 5) && tsc > 7) && T <= p.max_toa_bound) {
+			// the attempt exists but its window is larger than trxb200_detect_config() promised: -SIGERR_BOUNDS
+			if (at.seq >= 0 && sinfo[at.seq].len + at.len - 1 > p.ndmax) { rc = -1; write_all = true; }
 		}
 
-		// optional clipping scan over the whole burst (maxAmplitude :1711-1722), warp per burst
-		if (p.scan_clip) {
-			unsigned need = __ballot_sync(0xffffffffu, valid && !done);
-			for (unsigned m = need; m; m &= m - 1) {
-				const int lb = __ffs(m) - 1;
-				const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)(tile * 32 + lb) * p.stride;
-				float mx = 0.0f;
-				for (int i = lane; i < 625; i += 32) {
-					const float2 v = __ldg(&x[i]);
-					mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
-				}
-#pragma unroll
-				for (int o = 16; o; o >>= 1)
-					mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-				if (lane == lb)
-					clip = mx > kClipThresh;
+		if (run) {
+			const int len = at.len;
+			const SeqInfo si = sinfo[at.seq];
+			float2 *Cl = C + kPadRows * kRowPitch + lane; // row i of this lane's burst: Cl[i * kRowPitch]
+			// rows the interpolation may touch beyond the vector are zero; the vector's last sample is
+			// excluded from interpolation (end = size - 1, :1105) and is zeroed once the gates are done
+			for (int r = len; r < len + kPadRows && r < p.lmax + kPadRows; r++) Cl[r * kRowPitch] = make_float2(0.0f, 0.0f);
+			// fastPeakDetect
+			float mx = 0.0f;
+			int idx = -1;
+			float2 pk = make_float2(0.0f, 0.0f);
+			for (int i = 0; i < len; i++) {
+				const float2 v = Cl[i * kRowPitch];
+				const float pwv = norm2(v);
+				if (pwv > mx) { mx = pwv; idx = i; pk = v; }
 			}
-			if (clip) flags |= 4u;
-		}
-
-		for (int attempt = 0; attempt < 3; attempt++) {
-			Attempt at = make_attempt(type, tsc, T, attempt);
-			if (!done && at.seq >= 0 && sinfo[at.seq].len + at.len - 1 > p.ndmax) {
-				rc = -1; done = true; // window larger than trxb200_detect_config() promised: -SIGERR_BOUNDS
+			float t = (float)idx;
+			bool hit = !((t < 3.0f) || (t > (float)(len - 3)));
+			if (hit) {
+				// computePeakRatio (sps = 1)
+				int num = 0;
+				float avg = 0.0f;
+				for (int i = 2; i <= 5; i++) {
+					if (idx - i >= 0) { avg = fa(avg, norm2(Cl[(idx - i) * kRowPitch])); num++; }
+					if (idx + i < len) { avg = fa(avg, norm2(Cl[(idx + i) * kRowPitch])); num++; }
+				}
+				float ratio = 0.0f;
+				if (num >= 5) {
+					const float rms = (float)((double)sqrtf(avg / (float)num) + 0.00001);
+					ratio = sqrtf(norm2(pk)) / rms;
+				}
+				if (fabsf(ratio - p.thresh) < 1e-5f) flags |= 1u;
+				if (ratio < p.thresh) hit = false;
 			}
-			const bool need = !done && at.seq >= 0;
-			const unsigned mask = __ballot_sync(0xffffffffu, need);
-			if (!mask)
-				break;
-			const float2 *tile_x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)tile * 32 * p.stride;
-
-			// ---- phase A: kGroup bursts at a time, work items flattened over (burst, output) ----
-			unsigned m = mask;
-			while (m) {
-				// lanes 0..kGroup-1 publish the parameters of the next bursts of the mask
-				int ng = 0, ndpad = 0, lenpad = 0;
-				__syncwarp();
-#pragma unroll
-				for (int g = 0; g < kGroup; g++) {
-					if (m) {
-						const int lb = __ffs(m) - 1;
-						m &= m - 1;
-						const int seq = __shfl_sync(0xffffffffu, at.seq, lb);
-						const int start = __shfl_sync(0xffffffffu, at.start, lb);
-						const int len = __shfl_sync(0xffffffffu, at.len, lb);
-						const int hl = sinfo[seq].len;
-						if (lane == 0) {
-							GroupSlot gs;
-							gs.lb = lb; gs.seq_off = sinfo[seq].off; gs.hlen = hl; gs.start = start; gs.len = len;
-							gs.pad0 = gs.pad1 = gs.pad2 = 0;
-							slot[g] = gs;
-						}
-						ndpad = max(ndpad, hl + len - 1);
-						lenpad = max(lenpad, len);
-						ng = g + 1;
-					}
-				}
-				__syncwarp();
-				// decimation of the samples the correlators need (+ their powers for computeCI)
-				for (int it = lane; it < ng * ndpad; it += 32) {
-					const int g = (it >= ndpad) + (it >= 2 * ndpad) + (it >= 3 * ndpad);
-					const int j = it - g * ndpad;
-					const GroupSlot gs = slot[g];
-					if (j < gs.hlen + gs.len - 1) {
-						const int d = gs.start - (gs.hlen - 1) + j;
-						float2 v = make_float2(0.0f, 0.0f);
-						if (d >= 0 && d < 156)
-							v = decimate_one(tile_x + (size_t)gs.lb * p.stride, d);
-						dec[g * p.ndmax + j] = v;
-						pwr[j * 32 + gs.lb] = norm2(v);
-					}
-				}
-				__syncwarp();
-				// correlation
-				for (int it = lane; it < ng * lenpad; it += 32) {
-					const int g = (it >= lenpad) + (it >= 2 * lenpad) + (it >= 3 * lenpad);
-					const int i = it - g * lenpad;
-					const GroupSlot gs = slot[g];
-					if (i < gs.len)
-						corr[i * 32 + gs.lb] = correlate_one(dec + g * p.ndmax + i, sseq + gs.seq_off, gs.hlen);
-				}
-			}
-			__syncwarp();
-
-			// ---- phase C ----
-			if (need) {
-				const int len = at.len;
-				const SeqInfo si = sinfo[at.seq];
-				// fastPeakDetect
-				float mx = 0.0f;
-				int idx = -1;
-				float2 pk = make_float2(0.0f, 0.0f);
-				for (int i = 0; i < len; i++) {
-					const float2 v = corr[i * 32 + lane];
-					const float pwv = norm2(v);
-					if (pwv > mx) { mx = pwv; idx = i; pk = v; }
-				}
-				float t = (float)idx;
-				bool hit = !((t < 3.0f) || (t > (float)(len - 3)));
-				if (hit) {
-					// computePeakRatio (sps = 1)
-					int num = 0;
-					float avg = 0.0f;
-					for (int i = 2; i <= 5; i++) {
-						if (idx - i >= 0) { avg = fa(avg, norm2(corr[(idx - i) * 32 + lane])); num++; }
-						if (idx + i < len) { avg = fa(avg, norm2(corr[(idx + i) * 32 + lane])); num++; }
-					}
-					float ratio = 0.0f;
-					if (num >= 5) {
-						const float rms = (float)((double)sqrtf(avg / (float)num) + 0.00001);
-						ratio = sqrtf(norm2(pk)) / rms;
-					}
-					if (fabsf(ratio - p.thresh) < 1e-5f) flags |= 1u;
-					if (ratio < p.thresh) hit = false;
-				}
-				if (hit) {
-					// peakDetect: early/late bisection
-					float early = t - 1.0f, late = t + 1.0f, incr = 0.5f;
+			if (hit) {
+				Cl[(len - 1) * kRowPitch] = make_float2(0.0f, 0.0f);
+				// peakDetect: early/late bisection; the late point is always early + 2 (:1172), i.e. both sit on
+				// the same 1/512 grid position and share their 21 weights
+				float early = t - 1.0f, incr = 0.5f;
 #pragma unroll 1
-					for (int it = 0; it < 9; it++) {
-						float2 e, l;
-						interp_pair(corr, lane, len, early, W, e, l); // late == early + 2 throughout (:1172)
-						const float ne = norm2(e), nl = norm2(l);
-						if (near_tie(ne, nl)) flags |= 2u;
-						if (ne < nl) early += incr;
-						else if (ne > nl) early -= incr;
-						else break;
-						incr *= 0.5f;
-						late = early + 2.0f;
+				for (int it = 0; it < 9; it++) {
+					const int m = (int)floorf(early);
+					const int F = (int)((early - (float)m) * 512.0f);
+					const float2 *cp = Cl + (m - 10) * kRowPitch;
+					const float *qF = stab + F, *pF = stab - F;
+					float2 e = make_float2(0.0f, 0.0f), l = make_float2(0.0f, 0.0f);
+					float2 v0 = cp[0], v1 = cp[kRowPitch];
+#pragma unroll
+					for (int d = 0; d < 21; d++) {
+						const float w = (d <= 10) ? qF[512 * (10 - d)] : pF[512 * (d - 10)];
+						const float2 v2 = cp[(d + 2) * kRowPitch];
+						e = add2(e, mul2(v0, bc2(w), NZ));
+						l = add2(l, mul2(v2, bc2(w), NZ));
+						v0 = v1;
+						v1 = v2;
 					}
-					t = early + 1.0f;
-					const float2 xc = interp_point(corr, lane, len, t, W);
-					// computeCI
-					const int N = si.len;
-					const int rt = (int)roundf(t);
-					const int ps = at.start + 1 - N + rt;
-					if (ps < 0 || ps + N > 156 || rt < 0 || rt >= len) {
-						ci = 0.0f;
-					} else {
-						// S = mean |burst[ps..ps+N)|^2, sequential (:1622-1626); pwr index j = dec index - d0 = rt + k
-						float S = 0.0f;
-						for (int k = 0; k < N; k++)
-							S = fa(S, pwr[(rt + k) * 32 + lane]);
-						S = S / (float)N;
-						const float C = norm2(xc) / si.ci_den;
-						ci = fm(3.0103f, log2f(C / fs(S, C)));
-					}
-					amp = cmul_exact(xc, make_float2(si.inv_gr, si.inv_gi));
-					toa = fs(fs(t, si.toa), (float)at.head);
-					rc = at.rc_hit;
-					if (type == 2 || type == 3) tsc_out = attempt;
-					done = true;
+					const float ne = norm2(e), nl = norm2(l);
+					if (near_tie(ne, nl)) flags |= 2u;
+					if (ne < nl) early += incr;
+					else if (ne > nl) early -= incr;
+					else break;
+					incr *= 0.5f;
 				}
+				t = early + 1.0f;
+				float2 xc = make_float2(0.0f, 0.0f);
+				{
+					const int m = (int)floorf(t);
+					const int F = (int)((t - (float)m) * 512.0f);
+					const float2 *cp = Cl + (m - 10) * kRowPitch;
+					const float *qF = stab + F, *pF = stab - F;
+#pragma unroll
+					for (int d = 0; d < 21; d++) {
+						const float w = (d <= 10) ? qF[512 * (10 - d)] : pF[512 * (d - 10)];
+						xc = add2(xc, mul2(cp[d * kRowPitch], bc2(w), NZ));
+					}
+				}
+				// computeCI
+				const int N = si.len;
+				const int rt = (int)roundf(t);
+				const int ps = at.start + 1 - N + rt;
+				if (ps < 0 || ps + N > 156 || rt < 0 || rt >= len) {
+					ci = 0.0f;
+				} else {
+					// S = mean |burst[ps..ps+N)|^2, sequential (:1622-1626); pwr index j = dec index - d0 = rt + k
+					const float *pw = p.pwr + (size_t)b * p.ndmax + rt;
+					float S = 0.0f;
+#pragma unroll 8
+					for (int k = 0; k < N; k++)
+						S = fa(S, __ldg(&pw[k]));
+					S = S / (float)N;
+					const float Cn = norm2(xc) / si.ci_den;
+					ci = fm(3.0103f, log2f(Cn / fs(S, Cn)));
+				}
+				amp = cmul_exact(xc, make_float2(si.inv_gr, si.inv_gi));
+				toa = fs(fs(t, si.toa), (float)at.head);
+				rc = at.rc_hit;
+				tsc_out = (type == 2 || type == 3) ? p.round : ((type == 1 || type == 5) ? tsc : 0);
+				write_all = true;
 			}
+		}
+		if (valid && p.last_round && rc == 0 && type_known(type)) {
+			// a further attempt exists but no round was scheduled for it (trxb200_detect_config): never silently skipped
+			Attempt nx = make_attempt(type, tsc, T, p.round + 1);
+			if (nx.seq >= 0 && !((type == 1 || type == 5) && tsc > 7) && T <= p.max_toa_bound) { rc = -1; write_all = true; }
 		}
 
 		if (valid) {
-			if (rc == 0 && clip) rc = -2; // -SIGERR_CLIP only when nothing was detected (:1764)
-			p.rc[b] = rc;
-			reinterpret_cast<float2 *>(p.amp)[b] = amp;
-			p.toa[b] = toa;
-			p.ci[b] = ci;
-			p.tsc_out[b] = (uint8_t)tsc_out;
-			if (p.flags) p.flags[b] = (uint8_t)flags;
+			if (write_all) {
+				p.rc[b] = rc;
+				reinterpret_cast<float2 *>(p.amp)[b] = amp;
+				p.toa[b] = toa;
+				p.ci[b] = ci;
+				p.tsc_out[b] = (uint8_t)tsc_out;
+			}
+			if (p.flags) {
+				if (p.round == 0) p.flags[b] = (uint8_t)flags;
+				else if (flags) p.flags[b] |= (uint8_t)flags;
+			}
+		}
+	}
+}
+
+// maxAmplitude (sigProcLib.cpp:1711-1722) for the bursts detection left at rc == 0: -SIGERR_CLIP is only
+// reported when nothing was detected (:1764).  One warp per burst.
+__global__ void __launch_bounds__(256)
+clip_kernel(const float *bursts, int stride, int n, int32_t *rc, uint8_t *flags)
+{
+	const int lane = threadIdx.x & 31;
+	const int wpb = blockDim.x >> 5;
+	for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n; b += gridDim.x * wpb) {
+		if (rc[b] != 0) continue;
+		const float2 *x = reinterpret_cast<const float2 *>(bursts) + (size_t)b * stride;
+		float mx = 0.0f;
+		for (int i = lane; i < 625; i += 32) {
+			const float2 v = __ldg(&x[i]);
+			mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1)
+			mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+		if (lane == 0 && mx > kClipThresh) {
+			rc[b] = -2;
+			if (flags) flags[b] |= 4;
 		}
 	}
 }

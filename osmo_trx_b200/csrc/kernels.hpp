@@ -6,19 +6,36 @@
 
 namespace trxb200 {
 
-struct DetectParams {
+// detection = rounds of (corr_kernel, peak_kernel); all pointers are already offset to the chunk
+struct CorrParams {
 	const float *bursts; // complex[n][stride]
 	int stride, n;
 	const uint8_t *type, *tsc;
 	const uint16_t *max_toa;
+	const int32_t *rc; // state left by earlier rounds (read when round > 0)
+	int round;	   // attempt index (EDGE -> TSC fall-through, EXT_RACH sequences)
+	int max_toa_bound;
+	int lmax, ndmax; // row lengths of the intermediates: max correlation length / decimated window
+	float2 *corr;	 // [n][lmax]
+	float *pwr;	 // [n][ndmax] |decimated sample|^2 (computeCI)
+	float negzero;	 // -0.0f at run time (see mul2 in detect.cu)
+};
+
+struct PeakParams {
+	int n;
+	const uint8_t *type, *tsc;
+	const uint16_t *max_toa;
+	int round, last_round;
 	int max_toa_bound;
 	float thresh;
+	int lmax, ndmax;
+	const float2 *corr;
+	const float *pwr;
+	const float *sinc512; // [5632] table-sinc on the 1/512 TOA grid
 	int32_t *rc;
 	float *amp, *toa, *ci;
 	uint8_t *tsc_out, *flags;
-	const float *interp_w;
-	int lmax, ndmax; // shared-memory sizing: max correlation length / decimated window
-	int scan_clip;	 // 1: run maxAmplitude over the whole burst here; 0: deferred to the demod kernel
+	float negzero;
 };
 
 struct DemodParams {

@@ -7,6 +7,8 @@
 //  * the sinc lookup floors an index computed in double from a float argument (sigProcLib.cpp:990-998);
 //  * FIR sums made during setup follow the SSE3 lane order of arch/x86/convolve_sse_3.c.
 #include "tables.hpp"
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -364,6 +366,25 @@ void build_host_tables(HostTables &t)
 			float diff = (float)d - (float)F / (float)kInterpGrid; // exact in float
 			t.interp_w[(size_t)F * kInterpSpan + (d + 10)] = sinc_lookup(t, kPiF * diff);
 		}
+
+	// the same weights indexed by the distance a = |512*(d-10) - F| on the 1/512 grid (the lookup depends on |x| only);
+	// every (F, d) pair must land on a consistent entry
+	t.sinc512.assign((size_t)11 * kInterpGrid, 0.0f);
+	{
+		std::vector<char> seen(t.sinc512.size(), 0);
+		for (int F = 0; F < kInterpGrid; F++)
+			for (int d = 0; d <= 20; d++) {
+				int a = 512 * (d - 10) - F;
+				if (a < 0) a = -a;
+				const float w = t.interp_w[(size_t)F * kInterpSpan + d];
+				if (seen[a] && t.sinc512[a] != w) {
+					fprintf(stderr, "trxb200: sinc512 inconsistency at F=%d d=%d\n", F, d);
+					abort();
+				}
+				seen[a] = 1;
+				t.sinc512[a] = w;
+			}
+	}
 
 	// composite (fractional delay (*) decimator) filters, truncated from below for the leading outputs
 	t.comp.assign((size_t)kCompFilts * 16 * kCompStride, 0.0f);

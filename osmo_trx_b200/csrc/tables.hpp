@@ -40,6 +40,7 @@ struct HostTables {
 	cf psk8[8];
 	// derived
 	std::vector<float> interp_w;  // [kInterpGrid][kInterpSpan]: sinc(pi_f*(d - F/512)), d = -10..10
+	std::vector<float> sinc512;   // [11*512]: sinc(pi_f * a/512) as interpolatePoint sees it, a = |512*(d-10) - F| (same values as interp_w)
 	std::vector<float> comp;      // [kCompFilts][16 kmin][kCompStride]: truncated composite filters
 	cf edge_derot[16];	      // (cosf, -sinf) of (i%16)*3pi/8  (sigProcLib.cpp:703-704)
 	cf edge_ideal[9];	      // (cos, sin)(k*pi/4), k=-4..4 as computeEdgeCI evaluates them (:2082-2083)
