@@ -439,7 +439,7 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 		CK(cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		configured = true;
 	}
-	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * 3);
+	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * 2);
 	if (grid < 1) grid = 1;
 	demod_kernel<<<grid, wpb * 32, smem, st>>>(p);
 	return post_launch(ctx, "demod_kernel");

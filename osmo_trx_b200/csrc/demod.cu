@@ -20,11 +20,15 @@
 //
 // Work mapping, one warp per burst (the kernel is bound by the shared-memory data pipe, so every
 // window sample is written to and read from shared memory exactly once):
-//   stage   16-byte global loads (two samples) -> 16-byte shared stores into a 680-sample window; 16-byte
-//           slot s lives at s ^ ((s/40)&1), which keeps both the staging stores and the per-lane reads
-//           below (lane stride 10 slots) bank-conflict free; the window origin is aligned to the 16-byte
-//           grid of the row, the residual shift e is folded into the tap index.  The next burst of the
-//           warp is prefetched into L2 meanwhile.
+//   stage   TMA bulk copies (cp.async.bulk global -> shared, completion on a per-warp mbarrier) bring the
+//           burst into a 680-sample window, double buffered: the copies of the warp's NEXT burst are in
+//           flight while the current one is filtered, so no warp ever waits on HBM latency and the
+//           staging costs neither registers nor load/store-pipe wavefronts.  The window is 9 blocks of
+//           40 16-byte slots at a pitch of 41 slots (one bulk copy per block, issued by lanes 0..8),
+//           which keeps the per-lane 16-byte reads below (lane stride 10 slots) bank-conflict free.  The
+//           window origin is aligned to the 16-byte grid of the row, the residual shift e is folded into
+//           the tap index; slots outside the burst are zero-filled, the one sample pair straddling an end
+//           of the burst is patched with an ordinary 8-byte load.
 //   FIR     transposed form: lane l owns window samples 20l..20l+19 (10 LDS.128) and scatters each into
 //           the 13 outputs 5l-8..5l+4 it can reach (180 FFMA2 with the tap as scalar-broadcast operand,
 //           taps fetched warp-uniformly from __constant__ comp0[f][e]); the 8 partial sums that belong to
@@ -40,8 +44,11 @@ namespace trxb200 {
 namespace {
 
 constexpr int kPairs = 340;		 // 16-byte sample pairs (slots) in the window: samples 0 .. 679
+constexpr int kBlockSlots = 40;		 // slots per bulk-copy block (= 4 lanes' shares)
+constexpr int kBlockPitch = 41;		 // block pitch in slots (one pad slot: conflict-free lane reads)
+constexpr int kBufSlots = 9 * kBlockPitch; // one window buffer
 constexpr int kScratchFloats = 2 * 164;	 // output staging + Y scratch (GMSK) / complex decimated samples (EDGE)
-constexpr int kDemodWarpFloats = 4 * kPairs + kScratchFloats;
+constexpr int kDemodWarpFloats = 2 * 4 * kBufSlots + kScratchFloats + 4; // 2 window buffers + scratch + 2 mbarriers
 constexpr int kYOff = 192;		 // float offset of the Y scratch (float2[32]) inside the scratch area
 
 // ---- packed FP32 (sm_100 FFMA2): both halves are IEEE fma.rn ----
@@ -65,7 +72,39 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b)
 }
 
 // physical 16-byte slot of logical slot s (window samples 2s, 2s+1)
-__device__ __forceinline__ int slot_phys(int s) { return s ^ ((s / 40) & 1); }
+__device__ __forceinline__ int slot_phys(int s) { return s + s / kBlockSlots; }
+
+// ---- mbarrier / TMA bulk-copy primitives (shared-window 32-bit addresses) ----
+__device__ __forceinline__ unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+	unsigned done = 0;
+	unsigned spins = 0;
+	while (!done) {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+			     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			     "selp.u32 %0, 1, 0, p;\n\t}"
+			     : "=r"(done)
+			     : "r"(bar), "r"(parity)
+			     : "memory");
+		if (!done && ++spins > (1u << 24)) __trap(); // a lost copy must fail loudly, not hang the device
+	}
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+		     "r"(bytes), "r"(bar)
+		     : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ float2 win_get(const float2 *U, int w)
 {
@@ -178,27 +217,85 @@ __device__ __noinline__ void demod_edge_burst(const DemodParams &p, int b, const
 		p.ci[b] = fm(3.0103f, log2f(140.0f / err));
 }
 
-__device__ __forceinline__ void prefetch_row_l2(const float2 *x, int lane)
+} // namespace
+
+// window geometry of a detected burst (demodCommon / delayVector :1046-1060)
+struct BurstGeom {
+	int whole, f, e, off2;
+};
+__device__ __forceinline__ BurstGeom burst_geom(float toa, unsigned row_par)
 {
-	// 625 samples = 5000 B: one bulk L2 prefetch of the 16-byte aligned span inside the row
-	if (lane == 0) {
-		const uintptr_t a = (reinterpret_cast<uintptr_t>(x) + 15u) & ~(uintptr_t)15u;
-		asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(4976));
+	BurstGeom g;
+	const float delay = fm(-toa, 4.0f);
+	g.whole = (int)floorf(delay);
+	const float frac = fs(delay, (float)g.whole);
+	g.f = 64;
+	if ((double)fabsf(frac) > 1e-2) {
+		g.f = (int)floorf(fm(frac, 64.0f));
+		g.f = min(max(g.f, 0), 63);
+	}
+	const int off = -24 - g.whole;			  // window sample 0 <-> burst sample `off` (before alignment)
+	g.e = (int)(((unsigned)off - row_par) & 1u);	  // residual shift so that off2 has the row's 16B parity
+	g.off2 = off - g.e;				  // window sample w <-> burst sample w + off2; output i tap t reads w = 4i+t+e
+	return g;
+}
+
+// Stage burst row x into window buffer U (async): zero-fill the slots outside the burst, launch one bulk copy
+// per 40-slot block.  Called by the whole warp; bar is the buffer's mbarrier.  The one sample pair that straddles
+// an end of the burst cannot be bulk-copied (8-byte aligned only): lane 31 fetches it here and returns it in
+// (patch, patch_idx); the caller stores it right before the buffer is consumed, so its latency is hidden too.
+__device__ __forceinline__ void stage_async(const float2 *x, int off2, float2 *U, unsigned bar, int lane, float2 &patch,
+					    int &patch_idx)
+{
+	// slot s holds burst samples off2 + 2s, off2 + 2s + 1; fully inside the burst for s_first <= s <= s_last
+	const int s_first = off2 >= 0 ? 0 : ((-off2 + 1) >> 1);
+	const int s_last = min(kPairs - 1, (623 - off2) >> 1); // floor; negative when the window lies beyond the burst
+	const int count = max(0, s_last - s_first + 1);
+	patch_idx = -1;
+	if (lane == 31) {
+		// the straddling slot: samples (-1, 0) or (624, 625), one per burst depending on the row parity
+		if (((-1 - off2) & 1) == 0) {
+			const int sl = (-1 - off2) >> 1;
+			if (sl >= 0 && sl < kPairs) { patch = __ldg(&x[0]); patch_idx = 2 * slot_phys(sl) + 1; }
+		} else {
+			const int sl = (624 - off2) >> 1;
+			if (sl >= 0 && sl < kPairs) { patch = __ldg(&x[624]); patch_idx = 2 * slot_phys(sl); }
+		}
+	}
+	fence_proxy_async(); // this buffer's earlier generic-proxy accesses are ordered before the async writes below
+	__syncwarp();
+	float4 *U4 = reinterpret_cast<float4 *>(U);
+	const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	const int nz_hi = count > 0 ? kPairs - 1 - s_last : kPairs; // zero slots above the burst (all of them if no overlap)
+	const int nz_lo = count > 0 ? s_first : 0;
+	if (nz_lo + nz_hi <= 32) {
+		// the usual case: one predicated store per lane covers both ends
+		const int sidx = lane < nz_lo ? lane : kPairs - nz_hi + (lane - nz_lo);
+		if (lane < nz_lo + nz_hi) U4[slot_phys(sidx)] = z;
+	} else {
+		for (int sidx = lane; sidx < nz_lo; sidx += 32) U4[slot_phys(sidx)] = z;
+		for (int sidx = kPairs - nz_hi + lane; sidx < kPairs; sidx += 32) U4[slot_phys(sidx)] = z;
+	}
+	if (lane == 0) mbar_arrive_expect_tx(bar, (unsigned)count * 16u);
+	__syncwarp();
+	if (lane < 9 && count > 0) {
+		const int lo = max(kBlockSlots * lane, s_first), hi = min(kBlockSlots * lane + kBlockSlots - 1, s_last);
+		if (lo <= hi)
+			bulk_g2s(smem_u32(U4 + slot_phys(lo)), x + off2 + 2 * lo, (unsigned)(hi - lo + 1) * 16u, bar);
 	}
 }
 
-} // namespace
-
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 demod_kernel(DemodParams p)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int wpb = blockDim.x >> 5;
-	float2 *U = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * (kDemodWarpFloats / 2);
-	float *ostage = reinterpret_cast<float *>(U + 2 * kPairs);
+	float2 *Ubase = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * (kDemodWarpFloats / 2);
+	float *ostage = reinterpret_cast<float *>(Ubase + 2 * 2 * kBufSlots);
 	float2 *decs = reinterpret_cast<float2 *>(ostage);
 	float2 *yv = reinterpret_cast<float2 *>(ostage + kYOff);
+	const unsigned bar0 = smem_u32(ostage + kScratchFloats); // two 8-byte mbarriers, one per window buffer
 	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
 	const int step = gridDim.x * wpb;
 	// decimator taps this lane applies in the leading-output correction (k = 4*(lane&3) + kk)
@@ -206,28 +303,64 @@ demod_kernel(DemodParams p)
 #pragma unroll
 	for (int kk = 0; kk < 4; kk++) gk[kk] = p.dnsamp_g[4 * (lane & 3) + kk];
 
-	int b = blockIdx.x * wpb + warp;
-	// per-burst scalars are fetched one burst ahead
-	int rc_n = 0;
-	float2 amp_n = make_float2(1.0f, 0.0f);
-	float toa_n = 0.0f;
-	if (b < p.n) {
-		rc_n = p.rc[b];
-		amp_n = reinterpret_cast<const float2 *>(p.amp)[b];
-		toa_n = p.toa[b];
+	if (lane == 0) {
+		mbar_init(bar0, 1);
+		mbar_init(bar0 + 8, 1);
 	}
-	for (; b < p.n; b += step) {
-		const int rc = rc_n;
-		const float2 amp = amp_n;
-		const float toa = toa_n;
+	fence_proxy_async();
+	__syncwarp();
+
+	int b = blockIdx.x * wpb + warp;
+	// per-burst scalars run two bursts ahead of the filter, the staging copies one burst ahead
+	int rc0 = 0, rc1 = 0;
+	float2 amp0 = make_float2(1.0f, 0.0f), amp1 = amp0;
+	float toa0 = 0.0f, toa1 = 0.0f;
+	if (b < p.n) {
+		rc0 = p.rc[b];
+		amp0 = reinterpret_cast<const float2 *>(p.amp)[b];
+		toa0 = p.toa[b];
+	}
+	if (b + step < p.n) {
+		rc1 = p.rc[b + step];
+		amp1 = reinterpret_cast<const float2 *>(p.amp)[b + step];
+		toa1 = p.toa[b + step];
+	}
+	unsigned phase = 0; // bit k: parity the next wait on buffer k uses
+	int cur = 0;
+	float2 patch_n = make_float2(0.0f, 0.0f); // straddling sample of the burst being staged (lane 31)
+	int patch_idx_n = -1;
+	if (b < p.n && rc0 > 0) {
+		const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
+		const BurstGeom g0 = burst_geom(toa0, row_par);
+		stage_async(reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride, g0.off2, Ubase, bar0, lane, patch_n,
+			    patch_idx_n);
+	}
+	for (; b < p.n; b += step, cur ^= 1) {
+		const int rc = rc0;
+		const float2 amp = amp0;
+		const float toa = toa0;
 		const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
-		const int bn = b + step;
-		if (bn < p.n) {
-			rc_n = p.rc[bn];
-			amp_n = reinterpret_cast<const float2 *>(p.amp)[bn];
-			toa_n = p.toa[bn];
-			if (rc_n > 0)
-				prefetch_row_l2(reinterpret_cast<const float2 *>(p.bursts) + (size_t)bn * p.stride, lane);
+		float2 *U = Ubase + (size_t)cur * 2 * kBufSlots;
+		const float2 patch = patch_n;
+		const int patch_idx = patch_idx_n;
+		patch_idx_n = -1;
+		// next burst: start its copies into the other buffer; burst after next: fetch its scalars
+		{
+			const int bn = b + step;
+			rc0 = rc1; amp0 = amp1; toa0 = toa1;
+			if (bn < p.n && rc0 > 0) {
+				const unsigned rp = (base_par + (unsigned)(((size_t)bn * (size_t)p.stride) & 1u)) & 1u;
+				const BurstGeom gn = burst_geom(toa0, rp);
+				stage_async(reinterpret_cast<const float2 *>(p.bursts) + (size_t)bn * p.stride, gn.off2,
+					    Ubase + (size_t)(cur ^ 1) * 2 * kBufSlots, bar0 + 8 * (cur ^ 1), lane, patch_n, patch_idx_n);
+			}
+			const int bnn = bn + step;
+			rc1 = 0;
+			if (bnn < p.n) {
+				rc1 = p.rc[bnn];
+				amp1 = reinterpret_cast<const float2 *>(p.amp)[bnn];
+				toa1 = p.toa[bnn];
+			}
 		}
 
 		if (rc <= 0) {
@@ -249,60 +382,23 @@ demod_kernel(DemodParams p)
 			continue;
 		}
 
-		// ---- per-burst scalars (demodCommon / delayVector :1046-1060) ----
-		const float an = norm2(amp);
-		const float2 s = make_float2(amp.x / an, -amp.y / an); // (complex)1.0 / amp
-		const float delay = fm(-toa, 4.0f);
-		const int whole = (int)floorf(delay);
-		const float frac = fs(delay, (float)whole);
-		int f = 64;
-		if ((double)fabsf(frac) > 1e-2) {
-			f = (int)floorf(fm(frac, 64.0f));
-			f = min(max(f, 0), 63);
-		}
-		const int off = -24 - whole;		   // window sample 0 <-> burst sample `off` (before alignment)
+		// ---- per-burst scalars ----
+		const float ian = __frcp_rn(norm2(amp));
+		const float2 s = make_float2(amp.x * ian, -amp.y * ian); // (complex)1.0 / amp (soft bits carry a 1e-4 tolerance)
 		const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
-		const int e = (int)(((unsigned)off - row_par) & 1u); // residual shift so that off2 has the row's 16B parity
-		const int off2 = off - e;		   // window sample w <-> burst sample w + off2; output i tap t reads w = 4i+t+e
+		const BurstGeom bg = burst_geom(toa, row_par);
+		const int whole = bg.whole, f = bg.f, e = bg.e;
 		const bool edge = (rc == 5);
 
+		// ---- the burst's window: straddling sample, then wait for the bulk copies ----
+		if (patch_idx >= 0) U[patch_idx] = patch;
 		__syncwarp();
-		// ---- stage the raw burst into the window, zero outside the burst ----
-		// All 16-byte loads of the burst are issued before the first use (11 in flight per lane) so the warp
-		// pays the memory latency once per burst.  Slot s starts at burst sample p0 = off2 + 2s, 16-byte
-		// aligned by construction; the one slot that straddles an end of the burst is patched below.
-		{
-			float4 ld[11];
-#pragma unroll
-			for (int it = 0; it < 11; it++) {
-				const int sl = lane + 32 * it;
-				const int p0 = off2 + 2 * sl;
-				ld[it] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-				if ((it < 10 || sl < kPairs) && (unsigned)p0 <= 623u)
-					ld[it] = __ldg(reinterpret_cast<const float4 *>(x + p0));
-			}
-			float4 *U4 = reinterpret_cast<float4 *>(U);
-#pragma unroll
-			for (int it = 0; it < 11; it++) {
-				const int sl = lane + 32 * it;
-				if (it < 10 || sl < kPairs)
-					U4[slot_phys(sl)] = ld[it];
-			}
-			// the straddling slot: samples (-1, 0) or (624, 625), one per burst depending on the row parity
-			if (lane == 0) {
-				if (((-1 - off2) & 1) == 0) {
-					const int sl = (-1 - off2) >> 1;
-					if (sl >= 0 && sl < kPairs) U[2 * slot_phys(sl) + 1] = __ldg(&x[0]);
-				} else {
-					const int sl = (624 - off2) >> 1;
-					if (sl >= 0 && sl < kPairs) U[2 * slot_phys(sl)] = __ldg(&x[624]);
-				}
-			}
-		}
-		__syncwarp();
+		mbar_wait(bar0 + 8 * cur, (phase >> cur) & 1u);
+		phase ^= 1u << cur;
 
 		if (edge) {
 			demod_edge_burst(p, b, U, decs, s, e, f, whole, lane);
+			__syncwarp();
 			continue;
 		}
 
@@ -314,8 +410,7 @@ demod_kernel(DemodParams p)
 			float2 acc[13];
 #pragma unroll
 			for (int m = 0; m < 13; m++) acc[m] = make_float2(0.0f, 0.0f);
-			const float4 *U4 = reinterpret_cast<const float4 *>(U);
-			const int sw = (lane >> 2) & 1;
+			const float4 *xc4 = reinterpret_cast<const float4 *>(U) + 10 * lane + (lane >> 2);
 			const float *__restrict__ ce = c_tab.comp0[f][e];
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
@@ -323,7 +418,7 @@ demod_kernel(DemodParams p)
 				float2 xa[5], xb[5];
 #pragma unroll
 				for (int k = 0; k < 5; k++) {
-					const float4 v = U4[(10 * lane + 2 * k + h) ^ sw];
+					const float4 v = xc4[2 * k + h];
 					xa[k] = make_float2(v.x, v.y);
 					xb[k] = make_float2(v.z, v.w);
 				}
@@ -433,6 +528,7 @@ demod_kernel(DemodParams p)
 			for (int j = lane; j < nout; j += 32)
 				orow[j] = ostage[j];
 		}
+		__syncwarp();
 	}
 }
 
