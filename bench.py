@@ -31,8 +31,8 @@ ALG_BYTES = {"nb": 5000 + 592 + 24, "rach": 5000 + 592 + 24, "edge": 5000 + 1776
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="nb", choices=["nb", "rach", "edge"])
     ap.add_argument("--bursts", type=int, default=1 << 20, help="bursts per GPU per step")
@@ -53,53 +53,59 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 10 ms from a thread
+    (nvidia-smi -lms cannot sample a region that lasts a few hundred ms); falls back to one nvidia-smi query."""
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons, self.stop_flag, self.t, self.h, self.nv = [], set(), False, None, None, None
+        self.sm_max = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nv = None
+            return
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
+        if self.nv is None:
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                q = "clocks.sm,clocks.max.sm"
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                return {"sm_mhz": float(o[0]), "sm_max_mhz": float(o[1]), "reasons": [], "samples": 1,
+                        "how": "nvidia-smi after the timed region (NVML unavailable)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm), "how": "NVML polled every 10 ms during the timed region"}
 
 
 def make_workload(trx, kind, n, seed, device):
@@ -306,48 +312,41 @@ def main():
     ms_per_step = ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
 
-    # ---- per-kernel timing for the roofline (separate launches, CUDA events on the launch stream) ----
-    def time_fn(fn, reps=5):
-        for _ in range(2):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
-    import ctypes as C
-    P = osmo_trx_b200._ptr
-    lib = trx.lib
-
-    def det_only():
-        trx.use_current_stream()
-        # fused-mode detect (clip scan deferred) is not exposed separately; time the standalone detect_batch
-        lib.trxb200_detect_batch(trx.h, P(rx), C.c_int(625), C.c_int(n), P(typ), P(tsc), P(max_toa), C.c_int(bound),
-                                 C.c_float(4.0), P(out["rc"]), P(out["amp"]), P(out["toa"]), P(out["tsc"]), P(out["ci"]),
-                                 P(out["flags"]))
-
-    def dem_only():
-        trx.use_current_stream()
-        lib.trxb200_demod_batch(trx.h, P(rx), C.c_int(625), C.c_int(n), P(out["rc"]), P(out["amp"]), P(out["toa"]),
-                                P(out["ci"]), P(out["soft"]), C.c_int(148), C.c_int(148))
-
-    step()
-    torch.cuda.synchronize()
-    ms_det, ms_dem = time_fn(det_only), time_fn(dem_only)
-    step()
-    torch.cuda.synchronize()
+    # ---- per-kernel device time for the roofline: the same K steps once more with CUDA events around every
+    #      kernel on the launching stream (trxb200_profile_begin/end); the headline value above is un-instrumented ----
+    trx.profile_begin()
+    for _ in range(args.steps):
+        step()
+    prof = trx.profile_end()
     peak, peak_src = peaks()
+    kern_ms = {k: v[0] / v[1] for k, v in prof.items()}              # average launch duration
+    kern_step_ms = {k: v[0] / args.steps for k, v in prof.items()}     # per step (corr/peak run once per chunk)
+    dom = max(kern_step_ms, key=kern_step_ms.get)
+    # algorithmic bytes per burst of each kernel: demod reads the burst once and writes the
+    # soft row (+ per-burst scalars); corr reads the correlator window and writes the intermediates; the step
+    # figure is SURVEY.md 8(d)'s 5,616 B per normal burst (6,800 EDGE)
+    soft_b = 444 * 4 if args.workload == "edge" else 148 * 4
+    alg_kernel = {"demod_kernel": 5000 + soft_b + 16, "corr_kernel": (4 * (15 + 16 + bound) + 12) * 8 + (16 + bound) * 8 + (31 + bound) * 4,
+                  "peak_kernel": (16 + bound) * 8 + 16 * 4 + 24}
+    launches_per_step = {k: v[1] / args.steps for k, v in prof.items()}
     alg = ALG_BYTES[args.workload]
-    dom, dom_ms = ("demod_kernel", ms_dem) if ms_dem >= ms_det else ("detect_kernel", ms_det)
-    achieved = alg * n / (dom_ms * 1e-3) / 1e9
+    dom_alg = alg_kernel.get(dom, alg)
+    achieved = dom_alg * n / (kern_step_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath)).get(args.workload, {}).get(dom)
+            if tj:
+                traffic = tj["dram_bytes_per_burst"] * n / launches_per_step[dom]
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_burst": alg, "kernel_ms": {"detect_kernel(standalone,+clip scan)": ms_det,
-                                                                  "demod_kernel": ms_dem},
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_burst": dom_alg, "bursts_per_launch": n / launches_per_step[dom],
+                "launch_ms": kern_ms[dom], "kernel_ms_per_step": kern_step_ms, "kernel_launches_per_step": launches_per_step,
+                "kernel_share_of_step": {k: v / sum(kern_step_ms.values()) for k, v in kern_step_ms.items()},
+                "step_algorithmic_bytes_per_burst": alg,
                 "step_achieved": alg * n / (ms_per_step * 1e-3) / 1e9,
                 "step_frac": alg * n / (ms_per_step * 1e-3) / 1e9 / peak}
 

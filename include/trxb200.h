@@ -76,6 +76,11 @@ int trxb200_device(trxb200_ctx *ctx);
 int trxb200_sm_count(trxb200_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t trxb200_launch_count(trxb200_ctx *ctx);
+/* per-kernel device time of the detect / demod kernels launched between begin and end, measured with CUDA
+ * events on the launching stream (used by bench.py for the roofline line; adds event overhead, so it is
+ * not left on during throughput runs).  end() synchronises and writes "name:total_ms:launches;..." */
+int trxb200_profile_begin(trxb200_ctx *ctx);
+int trxb200_profile_end(trxb200_ctx *ctx, char *out, int cap);
 /* host copy of a setup table for bit-exact checks against sigProcLib.cpp:52-135 statics.
  * names: sinc rot4 rrot4 rot1 rrot1 delay pulse4_c0 pulse4_c1 pulse4_c0inv pulse1_c0 dnsamp psk8
  *        midamble edge_midamble rach sch dummy (+ "_meta" = gain.re, gain.im, toa)

@@ -109,6 +109,22 @@ class Trx:
             raise KeyError(name)
         return buf[:n].copy()
 
+    def profile_begin(self):
+        self._check(self.lib.trxb200_profile_begin(self.h), "profile_begin")
+
+    def profile_end(self):
+        """-> {kernel: (total_ms, launches)} for the detect/demod kernels launched since profile_begin()."""
+        buf = C.create_string_buffer(4096)
+        r = self.lib.trxb200_profile_end(self.h, buf, C.c_int(4096))
+        if r < 0:
+            self._check(r, "profile_end")
+        out = {}
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, ms, cnt = item.split(":")
+                out[name] = (float(ms), int(cnt))
+        return out
+
     def detect_config(self, max_seq_len=40, max_attempts=3):
         """max_seq_len 16: only TSC/EDGE/IDLE bursts will be submitted (smaller on-chip buffers); 40: any type.
         max_attempts: detection rounds per batch (1: TSC/RACH/IDLE only, 2: + EDGE, 3: + EXT_RACH)."""

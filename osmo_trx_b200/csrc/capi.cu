@@ -54,6 +54,10 @@ struct trxb200_ctx {
 	DetectScratch ws;     // used by the *_batch entry points (one stream at a time)
 	std::string err;
 	HostStage *stage = nullptr;
+	// optional per-kernel timing (trxb200_profile_begin/end): CUDA events around the detect/demod kernels
+	bool prof = false;
+	struct ProfRec { const char *name; cudaEvent_t a, b; };
+	std::vector<ProfRec> prof_recs;
 };
 
 struct HostStage {
@@ -97,6 +101,23 @@ int post_launch(trxb200_ctx *ctx, const char *name)
 	if (e != cudaSuccess)
 		return fail(ctx, TRXB200_ECUDA, name, e);
 	return TRXB200_OK;
+}
+
+// event pair around a kernel launch when profiling is on (events are recorded on the launching stream)
+void prof_pre(trxb200_ctx *ctx, cudaStream_t st)
+{
+	if (!ctx->prof) return;
+	trxb200_ctx::ProfRec r{ nullptr, nullptr, nullptr };
+	cudaEventCreate(&r.a);
+	cudaEventCreate(&r.b);
+	cudaEventRecord(r.a, st);
+	ctx->prof_recs.push_back(r);
+}
+void prof_post(trxb200_ctx *ctx, cudaStream_t st, const char *name)
+{
+	if (!ctx->prof || ctx->prof_recs.empty()) return;
+	ctx->prof_recs.back().name = name;
+	cudaEventRecord(ctx->prof_recs.back().b, st);
 }
 
 void fill_const_tables(const HostTables &t, ConstTables &c)
@@ -268,6 +289,45 @@ int trxb200_device(trxb200_ctx *ctx) { return ctx ? ctx->device : -1; }
 int trxb200_sm_count(trxb200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t trxb200_launch_count(trxb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int trxb200_profile_begin(trxb200_ctx *ctx)
+{
+	if (!ctx) return TRXB200_EINVAL;
+	for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+	ctx->prof_recs.clear();
+	ctx->prof = true;
+	return TRXB200_OK;
+}
+
+int trxb200_profile_end(trxb200_ctx *ctx, char *out, int cap)
+{
+	if (!ctx || !out || cap < 1) return TRXB200_EINVAL;
+	ctx->prof = false;
+	CK(cudaDeviceSynchronize());
+	struct Acc { const char *name; double ms; int count; };
+	std::vector<Acc> acc;
+	for (auto &r : ctx->prof_recs) {
+		float ms = 0.0f;
+		if (r.name && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+			bool found = false;
+			for (auto &a : acc)
+				if (!strcmp(a.name, r.name)) { a.ms += ms; a.count++; found = true; }
+			if (!found) acc.push_back(Acc{ r.name, ms, 1 });
+		}
+		cudaEventDestroy(r.a);
+		cudaEventDestroy(r.b);
+	}
+	ctx->prof_recs.clear();
+	std::string s;
+	for (auto &a : acc) {
+		char buf[160];
+		snprintf(buf, sizeof(buf), "%s%s:%.6f:%d", s.empty() ? "" : ";", a.name, a.ms, a.count);
+		s += buf;
+	}
+	if ((int)s.size() + 1 > cap) return TRXB200_EINVAL;
+	std::memcpy(out, s.c_str(), s.size() + 1);
+	return (int)acc.size();
+}
+
 int trxb200_detect_config(trxb200_ctx *ctx, int max_seq_len, int max_attempts)
 {
 	if (!ctx) return TRXB200_EINVAL;
@@ -403,7 +463,9 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			c.max_toa_bound = bound; c.lmax = lmax; c.ndmax = ndmax; c.corr = ws.corr; c.pwr = ws.pwr; c.negzero = -0.0f;
 			const int ngroups = (m + kGroup - 1) / kGroup;
 			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));
+			prof_pre(ctx, st);
 			corr_kernel<<<cgrid, cw * 32, csmem, st>>>(c);
+			prof_post(ctx, st, "corr_kernel");
 			int e = post_launch(ctx, "corr_kernel");
 			if (e) return e;
 			PeakParams q;
@@ -413,13 +475,17 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			q.tsc_out = tsc_out + lo; q.flags = flags ? flags + lo : nullptr;
 			const int ntiles = (m + 31) / 32;
 			const int pgrid = std::max(1, std::min((ntiles + pw - 1) / pw, ctx->sm_count * pbps));
+			prof_pre(ctx, st);
 			peak_kernel<<<pgrid, pw * 32, psmem, st>>>(q);
+			prof_post(ctx, st, "peak_kernel");
 			e = post_launch(ctx, "peak_kernel");
 			if (e) return e;
 		}
 	}
 	if (scan_clip) {
+		prof_pre(ctx, st);
 		clip_kernel<<<std::max(1, std::min((n + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(bursts, stride, n, rc, flags);
+		prof_post(ctx, st, "clip_kernel");
 		return post_launch(ctx, "clip_kernel");
 	}
 	return TRXB200_OK;
@@ -441,7 +507,9 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 	}
 	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * 2);
 	if (grid < 1) grid = 1;
+	prof_pre(ctx, st);
 	demod_kernel<<<grid, wpb * 32, smem, st>>>(p);
+	prof_post(ctx, st, "demod_kernel");
 	return post_launch(ctx, "demod_kernel");
 }
 
