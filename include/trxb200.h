@@ -76,6 +76,14 @@ int trxb200_device(trxb200_ctx *ctx);
 int trxb200_sm_count(trxb200_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t trxb200_launch_count(trxb200_ctx *ctx);
+/* Device memory helpers so that a binding needs no CUDA runtime of its own (cgo / JNI / ctypes / the C++ mirror in
+ * osmo_trx_b200/host).  Copies are ordered on the context's stream; copy_to_host also waits for the stream, i.e.
+ * for every kernel enqueued before it. */
+int trxb200_dev_alloc(trxb200_ctx *ctx, size_t bytes, void **out);
+int trxb200_dev_free(trxb200_ctx *ctx, void *p);
+int trxb200_copy_to_device(trxb200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int trxb200_copy_to_host(trxb200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int trxb200_memset_device(trxb200_ctx *ctx, void *dst, int value, size_t bytes);
 /* per-kernel device time of the detect / demod kernels launched between begin and end, measured with CUDA
  * events on the launching stream (used by bench.py for the roofline line; adds event overhead, so it is
  * not left on during throughput runs).  end() synchronises and writes "name:total_ms:launches;..." */

@@ -289,6 +289,42 @@ int trxb200_device(trxb200_ctx *ctx) { return ctx ? ctx->device : -1; }
 int trxb200_sm_count(trxb200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t trxb200_launch_count(trxb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+/* ---------------- device memory helpers for bindings that have no CUDA runtime of their own ---------------- */
+int trxb200_dev_alloc(trxb200_ctx *ctx, size_t bytes, void **out)
+{
+	if (!ctx || !out) return TRXB200_EINVAL;
+	*out = nullptr;
+	CK(cudaSetDevice(ctx->device));
+	cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+	if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? TRXB200_ENOMEM : TRXB200_ECUDA, "dev_alloc", e);
+	return TRXB200_OK;
+}
+int trxb200_dev_free(trxb200_ctx *ctx, void *p)
+{
+	if (!ctx) return TRXB200_EINVAL;
+	if (p) CK(cudaFree(p));
+	return TRXB200_OK;
+}
+int trxb200_copy_to_device(trxb200_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+	if (!ctx || (bytes && (!dst || !src))) return TRXB200_EINVAL;
+	if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	return TRXB200_OK;
+}
+int trxb200_copy_to_host(trxb200_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+	if (!ctx || (bytes && (!dst || !src))) return TRXB200_EINVAL;
+	if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return TRXB200_OK;
+}
+int trxb200_memset_device(trxb200_ctx *ctx, void *dst, int value, size_t bytes)
+{
+	if (!ctx || (bytes && !dst)) return TRXB200_EINVAL;
+	if (bytes) CK(cudaMemsetAsync(dst, value, bytes, ctx->stream));
+	return TRXB200_OK;
+}
+
 int trxb200_profile_begin(trxb200_ctx *ctx)
 {
 	if (!ctx) return TRXB200_EINVAL;
