@@ -23,12 +23,13 @@
 //   stage   TMA bulk copies (cp.async.bulk global -> shared, completion on a per-warp mbarrier) bring the
 //           burst into a 680-sample window, double buffered: the copies of the warp's NEXT burst are in
 //           flight while the current one is filtered, so no warp ever waits on HBM latency and the
-//           staging costs neither registers nor load/store-pipe wavefronts.  The window is 9 blocks of
-//           40 16-byte slots at a pitch of 41 slots (one bulk copy per block, issued by lanes 0..8),
-//           which keeps the per-lane 16-byte reads below (lane stride 10 slots) bank-conflict free.  The
-//           window origin is aligned to the 16-byte grid of the row, the residual shift e is folded into
-//           the tap index; slots outside the burst are zero-filled, the one sample pair straddling an end
-//           of the burst is patched with an ordinary 8-byte load.
+//           staging costs neither registers nor load/store-pipe wavefronts.  One bulk copy per burst
+//           (issued by lane 0) into a linear window of 340 16-byte slots; the per-lane 16-byte reads
+//           below (lane stride 10 slots) are 2-way bank conflicted, which the shared-memory pipe has room
+//           for, whereas a padded layout would need nine copies and a uniform-register loop to issue them.
+//           The window origin is aligned to the 16-byte grid of the row, the residual shift e is folded
+//           into the tap index; slots outside the burst are zero-filled, the one sample pair straddling
+//           an end of the burst is patched with an ordinary 8-byte load.
 //   FIR     transposed form: lane l owns window samples 20l..20l+19 (10 LDS.128) and scatters each into
 //           the 13 outputs 5l-8..5l+4 it can reach (180 FFMA2 with the tap as scalar-broadcast operand,
 //           taps fetched warp-uniformly from __constant__ comp0[f][e]); the 8 partial sums that belong to
@@ -44,9 +45,7 @@ namespace trxb200 {
 namespace {
 
 constexpr int kPairs = 340;		 // 16-byte sample pairs (slots) in the window: samples 0 .. 679
-constexpr int kBlockSlots = 40;		 // slots per bulk-copy block (= 4 lanes' shares)
-constexpr int kBlockPitch = 41;		 // block pitch in slots (one pad slot: conflict-free lane reads)
-constexpr int kBufSlots = 9 * kBlockPitch; // one window buffer
+constexpr int kBufSlots = kPairs;	 // one window buffer (linear)
 constexpr int kScratchFloats = 2 * 164;	 // output staging + Y scratch (GMSK) / complex decimated samples (EDGE)
 constexpr int kDemodWarpFloats = 2 * 4 * kBufSlots + kScratchFloats + 4; // 2 window buffers + scratch + 2 mbarriers
 constexpr int kYOff = 192;		 // float offset of the Y scratch (float2[32]) inside the scratch area
@@ -72,7 +71,7 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b)
 }
 
 // physical 16-byte slot of logical slot s (window samples 2s, 2s+1)
-__device__ __forceinline__ int slot_phys(int s) { return s + s / kBlockSlots; }
+__device__ __forceinline__ int slot_phys(int s) { return s; }
 
 // ---- mbarrier / TMA bulk-copy primitives (shared-window 32-bit addresses) ----
 __device__ __forceinline__ unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
@@ -240,8 +239,7 @@ __device__ __forceinline__ BurstGeom burst_geom(float toa, unsigned row_par)
 	return g;
 }
 
-// Stage burst row x into window buffer U (async): zero-fill the slots outside the burst, launch one bulk copy
-// per 40-slot block.  Called by the whole warp; bar is the buffer's mbarrier.  The one sample pair that straddles
+// Stage burst row x into window buffer U (async): zero-fill the slots outside the burst, launch the bulk copy.  Called by the whole warp; bar is the buffer's mbarrier.  The one sample pair that straddles
 // an end of the burst cannot be bulk-copied (8-byte aligned only): lane 31 fetches it here and returns it in
 // (patch, patch_idx); the caller stores it right before the buffer is consumed, so its latency is hidden too.
 __device__ __forceinline__ void stage_async(const float2 *x, int off2, float2 *U, unsigned bar, int lane, float2 &patch,
@@ -276,12 +274,10 @@ __device__ __forceinline__ void stage_async(const float2 *x, int off2, float2 *U
 		for (int sidx = lane; sidx < nz_lo; sidx += 32) U4[slot_phys(sidx)] = z;
 		for (int sidx = kPairs - nz_hi + lane; sidx < kPairs; sidx += 32) U4[slot_phys(sidx)] = z;
 	}
-	if (lane == 0) mbar_arrive_expect_tx(bar, (unsigned)count * 16u);
 	__syncwarp();
-	if (lane < 9 && count > 0) {
-		const int lo = max(kBlockSlots * lane, s_first), hi = min(kBlockSlots * lane + kBlockSlots - 1, s_last);
-		if (lo <= hi)
-			bulk_g2s(smem_u32(U4 + slot_phys(lo)), x + off2 + 2 * lo, (unsigned)(hi - lo + 1) * 16u, bar);
+	if (lane == 0) {
+		mbar_arrive_expect_tx(bar, (unsigned)count * 16u);
+		if (count > 0) bulk_g2s(smem_u32(U4 + s_first), x + off2 + 2 * s_first, (unsigned)count * 16u, bar);
 	}
 }
 
@@ -366,11 +362,15 @@ demod_kernel(DemodParams p)
 		if (rc <= 0) {
 			// undetected burst: only the deferred clipping report is left to do (sigProcLib.cpp:1746-1764)
 			if (p.fix_clip && rc == 0) {
-				float mx = 0.0f;
-				for (int i = lane; i < 625; i += 32) {
-					const float2 v = __ldg(&x[i]);
-					mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+				float2 v[20];
+#pragma unroll
+				for (int k = 0; k < 20; k++) {
+					const int i = lane + 32 * k;
+					v[k] = i < 625 ? __ldg(&x[i]) : make_float2(0.0f, 0.0f);
 				}
+				float mx = 0.0f;
+#pragma unroll
+				for (int k = 0; k < 20; k++) mx = fmaxf(mx, fmaxf(fabsf(v[k].x), fabsf(v[k].y)));
 #pragma unroll
 				for (int o = 16; o; o >>= 1)
 					mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -410,7 +410,7 @@ demod_kernel(DemodParams p)
 			float2 acc[13];
 #pragma unroll
 			for (int m = 0; m < 13; m++) acc[m] = make_float2(0.0f, 0.0f);
-			const float4 *xc4 = reinterpret_cast<const float4 *>(U) + 10 * lane + (lane >> 2);
+			const float4 *xc4 = reinterpret_cast<const float4 *>(U) + 10 * lane;
 			const float *__restrict__ ce = c_tab.comp0[f][e];
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
