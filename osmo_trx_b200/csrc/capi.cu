@@ -458,7 +458,8 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 		return fail(ctx, TRXB200_EINVAL, "detect: max_toa_bound too large for on-chip buffers");
 	static bool configured = false;
 	if (!configured) {
-		CK(cudaFuncSetAttribute(corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		CK(cudaFuncSetAttribute(corr_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		CK(cudaFuncSetAttribute(corr_kernel<35>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		configured = true;
 	}
@@ -500,7 +501,8 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			const int ngroups = (m + kGroup - 1) / kGroup;
 			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));
 			prof_pre(ctx, st);
-			corr_kernel<<<cgrid, cw * 32, csmem, st>>>(c);
+			if (ndmax == 35 && lmax == 20) corr_kernel<35><<<cgrid, cw * 32, csmem, st>>>(c);
+			else corr_kernel<0><<<cgrid, cw * 32, csmem, st>>>(c);
 			prof_post(ctx, st, "corr_kernel");
 			int e = post_launch(ctx, "corr_kernel");
 			if (e) return e;

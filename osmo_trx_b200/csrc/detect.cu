@@ -122,39 +122,43 @@ __device__ __forceinline__ bool near_tie(float a, float b)
 // ---------------------------------------------------------------------------------------------
 constexpr int kGroup = 4; // bursts staged / decimated / correlated together by one warp
 
-struct GroupSlot { int active, seq_off, hlen, start, len, nd, pad0, pad1; };
-
 // slots (16 B = 2 samples) per polyphase plane of one staged window; = 4 (mod 8) keeps the two planes
 // on disjoint bank groups for the staging stores
-__host__ __device__ inline int corr_plane_slots(int ndmax) { int s = ndmax + 3; while ((s & 7) != 4) s++; return s; }
+__host__ __device__ constexpr int corr_plane_slots(int ndmax) { int s = ndmax + 3; while ((s & 7) != 4) s++; return s; }
 __host__ __device__ inline size_t corr_warp_bytes(int ndmax)
 {
-	return (size_t)kGroup * 2 * corr_plane_slots(ndmax) * 16 + (size_t)kGroup * ndmax * 16 + kGroup * sizeof(GroupSlot);
+	return (size_t)kGroup * 2 * corr_plane_slots(ndmax) * 16 + (((size_t)kGroup * ndmax * 8 + 15) & ~(size_t)15);
 }
 __host__ __device__ inline size_t corr_hdr_bytes()
 {
-	return (size_t)SEQ_STORE * 16 + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
+	return (size_t)SEQ_STORE * 8 + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
 }
 
+// per-burst attempt parameters packed into one word: active | hlen << 1 | start << 8 | len << 16
+__device__ __forceinline__ int pk_active(int w) { return w & 1; }
+__device__ __forceinline__ int pk_hlen(int w) { return (w >> 1) & 127; }
+__device__ __forceinline__ int pk_start(int w) { return (w >> 8) & 255; }
+__device__ __forceinline__ int pk_len(int w) { return (w >> 16) & 0xffff; }
+
+// NDMAX > 0: compile-time row length of the decimated window (35 for normal / EDGE / dummy bursts at max_toa 4);
+// 0: taken from the parameter block
+template <int NDMAX>
 __global__ void __launch_bounds__(256, 3)
 corr_kernel(CorrParams p)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int wpb = blockDim.x >> 5;
-	// sync sequences as (hr, hr, -hi, hi): one 16-byte load feeds both packed products of a complex tap
-	float4 *hseq = reinterpret_cast<float4 *>(smem_raw);
-	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + (size_t)SEQ_STORE * 16);
-	const int PS = corr_plane_slots(p.ndmax);
-	unsigned char *wbase = smem_raw + corr_hdr_bytes() + corr_warp_bytes(p.ndmax) * warp;
-	float4 *raw = reinterpret_cast<float4 *>(wbase);			       // [kGroup][2][PS]
-	float4 *dec = raw + (size_t)kGroup * 2 * PS;				       // [kGroup][ndmax] (xr, xi, xi, xr)
-	GroupSlot *slot = reinterpret_cast<GroupSlot *>(dec + (size_t)kGroup * p.ndmax);
+	const int ndmax = NDMAX ? NDMAX : p.ndmax;
+	const int lmax = NDMAX ? NDMAX - 15 : p.lmax;
+	const int PS = NDMAX ? corr_plane_slots(NDMAX ? NDMAX : 1) : corr_plane_slots(p.ndmax);
+	float2 *hseq = reinterpret_cast<float2 *>(smem_raw); // sync sequences (hr, hi)
+	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + (size_t)SEQ_STORE * 8);
+	unsigned char *wbase = smem_raw + corr_hdr_bytes() + corr_warp_bytes(ndmax) * warp;
+	float4 *raw = reinterpret_cast<float4 *>(wbase);	      // [kGroup][2][PS]
+	float2 *dec = reinterpret_cast<float2 *>(raw + (size_t)kGroup * 2 * PS); // [kGroup][ndmax]
 
-	for (int k = threadIdx.x; k < SEQ_STORE; k += blockDim.x) {
-		const float2 h = c_tab.seq[k];
-		hseq[k] = make_float4(h.x, h.x, -h.y, h.y);
-	}
+	for (int k = threadIdx.x; k < SEQ_STORE; k += blockDim.x) hseq[k] = c_tab.seq[k];
 	for (int k = threadIdx.x; k < SEQ_COUNT; k += blockDim.x) sinfo[k] = c_tab.info[k];
 	__syncthreads();
 
@@ -167,36 +171,34 @@ corr_kernel(CorrParams p)
 	const int ngroups = (p.n + kGroup - 1) / kGroup;
 	for (int grp = blockIdx.x * wpb + warp; grp < ngroups; grp += gridDim.x * wpb) {
 		const int b0 = grp * kGroup;
-		__syncwarp();
-		// ---- lanes 0..3 publish the parameters of the group's bursts ----
+		// ---- lanes 0..3 work out the parameters of the group's bursts, everybody gets all four ----
+		int my_pk = 0, my_so = 0;
 		if (lane < kGroup) {
-			GroupSlot gs;
-			gs.active = 0; gs.seq_off = 0; gs.hlen = 0; gs.start = 0; gs.len = 0; gs.nd = 0; gs.pad0 = gs.pad1 = 0;
 			const int b = b0 + lane;
 			if (b < p.n) {
 				const int type = p.type[b], tsc = p.tsc[b], T = p.max_toa[b];
 				const int rc_prev = p.round > 0 ? p.rc[b] : 0;
 				Attempt at;
-				if (attempt_runs(type, tsc, T, p.max_toa_bound, p.ndmax, p.round, rc_prev, sinfo, at)) {
-					gs.active = 1;
-					gs.seq_off = sinfo[at.seq].off;
-					gs.hlen = sinfo[at.seq].len;
-					gs.start = at.start;
-					gs.len = at.len;
-					gs.nd = gs.hlen + gs.len - 1;
+				if (attempt_runs(type, tsc, T, p.max_toa_bound, ndmax, p.round, rc_prev, sinfo, at)) {
+					my_pk = 1 | (sinfo[at.seq].len << 1) | (at.start << 8) | (at.len << 16);
+					my_so = sinfo[at.seq].off;
 				}
 			}
-			slot[lane] = gs;
 		}
-		__syncwarp();
+		int pk[kGroup], so[kGroup];
 		int ndpad = 0, lenpad = 0;
 #pragma unroll
 		for (int g = 0; g < kGroup; g++) {
-			ndpad = max(ndpad, slot[g].nd);
-			lenpad = max(lenpad, slot[g].len);
+			pk[g] = __shfl_sync(0xffffffffu, my_pk, g);
+			so[g] = __shfl_sync(0xffffffffu, my_so, g);
+			if (pk_active(pk[g])) {
+				ndpad = max(ndpad, pk_hlen(pk[g]) + pk_len(pk[g]) - 1);
+				lenpad = max(lenpad, pk_len(pk[g]));
+			}
 		}
 		if (ndpad == 0)
 			continue;
+		__syncwarp();
 
 		// ---- stage: window samples s_lo .. s_lo + 4*nd + 11 of each burst; sample s of the window lives in
 		//      16-byte slot s>>1, slot sl goes to plane sl&1 at index sl>>1 (conflict-free 16-byte reads at lane
@@ -205,21 +207,21 @@ corr_kernel(CorrParams p)
 		bool fast = true;
 #pragma unroll
 		for (int g = 0; g < kGroup; g++) {
-			const GroupSlot gs = slot[g];
-			if (gs.active && (4 * (gs.start - gs.hlen + 1) - 15 < 1 || 2 * gs.nd + 7 > 96)) fast = false;
+			const int nd = pk_hlen(pk[g]) + pk_len(pk[g]) - 1;
+			if (pk_active(pk[g]) && (4 * (pk_start(pk[g]) - pk_hlen(pk[g]) + 1) - 15 < 1 || 2 * nd + 7 > 96)) fast = false;
 		}
 		if (fast) {
 			float4 ld[kGroup][3];
 			int dlt[kGroup], npr[kGroup];
 #pragma unroll
 			for (int g = 0; g < kGroup; g++) {
-				const GroupSlot gs = slot[g];
 				const int b = b0 + g;
 				const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
-				const int s_lo = 4 * (gs.start - gs.hlen + 1) - 15;
+				const int nd = pk_hlen(pk[g]) + pk_len(pk[g]) - 1;
+				const int s_lo = 4 * (pk_start(pk[g]) - pk_hlen(pk[g]) + 1) - 15;
 				const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
 				const int delta = (int)(((unsigned)s_lo + row_par) & 1u); // first aligned pair starts delta samples early
-				const int np = gs.active ? 2 * gs.nd + 6 + delta : 0;	    // aligned pairs covering the window
+				const int np = pk_active(pk[g]) ? 2 * nd + 6 + delta : 0;   // aligned pairs covering the window
 				dlt[g] = delta;
 				npr[g] = np;
 #pragma unroll
@@ -248,12 +250,12 @@ corr_kernel(CorrParams p)
 		} else {
 #pragma unroll 1
 			for (int g = 0; g < kGroup; g++) {
-				const GroupSlot gs = slot[g];
-				if (!gs.active) continue;
+				if (!pk_active(pk[g])) continue;
 				const int b = b0 + g;
 				const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
-				const int s_lo = 4 * (gs.start - gs.hlen + 1) - 15;
-				const int ns = 2 * gs.nd + 6;
+				const int nd = pk_hlen(pk[g]) + pk_len(pk[g]) - 1;
+				const int s_lo = 4 * (pk_start(pk[g]) - pk_hlen(pk[g]) + 1) - 15;
+				const int ns = 2 * nd + 6;
 				const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
 				const bool aligned = (((unsigned)s_lo + row_par) & 1u) == 0;
 				float4 *rg = raw + (size_t)g * 2 * PS;
@@ -278,9 +280,9 @@ corr_kernel(CorrParams p)
 		for (int it = lane; it < kGroup * ndpad; it += 32) {
 			const int g = (it >= ndpad) + (it >= 2 * ndpad) + (it >= 3 * ndpad);
 			const int j = it - g * ndpad;
-			const GroupSlot gs = slot[g];
-			if (!gs.active || j >= gs.nd) continue;
-			const int d = gs.start - (gs.hlen - 1) + j;
+			const int w = g == 0 ? pk[0] : g == 1 ? pk[1] : g == 2 ? pk[2] : pk[3];
+			if (!pk_active(w) || j >= pk_hlen(w) + pk_len(w) - 1) continue;
+			const int d = pk_start(w) - (pk_hlen(w) - 1) + j;
 			float2 y = make_float2(0.0f, 0.0f);
 			if (d >= 0 && d < 156) {
 				const float4 *r0 = raw + (size_t)g * 2 * PS + j; // plane 0: slots 2j, 2j+2, ...
@@ -300,38 +302,46 @@ corr_kernel(CorrParams p)
 					L[q] = add2(add2(pr[q], pr[4 + q]), add2(pr[8 + q], pr[12 + q]));
 				y = add2(add2(L[0], L[1]), add2(L[2], L[3]));
 			}
-			dec[(size_t)g * p.ndmax + j] = make_float4(y.x, y.y, y.y, y.x);
-			p.pwr[(size_t)(b0 + g) * p.ndmax + j] = norm2(y);
+			dec[g * ndmax + j] = y;
+			p.pwr[(size_t)(b0 + g) * ndmax + j] = norm2(y);
 		}
 		__syncwarp();
 
-		// ---- correlation: sse_conv_cmplx_8n order (convolve_sse_3.c:462-537); hlen is 16, 40 or 64 ----
+		// ---- correlation: sse_conv_cmplx_8n order (convolve_sse_3.c:462-537); hlen is 16, 40 or 64.
+		//      One complex tap = two packed products and one packed add: x*(hr,hr) + swap(x*(hi,-hi))
+		//      = (hr*xr - hi*xi, hr*xi + hi*xr); the per-half negation and the swap are operand modifiers. ----
 		for (int it = lane; it < kGroup * lenpad; it += 32) {
 			const int g = (it >= lenpad) + (it >= 2 * lenpad) + (it >= 3 * lenpad);
 			const int i = it - g * lenpad;
-			const GroupSlot gs = slot[g];
-			if (!gs.active || i >= gs.len) continue;
-			const float4 *dx = dec + (size_t)g * p.ndmax + i;
-			const float4 *hh = hseq + gs.seq_off;
+			const int w = g == 0 ? pk[0] : g == 1 ? pk[1] : g == 2 ? pk[2] : pk[3];
+			if (!pk_active(w) || i >= pk_len(w)) continue;
+			const int hlen = pk_hlen(w);
+			const float2 *dx = dec + g * ndmax + i;
+			const float2 *hh = hseq + (g == 0 ? so[0] : g == 1 ? so[1] : g == 2 ? so[2] : so[3]);
 			float2 A[4], B[4];
 #pragma unroll
 			for (int q = 0; q < 4; q++) { A[q] = make_float2(0.0f, 0.0f); B[q] = make_float2(0.0f, 0.0f); }
-			for (int t0 = 0; t0 < gs.hlen; t0 += 8) {
+			for (int t0 = 0; t0 < hlen; t0 += 8) {
 #pragma unroll
 				for (int q = 0; q < 4; q++) {
-					float4 xv = dx[t0 + q], hv = hh[t0 + q];
-					A[q] = add2(A[q], add2(mul2(make_float2(xv.x, xv.y), make_float2(hv.x, hv.y), NZ),
-							       mul2(make_float2(xv.z, xv.w), make_float2(hv.z, hv.w), NZ)));
-					xv = dx[t0 + 4 + q];
-					hv = hh[t0 + 4 + q];
-					B[q] = add2(B[q], add2(mul2(make_float2(xv.x, xv.y), make_float2(hv.x, hv.y), NZ),
-							       mul2(make_float2(xv.z, xv.w), make_float2(hv.z, hv.w), NZ)));
+					{
+						const float2 xv = dx[t0 + q], hv = hh[t0 + q];
+						const float2 p1 = mul2(xv, bc2(hv.x), NZ);
+						const float2 p2 = mul2(xv, make_float2(hv.y, -hv.y), NZ);
+						A[q] = add2(A[q], add2(p1, make_float2(p2.y, p2.x)));
+					}
+					{
+						const float2 xv = dx[t0 + 4 + q], hv = hh[t0 + 4 + q];
+						const float2 p1 = mul2(xv, bc2(hv.x), NZ);
+						const float2 p2 = mul2(xv, make_float2(hv.y, -hv.y), NZ);
+						B[q] = add2(B[q], add2(p1, make_float2(p2.y, p2.x)));
+					}
 				}
 			}
 			float2 L[4];
 #pragma unroll
 			for (int q = 0; q < 4; q++) L[q] = add2(A[q], B[q]);
-			p.corr[(size_t)(b0 + g) * p.lmax + i] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+			p.corr[(size_t)(b0 + g) * lmax + i] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
 		}
 	}
 }
