@@ -168,6 +168,11 @@ corr_kernel(CorrParams p)
 	for (int k = 0; k < 16; k++) g16[k] = c_tab.dnsamp[k];
 	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
 
+	// slot sl = lane + 32*it of a staged window lives in plane sl&1 at index sl>>1
+	int stage_off[3];
+#pragma unroll
+	for (int it = 0; it < 3; it++) stage_off[it] = ((lane + 32 * it) & 1) * PS + ((lane + 32 * it) >> 1);
+
 	const int ngroups = (p.n + kGroup - 1) / kGroup;
 	for (int grp = blockIdx.x * wpb + warp; grp < ngroups; grp += gridDim.x * wpb) {
 		const int b0 = grp * kGroup;
@@ -198,6 +203,10 @@ corr_kernel(CorrParams p)
 		}
 		if (ndpad == 0)
 			continue;
+		if (NDMAX) { // fixed work-item decomposition: (burst, sample) = (it / NDMAX, it % NDMAX), known per lane at compile time
+			ndpad = NDMAX;
+			lenpad = NDMAX - 15;
+		}
 		__syncwarp();
 
 		// ---- stage: window samples s_lo .. s_lo + 4*nd + 11 of each burst; sample s of the window lives in
@@ -212,7 +221,7 @@ corr_kernel(CorrParams p)
 		}
 		if (fast) {
 			float4 ld[kGroup][3];
-			int dlt[kGroup], npr[kGroup];
+			int npr[kGroup];
 #pragma unroll
 			for (int g = 0; g < kGroup; g++) {
 				const int b = b0 + g;
@@ -220,32 +229,35 @@ corr_kernel(CorrParams p)
 				const int nd = pk_hlen(pk[g]) + pk_len(pk[g]) - 1;
 				const int s_lo = 4 * (pk_start(pk[g]) - pk_hlen(pk[g]) + 1) - 15;
 				const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
-				const int delta = (int)(((unsigned)s_lo + row_par) & 1u); // first aligned pair starts delta samples early
-				const int np = pk_active(pk[g]) ? 2 * nd + 6 + delta : 0;   // aligned pairs covering the window
-				dlt[g] = delta;
+				const bool aligned = (((unsigned)s_lo + row_par) & 1u) == 0; // window slots sit on the row's 16-byte grid
+				const int np = pk_active(pk[g]) ? 2 * nd + 6 : 0;	      // slots of the window
 				npr[g] = np;
+				if (aligned) {
 #pragma unroll
-				for (int it = 0; it < 3; it++) {
-					const int sl = lane + 32 * it;
-					ld[g][it] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-					if (sl < np)
-						ld[g][it] = __ldg(reinterpret_cast<const float4 *>(x + (s_lo - delta + 2 * sl)));
+					for (int it = 0; it < 3; it++) {
+						const int sl = lane + 32 * it;
+						ld[g][it] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+						if (sl < np) ld[g][it] = __ldg(reinterpret_cast<const float4 *>(x + (s_lo + 2 * sl)));
+					}
+				} else {
+#pragma unroll
+					for (int it = 0; it < 3; it++) {
+						const int sl = lane + 32 * it;
+						float2 a = make_float2(0.0f, 0.0f), c = a;
+						if (sl < np) {
+							a = __ldg(x + (s_lo + 2 * sl));
+							c = __ldg(x + (s_lo + 2 * sl + 1));
+						}
+						ld[g][it] = make_float4(a.x, a.y, c.x, c.y);
+					}
 				}
 			}
 #pragma unroll
 			for (int g = 0; g < kGroup; g++) {
-				float2 *rg2 = reinterpret_cast<float2 *>(raw + (size_t)g * 2 * PS);
+				float4 *rg = raw + (size_t)g * 2 * PS;
 #pragma unroll
-				for (int it = 0; it < 3; it++) {
-					const int sl = lane + 32 * it;
-					// window sample positions of the pair: r, r + 1
-					const int r = 2 * sl - dlt[g];
-					const int r1 = r + 1;
-					if (sl < npr[g]) {
-						if (r >= 0) rg2[(((r >> 1) & 1) * PS + (r >> 2)) * 2 + (r & 1)] = make_float2(ld[g][it].x, ld[g][it].y);
-						rg2[(((r1 >> 1) & 1) * PS + (r1 >> 2)) * 2 + (r1 & 1)] = make_float2(ld[g][it].z, ld[g][it].w);
-					}
-				}
+				for (int it = 0; it < 3; it++)
+					if (lane + 32 * it < npr[g]) rg[stage_off[it]] = ld[g][it];
 			}
 		} else {
 #pragma unroll 1
@@ -277,6 +289,7 @@ corr_kernel(CorrParams p)
 
 		// ---- decimation: one 1-sps sample per work item, sse_conv_real16 order (convolve_sse_3.c:188-264):
 		//      p[k] = x[4d-15+k]*g[k], L_j = (p[j]+p[4+j]) + (p[8+j]+p[12+j]), y = (L0+L1)+(L2+L3) ----
+#pragma unroll
 		for (int it = lane; it < kGroup * ndpad; it += 32) {
 			const int g = (it >= ndpad) + (it >= 2 * ndpad) + (it >= 3 * ndpad);
 			const int j = it - g * ndpad;
@@ -310,6 +323,7 @@ corr_kernel(CorrParams p)
 		// ---- correlation: sse_conv_cmplx_8n order (convolve_sse_3.c:462-537); hlen is 16, 40 or 64.
 		//      One complex tap = two packed products and one packed add: x*(hr,hr) + swap(x*(hi,-hi))
 		//      = (hr*xr - hi*xi, hr*xi + hi*xr); the per-half negation and the swap are operand modifiers. ----
+#pragma unroll
 		for (int it = lane; it < kGroup * lenpad; it += 32) {
 			const int g = (it >= lenpad) + (it >= 2 * lenpad) + (it >= 3 * lenpad);
 			const int i = it - g * lenpad;
