@@ -178,8 +178,15 @@ def make_workload(trx, kind, n, seed, device):
     return rx, typ, tsc, max_toa, bound
 
 
-def cpu_baseline(rx_host, typ, tsc, max_toa, target_s=12.0):
-    """The reference's own detectAnyBurst+demodAnyBurst (oracle/_ref) on all host cores, bounded sample."""
+IQ_SCALE = 8000.0        # synthetic float bursts (|amp| <= ~1.7) -> int16 I/Q as a radio delivers them
+RX_FULL_SCALE = 32767.0  # RadioInterface::fullScaleInputValue() of an int16 device
+
+
+def cpu_baseline(rx_host, iq_host, typ, tsc, max_toa, fn, tn, target_s=8.0):
+    """The reference's own code (oracle/_ref) on all host cores, bounded sample of the same workload:
+    (1) detectAnyBurst+demodAnyBurst on the float bursts - the hot path `value` measures;
+    (2) int16 slot -> TRXD datagram (convert_short_float, energyDetect, detect, demod, vectorSlicer,
+        trxd_send_burst_ind_v1 into /dev/null) - the chain `e2e` measures."""
     import numpy as np
     import cpulibs
     if cpulibs.Ref.available():
@@ -193,16 +200,23 @@ def cpu_baseline(rx_host, typ, tsc, max_toa, target_s=12.0):
     dt = time.perf_counter() - t0
     rate = n0 / dt
     n1 = int(min(len(rx_host), max(n0, rate * target_s / 3)))
-    times = []
-    for _ in range(3):
-        t0 = time.perf_counter()
-        lib.detect_demod(rx_host[:n1], typ[:n1], tsc[:n1], max_toa[:n1], nthreads=cores)
-        times.append(time.perf_counter() - t0)
-    times.sort()
-    v = n1 / times[1]
+
+    def med3(f):
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            f()
+            times.append(time.perf_counter() - t0)
+        times.sort()
+        return n1 / times[1]
+
+    v = med3(lambda: lib.detect_demod(rx_host[:n1], typ[:n1], tsc[:n1], max_toa[:n1], nthreads=cores))
+    vp = med3(lambda: lib.pull(iq_host[:n1], typ[:n1], tsc[:n1], max_toa[:n1], fn[:n1], tn[:n1], full_scale=RX_FULL_SCALE,
+                               pkt_stride=160, nthreads=cores, capture=False))
     return {"value": v, "unit": "bursts/s", "cores": cores, "kind": kind,
             "sample": f"{n1} bursts of the same workload x 3 passes (median), {cores} threads",
-            "per_core": v / cores}
+            "per_core": v / cores, "int16_to_trxd": {"value": vp, "per_core": vp / cores,
+                                                    "what": "int16 slot -> TRXD v1 datagram (the chain e2e measures)"}}
 
 
 def run_reference(args):
@@ -231,18 +245,35 @@ def run_reference(args):
     rx, _ = synth.impair(w, rng, snr_db=snr, noise_only_frac=0.05)
     typ_a = np.full(n, typ, np.uint8)
     mt_a = np.full(n, mt, np.uint16)
+    # the chain the b200 arm's e2e measures: int16 slots in, TRXD v1 datagrams out (written to /dev/null here; the
+    # reference writes them to a UDP socket).  detect+demod alone on the float bursts is reported beside it.
+    iq = np.clip(np.rint(rx * IQ_SCALE), -32768, 32767).astype(np.int16)
+    fn = (np.arange(n) // 8).astype(np.uint32)
+    tn = (np.arange(n) % 8).astype(np.uint8)
+    pstride = 456 if args.workload == "edge" else 160
+
+    def one():
+        lib.pull(iq, typ_a, tsc, mt_a, fn, tn, full_scale=RX_FULL_SCALE, pkt_stride=pstride, nthreads=cores, capture=False)
+
     for _ in range(args.warmup):
-        lib.detect_demod(rx, typ_a, tsc, mt_a, nthreads=cores)
+        one()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        lib.detect_demod(rx, typ_a, tsc, mt_a, nthreads=cores)
+        one()
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 4)):
+        lib.detect_demod(rx, typ_a, tsc, mt_a, nthreads=cores)
+    v_dd = n * max(1, args.steps // 4) / (time.perf_counter() - t0)
     line = {"impl": "reference", "metric": "GSM bursts/sec detected+demodulated (sps=4)", "value": v, "unit": "bursts/s",
             "arfcn_equivalents": v / ARFCN_BURSTS_PER_S, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "bursts_per_step": n, "sps": 4},
+            "config": {"workload": workload_name(args.workload), "bursts_per_step": n, "sps": 4,
+                       "chain": "int16 slot -> convert_short_float -> energyDetect -> detectAnyBurst -> demodAnyBurst -> "
+                                "vectorSlicer -> trxd_send_burst_ind_v1 (fd=/dev/null)"},
+            "detect_demod_only": {"value": v_dd, "unit": "bursts/s", "what": "detectAnyBurst+demodAnyBurst on float bursts"},
             "cpu_baseline": {"value": v, "unit": "bursts/s", "cores": cores, "kind": kind,
                              "sample": f"{n} bursts per step, {cores} threads"},
             "e2e": {"value": v, "unit": "bursts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -352,7 +383,45 @@ def main():
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D + kernels + D2H in the timed region) ----
     e2e = None
+    e2e_f32 = None
+    pstride = 456 if args.workload == "edge" else 160
     if not args.no_e2e:
+        # (a) the widened boundary: int16 slots as the radio delivers them in, TRXD v1 datagrams out
+        ne = min(args.e2e_bursts, n)
+        h_iq = torch.empty((ne, 625, 2), dtype=torch.int16).pin_memory()
+        h_iq.copy_((rx[:ne] * IQ_SCALE).round().clamp(-32768, 32767).to(torch.int16))
+        h_typ, h_tsc, h_mt = typ[:ne].cpu().pin_memory(), tsc[:ne].cpu().pin_memory(), max_toa[:ne].cpu().pin_memory()
+        h_fn = (torch.arange(ne, dtype=torch.int32) // 8).pin_memory()
+        h_tn = (torch.arange(ne) % 8).to(torch.uint8).pin_memory()
+        h_pout = {k: v.pin_memory() for k, v in trx.alloc_pull_results(ne, pstride, device="cpu", extras=False).items()}
+
+        def pull_once():
+            trx.pull_host(h_iq, h_typ, h_tsc, h_mt, h_fn, h_tn, bound, h_pout, full_scale=RX_FULL_SCALE)
+
+        for _ in range(2):
+            pull_once()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = trx.launch_count
+        t0 = time.perf_counter()
+        reps = max(3, min(args.steps, 10))
+        for _ in range(reps):
+            pull_once()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e_launches = trx.launch_count - l0
+        if world > 1:
+            t = torch.tensor([dt], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * ne * reps / dt, "unit": "bursts/s", "h2d_bytes_per_step": ne * (2500 + 1 + 1 + 2 + 4 + 1),
+               "d2h_bytes_per_step": ne * (4 + 4 + pstride + 2 + 1), "bursts_per_call": ne,
+               "api": "trxb200_pull_host: int16 I/Q slots in (pinned host), TRXD v1 datagrams out (pinned host)",
+               "sent_fraction": float((h_pout["pkt_len"] > 11).float().mean().item()), "gpu_launches": int(e2e_launches)}
+        del h_iq, h_pout
+    if not args.no_e2e:
+        # (b) the strict float boundary (signalVector in, SoftVector out), PCIe-bound at 5 KB per burst
         ne = min(args.e2e_bursts, n)
         h_rx = torch.empty((ne, 625, 2), dtype=torch.float32).pin_memory()
         h_rx.copy_(rx[:ne])
@@ -375,15 +444,17 @@ def main():
             dt = float(t.item())
         h2d = ne * (5000 + 1 + 1 + 2)
         d2h = ne * (4 + 8 + 4 + 4 + 1 + 1 + 148 * 4)
-        e2e = {"value": world * ne * reps / dt, "unit": "bursts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "bursts_per_call": ne, "api": "trxb200_detect_demod_host (pinned host buffers)"}
+        e2e_f32 = {"value": world * ne * reps / dt, "unit": "bursts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "bursts_per_call": ne, "api": "trxb200_detect_demod_host: float32 bursts in, float32 soft bits out (pinned host)"}
 
     cpu = None
     det_frac = float((out["rc"] > 0).float().mean().item())
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(n, 1 << 18)
-        cpu = cpu_baseline(rx[:ns].cpu().numpy(), typ[:ns].cpu().numpy(), tsc[:ns].cpu().numpy(),
-                           max_toa[:ns].cpu().numpy().astype(np.uint16))
+        iq_s = (rx[:ns] * IQ_SCALE).round().clamp(-32768, 32767).to(torch.int16).cpu().numpy()
+        cpu = cpu_baseline(rx[:ns].cpu().numpy(), iq_s, typ[:ns].cpu().numpy(), tsc[:ns].cpu().numpy(),
+                           max_toa[:ns].cpu().numpy().astype(np.uint16), (np.arange(ns) // 8).astype(np.uint32),
+                           (np.arange(ns) % 8).astype(np.uint8))
 
     if rank == 0:
         line = {"metric": "GSM bursts/sec detected+demodulated (sps=4)", "value": value, "unit": "bursts/s",
@@ -393,7 +464,7 @@ def main():
                 "config": {"workload": workload_name(args.workload), "bursts_per_gpu_per_step": n, "sps": 4,
                            "l2": "inputs (5.2 GB/GPU) far exceed the 126 MB L2; no flush needed",
                            "detected_fraction": det_frac, "sharding": "independent bursts, no data-path collective"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -143,6 +143,53 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 			      int32_t *rc, float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags,
 			      float *soft, int soft_stride, int n_gmsk_soft);
 
+/* ---- the receive chain around the hot path: int16 slot in, TRXD uplink datagram out ----
+ * Per slot b, the DSP statements of Transceiver::pullRadioVector (Transceiver.cpp:665-815) with what feeds and
+ * follows them:
+ *   convert_short_float of the radio's int16 I/Q (RadioInterface::pullBuffer, radioInterface.cpp:345-349;
+ *   arch/x86/convert.c:37-79); slot b is the 625 samples at iq + b*stride (radioInterface.cpp:272-291 slices the
+ *   stream into consecutive 625-sample slots at 4 sps, i.e. stride 625 on a contiguous stream);
+ *   type OFF: nothing is computed or emitted (:713-716);
+ *   energy[b] = energyDetect(burst, 20*sps) (:725), RSSI = 20*log10(rx_full_scale / sqrt(energy)) + rssi_offset (:742-751);
+ *   type IDLE: idle indication (:754); otherwise rc[b] = detectAnyBurst(...) (:768), rc <= 0: idle indication,
+ *   -SIGERR_CLIP reported in rc (:769-782); rc > 0: demodAnyBurst (:786) and vectorSlicer (:803);
+ *   the datagram trxd_send_burst_ind_v0 / _v1 would write (proto_trxd.c:69-117): header (tn, fn, rssi, toa*256,
+ *   and for v1 idle/modulation/tsc/ci in cB) followed by 148 (GMSK) or 444 (8-PSK) soft bits normalised to 0..255
+ *   (v0: two more bytes, both written as 0; v0 emits nothing for idle slots).
+ * pkt: u8[n][pkt_stride], pkt_len[b] = datagram length (0: nothing to send).  pkt_stride >= 159 (v1) / 158 (v0);
+ * rows shorter than 455 / 454 cannot hold an 8-PSK burst: such a burst gets pkt_len 0 and TRXB200_FLAG_PKT_TRUNC.
+ * amp, toa, ci, tsc_out (the estim_burst_params fields) and flags are optional (NULL).  iq must be 4-byte aligned.
+ * rx_full_scale = RadioInterface::fullScaleInputValue(), rssi_offset = Transceiver::rssiOffset(chan).
+ * The noise-level average over IDLE slots (mNoises, :744-748) is caller state: feed it from energy[]. ---- */
+typedef struct trxb200_pull_args {
+	const int16_t *iq;
+	int stride; /* complex samples between consecutive slots, >= 625 */
+	int n;
+	const uint8_t *type, *tsc;
+	const uint16_t *max_toa;
+	const uint32_t *fn; /* TDMA frame number per slot */
+	const uint8_t *tn;  /* timeslot number per slot */
+	int max_toa_bound;
+	float thresh;
+	double rx_full_scale, rssi_offset;
+	int trxd_version; /* 0 or 1 */
+	int32_t *rc;
+	float *energy;
+	uint8_t *pkt;
+	int pkt_stride;
+	uint16_t *pkt_len;
+	uint8_t *flags;	 /* optional */
+	float *amp, *toa, *ci; /* optional */
+	uint8_t *tsc_out;      /* optional */
+} trxb200_pull_args;
+#define TRXB200_FLAG_PKT_TRUNC 8
+#define TRXB200_TRXD_V1_HDR 11
+#define TRXB200_TRXD_V0_HDR 8
+/* DEVICE pointers; enqueues on the context's stream */
+int trxb200_pull_batch(trxb200_ctx *ctx, const trxb200_pull_args *args);
+/* HOST pointers; H2D / kernels / D2H pipelined over internal streams (pinned buffers recommended) */
+int trxb200_pull_host(trxb200_ctx *ctx, const trxb200_pull_args *args);
+
 /* ---- small per-burst helpers of sigProcLib.h used around detection ---- */
 /* energyDetect(burst, window) (sigProcLib.cpp:1573-1585): mean |x|^2 of `window` samples at stride 4 */
 int trxb200_energy_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int blen, int n,

@@ -94,10 +94,22 @@ int orc_downsample_burst(const ocf *in, int blen, ocf *out /*156*/);
 void orc_convert_float_short(short *out, const float *in, float scale, int len); /* SSE semantics */
 void orc_convert_short_float(float *out, const short *in, int len);
 
+/* receive chain around the hot path (oracle_pull.c): int16 slot -> TRXD uplink datagram */
+int orc_trxd_pack(int version, uint32_t fn, uint8_t tn, double rssi, double toa, int idle, int is_8psk, uint8_t tsc,
+		  float ci, const float *soft01, int nbits, uint8_t *pkt);
+int orc_pull_burst(const int16_t *iq, int type, unsigned tsc, unsigned max_toa, uint32_t fn, uint8_t tn, float thresh,
+		   double full_scale, double rssi_offset, int version, uint8_t *pkt, int32_t *rc_out, float *energy_out,
+		   orc_ebp *ebp_out, int *flags_out);
+int orc_pull_batch(const int16_t *iq, int stride, int n, const uint8_t *type, const uint8_t *tsc, const uint16_t *max_toa,
+		   const uint32_t *fn, const uint8_t *tn, float thresh, double full_scale, double rssi_offset, int version,
+		   int32_t *rc, float *energy, uint8_t *pkt, int pkt_stride, uint16_t *pkt_len, uint8_t *flags, float *amp,
+		   float *toa, float *ci, uint8_t *tsc_out, int nthreads);
+
 /* flags written by detection (bit set) */
 #define ORC_FLAG_THRESH_EDGE 1 /* |peakRatio - thresh| < 1e-5 */
 #define ORC_FLAG_BISECT_TIE 2  /* early/late powers within 4 ulp at some bisection step */
 #define ORC_FLAG_CLIP 4	       /* max |I|,|Q| > 30000 */
+#define ORC_FLAG_PKT_TRUNC 8   /* pull path: datagram row too small for the burst (8-PSK), nothing emitted */
 
 /* Resampler.h:31-61 */
 typedef struct orc_resampler orc_resampler;

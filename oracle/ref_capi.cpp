@@ -30,7 +30,11 @@
 
 extern "C" {
 #include "convert.h"
+#include "proto_trxd.h" /* reference TRXD uplink datagram writers (proto_trxd.c, compiled unmodified) */
 }
+#include <unistd.h>
+#include <fcntl.h>
+#include <cerrno>
 
 int gVectorDebug = 0; /* declared CommonLibs/Vector.h:45, defined nowhere in the tree */
 
@@ -269,6 +273,110 @@ int ref_detect_demod_batch(const float *bursts, int stride, int blen, int n, con
 		amp[2 * b] = ebp.amp.real(); amp[2 * b + 1] = ebp.amp.imag();
 		toa[b] = ebp.toa; tsc_out[b] = ebp.tsc; ci[b] = ebp.ci;
 	});
+	return n;
+}
+
+/* ---- the receive chain around the hot path: int16 slot -> TRXD uplink datagram ----
+ * The DSP statements of Transceiver::pullRadioVector (Transceiver.cpp:665-815; the method itself needs the
+ * radio FIFO, libosmocore and the state machine, so its statements are replayed here around the reference's own
+ * functions), preceded by RadioInterface::pullBuffer's convert_short_float (radioInterface.cpp:345-349) and
+ * followed by the UNMODIFIED trxd_send_burst_ind_v0/_v1 (proto_trxd.c:69-117).  capture != 0: the datagram is
+ * written to a pipe and copied out (parity); capture == 0: written to /dev/null (timing: the reference pays one
+ * write() per burst, to a UDP socket in production). */
+int ref_pull_batch(const int16_t *iq, int stride, int n, const uint8_t *type, const uint8_t *tsc, const uint16_t *max_toa,
+		   const uint32_t *fn, const uint8_t *tn, float thresh, double full_scale, double rssi_offset, int version,
+		   int32_t *rc, float *energy, uint8_t *pkt, int pkt_stride, uint16_t *pkt_len, float *amp, float *toa,
+		   float *ci, uint8_t *tsc_out, int capture, int nthreads)
+{
+	if (nthreads < 1) nthreads = 1;
+	if (n < 2 * nthreads) nthreads = 1;
+	const int per = (n + nthreads - 1) / nthreads;
+	auto worker = [&](int lo, int hi) {
+		int fds[2] = { -1, -1 };
+		if (capture) {
+			if (pipe(fds) != 0) return;
+		} else {
+			fds[1] = open("/dev/null", O_WRONLY);
+		}
+		std::vector<float> xbuf(2 * 625);
+		for (int b = lo; b < hi; b++) {
+			struct trx_ul_burst_ind bi;
+			struct estim_burst_params ebp;
+			ebp.amp = 0.0f; ebp.toa = 0.0f; ebp.tsc = 0; ebp.ci = 0.0f;
+			rc[b] = 0; energy[b] = 0.0f; pkt_len[b] = 0;
+			if (amp) { amp[2 * b] = 0; amp[2 * b + 1] = 0; }
+			if (toa) toa[b] = 0;
+			if (ci) ci[b] = 0;
+			if (tsc_out) tsc_out[b] = 0;
+			/* Transceiver.cpp:693-704 */
+			bi.nbits = 0; bi.fn = fn[b]; bi.tn = tn[b]; bi.rssi = 0.0; bi.toa = 0.0; bi.noise = 0.0;
+			bi.idle = false; bi.modulation = MODULATION_GMSK; bi.tss = 0; bi.tsc = 0; bi.ci = 0.0;
+			const CorrType ctype = (CorrType)type[b];
+			if (ctype == OFF) /* :713-716 */
+				continue;
+			convert_short_float(xbuf.data(), iq + (size_t)b * stride * 2, 2 * 625);
+			BurstView bv(xbuf.data(), 625);
+			float max = -1.0, avg = 0.0;
+			int max_i = -1;
+			{ /* :723-731, one diversity path */
+				float pow = energyDetect(bv.v, 20 * 4);
+				if (pow > max) { max = pow; max_i = 0; }
+				avg += pow;
+				energy[b] = pow;
+			}
+			bool idle = true;
+			int r = 0;
+			if (max_i >= 0) {
+				avg = sqrt(avg / (size_t)1);				      /* :742 */
+				bi.rssi = 20.0 * log10(full_scale / avg) + rssi_offset;     /* :751 */
+				if (ctype != IDLE) {					      /* :754 */
+					r = detectAnyBurst(bv.v, tsc[b], thresh, 4, ctype, max_toa[b], &ebp); /* :768 */
+					if (r > 0) {
+						SoftVector *rxBurst = demodAnyBurst(bv.v, (CorrType)r, 4, &ebp); /* :786 */
+						bi.toa = ebp.toa; bi.tsc = ebp.tsc; bi.ci = ebp.ci;
+						if (rxBurst->size() == 444) { bi.modulation = MODULATION_8PSK; bi.nbits = 444; }
+						else { bi.modulation = MODULATION_GMSK; bi.nbits = 148; }
+						vectorSlicer(bi.rx_burst, rxBurst->begin(), bi.nbits);	  /* :803 */
+						delete rxBurst;
+						idle = false;
+					}
+				}
+			}
+			bi.idle = idle; /* ret_idle :810-814 */
+			rc[b] = r;
+			if (amp) { amp[2 * b] = ebp.amp.real(); amp[2 * b + 1] = ebp.amp.imag(); }
+			if (toa) toa[b] = ebp.toa;
+			if (ci) ci[b] = ebp.ci;
+			if (tsc_out) tsc_out[b] = ebp.tsc;
+			/* driveReceiveFIFO :1244-1250 */
+			if (version == 0) trxd_send_burst_ind_v0(0, fds[1], &bi);
+			else trxd_send_burst_ind_v1(0, fds[1], &bi);
+			if (capture) {
+				/* v0 drops idle indications without writing: poll the pipe without blocking */
+				uint8_t buf[1024];
+				int fl = fcntl(fds[0], F_GETFL, 0);
+				fcntl(fds[0], F_SETFL, fl | O_NONBLOCK);
+				ssize_t got = read(fds[0], buf, sizeof(buf));
+				if (got < 0) got = 0;
+				if (got > pkt_stride) got = 0;
+				memcpy(pkt + (size_t)b * pkt_stride, buf, (size_t)got);
+				pkt_len[b] = (uint16_t)got;
+			}
+		}
+		if (fds[0] >= 0) close(fds[0]);
+		if (fds[1] >= 0) close(fds[1]);
+	};
+	if (nthreads == 1) {
+		worker(0, n);
+	} else {
+		std::vector<std::thread> th;
+		for (int t = 0; t < nthreads; t++) {
+			int lo = t * per, hi = std::min(n, lo + per);
+			if (lo >= hi) break;
+			th.emplace_back(worker, lo, hi);
+		}
+		for (auto &t : th) t.join();
+	}
 	return n;
 }
 

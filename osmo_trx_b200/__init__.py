@@ -18,11 +18,21 @@ LIB_PATH = os.path.join(_HERE, "libtrxb200.so")
 
 OFF, TSC, EXT_RACH, RACH, SCH, EDGE, IDLE = range(7)
 SIGERR_NONE, SIGERR_BOUNDS, SIGERR_CLIP, SIGERR_UNSUPPORTED, SIGERR_INTERNAL = range(5)
-FLAG_THRESH_EDGE, FLAG_BISECT_TIE, FLAG_CLIP = 1, 2, 4
+FLAG_THRESH_EDGE, FLAG_BISECT_TIE, FLAG_CLIP, FLAG_PKT_TRUNC = 1, 2, 4, 8
 BURST_LEN = 625
 BURST_THRESH = 4.0  # sigProcLib.h:54
 
 _lib = None
+
+
+class PullArgs(C.Structure):
+    """trxb200_pull_args (include/trxb200.h)"""
+    _fields_ = [("iq", C.c_void_p), ("stride", C.c_int), ("n", C.c_int), ("type", C.c_void_p), ("tsc", C.c_void_p),
+                ("max_toa", C.c_void_p), ("fn", C.c_void_p), ("tn", C.c_void_p), ("max_toa_bound", C.c_int),
+                ("thresh", C.c_float), ("rx_full_scale", C.c_double), ("rssi_offset", C.c_double),
+                ("trxd_version", C.c_int), ("rc", C.c_void_p), ("energy", C.c_void_p), ("pkt", C.c_void_p),
+                ("pkt_stride", C.c_int), ("pkt_len", C.c_void_p), ("flags", C.c_void_p), ("amp", C.c_void_p),
+                ("toa", C.c_void_p), ("ci", C.c_void_p), ("tsc_out", C.c_void_p)]
 
 
 class TrxError(RuntimeError):
@@ -206,6 +216,45 @@ class Trx:
             C.c_int(max_toa_bound), C.c_float(thresh), _ptr(out["rc"]), _ptr(out["amp"]), _ptr(out["toa"]),
             _ptr(out["tsc"]), _ptr(out["ci"]), _ptr(out["flags"]), _ptr(out["soft"]), C.c_int(out["soft"].stride(0)),
             C.c_int(n_gmsk_soft)), "detect_demod_host")
+        return out
+
+    # -- receive chain around the hot path: int16 slots -> TRXD uplink datagrams --
+    def alloc_pull_results(self, n, pkt_stride=160, device=None, extras=True):
+        d = device or self.device
+        r = dict(rc=torch.zeros(n, dtype=torch.int32, device=d), energy=torch.zeros(n, dtype=torch.float32, device=d),
+                 pkt=torch.zeros((n, pkt_stride), dtype=torch.uint8, device=d),
+                 pkt_len=torch.zeros(n, dtype=torch.int16, device=d), flags=torch.zeros(n, dtype=torch.uint8, device=d))
+        if extras:
+            r.update(amp=torch.zeros((n, 2), dtype=torch.float32, device=d), toa=torch.zeros(n, dtype=torch.float32, device=d),
+                     ci=torch.zeros(n, dtype=torch.float32, device=d), tsc=torch.zeros(n, dtype=torch.uint8, device=d))
+        return r
+
+    def _pull_args(self, iq, type_, tsc, max_toa, fn, tn, max_toa_bound, out, thresh, full_scale, rssi_offset, version):
+        a = PullArgs()
+        a.iq = _ptr(iq); a.stride = iq.stride(0) // 2; a.n = iq.shape[0]
+        a.type = _ptr(type_); a.tsc = _ptr(tsc); a.max_toa = _ptr(max_toa); a.fn = _ptr(fn); a.tn = _ptr(tn)
+        a.max_toa_bound = max_toa_bound; a.thresh = thresh; a.rx_full_scale = full_scale; a.rssi_offset = rssi_offset
+        a.trxd_version = version
+        a.rc = _ptr(out["rc"]); a.energy = _ptr(out["energy"]); a.pkt = _ptr(out["pkt"]); a.pkt_stride = out["pkt"].stride(0)
+        a.pkt_len = _ptr(out["pkt_len"]); a.flags = _ptr(out.get("flags"))
+        a.amp = _ptr(out.get("amp")); a.toa = _ptr(out.get("toa")); a.ci = _ptr(out.get("ci")); a.tsc_out = _ptr(out.get("tsc"))
+        return a
+
+    def pull(self, iq, type_, tsc, max_toa, fn, tn, max_toa_bound, out=None, thresh=BURST_THRESH, full_scale=32767.0,
+             rssi_offset=0.0, version=1, pkt_stride=160):
+        """iq int16 [n, stride>=625, 2] (device); fn int32/uint32 [n]; tn uint8 [n].  Datagrams in out['pkt']."""
+        _chk_dev(iq, type_, tsc, max_toa, fn, tn)
+        r = out or self.alloc_pull_results(iq.shape[0], pkt_stride)
+        self.use_current_stream()
+        a = self._pull_args(iq, type_, tsc, max_toa, fn, tn, max_toa_bound, r, thresh, full_scale, rssi_offset, version)
+        self._check(self.lib.trxb200_pull_batch(self.h, C.byref(a)), "pull_batch")
+        return r
+
+    def pull_host(self, iq, type_, tsc, max_toa, fn, tn, max_toa_bound, out, thresh=BURST_THRESH, full_scale=32767.0,
+                  rssi_offset=0.0, version=1):
+        """Same with HOST tensors (ideally pinned); copies are inside the call."""
+        a = self._pull_args(iq, type_, tsc, max_toa, fn, tn, max_toa_bound, out, thresh, full_scale, rssi_offset, version)
+        self._check(self.lib.trxb200_pull_host(self.h, C.byref(a)), "pull_host")
         return out
 
     # -- helpers --

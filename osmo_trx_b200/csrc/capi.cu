@@ -26,6 +26,7 @@ __constant__ ConstTables c_tab;
 #include "misc.cu"
 #include "vitac.cu"
 #include "filterbank.cu"
+#include "pull.cu"
 
 using namespace trxb200;
 
@@ -37,6 +38,19 @@ struct DetectScratch {
 	float *pwr = nullptr;	// [cap][ndmax]
 	size_t corr_bytes = 0, pwr_bytes = 0;
 };
+
+// device scratch of the pull path (int16 slots -> TRXD datagrams) for one chunk of slots
+struct PullScratch {
+	int cap = 0, soft_stride = 0;
+	float *bursts = nullptr; // [cap][kPullStride] complex float (converted slots)
+	float *soft = nullptr;	 // [cap][soft_stride]
+	uint8_t *type2 = nullptr, *tsc_out = nullptr;
+	float *amp = nullptr, *toa = nullptr, *ci = nullptr;
+	DetectScratch ws;
+};
+constexpr int kPullStride = 626; // float rows of 5,008 B: every converted slot starts on a 16-byte boundary
+
+struct PullStage; // pinned-host pipeline state of trxb200_pull_host
 
 struct trxb200_ctx {
 	int device = -1;
@@ -54,6 +68,8 @@ struct trxb200_ctx {
 	DetectScratch ws;     // used by the *_batch entry points (one stream at a time)
 	std::string err;
 	HostStage *stage = nullptr;
+	PullScratch pull;	      // trxb200_pull_batch
+	PullStage *pull_stage = nullptr; // trxb200_pull_host
 	// optional per-kernel timing (trxb200_profile_begin/end): CUDA events around the detect/demod kernels
 	bool prof = false;
 	struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -246,6 +262,8 @@ int trxb200_init(int device, trxb200_ctx **out)
 }
 
 static void stage_free(HostStage *s);
+static void pull_scratch_free(PullScratch &w);
+static void pull_stage_free(PullStage *s);
 
 void trxb200_destroy(trxb200_ctx *ctx)
 {
@@ -253,6 +271,8 @@ void trxb200_destroy(trxb200_ctx *ctx)
 		return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stage) stage_free(ctx->stage);
+	if (ctx->pull_stage) pull_stage_free(ctx->pull_stage);
+	pull_scratch_free(ctx->pull);
 	if (ctx->d_sinc512) cudaFree(ctx->d_sinc512);
 	cudaFree(ctx->ws.corr);
 	cudaFree(ctx->ws.pwr);
@@ -531,9 +551,10 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 
 static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, int stride, int n, int32_t *rc,
 			const float *amp, const float *toa, float *ci, uint8_t *flags, float *soft, int soft_stride,
-			int n_gmsk_soft, int fix_clip)
+			int n_gmsk_soft, int fix_clip, const uint8_t *type = nullptr)
 {
 	DemodParams p;
+	p.type = type;
 	p.bursts = bursts; p.stride = stride; p.n = n; p.rc = rc; p.amp = amp; p.toa = toa; p.ci = ci; p.flags = flags;
 	p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp; p.dnsamp_g = ctx->d_comp + ctx->ht->comp.size(); p.edge_tab = ctx->d_edge_tab; p.fix_clip = fix_clip;
 	const int wpb = 8;
@@ -602,7 +623,7 @@ int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride
 	r = launch_detect(ctx, ctx->stream, ctx->ws, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp, toa,
 			  tsc_out, ci, flags, 0);
 	if (r) return r;
-	return launch_demod(ctx, ctx->stream, bursts, stride, n, rc, amp, toa, ci, flags, soft, soft_stride, n_gmsk_soft, 1);
+	return launch_demod(ctx, ctx->stream, bursts, stride, n, rc, amp, toa, ci, flags, soft, soft_stride, n_gmsk_soft, 1, type);
 }
 
 /* ---------------- host-buffer pipeline ---------------- */
@@ -679,7 +700,7 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 				  s->d_ci[slot], s->d_flags[slot], 0);
 		if (r) return r;
 		r = launch_demod(ctx, st, s->d_bursts[slot], stride, m, s->d_rc[slot], s->d_amp[slot], s->d_toa[slot],
-				 s->d_ci[slot], s->d_flags[slot], s->d_soft[slot], soft_stride, n_gmsk_soft, 1);
+				 s->d_ci[slot], s->d_flags[slot], s->d_soft[slot], soft_stride, n_gmsk_soft, 1, s->d_type[slot]);
 		if (r) return r;
 		CK(cudaMemcpyAsync(rc + lo, s->d_rc[slot], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(amp + (size_t)lo * 2, s->d_amp[slot], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
@@ -690,6 +711,188 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 		CK(cudaMemcpyAsync(soft + (size_t)lo * soft_stride, s->d_soft[slot], (size_t)m * soft_stride * 4, cudaMemcpyDeviceToHost, st));
 	}
 	for (int k = 0; k < HostStage::kSlots; k++)
+		CK(cudaStreamSynchronize(s->streams[k]));
+	return TRXB200_OK;
+}
+
+/* ---------------- pull path: int16 slots -> TRXD uplink datagrams ---------------- */
+static void pull_scratch_free(PullScratch &w)
+{
+	cudaFree(w.bursts); cudaFree(w.soft); cudaFree(w.type2); cudaFree(w.tsc_out); cudaFree(w.amp); cudaFree(w.toa);
+	cudaFree(w.ci); cudaFree(w.ws.corr); cudaFree(w.ws.pwr);
+	w = PullScratch();
+}
+
+static int pull_scratch_get(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, int cap, int soft_stride)
+{
+	if (w.cap >= cap && w.soft_stride == soft_stride) return TRXB200_OK;
+	CK(cudaStreamSynchronize(st));
+	DetectScratch keep = w.ws;
+	w.ws = DetectScratch();
+	pull_scratch_free(w);
+	w.ws = keep;
+	CK(cudaMalloc(&w.bursts, (size_t)cap * kPullStride * 8));
+	CK(cudaMalloc(&w.soft, (size_t)cap * soft_stride * 4));
+	CK(cudaMalloc(&w.type2, cap)); CK(cudaMalloc(&w.tsc_out, cap));
+	CK(cudaMalloc(&w.amp, (size_t)cap * 8)); CK(cudaMalloc(&w.toa, (size_t)cap * 4)); CK(cudaMalloc(&w.ci, (size_t)cap * 4));
+	w.cap = cap; w.soft_stride = soft_stride;
+	return TRXB200_OK;
+}
+
+static int pull_check(trxb200_ctx *ctx, const trxb200_pull_args *a)
+{
+	if (!ctx) return TRXB200_EINVAL;
+	if (!a) return fail(ctx, TRXB200_EINVAL, "pull: null argument block");
+	if (a->n == 0) return TRXB200_OK;
+	const int hdr = a->trxd_version == 1 ? 11 : 10;
+	if (a->n < 0 || !a->iq || a->stride < 625 || !a->type || !a->tsc || !a->max_toa || !a->fn || !a->tn || !a->rc || !a->energy ||
+	    !a->pkt || !a->pkt_len || (a->trxd_version != 0 && a->trxd_version != 1) || a->pkt_stride < hdr + 148 ||
+	    a->max_toa_bound < 0 || a->max_toa_bound > 1024)
+		return fail(ctx, TRXB200_EINVAL, "pull: bad argument");
+	return TRXB200_OK;
+}
+
+// soft-bit row the datagram rows can hold: 444 (8-PSK capable) or 148
+static int pull_soft_stride(const trxb200_pull_args *a)
+{
+	const int room = a->pkt_stride - (a->trxd_version == 1 ? 11 : 10);
+	return room >= 444 ? 444 : 148;
+}
+
+// m slots, all pointers on the device and already offset to the first slot of the chunk
+static int pull_chunk(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, const trxb200_pull_args *a, int m, const int16_t *iq,
+		      const uint8_t *type, const uint8_t *tsc, const uint16_t *max_toa, const uint32_t *fn, const uint8_t *tn,
+		      int32_t *rc, float *energy, uint8_t *pkt, uint16_t *pkt_len, uint8_t *flags, float *amp, float *toa, float *ci,
+		      uint8_t *tsc_out)
+{
+	IngestParams ip;
+	ip.iq = iq; ip.stride_in = a->stride; ip.n = m; ip.type = type; ip.out = w.bursts; ip.stride_out = kPullStride;
+	ip.energy = energy; ip.type_out = w.type2;
+	prof_pre(ctx, st);
+	ingest_kernel<<<std::max(1, std::min((m + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ip);
+	prof_post(ctx, st, "ingest_kernel");
+	int r = post_launch(ctx, "ingest_kernel");
+	if (r) return r;
+	if (!amp) amp = w.amp;
+	if (!toa) toa = w.toa;
+	if (!ci) ci = w.ci;
+	if (!tsc_out) tsc_out = w.tsc_out;
+	r = launch_detect(ctx, st, w.ws, w.bursts, kPullStride, m, w.type2, tsc, max_toa, a->max_toa_bound, a->thresh, rc, amp, toa,
+			  tsc_out, ci, flags, 0);
+	if (r) return r;
+	r = launch_demod(ctx, st, w.bursts, kPullStride, m, rc, amp, toa, ci, flags, w.soft, w.soft_stride, 148, 1, w.type2);
+	if (r) return r;
+	PackParams pp;
+	pp.n = m; pp.version = a->trxd_version; pp.type = type; pp.rc = rc; pp.toa = toa; pp.ci = ci; pp.energy = energy;
+	pp.tsc_out = tsc_out; pp.fn = fn; pp.tn = tn; pp.soft = w.soft; pp.soft_stride = w.soft_stride;
+	pp.full_scale = a->rx_full_scale; pp.rssi_offset = a->rssi_offset; pp.pkt = pkt; pp.pkt_stride = a->pkt_stride;
+	pp.pkt_len = pkt_len; pp.flags = flags;
+	prof_pre(ctx, st);
+	pack_kernel<<<std::max(1, std::min((m + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(pp);
+	prof_post(ctx, st, "pack_kernel");
+	return post_launch(ctx, "pack_kernel");
+}
+
+int trxb200_pull_batch(trxb200_ctx *ctx, const trxb200_pull_args *a)
+{
+	int r = pull_check(ctx, a);
+	if (r || a->n == 0) return r;
+	const int cap = 65536;
+	r = pull_scratch_get(ctx, ctx->stream, ctx->pull, std::min(cap, a->n), pull_soft_stride(a));
+	if (r) return r;
+	for (long lo = 0; lo < a->n; lo += ctx->pull.cap) {
+		const int m = (int)std::min<long>(ctx->pull.cap, a->n - lo);
+		r = pull_chunk(ctx, ctx->stream, ctx->pull, a, m, a->iq + (size_t)lo * a->stride * 2, a->type + lo, a->tsc + lo,
+			       a->max_toa + lo, a->fn + lo, a->tn + lo, a->rc + lo, a->energy + lo, a->pkt + (size_t)lo * a->pkt_stride,
+			       a->pkt_len + lo, a->flags ? a->flags + lo : nullptr, a->amp ? a->amp + (size_t)lo * 2 : nullptr,
+			       a->toa ? a->toa + lo : nullptr, a->ci ? a->ci + lo : nullptr, a->tsc_out ? a->tsc_out + lo : nullptr);
+		if (r) return r;
+	}
+	return TRXB200_OK;
+}
+
+struct PullStage {
+	static constexpr int kSlots = 3;
+	int chunk = 0, stride = 0, pkt_stride = 0;
+	cudaStream_t streams[kSlots] = {};
+	PullScratch w[kSlots];
+	int16_t *d_iq[kSlots] = {};
+	uint8_t *d_type[kSlots] = {}, *d_tsc[kSlots] = {}, *d_tn[kSlots] = {}, *d_flags[kSlots] = {}, *d_pkt[kSlots] = {};
+	uint16_t *d_max_toa[kSlots] = {}, *d_pkt_len[kSlots] = {};
+	uint32_t *d_fn[kSlots] = {};
+	int32_t *d_rc[kSlots] = {};
+	float *d_energy[kSlots] = {};
+};
+
+static void pull_stage_free(PullStage *s)
+{
+	for (int k = 0; k < PullStage::kSlots; k++) {
+		pull_scratch_free(s->w[k]);
+		cudaFree(s->d_iq[k]); cudaFree(s->d_type[k]); cudaFree(s->d_tsc[k]); cudaFree(s->d_tn[k]); cudaFree(s->d_flags[k]);
+		cudaFree(s->d_pkt[k]); cudaFree(s->d_max_toa[k]); cudaFree(s->d_pkt_len[k]); cudaFree(s->d_fn[k]); cudaFree(s->d_rc[k]);
+		cudaFree(s->d_energy[k]);
+		if (s->streams[k]) cudaStreamDestroy(s->streams[k]);
+	}
+	delete s;
+}
+
+int trxb200_pull_host(trxb200_ctx *ctx, const trxb200_pull_args *a)
+{
+	int r = pull_check(ctx, a);
+	if (r || a->n == 0) return r;
+	CK(cudaSetDevice(ctx->device));
+	const int chunk = 16384;
+	PullStage *s = ctx->pull_stage;
+	if (s && (s->stride != a->stride || s->pkt_stride != a->pkt_stride)) {
+		pull_stage_free(s);
+		ctx->pull_stage = s = nullptr;
+	}
+	if (!s) {
+		s = new PullStage();
+		s->chunk = chunk; s->stride = a->stride; s->pkt_stride = a->pkt_stride;
+		ctx->pull_stage = s;
+		for (int k = 0; k < PullStage::kSlots; k++) {
+			CK(cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking));
+			CK(cudaMalloc(&s->d_iq[k], (size_t)chunk * a->stride * 4));
+			CK(cudaMalloc(&s->d_type[k], chunk)); CK(cudaMalloc(&s->d_tsc[k], chunk)); CK(cudaMalloc(&s->d_tn[k], chunk));
+			CK(cudaMalloc(&s->d_flags[k], chunk)); CK(cudaMalloc(&s->d_pkt[k], (size_t)chunk * a->pkt_stride));
+			CK(cudaMalloc(&s->d_max_toa[k], (size_t)chunk * 2)); CK(cudaMalloc(&s->d_pkt_len[k], (size_t)chunk * 2));
+			CK(cudaMalloc(&s->d_fn[k], (size_t)chunk * 4)); CK(cudaMalloc(&s->d_rc[k], (size_t)chunk * 4));
+			CK(cudaMalloc(&s->d_energy[k], (size_t)chunk * 4));
+		}
+	}
+	const int ss = pull_soft_stride(a);
+	int slot = 0;
+	for (int lo = 0; lo < a->n; lo += chunk, slot = (slot + 1) % PullStage::kSlots) {
+		const int m = std::min(chunk, a->n - lo);
+		cudaStream_t st = s->streams[slot];
+		CK(cudaStreamSynchronize(st)); // the slot's previous chunk (incl. its D2H) has fully landed
+		r = pull_scratch_get(ctx, st, s->w[slot], chunk, ss);
+		if (r) return r;
+		PullScratch &w = s->w[slot];
+		CK(cudaMemcpyAsync(s->d_iq[slot], a->iq + (size_t)lo * a->stride * 2, (size_t)m * a->stride * 4, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(s->d_type[slot], a->type + lo, m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(s->d_tsc[slot], a->tsc + lo, m, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(s->d_max_toa[slot], a->max_toa + lo, (size_t)m * 2, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(s->d_fn[slot], a->fn + lo, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(s->d_tn[slot], a->tn + lo, m, cudaMemcpyHostToDevice, st));
+		// datagram rows of slots that emit nothing are never written by the kernels: defined as zero for host callers
+		CK(cudaMemsetAsync(s->d_pkt[slot], 0, (size_t)m * a->pkt_stride, st));
+		r = pull_chunk(ctx, st, w, a, m, s->d_iq[slot], s->d_type[slot], s->d_tsc[slot], s->d_max_toa[slot], s->d_fn[slot],
+			       s->d_tn[slot], s->d_rc[slot], s->d_energy[slot], s->d_pkt[slot], s->d_pkt_len[slot], s->d_flags[slot],
+			       nullptr, nullptr, nullptr, nullptr);
+		if (r) return r;
+		CK(cudaMemcpyAsync(a->rc + lo, s->d_rc[slot], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(a->energy + lo, s->d_energy[slot], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(a->pkt + (size_t)lo * a->pkt_stride, s->d_pkt[slot], (size_t)m * a->pkt_stride, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(a->pkt_len + lo, s->d_pkt_len[slot], (size_t)m * 2, cudaMemcpyDeviceToHost, st));
+		if (a->flags) CK(cudaMemcpyAsync(a->flags + lo, s->d_flags[slot], m, cudaMemcpyDeviceToHost, st));
+		if (a->amp) CK(cudaMemcpyAsync(a->amp + (size_t)lo * 2, w.amp, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+		if (a->toa) CK(cudaMemcpyAsync(a->toa + lo, w.toa, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+		if (a->ci) CK(cudaMemcpyAsync(a->ci + lo, w.ci, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+		if (a->tsc_out) CK(cudaMemcpyAsync(a->tsc_out + lo, w.tsc_out, m, cudaMemcpyDeviceToHost, st));
+	}
+	for (int k = 0; k < PullStage::kSlots; k++)
 		CK(cudaStreamSynchronize(s->streams[k]));
 	return TRXB200_OK;
 }

@@ -200,7 +200,7 @@ __device__ __noinline__ void demod_edge_burst(const DemodParams &p, int b, const
 			}
 		}
 		// softSliceEdgeBurst :1962-2006
-		if (i < 148) {
+		if (i < 148 && 3 * i + 2 < p.soft_stride) { // a row shorter than 444 values is never overrun
 			const float2 r1 = cmul_exact(rot, c_tab.edge_rot1);
 			float *o = p.soft + (size_t)b * p.soft_stride + 3 * i;
 			o[0] = -r1.y;
@@ -361,7 +361,7 @@ demod_kernel(DemodParams p)
 
 		if (rc <= 0) {
 			// undetected burst: only the deferred clipping report is left to do (sigProcLib.cpp:1746-1764)
-			if (p.fix_clip && rc == 0) {
+			if (p.fix_clip && rc == 0 && (!p.type || type_known(p.type[b]))) {
 				float2 v[20];
 #pragma unroll
 				for (int k = 0; k < 20; k++) {

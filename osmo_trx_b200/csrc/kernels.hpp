@@ -51,6 +51,35 @@ struct DemodParams {
 	const float *dnsamp_g; // [16] decimator taps in global memory (per-lane indexed)
 	const float2 *edge_tab; // [16] derotation (cosf,-sinf)((i%16)*3pi/8) then [9] ideal 8-PSK points k=-4..4
 	int fix_clip;
+	const uint8_t *type; // burst types as detection saw them (clip report only for types detectAnyBurst handles); may be null
+};
+
+// receive chain around the hot path (pull.cu)
+struct IngestParams {
+	const int16_t *iq; // [n][stride_in] complex int16 (I,Q)
+	int stride_in, n;
+	const uint8_t *type; // CorrType per slot as scheduled by the caller
+	float *out;	     // [n][stride_out] complex float
+	int stride_out;
+	float *energy;	   // energyDetect(burst, 80)
+	uint8_t *type_out; // type as detection must see it (OFF / IDLE -> 0)
+};
+
+struct PackParams {
+	int n, version;
+	const uint8_t *type; // caller's slot types (OFF emits nothing)
+	const int32_t *rc;
+	const float *toa, *ci, *energy;
+	const uint8_t *tsc_out;
+	const uint32_t *fn;
+	const uint8_t *tn;
+	const float *soft;
+	int soft_stride;
+	double full_scale, rssi_offset;
+	uint8_t *pkt;
+	int pkt_stride;
+	uint16_t *pkt_len;
+	uint8_t *flags; // may be null
 };
 
 } // namespace trxb200

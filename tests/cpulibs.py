@@ -176,6 +176,34 @@ class _Base:
         self.L[self.pfx + "convert_short_float"](_p(out), _p(x), C.c_int(x.size))
         return out
 
+    # --- receive chain around the hot path: int16 slots -> TRXD uplink datagrams ---
+    def pull(self, iq, type_, tsc, max_toa, fn, tn, thresh=4.0, full_scale=32767.0, rssi_offset=0.0, version=1,
+             pkt_stride=None, nthreads=1, capture=True):
+        """iq: int16 [n][stride][2].  Returns rc, energy, pkt [n][pkt_stride] u8, pkt_len, amp, toa, ci, tsc (+flags)."""
+        iq = np.ascontiguousarray(iq, np.int16)
+        n, stride = iq.shape[0], iq.shape[1]
+        type_ = np.ascontiguousarray(np.broadcast_to(type_, (n,)), np.uint8)
+        tsc = np.ascontiguousarray(np.broadcast_to(tsc, (n,)), np.uint8)
+        max_toa = np.ascontiguousarray(np.broadcast_to(max_toa, (n,)), np.uint16)
+        fn = np.ascontiguousarray(np.broadcast_to(fn, (n,)), np.uint32)
+        tn = np.ascontiguousarray(np.broadcast_to(tn, (n,)), np.uint8)
+        if pkt_stride is None:
+            pkt_stride = 11 + 444 + 2
+        r = dict(rc=np.zeros(n, np.int32), energy=np.zeros(n, np.float32), pkt=np.zeros((n, pkt_stride), np.uint8),
+                 pkt_len=np.zeros(n, np.uint16), flags=np.zeros(n, np.uint8), amp=np.zeros((n, 2), np.float32),
+                 toa=np.zeros(n, np.float32), ci=np.zeros(n, np.float32), tsc=np.zeros(n, np.uint8))
+        args = [_p(iq), C.c_int(stride), C.c_int(n), _p(type_), _p(tsc), _p(max_toa), _p(fn), _p(tn), C.c_float(thresh),
+                C.c_double(full_scale), C.c_double(rssi_offset), C.c_int(version), _p(r["rc"]), _p(r["energy"]),
+                _p(r["pkt"]), C.c_int(pkt_stride), _p(r["pkt_len"])]
+        if self.has_flags:
+            args.append(_p(r["flags"]))
+        args += [_p(r["amp"]), _p(r["toa"]), _p(r["ci"]), _p(r["tsc"])]
+        if not self.has_flags:
+            args.append(C.c_int(int(capture)))
+        args.append(C.c_int(nthreads))
+        self.L[self.pfx + "pull_batch"](*args)
+        return r
+
     # --- resampler / filterbanks ---
     def resampler(self, p, q, filt_len=16, bw=1.0):
         f = self.L[self.pfx + "resampler_create"]

@@ -71,3 +71,60 @@ def compare_soft(gpu_soft, ref_soft, mask, nsoft, what=""):
     near0 = np.abs(r) < 1e-5 * scale
     assert not (flips & ~near0).any(), f"{what}: {int((flips & ~near0).sum())} hard-bit flips away from zero"
     return dict(soft_rel_max=float(rel.max()), hard_flips=int(flips.sum()), hard_flips_near_zero=int((flips & near0).sum()))
+
+
+def compare_pkts(gpu, ref, ref_soft01=None, what="", version=1):
+    """TRXD uplink datagrams of the pull path (proto_trxd.c:27-117): gpu/ref dicts with rc, energy, pkt, pkt_len, flags.
+
+    Exact: pkt_len, tn/fn/rssi bytes, the v1 idle/modulation/tsc byte, TOA (1/256 symbol units) unless the burst
+    carries a bisection near-tie flag.  Soft bits are floats (1e-4 tolerance) quantised to 0..255: a byte may
+    differ by one LSB only where the reference's value sits within 1e-4 * 255 of a rounding boundary (checked when
+    ref_soft01, the reference's 0..1 soft values, is given); C/I in cB may differ by one unit for 8-PSK bursts
+    (computeEdgeCI is part of the demodulator, 1e-4 tolerance).  Bursts flagged THRESH_EDGE are excluded and counted.
+    """
+    n = len(ref["rc"])
+    flags = gpu.get("flags")
+    flags = np.zeros(n, np.uint8) if flags is None else flags
+    edge = (flags & 1) != 0
+    tie = (flags & 2) != 0
+    live = ~edge
+    assert np.array_equal(gpu["rc"][live], ref["rc"][live]), f"{what}: rc mismatch"
+    assert np.array_equal(gpu["energy"].view(np.uint32), ref["energy"].view(np.uint32)), f"{what}: energyDetect differs"
+    assert np.array_equal(gpu["pkt_len"][live].astype(np.int64), ref["pkt_len"][live].astype(np.int64)), f"{what}: pkt_len mismatch"
+    hdr = 11 if version == 1 else 8
+    soft_diff = 0
+    soft_total = 0
+    ci_off = 0
+    toa_off = 0
+    for b in np.nonzero(live & (ref["pkt_len"] > 0))[0]:
+        L = int(ref["pkt_len"][b])
+        g, r = gpu["pkt"][b, :L].astype(np.int64), ref["pkt"][b, :L].astype(np.int64)
+        assert np.array_equal(g[:6], r[:6]), f"{what}: burst {b} common/rssi header {g[:6]} vs {r[:6]}"
+        if not np.array_equal(g[6:8], r[6:8]):
+            assert tie[b], f"{what}: burst {b} TOA bytes differ without a near-tie flag"
+            toa_off += 1
+            continue  # a different TOA quantum moves every soft bit: counted, not compared
+        if version == 1:
+            assert g[8] == r[8], f"{what}: burst {b} v1 flags byte"
+            gc = int(np.int16((g[9] << 8) | g[10]))
+            rcb = int(np.int16((r[9] << 8) | r[10]))
+            if gc != rcb:
+                assert abs(gc - rcb) <= 1 and ref["rc"][b] == 5, f"{what}: burst {b} ci {gc} vs {rcb} cB"
+                ci_off += 1
+        nb = L - hdr - (2 if version == 0 else 0)
+        if nb > 0:
+            d = g[hdr:hdr + nb] - r[hdr:hdr + nb]
+            soft_total += nb
+            if d.any():
+                assert np.abs(d).max() <= 1, f"{what}: burst {b} soft byte off by {np.abs(d).max()}"
+                soft_diff += int((d != 0).sum())
+                if ref_soft01 is not None and not tie[b]:
+                    x = ref_soft01[b, :nb].astype(np.float64) * 255.0
+                    dist = np.abs(x - np.floor(x) - 0.5)
+                    assert (dist[d != 0] <= REL_TOL * 255.0).all(), \
+                        f"{what}: burst {b} soft byte differs away from a rounding boundary ({dist[d != 0].max()})"
+        if version == 0:
+            assert g[L - 1] == 0  # trailing NUL (proto_trxd.c:86); the byte before it is uninitialised in the reference
+    return dict(n=n, sent=int((ref["pkt_len"] > 0).sum()), detected=int((ref["rc"] > 0).sum()), thresh_edge=int(edge.sum()),
+                bisect_tie=int(tie.sum()), toa_bytes_off=toa_off, ci_cb_off_by_one=ci_off, soft_bytes=soft_total,
+                soft_bytes_off_by_one=soft_diff)

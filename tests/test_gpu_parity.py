@@ -358,3 +358,110 @@ def test_detect_config_hint(trx, checker):
     assert (g["rc"][rach] == -1).all()  # -SIGERR_BOUNDS, not a silent wrong answer
     for k in ("rc", "toa", "amp", "tsc"):
         assert np.array_equal(g[k][~rach], c[k][~rach]), k
+
+
+# ---- the receive chain around the hot path: int16 slots -> TRXD uplink datagrams ----
+def to_i16(rx, scale):
+    return np.clip(np.rint(rx * scale), -32768, 32767).astype(np.int16)
+
+
+def run_pull(trx, checker, iq, typ, tsc, max_toa, fn, tn, what, version=1, pkt_stride=160, rssi_offset=7.25):
+    n = iq.shape[0]
+    bound = int(np.max(max_toa))
+    typ = np.broadcast_to(np.asarray(typ, np.uint8), (n,)).copy()
+    mt = np.broadcast_to(np.asarray(max_toa, np.uint16), (n,)).copy()
+    out = trx.alloc_pull_results(n, pkt_stride)
+    trx.pull(dev(iq), dev(typ), dev(tsc.astype(np.uint8)), dev(mt.astype(np.int16)), dev(fn.astype(np.int32)), dev(tn), bound,
+             out=out, version=version, rssi_offset=rssi_offset)
+    torch.cuda.synchronize()
+    g = {k: v.cpu().numpy() for k, v in out.items()}
+    g["pkt_len"] = g["pkt_len"].view(np.uint16)
+    c = checker.pull(iq, typ, tsc, mt, fn, tn, version=version, rssi_offset=rssi_offset, pkt_stride=pkt_stride, nthreads=8)
+    # the reference's float soft values (0..1) for the rounding-boundary rule
+    x = iq.astype(np.float32)
+    typ_det = np.where((typ == 0) | (typ == IDLE), 0, typ).astype(np.uint8)
+    dd = checker.detect_demod(x, typ_det, tsc, mt, nthreads=8)
+    soft01 = checker.vector_slicer(dd["soft"]).reshape(dd["soft"].shape)
+    rep = parity.compare_pkts(g, c, soft01, what, version)
+    ok = (g["rc"] == c["rc"]) & (c["rc"] > 0)
+    assert np.array_equal(g["tsc"][ok], c["tsc"][ok])
+    assert np.abs(g["toa"][ok].astype(np.float64) - c["toa"][ok]).max() <= 1.0 / 256 + 1e-9
+    print(what, rep)
+    return g, c, rep
+
+
+def pull_inputs(checker, n, seed, kind="nb"):
+    rng = np.random.default_rng(seed)
+    tsc = (np.arange(n) % 8).astype(np.uint8)
+    if kind == "edge":
+        w = checker.modulate_edge_batch(synth.edge_bits(n, tsc, rng), nthreads=8)
+        rx, _ = synth.impair(w, rng, snr_db=np.choose(np.arange(n) % 3, [45.0, 25.0, 21.0]), noise_only_frac=0.05)
+    else:
+        w = checker.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng), nthreads=8)
+        rx, _ = synth.impair(w, rng, snr_db=np.choose(np.arange(n) % 3, [30.0, 10.0, 6.0]), noise_only_frac=0.05)
+    fn = rng.integers(0, 2715648, n).astype(np.uint32)
+    tn = rng.integers(0, 8, n).astype(np.uint8)
+    return rng, tsc, rx, fn, tn
+
+
+def test_pull_nb_trxd_v1(trx, checker):
+    n = 6000
+    rng, tsc, rx, fn, tn = pull_inputs(checker, n, 31)
+    iq = to_i16(rx, 8000.0)
+    iq[100:110] = to_i16(rx[100:110], 40000.0)  # saturating slots: clipping report / detection on clipped data
+    iq[200] = 0                                   # all-zero slot: energy 0, RSSI conversion corner
+    iq[300:305] = rng.integers(-32768, 32767, (5, 625, 2)).astype(np.int16)  # undetectable and clipping: -SIGERR_CLIP
+    typ = np.full(n, TSC, np.uint8)
+    typ[::37] = IDLE
+    typ[5::41] = 0  # OFF
+    g, c, rep = run_pull(trx, checker, iq, typ, tsc, 4, fn, tn, "pull nb v1")
+    assert rep["sent"] > 0.9 * n and (c["rc"] == -2).any() and (c["pkt_len"] == 0).any() and (c["pkt_len"] == 11).any()
+
+
+def test_pull_trxd_v0_and_rach(trx, checker):
+    n = 3000
+    rng = np.random.default_rng(32)
+    b = synth.ab_bits(n, 20, rng, 0)
+    w = checker.modulate_gmsk_batch(b, nthreads=8)
+    rx, _ = synth.impair(w, rng, snr_db=15.0, noise_only_frac=0.1)
+    iq = to_i16(rx, 6000.0)
+    fn = rng.integers(0, 2715648, n).astype(np.uint32)
+    tn = rng.integers(0, 8, n).astype(np.uint8)
+    typ = np.choose(np.arange(n) % 3, [RACH, EXT_RACH, RACH]).astype(np.uint8)
+    tsc = np.zeros(n, np.uint8)
+    g, c, rep = run_pull(trx, checker, iq, typ, tsc, 63, fn, tn, "pull rach v0", version=0, pkt_stride=158)
+    assert set(np.unique(c["pkt_len"])) == {0, 158}
+
+
+def test_pull_edge_and_truncated_rows(trx, checker):
+    n = 2000
+    rng, tsc, rx, fn, tn = pull_inputs(checker, n, 33, "edge")
+    iq = to_i16(rx, 8000.0)
+    g, c, rep = run_pull(trx, checker, iq, EDGE, tsc, 4, fn, tn, "pull edge v1", pkt_stride=456)
+    assert (c["pkt_len"] == 455).any()
+    # rows that cannot hold an 8-PSK burst: flagged, nothing emitted, nothing overrun
+    out = trx.alloc_pull_results(n, 160)
+    out["pkt"].fill_(0xAA)
+    trx.pull(dev(iq), dev(np.full(n, EDGE, np.uint8)), dev(tsc), dev(np.full(n, 4, np.int16)), dev(fn.astype(np.int32)), dev(tn), 4,
+             out=out)
+    torch.cuda.synchronize()
+    fl, pl, rc = out["flags"].cpu().numpy(), out["pkt_len"].cpu().numpy(), out["rc"].cpu().numpy()
+    assert ((fl & 8) != 0)[rc == 5].all() and (pl[rc == 5] == 0).all() and (out["pkt"].cpu().numpy()[rc == 5] == 0xAA).all()
+
+
+def test_pull_host_matches_device_path(trx, checker):
+    n = 40000  # > 2 chunks of the host pipeline
+    rng, tsc, rx, fn, tn = pull_inputs(checker, n, 34)
+    iq = to_i16(rx, 8000.0)
+    typ = np.full(n, TSC, np.uint8)
+    typ[::29] = IDLE
+    mt = np.full(n, 4, np.int16)
+    out = trx.alloc_pull_results(n, 160)
+    trx.pull(dev(iq), dev(typ), dev(tsc), dev(mt), dev(fn.astype(np.int32)), dev(tn), 4, out=out)
+    torch.cuda.synchronize()
+    h = {k: v.pin_memory() for k, v in trx.alloc_pull_results(n, 160, device="cpu").items()}
+    trx.pull_host(torch.from_numpy(iq).pin_memory(), torch.from_numpy(typ), torch.from_numpy(tsc), torch.from_numpy(mt),
+                  torch.from_numpy(fn.astype(np.int32)), torch.from_numpy(tn), 4, h)
+    for k in out:
+        assert np.array_equal(out[k].cpu().numpy(), h[k].numpy(), equal_nan=True), k
+    assert trx.pull(dev(iq[:0]), dev(typ[:0]), dev(tsc[:0]), dev(mt[:0]), dev(fn[:0].astype(np.int32)), dev(tn[:0]), 4) is not None

@@ -125,6 +125,46 @@ def test_oracle_vs_reference_live(oracle, ref):
         assert eqb(a[k], b[k]), k
 
 
+def _pull_same(a, b, version):
+    for k in ("rc", "energy", "pkt_len", "amp", "toa", "ci", "tsc"):
+        assert eqb(a[k], b[k]), k
+    pa, pb = a["pkt"].copy(), b["pkt"].copy()
+    if version == 0:  # the byte before the trailing NUL is uninitialised in the reference (proto_trxd.c:84-86)
+        for i in np.nonzero(a["pkt_len"])[0]:
+            pa[i, a["pkt_len"][i] - 2] = pb[i, a["pkt_len"][i] - 2] = 0
+    assert eqb(pa, pb), "datagram bytes"
+
+
+@pytest.mark.parametrize("version", [0, 1])
+def test_oracle_pull_vs_fixture(oracle, version):
+    """int16 slot -> TRXD datagram: the oracle restatement against vectors from the reference's own functions."""
+    fx = np.load(os.path.join(GOLD, "pull_fixtures.npz"))
+    o = oracle.pull(fx["iq"], fx["type"], fx["tsc"], fx["max_toa"], fx["fn"], fx["tn"], version=version,
+                    rssi_offset=float(fx["rssi_offset"]))
+    ref = {k: fx[f"v{version}/{k}"] for k in ("rc", "energy", "pkt", "pkt_len", "amp", "toa", "ci", "tsc")}
+    _pull_same(o, ref, version)
+    assert set(np.unique(ref["rc"])) >= {-2, 0, 1, 3, 5} and (ref["pkt_len"] == (455 if version else 454)).any()
+
+
+def test_oracle_pull_vs_reference_live(oracle, ref):
+    rng = np.random.default_rng(78)
+    n = 1200
+    tsc = (np.arange(n) % 8).astype(np.uint8)
+    rx, _ = synth.impair(ref.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng), nthreads=4), rng,
+                         snr_db=np.choose(np.arange(n) % 3, [30.0, 10.0, 6.0]), noise_only_frac=0.05)
+    iq = np.clip(np.rint(rx * 9000.0), -32768, 32767).astype(np.int16)
+    iq[10:20] = np.clip(np.rint(rx[10:20] * 50000.0), -32768, 32767).astype(np.int16)
+    typ = np.choose(np.arange(n) % 7, [TSC, TSC, IDLE, EDGE, RACH, EXT_RACH, 0]).astype(np.uint8)
+    mt = np.choose(np.arange(n) % 3, [0, 5, 63]).astype(np.uint16)
+    fn = rng.integers(0, 2715648, n).astype(np.uint32)
+    tn = rng.integers(0, 8, n).astype(np.uint8)
+    for version in (0, 1):
+        for off in (0.0, 61.25, -400.0):
+            a = oracle.pull(iq, typ, tsc, mt, fn, tn, version=version, rssi_offset=off, nthreads=4)
+            b = ref.pull(iq, typ, tsc, mt, fn, tn, version=version, rssi_offset=off, nthreads=4)
+            _pull_same(a, b, version)
+
+
 def test_ref_build_reproduces_convolve_test_ok():
     exe = os.path.join(ROOT, "oracle", "_ref", "convolve_test")
     ok = "/root/reference/tests/Transceiver52M/convolve_test.ok"
