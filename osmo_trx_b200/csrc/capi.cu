@@ -225,10 +225,18 @@ int trxb200_init(int device, trxb200_ctx **out)
 	cudaError_t e = cudaMemcpyToSymbol(c_tab, c, sizeof(ConstTables));
 	delete c;
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_sinc512, ctx->ht->sinc512.size() * sizeof(float));
+	// interpolation weights for peak_kernel: tap-major, columns bit-reversed (detect.cu kSinc512)
+	std::vector<float> wtab((size_t)21 * 512);
+	for (int d = 0; d < 21; d++)
+		for (int F = 0; F < 512; F++) {
+			int r = 0;
+			for (int bit = 0; bit < 9; bit++) r |= ((F >> bit) & 1) << (8 - bit);
+			wtab[(size_t)d * 512 + r] = ctx->ht->sinc512[(size_t)std::abs(512 * (d - 10) - F)];
+		}
+	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_sinc512, wtab.size() * sizeof(float));
 	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_comp, (ctx->ht->comp.size() + 16) * sizeof(float)); // + decimator taps
 	if (e == cudaSuccess)
-		e = cudaMemcpy(ctx->d_sinc512, ctx->ht->sinc512.data(), ctx->ht->sinc512.size() * sizeof(float), cudaMemcpyHostToDevice);
+		e = cudaMemcpy(ctx->d_sinc512, wtab.data(), wtab.size() * sizeof(float), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
 		e = cudaMemcpy(ctx->d_comp, ctx->ht->comp.data(), ctx->ht->comp.size() * sizeof(float), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess)
@@ -468,9 +476,12 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	const int lmax = 16 + bound;
 	const int ndmax = ctx->max_seq_len + lmax - 1; // decimated samples a correlation window needs
 	// ---- launch geometry ----
+	const bool nb = (ndmax == 35 && lmax == 20); // 16-symbol sync, max_toa <= 4: register-blocked corr_nb_kernel
 	int cw = 8; // warps per corr block
-	while (cw > 1 && corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw > 72 * 1024) cw >>= 1;
-	const size_t csmem = corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw;
+	if (!nb)
+		while (cw > 1 && corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw > 72 * 1024) cw >>= 1;
+	const size_t csmem = nb ? corr_nb_hdr_bytes() + corr_nb_warp_bytes() * cw : corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw;
+	const int cgroup = nb ? kNbGroup : kGroup;
 	int pw = 16; // warps per peak block
 	while (pw > 1 && peak_hdr_bytes() + peak_warp_bytes(lmax) * pw > 200 * 1024) pw >>= 1;
 	const size_t psmem = peak_hdr_bytes() + peak_warp_bytes(lmax) * pw;
@@ -479,13 +490,13 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	static bool configured = false;
 	if (!configured) {
 		CK(cudaFuncSetAttribute(corr_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-		CK(cudaFuncSetAttribute(corr_kernel<35>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		CK(cudaFuncSetAttribute(corr_nb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		configured = true;
 	}
-	const int cbps = (int)std::max<size_t>(1, std::min<size_t>(3, (225 * 1024) / (csmem + 1024)));
+	const int cbps = (int)std::max<size_t>(1, std::min<size_t>(nb ? 2 : 3, (225 * 1024) / (csmem + 1024)));
 	const int pbps = (int)std::max<size_t>(1, std::min<size_t>(2, (225 * 1024) / (psmem + 1024)));
-	const long corr_sweep = (long)ctx->sm_count * cbps * cw * kGroup; // bursts one full wave of corr warps covers
+	const long corr_sweep = (long)ctx->sm_count * cbps * cw * cgroup; // bursts one full wave of corr warps covers
 	const long peak_sweep = (long)ctx->sm_count * pbps * pw * 32;
 	// chunk: a whole number of sweeps of both kernels (no tail quantisation), small enough that the
 	// intermediates (lmax*8 + ndmax*4 bytes per burst) stay L2 resident
@@ -518,10 +529,10 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			c.bursts = bursts + (size_t)lo * stride * 2; c.stride = stride; c.n = m;
 			c.type = type + lo; c.tsc = tsc + lo; c.max_toa = max_toa + lo; c.rc = rc + lo; c.round = r;
 			c.max_toa_bound = bound; c.lmax = lmax; c.ndmax = ndmax; c.corr = ws.corr; c.pwr = ws.pwr; c.negzero = -0.0f;
-			const int ngroups = (m + kGroup - 1) / kGroup;
+			const int ngroups = (m + cgroup - 1) / cgroup;
 			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));
 			prof_pre(ctx, st);
-			if (ndmax == 35 && lmax == 20) corr_kernel<35><<<cgrid, cw * 32, csmem, st>>>(c);
+			if (nb) corr_nb_kernel<<<cgrid, cw * 32, csmem, st>>>(c);
 			else corr_kernel<0><<<cgrid, cw * 32, csmem, st>>>(c);
 			prof_post(ctx, st, "corr_kernel");
 			int e = post_launch(ctx, "corr_kernel");

@@ -18,8 +18,8 @@
 //            (conflict free) between zero rows, which makes the 21-tap interpolation branch free:
 //            a tap outside the reference's summation range multiplies a zero sample and adds +0.
 //            The interpolation weight of tap d at grid position F/512 is sinc(pi*|d-10-F/512|), i.e.
-//            one entry of the table-sinc folded onto the 1/512 grid (sinc512, 22 KB in shared
-//            memory): two per-lane base pointers per step, immediate offsets per tap.
+//            one entry of the table-sinc folded onto the 1/512 grid (43 KB in shared memory, tap-major
+//            with bit-reversed columns): one per-lane base pointer per step, immediate offsets per tap.
 // Multi-attempt types (EDGE -> TSC fall-through :1933-1941, EXT_RACH's three sequences :1793-1800)
 // run further rounds of the two kernels; only bursts still undetected take part.
 #include "device_tables.cuh"
@@ -361,11 +361,209 @@ corr_kernel(CorrParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// corr_nb_kernel — corr_kernel for the common configuration (16-symbol sync sequence, correlation length <= 20:
+// normal / EDGE / dummy bursts at max_toa <= 4), register blocked so that the shared-memory data pipe, which
+// bounds the generic kernel, carries each staged sample once per FOUR decimated outputs and each decimated
+// sample once per FIVE correlation outputs.  Same arithmetic per output (order of convolve_sse_3.c), hence the
+// same bits.
+//   warp = group of 7 bursts.
+//   stage     152 samples per burst as 76 16-byte slots; slot sl lives in plane sl & 7 at index sl >> 3 (plane
+//             pitch 11, burst pitch 89 slots: both the lane-consecutive staging stores and the 8-slot-strided
+//             decimation reads hit eight distinct 16-byte bank groups per quarter warp).
+//   decimate  work item = (burst, quad a): outputs 4a .. 4a+3 from slots 8a .. 8a+13 (14 LDS.128); 63 items.
+//   correlate work item = (burst, a): outputs 5a .. 5a+4 from decimated samples 5a .. 5a+19, which sit in five
+//             planes (sample j in plane j % 5 at index j / 5), and the burst's sync sequence (rows skewed by 18
+//             so that different sequences start on different banks); 28 items.
+// ---------------------------------------------------------------------------------------------
+constexpr int kNbGroup = 7;
+constexpr int kNbSlots = 76;
+constexpr int kNbPlanePitch = 11;
+constexpr int kNbRawPitch = 89;
+constexpr int kNbDecPitch = 36;
+constexpr int kNbSeqPitch = 18;
+__host__ __device__ constexpr size_t corr_nb_warp_bytes() { return (size_t)kNbGroup * kNbRawPitch * 16 + (size_t)kNbGroup * kNbDecPitch * 8; }
+__host__ __device__ constexpr size_t corr_nb_hdr_bytes()
+{
+	return (((size_t)SEQ_COUNT * kNbSeqPitch * 8 + 15) & ~(size_t)15) + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
+}
+
+__device__ __forceinline__ float2 cmul_tap(float2 xv, float2 hr, float2 hi, float2 NZ)
+{
+	const float2 p1 = mul2(xv, hr, NZ), p2 = mul2(xv, hi, NZ);
+	return add2(p1, make_float2(p2.y, p2.x));
+}
+
+__global__ void __launch_bounds__(256, 2)
+corr_nb_kernel(CorrParams p)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int wpb = blockDim.x >> 5;
+	float2 *hs = reinterpret_cast<float2 *>(smem_raw); // [SEQ_COUNT][kNbSeqPitch]
+	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + (((size_t)SEQ_COUNT * kNbSeqPitch * 8 + 15) & ~(size_t)15));
+	unsigned char *wbase = smem_raw + corr_nb_hdr_bytes() + corr_nb_warp_bytes() * warp;
+	float4 *raw = reinterpret_cast<float4 *>(wbase);			   // [kNbGroup][kNbRawPitch]
+	float2 *dec = reinterpret_cast<float2 *>(raw + kNbGroup * kNbRawPitch); // [kNbGroup][kNbDecPitch]
+
+	for (int k = threadIdx.x; k < SEQ_COUNT * 16; k += blockDim.x) {
+		const int id = k >> 4, t = k & 15;
+		if (c_tab.info[id].len == 16) hs[id * kNbSeqPitch + t] = c_tab.seq[c_tab.info[id].off + t];
+	}
+	for (int k = threadIdx.x; k < SEQ_COUNT; k += blockDim.x) sinfo[k] = c_tab.info[k];
+	__syncthreads();
+
+	const float2 NZ = bc2(p.negzero);
+	const float2 Z = make_float2(0.0f, 0.0f);
+	float g16[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++) g16[k] = c_tab.dnsamp[k];
+	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
+	const float2 *xall = reinterpret_cast<const float2 *>(p.bursts);
+
+	const int ngroups = (p.n + kNbGroup - 1) / kNbGroup;
+	for (int grp = blockIdx.x * wpb + warp; grp < ngroups; grp += gridDim.x * wpb) {
+		const int b0 = grp * kNbGroup;
+		// per-burst attempt parameters: active | start << 8 | len << 16 | seq << 24 (lanes 0..6)
+		int my_pk = 0;
+		if (lane < kNbGroup) {
+			const int b = b0 + lane;
+			if (b < p.n) {
+				const int type = p.type[b], tsc = p.tsc[b], T = p.max_toa[b];
+				const int rc_prev = p.round > 0 ? p.rc[b] : 0;
+				Attempt at;
+				if (attempt_runs(type, tsc, T, p.max_toa_bound, 35, p.round, rc_prev, sinfo, at) && sinfo[at.seq].len == 16)
+					my_pk = 1 | (at.start << 8) | (at.len << 16) | (at.seq << 24);
+			}
+		}
+		if (__ballot_sync(0xffffffffu, my_pk & 1) == 0u) continue;
+		__syncwarp();
+
+		// ---- stage: every 16-byte load of the group is issued before the first shared store ----
+		{
+			float4 ld[17];
+			int soff[17];
+#pragma unroll
+			for (int j = 0; j < 17; j++) {
+				const int flat = lane + 32 * j;
+				const int g = min(flat / kNbSlots, kNbGroup - 1);
+				const int sl = flat - kNbSlots * g;
+				const int w = __shfl_sync(0xffffffffu, my_pk, g);
+				soff[j] = -1;
+				ld[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+				if (flat < kNbGroup * kNbSlots && (w & 1)) {
+					const size_t row = (size_t)(b0 + g) * (size_t)p.stride;
+					const int s_lo = 4 * (((w >> 8) & 255) - 15) - 15;
+					const float2 *src = xall + row + (s_lo + 2 * sl);
+					const unsigned row_par = (base_par + (unsigned)(row & 1u)) & 1u;
+					if ((((unsigned)s_lo + row_par) & 1u) == 0) {
+						ld[j] = __ldg(reinterpret_cast<const float4 *>(src));
+					} else {
+						const float2 a = __ldg(src), c = __ldg(src + 1);
+						ld[j] = make_float4(a.x, a.y, c.x, c.y);
+					}
+					soff[j] = g * kNbRawPitch + (sl & 7) * kNbPlanePitch + (sl >> 3);
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < 17; j++)
+				if (soff[j] >= 0) raw[soff[j]] = ld[j];
+		}
+		__syncwarp();
+
+		// ---- decimation (sse_conv_real16 order, convolve_sse_3.c:188-264): 4 outputs per item ----
+#pragma unroll
+		for (int pass = 0; pass < 2; pass++) {
+			const int it = lane + 32 * pass;
+			const int g = min(it / 9, kNbGroup - 1);
+			const int a = it - 9 * g;
+			const int w = __shfl_sync(0xffffffffu, my_pk, g);
+			if (it < 9 * kNbGroup && (w & 1)) {
+				const float4 *r = raw + g * kNbRawPitch + a;
+				float4 s[14];
+#pragma unroll
+				for (int q = 0; q < 14; q++) s[q] = r[(q & 7) * kNbPlanePitch + (q >> 3)];
+				float2 *dg = dec + g * kNbDecPitch;
+				float *pw = p.pwr + (size_t)(b0 + g) * 35;
+#pragma unroll
+				for (int o = 0; o < 4; o++) {
+					float2 L[4];
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						// taps q, 4+q, 8+q, 12+q: sample k of the output sits in slot 2o + k/2, half k & 1
+						float2 pr[4];
+#pragma unroll
+						for (int m = 0; m < 4; m++) {
+							const int k = 4 * m + q;
+							const float4 v = s[2 * o + (k >> 1)];
+							pr[m] = mul2((k & 1) ? make_float2(v.z, v.w) : make_float2(v.x, v.y), bc2(g16[k]), NZ);
+						}
+						L[q] = add2(add2(pr[0], pr[1]), add2(pr[2], pr[3]));
+					}
+					const float2 y = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+					const int j = 4 * a + o;
+					if (j < 35) {
+						const int j5 = (j * 13) >> 6; // j / 5 for j < 64
+						dg[(j - 5 * j5) * 7 + j5] = y;
+						pw[j] = norm2(y);
+					}
+				}
+			}
+		}
+		__syncwarp();
+
+		// ---- correlation (sse_conv_cmplx_8n order, convolve_sse_3.c:462-537, h_len 16): 5 outputs per item ----
+		{
+			const int g = min(lane >> 2, kNbGroup - 1), a = lane & 3;
+			const int w = __shfl_sync(0xffffffffu, my_pk, g);
+			if (lane < 4 * kNbGroup && (w & 1)) {
+				const float2 *dx = dec + g * kNbDecPitch + a;
+				const float2 *hh = hs + ((w >> 24) & 255) * kNbSeqPitch;
+				const int len = (w >> 16) & 255;
+				float2 x[20];
+#pragma unroll
+				for (int t = 0; t < 20; t++) x[t] = dx[(t % 5) * 7 + t / 5];
+				float2 A[5], L0[5], S01[5], out[5];
+#pragma unroll
+				for (int step = 0; step < 8; step++) {
+					// tap pairs in the order (0,8) (4,12) (1,9) (5,13) (2,10) (6,14) (3,11) (7,15)
+					const int q = (step >> 1) + 4 * (step & 1);
+					const float2 h1 = hh[q], h2 = hh[q + 8];
+					const float2 h1r = bc2(h1.x), h1i = make_float2(h1.y, -h1.y);
+					const float2 h2r = bc2(h2.x), h2i = make_float2(h2.y, -h2.y);
+#pragma unroll
+					for (int o = 0; o < 5; o++) {
+						const float2 acc = add2(add2(Z, cmul_tap(x[o + q], h1r, h1i, NZ)), cmul_tap(x[o + q + 8], h2r, h2i, NZ));
+						if ((step & 1) == 0) {
+							A[o] = acc; // A[q]
+						} else {
+							const float2 Lq = add2(A[o], acc); // L[q - 4] = A[q - 4] + B[q - 4]
+							if (step == 1) L0[o] = Lq;
+							else if (step == 3) S01[o] = add2(L0[o], Lq);
+							else if (step == 5) L0[o] = Lq;
+							else out[o] = add2(S01[o], add2(L0[o], Lq));
+						}
+					}
+				}
+				float2 *co = p.corr + (size_t)(b0 + g) * 20 + 5 * a;
+#pragma unroll
+				for (int o = 0; o < 5; o++)
+					if (5 * a + o < len) co[o] = out[o];
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // peak_kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int kPadRows = 9;    // zero rows on either side of a correlation vector (interpolation reach)
 constexpr int kRowPitch = 32;  // float2 per row = one per lane: a lane's accesses stay on its own bank pair whatever the row
-constexpr int kSinc512 = 5632; // sinc512[a] = sinc(pi * a/512), a < 11*512
+// interpolation weights on the 1/512 TOA grid, tap-major with bit-reversed columns: wtab[d * 512 + brev9(F)] =
+// sinc(pi * |d - 10 - F/512|).  Bisection step k only ever visits F = odd multiples of 512 / 2^k, which in natural
+// column order all fall on ONE shared-memory bank (a 16-way conflict at k = 5); bit reversal spreads every
+// step's candidates over consecutive banks, and lanes on the same F still broadcast.
+constexpr int kSinc512 = 21 * 512;
+__device__ __forceinline__ int brev9(int F) { return (int)(__brev((unsigned)F) >> 23); }
 
 __host__ __device__ inline size_t peak_warp_bytes(int lmax) { return (size_t)(lmax + 2 * kPadRows) * kRowPitch * sizeof(float2); }
 __host__ __device__ inline size_t peak_hdr_bytes()
@@ -486,12 +684,12 @@ peak_kernel(PeakParams p)
 					const int m = (int)floorf(early);
 					const int F = (int)((early - (float)m) * 512.0f);
 					const float2 *cp = Cl + (m - 10) * kRowPitch;
-					const float *qF = stab + F, *pF = stab - F;
+					const float *wF = stab + brev9(F);
 					float2 e = make_float2(0.0f, 0.0f), l = make_float2(0.0f, 0.0f);
 					float2 v0 = cp[0], v1 = cp[kRowPitch];
 #pragma unroll
 					for (int d = 0; d < 21; d++) {
-						const float w = (d <= 10) ? qF[512 * (10 - d)] : pF[512 * (d - 10)];
+						const float w = wF[512 * d];
 						const float2 v2 = cp[(d + 2) * kRowPitch];
 						e = add2(e, mul2(v0, bc2(w), NZ));
 						l = add2(l, mul2(v2, bc2(w), NZ));
@@ -511,10 +709,10 @@ peak_kernel(PeakParams p)
 					const int m = (int)floorf(t);
 					const int F = (int)((t - (float)m) * 512.0f);
 					const float2 *cp = Cl + (m - 10) * kRowPitch;
-					const float *qF = stab + F, *pF = stab - F;
+					const float *wF = stab + brev9(F);
 #pragma unroll
 					for (int d = 0; d < 21; d++) {
-						const float w = (d <= 10) ? qF[512 * (10 - d)] : pF[512 * (d - 10)];
+						const float w = wF[512 * d];
 						xc = add2(xc, mul2(cp[d * kRowPitch], bc2(w), NZ));
 					}
 				}
