@@ -367,7 +367,7 @@ corr_kernel(CorrParams p)
 // sample once per FIVE correlation outputs.  Same arithmetic per output (order of convolve_sse_3.c), hence the
 // same bits.
 //   warp = group of 7 bursts.
-//   stage     152 samples per burst as 76 16-byte slots; slot sl lives in plane sl & 7 at index sl >> 3 (plane
+//   stage     (cp.async, one group ahead of the arithmetic) 152 samples per burst as 76 16-byte slots; slot sl lives in plane sl & 7 at index sl >> 3 (plane
 //             pitch 11, burst pitch 89 slots: both the lane-consecutive staging stores and the 8-slot-strided
 //             decimation reads hit eight distinct 16-byte bank groups per quarter warp).
 //   decimate  work item = (burst, quad a): outputs 4a .. 4a+3 from slots 8a .. 8a+13 (14 LDS.128); 63 items.
@@ -420,55 +420,83 @@ corr_nb_kernel(CorrParams p)
 	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
 	const float2 *xall = reinterpret_cast<const float2 *>(p.bursts);
 
+	// Software pipeline over the warp's groups: the window copies of the NEXT group (cp.async, global -> shared
+	// without a register round trip) are issued as soon as the decimator has consumed the current windows and land
+	// while the current group is correlated; the per-burst scalars (type, tsc, max_toa, rc) run one group further ahead.
 	const int ngroups = (p.n + kNbGroup - 1) / kNbGroup;
-	for (int grp = blockIdx.x * wpb + warp; grp < ngroups; grp += gridDim.x * wpb) {
-		const int b0 = grp * kNbGroup;
-		// per-burst attempt parameters: active | start << 8 | len << 16 | seq << 24 (lanes 0..6)
-		int my_pk = 0;
-		if (lane < kNbGroup) {
-			const int b = b0 + lane;
-			if (b < p.n) {
-				const int type = p.type[b], tsc = p.tsc[b], T = p.max_toa[b];
-				const int rc_prev = p.round > 0 ? p.rc[b] : 0;
-				Attempt at;
-				if (attempt_runs(type, tsc, T, p.max_toa_bound, 35, p.round, rc_prev, sinfo, at) && sinfo[at.seq].len == 16)
-					my_pk = 1 | (at.start << 8) | (at.len << 16) | (at.seq << 24);
-			}
-		}
-		if (__ballot_sync(0xffffffffu, my_pk & 1) == 0u) continue;
-		__syncwarp();
+	const int gstep = gridDim.x * wpb;
+	const unsigned raw_s = (unsigned)__cvta_generic_to_shared(raw) + 16u * (unsigned)((lane & 7) * kNbPlanePitch + (lane >> 3));
 
-		// ---- stage: every 16-byte load of the group is issued before the first shared store ----
-		{
-			float4 ld[17];
-			int soff[17];
+	struct Scal { int type, tsc, T, rc; };
+	auto load_scal = [&](int grp_) {
+		Scal q;
+		q.type = -1; q.tsc = 0; q.T = 0; q.rc = 0;
+		const int b = grp_ * kNbGroup + lane;
+		if (lane < kNbGroup && grp_ < ngroups && b < p.n) {
+			q.type = p.type[b]; q.tsc = p.tsc[b]; q.T = p.max_toa[b];
+			if (p.round > 0) q.rc = p.rc[b];
+		}
+		return q;
+	};
+	// per-burst attempt parameters: active | start << 8 | len << 16 | seq << 24 (lanes 0..6)
+	auto pack_scal = [&](const Scal &q) {
+		int pk = 0;
+		Attempt at;
+		if (q.type >= 0 && attempt_runs(q.type, q.tsc, q.T, p.max_toa_bound, 35, p.round, q.rc, sinfo, at) && sinfo[at.seq].len == 16)
+			pk = 1 | (at.start << 8) | (at.len << 16) | (at.seq << 24);
+		return pk;
+	};
+	// slot sl = lane + 32 * it of burst g goes to plane sl & 7, index sl >> 3: per lane a fixed shared offset plus
+	// immediates; row base, window start and alignment are warp-uniform per burst
+	auto issue_copies = [&](int grp_, int pk_) {
+		const int b0_ = grp_ * kNbGroup;
 #pragma unroll
-			for (int j = 0; j < 17; j++) {
-				const int flat = lane + 32 * j;
-				const int g = min(flat / kNbSlots, kNbGroup - 1);
-				const int sl = flat - kNbSlots * g;
-				const int w = __shfl_sync(0xffffffffu, my_pk, g);
-				soff[j] = -1;
-				ld[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-				if (flat < kNbGroup * kNbSlots && (w & 1)) {
-					const size_t row = (size_t)(b0 + g) * (size_t)p.stride;
-					const int s_lo = 4 * (((w >> 8) & 255) - 15) - 15;
-					const float2 *src = xall + row + (s_lo + 2 * sl);
-					const unsigned row_par = (base_par + (unsigned)(row & 1u)) & 1u;
-					if ((((unsigned)s_lo + row_par) & 1u) == 0) {
-						ld[j] = __ldg(reinterpret_cast<const float4 *>(src));
-					} else {
-						const float2 a = __ldg(src), c = __ldg(src + 1);
-						ld[j] = make_float4(a.x, a.y, c.x, c.y);
+		for (int g = 0; g < kNbGroup; g++) {
+			const int w = __shfl_sync(0xffffffffu, pk_, g);
+			const size_t row = (size_t)(b0_ + g) * (size_t)p.stride;
+			const int s_lo = 4 * (((w >> 8) & 255) - 15) - 15;
+			const float2 *src = xall + row + s_lo + 2 * lane;
+			const unsigned row_par = (base_par + (unsigned)(row & 1u)) & 1u;
+			const bool aligned = (((unsigned)s_lo + row_par) & 1u) == 0;
+			if (w & 1) {
+#pragma unroll
+				for (int it = 0; it < 3; it++) {
+					if (lane + 32 * it < kNbSlots) {
+						const unsigned dst = raw_s + 16u * (unsigned)(g * kNbRawPitch + 4 * it);
+						if (aligned) {
+							asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 64 * it) : "memory");
+						} else {
+							asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + 64 * it) : "memory");
+							asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u), "l"(src + 64 * it + 1) : "memory");
+						}
 					}
-					soff[j] = g * kNbRawPitch + (sl & 7) * kNbPlanePitch + (sl >> 3);
 				}
 			}
-#pragma unroll
-			for (int j = 0; j < 17; j++)
-				if (soff[j] >= 0) raw[soff[j]] = ld[j];
 		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+
+	int grp = blockIdx.x * wpb + warp;
+	int my_pk = 0;
+	Scal sc_next;
+	if (grp < ngroups) {
+		my_pk = pack_scal(load_scal(grp));
+		issue_copies(grp, my_pk);
+	}
+	sc_next = load_scal(grp + gstep);
+	for (; grp < ngroups; grp += gstep) {
+		const int b0 = grp * kNbGroup;
+		const int pk_next = pack_scal(sc_next);
+		const bool any = __ballot_sync(0xffffffffu, my_pk & 1) != 0u;
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncwarp();
+		if (!any) {
+			// nothing to do in this group: keep the pipeline moving
+			if (grp + gstep < ngroups) issue_copies(grp + gstep, pk_next);
+			sc_next = load_scal(grp + 2 * gstep);
+			my_pk = pk_next;
+			continue;
+		}
 
 		// ---- decimation (sse_conv_real16 order, convolve_sse_3.c:188-264): 4 outputs per item ----
 #pragma unroll
@@ -510,6 +538,9 @@ corr_nb_kernel(CorrParams p)
 			}
 		}
 		__syncwarp();
+		// the windows are consumed: start the next group's copies and the scalars of the one after
+		if (grp + gstep < ngroups) issue_copies(grp + gstep, pk_next);
+		sc_next = load_scal(grp + 2 * gstep);
 
 		// ---- correlation (sse_conv_cmplx_8n order, convolve_sse_3.c:462-537, h_len 16): 5 outputs per item ----
 		{
@@ -550,6 +581,7 @@ corr_nb_kernel(CorrParams p)
 					if (5 * a + o < len) co[o] = out[o];
 			}
 		}
+		my_pk = pk_next;
 	}
 }
 
@@ -610,10 +642,20 @@ peak_kernel(PeakParams p)
 			float2 *dst = C + kPadRows * kRowPitch + lane;
 			const int len = at.len;
 			if ((p.lmax & 1) == 0) {
-				for (int i = 0; i < len; i += 2) {
-					const float4 v = __ldg(reinterpret_cast<const float4 *>(src + i));
-					dst[i * kRowPitch] = make_float2(v.x, v.y);
-					dst[(i + 1) * kRowPitch] = make_float2(v.z, v.w);
+				// ten samples per round: the five 16-byte loads are in flight together (rows are lmax long, so a
+				// pair that starts inside the row ends inside it)
+				for (int i0 = 0; i0 < len; i0 += 10) {
+					float4 v[5];
+#pragma unroll
+					for (int k = 0; k < 5; k++) {
+						v[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+						if (i0 + 2 * k < len) v[k] = __ldg(reinterpret_cast<const float4 *>(src + i0 + 2 * k));
+					}
+#pragma unroll
+					for (int k = 0; k < 5; k++) {
+						if (i0 + 2 * k < len) dst[(i0 + 2 * k) * kRowPitch] = make_float2(v[k].x, v[k].y);
+						if (i0 + 2 * k + 1 < len) dst[(i0 + 2 * k + 1) * kRowPitch] = make_float2(v[k].z, v[k].w);
+					}
 				}
 			} else {
 				for (int i = 0; i < len; i++) dst[i * kRowPitch] = __ldg(&src[i]);
@@ -726,9 +768,13 @@ peak_kernel(PeakParams p)
 					// S = mean |burst[ps..ps+N)|^2, sequential (:1622-1626); pwr index j = dec index - d0 = rt + k
 					const float *pw = p.pwr + (size_t)b * p.ndmax + rt;
 					float S = 0.0f;
-#pragma unroll 8
-					for (int k = 0; k < N; k++)
-						S = fa(S, __ldg(&pw[k]));
+					for (int k0 = 0; k0 < N; k0 += 8) { // N is 16, 40 or 64; eight loads in flight, then the ordered sum
+						float v[8];
+#pragma unroll
+						for (int k = 0; k < 8; k++) v[k] = __ldg(&pw[k0 + k]);
+#pragma unroll
+						for (int k = 0; k < 8; k++) S = fa(S, v[k]);
+					}
 					S = S / (float)N;
 					const float Cn = norm2(xc) / si.ci_den;
 					ci = fm(3.0103f, log2f(Cn / fs(S, Cn)));
