@@ -66,6 +66,19 @@ struct trxb200_ctx {
 	int max_seq_len = 40; // longest sync sequence detect batches may need (sizes on-chip buffers)
 	int max_attempts = 3; // detection rounds scheduled per batch (EXT_RACH needs 3, EDGE 2, others 1)
 	DetectScratch ws;     // used by the *_batch entry points (one stream at a time)
+	// detect -> demod pipelining inside trxb200_detect_demod_batch: the demodulation of chunk i runs on a side
+	// stream while chunk i+1 is being detected (FP32-bound correlator / peak search beside the HBM-bound demod)
+	cudaStream_t side_stream = nullptr;
+	cudaEvent_t pipe_ev[4] = {};
+	int pipe_ev_next = 0;
+	struct Tune { // launch geometry; environment overrides (TRXB200_*) are read once in trxb200_init
+		// overlap: measured on B200 (tools/sweep_overlap.py, profiles/r1t_overlap_sweep.txt): every overlapped geometry is
+		// slower than the serial order (1.75-2.4 ms vs 1.71 ms per 2^20 bursts) - corr_nb_kernel and demod_kernel each
+		// need the whole register file of an SM to hide their latencies - so the pipeline is off unless asked for
+		int overlap = 0, chunk_cap = 131072;
+		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
+		int ov_corr_bps = 1, ov_peak_bps = 1, ov_peak_warps = 8, ov_demod_bps = 1; // while overlapping: leave room for the other kernel
+	} tune;
 	std::string err;
 	HostStage *stage = nullptr;
 	PullScratch pull;	      // trxb200_pull_batch
@@ -264,6 +277,33 @@ int trxb200_init(int device, trxb200_ctx **out)
 		trxb200_destroy(ctx);
 		return TRXB200_ECUDA;
 	}
+	if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess) {
+		trxb200_destroy(ctx);
+		return TRXB200_ECUDA;
+	}
+	for (auto &ev : ctx->pipe_ev)
+		if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+			trxb200_destroy(ctx);
+			return TRXB200_ECUDA;
+		}
+	{
+		auto env_int = [](const char *name, int &v) {
+			const char *e = getenv(name);
+			if (e && *e) v = atoi(e);
+		};
+		trxb200_ctx::Tune &t = ctx->tune;
+		env_int("TRXB200_OVERLAP", t.overlap);
+		env_int("TRXB200_CHUNK", t.chunk_cap);
+		env_int("TRXB200_CORR_BPS", t.corr_bps);
+		env_int("TRXB200_PEAK_BPS", t.peak_bps);
+		env_int("TRXB200_PEAK_WARPS", t.peak_warps);
+		env_int("TRXB200_DEMOD_BPS", t.demod_bps);
+		env_int("TRXB200_OV_CORR_BPS", t.ov_corr_bps);
+		env_int("TRXB200_OV_PEAK_BPS", t.ov_peak_bps);
+		env_int("TRXB200_OV_PEAK_WARPS", t.ov_peak_warps);
+		env_int("TRXB200_OV_DEMOD_BPS", t.ov_demod_bps);
+		if (t.chunk_cap < 4096) t.chunk_cap = 4096;
+	}
 	ctx->stream = ctx->own_stream;
 	*out = ctx;
 	return TRXB200_OK;
@@ -288,6 +328,9 @@ void trxb200_destroy(trxb200_ctx *ctx)
 	if (ctx->d_edge_tab) cudaFree(ctx->d_edge_tab);
 	if (ctx->d_mod_tab) cudaFree(ctx->d_mod_tab);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+	if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+	for (auto ev : ctx->pipe_ev)
+		if (ev) cudaEventDestroy(ev);
 	delete ctx->ht;
 	delete ctx;
 }
@@ -452,7 +495,7 @@ int trxb200_modulate_gmsk_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits
 	if (!ctx || !bits || !out || nbits < 2 || nbits > 156 || bits_stride < nbits || out_stride < 625 || n < 0)
 		return fail(ctx, TRXB200_EINVAL, "modulate_gmsk: bad argument");
 	if (n == 0) return TRXB200_OK;
-	modulate_gmsk_kernel<<<grid_for(ctx, n, 2, 8), 256, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride, ctx->d_mod_tab);
+	modulate_gmsk_kernel<<<grid_for(ctx, n, kModWarps, 8), kModWarps * 32, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride, ctx->d_mod_tab, -0.0f);
 	return post_launch(ctx, "modulate_gmsk_kernel");
 }
 
@@ -462,17 +505,25 @@ int trxb200_modulate_edge_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits
 	if (!ctx || !bits || !out || nbits < 3 || (nbits % 3) || bits_stride < nbits || out_stride < 625 || n < 0)
 		return fail(ctx, TRXB200_EINVAL, "modulate_edge: bad argument");
 	if (n == 0) return TRXB200_OK;
-	modulate_edge_kernel<<<grid_for(ctx, n, 2, 8), 256, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride, ctx->d_mod_tab);
+	modulate_edge_kernel<<<grid_for(ctx, n, kModWarps, 8), kModWarps * 32, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride, ctx->d_mod_tab, -0.0f);
 	return post_launch(ctx, "modulate_edge_kernel");
 }
 
 /* ---------------- detection / demodulation ---------------- */
 static int gcd_i(long a, long b) { while (b) { long t = a % b; a = b; b = t; } return (int)a; }
 
+// after_chunk (optional) is called once the detection of bursts [lo, lo + m) has been enqueued on st: the fused
+// entry point uses it to start their demodulation on the side stream.  overlapped = the launch geometry leaves
+// room on every SM for the demod kernel running beside detection.
+struct ChunkHook {
+	virtual int operator()(long lo, int m) = 0;
+};
 static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, const float *bursts, int stride, int n,
 			 const uint8_t *type, const uint8_t *tsc, const uint16_t *max_toa, int bound, float thresh, int32_t *rc,
-			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags, int scan_clip)
+			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags, int scan_clip,
+			 ChunkHook *after_chunk = nullptr, bool overlapped = false)
 {
+	const trxb200_ctx::Tune &tn = ctx->tune;
 	const int lmax = 16 + bound;
 	const int ndmax = ctx->max_seq_len + lmax - 1; // decimated samples a correlation window needs
 	// ---- launch geometry ----
@@ -482,7 +533,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 		while (cw > 1 && corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw > 72 * 1024) cw >>= 1;
 	const size_t csmem = nb ? corr_nb_hdr_bytes() + corr_nb_warp_bytes() * cw : corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw;
 	const int cgroup = nb ? kNbGroup : kGroup;
-	int pw = 16; // warps per peak block
+	int pw = std::max(1, std::min(32, overlapped ? tn.ov_peak_warps : tn.peak_warps)); // warps per peak block
 	while (pw > 1 && peak_hdr_bytes() + peak_warp_bytes(lmax) * pw > 200 * 1024) pw >>= 1;
 	const size_t psmem = peak_hdr_bytes() + peak_warp_bytes(lmax) * pw;
 	if (csmem > 227 * 1024 || psmem > 227 * 1024)
@@ -494,14 +545,17 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 		CK(cudaFuncSetAttribute(peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		configured = true;
 	}
-	const int cbps = (int)std::max<size_t>(1, std::min<size_t>(nb ? 2 : 3, (225 * 1024) / (csmem + 1024)));
-	const int pbps = (int)std::max<size_t>(1, std::min<size_t>(2, (225 * 1024) / (psmem + 1024)));
+	int cbps = (int)std::max<size_t>(1, std::min<size_t>(nb ? 2 : 3, (225 * 1024) / (csmem + 1024)));
+	int pbps = (int)std::max<size_t>(1, std::min<size_t>(2, (225 * 1024) / (psmem + 1024)));
+	const int want_c = overlapped ? tn.ov_corr_bps : tn.corr_bps, want_p = overlapped ? tn.ov_peak_bps : tn.peak_bps;
+	if (want_c > 0) cbps = std::min(cbps, want_c);
+	if (want_p > 0) pbps = std::min(pbps, want_p);
 	const long corr_sweep = (long)ctx->sm_count * cbps * cw * cgroup; // bursts one full wave of corr warps covers
 	const long peak_sweep = (long)ctx->sm_count * pbps * pw * 32;
 	// chunk: a whole number of sweeps of both kernels (no tail quantisation), small enough that the
 	// intermediates (lmax*8 + ndmax*4 bytes per burst) stay L2 resident
 	long chunk = corr_sweep / gcd_i(corr_sweep, peak_sweep) * peak_sweep;
-	const long cap = 262144;
+	const long cap = after_chunk ? tn.chunk_cap : 262144;
 	if (chunk > cap) chunk = std::max<long>(1, cap / peak_sweep) * peak_sweep;
 	else chunk *= std::max<long>(1, cap / chunk);
 	if (chunk > n) chunk = n;
@@ -550,6 +604,10 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			e = post_launch(ctx, "peak_kernel");
 			if (e) return e;
 		}
+		if (after_chunk) {
+			const int e = (*after_chunk)(lo, m);
+			if (e) return e;
+		}
 	}
 	if (scan_clip) {
 		prof_pre(ctx, st);
@@ -562,7 +620,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 
 static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, int stride, int n, int32_t *rc,
 			const float *amp, const float *toa, float *ci, uint8_t *flags, float *soft, int soft_stride,
-			int n_gmsk_soft, int fix_clip, const uint8_t *type = nullptr)
+			int n_gmsk_soft, int fix_clip, const uint8_t *type = nullptr, int bps = 0)
 {
 	DemodParams p;
 	p.type = type;
@@ -575,7 +633,8 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 		CK(cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		configured = true;
 	}
-	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * 2);
+	if (bps <= 0) bps = ctx->tune.demod_bps;
+	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * std::max(1, std::min(2, bps)));
 	if (grid < 1) grid = 1;
 	prof_pre(ctx, st);
 	demod_kernel<<<grid, wpb * 32, smem, st>>>(p);
@@ -631,10 +690,42 @@ int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride
 	    n_gmsk_soft > 156 || soft_stride < n_gmsk_soft)
 		return fail(ctx, TRXB200_EINVAL, "detect_demod: bad argument");
 	if (n == 0) return TRXB200_OK;
+	// Small batches, and the per-kernel profiling pass (which wants clean, serialised kernel times): one demod
+	// launch after detection.  Otherwise the batch is pipelined chunk by chunk over two streams.
+	if (!ctx->tune.overlap || ctx->prof || n <= ctx->tune.chunk_cap) {
+		r = launch_detect(ctx, ctx->stream, ctx->ws, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp,
+				  toa, tsc_out, ci, flags, 0);
+		if (r) return r;
+		return launch_demod(ctx, ctx->stream, bursts, stride, n, rc, amp, toa, ci, flags, soft, soft_stride, n_gmsk_soft, 1,
+				    type);
+	}
+	struct Hook : ChunkHook {
+		trxb200_ctx *ctx;
+		const float *bursts; int stride;
+		int32_t *rc; float *amp, *toa, *ci; uint8_t *flags; float *soft; int soft_stride, n_gmsk_soft;
+		const uint8_t *type;
+		int operator()(long lo, int m) override
+		{
+			cudaEvent_t ev = ctx->pipe_ev[ctx->pipe_ev_next];
+			ctx->pipe_ev_next = (ctx->pipe_ev_next + 1) & 3;
+			CK(cudaEventRecord(ev, ctx->stream));
+			CK(cudaStreamWaitEvent(ctx->side_stream, ev, 0));
+			return launch_demod(ctx, ctx->side_stream, bursts + (size_t)lo * stride * 2, stride, m, rc + lo, amp + 2 * lo,
+					    toa + lo, ci + lo, flags ? flags + lo : nullptr, soft + (size_t)lo * soft_stride, soft_stride,
+					    n_gmsk_soft, 1, type + lo, ctx->tune.ov_demod_bps);
+		}
+	} hook;
+	hook.ctx = ctx; hook.bursts = bursts; hook.stride = stride; hook.rc = rc; hook.amp = amp; hook.toa = toa; hook.ci = ci;
+	hook.flags = flags; hook.soft = soft; hook.soft_stride = soft_stride; hook.n_gmsk_soft = n_gmsk_soft; hook.type = type;
 	r = launch_detect(ctx, ctx->stream, ctx->ws, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp, toa,
-			  tsc_out, ci, flags, 0);
+			  tsc_out, ci, flags, 0, &hook, true);
 	if (r) return r;
-	return launch_demod(ctx, ctx->stream, bursts, stride, n, rc, amp, toa, ci, flags, soft, soft_stride, n_gmsk_soft, 1, type);
+	// join: everything enqueued on the caller's stream after this call sees the demodulated results
+	cudaEvent_t ev = ctx->pipe_ev[ctx->pipe_ev_next];
+	ctx->pipe_ev_next = (ctx->pipe_ev_next + 1) & 3;
+	CK(cudaEventRecord(ev, ctx->side_stream));
+	CK(cudaStreamWaitEvent(ctx->stream, ev, 0));
+	return TRXB200_OK;
 }
 
 /* ---------------- host-buffer pipeline ---------------- */

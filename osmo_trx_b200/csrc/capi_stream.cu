@@ -87,6 +87,18 @@ int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, 
 	if (in_len % r->q || out_len % r->p || in_len / r->q != out_len / r->p || out_len > 4096 * 4)
 		return fail(ctx, TRXB200_EINVAL, "resampler_rotate: block length mismatch");
 	if (n_streams == 0) return TRXB200_OK;
+	if (r->L == 16 && r->p <= 256 && r->q < 2 * r->p) {
+		// shared-memory staged, taps-in-registers kernel: P polyphase periods of one stream per tile (about 3,000
+		// input samples, so that a tile's compute phase is long against the latency of its staging loads)
+		const int P = std::max(1, std::min(4096 / r->p, 3072 / r->q));
+		const int slots = P * r->q + 15;
+		const size_t smem = (size_t)slots * sizeof(float2);
+		const long tiles = (long)n_streams * ((out_len / r->p + P - 1) / P);
+		const int grid = (int)std::max<long>(1, std::min<long>(tiles, (long)ctx->sm_count * 4));
+		resampler16_kernel<<<grid, 256, smem, ctx->stream>>>(in, in_stride, out, out_len, out_stride, n_streams, r->p, r->q, P,
+								     r->d_taps, -0.0f);
+		return post_launch(ctx, "resampler16_kernel");
+	}
 	resampler_kernel<<<grid_for(ctx, (long)n_streams * out_len, 256, 8), 256, 0, ctx->stream>>>(
 		in, in_stride, out, out_len, out_stride, n_streams, r->p, r->q, r->L, r->d_taps);
 	return post_launch(ctx, "resampler_kernel");
@@ -158,11 +170,24 @@ int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *o
 	if (fb->synth || !in || !out || n_blocks < 0) return fail(ctx, TRXB200_EINVAL, "channelizer_rotate: bad argument");
 	if (n_blocks == 0) return TRXB200_OK;
 	const long total_t = (long)n_blocks * fb->block_len;
-	const size_t smem = ((size_t)fb->m * 33 + fb->m) * sizeof(float2);
-	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(channelizer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	const int grid = (int)std::min<long>((total_t + 31) / 32, (long)ctx->sm_count * 4);
-	channelizer_kernel<<<grid, 256, smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, fb->m, fb->L, total_t, fb->d_taps, fb->d_tw);
-	int r = post_launch(ctx, "channelizer_kernel");
+	int r;
+	if (fb->m == 64 && fb->L == 16 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+		// 8 x 8 split transform + register sliding-window FIRs (filterbank.cu)
+		static bool configured = false;
+		if (!configured) {
+			CK(cudaFuncSetAttribute(channelizer64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCh64Smem));
+			configured = true;
+		}
+		const int grid = (int)std::min<long>((total_t + kFbT - 1) / kFbT, (long)ctx->sm_count * 3);
+		channelizer64_kernel<<<grid, 256, kCh64Smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		r = post_launch(ctx, "channelizer64_kernel");
+	} else {
+		const size_t smem = ((size_t)fb->m * 33 + fb->m) * sizeof(float2);
+		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(channelizer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		const int grid = (int)std::min<long>((total_t + 31) / 32, (long)ctx->sm_count * 4);
+		channelizer_kernel<<<grid, 256, smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, fb->m, fb->L, total_t, fb->d_taps, fb->d_tw);
+		r = post_launch(ctx, "channelizer_kernel");
+	}
 	if (r) return r;
 	channelizer_hist_kernel<<<(fb->m * fb->L + 127) / 128, 128, 0, ctx->stream>>>(in, fb->d_hist[fb->cur ^ 1], fb->m, fb->L, total_t);
 	fb->cur ^= 1;
@@ -176,11 +201,26 @@ int trxb200_synthesis_rotate(trxb200_filterbank *fb, const float *in, float *out
 	if (!fb->synth || !in || !out || n_blocks < 0) return fail(ctx, TRXB200_EINVAL, "synthesis_rotate: bad argument");
 	if (n_blocks == 0) return TRXB200_OK;
 	const long total_t = (long)n_blocks * fb->block_len;
-	const size_t smem = ((size_t)fb->m * 65 * 2 + fb->m) * sizeof(float2);
-	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	const int grid = (int)std::min<long>((total_t + 31) / 32, (long)ctx->sm_count * 2);
-	synthesis_kernel<<<grid, 256, smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, fb->m, fb->L, total_t, fb->d_taps, fb->d_tw);
-	int r = post_launch(ctx, "synthesis_kernel");
+	int r;
+	if (fb->m == 64 && fb->L == 16) {
+		static bool configured = false;
+		if (!configured) {
+			CK(cudaFuncSetAttribute(synthesis64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSy64Smem));
+			configured = true;
+		}
+		const long ntiles = (total_t + kFbT - 1) / kFbT;
+		const long want = std::min<long>(ntiles, (long)ctx->sm_count * 3);
+		const int per = (int)((ntiles + want - 1) / want); // consecutive tiles per CTA (the FIR halo is carried on chip)
+		const int grid = (int)((ntiles + per - 1) / per);
+		synthesis64_kernel<<<grid, 256, kSy64Smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, total_t, per, fb->d_taps, fb->d_tw);
+		r = post_launch(ctx, "synthesis64_kernel");
+	} else {
+		const size_t smem = ((size_t)fb->m * 65 * 2 + fb->m) * sizeof(float2);
+		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		const int grid = (int)std::min<long>((total_t + 31) / 32, (long)ctx->sm_count * 2);
+		synthesis_kernel<<<grid, 256, smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, fb->m, fb->L, total_t, fb->d_taps, fb->d_tw);
+		r = post_launch(ctx, "synthesis_kernel");
+	}
 	if (r) return r;
 	synthesis_tail_kernel<<<(fb->m * fb->L + 127) / 128, 128, 0, ctx->stream>>>(in, fb->d_hist[fb->cur ^ 1], fb->m, fb->L, total_t);
 	fb->cur ^= 1;

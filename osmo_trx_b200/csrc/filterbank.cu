@@ -15,6 +15,7 @@
 // input tail), then the branch FIRs, written interleaved.
 #include "device_tables.cuh"
 #include "kernels.hpp"
+#include "fft8.cuh"
 
 namespace trxb200 {
 namespace {
@@ -75,6 +76,54 @@ resampler_kernel(const float *__restrict__ in, int in_stride, float *__restrict_
 		const int n = (int)(((long)q * i) / p), path = (int)(((long)q * i) % p);
 		const float2 *x = reinterpret_cast<const float2 *>(in) + (size_t)s * in_stride + (n - (L - 1));
 		reinterpret_cast<float2 *>(out)[(size_t)s * out_stride + i] = fir_real_exact(x, parts + (size_t)path * L, L);
+	}
+}
+
+// 16-tap fast path: a CTA stages the input span of P polyphase periods of one stream in shared memory;
+// thread = (path, period group) keeps its path's 16 taps in registers for the whole kernel, walks the periods
+// of the tile and evaluates sse_conv_real16's tree on the packed FP32 pipe (exact: no contraction), so the
+// result stays bit-identical to Resampler::rotate.  Lanes walk consecutive outputs: coalesced stores, and the
+// 16 window reads of a half-warp fall into one bank sweep as long as q < 2p (decimating ratios keep the
+// one-thread-per-output kernel above, whose strided reads the L1 serves better than a bank-conflicted row).
+__global__ void __launch_bounds__(256)
+resampler16_kernel(const float *__restrict__ in, int in_stride, float *__restrict__ out, int out_len, int out_stride,
+		   int n_streams, int p, int q, int P, const float *__restrict__ parts, float negzero)
+{
+	extern __shared__ __align__(16) float2 rsm[];
+	const int tid = threadIdx.x;
+	const int G = 256 / p, rho = tid % p, grp = tid / p;
+	const bool active = grp < G;
+	const float2 nz = make_float2(negzero, negzero);
+	float h[16];
+	const int path = (int)(((long)q * rho) % p), nrel = (int)(((long)q * rho) / p);
+#pragma unroll
+	for (int k = 0; k < 16; k++) h[k] = __ldg(&parts[(size_t)path * 16 + k]);
+	const int periods_total = out_len / p;
+	const int tiles_per_stream = (periods_total + P - 1) / P;
+	const long total_tiles = (long)n_streams * tiles_per_stream;
+	for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+		const int s = (int)(tile / tiles_per_stream), per0 = (int)(tile % tiles_per_stream) * P;
+		const int np = min(P, periods_total - per0);
+		const float2 *src = reinterpret_cast<const float2 *>(in) + (size_t)s * in_stride + ((long)per0 * q - 15);
+		const int cnt = np * q + 15;
+		__syncthreads();
+		for (int idx = tid; idx < cnt; idx += 256) rsm[idx] = __ldg(&src[idx]);
+		__syncthreads();
+		if (!active) continue;
+		float2 *orow = reinterpret_cast<float2 *>(out) + (size_t)s * out_stride + (size_t)per0 * p + rho;
+		for (int per = grp; per < np; per += G) {
+			const int nb = per * q + nrel;
+			float2 L[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const float2 p0 = mul2(rsm[nb + j], bc2(h[j]), nz);
+				const float2 p1 = mul2(rsm[nb + 4 + j], bc2(h[4 + j]), nz);
+				const float2 p2 = mul2(rsm[nb + 8 + j], bc2(h[8 + j]), nz);
+				const float2 p3 = mul2(rsm[nb + 12 + j], bc2(h[12 + j]), nz);
+				L[j] = add2(add2(p0, p1), add2(p2, p3));
+			}
+			orow[(size_t)per * p] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+		}
 	}
 }
 
@@ -192,6 +241,224 @@ synthesis_kernel(const float *__restrict__ in, const float *__restrict__ tail_in
 			if (t < total_t) {
 				const float2 y = fir_real_exact(&v[r * (TW + 1) + tt], sub + (size_t)r * L, L);
 				reinterpret_cast<float2 *>(out)[t * m + r] = y;
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// M = 64, 16-tap fast paths (BASELINE config 5: 64-ARFCN wideband stream)
+// ---------------------------------------------------------------------------------------------
+// The generic kernels above evaluate the branch transform as an O(M^2) DFT (16,384 FMA per time index at
+// M = 64), which makes them FP32 bound at a few percent of the HBM roofline.  Here the transform is the
+// 8 x 8 Cooley-Tukey split of fft8.cuh (two in-register 8-point passes joined through shared memory,
+// about 1,100 lane operations per time index) and the branch FIRs run as sliding windows in registers
+// (thread = one branch x 8 consecutive time indices: 23 LDS.64 and 128 packed FMAs for 8 outputs).  The
+// branch sums pass through the transform, whose parity bar is the mathematical DFT at 1e-4 (FFTW is
+// unpinned in the reference), so FMA contraction is allowed in the FIR.
+// Tile = 32 time indices x 64 branches per CTA pass, 256 threads:
+//   FIR role   col = tid & 63 (lanes walk the wideband columns: coalesced / conflict free), g = tid >> 6
+//   FFT role   lane = time index, warp w = residue of the branch index mod 8 (pass A) / output channel mod 8 (pass B)
+// Every shared row has an odd float2 pitch, so lanes = time and lanes = branch are both conflict free.
+constexpr int kFbT = 32;		   // time indices per tile
+constexpr int kFbRows = kFbT + 15;	   // staged rows / columns incl. the 15-sample FIR halo
+constexpr int kFbPitch = kFbT + 1;	   // float2 pitch of the [64][32] transform tiles
+constexpr int kFbVPitch = kFbRows + 2;	   // float2 pitch of the synthesis FIR input rows (49)
+constexpr size_t kCh64Smem = ((size_t)kFbRows * 64 + 2 * 64 * kFbPitch) * sizeof(float2);
+constexpr size_t kSy64Smem = ((size_t)64 * kFbPitch + 64 * kFbVPitch) * sizeof(float2);
+
+__device__ __forceinline__ float2 fb_fma2(float2 a, float h, float2 c)
+{
+	unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+	float2 hh = make_float2(h, h);
+	unsigned long long rb = *reinterpret_cast<unsigned long long *>(&hh);
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+	return *reinterpret_cast<float2 *>(&rd);
+}
+
+// pass A of the 64-point transform for column `lane`: a[i] = sample of branch w + 8i  ->  z[(w*8 + k1)][lane]
+__device__ __forceinline__ void fb_pass_a(float2 (&a)[8], const float2 (&twa)[8], float2 *z, int w, int lane)
+{
+	fft8(a);
+#pragma unroll
+	for (int k1 = 0; k1 < 8; k1++)
+		z[(w * 8 + k1) * kFbPitch + lane] = k1 == 0 ? a[0] : c_mul(a[k1], twa[k1]);
+}
+
+// in: [total_t][64] wideband samples (time-major), hist_in: [64][16] previous tail per branch,
+// out: [64][total_t]
+__global__ void __launch_bounds__(256, 3)
+channelizer64_kernel(const float *__restrict__ in, const float *__restrict__ hist_in, float *__restrict__ out, long total_t,
+		     const float *__restrict__ sub, const float2 *__restrict__ tw)
+{
+	extern __shared__ __align__(16) float2 fsm[];
+	float2 *xs = fsm;			  // [47][64] wideband rows t0-15 .. t0+31
+	float2 *y = fsm + kFbRows * 64;		  // [64][33] branch FIR outputs
+	float2 *z = y + 64 * kFbPitch;		  // [64][33] pass-A outputs
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const int col = tid & 63, g = tid >> 6, r = 63 - col; // deinterleave: in[i*m + n] -> branch m-1-n (Channelizer.cpp:44-45)
+	float h[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++) h[k] = __ldg(&sub[r * 16 + k]);
+	float2 twa[8];
+#pragma unroll
+	for (int k1 = 0; k1 < 8; k1++) twa[k1] = __ldg(&tw[(w * k1) & 63]);
+	const float2 *xin = reinterpret_cast<const float2 *>(in);
+	const float2 *hin = reinterpret_cast<const float2 *>(hist_in);
+	const long ntiles = (total_t + kFbT - 1) / kFbT;
+	for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const long t0 = tile * kFbT;
+		__syncthreads(); // previous tile is done with xs
+		if (t0 >= 15 && t0 + kFbT <= total_t) {
+			// interior tile: one contiguous 24,064-byte chunk, 16-byte loads
+			const float4 *src = reinterpret_cast<const float4 *>(xin + (t0 - 15) * 64);
+			float4 *dst = reinterpret_cast<float4 *>(xs);
+			float4 v[6];
+#pragma unroll
+			for (int i = 0; i < 6; i++) {
+				const int idx = tid + 256 * i;
+				if (idx < kFbRows * 32) v[i] = __ldg(&src[idx]);
+			}
+#pragma unroll
+			for (int i = 0; i < 6; i++) {
+				const int idx = tid + 256 * i;
+				if (idx < kFbRows * 32) dst[idx] = v[i];
+			}
+		} else {
+			for (int idx = tid; idx < kFbRows * 64; idx += 256) {
+				const int row = idx >> 6, c = idx & 63;
+				const long t = t0 - 15 + row;
+				float2 v = make_float2(0.0f, 0.0f);
+				if (t < 0) v = hin[(63 - c) * 16 + (int)(16 + t)];
+				else if (t < total_t) v = __ldg(&xin[t * 64 + c]);
+				xs[idx] = v;
+			}
+		}
+		__syncthreads();
+		// ---- branch FIRs: y[r][8g + o] = sum_k xs[8g + o + k][col] * h[k] ----
+		{
+			float2 acc[8];
+#pragma unroll
+			for (int o = 0; o < 8; o++) acc[o] = make_float2(0.0f, 0.0f);
+#pragma unroll
+			for (int j = 0; j < 23; j++) {
+				const float2 x = xs[(8 * g + j) * 64 + col];
+#pragma unroll
+				for (int o = 0; o < 8; o++)
+					if (j - o >= 0 && j - o < 16) acc[o] = fb_fma2(x, h[j - o], acc[o]);
+			}
+#pragma unroll
+			for (int o = 0; o < 8; o++) y[r * kFbPitch + 8 * g + o] = acc[o];
+		}
+		__syncthreads();
+		// ---- pass A: 8-point transforms over i of branch r = w + 8i, twiddled ----
+		{
+			float2 a[8];
+#pragma unroll
+			for (int i = 0; i < 8; i++) a[i] = y[(w + 8 * i) * kFbPitch + lane];
+			fb_pass_a(a, twa, z, w, lane);
+		}
+		__syncthreads();
+		// ---- pass B: 8-point transforms over j -> channels k1 + 8*k2, k1 = w; coalesced channel rows ----
+		{
+			float2 c[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++) c[j] = z[(j * 8 + w) * kFbPitch + lane];
+			fft8(c);
+			const long t = t0 + lane;
+			if (t < total_t) {
+#pragma unroll
+				for (int k2 = 0; k2 < 8; k2++)
+					reinterpret_cast<float2 *>(out)[(size_t)(w + 8 * k2) * total_t + t] = c[k2];
+			}
+		}
+	}
+}
+
+// in: [64][total_t] per-channel samples, tail_in: [64][16] previous input tail per channel, out: [total_t][64].
+// Each CTA owns a contiguous span of tiles, so the transformed columns the FIRs reach back to (15 per
+// branch) are carried in shared memory from tile to tile; only a CTA's first tile recomputes them.
+__global__ void __launch_bounds__(256, 3)
+synthesis64_kernel(const float *__restrict__ in, const float *__restrict__ tail_in, float *__restrict__ out, long total_t,
+		   int tiles_per_cta, const float *__restrict__ sub, const float2 *__restrict__ tw)
+{
+	extern __shared__ __align__(16) float2 fsm[];
+	float2 *z = fsm;		      // [64][33] pass-A outputs
+	float2 *v = fsm + 64 * kFbPitch;      // [64][49] transformed columns t0-15 .. t0+31 per branch
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const int r = tid & 63, g = tid >> 6;
+	float h[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++) h[k] = __ldg(&sub[r * 16 + k]);
+	float2 twa[8];
+#pragma unroll
+	for (int k1 = 0; k1 < 8; k1++) twa[k1] = __ldg(&tw[(w * k1) & 63]);
+	const float2 *xin = reinterpret_cast<const float2 *>(in);
+	const float2 *tin = reinterpret_cast<const float2 *>(tail_in);
+	const long ntiles = (total_t + kFbT - 1) / kFbT;
+	const long tile_lo = (long)blockIdx.x * tiles_per_cta;
+	const long tile_hi = tile_lo + tiles_per_cta < ntiles ? tile_lo + tiles_per_cta : ntiles;
+	for (long tile = tile_lo; tile < tile_hi; tile++) {
+		const long t0 = tile * kFbT;
+		// columns to transform this pass: the halo (first tile of the span) and then the tile itself
+		for (int pass = (tile == tile_lo ? 0 : 1); pass < 2; pass++) {
+			const long tb = pass ? t0 : t0 - 32; // column `lane` <-> time tb + lane; halo pass uses lanes 17..31
+			const int vcol = pass ? 15 : -17;    // v column of lane 0
+			const long t = tb + lane;
+			float2 a[8];
+#pragma unroll
+			for (int i = 0; i < 8; i++) {
+				const int c = w + 8 * i;
+				float2 x = make_float2(0.0f, 0.0f);
+				if (t >= 0) { if (t < total_t) x = __ldg(&xin[(size_t)c * total_t + t]); }
+				else if (t >= -16) x = tin[c * 16 + (int)(16 + t)];
+				a[i] = x;
+			}
+			__syncthreads(); // z free (previous pass B done), v columns of the previous tile consumed
+			fb_pass_a(a, twa, z, w, lane);
+			__syncthreads();
+			float2 c[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++) c[j] = z[(j * 8 + w) * kFbPitch + lane];
+			fft8(c);
+			if (vcol + lane >= 0) {
+#pragma unroll
+				for (int k2 = 0; k2 < 8; k2++) v[(w + 8 * k2) * kFbVPitch + vcol + lane] = c[k2];
+			}
+		}
+		__syncthreads();
+		// ---- branch FIRs over time, written interleaved out[t*64 + r] (Synthesis.cpp:38-49) ----
+		{
+			float2 acc[8];
+#pragma unroll
+			for (int o = 0; o < 8; o++) acc[o] = make_float2(0.0f, 0.0f);
+#pragma unroll
+			for (int j = 0; j < 23; j++) {
+				const float2 x = v[r * kFbVPitch + 8 * g + j];
+#pragma unroll
+				for (int o = 0; o < 8; o++)
+					if (j - o >= 0 && j - o < 16) acc[o] = fb_fma2(x, h[j - o], acc[o]);
+			}
+#pragma unroll
+			for (int o = 0; o < 8; o++) {
+				const long t = t0 + 8 * g + o;
+				if (t < total_t) reinterpret_cast<float2 *>(out)[t * 64 + r] = acc[o];
+			}
+		}
+		__syncthreads();
+		// carry the last 15 transformed columns over as the next tile's halo
+		if (tile + 1 < tile_hi) {
+			float2 keep[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const int idx = tid + 256 * i; // 64 rows x 15 columns = 960 items
+				if (idx < 960) keep[i] = v[(idx / 15) * kFbVPitch + 32 + idx % 15];
+			}
+			__syncthreads();
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const int idx = tid + 256 * i;
+				if (idx < 960) v[(idx / 15) * kFbVPitch + idx % 15] = keep[i];
 			}
 		}
 	}

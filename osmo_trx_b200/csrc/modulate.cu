@@ -6,118 +6,148 @@
 // non-zero sample, exactly one SSE lane carries data and the reference's summation tree collapses
 // to (p_a + p_b) + (p_c + p_d) for C0 and p_a + p_b for C1 — four (two) products per output,
 // evaluated here in that order, so the waveform is bit-identical (up to the sign of exact zeros).
-// One thread per output sample, one warp-group of 160 threads... simply: block = 4 bursts x 160
-// threads would waste lanes, so a block of 256 threads walks its bursts' samples linearly and writes
-// fully coalesced float2.
+//
+// Work mapping (HBM-write bound: 148 B in, 5,000 B out per burst): one warp per burst.
+//   symbols  the burst's bits are read once (one byte per lane) and turned into five ballot words; the
+//            three bits each symbol slot needs come out of funnel shifts of those words, so the rotated
+//            symbols x[m] = rot4[4m] * nrz[m] and the C1 stream c1[m] are built with no further loads
+//            and written to a per-warp shared row (8-PSK: three byte loads per symbol, Gray map, rotation).
+//   outputs  output n = 4q + r only meets symbols m = q-3..q (C0) and q-1..q (C1) with taps 3-r+4g; lane
+//            = n mod 32 keeps r, hence its six taps, in registers for the whole kernel, reads the symbols
+//            with broadcast LDS.64 and evaluates the (re,im) pairs on the packed FP32 pipe (exact FMUL2 /
+//            FADD2, no contraction).  Each warp store instruction writes 256 contiguous bytes.
 #include "device_tables.cuh"
 #include "kernels.hpp"
 
 namespace trxb200 {
 
-__global__ void __launch_bounds__(256)
+constexpr int kModWarps = 8;
+constexpr int kModRow = 168; // symbol slots m = -3 .. 164 of one burst (index m + 3)
+
+// bit `lane + 32*i - back` of the 160-bit ballot bitmap w[0..4] (zero outside), i compile-time
+__device__ __forceinline__ unsigned mod_bit(const unsigned (&w)[5], int i, int back, int lane)
+{
+	const unsigned lo = (i >= 1 && i <= 5) ? w[i - 1] : 0u;
+	const unsigned hi = (i >= 0 && i <= 4) ? w[i] : 0u;
+	return (__funnelshift_r(lo, hi, 32 - back) >> lane) & 1u;
+}
+
+__global__ void __launch_bounds__(kModWarps * 32)
 modulate_gmsk_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_stride, int n, float *__restrict__ out,
-		     int out_stride, const float *__restrict__ mtab)
+		     int out_stride, const float *__restrict__ mtab, float negzero)
 {
 	const float2 *__restrict__ rot4 = reinterpret_cast<const float2 *>(mtab + kModRot4);
 	const float *__restrict__ pc0 = mtab + kModC0, *__restrict__ pc1 = mtab + kModC1;
-	__shared__ float sym[2][160];  // NRZ symbols incl. the two padded "0" symbols
-	__shared__ float ph1[2][160];  // C1 phase sign per symbol slot
-	for (int b0 = blockIdx.x * 2; b0 < n; b0 += gridDim.x * 2) {
-		__syncthreads();
-		for (int t = threadIdx.x; t < 2 * 160; t += blockDim.x) {
-			const int w = t / 160, m = t % 160, b = b0 + w;
-			float s = 0.0f, ph = 0.0f;
-			if (b < n && m <= nbits + 1 && 4 * m < 625) {
-				const uint8_t *bb = bits + (size_t)b * bits_stride;
-				s = (m == 0 || m == nbits + 1) ? -1.0f : (float)(2.0 * (bb[m - 1] & 1) - 1.0);
-				if (m == 2) ph = -1.0f;
-				else if (m >= 3) ph = (float)(2.0 * ((bb[m - 2] & 1) ^ (bb[m - 3] & 1)) - 1.0);
-			}
-			sym[w][m] = s;
-			ph1[w][m] = ph;
+	__shared__ float2 xs[kModWarps][kModRow];  // C0 stream: rotated NRZ symbols incl. the two padded "0" symbols
+	__shared__ float2 c1s[kModWarps][kModRow]; // C1 stream
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const float2 nz = make_float2(negzero, negzero);
+	const int r = lane & 3;
+	float t0[4], t1[2];
+#pragma unroll
+	for (int g = 0; g < 4; g++) t0[g] = __ldg(&pc0[3 - r + 4 * g]);
+#pragma unroll
+	for (int g = 0; g < 2; g++) t1[g] = __ldg(&pc1[3 - r + 4 * g]);
+	// the rotator at the symbol instants this lane builds (slot j = lane + 32*i, m = j - 3)
+	float2 rt[6];
+#pragma unroll
+	for (int i = 0; i < 6; i++) {
+		const int m = lane + 32 * i - 3;
+		rt[i] = (m >= 0 && 4 * m < 625) ? __ldg(&rot4[4 * m]) : make_float2(0.0f, 0.0f);
+	}
+	float2 *xw = xs[warp], *cw = c1s[warp];
+	for (int b = blockIdx.x * kModWarps + warp; b < n; b += gridDim.x * kModWarps) {
+		const uint8_t *bb = bits + (size_t)b * bits_stride;
+		unsigned w[5];
+#pragma unroll
+		for (int i = 0; i < 5; i++) {
+			const int k = lane + 32 * i;
+			w[i] = __ballot_sync(0xffffffffu, k < nbits && (bb[k] & 1));
 		}
-		__syncthreads();
-		for (int t = threadIdx.x; t < 2 * 625; t += blockDim.x) {
-			const int w = t / 625, nn = t % 625, b = b0 + w;
-			if (b >= n) break;
-			const int js = (15 - nn) & 3;
-			// C0: samples 4m = nn-15+k, k = js + 4g
-			float pr[4], pi[4];
+		__syncwarp(); // the previous burst's output pass is done with the rows
 #pragma unroll
-			for (int g = 0; g < 4; g++) {
-				const int k = js + 4 * g, idx = nn - 15 + k, m = idx >> 2;
-				float xr = 0.0f, xi = 0.0f;
-				if (idx >= 0 && m < 160) {
-					const float2 r = __ldg(&rot4[idx]);
-					xr = fm(r.x, sym[w][m]);
-					xi = fm(r.y, sym[w][m]);
+		for (int i = 0; i < 6; i++) {
+			const int j = lane + 32 * i, m = j - 3;
+			if (j < kModRow) {
+				// bits m-1, m-2, m-3  <->  bitmap index j - 4, j - 5, j - 6
+				const unsigned b1 = mod_bit(w, i, 4, lane), b2 = mod_bit(w, i, 5, lane), b3 = mod_bit(w, i, 6, lane);
+				float s = 0.0f, ph = 0.0f;
+				if (m >= 0 && m <= nbits + 1 && 4 * m < 625) {
+					s = (m == 0 || m == nbits + 1) ? -1.0f : (b1 ? 1.0f : -1.0f);
+					if (m == 2) ph = -1.0f;
+					else if (m >= 3) ph = (b2 ^ b3) ? 1.0f : -1.0f;
 				}
-				pr[g] = fm(xr, __ldg(&pc0[k]));
-				pi[g] = fm(xi, __ldg(&pc0[k]));
+				const float c0r = fm(rt[i].x, s), c0i = fm(rt[i].y, s);
+				xw[j] = make_float2(c0r, c0i);
+				cw[j] = make_float2(fs(fm(c0r, 0.0f), fm(c0i, ph)), fa(fm(c0r, ph), fm(c0i, 0.0f)));
 			}
-			float yr = fa(fa(pr[0], pr[1]), fa(pr[2], pr[3]));
-			float yi = fa(fa(pi[0], pi[1]), fa(pi[2], pi[3]));
-			// C1: samples 4m = nn-7+k, k = js + 4g, c1 = c0 * (0, ph)
-			float qr[2], qi[2];
-#pragma unroll
-			for (int g = 0; g < 2; g++) {
-				const int k = js + 4 * g, idx = nn - 7 + k, m = idx >> 2;
-				float xr = 0.0f, xi = 0.0f;
-				if (idx >= 0 && m < 160) {
-					const float2 r = __ldg(&rot4[idx]);
-					const float c0r = fm(r.x, sym[w][m]), c0i = fm(r.y, sym[w][m]);
-					const float ph = ph1[w][m];
-					xr = fs(fm(c0r, 0.0f), fm(c0i, ph));
-					xi = fa(fm(c0r, ph), fm(c0i, 0.0f));
-				}
-				qr[g] = fm(xr, __ldg(&pc1[k]));
-				qi[g] = fm(xi, __ldg(&pc1[k]));
+		}
+		__syncwarp();
+		float2 *orow = reinterpret_cast<float2 *>(out) + (size_t)b * out_stride;
+#pragma unroll 4
+		for (int i = 0; i < 20; i++) {
+			const int nn = lane + 32 * i;
+			if (nn < 625) {
+				const int q = nn >> 2; // symbols m = q-3+g  <->  row index q+g
+				const float2 p0 = mul2(xw[q], bc2(t0[0]), nz), p1 = mul2(xw[q + 1], bc2(t0[1]), nz);
+				const float2 p2 = mul2(xw[q + 2], bc2(t0[2]), nz), p3 = mul2(xw[q + 3], bc2(t0[3]), nz);
+				const float2 q0 = mul2(cw[q + 2], bc2(t1[0]), nz), q1 = mul2(cw[q + 3], bc2(t1[1]), nz);
+				orow[nn] = add2(add2(add2(p0, p1), add2(p2, p3)), add2(q0, q1));
 			}
-			yr = fa(yr, fa(qr[0], qr[1]));
-			yi = fa(yi, fa(qi[0], qi[1]));
-			reinterpret_cast<float2 *>(out)[(size_t)b * out_stride + nn] = make_float2(yr, yi);
 		}
 	}
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kModWarps * 32)
 modulate_edge_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_stride, int n, float *__restrict__ out,
-		     int out_stride, const float *__restrict__ mtab)
+		     int out_stride, const float *__restrict__ mtab, float negzero)
 {
 	const float *__restrict__ pc0 = mtab + kModC0;
 	const float2 *__restrict__ erot = reinterpret_cast<const float2 *>(mtab + kModEdgeRot);
 	const float2 *__restrict__ psk8 = reinterpret_cast<const float2 *>(mtab + kModPsk8);
-	__shared__ float2 sym[2][160]; // rotated symbols at sample 4 + 4i -> slot m = i + 1
+	__shared__ float2 xs[kModWarps][kModRow]; // rotated symbols at sample 4 + 4i -> slot m = i + 1
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const float2 nz = make_float2(negzero, negzero);
+	const int r = lane & 3;
+	float t0[4];
+#pragma unroll
+	for (int g = 0; g < 4; g++) t0[g] = __ldg(&pc0[3 - r + 4 * g]);
+	float2 rt[6];
+#pragma unroll
+	for (int i = 0; i < 6; i++) {
+		const int m = lane + 32 * i - 3;
+		rt[i] = (m >= 1 && m <= 156) ? __ldg(&erot[m - 1]) : make_float2(0.0f, 0.0f);
+	}
 	int nsym = nbits / 3;
 	if (nsym * 4 > 625) nsym = 156;
-	for (int b0 = blockIdx.x * 2; b0 < n; b0 += gridDim.x * 2) {
-		__syncthreads();
-		for (int t = threadIdx.x; t < 2 * 160; t += blockDim.x) {
-			const int w = t / 160, m = t % 160, b = b0 + w;
-			float2 v = make_float2(0.0f, 0.0f);
-			if (b < n && m >= 1 && m <= nsym && 4 * m < 625) {
-				const uint8_t *bb = bits + (size_t)b * bits_stride + 3 * (m - 1);
-				const unsigned idx = (bb[0] & 1u) | ((bb[1] & 1u) << 1) | ((bb[2] & 1u) << 2);
-				v = cmul_exact(__ldg(&psk8[idx]), __ldg(&erot[m - 1]));
-			}
-			sym[w][m] = v;
-		}
-		__syncthreads();
-		for (int t = threadIdx.x; t < 2 * 625; t += blockDim.x) {
-			const int w = t / 625, nn = t % 625, b = b0 + w;
-			if (b >= n) break;
-			const int js = (15 - nn) & 3;
-			float pr[4], pi[4];
+	float2 *xw = xs[warp];
+	for (int b = blockIdx.x * kModWarps + warp; b < n; b += gridDim.x * kModWarps) {
+		const uint8_t *bb = bits + (size_t)b * bits_stride;
+		__syncwarp();
 #pragma unroll
-			for (int g = 0; g < 4; g++) {
-				const int k = js + 4 * g, idx = nn - 15 + k, m = idx >> 2;
-				float2 xv = make_float2(0.0f, 0.0f);
-				if (idx >= 0 && m < 160) xv = sym[w][m];
-				pr[g] = fm(xv.x, __ldg(&pc0[k]));
-				pi[g] = fm(xv.y, __ldg(&pc0[k]));
+		for (int i = 0; i < 6; i++) {
+			const int j = lane + 32 * i, m = j - 3;
+			if (j < kModRow) {
+				float2 v = make_float2(0.0f, 0.0f);
+				if (m >= 1 && m <= nsym && 4 * m < 625) {
+					const uint8_t *b3 = bb + 3 * (m - 1);
+					const unsigned idx = (b3[0] & 1u) | ((b3[1] & 1u) << 1) | ((b3[2] & 1u) << 2);
+					v = cmul_exact(__ldg(&psk8[idx]), rt[i]);
+				}
+				xw[j] = v;
 			}
-			reinterpret_cast<float2 *>(out)[(size_t)b * out_stride + nn] =
-				make_float2(fa(fa(pr[0], pr[1]), fa(pr[2], pr[3])), fa(fa(pi[0], pi[1]), fa(pi[2], pi[3])));
+		}
+		__syncwarp();
+		float2 *orow = reinterpret_cast<float2 *>(out) + (size_t)b * out_stride;
+#pragma unroll 4
+		for (int i = 0; i < 20; i++) {
+			const int nn = lane + 32 * i;
+			if (nn < 625) {
+				const int q = nn >> 2;
+				const float2 p0 = mul2(xw[q], bc2(t0[0]), nz), p1 = mul2(xw[q + 1], bc2(t0[1]), nz);
+				const float2 p2 = mul2(xw[q + 2], bc2(t0[2]), nz), p3 = mul2(xw[q + 3], bc2(t0[3]), nz);
+				orow[nn] = add2(add2(p0, p1), add2(p2, p3));
+			}
 		}
 	}
 }

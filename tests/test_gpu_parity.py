@@ -106,6 +106,32 @@ def test_nb_detect_demod_cfg1(trx, checker):
     assert np.array_equal(g2["soft"], g["soft"][:512, :148])
 
 
+def test_detect_demod_pipeline_same_bits(trx, checker, monkeypatch):
+    """The optional two-stream detect -> demod pipeline (TRXB200_OVERLAP=1, off by default: measured slower on B200)
+    must give the serial path's results bit for bit, chunk boundaries and undetected-burst clip reports included."""
+    import osmo_trx_b200
+    rng = np.random.default_rng(77)
+    n = 9000
+    tsc = np.arange(n) % 8
+    w = checker.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng), nthreads=8)
+    rx, _ = synth.impair(w, rng, snr_db=12.0, full_scale=20000.0, noise_only_frac=0.2)
+    rx[::9] = (rng.standard_normal((len(rx[::9]), 625, 2)) * 15000.0).astype(np.float32)  # loud noise: clip, no burst
+    ref = run_gpu_dd(trx, rx, TSC, tsc, 4, 4, n_soft=148, soft_stride=148)
+    monkeypatch.setenv("TRXB200_OVERLAP", "1")
+    monkeypatch.setenv("TRXB200_CHUNK", "4096")
+    t2 = osmo_trx_b200.Trx(0)
+    try:
+        got = run_gpu_dd(t2, rx, TSC, tsc, 4, 4, n_soft=148, soft_stride=148)
+    finally:
+        t2.close()
+    det = ref["rc"] > 0
+    assert det.sum() > 0.7 * n and (ref["rc"] < 0).any()
+    for k in ("rc", "flags"):
+        assert np.array_equal(got[k], ref[k]), k
+    for k in ("toa", "amp", "ci", "tsc", "soft"):
+        assert np.array_equal(got[k][det], ref[k][det]), k
+
+
 def test_nb_full_scale_and_clipping(trx, checker):
     rng = np.random.default_rng(5)
     n = 1024
@@ -303,12 +329,13 @@ def test_resampler(trx, checker):
     for (p, q, bw, L) in [(1, 4, 1.0, 16), (65, 48, 1.0, 16), (48, 65, 1.0, 16), (65, 96, 1.0, 16), (52, 75, 0.45, 16), (3, 2, 1.0, 8), (2, 3, 1.0, 12)]:
         rs = osmo_trx_b200.Resampler(trx, p, q, L, bw)
         hc = checker.resampler(p, q, L, bw)
-        nblk, ns = 4, 3
-        x = rng.standard_normal((ns, L + q * nblk, 2)).astype(np.float32)
-        y = rs.rotate(dev(x), p * nblk).cpu().numpy()
-        for s in range(ns):
-            rc, yr = checker.resampler_rotate(hc, x[s], L, p * nblk)
-            assert rc == p * nblk and np.array_equal(y[s], yr), (p, q, s)
+        # 4 periods (one reference block) and a long row that spans several tiles of the staged kernel
+        for nblk, ns in ((4, 3), (min(16384 // p, 2500), 2)):
+            x = rng.standard_normal((ns, L + q * nblk, 2)).astype(np.float32)
+            y = rs.rotate(dev(x), p * nblk).cpu().numpy()
+            for s in range(ns):
+                rc, yr = checker.resampler_rotate(hc, x[s], L, p * nblk)
+                assert rc == p * nblk and np.array_equal(y[s], yr), (p, q, s, nblk)
 
 
 @pytest.mark.parametrize("m", [4, 64, 5])
@@ -327,6 +354,17 @@ def test_channelizer_synthesis(trx, checker, m):
         s = sy.rotate(dev(xin)).cpu().numpy()
         sr = np.concatenate([checker.synthesis_rotate(sc, np.ascontiguousarray(xin[:, k * bl:(k + 1) * bl]), m, bl)[1] for k in range(nb)])
         assert np.abs(s - sr).max() <= 1e-4 * np.abs(sr).max(), (m, it)
+    if m == 64:
+        # one long call: more tiles than resident CTAs, so the kernels' grid-stride / carried-halo paths run
+        nb = 100
+        x = rng.standard_normal((nb * m * bl, 2)).astype(np.float32)
+        y = ch.rotate(dev(x)).cpu().numpy()
+        yr = np.concatenate([checker.channelizer_rotate(cc, x[k * m * bl:(k + 1) * m * bl], m, bl)[1] for k in range(nb)], axis=1)
+        assert np.abs(y - yr).max() <= 1e-4 * np.abs(yr).max()
+        xin = rng.standard_normal((m, nb * bl, 2)).astype(np.float32)
+        s = sy.rotate(dev(xin)).cpu().numpy()
+        sr = np.concatenate([checker.synthesis_rotate(sc, np.ascontiguousarray(xin[:, k * bl:(k + 1) * bl]), m, bl)[1] for k in range(nb)])
+        assert np.abs(s - sr).max() <= 1e-4 * np.abs(sr).max()
     # synthesis -> channelizer loopback after reset(), against the checker's own loopback
     ch.reset(); sy.reset()
     cc2, sc2 = checker.channelizer(m, bl), checker.synthesis(m, bl)

@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""sweep_overlap.py — time the bench.py step (detect+demod over 2^20 resident bursts) under different
+launch geometries of the detect -> demod pipeline (TRXB200_* environment knobs read by trxb200_init).
+
+    python tools/sweep_overlap.py [--workload nb] [--steps 30] > gpurun_out/sweep.txt
+
+One workload is generated once; every configuration gets a fresh context.  Results are checked against
+the first (serial) configuration bit for bit, so a geometry that breaks the pipeline's ordering shows up.
+"""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import osmo_trx_b200  # noqa: E402
+
+
+def run(cfg, rx, typ, tsc, mt, bound, det_cfg, steps, ref=None):
+    for k in list(os.environ):
+        if k.startswith("TRXB200_"):
+            del os.environ[k]
+    for k, v in cfg.items():
+        os.environ["TRXB200_" + k] = str(v)
+    trx = osmo_trx_b200.Trx(0)
+    trx.detect_config(*det_cfg)
+    n = rx.shape[0]
+    out = trx.alloc_results(n, 148)
+    for _ in range(3):
+        trx.detect_demod(rx, typ, tsc, mt, bound, n_gmsk_soft=148, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        trx.detect_demod(rx, typ, tsc, mt, bound, n_gmsk_soft=148, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    same = None
+    if ref is not None:
+        same = all(torch.equal(out[k], ref[k]) for k in ("rc", "toa", "amp", "ci", "tsc", "flags")) and \
+            torch.equal(out["soft"][out["rc"] > 0], ref["soft"][ref["rc"] > 0])
+    res = {k: v.clone() for k, v in out.items()} if ref is None else None
+    trx.close()
+    print(json.dumps({"cfg": cfg, "ms_per_step": round(ms, 4), "bursts_per_s": round(n / ms * 1e3, 0), "same_as_serial": same}),
+          flush=True)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="nb")
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--bursts", type=int, default=1 << 20)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    trx0 = osmo_trx_b200.Trx(0)
+    rx, typ, tsc, mt, bound = bench.make_workload(trx0, args.workload, args.bursts, seed=1000, device=dev)
+    trx0.close()
+    det_cfg = {"nb": (16, 1), "rach": (40, 1), "edge": (16, 2)}[args.workload]
+    ref = run({"OVERLAP": 0}, rx, typ, tsc, mt, bound, det_cfg, args.steps)
+    run({"OVERLAP": 0, "DEMOD_BPS": 1}, rx, typ, tsc, mt, bound, det_cfg, args.steps, ref)
+    for chunk, dbps, cbps, pw, pbps in itertools.product((65536, 131072), (1, 2), (1, 2), (8, 16), (1,)):
+        run({"OVERLAP": 1, "CHUNK": chunk, "OV_DEMOD_BPS": dbps, "OV_CORR_BPS": cbps, "OV_PEAK_WARPS": pw, "OV_PEAK_BPS": pbps},
+            rx, typ, tsc, mt, bound, det_cfg, args.steps, ref)
+
+
+if __name__ == "__main__":
+    main()
