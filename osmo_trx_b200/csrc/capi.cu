@@ -1015,7 +1015,8 @@ int trxb200_vector_slicer(trxb200_ctx *ctx, float *dst, const float *src, size_t
 {
 	if (!ctx || !dst || !src) return fail(ctx, TRXB200_EINVAL, "vector_slicer: bad argument");
 	if (len == 0) return TRXB200_OK;
-	vector_slicer_kernel<<<grid_for(ctx, (long)len, 256 * 4, 8), 256, 0, ctx->stream>>>(dst, src, len);
+	const int vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+	vector_slicer_kernel<<<grid_for(ctx, (long)len, 256 * 8, 8), 256, 0, ctx->stream>>>(dst, src, len, vec);
 	return post_launch(ctx, "vector_slicer_kernel");
 }
 
@@ -1061,7 +1062,8 @@ int trxb200_convert_float_short(trxb200_ctx *ctx, int16_t *out, const float *in,
 {
 	if (!ctx || !out || !in) return fail(ctx, TRXB200_EINVAL, "convert: bad argument");
 	if (len == 0) return TRXB200_OK;
-	convert_float_short_kernel<<<grid_for(ctx, (long)len, 1024, 8), 256, 0, ctx->stream>>>(out, in, scale, len);
+	const int vec = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(in)) & 15) == 0;
+	convert_float_short_kernel<<<grid_for(ctx, (long)len, 256 * 8, 8), 256, 0, ctx->stream>>>(out, in, scale, len, vec);
 	return post_launch(ctx, "convert_float_short_kernel");
 }
 
@@ -1069,7 +1071,8 @@ int trxb200_convert_short_float(trxb200_ctx *ctx, float *out, const int16_t *in,
 {
 	if (!ctx || !out || !in) return fail(ctx, TRXB200_EINVAL, "convert: bad argument");
 	if (len == 0) return TRXB200_OK;
-	convert_short_float_kernel<<<grid_for(ctx, (long)len, 1024, 8), 256, 0, ctx->stream>>>(out, in, len);
+	const int vec = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(in)) & 15) == 0;
+	convert_short_float_kernel<<<grid_for(ctx, (long)len, 256 * 8, 8), 256, 0, ctx->stream>>>(out, in, len, vec);
 	return post_launch(ctx, "convert_short_float_kernel");
 }
 

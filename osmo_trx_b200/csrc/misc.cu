@@ -20,14 +20,45 @@ __global__ void energy_detect_kernel(const float *__restrict__ bursts, int strid
 	energy[b] = e / (float)window;
 }
 
-// vectorSlicer (sigProcLib.cpp:546-556): 0.5*(s+1) computed in double, clamped to [0,1]
-__global__ void vector_slicer_kernel(float *__restrict__ dst, const float *__restrict__ src, size_t len)
+// vectorSlicer (sigProcLib.cpp:546-556): 0.5*(s+1) computed in double, clamped to [0,1].  The double product of
+// 0.5 and a float is exact and rounds back to the same float as the single-precision product (no flush to zero in
+// this build), and the comparisons against 1.0 / 0.0 see the same value either way, so the float form is bit-identical.
+__device__ __forceinline__ float slice1(float s)
 {
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
-		float v = (float)(0.5 * (double)fa(src[i], 1.0f));
-		if ((double)v > 1.0) v = 1.0f;
-		else if ((double)v < 0.0) v = 0.0f;
-		dst[i] = v;
+	float v = fm(0.5f, fa(s, 1.0f));
+	if (v > 1.0f) v = 1.0f;
+	else if (v < 0.0f) v = 0.0f;
+	return v;
+}
+
+// vec: both pointers 16-byte aligned -> one float4 per work item, the (len & 3) tail by block 0
+__global__ void __launch_bounds__(256)
+vector_slicer_kernel(float *dst, const float *src, size_t len, int vec)
+{
+	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+	if (!vec) {
+		for (size_t i = tid; i < len; i += nth) dst[i] = slice1(src[i]);
+		return;
+	}
+	const size_t nv = len >> 2;
+	const float4 *s4 = reinterpret_cast<const float4 *>(src);
+	float4 *d4 = reinterpret_cast<float4 *>(dst);
+	size_t i = tid;
+	for (; i + nth < nv; i += 2 * nth) {
+		float4 a = __ldcs(&s4[i]), b = __ldcs(&s4[i + nth]);
+		a.x = slice1(a.x); a.y = slice1(a.y); a.z = slice1(a.z); a.w = slice1(a.w);
+		b.x = slice1(b.x); b.y = slice1(b.y); b.z = slice1(b.z); b.w = slice1(b.w);
+		__stcs(&d4[i], a);
+		__stcs(&d4[i + nth], b);
+	}
+	if (i < nv) {
+		float4 a = __ldcs(&s4[i]);
+		a.x = slice1(a.x); a.y = slice1(a.y); a.z = slice1(a.z); a.w = slice1(a.w);
+		__stcs(&d4[i], a);
+	}
+	if (blockIdx.x == 0 && threadIdx.x < (len & 3)) {
+		const size_t k = (nv << 2) + threadIdx.x;
+		dst[k] = slice1(src[k]);
 	}
 }
 
@@ -78,21 +109,65 @@ delay_vector_kernel(const float *__restrict__ in, int stride, int len, int n, co
 
 // convert_float_short (arch/x86/convert_sse_3.c / convert_sse_4_1.c semantics: multiply, convert with
 // round-to-nearest-even, saturate to int16)
-__global__ void convert_float_short_kernel(int16_t *__restrict__ out, const float *__restrict__ in, float scale, size_t len)
+__device__ __forceinline__ int f2s1(float x, float scale)
 {
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
-		const float v = fm(in[i], scale);
-		int r;
-		if (!(v == v) || v >= 2147483648.0f || v < -2147483648.0f) r = -32768;
-		else r = max(-32768, min(32767, __float2int_rn(v)));
-		out[i] = (int16_t)r;
+	const float v = fm(x, scale);
+	if (!(v == v) || v >= 2147483648.0f || v < -2147483648.0f) return -32768;
+	return max(-32768, min(32767, __float2int_rn(v)));
+}
+__device__ __forceinline__ unsigned f2s2(float a, float b, float scale)
+{
+	return ((unsigned)f2s1(a, scale) & 0xffffu) | ((unsigned)f2s1(b, scale) << 16);
+}
+
+// vec: both pointers 16-byte aligned -> eight values per work item (two 16-byte loads, one 16-byte store)
+__global__ void __launch_bounds__(256)
+convert_float_short_kernel(int16_t *__restrict__ out, const float *__restrict__ in, float scale, size_t len, int vec)
+{
+	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+	if (!vec) {
+		for (size_t i = tid; i < len; i += nth) out[i] = (int16_t)f2s1(in[i], scale);
+		return;
+	}
+	const size_t nv = len >> 3;
+	const float4 *s4 = reinterpret_cast<const float4 *>(in);
+	uint4 *d4 = reinterpret_cast<uint4 *>(out);
+	for (size_t i = tid; i < nv; i += nth) {
+		const float4 a = __ldcs(&s4[2 * i]), b = __ldcs(&s4[2 * i + 1]);
+		uint4 r;
+		r.x = f2s2(a.x, a.y, scale); r.y = f2s2(a.z, a.w, scale);
+		r.z = f2s2(b.x, b.y, scale); r.w = f2s2(b.z, b.w, scale);
+		__stcs(&d4[i], r);
+	}
+	if (blockIdx.x == 0 && threadIdx.x < (len & 7)) {
+		const size_t k = (nv << 3) + threadIdx.x;
+		out[k] = (int16_t)f2s1(in[k], scale);
 	}
 }
 
-__global__ void convert_short_float_kernel(float *__restrict__ out, const int16_t *__restrict__ in, size_t len)
+__device__ __forceinline__ float2 s2f2(unsigned w) { return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16)); }
+
+__global__ void __launch_bounds__(256)
+convert_short_float_kernel(float *__restrict__ out, const int16_t *__restrict__ in, size_t len, int vec)
 {
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x)
-		out[i] = (float)in[i];
+	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+	if (!vec) {
+		for (size_t i = tid; i < len; i += nth) out[i] = (float)in[i];
+		return;
+	}
+	const size_t nv = len >> 3;
+	const uint4 *s4 = reinterpret_cast<const uint4 *>(in);
+	float4 *d4 = reinterpret_cast<float4 *>(out);
+	for (size_t i = tid; i < nv; i += nth) {
+		const uint4 a = __ldcs(&s4[i]);
+		const float2 p0 = s2f2(a.x), p1 = s2f2(a.y), p2 = s2f2(a.z), p3 = s2f2(a.w);
+		__stcs(&d4[2 * i], make_float4(p0.x, p0.y, p1.x, p1.y));
+		__stcs(&d4[2 * i + 1], make_float4(p2.x, p2.y, p3.x, p3.y));
+	}
+	if (blockIdx.x == 0 && threadIdx.x < (len & 7)) {
+		const size_t k = (nv << 3) + threadIdx.x;
+		out[k] = (float)in[k];
+	}
 }
 
 } // namespace trxb200

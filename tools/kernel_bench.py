@@ -73,7 +73,11 @@ def main():
         t_dem = timed(lambda: trx.demod(rx, res["rc"], res["amp"], res["toa"], res["ci"], soft=res["soft"], n_gmsk_soft=148))
         add(f"demod_kernel[{kind}]", "burst", n, 5000 + soft * 4 + 16, t_dem)
         t_dd = timed(lambda: trx.detect_demod(rx, typ, tsc, mt, bound, n_gmsk_soft=148, out=res))
-        add(f"detect_demod[{kind}] fused step", "burst", n, 5000 + soft * 4 + 24, t_dd, "the bench.py step")
+        trx.profile_begin()
+        trx.detect_demod(rx, typ, tsc, mt, bound, n_gmsk_soft=148, out=res)
+        pr = trx.profile_end()
+        split = ", ".join(f"{k} {v[0]:.3f} ms/{v[1]}" for k, v in pr.items())
+        add(f"detect_demod[{kind}] fused step", "burst", n, 5000 + soft * 4 + 24, t_dd, "the bench.py step; " + split)
         if kind == "nb":
             # ---- pull path on device (8(f) rows 1-3): int16 in, TRXD out ----
             iq = (rx * bench.IQ_SCALE).round().clamp(-32768, 32767).to(torch.int16)
@@ -85,7 +89,8 @@ def main():
                 "ingest + detect + demod + pack through a float32 scratch (v1 of the chain; not yet fused)")
             # ---- helpers ----
             e_t = timed(lambda: trx.energy_detect(rx, 80))
-            add("energy_detect_kernel", "burst", n, 80 * 8 + 4, e_t, "80 samples at stride 4: sector-granular reads")
+            add("energy_detect_kernel", "burst", n, 80 * 32 + 4, e_t,
+                "80 samples at stride 4 = one 8-byte sample per 32-byte DRAM sector: bytes counted per sector (2,564 B/burst; 644 B of samples)")
             flat = res["soft"].reshape(-1)
             add("vector_slicer_kernel", "value", flat.numel(), 8, timed(lambda: trx.vector_slicer(flat)))
             xi = iq.reshape(-1)
