@@ -530,9 +530,9 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	const bool nb = (ndmax == 35 && lmax == 20); // 16-symbol sync, max_toa <= 4: register-blocked corr_nb_kernel
 	int cw = 8; // warps per corr block
 	if (!nb)
-		while (cw > 1 && corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw > 72 * 1024) cw >>= 1;
-	const size_t csmem = nb ? corr_nb_hdr_bytes() + corr_nb_warp_bytes() * cw : corr_hdr_bytes() + corr_warp_bytes(ndmax) * cw;
-	const int cgroup = nb ? kNbGroup : kGroup;
+		while (cw > 1 && corr_lg_warp_bytes(ndmax) * cw > 100 * 1024) cw >>= 1;
+	const size_t csmem = nb ? corr_nb_hdr_bytes() + corr_nb_warp_bytes() * cw : corr_lg_warp_bytes(ndmax) * cw;
+	const int cgroup = nb ? kNbGroup : 1;
 	int pw = std::max(1, std::min(32, overlapped ? tn.ov_peak_warps : tn.peak_warps)); // warps per peak block
 	while (pw > 1 && peak_hdr_bytes() + peak_warp_bytes(lmax) * pw > 200 * 1024) pw >>= 1;
 	const size_t psmem = peak_hdr_bytes() + peak_warp_bytes(lmax) * pw;
@@ -540,12 +540,12 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 		return fail(ctx, TRXB200_EINVAL, "detect: max_toa_bound too large for on-chip buffers");
 	static bool configured = false;
 	if (!configured) {
-		CK(cudaFuncSetAttribute(corr_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		CK(cudaFuncSetAttribute(corr_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(corr_nb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		configured = true;
 	}
-	int cbps = (int)std::max<size_t>(1, std::min<size_t>(nb ? 2 : 3, (225 * 1024) / (csmem + 1024)));
+	int cbps = (int)std::max<size_t>(1, std::min<size_t>(2, (225 * 1024) / (csmem + 1024)));
 	int pbps = (int)std::max<size_t>(1, std::min<size_t>(2, (225 * 1024) / (psmem + 1024)));
 	const int want_c = overlapped ? tn.ov_corr_bps : tn.corr_bps, want_p = overlapped ? tn.ov_peak_bps : tn.peak_bps;
 	if (want_c > 0) cbps = std::min(cbps, want_c);
@@ -587,7 +587,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));
 			prof_pre(ctx, st);
 			if (nb) corr_nb_kernel<<<cgrid, cw * 32, csmem, st>>>(c);
-			else corr_kernel<0><<<cgrid, cw * 32, csmem, st>>>(c);
+			else corr_long_kernel<<<cgrid, cw * 32, csmem, st>>>(c);
 			prof_post(ctx, st, "corr_kernel");
 			int e = post_launch(ctx, "corr_kernel");
 			if (e) return e;

@@ -46,9 +46,11 @@ namespace {
 
 constexpr int kPairs = 340;		 // 16-byte sample pairs (slots) in the window: samples 0 .. 679
 constexpr int kBufSlots = kPairs;	 // one window buffer (linear)
-constexpr int kScratchFloats = 2 * 164;	 // output staging + Y scratch (GMSK) / complex decimated samples (EDGE)
+constexpr int kYOff = 320;		 // float offset of the leading-edge Y scratch (float2[32]); outputs (float[156] GMSK /
+					 // float2[160] EDGE) sit below it
+constexpr int kYTopOff = kYOff + 64;	 // float offset of the trailing-edge Y scratch (float2[16])
+constexpr int kScratchFloats = kYTopOff + 64;	 // >= 444: the EDGE soft row is staged over the whole area
 constexpr int kDemodWarpFloats = 2 * 4 * kBufSlots + kScratchFloats + 4; // 2 window buffers + scratch + 2 mbarriers
-constexpr int kYOff = 192;		 // float offset of the Y scratch (float2[32]) inside the scratch area
 
 // ---- packed FP32 (sm_100 FFMA2): both halves are IEEE fma.rn ----
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
@@ -157,57 +159,72 @@ __device__ __forceinline__ float2 comp_output(const DemodParams &p, const float2
 	return d;
 }
 
-// ---- EDGE: demodEdgeBurst :2105-2128 on the staged window (complex outputs) ----
-__device__ __noinline__ void demod_edge_burst(const DemodParams &p, int b, const float2 *U, float2 *decs, float2 s, int e, int f,
-					      int whole, int lane)
+// ---- EDGE: demodEdgeBurst :2105-2128 after the decimator: decs[2 + i], i < 156, hold the scaled complex
+//      1-sps samples (the shared FIR pass below produced them) ----
+__device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2 *decs, int lane)
 {
-	for (int i = lane; i < 160; i += 32) {
-		float2 d = make_float2(0.0f, 0.0f);
-		if (i < 156) {
-			const int kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
-			const int kmax = min(15, 639 + whole - 4 * i);
-			if (kmin <= kmax) {
-				if (kmax == 15)
-					d = comp_output(p, U, i, e, f, kmin);
-				else
-					d = slow_output(U, 4 * i + e, f, kmin, kmax);
-			}
-			decs[2 + i] = cscale(d, s);
-		}
-	}
 	if (lane < 2) { decs[lane] = make_float2(0.0f, 0.0f); decs[158 + lane] = make_float2(0.0f, 0.0f); }
 	__syncwarp();
 	float err = 0.0f;
-	for (int i = lane; i < 160; i += 32) {
-		float2 rot = make_float2(0.0f, 0.0f);
-		if (i < 156) {
+	float2 rot[5];
+	float c0[5];
+#pragma unroll
+	for (int k = 0; k < 5; k++) c0[k] = c_tab.c0_inv[k];
+#pragma unroll
+	for (int r = 0; r < 5; r++) {
+		const int i = lane + 32 * r;
+		rot[r] = make_float2(0.0f, 0.0f);
+		if (i < 148) { // softSliceEdgeBurst consumes symbols 0..147 only, computeEdgeCI 8..147
 			// 5-tap static equaliser, NO_DELAY span, sequential MAC (convolve_base.c:27-60)
 			float er = 0.0f, ei = 0.0f;
 #pragma unroll
 			for (int k = 0; k < 5; k++) {
-				er = fa(er, fm(decs[i + k].x, c_tab.c0_inv[k]));
-				ei = fa(ei, fm(decs[i + k].y, c_tab.c0_inv[k]));
+				const float2 dk = decs[i + k];
+				er = fa(er, fm(dk.x, c0[k]));
+				ei = fa(ei, fm(dk.y, c0[k]));
 			}
-			rot = cmul_exact(make_float2(er, ei), p.edge_tab[i & 15]); // derotateEdgeBurst :691-711
-			if (i >= 8 && i < 148) {
-				// computeEdgeCI :2074-2093
-				const float step = 2.0f * 3.14159274f / 8.0f;
-				int k = (int)roundf(atan2f(rot.y, rot.x) / step);
-				k = min(max(k, -4), 4);
+			rot[r] = cmul_exact(make_float2(er, ei), p.edge_tab[i & 15]); // derotateEdgeBurst :691-711
+			if (i >= 8) {
+				// computeEdgeCI :2074-2093: distance to the nearest ideal 8-PSK point.  The reference picks it as
+				// round(atan2(y, x) / (pi/4)); the octant comparisons below pick the same point except within
+				// rounding of an octant boundary, where both neighbours are equally far (C/I carries 1e-4).
+				const float ax = fabsf(rot[r].x), ay = fabsf(rot[r].y);
+				const float t8 = 0.41421357f; // tan(pi/8)
+				int k;
+				if (ay <= t8 * ax) k = rot[r].x >= 0.0f ? 0 : (rot[r].y >= 0.0f ? 4 : -4);
+				else if (ax < t8 * ay) k = rot[r].y > 0.0f ? 2 : -2;
+				else k = (rot[r].x > 0.0f ? 1 : 3) * (rot[r].y > 0.0f ? 1 : -1);
 				const float2 ideal = p.edge_tab[16 + k + 4];
-				const float2 er2 = make_float2(fs(ideal.x, rot.x), fs(ideal.y, rot.y));
+				const float2 er2 = make_float2(fs(ideal.x, rot[r].x), fs(ideal.y, rot[r].y));
 				err += norm2(er2);
 			}
 		}
-		// softSliceEdgeBurst :1962-2006
-		if (i < 148 && 3 * i + 2 < p.soft_stride) { // a row shorter than 444 values is never overrun
-			const float2 r1 = cmul_exact(rot, c_tab.edge_rot1);
-			float *o = p.soft + (size_t)b * p.soft_stride + 3 * i;
-			o[0] = -r1.y;
-			o[1] = r1.x;
-			const float2 r2 = cmul_exact(make_float2(fabsf(r1.x), fabsf(r1.y)), c_tab.edge_rot2);
-			o[2] = -r2.y;
+	}
+	__syncwarp(); // every lane has read its decimated samples: the area becomes the soft-row staging buffer
+	// softSliceEdgeBurst :1962-2006
+	float *ost = reinterpret_cast<float *>(decs);
+	const float2 rot1 = c_tab.edge_rot1, rot2 = c_tab.edge_rot2;
+#pragma unroll
+	for (int r = 0; r < 5; r++) {
+		const int i = lane + 32 * r;
+		if (i < 148) {
+			const float2 r1 = cmul_exact(rot[r], rot1);
+			const float2 r2 = cmul_exact(make_float2(fabsf(r1.x), fabsf(r1.y)), rot2);
+			ost[3 * i] = -r1.y;
+			ost[3 * i + 1] = r1.x;
+			ost[3 * i + 2] = -r2.y;
 		}
+	}
+	__syncwarp();
+	const int nvals = 3 * min(148, p.soft_stride / 3); // a row shorter than 444 values is never overrun
+	float *orow = p.soft + (size_t)b * p.soft_stride;
+	if ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0 && (nvals & 3) == 0) {
+		const float4 *os4 = reinterpret_cast<const float4 *>(ost);
+		for (int j = lane; j < (nvals >> 2); j += 32)
+			reinterpret_cast<float4 *>(orow)[j] = os4[j];
+	} else {
+		for (int j = lane; j < nvals; j += 32)
+			orow[j] = ost[j];
 	}
 #pragma unroll
 	for (int o = 16; o; o >>= 1)
@@ -291,6 +308,7 @@ demod_kernel(DemodParams p)
 	float *ostage = reinterpret_cast<float *>(Ubase + 2 * 2 * kBufSlots);
 	float2 *decs = reinterpret_cast<float2 *>(ostage);
 	float2 *yv = reinterpret_cast<float2 *>(ostage + kYOff);
+	float2 *ytop = reinterpret_cast<float2 *>(ostage + kYTopOff);
 	const unsigned bar0 = smem_u32(ostage + kScratchFloats); // two 8-byte mbarriers, one per window buffer
 	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
 	const int step = gridDim.x * wpb;
@@ -396,16 +414,10 @@ demod_kernel(DemodParams p)
 		mbar_wait(bar0 + 8 * cur, (phase >> cur) & 1u);
 		phase ^= 1u << cur;
 
-		if (edge) {
-			demod_edge_burst(p, b, U, decs, s, e, f, whole, lane);
-			__syncwarp();
-			continue;
-		}
-
-		// ---- GMSK main pass (transposed FIR): lane owns window samples 20*lane .. 20*lane+19 and
-		//      accumulates into outputs i = 5*lane - 8 + m, m = 0..12; sample j meets output m with
-		//      tap u = j + 32 - 4m (0 <= u <= 35), coefficient ce[u] = comp0[f][e][u] ----
-		const int nout = p.n_gmsk_soft;
+		// ---- main pass (transposed FIR), shared by GMSK and EDGE: lane owns window samples 20*lane ..
+		//      20*lane+19 and accumulates into outputs i = 5*lane - 8 + m, m = 0..12; sample j meets output m
+		//      with tap u = j + 32 - 4m (0 <= u <= 35), coefficient ce[u] = comp0[f][e][u] ----
+		const int nout = edge ? 156 : p.n_gmsk_soft;
 		{
 			float2 acc[13];
 #pragma unroll
@@ -450,74 +462,158 @@ demod_kernel(DemodParams p)
 					fin[a] = fadd2(fin[a], t2);
 				}
 			}
-			// soft value = Re(z_i * sum), z_i = (1/amp) * (-j)^i, i = 5*lane + a  (i mod 4 = (lane + a) mod 4);
-			// lanes 30, 31 lack their right-hand neighbours: outputs >= 150 are finished by the generic path
+			// lanes 30, 31 lack their right-hand neighbours: outputs >= 150 are finished by the split pass below
 			if (lane < 30) {
-				float zx = (lane & 1) ? s.y : s.x, zy = (lane & 1) ? -s.x : s.y;
-				if (lane & 2) { zx = -zx; zy = -zy; }
+				if (!edge) {
+					// soft value = Re(z_i * sum), z_i = (1/amp) * (-j)^i, i = 5*lane + a  (i mod 4 = (lane + a) mod 4)
+					float zx = (lane & 1) ? s.y : s.x, zy = (lane & 1) ? -s.x : s.y;
+					if (lane & 2) { zx = -zx; zy = -zy; }
 #pragma unroll
-				for (int a = 0; a < 5; a++) {
-					ostage[5 * lane + a] = fmaf(zx, fin[a].x, -zy * fin[a].y);
-					const float t = zx; // z *= -j
-					zx = zy;
-					zy = -t;
+					for (int a = 0; a < 5; a++) {
+						ostage[5 * lane + a] = fmaf(zx, fin[a].x, -zy * fin[a].y);
+						const float t = zx; // z *= -j
+						zx = zy;
+						zy = -t;
+					}
+				} else {
+#pragma unroll
+					for (int a = 0; a < 5; a++) decs[2 + 5 * lane + a] = cscale(fin[a], s);
 				}
 			}
 		}
-		// leading outputs have their decimator taps truncated from below (corrected next); outputs with
-		// 4i > 624 + whole are truncated from above, outputs >= 150 lack window lanes (generic path below)
+		// ---- outputs 150 .. nout-1 (EDGE, or GMSK callers asking for all 156): 4 lanes per output, 9 taps each ----
+		if (nout > 150) {
+			const int i = 150 + (lane >> 2), part = lane & 3;
+			const float *__restrict__ c = p.comp + (size_t)f * 16 * 36;
+			float2 d = make_float2(0.0f, 0.0f);
+			if (i < nout) {
+#pragma unroll
+				for (int tt = 0; tt < 9; tt++) {
+					const int t = 9 * part + tt;
+					if (t < 35) {
+						const float ct = __ldg(&c[t]);
+						d = ffma2(win_get(U, 4 * i + t + e), make_float2(ct, ct), d);
+					}
+				}
+			}
+			d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
+			d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
+			d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
+			d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
+			if (i < nout && part == 0) {
+				if (edge) decs[2 + i] = cscale(d, s);
+				else ostage[i] = soft_out(i, d, s);
+			}
+		}
+		// The pass above is the full composite over the zero-extended window.  Where the reference's intermediate
+		// vectors are truncated the dropped terms are subtracted: leading outputs lose decimator taps k < kmin
+		// (history / samples shifted in from below), trailing ones taps k > kmax (the delayed vector ends at sample
+		// 624 before the shift: delayed samples q >= q0 = 640 + whole never reach the decimator).
 		const int nlead = min(nout, (max(15, 15 + whole) + 3) >> 2);
-		const int top = 624 + whole;
-		const int nv = 15 + max(0, whole); // delayed samples Y[v], v < nv, are what the dropped taps would read
+		const int nv = 15 + max(0, whole); // delayed samples Y[v], v < nv, are what the dropped leading taps would read
+		const int q0 = 640 + whole;
+		const bool top_trunc = q0 <= 4 * (nout - 1) + 15;
 		__syncwarp();
-		if (nv <= 32) {
-			// Y[v] = sum_j win(v + e + j) * delay[f][j]: the delayed sample decimator tap k of output i reads, v = 4i + k
-			float2 y = make_float2(0.0f, 0.0f);
+		if (nv <= 32 || top_trunc) {
+			// Y[v] = sum_j win(v + e + j) * delay[f][j]: the delayed sample decimator tap k of output i reads, v = 4i + k.
+			// Lanes evaluate v = lane (leading edge); lanes 0..15 also v = q0 + lane (trailing edge).
+			const int q0c = min(max(q0, 0), 644);
+			float2 y = make_float2(0.0f, 0.0f), yt = make_float2(0.0f, 0.0f);
 			if (f < 64) {
 #pragma unroll
 				for (int j = 0; j < 20; j++) {
 					const float hj = c_tab.delay[f][j];
-					y = ffma2(U[lane + e + j], make_float2(hj, hj), y); // w < 80: slot_phys is the identity
+					y = ffma2(U[lane + e + j], make_float2(hj, hj), y);
+				}
+				if (top_trunc && lane < 16) {
+#pragma unroll
+					for (int j = 0; j < 20; j++) {
+						const float hj = c_tab.delay[f][j];
+						yt = ffma2(U[q0c + lane + e + j], make_float2(hj, hj), yt);
+					}
 				}
 			} else {
 				y = U[lane + e + 9];
+				if (top_trunc && lane < 16) yt = U[q0c + lane + e + 9];
 			}
 			yv[lane] = y;
+			if (lane < 16) ytop[lane] = yt;
 			__syncwarp();
-			for (int base = 0; base < nlead; base += 8) {
-				const int i = base + (lane >> 2), part = lane & 3;
-				const int kmin = min(16, max(0, max(15 - 4 * i, 15 - 4 * i + whole)));
+			if (nv <= 32) {
+				for (int base = 0; base < nlead; base += 8) {
+					const int i = base + (lane >> 2), part = lane & 3;
+					const int kmin = min(16, max(0, max(15 - 4 * i, 15 - 4 * i + whole)));
+					float2 d = make_float2(0.0f, 0.0f);
+					if (i < nlead) {
+#pragma unroll
+						for (int kk = 0; kk < 4; kk++) {
+							const int k = 4 * part + kk;
+							if (k < kmin)
+								d = ffma2(yv[4 * i + k], make_float2(gk[kk], gk[kk]), d);
+						}
+					}
+					d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
+					d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
+					d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
+					d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
+					if (i < nlead && part == 0) {
+						if (edge) {
+							const float2 c2 = cscale(d, s);
+							decs[2 + i].x -= c2.x;
+							decs[2 + i].y -= c2.y;
+						} else {
+							ostage[i] -= soft_out(i, d, s);
+						}
+					}
+				}
+			}
+			if (top_trunc) {
+				// outputs whose taps reach q >= q0: at most 8 of them (Y beyond q0 + 8 is zero: the burst has ended)
+				const int i = max(0, (q0 - 12) >> 2) + (lane >> 2), part = lane & 3;
 				float2 d = make_float2(0.0f, 0.0f);
-				if (i < nlead) {
+				if (i < nout) {
 #pragma unroll
 					for (int kk = 0; kk < 4; kk++) {
-						const int k = 4 * part + kk;
-						if (k < kmin)
-							d = ffma2(yv[4 * i + k], make_float2(gk[kk], gk[kk]), d);
+						const int m = 4 * i + 4 * part + kk - q0;
+						if (m >= 0 && m < 16)
+							d = ffma2(ytop[m], make_float2(gk[kk], gk[kk]), d);
 					}
 				}
 				d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
 				d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
 				d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
 				d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
-				if (i < nlead && part == 0)
-					ostage[i] -= soft_out(i, d, s);
+				if (i < nout && part == 0) {
+					// no tap left at all (the reference's sample is an exact zero): store the zero, not a rounding residue
+					const bool none = max(0, max(15 - 4 * i, 15 - 4 * i + whole)) > min(15, 639 + whole - 4 * i);
+					if (edge) {
+						const float2 c2 = cscale(d, s);
+						decs[2 + i] = none ? make_float2(0.0f, 0.0f) : make_float2(decs[2 + i].x - c2.x, decs[2 + i].y - c2.y);
+					} else {
+						ostage[i] = none ? 0.0f : ostage[i] - soft_out(i, d, s);
+					}
+				}
 			}
 		}
-		// ---- generic per-output path (rare): outputs truncated from above (shifted burst runs past sample
-		//      624), outputs beyond the main pass (>= 150), leading outputs of very early bursts (nv > 32) ----
-		if (4 * (nout - 1) > top || nout > 150 || nv > 32) {
-			for (int i = lane; i < nout; i += 32) {
-				if (4 * i <= top && i < 150 && !(nv > 32 && i < nlead)) continue; // main pass result stands
+		// ---- generic per-output path (rare): leading outputs of very late bursts (more than 32 delayed samples
+		//      feed the dropped taps) ----
+		if (nv > 32) {
+			for (int i = lane; i < nlead; i += 32) {
 				const int kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
 				const int kmax = min(15, 639 + whole - 4 * i);
 				float2 d = make_float2(0.0f, 0.0f);
 				if (kmin <= kmax)
 					d = (kmax == 15) ? comp_output(p, U, i, e, f, kmin) : slow_output(U, 4 * i + e, f, kmin, kmax);
-				ostage[i] = soft_out(i, d, s);
+				if (edge) decs[2 + i] = cscale(d, s);
+				else ostage[i] = soft_out(i, d, s);
 			}
 		}
 		__syncwarp();
+		if (edge) {
+			demod_edge_tail(p, b, decs, lane);
+			__syncwarp();
+			continue;
+		}
 		// ---- coalesced store of the soft row ----
 		float *orow = p.soft + (size_t)b * p.soft_stride;
 		if (((reinterpret_cast<uintptr_t>(orow) & 15u) == 0) && (nout & 3) == 0) {

@@ -586,6 +586,182 @@ corr_nb_kernel(CorrParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// corr_long_kernel — every other configuration (access bursts with their 40-symbol sync sequence and 60+ symbol
+// search window, normal bursts with a wide max_toa): one warp per burst, register blocked like corr_nb_kernel.
+// The arithmetic is bound by the FP32 pipe here (a RACH burst costs 79 x 40 complex taps = 12.6 k packed
+// operations against 3.9 KB of samples), so the layout is chosen to keep everything else off the issue slots:
+//   stage     cp.async copies of the NEXT burst's window (zero filled outside samples 0..623 through the
+//             src-size operand) land in the second buffer while the current burst is processed.  Slot sl
+//             (2 samples) lives in plane sl & 7 at index sl >> 3, plane pitch odd.
+//   decimate  lane a: outputs 4a .. 4a+3 from slots 8a .. 8a+13 (14 conflict-free LDS.128).
+//   correlate lane a: outputs 3a .. 3a+2; per block of 8 taps 10 decimated samples are loaded once and feed all
+//             three outputs; the taps come from __constant__ (the sequence is the same for the whole warp);
+//             24 independent accumulation chains per lane (A[q], B[q] of convolve_sse_3.c:462-537 per output).
+// Same operations in the same order per output as corr_kernel / the reference, hence the same bits.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int corr_lg_pp(int ndmax) { return (((ndmax + 3) >> 2) + 2) | 1; } // plane pitch in slots
+__host__ __device__ constexpr size_t corr_lg_warp_bytes(int ndmax)
+{
+	return (size_t)2 * 8 * corr_lg_pp(ndmax) * 16 + ((((size_t)ndmax + 8) * 8 + 15) & ~(size_t)15);
+}
+
+__global__ void __launch_bounds__(256, 2)
+corr_long_kernel(CorrParams p)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int wpb = blockDim.x >> 5;
+	const int ndmax = p.ndmax, lmax = p.lmax;
+	const int PP = corr_lg_pp(ndmax);
+	unsigned char *wbase = smem_raw + corr_lg_warp_bytes(ndmax) * warp;
+	float4 *raw0 = reinterpret_cast<float4 *>(wbase);		      // [2][8][PP]
+	float2 *dec = reinterpret_cast<float2 *>(raw0 + (size_t)2 * 8 * PP); // [ndmax + 8]
+	const unsigned raw_s = (unsigned)__cvta_generic_to_shared(raw0);
+
+	const float2 NZ = bc2(p.negzero);
+	float g16[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++) g16[k] = c_tab.dnsamp[k];
+	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
+	const float2 *xall = reinterpret_cast<const float2 *>(p.bursts);
+	const int step = gridDim.x * wpb;
+
+	struct Scal { int type, tsc, T, rc; };
+	auto load_scal = [&](int b_) {
+		Scal q;
+		q.type = -1; q.tsc = 0; q.T = 0; q.rc = 0;
+		if (b_ < p.n) {
+			q.type = p.type[b_]; q.tsc = p.tsc[b_]; q.T = p.max_toa[b_];
+			if (p.round > 0) q.rc = p.rc[b_];
+		}
+		return q;
+	};
+	// attempt parameters: x = active | hlen << 1 | start << 8 | len << 16, y = offset of the sequence in c_tab.seq
+	auto plan = [&](const Scal &q) {
+		int2 r = make_int2(0, 0);
+		Attempt at;
+		if (q.type >= 0 && attempt_runs(q.type, q.tsc, q.T, p.max_toa_bound, ndmax, p.round, q.rc, c_tab.info, at)) {
+			r.x = 1 | (c_tab.info[at.seq].len << 1) | (at.start << 8) | (at.len << 16);
+			r.y = c_tab.info[at.seq].off;
+		}
+		return r;
+	};
+	auto issue_copies = [&](int b_, int pk_, int buf) {
+		if (pk_active(pk_)) {
+			const int nd = pk_hlen(pk_) + pk_len(pk_) - 1;
+			const int s_lo = 4 * (pk_start(pk_) - pk_hlen(pk_) + 1) - 15;
+			const int ns = 2 * nd + 6;
+			const size_t row = (size_t)b_ * (size_t)p.stride;
+			const float2 *x = xall + row;
+			const unsigned row_par = (base_par + (unsigned)(row & 1u)) & 1u;
+			const bool aligned = (((unsigned)s_lo + row_par) & 1u) == 0; // window slots sit on the row's 16-byte grid
+			const unsigned dst0 = raw_s + 16u * (unsigned)(buf * 8 * PP);
+			for (int sl = lane; sl < ns; sl += 32) {
+				const int idx = s_lo + 2 * sl;
+				const unsigned dst = dst0 + 16u * (unsigned)((sl & 7) * PP + (sl >> 3));
+				if (aligned && idx >= 0 && idx <= 622) {
+					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(x + idx) : "memory");
+				} else {
+					// downsampleBurst reads samples 0..623 behind 16 zero history samples (:1590-1593)
+					const unsigned n0 = (idx >= 0 && idx <= 623) ? 8u : 0u, n1 = (idx + 1 >= 0 && idx + 1 <= 623) ? 8u : 0u;
+					const float2 *s0 = x + min(max(idx, 0), 623), *s1 = x + min(max(idx + 1, 0), 623);
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(s0), "r"(n0) : "memory");
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8u), "l"(s1), "r"(n1) : "memory");
+				}
+			}
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+
+	int b = blockIdx.x * wpb + warp;
+	int2 pk0 = plan(load_scal(b));
+	if (b < p.n) issue_copies(b, pk0.x, 0);
+	Scal s1 = load_scal(b + step);
+	int cur = 0;
+	for (; b < p.n; b += step, cur ^= 1) {
+		const int2 pk1 = plan(s1);
+		s1 = load_scal(b + 2 * step);
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncwarp();
+		// the other buffer was consumed by the previous burst's decimation: refill it with the next window
+		if (b + step < p.n) issue_copies(b + step, pk1.x, cur ^ 1);
+		if (pk_active(pk0.x)) {
+			const int hlen = pk_hlen(pk0.x), len = pk_len(pk0.x);
+			const int nd = hlen + len - 1;
+			const int dstart = pk_start(pk0.x) - (hlen - 1);
+			const float4 *raw = raw0 + (size_t)cur * 8 * PP;
+			// ---- decimation (sse_conv_real16 order, convolve_sse_3.c:188-264): 4 outputs per item ----
+			for (int a = lane; 4 * a < nd; a += 32) {
+				float4 s[14];
+#pragma unroll
+				for (int q = 0; q < 14; q++) s[q] = raw[(q & 7) * PP + a + (q >> 3)];
+				float *pw = p.pwr + (size_t)b * ndmax;
+#pragma unroll
+				for (int o = 0; o < 4; o++) {
+					float2 L[4];
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						// taps q, 4+q, 8+q, 12+q: sample k of the output sits in slot 2o + k/2, half k & 1
+						float2 pr[4];
+#pragma unroll
+						for (int m = 0; m < 4; m++) {
+							const int k = 4 * m + q;
+							const float4 v = s[2 * o + (k >> 1)];
+							pr[m] = mul2((k & 1) ? make_float2(v.z, v.w) : make_float2(v.x, v.y), bc2(g16[k]), NZ);
+						}
+						L[q] = add2(add2(pr[0], pr[1]), add2(pr[2], pr[3]));
+					}
+					float2 y = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+					const int j = 4 * a + o, d = dstart + j;
+					if (j < nd) {
+						if (d < 0 || d >= 156) y = make_float2(0.0f, 0.0f);
+						dec[j] = y;
+						pw[j] = norm2(y);
+					}
+				}
+			}
+			__syncwarp();
+			// ---- correlation (sse_conv_cmplx_8n order, convolve_sse_3.c:462-537): 3 outputs per item ----
+			const float2 *hh = c_tab.seq + pk0.y;
+			for (int a = lane; 3 * a < len; a += 32) {
+				const float2 *dx = dec + 3 * a;
+				float2 A[4][3], B[4][3];
+#pragma unroll
+				for (int q = 0; q < 4; q++)
+#pragma unroll
+					for (int o = 0; o < 3; o++) { A[q][o] = make_float2(0.0f, 0.0f); B[q][o] = make_float2(0.0f, 0.0f); }
+				for (int t0 = 0; t0 < hlen; t0 += 8) {
+					float2 xw[10];
+#pragma unroll
+					for (int k = 0; k < 10; k++) xw[k] = dx[t0 + k];
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						const float2 h1 = hh[t0 + q], h2 = hh[t0 + 4 + q];
+						const float2 h1r = bc2(h1.x), h1i = make_float2(h1.y, -h1.y);
+						const float2 h2r = bc2(h2.x), h2i = make_float2(h2.y, -h2.y);
+#pragma unroll
+						for (int o = 0; o < 3; o++) {
+							A[q][o] = add2(A[q][o], cmul_tap(xw[q + o], h1r, h1i, NZ));
+							B[q][o] = add2(B[q][o], cmul_tap(xw[4 + q + o], h2r, h2i, NZ));
+						}
+					}
+				}
+				float2 *co = p.corr + (size_t)b * lmax + 3 * a;
+#pragma unroll
+				for (int o = 0; o < 3; o++) {
+					float2 L[4];
+#pragma unroll
+					for (int q = 0; q < 4; q++) L[q] = add2(A[q][o], B[q][o]);
+					if (3 * a + o < len) co[o] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+				}
+			}
+			__syncwarp();
+		}
+		pk0 = pk1;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // peak_kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int kPadRows = 9;    // zero rows on either side of a correlation vector (interpolation reach)
