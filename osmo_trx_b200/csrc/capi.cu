@@ -524,8 +524,8 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			 ChunkHook *after_chunk = nullptr, bool overlapped = false)
 {
 	const trxb200_ctx::Tune &tn = ctx->tune;
-	const int lmax = 16 + bound;
-	const int ndmax = ctx->max_seq_len + lmax - 1; // decimated samples a correlation window needs
+	const int lmax = (16 + bound + 1) & ~1;		    // row pitch of the correlation vectors (even: 16-byte row loads in peak_kernel)
+	const int ndmax = ctx->max_seq_len + 16 + bound - 1; // decimated samples a correlation window needs
 	// ---- launch geometry ----
 	const bool nb = (ndmax == 35 && lmax == 20); // 16-symbol sync, max_toa <= 4: register-blocked corr_nb_kernel
 	int cw = 8; // warps per corr block

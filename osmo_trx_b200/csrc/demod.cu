@@ -139,6 +139,12 @@ __device__ __forceinline__ float2 cscale(float2 a, float2 s)
 	return make_float2(fmaf(a.x, s.x, -a.y * s.y), fmaf(a.x, s.y, a.y * s.x));
 }
 
+// complex product with fused multiply-adds (non-decision chains)
+__device__ __forceinline__ float2 cmul_fast(float2 a, float2 b)
+{
+	return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
 // Re(e^{-j*pi*i/2} * s * a): scale + GMSKReverseRotate(1 sps) + real part (sigProcLib.cpp:262-287,2011-2022)
 __device__ __forceinline__ float soft_out(int i, float2 a, float2 s)
 {
@@ -170,33 +176,30 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 	float c0[5];
 #pragma unroll
 	for (int k = 0; k < 5; k++) c0[k] = c_tab.c0_inv[k];
+	// none of this chain feeds a decision (soft bits and C/I carry the 1e-4 tolerance): FMA forms throughout
 #pragma unroll
 	for (int r = 0; r < 5; r++) {
 		const int i = lane + 32 * r;
 		rot[r] = make_float2(0.0f, 0.0f);
 		if (i < 148) { // softSliceEdgeBurst consumes symbols 0..147 only, computeEdgeCI 8..147
-			// 5-tap static equaliser, NO_DELAY span, sequential MAC (convolve_base.c:27-60)
-			float er = 0.0f, ei = 0.0f;
+			// 5-tap static equaliser, NO_DELAY span (convolve_base.c:27-60)
+			float2 eq = make_float2(0.0f, 0.0f);
 #pragma unroll
-			for (int k = 0; k < 5; k++) {
-				const float2 dk = decs[i + k];
-				er = fa(er, fm(dk.x, c0[k]));
-				ei = fa(ei, fm(dk.y, c0[k]));
-			}
-			rot[r] = cmul_exact(make_float2(er, ei), p.edge_tab[i & 15]); // derotateEdgeBurst :691-711
+			for (int k = 0; k < 5; k++) eq = ffma2(decs[i + k], make_float2(c0[k], c0[k]), eq);
+			rot[r] = cmul_fast(eq, p.edge_tab[i & 15]); // derotateEdgeBurst :691-711
 			if (i >= 8) {
 				// computeEdgeCI :2074-2093: distance to the nearest ideal 8-PSK point.  The reference picks it as
-				// round(atan2(y, x) / (pi/4)); the octant comparisons below pick the same point except within
-				// rounding of an octant boundary, where both neighbours are equally far (C/I carries 1e-4).
+				// round(atan2(y, x) / (pi/4)); the octant test below picks the same point except within rounding
+				// of an octant boundary, where both neighbours are equally far.
 				const float ax = fabsf(rot[r].x), ay = fabsf(rot[r].y);
-				const float t8 = 0.41421357f; // tan(pi/8)
-				int k;
-				if (ay <= t8 * ax) k = rot[r].x >= 0.0f ? 0 : (rot[r].y >= 0.0f ? 4 : -4);
-				else if (ax < t8 * ay) k = rot[r].y > 0.0f ? 2 : -2;
-				else k = (rot[r].x > 0.0f ? 1 : 3) * (rot[r].y > 0.0f ? 1 : -1);
-				const float2 ideal = p.edge_tab[16 + k + 4];
-				const float2 er2 = make_float2(fs(ideal.x, rot[r].x), fs(ideal.y, rot[r].y));
-				err += norm2(er2);
+				const unsigned sel = (fminf(ax, ay) > 0.41421357f * fmaxf(ax, ay) ? 8u : 0u) | (ay > ax ? 4u : 0u) |
+						     (rot[r].x < 0.0f ? 2u : 0u) | (rot[r].y < 0.0f ? 1u : 0u);
+				// k + 4 per (diagonal, vertical, x < 0, y < 0): axis points 0, +-4, +-2; diagonal points +-1, +-3
+				const unsigned long long lut = 0x1735173526260844ull;
+				const int k4 = (int)((lut >> (4 * sel)) & 15u);
+				const float2 ideal = p.edge_tab[16 + k4];
+				const float ex = ideal.x - rot[r].x, ey = ideal.y - rot[r].y;
+				err = fmaf(ex, ex, fmaf(ey, ey, err));
 			}
 		}
 	}
@@ -208,11 +211,11 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 	for (int r = 0; r < 5; r++) {
 		const int i = lane + 32 * r;
 		if (i < 148) {
-			const float2 r1 = cmul_exact(rot[r], rot1);
-			const float2 r2 = cmul_exact(make_float2(fabsf(r1.x), fabsf(r1.y)), rot2);
+			const float2 r1 = cmul_fast(rot[r], rot1);
+			const float r2y = fmaf(fabsf(r1.x), rot2.y, fabsf(r1.y) * rot2.x);
 			ost[3 * i] = -r1.y;
 			ost[3 * i + 1] = r1.x;
-			ost[3 * i + 2] = -r2.y;
+			ost[3 * i + 2] = -r2y;
 		}
 	}
 	__syncwarp();
@@ -220,8 +223,13 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 	float *orow = p.soft + (size_t)b * p.soft_stride;
 	if ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0 && (nvals & 3) == 0) {
 		const float4 *os4 = reinterpret_cast<const float4 *>(ost);
-		for (int j = lane; j < (nvals >> 2); j += 32)
-			reinterpret_cast<float4 *>(orow)[j] = os4[j];
+		float4 *o4 = reinterpret_cast<float4 *>(orow);
+		const int n4 = nvals >> 2; // <= 111
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int j = lane + 32 * k;
+			if (j < n4) o4[j] = os4[j];
+		}
 	} else {
 		for (int j = lane; j < nvals; j += 32)
 			orow[j] = ost[j];
@@ -230,7 +238,7 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 	for (int o = 16; o; o >>= 1)
 		err += __shfl_xor_sync(0xffffffffu, err, o);
 	if (lane == 0)
-		p.ci[b] = fm(3.0103f, log2f(140.0f / err));
+		p.ci[b] = 3.0103f * __log2f(__fdividef(140.0f, err));
 }
 
 } // namespace

@@ -605,6 +605,48 @@ __host__ __device__ constexpr size_t corr_lg_warp_bytes(int ndmax)
 	return (size_t)2 * 8 * corr_lg_pp(ndmax) * 16 + ((((size_t)ndmax + 8) * 8 + 15) & ~(size_t)15);
 }
 
+// HLEN > 0: compile-time sequence length (fully unrolled, immediate offsets); 0: run-time multiple of 8
+template <int HLEN>
+__device__ __forceinline__ void corr_long_items(const float2 *dec, const float2 *hh, int len, int hlen_rt, int lane, float2 *crow,
+						 float2 NZ)
+{
+	const int hlen = HLEN ? HLEN : hlen_rt;
+	for (int a = lane; 3 * a < len; a += 32) {
+		const float2 *dx = dec + 3 * a;
+		float2 A[4][3], B[4][3];
+#pragma unroll
+		for (int q = 0; q < 4; q++)
+#pragma unroll
+			for (int o = 0; o < 3; o++) { A[q][o] = make_float2(0.0f, 0.0f); B[q][o] = make_float2(0.0f, 0.0f); }
+#pragma unroll
+		for (int t0 = 0; t0 < hlen; t0 += 8) {
+			asm volatile("" ::: "memory"); // keeps the unrolled blocks' loads in their own block (register pressure)
+			float2 xw[10];
+#pragma unroll
+			for (int k = 0; k < 10; k++) xw[k] = dx[t0 + k];
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const float2 h1 = hh[t0 + q], h2 = hh[t0 + 4 + q];
+				const float2 h1r = bc2(h1.x), h1i = make_float2(h1.y, -h1.y);
+				const float2 h2r = bc2(h2.x), h2i = make_float2(h2.y, -h2.y);
+#pragma unroll
+				for (int o = 0; o < 3; o++) {
+					A[q][o] = add2(A[q][o], cmul_tap(xw[q + o], h1r, h1i, NZ));
+					B[q][o] = add2(B[q][o], cmul_tap(xw[4 + q + o], h2r, h2i, NZ));
+				}
+			}
+		}
+		float2 *co = crow + 3 * a;
+#pragma unroll
+		for (int o = 0; o < 3; o++) {
+			float2 L[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) L[q] = add2(A[q][o], B[q][o]);
+			if (3 * a + o < len) co[o] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+		}
+	}
+}
+
 __global__ void __launch_bounds__(256, 2)
 corr_long_kernel(CorrParams p)
 {
@@ -656,13 +698,21 @@ corr_long_kernel(CorrParams p)
 			const unsigned row_par = (base_par + (unsigned)(row & 1u)) & 1u;
 			const bool aligned = (((unsigned)s_lo + row_par) & 1u) == 0; // window slots sit on the row's 16-byte grid
 			const unsigned dst0 = raw_s + 16u * (unsigned)(buf * 8 * PP);
-			for (int sl = lane; sl < ns; sl += 32) {
-				const int idx = s_lo + 2 * sl;
-				const unsigned dst = dst0 + 16u * (unsigned)((sl & 7) * PP + (sl >> 3));
-				if (aligned && idx >= 0 && idx <= 622) {
-					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(x + idx) : "memory");
+			// slot sl = lane + 32 * it: plane sl & 7 = lane & 7, index sl >> 3 = (lane >> 3) + 4 * it
+			unsigned dst = dst0 + 16u * (unsigned)((lane & 7) * PP + (lane >> 3));
+			const float2 *src = x + s_lo + 2 * lane;
+			int idx = s_lo + 2 * lane;
+			for (int sl = lane; sl < ns; sl += 32, dst += 64u, src += 64, idx += 64) {
+				if (idx >= 0 && idx <= 622) {
+					if (aligned) {
+						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+					} else {
+						asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+						asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u), "l"(src + 1) : "memory");
+					}
 				} else {
-					// downsampleBurst reads samples 0..623 behind 16 zero history samples (:1590-1593)
+					// downsampleBurst reads samples 0..623 behind 16 zero history samples (:1590-1593): zero fill
+					// through the src-size operand (the clamped address is never read when the size is 0)
 					const unsigned n0 = (idx >= 0 && idx <= 623) ? 8u : 0u, n1 = (idx + 1 >= 0 && idx + 1 <= 623) ? 8u : 0u;
 					const float2 *s0 = x + min(max(idx, 0), 623), *s1 = x + min(max(idx + 1, 0), 623);
 					asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(s0), "r"(n0) : "memory");
@@ -723,38 +773,11 @@ corr_long_kernel(CorrParams p)
 			__syncwarp();
 			// ---- correlation (sse_conv_cmplx_8n order, convolve_sse_3.c:462-537): 3 outputs per item ----
 			const float2 *hh = c_tab.seq + pk0.y;
-			for (int a = lane; 3 * a < len; a += 32) {
-				const float2 *dx = dec + 3 * a;
-				float2 A[4][3], B[4][3];
-#pragma unroll
-				for (int q = 0; q < 4; q++)
-#pragma unroll
-					for (int o = 0; o < 3; o++) { A[q][o] = make_float2(0.0f, 0.0f); B[q][o] = make_float2(0.0f, 0.0f); }
-				for (int t0 = 0; t0 < hlen; t0 += 8) {
-					float2 xw[10];
-#pragma unroll
-					for (int k = 0; k < 10; k++) xw[k] = dx[t0 + k];
-#pragma unroll
-					for (int q = 0; q < 4; q++) {
-						const float2 h1 = hh[t0 + q], h2 = hh[t0 + 4 + q];
-						const float2 h1r = bc2(h1.x), h1i = make_float2(h1.y, -h1.y);
-						const float2 h2r = bc2(h2.x), h2i = make_float2(h2.y, -h2.y);
-#pragma unroll
-						for (int o = 0; o < 3; o++) {
-							A[q][o] = add2(A[q][o], cmul_tap(xw[q + o], h1r, h1i, NZ));
-							B[q][o] = add2(B[q][o], cmul_tap(xw[4 + q + o], h2r, h2i, NZ));
-						}
-					}
-				}
-				float2 *co = p.corr + (size_t)b * lmax + 3 * a;
-#pragma unroll
-				for (int o = 0; o < 3; o++) {
-					float2 L[4];
-#pragma unroll
-					for (int q = 0; q < 4; q++) L[q] = add2(A[q][o], B[q][o]);
-					if (3 * a + o < len) co[o] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
-				}
-			}
+			float2 *crow = p.corr + (size_t)b * lmax;
+			if (hlen == 40) corr_long_items<40>(dec, hh, len, hlen, lane, crow, NZ);
+			else if (hlen == 16) corr_long_items<16>(dec, hh, len, hlen, lane, crow, NZ);
+			else if (hlen == 64) corr_long_items<64>(dec, hh, len, hlen, lane, crow, NZ);
+			else corr_long_items<0>(dec, hh, len, hlen, lane, crow, NZ);
 			__syncwarp();
 		}
 		pk0 = pk1;
