@@ -1041,6 +1041,14 @@ static int conv_common(trxb200_ctx *ctx, const float *x, int x_len, int x_stride
 	if (start + len > x_len || len > y_len || x_len < h_len) return TRXB200_EBOUNDS;
 	if (h_len > 4096) return fail(ctx, TRXB200_EINVAL, "convolve: h_len > 4096");
 	if (n == 0) return TRXB200_OK;
+	if ((mode == 0 || mode == 1) && !(h_len % 4) && h_len <= 24) {
+		// SSE-order cases the reference actually runs (decimator 16, fractional delay 20, pulse shapes 4..24)
+		const long tiles = (long)n * ((len + kCvTile - 1) / kCvTile);
+		const int grid = grid_for(ctx, tiles * 32, 256, 8);
+		const bool ok = mode ? launch_convolve_blk<true>(h_len, grid, ctx->stream, x, x_stride, h, y, y_stride, start, len, n)
+				     : launch_convolve_blk<false>(h_len, grid, ctx->stream, x, x_stride, h, y, y_stride, start, len, n);
+		if (ok) return post_launch(ctx, "convolve_blk_kernel");
+	}
 	const size_t smem = (size_t)h_len * 8;
 	convolve_kernel<<<grid_for(ctx, (long)n * len, 256, 8), 256, smem, ctx->stream>>>(x, x_stride, h, h_len, y, y_stride, start, len, n, mode);
 	return post_launch(ctx, "convolve_kernel");

@@ -36,8 +36,12 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 	p.bufs = bufs; p.stride = stride; p.offset = offset; p.n = n; p.is_ab = is_ab; p.tsc = tsc; p.max_delay = max_delay;
 	p.clamp_lo = clamp_lo; p.clamp_hi = clamp_hi; p.bits = bits; p.start = start; p.corr_max = corr_max; p.cir = cir;
 	p.nwin_max = s1 - s0;
+	p.lo = std::min(clamp_lo, s0);
+	p.range = std::max(clamp_hi + 4 * N, s1 + 4 * (tlen - 1)) - p.lo;
+	p.pitch = vitac_pitch(p.range);
 	const int wpb = 4;
-	const size_t smem = (size_t)wpb * ((3 * p.nwin_max + 2 * 160 + 16 + 2 * 160 + 8 + 3) & ~3) * sizeof(float);
+	const size_t smem = (size_t)wpb * vitac_warp_floats(p.nwin_max, p.pitch) * sizeof(float);
+	if (smem > 200 * 1024) return fail(ctx, TRXB200_EINVAL, "vitac: clamp range too wide for the on-chip window");
 	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int grid = std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
 	if (grid < 1) grid = 1;

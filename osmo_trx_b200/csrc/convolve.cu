@@ -108,4 +108,126 @@ convolve_kernel(const float *__restrict__ x, int x_stride, const float *__restri
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// convolve_blk_kernel — the SSE-order cases with h_len in {4, 8, .., 24}, register blocked: a warp owns a tile of
+// 128 consecutive outputs of one row, stages the 128 + h_len - 1 samples it needs with coalesced loads into a
+// transposed shared window (sample s in plane s & 3 at index s >> 2: the per-lane reads below are conflict free),
+// and every lane evaluates 4 consecutive outputs from h_len + 3 samples held in registers.  Each output is the same
+// expression tree as above on the packed FP32 pipe ((re, im) pairs; exact, see mul2 in detect.cu), so the bits do
+// not change; per output the kernel issues 1/3 of the instructions and 1/6 of the load wavefronts of convolve_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCvTile = 128;  // outputs per warp tile
+constexpr int kCvPitch = 52;  // plane pitch in samples (>= (128 + 23 + 3) / 4, = 4 mod 16: conflict-free staging stores)
+
+template <int HLEN, bool CPLX>
+__global__ void __launch_bounds__(256)
+convolve_blk_kernel(const float *__restrict__ x, int x_stride, const float *__restrict__ h, float *__restrict__ y, int y_stride,
+		    int start, int len, int n, float negzero)
+{
+	__shared__ __align__(16) float2 win_all[8][4 * kCvPitch];
+	__shared__ __align__(16) float2 hs[HLEN];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (threadIdx.x < HLEN) hs[threadIdx.x] = reinterpret_cast<const float2 *>(h)[threadIdx.x];
+	__syncthreads();
+	float2 *win = win_all[warp];
+	const float2 NZ = bc2(negzero);
+	const int tpr = (len + kCvTile - 1) / kCvTile; // tiles per row
+	const long ntiles = (long)n * tpr;
+	constexpr int NW = kCvTile + HLEN - 1; // samples a tile needs
+	constexpr int KL = (NW + 31) / 32;
+	// the samples of the NEXT tile are fetched into registers while the current tile is evaluated
+	float2 nxt[KL];
+	auto fetch = [&](long t_) {
+		const int b_ = (int)(t_ / tpr), i0_ = (int)(t_ % tpr) * kCvTile;
+		const float2 *xr = reinterpret_cast<const float2 *>(x) + (size_t)b_ * x_stride + (i0_ + start - (HLEN - 1));
+		const int nvalid = min(NW, len - i0_ + HLEN - 1); // samples of the tile inside the range the contract covers
+#pragma unroll
+		for (int k = 0; k < KL; k++) {
+			const int sidx = lane + 32 * k;
+			nxt[k] = make_float2(0.0f, 0.0f);
+			if (sidx < nvalid) nxt[k] = __ldg(&xr[sidx]);
+		}
+	};
+	const long tstep = (long)gridDim.x * 8;
+	long t = (long)blockIdx.x * 8 + warp;
+	if (t < ntiles) fetch(t);
+	for (; t < ntiles; t += tstep) {
+		const int b = (int)(t / tpr), i0 = (int)(t % tpr) * kCvTile;
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < KL; k++) {
+			const int sidx = lane + 32 * k;
+			if (sidx < NW) win[(sidx & 3) * kCvPitch + (sidx >> 2)] = nxt[k];
+		}
+		__syncwarp();
+		if (t + tstep < ntiles) fetch(t + tstep);
+		float2 w[HLEN + 3];
+#pragma unroll
+		for (int j = 0; j < HLEN + 3; j++) w[j] = win[(j & 3) * kCvPitch + lane + (j >> 2)];
+		float2 out[4];
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			float2 L[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if constexpr (!CPLX) {
+#define PX(k) mul2(w[r + (k)], bc2(hs[(k)].x), NZ)
+					if constexpr (HLEN == 4) L[j] = PX(j);
+					else if constexpr (HLEN == 8) L[j] = add2(PX(j), PX(4 + j));
+					else if constexpr (HLEN == 12) L[j] = add2(add2(PX(j), PX(4 + j)), PX(8 + j));
+					else if constexpr (HLEN == 16) L[j] = add2(add2(PX(j), PX(4 + j)), add2(PX(8 + j), PX(12 + j)));
+					else if constexpr (HLEN == 20) L[j] = add2(add2(add2(PX(j), PX(4 + j)), PX(8 + j)), add2(PX(12 + j), PX(16 + j)));
+					else {
+						float2 a = make_float2(0.0f, 0.0f);
+#pragma unroll
+						for (int g = 0; g < HLEN / 4; g++) a = add2(a, PX(4 * g + j));
+						L[j] = a;
+					}
+#undef PX
+				} else {
+#define TAP(k) cmul_tap(w[r + (k)], bc2(hs[(k)].x), make_float2(hs[(k)].y, -hs[(k)].y), NZ)
+					float2 a = make_float2(0.0f, 0.0f);
+					if constexpr (HLEN % 8 == 0) {
+						float2 c = make_float2(0.0f, 0.0f);
+#pragma unroll
+						for (int g = 0; g < HLEN; g += 8) {
+							a = add2(a, TAP(g + j));
+							c = add2(c, TAP(g + 4 + j));
+						}
+						L[j] = add2(a, c);
+					} else {
+#pragma unroll
+						for (int g = 0; g < HLEN; g += 4) a = add2(a, TAP(g + j));
+						L[j] = a;
+					}
+#undef TAP
+				}
+			}
+			out[r] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+		}
+		float2 *yr = reinterpret_cast<float2 *>(y) + (size_t)b * y_stride + i0 + 4 * lane;
+		const int left = len - (i0 + 4 * lane);
+		if (left >= 4 && (reinterpret_cast<uintptr_t>(yr) & 15u) == 0) {
+			reinterpret_cast<float4 *>(yr)[0] = make_float4(out[0].x, out[0].y, out[1].x, out[1].y);
+			reinterpret_cast<float4 *>(yr)[1] = make_float4(out[2].x, out[2].y, out[3].x, out[3].y);
+		} else {
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+				if (r < left) yr[r] = out[r];
+		}
+	}
+}
+
+template <bool CPLX>
+static bool launch_convolve_blk(int h_len, int grid, cudaStream_t st, const float *x, int x_stride, const float *h, float *y,
+				int y_stride, int start, int len, int n)
+{
+	switch (h_len) {
+#define CV_CASE(H) case H: convolve_blk_kernel<H, CPLX><<<grid, 256, 0, st>>>(x, x_stride, h, y, y_stride, start, len, n, -0.0f); return true;
+	CV_CASE(4) CV_CASE(8) CV_CASE(12) CV_CASE(16) CV_CASE(20) CV_CASE(24)
+#undef CV_CASE
+	default: return false;
+	}
+}
+
 } // namespace trxb200

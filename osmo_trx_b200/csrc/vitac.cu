@@ -27,6 +27,7 @@ struct VitacParams {
 	int32_t *start;
 	float *corr_max, *cir;
 	int nwin_max;
+	int lo, range, pitch; // staged part of each row: samples [lo, lo + range) relative to the burst; plane pitch of the window
 };
 
 namespace {
@@ -42,19 +43,36 @@ __device__ __forceinline__ float cabs_ref(float2 c)
 
 } // namespace
 
-// shared memory per warp (floats): cb[2*nwin] | pw[nwin] | filt[2][160] | inc[2][8] | words[2][160] | misc[8]
+// plane pitch (in samples) of the staged window: >= range / 4 + 1 and = 4 (mod 16), so that a warp's 32 consecutive
+// samples (8 per plane) and a warp's 32 samples at stride 4 (one plane) both fall on distinct banks
+__host__ __device__ inline int vitac_pitch(int range) { int pp = (range + 3) / 4 + 1; while ((pp & 15) != 4) pp++; return pp; }
+__host__ __device__ inline int vitac_warp_floats(int nwin_max, int pitch)
+{
+	return (8 * pitch + 2 * nwin_max + ((nwin_max + 1) & ~1) + 2 * 160 + 16 + 80 + 2 * 160 + 8 + 3) & ~3;
+}
+
+// shared memory per warp (floats): xs[4][pitch] complex | cb[2*nwin] | pw[nwin] | filt[2][160] | inc[2][8] | csel[2][20] complex |
+// words[160][2] | misc[8]
+//
+// Each row is staged ONCE (coalesced 8-byte loads) into a transposed window, sample r in plane r & 3 at index r >> 2:
+// the correlation windows (lanes = consecutive samples, taps 4 samples apart) and the matched filter (lanes = outputs
+// 4 samples apart, taps consecutive) then read it conflict free, instead of fetching 32 different 32-byte sectors per
+// matched-filter load from L1.
 __global__ void __launch_bounds__(128)
 vitac_kernel(VitacParams p)
 {
 	extern __shared__ __align__(16) float vsm[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-	const int per_warp = (3 * p.nwin_max + 2 * 160 + 16 + 2 * 160 + 8 + 3) & ~3; // keep float2 alignment per warp
+	const int P = p.pitch;
+	const int per_warp = vitac_warp_floats(p.nwin_max, P);
 	float *base = vsm + (size_t)warp * per_warp;
-	float2 *cb = reinterpret_cast<float2 *>(base);
-	float *pw = base + 2 * p.nwin_max;
-	float *filt = pw + p.nwin_max;	       // [2][160]
+	float2 *xs = reinterpret_cast<float2 *>(base);
+	float2 *cb = xs + 4 * P;
+	float *pw = reinterpret_cast<float *>(cb + p.nwin_max);
+	float *filt = pw + ((p.nwin_max + 1) & ~1); // [2][160], 8-byte aligned
 	float *inc = filt + 320;	       // [2][8]
-	unsigned *words = reinterpret_cast<unsigned *>(inc + 16); // [160][2]: gt, lt
+	float2 *csel = reinterpret_cast<float2 *>(inc + 16); // [2][20]: CIR taps arranged for the imaginary / real matched-filter outputs
+	unsigned *words = reinterpret_cast<unsigned *>(base + (per_warp - 8 - 320)); // [160][2]: gt, lt (16-byte aligned)
 	int *misc = reinterpret_cast<int *>(words + 320);
 
 	const int N = p.is_ab ? 88 : 148;
@@ -63,6 +81,7 @@ vitac_kernel(VitacParams p)
 	const int s1 = (center + 5 + 5 + (p.is_ab ? p.max_delay : 0)) * kOSR;
 	const int nwin = s1 - s0;
 	const int tlen = p.is_ab ? 31 : 16;
+	const float ftlen = (float)tlen;
 
 	const int npairs = (p.n + 1) >> 1;
 	for (int pair = blockIdx.x * wpb + warp; pair < npairs; pair += gridDim.x * wpb) {
@@ -74,18 +93,35 @@ vitac_kernel(VitacParams p)
 				if (lane < 8) inc[h * 8 + lane] = 0.0f;
 				continue;
 			}
-			const float2 *in = reinterpret_cast<const float2 *>(p.bufs) + (size_t)b * p.stride + p.offset;
+			const float2 *in = reinterpret_cast<const float2 *>(p.bufs) + (size_t)b * p.stride + p.offset + p.lo;
 			const float2 *tseq = p.is_ab ? &c_tab.vitac_access[5] : &c_tab.vitac_norm[p.tsc[b] > 8 ? 8 : p.tsc[b]][5];
+			// ---- stage the row ----
+			for (int r0 = 0; r0 < p.range; r0 += 256) {
+				float2 v[8];
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					const int r = r0 + lane + 32 * k;
+					v[k] = make_float2(0.0f, 0.0f);
+					if (r < p.range) v[k] = __ldg(&in[r]);
+				}
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					const int r = r0 + lane + 32 * k;
+					if (r < p.range) xs[(r & 3) * P + (r >> 2)] = v[k];
+				}
+			}
+			__syncwarp();
 			// ---- correlation per search window (correlate_sequence :148-156) ----
 			for (int w = lane; w < nwin; w += 32) {
-				const float2 *x = in + s0 + w;
+				const int r = s0 + w - p.lo;
+				const float2 *x = xs + (r & 3) * P + (r >> 2); // taps 4 samples apart: consecutive in the plane
 				float rr = 0.0f, ri = 0.0f;
 				for (int ii = 0; ii < tlen; ii++) {
-					const float2 s = tseq[ii], v = __ldg(&x[ii * kOSR]);
+					const float2 s = tseq[ii], v = x[ii];
 					rr = fa(rr, fs(fm(s.x, v.x), fm(s.y, v.y)));
 					ri = fa(ri, fa(fm(s.x, v.y), fm(s.y, v.x)));
 				}
-				const float2 c = make_float2(rr / (float)tlen, -ri / (float)tlen);
+				const float2 c = make_float2(rr / ftlen, -ri / ftlen);
 				cb[w] = c;
 				const float a = cabs_ref(c);
 				pw[w] = (float)((double)a * (double)a); // std::pow(abs(c), 2) evaluated in double
@@ -138,18 +174,40 @@ vitac_kernel(VitacParams p)
 				const float c = (lane & 4) ? r3i : -r3i;
 				inc[h * 8 + lane] = fa(fa(fa(a, bq), c), r4r);
 			}
-			// ---- matched filter (mafi :168-181), only the component the trellis reads ----
-			for (int nn = lane; nn < N; nn += 32) {
-				const float2 *x = in + st + nn * kOSR;
-				float acc = 0.0f;
-				const bool want_imag = !(nn & 1);
-				for (int ii = 0; ii < kCirLen; ii++) {
-					if (nn * kOSR + ii >= N * kOSR) break;
-					const float2 v = __ldg(&x[ii]), c = cir[ii];
-					const float t = want_imag ? fa(fm(v.x, c.y), fm(v.y, c.x)) : fs(fm(v.x, c.x), fm(v.y, c.y));
-					acc = fa(acc, t);
+			// ---- matched filter (mafi :168-181), only the component the trellis reads: even outputs the imaginary
+			//      part v.x*c.y + v.y*c.x, odd outputs the real part v.x*c.x - v.y*c.y.  Output parity = lane parity, so
+			//      each lane reads its taps from the arrangement (c.y, c.x) or (c.x, -c.y): one expression, no divergence
+			//      (a - b and a + (-b) are the same float). ----
+			if (lane < kCirLen) {
+				const float2 c = cir[lane];
+				csel[lane] = make_float2(c.y, c.x);
+				csel[kCirLen + lane] = make_float2(c.x, -c.y);
+			}
+			__syncwarp();
+			{
+				const int rb = st - p.lo; // window position of the burst's first sample (warp uniform)
+				const int e0 = rb & 3;
+				const float2 *cs = csel + (lane & 1) * kCirLen;
+				for (int nn = lane; nn < N; nn += 32) {
+					const float2 *xq = xs + (rb >> 2) + nn; // sample rb + 4 nn + ii: plane (e0 + ii) & 3, index + (e0 + ii) >> 2
+					const int lim = min(kCirLen, kOSR * (N - nn));
+					float acc = 0.0f;
+					if (lim == kCirLen) {
+#pragma unroll
+						for (int ii = 0; ii < kCirLen; ii++) {
+							const int e = e0 + ii;
+							const float2 v = xq[(e & 3) * P + (e >> 2)], c = cs[ii];
+							acc = fa(acc, fa(fm(v.x, c.x), fm(v.y, c.y)));
+						}
+					} else {
+						for (int ii = 0; ii < lim; ii++) {
+							const int e = e0 + ii;
+							const float2 v = xq[(e & 3) * P + (e >> 2)], c = cs[ii];
+							acc = fa(acc, fa(fm(v.x, c.x), fm(v.y, c.y)));
+						}
+					}
+					filt[h * 160 + nn] = acc;
 				}
-				filt[h * 160 + nn] = acc;
 			}
 			__syncwarp();
 		}
@@ -164,43 +222,88 @@ vitac_kernel(VitacParams p)
 			const float i1R = odd ? ic[7 - pp] : -ic[7 - pp], i2R = odd ? -ic[pp] : ic[pp];
 			float pm = (s == 3) ? 0.0f : (float)(-10e30);
 			const int src1 = (h << 4) + pp, src2 = src1 + 8;
-			const float *f = filt + h * 160;
-			for (int k = 0; k < N; k++) {
-				const float o1 = __shfl_sync(0xffffffffu, pm, src1), o2 = __shfl_sync(0xffffffffu, pm, src2);
-				const float x = f[k];
-				float c1, c2;
-				if (!(k & 1)) { // imaginary step
-					const float sx = odd ? -x : x;
-					c1 = fa(fa(o1, sx), i1I);
-					c2 = fa(fa(o2, sx), i2I);
-				} else {
-					const float sx = odd ? x : -x;
-					c1 = fa(fa(o1, sx), i1R);
-					c2 = fa(fa(o2, sx), i2R);
+			const float2 *f2 = reinterpret_cast<const float2 *>(filt + h * 160);
+			// two trellis steps per iteration (N is even): the imaginary step, then the real one
+			for (int k = 0; k < N; k += 2) {
+				const float2 x = f2[k >> 1];
+				uint4 wd;
+				{
+					const float o1 = __shfl_sync(0xffffffffu, pm, src1), o2 = __shfl_sync(0xffffffffu, pm, src2);
+					const float sx = odd ? -x.x : x.x;
+					const float c1 = fa(fa(o1, sx), i1I), c2 = fa(fa(o2, sx), i2I);
+					// the reference tests the sign of c2 - c1; a float difference has the sign of the comparison
+					pm = (c2 < c1) ? c1 : c2;
+					wd.x = __ballot_sync(0xffffffffu, c2 > c1);
+					wd.y = __ballot_sync(0xffffffffu, c2 < c1);
 				}
-				const float d = fs(c2, c1);
-				pm = (d < 0.0f) ? c1 : c2;
-				const unsigned gt = __ballot_sync(0xffffffffu, d > 0.0f), lt = __ballot_sync(0xffffffffu, d < 0.0f);
-				if (lane == 0) { words[2 * k] = gt; words[2 * k + 1] = lt; }
+				{
+					const float o1 = __shfl_sync(0xffffffffu, pm, src1), o2 = __shfl_sync(0xffffffffu, pm, src2);
+					const float sx = odd ? x.y : -x.y;
+					const float c1 = fa(fa(o1, sx), i1R), c2 = fa(fa(o2, sx), i2R);
+					pm = (c2 < c1) ? c1 : c2;
+					wd.z = __ballot_sync(0xffffffffu, c2 > c1);
+					wd.w = __ballot_sync(0xffffffffu, c2 < c1);
+				}
+				if (lane == 0) reinterpret_cast<uint4 *>(words)[k >> 1] = wd;
 			}
 			// best stop state (viterbi_detector.cc:342-350)
 			const float m4 = __shfl_sync(0xffffffffu, pm, (h << 4) + 4), m12 = __shfl_sync(0xffffffffu, pm, (h << 4) + 12);
 			__syncwarp();
-			// ---- traceback (:371-391), one lane per burst ----
-			if (s == 0 && 2 * pair + h < p.n) {
-				unsigned state = (m12 > m4) ? 12u : 4u;
-				unsigned out_bit = 0, real_imag = ((N - 1) & 1) ? 0u : 1u;
-				int8_t *ob = p.bits + (size_t)(2 * pair + h) * N;
-				const unsigned par = 0x6666u; // parity_table bits
-				for (int k = N - 1; k >= 0; k--) {
-					const unsigned sh = (h << 4) + state;
-					const unsigned g = (words[2 * k] >> sh) & 1u, l = (words[2 * k + 1] >> sh) & 1u;
-					const unsigned decision = g;
-					const unsigned pos = (decision != out_bit) ? l : g; // output[k] > 0
-					ob[k] = pos ? (int8_t)-127 : (int8_t)127;
-					out_bit = out_bit ^ real_imag ^ ((par >> state) & 1u);
-					state = (state >> 1) + (decision ? 8u : 0u);
-					real_imag ^= 1u;
+			// ---- traceback (:371-391).  Serial part, one lane per burst: only the decision chain
+			//      state' = (state >> 1) + 8 * decision, collected as a bit string G (bit k = decision at step k). ----
+			unsigned gw[5] = { 0u, 0u, 0u, 0u, 0u };
+			unsigned sF = (m12 > m4) ? 12u : 4u;
+			if (s == 0) {
+				unsigned state = sF;
+#pragma unroll
+				for (int wi = 4; wi >= 0; wi--) {
+					unsigned acc = 0u;
+					for (int k = min(N - 1, 32 * wi + 31); k >= 32 * wi; k--) {
+						const unsigned g = (words[2 * k] >> ((h << 4) + state)) & 1u;
+						acc |= g << (k & 31);
+						state = (state >> 1) + (g << 3);
+					}
+					gw[wi] = acc;
+				}
+			}
+			// ---- parallel part, lanes = steps.  Along the path state_k = g[k+1] g[k+2] g[k+3] g[k+4] (the start state
+			//      supplies the bits beyond the end), which gives every step its parity-table bit; out_bit at step k is the
+			//      XOR of (real_imag ^ parity) over the steps above k; the output sign is then one table lookup. ----
+#pragma unroll
+			for (int hh = 0; hh < 2; hh++) {
+				const int bb = 2 * pair + hh;
+				unsigned G[6];
+#pragma unroll
+				for (int wi = 0; wi < 5; wi++) G[wi] = __shfl_sync(0xffffffffu, gw[wi], hh << 4);
+				G[5] = 0u;
+				const unsigned sf = __shfl_sync(0xffffffffu, sF, hh << 4);
+				// bits N .. N+3 = start state, most significant bit first
+				const unsigned ext = ((sf >> 3) & 1u) | (((sf >> 2) & 1u) << 1) | (((sf >> 1) & 1u) << 2) | ((sf & 1u) << 3);
+				if (N == 148) G[4] |= ext << 20; // bits N .. N+3 (N = 148 or 88: they stay inside one word)
+				else G[2] |= ext << 24;
+				const unsigned ri0 = ((N - 1) & 1) ? 0u : 1u;
+				unsigned X[5], st_k[5];
+#pragma unroll
+				for (int wi = 0; wi < 5; wi++) {
+					const int k = 32 * wi + lane;
+					const unsigned nib = __funnelshift_rc(G[wi], G[wi + 1], lane + 1) & 15u; // g[k+1] .. g[k+4], LSB first
+					st_k[wi] = __brev(nib) >> 28;
+					const unsigned x = (ri0 ^ ((unsigned)(N - 1 - k) & 1u) ^ ((0x6666u >> st_k[wi]) & 1u)) & 1u;
+					X[wi] = __ballot_sync(0xffffffffu, k < N && x);
+				}
+				unsigned carry = 0u; // parity of the X bits in the words above
+#pragma unroll
+				for (int wi = 4; wi >= 0; wi--) {
+					const int k = 32 * wi + lane;
+					const unsigned above = (lane == 31) ? 0u : (X[wi] >> (lane + 1));
+					const unsigned out_bit = (__popc(above) + carry) & 1u;
+					carry = (carry + __popc(X[wi])) & 1u;
+					if (bb < p.n && k < N) {
+						const unsigned g = (G[wi] >> lane) & 1u;
+						const unsigned l = (words[2 * k + 1] >> ((hh << 4) + st_k[wi])) & 1u;
+						const unsigned pos = (g != out_bit) ? l : g; // output[k] > 0
+						p.bits[(size_t)bb * N + k] = pos ? (int8_t)-127 : (int8_t)127;
+					}
 				}
 			}
 		}
