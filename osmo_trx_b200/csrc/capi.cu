@@ -1026,6 +1026,11 @@ int trxb200_delay_vector_batch(trxb200_ctx *ctx, const float *in, int stride, in
 	if (!ctx || !in || !out || !delay || len < 1 || stride < len || out_stride < len || n < 0)
 		return fail(ctx, TRXB200_EINVAL, "delay_vector: bad argument");
 	if (n == 0) return TRXB200_OK;
+	const long tiles = (long)n * ((len + kCvTile - 1) / kCvTile);
+	if (tiles < (1L << 30)) {
+		delay_vector_blk_kernel<<<grid_for(ctx, tiles * 32, 256, 8), 256, 0, ctx->stream>>>(in, stride, len, n, delay, out, out_stride, -0.0f);
+		return post_launch(ctx, "delay_vector_blk_kernel");
+	}
 	delay_vector_kernel<<<std::min(n, ctx->sm_count * 8), 256, 0, ctx->stream>>>(in, stride, len, n, delay, out, out_stride);
 	return post_launch(ctx, "delay_vector_kernel");
 }
@@ -1041,7 +1046,7 @@ static int conv_common(trxb200_ctx *ctx, const float *x, int x_len, int x_stride
 	if (start + len > x_len || len > y_len || x_len < h_len) return TRXB200_EBOUNDS;
 	if (h_len > 4096) return fail(ctx, TRXB200_EINVAL, "convolve: h_len > 4096");
 	if (n == 0) return TRXB200_OK;
-	if ((mode == 0 || mode == 1) && !(h_len % 4) && h_len <= 24) {
+	if ((mode == 0 || mode == 1) && !(h_len % 4) && h_len <= 24 && (long)n * ((len + kCvTile - 1) / kCvTile) < (1L << 30)) {
 		// SSE-order cases the reference actually runs (decimator 16, fractional delay 20, pulse shapes 4..24)
 		const long tiles = (long)n * ((len + kCvTile - 1) / kCvTile);
 		const int grid = grid_for(ctx, tiles * 32, 256, 8);

@@ -132,13 +132,13 @@ convolve_blk_kernel(const float *__restrict__ x, int x_stride, const float *__re
 	float2 *win = win_all[warp];
 	const float2 NZ = bc2(negzero);
 	const int tpr = (len + kCvTile - 1) / kCvTile; // tiles per row
-	const long ntiles = (long)n * tpr;
+	const int ntiles = n * tpr; // the launcher keeps n * tpr inside 31 bits (32-bit index arithmetic below)
 	constexpr int NW = kCvTile + HLEN - 1; // samples a tile needs
 	constexpr int KL = (NW + 31) / 32;
 	// the samples of the NEXT tile are fetched into registers while the current tile is evaluated
 	float2 nxt[KL];
-	auto fetch = [&](long t_) {
-		const int b_ = (int)(t_ / tpr), i0_ = (int)(t_ % tpr) * kCvTile;
+	auto fetch = [&](int t_) {
+		const int b_ = t_ / tpr, i0_ = (t_ - b_ * tpr) * kCvTile;
 		const float2 *xr = reinterpret_cast<const float2 *>(x) + (size_t)b_ * x_stride + (i0_ + start - (HLEN - 1));
 		const int nvalid = min(NW, len - i0_ + HLEN - 1); // samples of the tile inside the range the contract covers
 #pragma unroll
@@ -148,11 +148,11 @@ convolve_blk_kernel(const float *__restrict__ x, int x_stride, const float *__re
 			if (sidx < nvalid) nxt[k] = __ldg(&xr[sidx]);
 		}
 	};
-	const long tstep = (long)gridDim.x * 8;
-	long t = (long)blockIdx.x * 8 + warp;
+	const int tstep = gridDim.x * 8;
+	int t = blockIdx.x * 8 + warp;
 	if (t < ntiles) fetch(t);
 	for (; t < ntiles; t += tstep) {
-		const int b = (int)(t / tpr), i0 = (int)(t % tpr) * kCvTile;
+		const int b = t / tpr, i0 = (t - b * tpr) * kCvTile;
 		__syncwarp();
 #pragma unroll
 		for (int k = 0; k < KL; k++) {

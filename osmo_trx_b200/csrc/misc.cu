@@ -107,6 +107,92 @@ delay_vector_kernel(const float *__restrict__ in, int stride, int len, int n, co
 	}
 }
 
+// delay_vector_blk_kernel — the same arithmetic, register blocked like convolve_blk_kernel (convolve.cu): a warp owns
+// 128 consecutive outputs of one burst, stages the 147 input samples they depend on (zero outside the vector) into a
+// transposed shared window, and each lane evaluates 4 consecutive outputs from 23 samples in registers with the
+// burst's 20 taps read warp-uniformly from __constant__.  The integer shift only moves the window.
+__global__ void __launch_bounds__(256)
+delay_vector_blk_kernel(const float *__restrict__ in, int stride, int len, int n, const float *__restrict__ delay,
+			float *__restrict__ out, int out_stride, float negzero)
+{
+	constexpr int NW = kCvTile + 19, KL = (NW + 31) / 32;
+	__shared__ __align__(16) float2 win_all[8][4 * kCvPitch];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	float2 *win = win_all[warp];
+	const float2 NZ = bc2(negzero);
+	const int tpr = (len + kCvTile - 1) / kCvTile;
+	const int ntiles = n * tpr;
+	float2 nxt[KL];
+	int whole_n = 0, f_n = -1;
+	auto fetch = [&](int t_) {
+		const int b_ = t_ / tpr, i0_ = (t_ - b_ * tpr) * kCvTile;
+		const float dly = delay[b_];
+		whole_n = (int)floorf(dly);
+		const float frac = fs(dly, (float)whole_n);
+		f_n = -1;
+		if ((double)fabsf(frac) > 1e-2) f_n = min(max((int)floorf(fm(frac, 64.0f)), 0), 63);
+		const float2 *x = reinterpret_cast<const float2 *>(in) + (size_t)b_ * stride;
+		const int x0 = i0_ - whole_n - 9; // input index of window sample 0
+#pragma unroll
+		for (int k = 0; k < KL; k++) {
+			const int xi = x0 + lane + 32 * k;
+			nxt[k] = make_float2(0.0f, 0.0f);
+			if (lane + 32 * k < NW && xi >= 0 && xi < len) nxt[k] = __ldg(&x[xi]);
+		}
+	};
+	const int tstep = gridDim.x * 8;
+	int t = blockIdx.x * 8 + warp;
+	if (t < ntiles) fetch(t);
+	for (; t < ntiles; t += tstep) {
+		const int b = t / tpr, i0 = (t - b * tpr) * kCvTile;
+		const int whole = whole_n, f = f_n;
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < KL; k++) {
+			const int sidx = lane + 32 * k;
+			if (sidx < NW) win[(sidx & 3) * kCvPitch + (sidx >> 2)] = nxt[k];
+		}
+		__syncwarp();
+		if (t + tstep < ntiles) fetch(t + tstep);
+		float2 w[23];
+#pragma unroll
+		for (int j = 0; j < 23; j++) w[j] = win[(j & 3) * kCvPitch + lane + (j >> 2)];
+		float2 res[4];
+		if (f >= 0) {
+			const float *hd = c_tab.delay[f];
+#pragma unroll
+			for (int r = 0; r < 4; r++) {
+				float2 L[4];
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+#define PX(k) mul2(w[r + (k)], bc2(hd[(k)]), NZ)
+					L[j] = add2(add2(add2(PX(j), PX(4 + j)), PX(8 + j)), add2(PX(12 + j), PX(16 + j)));
+#undef PX
+				}
+				res[r] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+			}
+		} else {
+#pragma unroll
+			for (int r = 0; r < 4; r++) res[r] = w[r + 9];
+		}
+		float2 *o = reinterpret_cast<float2 *>(out) + (size_t)b * out_stride + i0 + 4 * lane;
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			const int m = i0 + 4 * lane + r - whole; // shifted[i] = y[i - whole], zero where that falls outside the vector
+			if (m < 0 || m >= len) res[r] = make_float2(0.0f, 0.0f);
+		}
+		const int left = len - (i0 + 4 * lane);
+		if (left >= 4 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+			reinterpret_cast<float4 *>(o)[0] = make_float4(res[0].x, res[0].y, res[1].x, res[1].y);
+			reinterpret_cast<float4 *>(o)[1] = make_float4(res[2].x, res[2].y, res[3].x, res[3].y);
+		} else {
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+				if (r < left) o[r] = res[r];
+		}
+	}
+}
+
 // convert_float_short (arch/x86/convert_sse_3.c / convert_sse_4_1.c semantics: multiply, convert with
 // round-to-nearest-even, saturate to int16)
 __device__ __forceinline__ int f2s1(float x, float scale)
