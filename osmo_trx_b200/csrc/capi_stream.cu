@@ -185,6 +185,11 @@ int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *o
 		const int grid = (int)std::min<long>((total_t + kFbT - 1) / kFbT, (long)ctx->sm_count * 3);
 		channelizer64_kernel<<<grid, 256, kCh64Smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
 		r = post_launch(ctx, "channelizer64_kernel");
+	} else if (fb->L == 16 && (fb->m == 4 || fb->m == 8 || fb->m == 16)) {
+		if (fb->m == 4) launch_channelizer_small<4>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		else if (fb->m == 8) launch_channelizer_small<8>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		else launch_channelizer_small<16>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		r = post_launch(ctx, "channelizer_small_kernel");
 	} else {
 		const size_t smem = ((size_t)fb->m * 33 + fb->m) * sizeof(float2);
 		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(channelizer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -218,6 +223,11 @@ int trxb200_synthesis_rotate(trxb200_filterbank *fb, const float *in, float *out
 		const int grid = (int)((ntiles + per - 1) / per);
 		synthesis64_kernel<<<grid, 256, kSy64Smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, total_t, per, fb->d_taps, fb->d_tw);
 		r = post_launch(ctx, "synthesis64_kernel");
+	} else if (fb->L == 16 && (fb->m == 4 || fb->m == 8 || fb->m == 16)) {
+		if (fb->m == 4) launch_synthesis_small<4>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		else if (fb->m == 8) launch_synthesis_small<8>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		else launch_synthesis_small<16>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		r = post_launch(ctx, "synthesis_small_kernel");
 	} else {
 		const size_t smem = ((size_t)fb->m * 65 * 2 + fb->m) * sizeof(float2);
 		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

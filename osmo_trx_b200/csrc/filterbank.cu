@@ -464,6 +464,179 @@ synthesis64_kernel(const float *__restrict__ in, const float *__restrict__ tail_
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// M = 4, 8, 16 with 16-tap branches (the reference's own multi-ARFCN configuration is M = 4, radioInterfaceMulti.cpp:42)
+// ---------------------------------------------------------------------------------------------
+// With few branches a 32-index time tile leaves most of a CTA idle between two barriers.  Here a tile is 8 * 256 / M
+// time indices (512 at M = 4): the FIR role is thread = (branch, 8 consecutive time indices) with a sliding register
+// window as in the M = 64 kernels, the transform role is thread = time index with the M x M twiddle products unrolled
+// from registers, so the wideband side moves in contiguous chunks and every channel row is written 256 bytes per
+// warp instruction.  Rows of M samples get one pad row every 8 (position t + t / 8): both roles then read and write
+// shared memory conflict free.  FMA contraction is allowed for the same reason as at M = 64 (the DFT's parity bar).
+template <int M> struct FbSmall {
+	static constexpr int G = 256 / M;	     // time groups of the FIR role
+	static constexpr int T = 8 * G;		     // time indices per tile
+	static constexpr int XROWS = T + 15 + (T + 15) / 8 + 1;
+	static constexpr int YROWS = T + T / 8;
+	static constexpr size_t kChSmem = (size_t)(XROWS + YROWS) * M * sizeof(float2);
+	static constexpr size_t kSySmem = (size_t)XROWS * M * sizeof(float2);
+};
+
+template <int M>
+__global__ void __launch_bounds__(256)
+channelizer_small_kernel(const float *__restrict__ in, const float *__restrict__ hist_in, float *__restrict__ out, long total_t,
+			 const float *__restrict__ sub, const float2 *__restrict__ tw)
+{
+	using C = FbSmall<M>;
+	extern __shared__ __align__(16) float2 fsm[];
+	float2 *xs = fsm;		       // [XROWS][M] wideband rows t0-15 .. t0+T-1 (padded positions)
+	float2 *y = fsm + C::XROWS * M;	       // [YROWS][M] branch FIR outputs
+	const int tid = threadIdx.x;
+	const int col = tid % M, g = tid / M, r = M - 1 - col; // deinterleave: in[i*m + n] -> branch m-1-n (Channelizer.cpp:44-45)
+	float h[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++) h[k] = __ldg(&sub[r * 16 + k]);
+	float2 w[M];
+#pragma unroll
+	for (int k = 0; k < M; k++) w[k] = __ldg(&tw[k]);
+	const float2 *xin = reinterpret_cast<const float2 *>(in);
+	const float2 *hin = reinterpret_cast<const float2 *>(hist_in);
+	const long ntiles = (total_t + C::T - 1) / C::T;
+	for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const long t0 = tile * C::T;
+		__syncthreads();
+		for (int idx = tid; idx < (C::T + 15) * M; idx += 256) {
+			const int row = idx / M, c = idx % M;
+			const long t = t0 - 15 + row;
+			float2 v = make_float2(0.0f, 0.0f);
+			if (t < 0) v = hin[(M - 1 - c) * 16 + (int)(16 + t)];
+			else if (t < total_t) v = __ldg(&xin[t * M + c]);
+			xs[(row + (row >> 3)) * M + c] = v;
+		}
+		__syncthreads();
+		{
+			float2 acc[8];
+#pragma unroll
+			for (int o = 0; o < 8; o++) acc[o] = make_float2(0.0f, 0.0f);
+#pragma unroll
+			for (int j = 0; j < 23; j++) {
+				const float2 x = xs[(9 * g + j + (j >> 3)) * M + col];
+#pragma unroll
+				for (int o = 0; o < 8; o++)
+					if (j - o >= 0 && j - o < 16) acc[o] = fb_fma2(x, h[j - o], acc[o]);
+			}
+#pragma unroll
+			for (int o = 0; o < 8; o++) y[(9 * g + o) * M + r] = acc[o];
+		}
+		__syncthreads();
+		for (int tt = tid; tt < C::T; tt += 256) {
+			const long t = t0 + tt;
+			float2 yv[M];
+#pragma unroll
+			for (int q = 0; q < M; q++) yv[q] = y[(tt + (tt >> 3)) * M + q];
+			if (t < total_t) {
+#pragma unroll
+				for (int c = 0; c < M; c++) {
+					float ar = 0.0f, ai = 0.0f;
+#pragma unroll
+					for (int q = 0; q < M; q++) {
+						const float2 ww = w[(q * c) % M];
+						ar = fmaf(yv[q].x, ww.x, ar); ar = fmaf(-yv[q].y, ww.y, ar);
+						ai = fmaf(yv[q].x, ww.y, ai); ai = fmaf(yv[q].y, ww.x, ai);
+					}
+					reinterpret_cast<float2 *>(out)[(size_t)c * total_t + t] = make_float2(ar, ai);
+				}
+			}
+		}
+	}
+}
+
+template <int M>
+__global__ void __launch_bounds__(256)
+synthesis_small_kernel(const float *__restrict__ in, const float *__restrict__ tail_in, float *__restrict__ out, long total_t,
+		       const float *__restrict__ sub, const float2 *__restrict__ tw)
+{
+	using C = FbSmall<M>;
+	extern __shared__ __align__(16) float2 fsm[];
+	float2 *vs = fsm; // [XROWS][M] transformed columns t0-15 .. t0+T-1 (padded positions)
+	const int tid = threadIdx.x;
+	const int r = tid % M, g = tid / M;
+	float h[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++) h[k] = __ldg(&sub[r * 16 + k]);
+	float2 w[M];
+#pragma unroll
+	for (int k = 0; k < M; k++) w[k] = __ldg(&tw[k]);
+	const float2 *xin = reinterpret_cast<const float2 *>(in);
+	const float2 *tin = reinterpret_cast<const float2 *>(tail_in);
+	const long ntiles = (total_t + C::T - 1) / C::T;
+	for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const long t0 = tile * C::T;
+		__syncthreads();
+		// forward DFT across channels for every column of the tile and its 15-column halo (recomputed: 3 % at M = 4)
+		for (int j = tid; j < C::T + 15; j += 256) {
+			const long t = t0 - 15 + j;
+			float2 x[M];
+#pragma unroll
+			for (int c = 0; c < M; c++) {
+				x[c] = make_float2(0.0f, 0.0f);
+				if (t >= 0) { if (t < total_t) x[c] = __ldg(&xin[(size_t)c * total_t + t]); }
+				else x[c] = tin[c * 16 + (int)(16 + t)];
+			}
+			float2 *vrow = vs + (j + (j >> 3)) * M;
+#pragma unroll
+			for (int q = 0; q < M; q++) {
+				float ar = 0.0f, ai = 0.0f;
+#pragma unroll
+				for (int c = 0; c < M; c++) {
+					const float2 ww = w[(q * c) % M];
+					ar = fmaf(x[c].x, ww.x, ar); ar = fmaf(-x[c].y, ww.y, ar);
+					ai = fmaf(x[c].x, ww.y, ai); ai = fmaf(x[c].y, ww.x, ai);
+				}
+				vrow[q] = make_float2(ar, ai);
+			}
+		}
+		__syncthreads();
+		// branch FIRs over time, written interleaved out[t*M + r] (Synthesis.cpp:38-49)
+		{
+			float2 acc[8];
+#pragma unroll
+			for (int o = 0; o < 8; o++) acc[o] = make_float2(0.0f, 0.0f);
+#pragma unroll
+			for (int j = 0; j < 23; j++) {
+				const float2 x = vs[(9 * g + j + (j >> 3)) * M + r];
+#pragma unroll
+				for (int o = 0; o < 8; o++)
+					if (j - o >= 0 && j - o < 16) acc[o] = fb_fma2(x, h[j - o], acc[o]);
+			}
+#pragma unroll
+			for (int o = 0; o < 8; o++) {
+				const long t = t0 + 8 * g + o;
+				if (t < total_t) reinterpret_cast<float2 *>(out)[t * M + r] = acc[o];
+			}
+		}
+	}
+}
+
+template <int M>
+static void launch_channelizer_small(int sm_count, cudaStream_t st, const float *in, const float *hist, float *out, long total_t,
+				     const float *sub, const float2 *tw)
+{
+	using C = FbSmall<M>;
+	const long ntiles = (total_t + C::T - 1) / C::T;
+	const int grid = (int)std::max<long>(1, std::min<long>(ntiles, (long)sm_count * 4));
+	channelizer_small_kernel<M><<<grid, 256, C::kChSmem, st>>>(in, hist, out, total_t, sub, tw);
+}
+template <int M>
+static void launch_synthesis_small(int sm_count, cudaStream_t st, const float *in, const float *tail, float *out, long total_t,
+				   const float *sub, const float2 *tw)
+{
+	using C = FbSmall<M>;
+	const long ntiles = (total_t + C::T - 1) / C::T;
+	const int grid = (int)std::max<long>(1, std::min<long>(ntiles, (long)sm_count * 4));
+	synthesis_small_kernel<M><<<grid, 256, C::kSySmem, st>>>(in, tail, out, total_t, sub, tw);
+}
+
 __global__ void synthesis_tail_kernel(const float *__restrict__ in, float *__restrict__ tail_out, int m, int L, long total_t)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
