@@ -42,13 +42,13 @@ struct DetectScratch {
 // device scratch of the pull path (int16 slots -> TRXD datagrams) for one chunk of slots
 struct PullScratch {
 	int cap = 0, soft_stride = 0;
-	float *bursts = nullptr; // [cap][kPullStride] complex float (converted slots)
+	float *bursts = nullptr; // [cap][win] complex float: the correlator windows of the slots (extract_kernel)
+	int win = 0;
 	float *soft = nullptr;	 // [cap][soft_stride]
 	uint8_t *type2 = nullptr, *tsc_out = nullptr;
 	float *amp = nullptr, *toa = nullptr, *ci = nullptr;
 	DetectScratch ws;
 };
-constexpr int kPullStride = 626; // float rows of 5,008 B: every converted slot starts on a 16-byte boundary
 
 struct PullStage; // pinned-host pipeline state of trxb200_pull_host
 
@@ -76,6 +76,7 @@ struct trxb200_ctx {
 		// slower than the serial order (1.75-2.4 ms vs 1.71 ms per 2^20 bursts) - corr_nb_kernel and demod_kernel each
 		// need the whole register file of an SM to hide their latencies - so the pipeline is off unless asked for
 		int overlap = 0, chunk_cap = 131072;
+		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
 		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
 		int ov_corr_bps = 1, ov_peak_bps = 1, ov_peak_warps = 8, ov_demod_bps = 1; // while overlapping: leave room for the other kernel
 	} tune;
@@ -294,6 +295,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		trxb200_ctx::Tune &t = ctx->tune;
 		env_int("TRXB200_OVERLAP", t.overlap);
 		env_int("TRXB200_CHUNK", t.chunk_cap);
+		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
 		env_int("TRXB200_CORR_BPS", t.corr_bps);
 		env_int("TRXB200_PEAK_BPS", t.peak_bps);
 		env_int("TRXB200_PEAK_WARPS", t.peak_warps);
@@ -303,6 +305,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_OV_PEAK_WARPS", t.ov_peak_warps);
 		env_int("TRXB200_OV_DEMOD_BPS", t.ov_demod_bps);
 		if (t.chunk_cap < 4096) t.chunk_cap = 4096;
+		if (t.pull_chunk < 1024) t.pull_chunk = 1024;
 	}
 	ctx->stream = ctx->own_stream;
 	*out = ctx;
@@ -620,24 +623,28 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 
 static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, int stride, int n, int32_t *rc,
 			const float *amp, const float *toa, float *ci, uint8_t *flags, float *soft, int soft_stride,
-			int n_gmsk_soft, int fix_clip, const uint8_t *type = nullptr, int bps = 0)
+			int n_gmsk_soft, int fix_clip, const uint8_t *type = nullptr, int bps = 0, const int16_t *iq = nullptr,
+			int iq_stride = 0, const uint8_t *type_raw = nullptr, float *energy = nullptr)
 {
 	DemodParams p;
 	p.type = type;
+	p.iq = iq; p.iq_stride = iq_stride; p.type_raw = type_raw; p.energy = energy;
 	p.bursts = bursts; p.stride = stride; p.n = n; p.rc = rc; p.amp = amp; p.toa = toa; p.ci = ci; p.flags = flags;
 	p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp; p.dnsamp_g = ctx->d_comp + ctx->ht->comp.size(); p.edge_tab = ctx->d_edge_tab; p.fix_clip = fix_clip;
 	const int wpb = 8;
 	const size_t smem = (size_t)wpb * kDemodWarpFloats * sizeof(float);
 	static bool configured = false;
 	if (!configured) {
-		CK(cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(demod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(demod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		configured = true;
 	}
 	if (bps <= 0) bps = ctx->tune.demod_bps;
 	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * std::max(1, std::min(2, bps)));
 	if (grid < 1) grid = 1;
 	prof_pre(ctx, st);
-	demod_kernel<<<grid, wpb * 32, smem, st>>>(p);
+	if (iq) demod_kernel<true><<<grid, wpb * 32, smem, st>>>(p);
+	else demod_kernel<false><<<grid, wpb * 32, smem, st>>>(p);
 	prof_post(ctx, st, "demod_kernel");
 	return post_launch(ctx, "demod_kernel");
 }
@@ -825,19 +832,28 @@ static void pull_scratch_free(PullScratch &w)
 	w = PullScratch();
 }
 
-static int pull_scratch_get(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, int cap, int soft_stride)
+// part of a slot the detection kernels can read: correlator windows of every burst type the configuration allows
+// (make_attempt in detect.cu: 16-symbol sequences start at sample 209, access bursts at -15; all end by 345 + 4 T)
+static void pull_window(const trxb200_ctx *ctx, int bound, int &s_min, int &W)
 {
-	if (w.cap >= cap && w.soft_stride == soft_stride) return TRXB200_OK;
+	s_min = ctx->max_seq_len >= 40 ? 0 : 208;
+	const int s_max = std::min(624, 345 + 4 * bound + 4);
+	W = ((s_max - s_min) + 3) & ~3;
+}
+
+static int pull_scratch_get(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, int cap, int soft_stride, int win)
+{
+	if (w.cap >= cap && w.soft_stride == soft_stride && w.win == win) return TRXB200_OK;
 	CK(cudaStreamSynchronize(st));
 	DetectScratch keep = w.ws;
 	w.ws = DetectScratch();
 	pull_scratch_free(w);
 	w.ws = keep;
-	CK(cudaMalloc(&w.bursts, (size_t)cap * kPullStride * 8));
+	CK(cudaMalloc(&w.bursts, (size_t)cap * win * 8));
 	CK(cudaMalloc(&w.soft, (size_t)cap * soft_stride * 4));
 	CK(cudaMalloc(&w.type2, cap)); CK(cudaMalloc(&w.tsc_out, cap));
 	CK(cudaMalloc(&w.amp, (size_t)cap * 8)); CK(cudaMalloc(&w.toa, (size_t)cap * 4)); CK(cudaMalloc(&w.ci, (size_t)cap * 4));
-	w.cap = cap; w.soft_stride = soft_stride;
+	w.cap = cap; w.soft_stride = soft_stride; w.win = win;
 	return TRXB200_OK;
 }
 
@@ -867,22 +883,26 @@ static int pull_chunk(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, const t
 		      int32_t *rc, float *energy, uint8_t *pkt, uint16_t *pkt_len, uint8_t *flags, float *amp, float *toa, float *ci,
 		      uint8_t *tsc_out)
 {
-	IngestParams ip;
-	ip.iq = iq; ip.stride_in = a->stride; ip.n = m; ip.type = type; ip.out = w.bursts; ip.stride_out = kPullStride;
-	ip.energy = energy; ip.type_out = w.type2;
+	int s_min, W;
+	pull_window(ctx, a->max_toa_bound, s_min, W);
+	ExtractParams ip;
+	ip.iq = iq; ip.stride_in = a->stride; ip.n = m; ip.type = type; ip.type_out = w.type2; ip.win = w.bursts; ip.W = W; ip.s_min = s_min;
 	prof_pre(ctx, st);
-	ingest_kernel<<<std::max(1, std::min((m + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ip);
-	prof_post(ctx, st, "ingest_kernel");
-	int r = post_launch(ctx, "ingest_kernel");
+	extract_kernel<<<std::max(1, std::min((m + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ip);
+	prof_post(ctx, st, "extract_kernel");
+	int r = post_launch(ctx, "extract_kernel");
 	if (r) return r;
+	// the detection kernels index samples of the full slot: hand them the window buffer shifted back by s_min samples
+	const float *det_rows = w.bursts - (ptrdiff_t)2 * s_min;
 	if (!amp) amp = w.amp;
 	if (!toa) toa = w.toa;
 	if (!ci) ci = w.ci;
 	if (!tsc_out) tsc_out = w.tsc_out;
-	r = launch_detect(ctx, st, w.ws, w.bursts, kPullStride, m, w.type2, tsc, max_toa, a->max_toa_bound, a->thresh, rc, amp, toa,
+	r = launch_detect(ctx, st, w.ws, det_rows, W, m, w.type2, tsc, max_toa, a->max_toa_bound, a->thresh, rc, amp, toa,
 			  tsc_out, ci, flags, 0);
 	if (r) return r;
-	r = launch_demod(ctx, st, w.bursts, kPullStride, m, rc, amp, toa, ci, flags, w.soft, w.soft_stride, 148, 1, w.type2);
+	r = launch_demod(ctx, st, nullptr, 0, m, rc, amp, toa, ci, flags, w.soft, w.soft_stride, 148, 1, w.type2, 0, iq, a->stride, type,
+			 energy);
 	if (r) return r;
 	PackParams pp;
 	pp.n = m; pp.version = a->trxd_version; pp.type = type; pp.rc = rc; pp.toa = toa; pp.ci = ci; pp.energy = energy;
@@ -890,7 +910,7 @@ static int pull_chunk(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, const t
 	pp.full_scale = a->rx_full_scale; pp.rssi_offset = a->rssi_offset; pp.pkt = pkt; pp.pkt_stride = a->pkt_stride;
 	pp.pkt_len = pkt_len; pp.flags = flags;
 	prof_pre(ctx, st);
-	pack_kernel<<<std::max(1, std::min((m + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(pp);
+	pack_kernel<<<std::max(1, std::min((m + 255) / 256, ctx->sm_count * 8)), 256, 0, st>>>(pp);
 	prof_post(ctx, st, "pack_kernel");
 	return post_launch(ctx, "pack_kernel");
 }
@@ -899,8 +919,10 @@ int trxb200_pull_batch(trxb200_ctx *ctx, const trxb200_pull_args *a)
 {
 	int r = pull_check(ctx, a);
 	if (r || a->n == 0) return r;
-	const int cap = 65536;
-	r = pull_scratch_get(ctx, ctx->stream, ctx->pull, std::min(cap, a->n), pull_soft_stride(a));
+	const int cap = ctx->tune.pull_chunk;
+	int s_min_, W_;
+	pull_window(ctx, a->max_toa_bound, s_min_, W_);
+	r = pull_scratch_get(ctx, ctx->stream, ctx->pull, std::min(cap, a->n), pull_soft_stride(a), W_);
 	if (r) return r;
 	for (long lo = 0; lo < a->n; lo += ctx->pull.cap) {
 		const int m = (int)std::min<long>(ctx->pull.cap, a->n - lo);
@@ -964,12 +986,14 @@ int trxb200_pull_host(trxb200_ctx *ctx, const trxb200_pull_args *a)
 		}
 	}
 	const int ss = pull_soft_stride(a);
+	int s_min_, W_;
+	pull_window(ctx, a->max_toa_bound, s_min_, W_);
 	int slot = 0;
 	for (int lo = 0; lo < a->n; lo += chunk, slot = (slot + 1) % PullStage::kSlots) {
 		const int m = std::min(chunk, a->n - lo);
 		cudaStream_t st = s->streams[slot];
 		CK(cudaStreamSynchronize(st)); // the slot's previous chunk (incl. its D2H) has fully landed
-		r = pull_scratch_get(ctx, st, s->w[slot], chunk, ss);
+		r = pull_scratch_get(ctx, st, s->w[slot], chunk, ss, W_);
 		if (r) return r;
 		PullScratch &w = s->w[slot];
 		CK(cudaMemcpyAsync(s->d_iq[slot], a->iq + (size_t)lo * a->stride * 2, (size_t)m * a->stride * 4, cudaMemcpyHostToDevice, st));

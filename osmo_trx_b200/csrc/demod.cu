@@ -49,7 +49,9 @@ constexpr int kBufSlots = kPairs;	 // one window buffer (linear)
 constexpr int kYOff = 320;		 // float offset of the leading-edge Y scratch (float2[32]); outputs (float[156] GMSK /
 					 // float2[160] EDGE) sit below it
 constexpr int kYTopOff = kYOff + 64;	 // float offset of the trailing-edge Y scratch (float2[16])
-constexpr int kScratchFloats = kYTopOff + 64;	 // >= 444: the EDGE soft row is staged over the whole area
+constexpr int kYxOff = kYTopOff + 64;	 // float offset of the converted head of an int16 window (float2[56]); >= 444: the EDGE soft
+					 // row is staged over the area below
+constexpr int kScratchFloats = kYxOff + 112;
 constexpr int kDemodWarpFloats = 2 * 4 * kBufSlots + kScratchFloats + 4; // 2 window buffers + scratch + 2 mbarriers
 
 // ---- packed FP32 (sm_100 FFMA2): both halves are IEEE fma.rn ----
@@ -107,13 +109,28 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// int16 I/Q pair (one 32-bit word) -> complex float without the conversion unit: 0x4B000000 | u is the float 2^23 + u
+// for u < 2^23, so with u = int16 ^ 0x8000 (= value + 32768) one subtraction of 2^23 + 32768 leaves the value, exactly.
+// One LOP3 / PRMT+LOP3 per component and a packed add per sample, all on the full-rate pipes.
+__device__ __forceinline__ float2 cvt_s2(unsigned word)
+{
+	const unsigned lo = (word & 0x0000ffffu) ^ 0x4b008000u;
+	const unsigned hi = __byte_perm(word, 0x4b000000u, 0x7632) ^ 0x00008000u;
+	return fadd2(make_float2(__uint_as_float(lo), __uint_as_float(hi)), make_float2(-8421376.0f, -8421376.0f));
+}
+
+// window sample w as complex float.  I16: the window holds the radio's int16 I/Q pairs as they arrived (pull path:
+// convert_short_float, arch/x86/convert.c:37-79, happens here, on the way to the FIR; (float)int16 is exact)
+template <bool I16>
 __device__ __forceinline__ float2 win_get(const float2 *U, int w)
 {
-	return U[2 * slot_phys(w >> 1) + (w & 1)];
+	if constexpr (I16) return cvt_s2(reinterpret_cast<const unsigned *>(U)[w]);
+	else return U[w];
 }
 
 // generic two-stage evaluation of one decimated sample restricted to decimator taps [kmin,kmax]
 // (only when the shifted burst runs off the top of the 625-sample vector); w0 = window index of tap 0
+template <bool I16>
 __device__ __noinline__ float2 slow_output(const float2 *U, int w0, int f, int kmin, int kmax)
 {
 	float2 acc = make_float2(0.0f, 0.0f);
@@ -122,10 +139,10 @@ __device__ __noinline__ float2 slow_output(const float2 *U, int w0, int f, int k
 		if (f < 64) {
 			for (int j = 0; j < 20; j++) {
 				const float h = c_tab.delay[f][j];
-				y = ffma2(win_get(U, w0 + k + j), make_float2(h, h), y);
+				y = ffma2(win_get<I16>(U, w0 + k + j), make_float2(h, h), y);
 			}
 		} else {
-			y = win_get(U, w0 + k + 9);
+			y = win_get<I16>(U, w0 + k + 9);
 		}
 		const float g = c_tab.dnsamp[k];
 		acc = ffma2(y, make_float2(g, g), acc);
@@ -153,6 +170,7 @@ __device__ __forceinline__ float soft_out(int i, float2 a, float2 s)
 }
 
 // one output with a (possibly truncated) composite: kmin..15 decimator taps present, 35 composite taps
+template <bool I16>
 __device__ __forceinline__ float2 comp_output(const DemodParams &p, const float2 *U, int i, int e, int f, int kmin)
 {
 	const float *__restrict__ c = p.comp + ((size_t)f * 16 + kmin) * 36;
@@ -160,7 +178,7 @@ __device__ __forceinline__ float2 comp_output(const DemodParams &p, const float2
 #pragma unroll 5
 	for (int t = 0; t < 35; t++) {
 		const float ct = __ldg(&c[t]);
-		d = ffma2(win_get(U, 4 * i + t + e), make_float2(ct, ct), d);
+		d = ffma2(win_get<I16>(U, 4 * i + t + e), make_float2(ct, ct), d);
 	}
 	return d;
 }
@@ -247,7 +265,10 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 struct BurstGeom {
 	int whole, f, e, off2;
 };
-__device__ __forceinline__ BurstGeom burst_geom(float toa, unsigned row_par)
+// phase: position of the row's first sample on the 16-byte grid, in samples (float rows: 0..1, int16 rows: 0..3);
+// the window origin off2 is moved down to the grid, the residual shift e is folded into the tap index
+template <bool I16>
+__device__ __forceinline__ BurstGeom burst_geom(float toa, unsigned phase)
 {
 	BurstGeom g;
 	const float delay = fm(-toa, 4.0f);
@@ -259,7 +280,7 @@ __device__ __forceinline__ BurstGeom burst_geom(float toa, unsigned row_par)
 		g.f = min(max(g.f, 0), 63);
 	}
 	const int off = -24 - g.whole;			  // window sample 0 <-> burst sample `off` (before alignment)
-	g.e = (int)(((unsigned)off - row_par) & 1u);	  // residual shift so that off2 has the row's 16B parity
+	g.e = (int)(((unsigned)off + phase) & (I16 ? 3u : 1u)); // residual shift so that off2 sits on the row's 16-byte grid
 	g.off2 = off - g.e;				  // window sample w <-> burst sample w + off2; output i tap t reads w = 4i+t+e
 	return g;
 }
@@ -306,6 +327,73 @@ __device__ __forceinline__ void stage_async(const float2 *x, int off2, float2 *U
 	}
 }
 
+// int16 rows: a 16-byte slot holds FOUR samples, so up to three samples straddle either end of the burst; lanes
+// 24..27 fetch the head slot's samples, lanes 28..31 the tail slot's (patch = the raw 32-bit I/Q word in .x).
+constexpr int kSlots16 = 171; // 684 samples
+__device__ __forceinline__ void stage_async16(const short2 *x, int off2, float2 *U, unsigned bar, int lane, float2 &patch,
+					      int &patch_idx)
+{
+	// slot s holds burst samples off2 + 4s .. off2 + 4s + 3; fully inside the burst for s_first <= s <= s_last
+	const int s_first = off2 >= 0 ? 0 : ((-off2 + 3) >> 2);
+	const int s_last = min(kSlots16 - 1, (621 - off2) >> 2); // floor; negative when the window lies beyond the burst
+	const int count = max(0, s_last - s_first + 1);
+	patch_idx = -1;
+	if (lane >= 24) {
+		const int sl = (lane < 28) ? s_first - 1 : s_last + 1;
+		const int w = 4 * sl + (lane & 3), nidx = off2 + w;
+		if (sl >= 0 && sl < kSlots16 && nidx >= 0 && nidx <= 624) {
+			patch.x = __int_as_float(__ldg(reinterpret_cast<const int *>(x) + nidx));
+			patch_idx = w;
+		}
+	}
+	fence_proxy_async();
+	__syncwarp();
+	float4 *U4 = reinterpret_cast<float4 *>(U);
+	const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	const int nz_hi = count > 0 ? kSlots16 - 1 - s_last : kSlots16;
+	const int nz_lo = count > 0 ? s_first : 0;
+	if (nz_lo + nz_hi <= 32) {
+		const int sidx = lane < nz_lo ? lane : kSlots16 - nz_hi + (lane - nz_lo);
+		if (lane < nz_lo + nz_hi) U4[sidx] = z;
+	} else {
+		for (int sidx = lane; sidx < nz_lo; sidx += 32) U4[sidx] = z;
+		for (int sidx = kSlots16 - nz_hi + lane; sidx < kSlots16; sidx += 32) U4[sidx] = z;
+	}
+	__syncwarp();
+	if (lane == 0) {
+		mbar_arrive_expect_tx(bar, (unsigned)count * 16u);
+		if (count > 0) bulk_g2s(smem_u32(U4 + s_first), x + off2 + 4 * s_first, (unsigned)count * 16u, bar);
+	}
+}
+
+// energyDetect(burst, 20 * sps) of pullRadioVector (Transceiver.cpp:723-731, sigProcLib.cpp:1573-1585) on an int16 slot:
+// sequential float sum of |x[4i]|^2, i < 80, divided by 80.  The samples come from the staged window when it covers
+// them (Uw != nullptr), else from the row; scr: 80 floats of scratch.
+__device__ __forceinline__ void energy16(const short2 *xg, const short2 *Uw, int off2, int lane, float *scr, float *dst)
+{
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const int idx = lane + 32 * k;
+		if (idx < 80) {
+			const unsigned v = Uw ? reinterpret_cast<const unsigned *>(Uw)[4 * idx - off2]
+					      : __ldg(reinterpret_cast<const unsigned *>(xg) + 4 * idx);
+			scr[idx] = norm2(cvt_s2(v));
+		}
+	}
+	__syncwarp();
+	if (lane == 0) {
+		float e = 0.0f;
+#pragma unroll
+		for (int i = 0; i < 20; i++) {
+			const float4 q = reinterpret_cast<const float4 *>(scr)[i];
+			e = fa(fa(fa(fa(e, q.x), q.y), q.z), q.w);
+		}
+		*dst = e / 80.0f;
+	}
+	__syncwarp();
+}
+
+template <bool I16>
 __global__ void __launch_bounds__(256, 2)
 demod_kernel(DemodParams p)
 {
@@ -317,9 +405,20 @@ demod_kernel(DemodParams p)
 	float2 *decs = reinterpret_cast<float2 *>(ostage);
 	float2 *yv = reinterpret_cast<float2 *>(ostage + kYOff);
 	float2 *ytop = reinterpret_cast<float2 *>(ostage + kYTopOff);
+	float2 *yx = reinterpret_cast<float2 *>(ostage + kYxOff);
 	const unsigned bar0 = smem_u32(ostage + kScratchFloats); // two 8-byte mbarriers, one per window buffer
-	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
 	const int step = gridDim.x * wpb;
+	// row pointer (float2 or short2 samples), its phase on the 16-byte grid, and the staging call for one burst
+	auto row_f = [&](int b_) { return reinterpret_cast<const float2 *>(p.bursts) + (size_t)b_ * p.stride; };
+	auto row_s = [&](int b_) { return reinterpret_cast<const short2 *>(p.iq) + (size_t)b_ * p.iq_stride; };
+	auto row_phase = [&](int b_) {
+		if constexpr (I16) return (unsigned)((reinterpret_cast<uintptr_t>(row_s(b_)) >> 2) & 3u);
+		else return (unsigned)((reinterpret_cast<uintptr_t>(row_f(b_)) >> 3) & 1u);
+	};
+	auto stage = [&](int b_, int off2, float2 *Ub, unsigned bar, float2 &patch, int &patch_idx) {
+		if constexpr (I16) stage_async16(row_s(b_), off2, Ub, bar, lane, patch, patch_idx);
+		else stage_async(row_f(b_), off2, Ub, bar, lane, patch, patch_idx);
+	};
 	// decimator taps this lane applies in the leading-output correction (k = 4*(lane&3) + kk)
 	float gk[4];
 #pragma unroll
@@ -352,16 +451,13 @@ demod_kernel(DemodParams p)
 	float2 patch_n = make_float2(0.0f, 0.0f); // straddling sample of the burst being staged (lane 31)
 	int patch_idx_n = -1;
 	if (b < p.n && rc0 > 0) {
-		const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
-		const BurstGeom g0 = burst_geom(toa0, row_par);
-		stage_async(reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride, g0.off2, Ubase, bar0, lane, patch_n,
-			    patch_idx_n);
+		const BurstGeom g0 = burst_geom<I16>(toa0, row_phase(b));
+		stage(b, g0.off2, Ubase, bar0, patch_n, patch_idx_n);
 	}
 	for (; b < p.n; b += step, cur ^= 1) {
 		const int rc = rc0;
 		const float2 amp = amp0;
 		const float toa = toa0;
-		const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
 		float2 *U = Ubase + (size_t)cur * 2 * kBufSlots;
 		const float2 patch = patch_n;
 		const int patch_idx = patch_idx_n;
@@ -371,10 +467,8 @@ demod_kernel(DemodParams p)
 			const int bn = b + step;
 			rc0 = rc1; amp0 = amp1; toa0 = toa1;
 			if (bn < p.n && rc0 > 0) {
-				const unsigned rp = (base_par + (unsigned)(((size_t)bn * (size_t)p.stride) & 1u)) & 1u;
-				const BurstGeom gn = burst_geom(toa0, rp);
-				stage_async(reinterpret_cast<const float2 *>(p.bursts) + (size_t)bn * p.stride, gn.off2,
-					    Ubase + (size_t)(cur ^ 1) * 2 * kBufSlots, bar0 + 8 * (cur ^ 1), lane, patch_n, patch_idx_n);
+				const BurstGeom gn = burst_geom<I16>(toa0, row_phase(bn));
+				stage(bn, gn.off2, Ubase + (size_t)(cur ^ 1) * 2 * kBufSlots, bar0 + 8 * (cur ^ 1), patch_n, patch_idx_n);
 			}
 			const int bnn = bn + step;
 			rc1 = 0;
@@ -385,6 +479,13 @@ demod_kernel(DemodParams p)
 			}
 		}
 
+		// pull path: the slot's power measurement (every slot that is not switched off, detected or not)
+		bool want_energy = false;
+		if constexpr (I16) {
+			want_energy = p.type_raw[b] != 0;
+			if (!want_energy && lane == 0) p.energy[b] = 0.0f;
+			if (want_energy && rc <= 0) energy16(row_s(b), nullptr, 0, lane, reinterpret_cast<float *>(yv), &p.energy[b]);
+		}
 		if (rc <= 0) {
 			// undetected burst: only the deferred clipping report is left to do (sigProcLib.cpp:1746-1764)
 			if (p.fix_clip && rc == 0 && (!p.type || type_known(p.type[b]))) {
@@ -392,7 +493,14 @@ demod_kernel(DemodParams p)
 #pragma unroll
 				for (int k = 0; k < 20; k++) {
 					const int i = lane + 32 * k;
-					v[k] = i < 625 ? __ldg(&x[i]) : make_float2(0.0f, 0.0f);
+					v[k] = make_float2(0.0f, 0.0f);
+					if (i < 625) {
+						if constexpr (I16) {
+							v[k] = cvt_s2(__ldg(reinterpret_cast<const unsigned *>(row_s(b)) + i));
+						} else {
+							v[k] = __ldg(&row_f(b)[i]);
+						}
+					}
 				}
 				float mx = 0.0f;
 #pragma unroll
@@ -411,16 +519,25 @@ demod_kernel(DemodParams p)
 		// ---- per-burst scalars ----
 		const float ian = __frcp_rn(norm2(amp));
 		const float2 s = make_float2(amp.x * ian, -amp.y * ian); // (complex)1.0 / amp (soft bits carry a 1e-4 tolerance)
-		const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
-		const BurstGeom bg = burst_geom(toa, row_par);
-		const int whole = bg.whole, f = bg.f, e = bg.e;
+		const BurstGeom bg = burst_geom<I16>(toa, row_phase(b));
+		const int whole = bg.whole, f = bg.f, e = bg.e; // e: 0..1 (float rows) / 0..3 (int16 rows)
 		const bool edge = (rc == 5);
 
 		// ---- the burst's window: straddling sample, then wait for the bulk copies ----
-		if (patch_idx >= 0) U[patch_idx] = patch;
+		if (patch_idx >= 0) {
+			if constexpr (I16) reinterpret_cast<int *>(U)[patch_idx] = __float_as_int(patch.x);
+			else U[patch_idx] = patch;
+		}
 		__syncwarp();
 		mbar_wait(bar0 + 8 * cur, (phase >> cur) & 1u);
 		phase ^= 1u << cur;
+		if constexpr (I16) {
+			if (want_energy) {
+				const bool in_win = bg.off2 <= 0 && 316 - bg.off2 < 4 * kSlots16;
+				energy16(row_s(b), in_win ? reinterpret_cast<const short2 *>(U) : nullptr, bg.off2, lane,
+					 reinterpret_cast<float *>(yv), &p.energy[b]);
+			}
+		}
 
 		// ---- main pass (transposed FIR), shared by GMSK and EDGE: lane owns window samples 20*lane ..
 		//      20*lane+19 and accumulates into outputs i = 5*lane - 8 + m, m = 0..12; sample j meets output m
@@ -431,16 +548,24 @@ demod_kernel(DemodParams p)
 #pragma unroll
 			for (int m = 0; m < 13; m++) acc[m] = make_float2(0.0f, 0.0f);
 			const float4 *xc4 = reinterpret_cast<const float4 *>(U) + 10 * lane;
-			const float *__restrict__ ce = c_tab.comp0[f][e];
+			// int16 rows: the same 20 samples as ten 8-byte pairs, starting (e & 2) samples in
+			const uint2 *xc2 = reinterpret_cast<const uint2 *>(reinterpret_cast<const short2 *>(U) + 20 * lane + (e & 2));
+			const float *__restrict__ ce = c_tab.comp0[f][e & 1];
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
 				// samples j = 4k + 2h and 4k + 2h + 1, k = 0..4
 				float2 xa[5], xb[5];
 #pragma unroll
 				for (int k = 0; k < 5; k++) {
-					const float4 v = xc4[2 * k + h];
-					xa[k] = make_float2(v.x, v.y);
-					xb[k] = make_float2(v.z, v.w);
+					if constexpr (I16) {
+						const uint2 v = xc2[2 * k + h];
+						xa[k] = cvt_s2(v.x);
+						xb[k] = cvt_s2(v.y);
+					} else {
+						const float4 v = xc4[2 * k + h];
+						xa[k] = make_float2(v.x, v.y);
+						xb[k] = make_float2(v.z, v.w);
+					}
 				}
 #pragma unroll
 				for (int g = 0; g < 9; g++) {
@@ -500,7 +625,7 @@ demod_kernel(DemodParams p)
 					const int t = 9 * part + tt;
 					if (t < 35) {
 						const float ct = __ldg(&c[t]);
-						d = ffma2(win_get(U, 4 * i + t + e), make_float2(ct, ct), d);
+						d = ffma2(win_get<I16>(U, 4 * i + t + e), make_float2(ct, ct), d);
 					}
 				}
 			}
@@ -527,22 +652,33 @@ demod_kernel(DemodParams p)
 			// Lanes evaluate v = lane (leading edge); lanes 0..15 also v = q0 + lane (trailing edge).
 			const int q0c = min(max(q0, 0), 644);
 			float2 y = make_float2(0.0f, 0.0f), yt = make_float2(0.0f, 0.0f);
+			// int16 rows: the 52 window samples the leading Y values share are converted once (two per lane)
+			const float2 *uy = U + e;
+			if constexpr (I16) {
+				if (lane < 28) {
+					const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned *>(U) + (e & 2) + 2 * lane);
+					const float2 a = cvt_s2(v.x), c = cvt_s2(v.y);
+					reinterpret_cast<float4 *>(yx)[lane] = make_float4(a.x, a.y, c.x, c.y);
+				}
+				__syncwarp();
+				uy = yx + (e & 1);
+			}
 			if (f < 64) {
 #pragma unroll
 				for (int j = 0; j < 20; j++) {
 					const float hj = c_tab.delay[f][j];
-					y = ffma2(U[lane + e + j], make_float2(hj, hj), y);
+					y = ffma2(uy[lane + j], make_float2(hj, hj), y);
 				}
 				if (top_trunc && lane < 16) {
 #pragma unroll
 					for (int j = 0; j < 20; j++) {
 						const float hj = c_tab.delay[f][j];
-						yt = ffma2(U[q0c + lane + e + j], make_float2(hj, hj), yt);
+						yt = ffma2(win_get<I16>(U, q0c + lane + e + j), make_float2(hj, hj), yt);
 					}
 				}
 			} else {
-				y = U[lane + e + 9];
-				if (top_trunc && lane < 16) yt = U[q0c + lane + e + 9];
+				y = uy[lane + 9];
+				if (top_trunc && lane < 16) yt = win_get<I16>(U, q0c + lane + e + 9);
 			}
 			yv[lane] = y;
 			if (lane < 16) ytop[lane] = yt;
@@ -611,7 +747,7 @@ demod_kernel(DemodParams p)
 				const int kmax = min(15, 639 + whole - 4 * i);
 				float2 d = make_float2(0.0f, 0.0f);
 				if (kmin <= kmax)
-					d = (kmax == 15) ? comp_output(p, U, i, e, f, kmin) : slow_output(U, 4 * i + e, f, kmin, kmax);
+					d = (kmax == 15) ? comp_output<I16>(p, U, i, e, f, kmin) : slow_output<I16>(U, 4 * i + e, f, kmin, kmax);
 				if (edge) decs[2 + i] = cscale(d, s);
 				else ostage[i] = soft_out(i, d, s);
 			}

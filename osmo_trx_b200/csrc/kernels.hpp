@@ -52,17 +52,22 @@ struct DemodParams {
 	const float2 *edge_tab; // [16] derotation (cosf,-sinf)((i%16)*3pi/8) then [9] ideal 8-PSK points k=-4..4
 	int fix_clip;
 	const uint8_t *type; // burst types as detection saw them (clip report only for types detectAnyBurst handles); may be null
+	// pull path (demod_kernel<true>): the slots as the radio delivered them, and the per-slot power measurement
+	const int16_t *iq;	 // [n][iq_stride] complex int16 (I,Q); replaces `bursts`
+	int iq_stride;
+	const uint8_t *type_raw; // slot types as scheduled by the caller (0 = off: no measurement)
+	float *energy;		 // energyDetect(slot, 80)
 };
 
 // receive chain around the hot path (pull.cu)
-struct IngestParams {
-	const int16_t *iq; // [n][stride_in] complex int16 (I,Q)
+// pull path, detection input: per slot the part of the slot the correlators read, as complex float
+struct ExtractParams {
+	const int16_t *iq; // [n][stride_in] complex int16
 	int stride_in, n;
 	const uint8_t *type; // CorrType per slot as scheduled by the caller
-	float *out;	     // [n][stride_out] complex float
-	int stride_out;
-	float *energy;	   // energyDetect(burst, 80)
-	uint8_t *type_out; // type as detection must see it (OFF / IDLE -> 0)
+	uint8_t *type_out;   // type as detection must see it (OFF / IDLE -> 0)
+	float *win;	     // [n][W] complex float: samples s_min .. s_min + W - 1 of each slot
+	int W, s_min;
 };
 
 struct PackParams {

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--case", default="nb")
     ap.add_argument("--n", type=int, default=1 << 16)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--prof", action="store_true", help="print the per-kernel CUDA-event split of one call (ms, launches)")
+    ap.add_argument("--time", action="store_true", help="print the CUDA-event time per call after warm-up")
     args = ap.parse_args()
     import bench
     from osmo_trx_b200 import Trx, Resampler, Channelizer, Synthesis
@@ -72,6 +74,19 @@ def main():
     for _ in range(args.reps):
         fn()
     torch.cuda.synchronize()
+    if args.prof:
+        trx.profile_begin()
+        fn()
+        print({k: (round(v[0], 4), v[1]) for k, v in trx.profile_end().items()})
+    if args.time:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        print(f"{args.case} n={n}: {ms:.4f} ms per call, {n / ms * 1e3:.4g} units/s")
 
 
 if __name__ == "__main__":
