@@ -277,7 +277,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "bursts/s", "cores": cores, "kind": kind,
                              "sample": f"{n} bursts per step, {cores} threads"},
             "e2e": {"value": v, "unit": "bursts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(kind):
@@ -287,8 +287,27 @@ def workload_name(kind):
             "edge": "cfg3: EDGE 8-PSK normal bursts, detectAnyBurst(EDGE,max_toa=4)+demodAnyBurst"}[kind]
 
 
+_REAL_STDOUT = None
+
+
+def _stdout_to_stderr():
+    """stdout carries exactly one JSON line: everything else written to fd 1 (NCCL prints its version banner there
+    from C) goes to stderr; emit() writes the line to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    _stdout_to_stderr()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -465,7 +484,7 @@ def main():
                            "l2": "inputs (5.2 GB/GPU) far exceed the 126 MB L2; no flush needed",
                            "detected_fraction": det_frac, "sharding": "independent bursts, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32, "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
