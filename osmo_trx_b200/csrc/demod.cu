@@ -701,12 +701,13 @@ demod_kernel(DemodParams p)
 					d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
 					d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
 					if (i < nlead && part == 0) {
+						// every tap dropped: the reference's sample is an exact zero - store the zero, not a rounding residue
+						const bool none = kmin > min(15, 639 + whole - 4 * i);
 						if (edge) {
 							const float2 c2 = cscale(d, s);
-							decs[2 + i].x -= c2.x;
-							decs[2 + i].y -= c2.y;
+							decs[2 + i] = none ? make_float2(0.0f, 0.0f) : make_float2(decs[2 + i].x - c2.x, decs[2 + i].y - c2.y);
 						} else {
-							ostage[i] -= soft_out(i, d, s);
+							ostage[i] = none ? 0.0f : ostage[i] - soft_out(i, d, s);
 						}
 					}
 				}

@@ -1,0 +1,161 @@
+"""BASELINE.json's full sizes on the GPU: the CPU checker cannot run millions of bursts in a test, so the large
+batches are checked through size-independent properties plus exact parity on a random subset.
+
+* subset parity: a few thousand bursts drawn at random from the big batch go through the CPU checker
+  (the same criteria as tests/parity.py everywhere else);
+* power-of-two scaling: multiplying every sample by 2 is exact in float32, and every stage of the chain is
+  homogeneous, so rc / TSC / TOA / C/I / soft bits must come back bit-identical and amp exactly doubled - except
+  where the detection threshold's additive 1e-5 (sigProcLib.cpp:1541-1571) decides a burst sitting on the threshold;
+* batch independence: the two halves processed separately equal the whole batch, bit for bit;
+* sanity of the decisions against the generator (detected fraction, TOA inside the search window).
+"""
+import numpy as np
+import pytest
+import torch
+
+import bench
+import parity
+from cpulibs import TSC, RACH, EDGE
+
+pytestmark = pytest.mark.gpu
+
+N = 1 << 20
+SUBSET = 1500
+
+
+def beq(a, b):
+    """bitwise equality (NaNs of undetected bursts compare equal to themselves)"""
+    if a.dtype == torch.float32:
+        a, b = a.contiguous().view(torch.int32), b.contiguous().view(torch.int32)
+    return bool(torch.equal(a, b))
+
+
+def _run(trx, rx, typ, tsc, mt, bound, soft):
+    out = trx.alloc_results(rx.shape[0], soft)
+    trx.detect_demod(rx, typ, tsc, mt, bound, n_gmsk_soft=148, out=out)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("kind,batches", [("nb", 1), ("rach", 1), ("edge", 10)])
+def test_fullsize_detect_demod(trx, checker, kind, batches):
+    """cfg1 recipe at GPU scale (2^20), cfg2 (1M access bursts), cfg3 (10M EDGE bursts as 10 batches of 2^20)."""
+    soft = 444 if kind == "edge" else 148
+    cfg = {"nb": (16, 1), "rach": (40, 1), "edge": (16, 2)}[kind]
+    rng = np.random.default_rng(77)
+    try:
+        trx.detect_config(*cfg)
+        for bi in range(batches):
+            rx, typ, tsc, mt, bound = bench.make_workload(trx, kind, N, seed=500 + bi, device=trx.device)
+            full = _run(trx, rx, typ, tsc, mt, bound, soft)
+            rc = full["rc"].cpu().numpy()
+            toa = full["toa"].cpu().numpy()
+            det = rc > 0
+            # the generator kills 5 % of the bursts and draws SNRs 30/10/6 dB (+15 dB for EDGE)
+            assert 0.90 < det.mean() <= 0.9501 + 0.002, (kind, det.mean())
+            assert (rc[det] == {"nb": TSC, "rach": RACH, "edge": EDGE}[kind]).mean() > 0.999
+            assert np.all(np.abs(toa[det]) <= bound + 12.0)  # search window: head 10 (8 for RACH), tail 6 + max_toa
+            assert not np.isnan(full["soft"][:1024].cpu().numpy()).any()
+
+            # ---- exact parity on a random subset, through the CPU checker ----
+            idx = np.sort(rng.choice(N, SUBSET, replace=False))
+            tidx = torch.from_numpy(idx).to(trx.device)
+            sub = {k: v[tidx].cpu().numpy() for k, v in full.items()}
+            c = checker.detect_demod(rx[tidx].cpu().numpy(), typ[tidx].cpu().numpy(), tsc[tidx].cpu().numpy(),
+                                     mt[tidx].cpu().numpy().astype(np.int64), nthreads=8)
+            rep = parity.compare_detect(sub, c, sub["flags"], f"{kind} full-size subset")
+            ok = rep["ok_mask"]
+            parity.compare_ci(sub["ci"], c["ci"], ok, kind)
+            # 8-PSK bursts carry 444 soft values, GMSK ones (incl. the EDGE -> TSC fall-through) the 148 asked for
+            sr = parity.compare_soft(sub["soft"], c["soft"], ok & (c["rc"] != EDGE), 148, kind + " gmsk")
+            se = parity.compare_soft(sub["soft"], c["soft"], ok & (c["rc"] == EDGE), 444, kind + " 8psk")
+            print(kind, bi, {k: v for k, v in rep.items() if k not in ("ok_mask", "_ga")}, sr, se)
+
+            if bi == 0:
+                # ---- batch independence ----
+                h = N // 2 + 13  # odd split: different warp / tile boundaries
+                a = _run(trx, rx[:h], typ[:h], tsc[:h], mt[:h], bound, soft)
+                b = _run(trx, rx[h:], typ[h:], tsc[h:], mt[h:], bound, soft)
+                for k in ("rc", "toa", "amp", "tsc", "ci", "soft"):
+                    assert beq(full[k][:h], a[k]) and beq(full[k][h:], b[k]), (kind, "split", k)
+                del a, b
+
+                # ---- power-of-two scaling ----
+                keep = {k: full[k].clone() for k in ("rc", "toa", "amp", "tsc", "ci", "soft")}
+                rx.mul_(2.0)
+                dbl = _run(trx, rx, typ, tsc, mt, bound, soft)
+                same_rc = keep["rc"] == dbl["rc"]
+                flips = int((~same_rc).sum())
+                assert flips <= N // 10000, (kind, "threshold flips under x2 scaling", flips)
+                m = same_rc
+                assert beq(keep["toa"][m], dbl["toa"][m]), kind
+                assert beq(keep["tsc"][m], dbl["tsc"][m]), kind
+                assert beq(keep["amp"][m] * 2.0, dbl["amp"][m]), kind
+                assert beq(keep["soft"][m], dbl["soft"][m]), kind
+                assert beq(keep["ci"][m], dbl["ci"][m]), kind
+                print(kind, "x2 scaling: threshold flips", flips, "of", N)
+                del keep, dbl
+            del rx, full
+    finally:
+        trx.detect_config(40, 3)
+
+
+def test_fullsize_vitac(trx, checker):
+    """cfg4: the MLSE equaliser on 2^20-burst batches (10 M = ten of them; three are run here): subset parity with the
+    CPU checker (start and all 148 decisions exact) and batch independence."""
+    rng = np.random.default_rng(78)
+    for bi in range(3):
+        rx, typ, tsc, mt, bound = bench.make_workload(trx, "nb", N, seed=600 + bi, device=trx.device)
+        buf = torch.zeros((N, 40 + 625 + 63, 2), dtype=torch.float32, device=trx.device)
+        buf[:, 40:665] = rx
+        del rx
+        g = trx.vitac(buf, 40, tsc)
+        torch.cuda.synchronize()
+        idx = np.sort(rng.choice(N, SUBSET, replace=False))
+        tidx = torch.from_numpy(idx).to(trx.device)
+        c = checker.vitac(buf[tidx].cpu().numpy(), 40, tsc[tidx].cpu().numpy(), nthreads=8)
+        assert np.array_equal(g["start"][tidx].cpu().numpy(), c["start"])
+        assert np.array_equal(g["bits"][tidx].cpu().numpy(), c["bits"])
+        assert np.allclose(g["corr_max"][tidx].cpu().numpy(), c["corr_max"], rtol=1e-4, atol=0)
+        if bi == 0:
+            h = N // 2 + 7  # odd split: the pair kernel's tail
+            a = trx.vitac(buf[:h], 40, tsc[:h])
+            b = trx.vitac(buf[h:], 40, tsc[h:])
+            torch.cuda.synchronize()
+            for k in ("start", "bits", "corr_max"):
+                assert beq(g[k][:h], a[k]) and beq(g[k][h:], b[k]), k
+        del buf, g
+
+
+def test_fullsize_pull(trx, checker):
+    """The int16 -> TRXD chain on 2^20 slots: datagrams of a random subset equal the CPU checker's, batch independent."""
+    rng = np.random.default_rng(79)
+    try:
+        trx.detect_config(16, 1)
+        rx, typ, tsc, mt, bound = bench.make_workload(trx, "nb", N, seed=700, device=trx.device)
+        iq = (rx * bench.IQ_SCALE).round().clamp(-32768, 32767).to(torch.int16)
+        del rx
+        fn = (torch.arange(N, device=trx.device, dtype=torch.int32) // 8)
+        tn = (torch.arange(N, device=trx.device) % 8).to(torch.uint8)
+        po = trx.alloc_pull_results(N, 160)
+        trx.pull(iq, typ, tsc, mt, fn, tn, bound, out=po)
+        torch.cuda.synchronize()
+        h = N // 2 + 5
+        pa = trx.alloc_pull_results(h, 160)
+        trx.pull(iq[:h], typ[:h], tsc[:h], mt[:h], fn[:h], tn[:h], bound, out=pa)
+        torch.cuda.synchronize()
+        for k in ("rc", "energy", "pkt_len"):
+            assert beq(po[k][:h], pa[k]), k
+        live = pa["pkt_len"] > 0
+        assert torch.equal(po["pkt"][:h][live], pa["pkt"][live])
+        idx = np.sort(rng.choice(N, SUBSET, replace=False))
+        tidx = torch.from_numpy(idx).to(trx.device)
+        g = {k: po[k][tidx].cpu().numpy() for k in ("rc", "energy", "pkt", "pkt_len", "flags")}
+        g["pkt_len"] = g["pkt_len"].view(np.uint16)
+        c = checker.pull(iq[tidx].cpu().numpy(), typ[tidx].cpu().numpy(), tsc[tidx].cpu().numpy(),
+                         mt[tidx].cpu().numpy().astype(np.uint16), fn[tidx].cpu().numpy().astype(np.uint32), tn[tidx].cpu().numpy(),
+                         version=1, rssi_offset=0.0, pkt_stride=160, nthreads=8)
+        rep = parity.compare_pkts(g, c, None, "pull full-size subset", version=1)
+        print("pull full-size", rep)
+    finally:
+        trx.detect_config(40, 3)
