@@ -159,3 +159,93 @@ def test_fullsize_pull(trx, checker):
         print("pull full-size", rep)
     finally:
         trx.detect_config(40, 3)
+
+
+def test_cfg5_wideband_chain(trx, checker):
+    """BASELINE configs[4] at test scale: 64 ARFCNs, 52 normal bursts each.  TX mirror on the CPU checker
+    (Resampler(48,65) per channel -> Synthesis(64,192), radioInterfaceMulti.cpp:323-344); RX on the GPU
+    (Channelizer(64,192) -> Resampler(65,48) -> slot slicing -> detectAnyBurst + demodAnyBurst), against the same RX
+    chain on the CPU checker.  The channelizer's DFT carries the 1e-4 bar (FFTW is unpinned in the reference), so
+    the chain is compared at decision level: rc and TSC equal, TOA within one interpolation quantum (1/256 symbol,
+    the reference's own SSE/scalar noise floor), soft bits within 1e-3 of the burst's scale."""
+    import osmo_trx_b200
+    import synth
+    M, BL, K = 64, 192, 52            # 52 bursts x 625 samples = 125 blocks of 260 samples at 4 sps per channel
+    rng = np.random.default_rng(81)
+    nblk = K * 625 // 260
+    tsc = (np.arange(M * K) % 8).astype(np.uint8)
+    w = checker.modulate_gmsk_batch(synth.nb_bits(M * K, tsc, rng), nthreads=8)
+    gain = rng.uniform(0.3, 1.0, (M * K, 1, 1)).astype(np.float32)
+    streams = (w * gain).reshape(M, K * 625, 2)
+    def cpu_resample(p_, q_, x, n_in, n_out):
+        """block by block as radioInterfaceMulti does (Resampler::rotate precomputes its paths for short outputs)"""
+        hr = checker.resampler(p_, q_)
+        xx = np.concatenate([np.zeros((16, 2), np.float32), x])
+        out = []
+        for k in range(len(x) // n_in):
+            rc, y = checker.resampler_rotate(hr, xx[k * n_in:k * n_in + n_in + 16], 16, n_out)
+            assert rc == n_out
+            out.append(y)
+        return np.concatenate(out)
+
+    # ---- TX mirror on the checker ----
+    chan = np.zeros((M, nblk * BL, 2), np.float32)
+    for c in range(M):
+        chan[c] = cpu_resample(48, 65, streams[c], 260, BL)
+    sy = checker.synthesis(M, BL)
+    wide = np.concatenate([checker.synthesis_rotate(sy, np.ascontiguousarray(chan[:, k * BL:(k + 1) * BL]), M, BL)[1]
+                           for k in range(nblk)])
+    wide += rng.standard_normal(wide.shape).astype(np.float32) * 1e-3
+    # ---- RX on the checker ----
+    cc = checker.channelizer(M, BL)
+    rxc = np.concatenate([checker.channelizer_rotate(cc, wide[k * M * BL:(k + 1) * M * BL], M, BL)[1] for k in range(nblk)], axis=1)
+    back_c = np.zeros((M, K * 625, 2), np.float32)
+    for c in range(M):
+        back_c[c] = cpu_resample(65, 48, rxc[c], BL, 260)
+    # ---- RX on the GPU ----
+    ch = osmo_trx_b200.Channelizer(trx, M, BL)
+    rs = osmo_trx_b200.Resampler(trx, 65, 48)
+    rxg = ch.rotate(torch.from_numpy(wide).cuda())                      # [M][nblk*BL][2]
+    assert np.abs(rxg.cpu().numpy() - rxc).max() <= 1e-4 * np.abs(rxc).max()
+    # every (channel, block) is one stream of the batched rotate: 16 samples of history, then the 192 new ones
+    pad = torch.zeros((M, 16 + nblk * BL, 2), dtype=torch.float32, device=trx.device)
+    pad[:, 16:] = rxg
+    xin = pad.unfold(1, 16 + BL, BL).permute(0, 1, 3, 2).reshape(M * nblk, 16 + BL, 2).contiguous()
+    back_g = rs.rotate(xin, 260).reshape(M, nblk * 260, 2)              # [M][K*625][2]
+    torch.cuda.synchronize()
+    # ---- the filterbank chain delays the streams: find the whole-sample lag on channel 0 and slice both alike ----
+    ref0 = streams[0, :, 0] + 1j * streams[0, :, 1]
+    got0 = back_c[0, :, 0] + 1j * back_c[0, :, 1]
+    lags = np.arange(0, 200)
+    corr = [np.abs(np.vdot(ref0[:20000], got0[l:l + 20000])) for l in lags]
+    lag = int(lags[int(np.argmax(corr))])
+    assert max(corr) > 0.5 * np.vdot(ref0[:20000], ref0[:20000]).real, "chain output does not resemble its input"
+    nb = K - 1                                                          # the last slot runs off the end by `lag`
+
+    def slots(a):
+        return np.ascontiguousarray(a[:, lag:lag + nb * 625].reshape(M * nb, 625, 2))
+    sg, sc = slots(back_g.cpu().numpy()), slots(back_c)
+    tsc_s = np.ascontiguousarray(tsc.reshape(M, K)[:, :nb].reshape(-1))
+    try:
+        trx.detect_config(16, 1)
+        n = M * nb
+        r = trx.detect_demod(torch.from_numpy(sg).cuda(), torch.full((n,), TSC, dtype=torch.uint8, device=trx.device),
+                             torch.from_numpy(tsc_s).cuda(), torch.full((n,), 4, dtype=torch.int16, device=trx.device), 4,
+                             n_gmsk_soft=148)
+        torch.cuda.synchronize()
+    finally:
+        trx.detect_config(40, 3)
+    g = {k: v.cpu().numpy() for k, v in r.items()}
+    c = checker.detect_demod(sc, TSC, tsc_s, 4, nthreads=8)
+    assert (c["rc"] == TSC).mean() > 0.99, "the CPU chain itself must detect its bursts"
+    assert np.array_equal(g["rc"], c["rc"]) and np.array_equal(g["tsc"][c["rc"] > 0], c["tsc"][c["rc"] > 0])
+    det = c["rc"] > 0
+    dtoa = np.abs(g["toa"][det].astype(np.float64) - c["toa"][det])
+    assert dtoa.max() <= 1.0 / 256 + 1e-9, dtoa.max()
+    same = det.copy()
+    same[det] = dtoa == 0
+    scale = np.abs(c["soft"][same][:, :148]).max(axis=1, keepdims=True)
+    rel = np.abs(g["soft"][same][:, :148].astype(np.float64) - c["soft"][same][:, :148]) / scale
+    assert rel.max() <= 1e-3, rel.max()
+    print("cfg5 chain: lag", lag, "slots", n, "detected", int(det.sum()), "toa quantum flips", int((dtoa > 0).sum()),
+          "soft rel max", float(rel.max()))
