@@ -46,11 +46,24 @@ def main():
     n = args.n
     rows = []
 
-    def add(name, unit, units, bytes_per_unit, ms, note=""):
+    # FP32 pipe: 128 lanes per SM per clock; a multiply, an add or an FMA each occupy one lane slot ("lane-op")
+    props = torch.cuda.get_device_properties(dev)
+    fp32_peak = props.multi_processor_count * 128 * 1.965e9
+
+    def add(name, unit, units, bytes_per_unit, ms, note="", ops=None):
+        """ops: FP32 lane-ops per unit in the reference's operation order (exact chains cannot fuse mul+add), for the
+        kernels whose arithmetic rather than their bytes bounds them"""
         gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9
-        rows.append(dict(kernel=name, unit=unit, units_per_launch=units, alg_bytes_per_unit=bytes_per_unit, ms=ms,
-                         units_per_s=units / (ms * 1e-3), achieved_gbs=gbs, frac_of_hbm_peak=gbs / peak, note=note))
-        print(f"{name:34s} {units / (ms * 1e-3):12.4g} {unit}/s  {gbs:8.1f} GB/s  {100 * gbs / peak:5.1f} % of HBM peak  {note}")
+        row = dict(kernel=name, unit=unit, units_per_launch=units, alg_bytes_per_unit=bytes_per_unit, ms=ms,
+                   units_per_s=units / (ms * 1e-3), achieved_gbs=gbs, frac_of_hbm_peak=gbs / peak, note=note)
+        extra = ""
+        if ops:
+            f32 = units * ops / (ms * 1e-3)
+            row.update(fp32_lane_ops_per_unit=ops, achieved_fp32_lane_ops=f32, frac_of_fp32_peak=f32 / fp32_peak,
+                       bound="fp32" if f32 / fp32_peak > gbs / peak else "hbm")
+            extra = f"  {100 * f32 / fp32_peak:5.1f} % of FP32 pipe"
+        rows.append(row)
+        print(f"{name:34s} {units / (ms * 1e-3):12.4g} {unit}/s  {gbs:8.1f} GB/s  {100 * gbs / peak:5.1f} % of HBM peak{extra}  {note}")
 
     # ---- modulators (a37-a40) ----
     bits = torch.randint(0, 2, (n, 148), dtype=torch.uint8, device=dev)
@@ -68,10 +81,12 @@ def main():
         hl = 40 if kind == "rach" else 16
         win = (4 * (hl + 16 + bound - 1) + 12) * 8
         t_det = timed(lambda: trx.detect(rx, typ, tsc, mt, bound, out=res))
+        nd = hl + 16 + bound - 1
+        det_ops = nd * 62 + (16 + bound) * hl * 8 + 9 * 2 * 21 * 4  # decimate + correlate + early/late interpolation
         add(f"detect[{kind}] corr+peak(+clip)", "burst", n, 5000 + 24, t_det,
-            f"standalone detectAnyBurst incl. the 625-sample clip scan; correlator window alone is {win} B")
+            f"standalone detectAnyBurst incl. the 625-sample clip scan; correlator window alone is {win} B", ops=det_ops)
         t_dem = timed(lambda: trx.demod(rx, res["rc"], res["amp"], res["toa"], res["ci"], soft=res["soft"], n_gmsk_soft=148))
-        add(f"demod_kernel[{kind}]", "burst", n, 5000 + soft * 4 + 16, t_dem)
+        add(f"demod_kernel[{kind}]", "burst", n, 5000 + soft * 4 + 16, t_dem, ops=156 * 35 * 2 + 32 * 20 * 2 + (148 * 40 if kind == "edge" else 0))
         t_dd = timed(lambda: trx.detect_demod(rx, typ, tsc, mt, bound, n_gmsk_soft=148, out=res))
         trx.profile_begin()
         trx.detect_demod(rx, typ, tsc, mt, bound, n_gmsk_soft=148, out=res)
@@ -86,7 +101,7 @@ def main():
             po = trx.alloc_pull_results(n, 160)
             t_pull = timed(lambda: trx.pull(iq, typ, tsc, mt, fn, tn, bound, out=po))
             add("pull[nb] int16 -> TRXD v1", "burst", n, 2500 + 159 + 10, t_pull,
-                "ingest + detect + demod + pack through a float32 scratch (v1 of the chain; not yet fused)")
+                "extract (correlator windows) + detect + demod on the int16 slot + pack; issue bound in demod_kernel<true>, not HBM bound")
             # ---- helpers ----
             e_t = timed(lambda: trx.energy_detect(rx, 80))
             add("energy_detect_kernel", "burst", n, 80 * 32 + 4, e_t,
@@ -98,14 +113,14 @@ def main():
             xf = rx.reshape(-1)
             add("convert_float_short_kernel", "value", xf.numel(), 6, timed(lambda: trx.convert_float_short(xf, 0.5)))
             dl = torch.rand(n, device=dev) * 8 - 4
-            add("delay_vector_kernel", "burst", n, 10000, timed(lambda: trx.delay_vector(rx, dl), reps=5))
+            add("delay_vector_kernel", "burst", n, 10000, timed(lambda: trx.delay_vector(rx, dl), reps=5), ops=625 * 78)
             h = torch.randn((16, 2), device=dev)
             h[:, 1] = 0
             add("convolve_kernel real16", "output", n * 600, 16,
-                timed(lambda: trx.convolve(rx, 20, 600, h, 0, 600, False), reps=5), "x read once + y written")
+                timed(lambda: trx.convolve(rx, 20, 600, h, 0, 600, False), reps=5), "x read once + y written", ops=62)
             hc = torch.randn((16, 2), device=dev)
             add("convolve_kernel complex16", "output", n * 600, 16,
-                timed(lambda: trx.convolve(rx, 20, 600, hc, 0, 600, True), reps=5))
+                timed(lambda: trx.convolve(rx, 20, 600, hc, 0, 600, True), reps=5), ops=126)
             del iq, po, dl
         del rx, res
     trx.detect_config(40, 3)
