@@ -524,13 +524,14 @@ struct ChunkHook {
 static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, const float *bursts, int stride, int n,
 			 const uint8_t *type, const uint8_t *tsc, const uint16_t *max_toa, int bound, float thresh, int32_t *rc,
 			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags, int scan_clip,
-			 ChunkHook *after_chunk = nullptr, bool overlapped = false)
+			 ChunkHook *after_chunk = nullptr, bool overlapped = false, const int16_t *iq = nullptr, int iq_stride = 0)
 {
 	const trxb200_ctx::Tune &tn = ctx->tune;
 	const int lmax = (16 + bound + 1) & ~1;		    // row pitch of the correlation vectors (even: 16-byte row loads in peak_kernel)
 	const int ndmax = ctx->max_seq_len + 16 + bound - 1; // decimated samples a correlation window needs
 	// ---- launch geometry ----
 	const bool nb = (ndmax == 35 && lmax == 20); // 16-symbol sync, max_toa <= 4: register-blocked corr_nb_kernel
+	if (iq && !nb) return fail(ctx, TRXB200_EINVAL, "detect: int16 rows are read by corr_nb_kernel only");
 	int cw = 8; // warps per corr block
 	if (!nb)
 		while (cw > 1 && corr_lg_warp_bytes(ndmax) * cw > 100 * 1024) cw >>= 1;
@@ -544,7 +545,8 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	static bool configured = false;
 	if (!configured) {
 		CK(cudaFuncSetAttribute(corr_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-		CK(cudaFuncSetAttribute(corr_nb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		CK(cudaFuncSetAttribute(corr_nb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		CK(cudaFuncSetAttribute(corr_nb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		configured = true;
 	}
@@ -583,13 +585,15 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 		const int m = (int)std::min<long>(chunk, n - lo);
 		for (int r = 0; r < rounds; r++) {
 			CorrParams c;
-			c.bursts = bursts + (size_t)lo * stride * 2; c.stride = stride; c.n = m;
+			c.bursts = bursts ? bursts + (size_t)lo * stride * 2 : nullptr; c.stride = stride; c.n = m;
+			c.iq = iq ? iq + (size_t)lo * iq_stride * 2 : nullptr; c.iq_stride = iq_stride;
 			c.type = type + lo; c.tsc = tsc + lo; c.max_toa = max_toa + lo; c.rc = rc + lo; c.round = r;
 			c.max_toa_bound = bound; c.lmax = lmax; c.ndmax = ndmax; c.corr = ws.corr; c.pwr = ws.pwr; c.negzero = -0.0f;
 			const int ngroups = (m + cgroup - 1) / cgroup;
 			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));
 			prof_pre(ctx, st);
-			if (nb) corr_nb_kernel<<<cgrid, cw * 32, csmem, st>>>(c);
+			if (nb && iq) corr_nb_kernel<true><<<cgrid, cw * 32, csmem, st>>>(c);
+			else if (nb) corr_nb_kernel<false><<<cgrid, cw * 32, csmem, st>>>(c);
 			else corr_long_kernel<<<cgrid, cw * 32, csmem, st>>>(c);
 			prof_post(ctx, st, "corr_kernel");
 			int e = post_launch(ctx, "corr_kernel");
@@ -885,21 +889,30 @@ static int pull_chunk(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, const t
 {
 	int s_min, W;
 	pull_window(ctx, a->max_toa_bound, s_min, W);
+	// 16-symbol sequences at max_toa <= 4 (launch_detect's corr_nb_kernel case): the correlator reads the int16 slots
+	// itself and no window is extracted; otherwise the windows are converted for corr_long_kernel
+	const bool nb = (ctx->max_seq_len + 16 + a->max_toa_bound - 1 == 35) && (((16 + a->max_toa_bound + 1) & ~1) == 20);
 	ExtractParams ip;
-	ip.iq = iq; ip.stride_in = a->stride; ip.n = m; ip.type = type; ip.type_out = w.type2; ip.win = w.bursts; ip.W = W; ip.s_min = s_min;
+	ip.iq = iq; ip.stride_in = a->stride; ip.n = m; ip.type = type; ip.type_out = w.type2; ip.win = w.bursts; ip.W = nb ? 0 : W;
+	ip.s_min = s_min;
 	prof_pre(ctx, st);
 	extract_kernel<<<std::max(1, std::min((m + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(ip);
 	prof_post(ctx, st, "extract_kernel");
 	int r = post_launch(ctx, "extract_kernel");
 	if (r) return r;
-	// the detection kernels index samples of the full slot: hand them the window buffer shifted back by s_min samples
-	const float *det_rows = w.bursts - (ptrdiff_t)2 * s_min;
 	if (!amp) amp = w.amp;
 	if (!toa) toa = w.toa;
 	if (!ci) ci = w.ci;
 	if (!tsc_out) tsc_out = w.tsc_out;
-	r = launch_detect(ctx, st, w.ws, det_rows, W, m, w.type2, tsc, max_toa, a->max_toa_bound, a->thresh, rc, amp, toa,
-			  tsc_out, ci, flags, 0);
+	if (nb) {
+		r = launch_detect(ctx, st, w.ws, nullptr, 0, m, w.type2, tsc, max_toa, a->max_toa_bound, a->thresh, rc, amp, toa, tsc_out,
+				  ci, flags, 0, nullptr, false, iq, a->stride);
+	} else {
+		// the detection kernels index samples of the full slot: hand them the window buffer shifted back by s_min samples
+		const float *det_rows = w.bursts - (ptrdiff_t)2 * s_min;
+		r = launch_detect(ctx, st, w.ws, det_rows, W, m, w.type2, tsc, max_toa, a->max_toa_bound, a->thresh, rc, amp, toa,
+				  tsc_out, ci, flags, 0);
+	}
 	if (r) return r;
 	r = launch_demod(ctx, st, nullptr, 0, m, rc, amp, toa, ci, flags, w.soft, w.soft_stride, 148, 1, w.type2, 0, iq, a->stride, type,
 			 energy);

@@ -109,16 +109,6 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// int16 I/Q pair (one 32-bit word) -> complex float without the conversion unit: 0x4B000000 | u is the float 2^23 + u
-// for u < 2^23, so with u = int16 ^ 0x8000 (= value + 32768) one subtraction of 2^23 + 32768 leaves the value, exactly.
-// One LOP3 / PRMT+LOP3 per component and a packed add per sample, all on the full-rate pipes.
-__device__ __forceinline__ float2 cvt_s2(unsigned word)
-{
-	const unsigned lo = (word & 0x0000ffffu) ^ 0x4b008000u;
-	const unsigned hi = __byte_perm(word, 0x4b000000u, 0x7632) ^ 0x00008000u;
-	return fadd2(make_float2(__uint_as_float(lo), __uint_as_float(hi)), make_float2(-8421376.0f, -8421376.0f));
-}
-
 // window sample w as complex float.  I16: the window holds the radio's int16 I/Q pairs as they arrived (pull path:
 // convert_short_float, arch/x86/convert.c:37-79, happens here, on the way to the FIR; (float)int16 is exact)
 template <bool I16>

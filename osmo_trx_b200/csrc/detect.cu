@@ -56,6 +56,16 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b)
 }
 __device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
 
+// int16 I/Q pair (one 32-bit word) -> complex float without the conversion unit: 0x4B000000 | u is the float 2^23 + u
+// for u < 2^23, so with u = int16 ^ 0x8000 (= value + 32768) one subtraction of 2^23 + 32768 leaves the value, exactly.
+// One LOP3 / PRMT+LOP3 per component and a packed add per sample, all on the full-rate pipes.
+__device__ __forceinline__ float2 cvt_s2(unsigned word)
+{
+	const unsigned lo = (word & 0x0000ffffu) ^ 0x4b008000u;
+	const unsigned hi = __byte_perm(word, 0x4b000000u, 0x7632) ^ 0x00008000u;
+	return add2(make_float2(__uint_as_float(lo), __uint_as_float(hi)), make_float2(-8421376.0f, -8421376.0f));
+}
+
 struct Attempt {
 	int seq;   // sequence id or -1
 	int head;  // search symbols before target
@@ -393,6 +403,9 @@ __device__ __forceinline__ float2 cmul_tap(float2 xv, float2 hr, float2 hi, floa
 	return add2(p1, make_float2(p2.y, p2.x));
 }
 
+// I16: the windows are read from the radio's int16 slots (p.iq, pull chain): 8-byte slots, converted after the
+// shared-memory read - detection then needs no float copy of the slot at all.
+template <bool I16>
 __global__ void __launch_bounds__(256, 2)
 corr_nb_kernel(CorrParams p)
 {
@@ -417,15 +430,19 @@ corr_nb_kernel(CorrParams p)
 	float g16[16];
 #pragma unroll
 	for (int k = 0; k < 16; k++) g16[k] = c_tab.dnsamp[k];
-	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
+	constexpr unsigned SB = I16 ? 8u : 16u; // bytes per slot (two samples)
+	const unsigned base_par = I16 ? (unsigned)((reinterpret_cast<uintptr_t>(p.iq) >> 2) & 1u)
+				      : (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
 	const float2 *xall = reinterpret_cast<const float2 *>(p.bursts);
+	const unsigned *qall = reinterpret_cast<const unsigned *>(p.iq); // one word per int16 sample
+	const int rstride = I16 ? p.iq_stride : p.stride;
 
 	// Software pipeline over the warp's groups: the window copies of the NEXT group (cp.async, global -> shared
 	// without a register round trip) are issued as soon as the decimator has consumed the current windows and land
 	// while the current group is correlated; the per-burst scalars (type, tsc, max_toa, rc) run one group further ahead.
 	const int ngroups = (p.n + kNbGroup - 1) / kNbGroup;
 	const int gstep = gridDim.x * wpb;
-	const unsigned raw_s = (unsigned)__cvta_generic_to_shared(raw) + 16u * (unsigned)((lane & 7) * kNbPlanePitch + (lane >> 3));
+	const unsigned raw_s = (unsigned)__cvta_generic_to_shared(raw) + SB * (unsigned)((lane & 7) * kNbPlanePitch + (lane >> 3));
 
 	struct Scal { int type, tsc, T, rc; };
 	auto load_scal = [&](int grp_) {
@@ -453,21 +470,31 @@ corr_nb_kernel(CorrParams p)
 #pragma unroll
 		for (int g = 0; g < kNbGroup; g++) {
 			const int w = __shfl_sync(0xffffffffu, pk_, g);
-			const size_t row = (size_t)(b0_ + g) * (size_t)p.stride;
+			const size_t row = (size_t)(b0_ + g) * (size_t)rstride;
 			const int s_lo = 4 * (((w >> 8) & 255) - 15) - 15;
-			const float2 *src = xall + row + s_lo + 2 * lane;
 			const unsigned row_par = (base_par + (unsigned)(row & 1u)) & 1u;
 			const bool aligned = (((unsigned)s_lo + row_par) & 1u) == 0;
 			if (w & 1) {
 #pragma unroll
 				for (int it = 0; it < 3; it++) {
 					if (lane + 32 * it < kNbSlots) {
-						const unsigned dst = raw_s + 16u * (unsigned)(g * kNbRawPitch + 4 * it);
-						if (aligned) {
-							asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 64 * it) : "memory");
+						const unsigned dst = raw_s + SB * (unsigned)(g * kNbRawPitch + 4 * it);
+						if constexpr (I16) {
+							const unsigned *src = qall + row + s_lo + 2 * lane + 64 * it;
+							if (aligned) {
+								asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+							} else {
+								asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+								asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u), "l"(src + 1) : "memory");
+							}
 						} else {
-							asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + 64 * it) : "memory");
-							asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u), "l"(src + 64 * it + 1) : "memory");
+							const float2 *src = xall + row + s_lo + 2 * lane + 64 * it;
+							if (aligned) {
+								asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+							} else {
+								asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+								asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u), "l"(src + 1) : "memory");
+							}
 						}
 					}
 				}
@@ -506,10 +533,20 @@ corr_nb_kernel(CorrParams p)
 			const int a = it - 9 * g;
 			const int w = __shfl_sync(0xffffffffu, my_pk, g);
 			if (it < 9 * kNbGroup && (w & 1)) {
-				const float4 *r = raw + g * kNbRawPitch + a;
 				float4 s[14];
+				if constexpr (I16) {
+					const uint2 *r = reinterpret_cast<const uint2 *>(raw) + g * kNbRawPitch + a;
 #pragma unroll
-				for (int q = 0; q < 14; q++) s[q] = r[(q & 7) * kNbPlanePitch + (q >> 3)];
+					for (int q = 0; q < 14; q++) {
+						const uint2 wv = r[(q & 7) * kNbPlanePitch + (q >> 3)];
+						const float2 lo = cvt_s2(wv.x), hi = cvt_s2(wv.y);
+						s[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+					}
+				} else {
+					const float4 *r = raw + g * kNbRawPitch + a;
+#pragma unroll
+					for (int q = 0; q < 14; q++) s[q] = r[(q & 7) * kNbPlanePitch + (q >> 3)];
+				}
 				float2 *dg = dec + g * kNbDecPitch;
 				float *pw = p.pwr + (size_t)(b0 + g) * 35;
 #pragma unroll

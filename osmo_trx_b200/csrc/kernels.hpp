@@ -19,6 +19,9 @@ struct CorrParams {
 	float2 *corr;	 // [n][lmax]
 	float *pwr;	 // [n][ndmax] |decimated sample|^2 (computeCI)
 	float negzero;	 // -0.0f at run time (see mul2 in detect.cu)
+	// pull chain (corr_nb_kernel<true>): the windows are read from the int16 slots instead of `bursts`
+	const int16_t *iq; // [n][iq_stride] complex int16, or null
+	int iq_stride;
 };
 
 struct PeakParams {
