@@ -878,17 +878,17 @@ peak_kernel(PeakParams p)
 			float2 *dst = C + kPadRows * kRowPitch + lane;
 			const int len = at.len;
 			if ((p.lmax & 1) == 0) {
-				// ten samples per round: the five 16-byte loads are in flight together (rows are lmax long, so a
-				// pair that starts inside the row ends inside it)
-				for (int i0 = 0; i0 < len; i0 += 10) {
-					float4 v[5];
+				// twenty samples per round: the ten 16-byte loads are in flight together - a normal burst's whole
+				// vector in one round trip (rows are lmax long, so a pair that starts inside the row ends inside it)
+				for (int i0 = 0; i0 < len; i0 += 20) {
+					float4 v[10];
 #pragma unroll
-					for (int k = 0; k < 5; k++) {
+					for (int k = 0; k < 10; k++) {
 						v[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 						if (i0 + 2 * k < len) v[k] = __ldg(reinterpret_cast<const float4 *>(src + i0 + 2 * k));
 					}
 #pragma unroll
-					for (int k = 0; k < 5; k++) {
+					for (int k = 0; k < 10; k++) {
 						if (i0 + 2 * k < len) dst[(i0 + 2 * k) * kRowPitch] = make_float2(v[k].x, v[k].y);
 						if (i0 + 2 * k + 1 < len) dst[(i0 + 2 * k + 1) * kRowPitch] = make_float2(v[k].z, v[k].w);
 					}
@@ -1004,12 +1004,13 @@ peak_kernel(PeakParams p)
 					// S = mean |burst[ps..ps+N)|^2, sequential (:1622-1626); pwr index j = dec index - d0 = rt + k
 					const float *pw = p.pwr + (size_t)b * p.ndmax + rt;
 					float S = 0.0f;
-					for (int k0 = 0; k0 < N; k0 += 8) { // N is 16, 40 or 64; eight loads in flight, then the ordered sum
-						float v[8];
+					for (int k0 = 0; k0 < N; k0 += 16) { // N is 16, 40 or 64; sixteen loads in flight, then the ordered sum
+						float v[16];
 #pragma unroll
-						for (int k = 0; k < 8; k++) v[k] = __ldg(&pw[k0 + k]);
+						for (int k = 0; k < 16; k++) v[k] = (k0 + k < N) ? __ldg(&pw[k0 + k]) : 0.0f;
 #pragma unroll
-						for (int k = 0; k < 8; k++) S = fa(S, v[k]);
+						for (int k = 0; k < 16; k++)
+							if (k0 + k < N) S = fa(S, v[k]);
 					}
 					S = S / (float)N;
 					const float Cn = norm2(xc) / si.ci_den;
