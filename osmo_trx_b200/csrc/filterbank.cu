@@ -306,34 +306,39 @@ channelizer64_kernel(const float *__restrict__ in, const float *__restrict__ his
 	const float2 *xin = reinterpret_cast<const float2 *>(in);
 	const float2 *hin = reinterpret_cast<const float2 *>(hist_in);
 	const long ntiles = (total_t + kFbT - 1) / kFbT;
+	// Interior tiles are one contiguous 24,064-byte chunk: it is brought in with 16-byte cp.async copies issued as soon as
+	// the FIR stage of the PREVIOUS tile has consumed xs, so the copy runs under that tile's two transform passes.
+	auto interior = [&](long tile_) { const long t0_ = tile_ * kFbT; return t0_ >= 15 && t0_ + kFbT <= total_t; };
+	auto prefetch = [&](long tile_) {
+		const float4 *src = reinterpret_cast<const float4 *>(xin + (tile_ * kFbT - 15) * 64);
+		const unsigned dst = (unsigned)__cvta_generic_to_shared(xs);
+#pragma unroll
+		for (int i = 0; i < 6; i++) {
+			const int idx = tid + 256 * i;
+			if (idx < kFbRows * 32)
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)idx), "l"(src + idx) : "memory");
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	bool fetched = false; // the current tile's rows are already on their way
 	for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 		const long t0 = tile * kFbT;
-		__syncthreads(); // previous tile is done with xs
-		if (t0 >= 15 && t0 + kFbT <= total_t) {
-			// interior tile: one contiguous 24,064-byte chunk, 16-byte loads
-			const float4 *src = reinterpret_cast<const float4 *>(xin + (t0 - 15) * 64);
-			float4 *dst = reinterpret_cast<float4 *>(xs);
-			float4 v[6];
-#pragma unroll
-			for (int i = 0; i < 6; i++) {
-				const int idx = tid + 256 * i;
-				if (idx < kFbRows * 32) v[i] = __ldg(&src[idx]);
-			}
-#pragma unroll
-			for (int i = 0; i < 6; i++) {
-				const int idx = tid + 256 * i;
-				if (idx < kFbRows * 32) dst[idx] = v[i];
-			}
-		} else {
-			for (int idx = tid; idx < kFbRows * 64; idx += 256) {
-				const int row = idx >> 6, c = idx & 63;
-				const long t = t0 - 15 + row;
-				float2 v = make_float2(0.0f, 0.0f);
-				if (t < 0) v = hin[(63 - c) * 16 + (int)(16 + t)];
-				else if (t < total_t) v = __ldg(&xin[t * 64 + c]);
-				xs[idx] = v;
+		if (!fetched) {
+			__syncthreads(); // previous tile is done with xs
+			if (interior(tile)) {
+				prefetch(tile);
+			} else {
+				for (int idx = tid; idx < kFbRows * 64; idx += 256) {
+					const int row = idx >> 6, c = idx & 63;
+					const long t = t0 - 15 + row;
+					float2 v = make_float2(0.0f, 0.0f);
+					if (t < 0) v = hin[(63 - c) * 16 + (int)(16 + t)];
+					else if (t < total_t) v = __ldg(&xin[t * 64 + c]);
+					xs[idx] = v;
+				}
 			}
 		}
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncthreads();
 		// ---- branch FIRs: y[r][8g + o] = sum_k xs[8g + o + k][col] * h[k] ----
 		{
@@ -351,6 +356,12 @@ channelizer64_kernel(const float *__restrict__ in, const float *__restrict__ his
 			for (int o = 0; o < 8; o++) y[r * kFbPitch + 8 * g + o] = acc[o];
 		}
 		__syncthreads();
+		// xs is consumed: start the next tile's copy, it lands while the transform passes run
+		{
+			const long nxt = tile + gridDim.x;
+			fetched = nxt < ntiles && interior(nxt);
+			if (fetched) prefetch(nxt);
+		}
 		// ---- pass A: 8-point transforms over i of branch r = w + 8i, twiddled ----
 		{
 			float2 a[8];
