@@ -513,17 +513,39 @@ channelizer_small_kernel(const float *__restrict__ in, const float *__restrict__
 	const float2 *xin = reinterpret_cast<const float2 *>(in);
 	const float2 *hin = reinterpret_cast<const float2 *>(hist_in);
 	const long ntiles = (total_t + C::T - 1) / C::T;
+	// Interior tiles (16-byte aligned input) are fetched with 16-byte cp.async copies, two samples of a row each, issued
+	// as soon as the FIR stage of the previous tile has consumed xs: the copy runs under that tile's transform stage.
+	const bool al16 = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+	auto interior = [&](long tile_) { const long t0_ = tile_ * C::T; return al16 && t0_ >= 15 && t0_ + C::T <= total_t; };
+	auto prefetch = [&](long tile_) {
+		const float4 *src = reinterpret_cast<const float4 *>(xin + (tile_ * C::T - 15) * M);
+		const unsigned dst = (unsigned)__cvta_generic_to_shared(xs);
+		for (int pc = tid; pc < (C::T + 15) * M / 2; pc += 256) {
+			const int row = (2 * pc) / M, c = (2 * pc) % M;
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 8u * (unsigned)((row + (row >> 3)) * M + c)), "l"(src + pc)
+				     : "memory");
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	bool fetched = false;
 	for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 		const long t0 = tile * C::T;
-		__syncthreads();
-		for (int idx = tid; idx < (C::T + 15) * M; idx += 256) {
-			const int row = idx / M, c = idx % M;
-			const long t = t0 - 15 + row;
-			float2 v = make_float2(0.0f, 0.0f);
-			if (t < 0) v = hin[(M - 1 - c) * 16 + (int)(16 + t)];
-			else if (t < total_t) v = __ldg(&xin[t * M + c]);
-			xs[(row + (row >> 3)) * M + c] = v;
+		if (!fetched) {
+			__syncthreads();
+			if (interior(tile)) {
+				prefetch(tile);
+			} else {
+				for (int idx = tid; idx < (C::T + 15) * M; idx += 256) {
+					const int row = idx / M, c = idx % M;
+					const long t = t0 - 15 + row;
+					float2 v = make_float2(0.0f, 0.0f);
+					if (t < 0) v = hin[(M - 1 - c) * 16 + (int)(16 + t)];
+					else if (t < total_t) v = __ldg(&xin[t * M + c]);
+					xs[(row + (row >> 3)) * M + c] = v;
+				}
+			}
 		}
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncthreads();
 		{
 			float2 acc[8];
@@ -540,6 +562,11 @@ channelizer_small_kernel(const float *__restrict__ in, const float *__restrict__
 			for (int o = 0; o < 8; o++) y[(9 * g + o) * M + r] = acc[o];
 		}
 		__syncthreads();
+		{
+			const long nxt = tile + gridDim.x; // xs is consumed: the next tile's copy lands during the transform stage
+			fetched = nxt < ntiles && interior(nxt);
+			if (fetched) prefetch(nxt);
+		}
 		for (int tt = tid; tt < C::T; tt += 256) {
 			const long t = t0 + tt;
 			float2 yv[M];
