@@ -94,9 +94,9 @@ int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, 
 	if (r->L == 16 && r->p <= 256 && r->q < 2 * r->p) {
 		// shared-memory staged, taps-in-registers kernel: P polyphase periods of one stream per tile (about 3,000
 		// input samples, so that a tile's compute phase is long against the latency of its staging loads)
-		const int P = std::max(1, std::min(4096 / r->p, 3072 / r->q));
+		const int P = std::max(1, std::min(4096 / r->p, 3000 / r->q));
 		const int slots = P * r->q + 15;
-		const size_t smem = (size_t)slots * sizeof(float2);
+		const size_t smem = (size_t)2 * slots * sizeof(float2); // two window buffers
 		const long tiles = (long)n_streams * ((out_len / r->p + P - 1) / P);
 		const int grid = (int)std::max<long>(1, std::min<long>(tiles, (long)ctx->sm_count * 4));
 		resampler16_kernel<<<grid, 256, smem, ctx->stream>>>(in, in_stride, out, out_len, out_stride, n_streams, r->p, r->q, P,

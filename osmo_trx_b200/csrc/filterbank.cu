@@ -101,14 +101,28 @@ resampler16_kernel(const float *__restrict__ in, int in_stride, float *__restric
 	const int periods_total = out_len / p;
 	const int tiles_per_stream = (periods_total + P - 1) / P;
 	const long total_tiles = (long)n_streams * tiles_per_stream;
-	for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+	// two window buffers: the next tile's input span is copied (cp.async, 8 bytes per sample) while this one is evaluated
+	const int bufslots = P * q + 15;
+	const unsigned rsm_s = (unsigned)__cvta_generic_to_shared(rsm);
+	auto issue = [&](long tile_, int buf_) {
+		const int s_ = (int)(tile_ / tiles_per_stream), per0_ = (int)(tile_ % tiles_per_stream) * P;
+		const int np_ = min(P, periods_total - per0_);
+		const float2 *src = reinterpret_cast<const float2 *>(in) + (size_t)s_ * in_stride + ((long)per0_ * q - 15);
+		const int cnt = np_ * q + 15;
+		const unsigned dst = rsm_s + 8u * (unsigned)(buf_ * bufslots);
+		for (int idx = tid; idx < cnt; idx += 256)
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (unsigned)idx), "l"(src + idx) : "memory");
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	int buf = 0;
+	if ((long)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+	for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
 		const int s = (int)(tile / tiles_per_stream), per0 = (int)(tile % tiles_per_stream) * P;
 		const int np = min(P, periods_total - per0);
-		const float2 *src = reinterpret_cast<const float2 *>(in) + (size_t)s * in_stride + ((long)per0 * q - 15);
-		const int cnt = np * q + 15;
-		__syncthreads();
-		for (int idx = tid; idx < cnt; idx += 256) rsm[idx] = __ldg(&src[idx]);
-		__syncthreads();
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads(); // this tile's span has landed; everybody is done with the other buffer
+		if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x, buf ^ 1);
+		const float2 *rs = rsm + (size_t)buf * bufslots;
 		if (!active) continue;
 		float2 *orow = reinterpret_cast<float2 *>(out) + (size_t)s * out_stride + (size_t)per0 * p + rho;
 		for (int per = grp; per < np; per += G) {
@@ -116,10 +130,10 @@ resampler16_kernel(const float *__restrict__ in, int in_stride, float *__restric
 			float2 L[4];
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
-				const float2 p0 = mul2(rsm[nb + j], bc2(h[j]), nz);
-				const float2 p1 = mul2(rsm[nb + 4 + j], bc2(h[4 + j]), nz);
-				const float2 p2 = mul2(rsm[nb + 8 + j], bc2(h[8 + j]), nz);
-				const float2 p3 = mul2(rsm[nb + 12 + j], bc2(h[12 + j]), nz);
+				const float2 p0 = mul2(rs[nb + j], bc2(h[j]), nz);
+				const float2 p1 = mul2(rs[nb + 4 + j], bc2(h[4 + j]), nz);
+				const float2 p2 = mul2(rs[nb + 8 + j], bc2(h[8 + j]), nz);
+				const float2 p3 = mul2(rs[nb + 12 + j], bc2(h[12 + j]), nz);
 				L[j] = add2(add2(p0, p1), add2(p2, p3));
 			}
 			orow[(size_t)per * p] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
