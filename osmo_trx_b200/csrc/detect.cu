@@ -3,9 +3,9 @@
 // Two kernels per detection attempt, joined by a small L2-resident intermediate (per burst the
 // correlation vector and the powers of the decimated samples, 300 B for a normal burst):
 //
-//   corr_kernel  (warp = group of 4 bursts, lanes = output samples)
-//            stages the part of each burst the correlator window needs (152 of 625 samples for a
-//            normal burst) into shared memory with 16-byte loads, decimates 4 sps -> 1 sps
+//   corr_nb_kernel / corr_long_kernel  (register-blocked; warp = 7 bursts / one burst, see below)
+//            stage the part of each burst the correlator window needs (152 of 625 samples for a
+//            normal burst) into shared memory with asynchronous copies, decimate 4 sps -> 1 sps
 //            (downsampleBurst :1587-1601) and correlates against the sync sequence (:1674).  Every
 //            output is an independent dot product evaluated in the reference's float32 order (SSE3
 //            summation trees of convolve_sse_3.c, no FMA contraction) on the packed FP32 pipe: one
@@ -127,248 +127,11 @@ __device__ __forceinline__ bool near_tie(float a, float b)
 
 } // namespace
 
-// ---------------------------------------------------------------------------------------------
-// corr_kernel
-// ---------------------------------------------------------------------------------------------
-constexpr int kGroup = 4; // bursts staged / decimated / correlated together by one warp
-
-// slots (16 B = 2 samples) per polyphase plane of one staged window; = 4 (mod 8) keeps the two planes
-// on disjoint bank groups for the staging stores
-__host__ __device__ constexpr int corr_plane_slots(int ndmax) { int s = ndmax + 3; while ((s & 7) != 4) s++; return s; }
-__host__ __device__ inline size_t corr_warp_bytes(int ndmax)
-{
-	return (size_t)kGroup * 2 * corr_plane_slots(ndmax) * 16 + (((size_t)kGroup * ndmax * 8 + 15) & ~(size_t)15);
-}
-__host__ __device__ inline size_t corr_hdr_bytes()
-{
-	return (size_t)SEQ_STORE * 8 + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
-}
-
 // per-burst attempt parameters packed into one word: active | hlen << 1 | start << 8 | len << 16
 __device__ __forceinline__ int pk_active(int w) { return w & 1; }
 __device__ __forceinline__ int pk_hlen(int w) { return (w >> 1) & 127; }
 __device__ __forceinline__ int pk_start(int w) { return (w >> 8) & 255; }
 __device__ __forceinline__ int pk_len(int w) { return (w >> 16) & 0xffff; }
-
-// NDMAX > 0: compile-time row length of the decimated window (35 for normal / EDGE / dummy bursts at max_toa 4);
-// 0: taken from the parameter block
-template <int NDMAX>
-__global__ void __launch_bounds__(256, 3)
-corr_kernel(CorrParams p)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int wpb = blockDim.x >> 5;
-	const int ndmax = NDMAX ? NDMAX : p.ndmax;
-	const int lmax = NDMAX ? NDMAX - 15 : p.lmax;
-	const int PS = NDMAX ? corr_plane_slots(NDMAX ? NDMAX : 1) : corr_plane_slots(p.ndmax);
-	float2 *hseq = reinterpret_cast<float2 *>(smem_raw); // sync sequences (hr, hi)
-	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + (size_t)SEQ_STORE * 8);
-	unsigned char *wbase = smem_raw + corr_hdr_bytes() + corr_warp_bytes(ndmax) * warp;
-	float4 *raw = reinterpret_cast<float4 *>(wbase);	      // [kGroup][2][PS]
-	float2 *dec = reinterpret_cast<float2 *>(raw + (size_t)kGroup * 2 * PS); // [kGroup][ndmax]
-
-	for (int k = threadIdx.x; k < SEQ_STORE; k += blockDim.x) hseq[k] = c_tab.seq[k];
-	for (int k = threadIdx.x; k < SEQ_COUNT; k += blockDim.x) sinfo[k] = c_tab.info[k];
-	__syncthreads();
-
-	const float2 NZ = bc2(p.negzero);
-	float g16[16]; // decimator taps (Resampler(1,4) partition, reversed)
-#pragma unroll
-	for (int k = 0; k < 16; k++) g16[k] = c_tab.dnsamp[k];
-	const unsigned base_par = (unsigned)((reinterpret_cast<uintptr_t>(p.bursts) >> 3) & 1u);
-
-	// slot sl = lane + 32*it of a staged window lives in plane sl&1 at index sl>>1
-	int stage_off[3];
-#pragma unroll
-	for (int it = 0; it < 3; it++) stage_off[it] = ((lane + 32 * it) & 1) * PS + ((lane + 32 * it) >> 1);
-
-	const int ngroups = (p.n + kGroup - 1) / kGroup;
-	for (int grp = blockIdx.x * wpb + warp; grp < ngroups; grp += gridDim.x * wpb) {
-		const int b0 = grp * kGroup;
-		// ---- lanes 0..3 work out the parameters of the group's bursts, everybody gets all four ----
-		int my_pk = 0, my_so = 0;
-		if (lane < kGroup) {
-			const int b = b0 + lane;
-			if (b < p.n) {
-				const int type = p.type[b], tsc = p.tsc[b], T = p.max_toa[b];
-				const int rc_prev = p.round > 0 ? p.rc[b] : 0;
-				Attempt at;
-				if (attempt_runs(type, tsc, T, p.max_toa_bound, ndmax, p.round, rc_prev, sinfo, at)) {
-					my_pk = 1 | (sinfo[at.seq].len << 1) | (at.start << 8) | (at.len << 16);
-					my_so = sinfo[at.seq].off;
-				}
-			}
-		}
-		int pk[kGroup], so[kGroup];
-		int ndpad = 0, lenpad = 0;
-#pragma unroll
-		for (int g = 0; g < kGroup; g++) {
-			pk[g] = __shfl_sync(0xffffffffu, my_pk, g);
-			so[g] = __shfl_sync(0xffffffffu, my_so, g);
-			if (pk_active(pk[g])) {
-				ndpad = max(ndpad, pk_hlen(pk[g]) + pk_len(pk[g]) - 1);
-				lenpad = max(lenpad, pk_len(pk[g]));
-			}
-		}
-		if (ndpad == 0)
-			continue;
-		if (NDMAX) { // fixed work-item decomposition: (burst, sample) = (it / NDMAX, it % NDMAX), known per lane at compile time
-			ndpad = NDMAX;
-			lenpad = NDMAX - 15;
-		}
-		__syncwarp();
-
-		// ---- stage: window samples s_lo .. s_lo + 4*nd + 11 of each burst; sample s of the window lives in
-		//      16-byte slot s>>1, slot sl goes to plane sl&1 at index sl>>1 (conflict-free 16-byte reads at lane
-		//      stride 2 slots).  Fast path (windows inside the burst, <= 96 aligned pairs): all 16-byte loads of
-		//      the group are issued before the first shared store, so the warp pays the memory latency once. ----
-		bool fast = true;
-#pragma unroll
-		for (int g = 0; g < kGroup; g++) {
-			const int nd = pk_hlen(pk[g]) + pk_len(pk[g]) - 1;
-			if (pk_active(pk[g]) && (4 * (pk_start(pk[g]) - pk_hlen(pk[g]) + 1) - 15 < 1 || 2 * nd + 7 > 96)) fast = false;
-		}
-		if (fast) {
-			float4 ld[kGroup][3];
-			int npr[kGroup];
-#pragma unroll
-			for (int g = 0; g < kGroup; g++) {
-				const int b = b0 + g;
-				const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
-				const int nd = pk_hlen(pk[g]) + pk_len(pk[g]) - 1;
-				const int s_lo = 4 * (pk_start(pk[g]) - pk_hlen(pk[g]) + 1) - 15;
-				const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
-				const bool aligned = (((unsigned)s_lo + row_par) & 1u) == 0; // window slots sit on the row's 16-byte grid
-				const int np = pk_active(pk[g]) ? 2 * nd + 6 : 0;	      // slots of the window
-				npr[g] = np;
-				if (aligned) {
-#pragma unroll
-					for (int it = 0; it < 3; it++) {
-						const int sl = lane + 32 * it;
-						ld[g][it] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-						if (sl < np) ld[g][it] = __ldg(reinterpret_cast<const float4 *>(x + (s_lo + 2 * sl)));
-					}
-				} else {
-#pragma unroll
-					for (int it = 0; it < 3; it++) {
-						const int sl = lane + 32 * it;
-						float2 a = make_float2(0.0f, 0.0f), c = a;
-						if (sl < np) {
-							a = __ldg(x + (s_lo + 2 * sl));
-							c = __ldg(x + (s_lo + 2 * sl + 1));
-						}
-						ld[g][it] = make_float4(a.x, a.y, c.x, c.y);
-					}
-				}
-			}
-#pragma unroll
-			for (int g = 0; g < kGroup; g++) {
-				float4 *rg = raw + (size_t)g * 2 * PS;
-#pragma unroll
-				for (int it = 0; it < 3; it++)
-					if (lane + 32 * it < npr[g]) rg[stage_off[it]] = ld[g][it];
-			}
-		} else {
-#pragma unroll 1
-			for (int g = 0; g < kGroup; g++) {
-				if (!pk_active(pk[g])) continue;
-				const int b = b0 + g;
-				const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
-				const int nd = pk_hlen(pk[g]) + pk_len(pk[g]) - 1;
-				const int s_lo = 4 * (pk_start(pk[g]) - pk_hlen(pk[g]) + 1) - 15;
-				const int ns = 2 * nd + 6;
-				const unsigned row_par = (base_par + (unsigned)(((size_t)b * (size_t)p.stride) & 1u)) & 1u;
-				const bool aligned = (((unsigned)s_lo + row_par) & 1u) == 0;
-				float4 *rg = raw + (size_t)g * 2 * PS;
-				for (int sl = lane; sl < ns; sl += 32) {
-					const int idx = s_lo + 2 * sl;
-					float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-					if (aligned && idx >= 0 && idx <= 622) {
-						v = __ldg(reinterpret_cast<const float4 *>(x + idx));
-					} else {
-						// downsampleBurst reads samples 0..623 behind 16 zero history samples (:1590-1593)
-						if (idx >= 0 && idx <= 623) { const float2 a = __ldg(&x[idx]); v.x = a.x; v.y = a.y; }
-						if (idx + 1 >= 0 && idx + 1 <= 623) { const float2 a = __ldg(&x[idx + 1]); v.z = a.x; v.w = a.y; }
-					}
-					rg[(sl & 1) * PS + (sl >> 1)] = v;
-				}
-			}
-		}
-		__syncwarp();
-
-		// ---- decimation: one 1-sps sample per work item, sse_conv_real16 order (convolve_sse_3.c:188-264):
-		//      p[k] = x[4d-15+k]*g[k], L_j = (p[j]+p[4+j]) + (p[8+j]+p[12+j]), y = (L0+L1)+(L2+L3) ----
-#pragma unroll
-		for (int it = lane; it < kGroup * ndpad; it += 32) {
-			const int g = (it >= ndpad) + (it >= 2 * ndpad) + (it >= 3 * ndpad);
-			const int j = it - g * ndpad;
-			const int w = g == 0 ? pk[0] : g == 1 ? pk[1] : g == 2 ? pk[2] : pk[3];
-			if (!pk_active(w) || j >= pk_hlen(w) + pk_len(w) - 1) continue;
-			const int d = pk_start(w) - (pk_hlen(w) - 1) + j;
-			float2 y = make_float2(0.0f, 0.0f);
-			if (d >= 0 && d < 156) {
-				const float4 *r0 = raw + (size_t)g * 2 * PS + j; // plane 0: slots 2j, 2j+2, ...
-				const float4 *r1 = r0 + PS;			  // plane 1: slots 2j+1, ...
-				float2 pr[16];
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					const float4 a = r0[q], c = r1[q]; // samples 4q..4q+3 of the 16-sample window
-					pr[4 * q + 0] = mul2(make_float2(a.x, a.y), bc2(g16[4 * q + 0]), NZ);
-					pr[4 * q + 1] = mul2(make_float2(a.z, a.w), bc2(g16[4 * q + 1]), NZ);
-					pr[4 * q + 2] = mul2(make_float2(c.x, c.y), bc2(g16[4 * q + 2]), NZ);
-					pr[4 * q + 3] = mul2(make_float2(c.z, c.w), bc2(g16[4 * q + 3]), NZ);
-				}
-				float2 L[4];
-#pragma unroll
-				for (int q = 0; q < 4; q++)
-					L[q] = add2(add2(pr[q], pr[4 + q]), add2(pr[8 + q], pr[12 + q]));
-				y = add2(add2(L[0], L[1]), add2(L[2], L[3]));
-			}
-			dec[g * ndmax + j] = y;
-			p.pwr[(size_t)(b0 + g) * ndmax + j] = norm2(y);
-		}
-		__syncwarp();
-
-		// ---- correlation: sse_conv_cmplx_8n order (convolve_sse_3.c:462-537); hlen is 16, 40 or 64.
-		//      One complex tap = two packed products and one packed add: x*(hr,hr) + swap(x*(hi,-hi))
-		//      = (hr*xr - hi*xi, hr*xi + hi*xr); the per-half negation and the swap are operand modifiers. ----
-#pragma unroll
-		for (int it = lane; it < kGroup * lenpad; it += 32) {
-			const int g = (it >= lenpad) + (it >= 2 * lenpad) + (it >= 3 * lenpad);
-			const int i = it - g * lenpad;
-			const int w = g == 0 ? pk[0] : g == 1 ? pk[1] : g == 2 ? pk[2] : pk[3];
-			if (!pk_active(w) || i >= pk_len(w)) continue;
-			const int hlen = pk_hlen(w);
-			const float2 *dx = dec + g * ndmax + i;
-			const float2 *hh = hseq + (g == 0 ? so[0] : g == 1 ? so[1] : g == 2 ? so[2] : so[3]);
-			float2 A[4], B[4];
-#pragma unroll
-			for (int q = 0; q < 4; q++) { A[q] = make_float2(0.0f, 0.0f); B[q] = make_float2(0.0f, 0.0f); }
-			for (int t0 = 0; t0 < hlen; t0 += 8) {
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					{
-						const float2 xv = dx[t0 + q], hv = hh[t0 + q];
-						const float2 p1 = mul2(xv, bc2(hv.x), NZ);
-						const float2 p2 = mul2(xv, make_float2(hv.y, -hv.y), NZ);
-						A[q] = add2(A[q], add2(p1, make_float2(p2.y, p2.x)));
-					}
-					{
-						const float2 xv = dx[t0 + 4 + q], hv = hh[t0 + 4 + q];
-						const float2 p1 = mul2(xv, bc2(hv.x), NZ);
-						const float2 p2 = mul2(xv, make_float2(hv.y, -hv.y), NZ);
-						B[q] = add2(B[q], add2(p1, make_float2(p2.y, p2.x)));
-					}
-				}
-			}
-			float2 L[4];
-#pragma unroll
-			for (int q = 0; q < 4; q++) L[q] = add2(A[q], B[q]);
-			p.corr[(size_t)(b0 + g) * lmax + i] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
-		}
-	}
-}
 
 // ---------------------------------------------------------------------------------------------
 // corr_nb_kernel — corr_kernel for the common configuration (16-symbol sync sequence, correlation length <= 20:
