@@ -190,6 +190,27 @@ int trxb200_pull_batch(trxb200_ctx *ctx, const trxb200_pull_args *args);
 /* HOST pointers; H2D / kernels / D2H pipelined over internal streams (pinned buffers recommended) */
 int trxb200_pull_host(trxb200_ctx *ctx, const trxb200_pull_args *args);
 
+/* ---- burst-type scheduler: Transceiver::expectedCorrType (Transceiver.cpp:513-601) and the search window
+ *      pullRadioVector derives from it (:757-758: max_toa = RACH / EXT_RACH ? mMaxExpectedDelayAB : mMaxExpectedDelayNB).
+ *      Per slot (fn, tn, chan) -> CorrType + max_toa, ready to be handed to trxb200_pull_batch / detect_batch as the
+ *      `type` and `max_toa` arrays.  All pointers are device pointers.
+ *        chan_type  u8[n_chan][8]  ChannelCombination per timeslot (Transceiver.h:131-148: FILL 0, I 1 .. XIII 13,
+ *                                  NONE 14, LOOPBACK 15), i.e. TransceiverState::chanType
+ *        handover   u8[8]          per timeslot, bit s set = mHandover[tn][s] (Transceiver.h:225)
+ *        chan       u16[n] or NULL (all slots belong to channel 0); a channel index >= n_chan gives OFF
+ *        max_toa    u16[n] or NULL ---- */
+typedef struct trxb200_sched_cfg {
+	int n_chan;
+	const uint8_t *chan_type;
+	const uint8_t *handover;
+	int ext_rach;	/* cfg->ext_rach */
+	int egprs;	/* cfg->egprs */
+	int max_toa_nb; /* mMaxExpectedDelayNB */
+	int max_toa_ab; /* mMaxExpectedDelayAB */
+} trxb200_sched_cfg;
+int trxb200_expected_corr_type_batch(trxb200_ctx *ctx, const trxb200_sched_cfg *cfg, const uint32_t *fn, const uint8_t *tn,
+				     const uint16_t *chan, int n, uint8_t *type, uint16_t *max_toa);
+
 /* ---- small per-burst helpers of sigProcLib.h used around detection ---- */
 /* energyDetect(burst, window) (sigProcLib.cpp:1573-1585): mean |x|^2 of `window` samples at stride 4 */
 int trxb200_energy_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int blen, int n,

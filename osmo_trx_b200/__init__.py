@@ -25,6 +25,12 @@ BURST_THRESH = 4.0  # sigProcLib.h:54
 _lib = None
 
 
+class SchedCfg(C.Structure):
+    """trxb200_sched_cfg (include/trxb200.h)"""
+    _fields_ = [("n_chan", C.c_int), ("chan_type", C.c_void_p), ("handover", C.c_void_p), ("ext_rach", C.c_int),
+                ("egprs", C.c_int), ("max_toa_nb", C.c_int), ("max_toa_ab", C.c_int)]
+
+
 class PullArgs(C.Structure):
     """trxb200_pull_args (include/trxb200.h)"""
     _fields_ = [("iq", C.c_void_p), ("stride", C.c_int), ("n", C.c_int), ("type", C.c_void_p), ("tsc", C.c_void_p),
@@ -256,6 +262,25 @@ class Trx:
         a = self._pull_args(iq, type_, tsc, max_toa, fn, tn, max_toa_bound, out, thresh, full_scale, rssi_offset, version)
         self._check(self.lib.trxb200_pull_host(self.h, C.byref(a)), "pull_host")
         return out
+
+    # -- burst-type scheduler --
+    def expected_corr_type(self, fn, tn, chan_type, handover, chan=None, ext_rach=False, egprs=False, max_toa_nb=4,
+                           max_toa_ab=63):
+        """Transceiver::expectedCorrType per slot.  fn int32/uint32 [n], tn uint8 [n], chan_type uint8 [n_chan, 8]
+        (ChannelCombination per timeslot), handover uint8 [8] (sub-slot bit mask per timeslot), chan int16 [n] or None.
+        -> (type uint8 [n], max_toa int16 [n]) ready for pull() / detect()."""
+        _chk_dev(fn, tn, chan_type, handover)
+        n = fn.shape[0]
+        typ = torch.empty(n, dtype=torch.uint8, device=fn.device)
+        mt = torch.empty(n, dtype=torch.int16, device=fn.device)
+        cfg = SchedCfg()
+        cfg.n_chan = chan_type.shape[0]; cfg.chan_type = _ptr(chan_type); cfg.handover = _ptr(handover)
+        cfg.ext_rach = int(ext_rach); cfg.egprs = int(egprs); cfg.max_toa_nb = int(max_toa_nb); cfg.max_toa_ab = int(max_toa_ab)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_expected_corr_type_batch(self.h, C.byref(cfg), _ptr(fn), _ptr(tn),
+                                                              _ptr(chan) if chan is not None else None, C.c_int(n), _ptr(typ),
+                                                              _ptr(mt)), "expected_corr_type_batch")
+        return typ, mt
 
     # -- helpers --
     def energy_detect(self, bursts, window, blen=BURST_LEN):

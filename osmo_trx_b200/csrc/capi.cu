@@ -948,6 +948,38 @@ int trxb200_pull_batch(trxb200_ctx *ctx, const trxb200_pull_args *a)
 	return TRXB200_OK;
 }
 
+int trxb200_expected_corr_type_batch(trxb200_ctx *ctx, const trxb200_sched_cfg *cfg, const uint32_t *fn, const uint8_t *tn,
+				     const uint16_t *chan, int n, uint8_t *type, uint16_t *max_toa)
+{
+	if (!ctx) return TRXB200_EINVAL;
+	if (!cfg || n < 0 || cfg->n_chan < 1 || !cfg->chan_type || !cfg->handover || (n > 0 && (!fn || !tn || !type)))
+		return fail(ctx, TRXB200_EINVAL, "expected_corr_type: bad argument");
+	if (n == 0) return TRXB200_OK;
+	static bool tables = false;
+	if (!tables) {
+		// SDCCH/4 and SDCCH/8 sub-slot per 102-multiframe position (Transceiver.cpp:517-520), as (value, run length)
+		static const unsigned char sd4_rl[] = { 3,4, 0,2, 2,4, 3,4, 0,27, 1,4, 0,2, 2,4, 3,4, 0,6, 1,4, 0,27, 1,4, 0,2, 2,4 };
+		static const unsigned char sd8_rl[] = { 5,4, 6,4, 7,4, 0,7, 1,4, 2,4, 3,4, 4,4, 5,4, 6,4, 7,4, 0,4,
+							1,4, 2,4, 3,4, 0,7, 1,4, 2,4, 3,4, 4,4, 5,4, 6,4, 7,4, 4,4 };
+		unsigned char t4[102], t8[102];
+		int k = 0;
+		for (size_t i = 0; i < sizeof(sd4_rl); i += 2) for (int c = 0; c < sd4_rl[i + 1]; c++) t4[k++] = sd4_rl[i];
+		if (k != 102) return fail(ctx, TRXB200_EINVAL, "expected_corr_type: internal table");
+		k = 0;
+		for (size_t i = 0; i < sizeof(sd8_rl); i += 2) for (int c = 0; c < sd8_rl[i + 1]; c++) t8[k++] = sd8_rl[i];
+		if (k != 102) return fail(ctx, TRXB200_EINVAL, "expected_corr_type: internal table");
+		CK(cudaMemcpyToSymbol(c_sd4, t4, 102));
+		CK(cudaMemcpyToSymbol(c_sd8, t8, 102));
+		tables = true;
+	}
+	SchedParams p;
+	p.n = n; p.n_chan = cfg->n_chan; p.fn = fn; p.tn = tn; p.chan = chan; p.chan_type = cfg->chan_type; p.handover = cfg->handover;
+	p.ext_rach = cfg->ext_rach; p.egprs = cfg->egprs; p.max_toa_nb = cfg->max_toa_nb; p.max_toa_ab = cfg->max_toa_ab;
+	p.type_out = type; p.max_toa_out = max_toa;
+	sched_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(p);
+	return post_launch(ctx, "sched_kernel");
+}
+
 struct PullStage {
 	static constexpr int kSlots = 3;
 	int chunk = 0, stride = 0, pkt_stride = 0;

@@ -73,6 +73,19 @@ struct ExtractParams {
 	int W, s_min;
 };
 
+// burst-type scheduler (pull.cu)
+struct SchedParams {
+	int n, n_chan;
+	const uint32_t *fn;
+	const uint8_t *tn;
+	const uint16_t *chan;	   // channel index per slot, or null (channel 0)
+	const uint8_t *chan_type;  // [n_chan][8] ChannelCombination per timeslot
+	const uint8_t *handover;   // [8] per timeslot: bit s = handover expected on sub-slot s
+	int ext_rach, egprs, max_toa_nb, max_toa_ab;
+	uint8_t *type_out;
+	uint16_t *max_toa_out;	   // may be null
+};
+
 struct PackParams {
 	int n, version;
 	const uint8_t *type; // caller's slot types (OFF emits nothing)

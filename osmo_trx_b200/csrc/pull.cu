@@ -50,6 +50,60 @@ extract_kernel(ExtractParams p)
 	}
 }
 
+// ---- burst-type scheduler: Transceiver::expectedCorrType (Transceiver.cpp:513-601) and the
+// search window pullRadioVector picks from it (:757-758), one thread per slot.  With it the host ships raw slots
+// plus (FN, TN, channel) and the per-channel timeslot configuration instead of a CorrType per slot. ----
+__constant__ unsigned char c_sd4[102], c_sd8[102]; // SDCCH/4, SDCCH/8 sub-slot per 102-multiframe position
+
+__global__ void __launch_bounds__(256)
+sched_kernel(SchedParams p)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= p.n) return;
+	enum { CC_FILL, CC_I, CC_II, CC_III, CC_IV, CC_V, CC_VI, CC_VII, CC_VIII, CC_IX, CC_X, CC_XI, CC_XII, CC_XIII, CC_NONE, CC_LOOPBACK };
+	const unsigned t = p.tn[i] & 7u, f = p.fn[i];
+	const unsigned ch = p.chan ? p.chan[i] : 0u;
+	int r = 0; // OFF
+	if (ch < (unsigned)p.n_chan) {
+		const unsigned ho = p.handover[t];
+		const int rach = p.ext_rach ? 2 : 3;
+		// half-rate sub-slot of the 26-multiframe position: 0,1 alternating, 0,0 at 12-13, then 1,0 alternating, 1 at 25
+		const unsigned f26 = f % 26u;
+		const unsigned hsub = f26 < 12u ? (f26 & 1u) : (f26 == 12u ? 0u : (f26 < 25u ? ((f26 & 1u) ^ 1u) : 1u));
+		switch (p.chan_type[ch * 8u + t]) {
+		case CC_FILL: r = 6; break;
+		case CC_I: r = (ho & 1u) ? 3 : 1; break;
+		case CC_II: r = hsub == 1u ? 6 : ((ho & 1u) ? 3 : 1); break;
+		case CC_III: r = ((ho >> hsub) & 1u) ? 3 : 1; break;
+		case CC_IV:
+		case CC_VI: r = rach; break;
+		case CC_V: {
+			const unsigned m = f % 51u;
+			if ((m >= 14u && m <= 36u) || m == 4u || m == 5u || m == 45u || m == 46u) r = rach;
+			else r = ((ho >> c_sd4[f % 102u]) & 1u) ? 3 : 1;
+			break;
+		}
+		case CC_VII: {
+			const unsigned m = f % 51u;
+			if (m >= 12u && m <= 14u) r = 6;
+			else r = ((ho >> c_sd8[f % 102u]) & 1u) ? 3 : 1;
+			break;
+		}
+		case CC_XIII: {
+			const unsigned m = f % 52u;
+			if (m == 12u || m == 38u) r = 3; // PTCCH/U: always the 8-bit access burst
+			else if (m == 25u || m == 51u) r = 6;
+			else r = p.egprs ? 5 : 1;
+			break;
+		}
+		case CC_LOOPBACK: r = (f % 51u >= 48u) ? 6 : 1; break;
+		default: r = 0; break; // NONE and the combinations the reference does not schedule
+		}
+	}
+	p.type_out[i] = (uint8_t)r;
+	if (p.max_toa_out) p.max_toa_out[i] = (uint16_t)((r == 3 || r == 2) ? p.max_toa_ab : p.max_toa_nb);
+}
+
 namespace {
 
 // `(int32) = double` the way x86-64 cvttsd2si does it (the reference's implicit conversions in proto_trxd.c

@@ -241,6 +241,18 @@ class _Base:
         rc = self.L[self.pfx + "synthesis_rotate"](h, _p(x), C.c_int(m), C.c_int(block_len), _p(out))
         return rc, out
 
+    # --- burst-type scheduler (Transceiver::expectedCorrType) ---
+    def expected_corr_type(self, chan_type8, handover8, ext_rach, egprs, fn, tn):
+        """chan_type8: ChannelCombination per timeslot of one channel (u8[8]); handover8: sub-slot bit mask per timeslot."""
+        ct = np.ascontiguousarray(chan_type8, np.uint8)
+        ho = np.ascontiguousarray(handover8, np.uint8)
+        fn = np.ascontiguousarray(fn, np.uint32)
+        tn = np.ascontiguousarray(tn, np.uint8)
+        out = np.zeros(len(fn), np.uint8)
+        self.L[self.pfx + "expected_corr_type"](_p(ct), _p(ho), C.c_int(int(ext_rach)), C.c_int(int(egprs)), _p(fn), _p(tn),
+                                                C.c_int(len(fn)), _p(out))
+        return out
+
     # --- vitac ---
     def vitac_table(self, which, idx=0):
         buf = np.zeros((64, 2), np.float32)

@@ -503,3 +503,32 @@ def test_pull_host_matches_device_path(trx, checker):
     for k in out:
         assert np.array_equal(out[k].cpu().numpy(), h[k].numpy(), equal_nan=True), k
     assert trx.pull(dev(iq[:0]), dev(typ[:0]), dev(tsc[:0]), dev(mt[:0]), dev(fn[:0].astype(np.int32)), dev(tn[:0]), 4) is not None
+
+
+def test_scheduler_expected_corr_type(trx, checker):
+    """Burst-type scheduler (Transceiver::expectedCorrType + the max_toa choice of pullRadioVector) on the device:
+    several channels with different timeslot configurations in one batch, against the CPU checker per channel."""
+    rng = np.random.default_rng(41)
+    n_chan, n = 6, 40000
+    ct = rng.integers(0, 16, (n_chan, 8)).astype(np.uint8)
+    ct[0] = [4, 7, 1, 2, 3, 13, 5, 15]  # a realistic C0: IV, VII, TCH/F, TCH/H x2, PDCH, V, loopback
+    ho = rng.integers(0, 256, 8).astype(np.uint8)
+    fn = rng.integers(0, 2715648, n).astype(np.uint32)
+    tn = rng.integers(0, 8, n).astype(np.uint8)
+    chan = rng.integers(0, n_chan + 1, n).astype(np.int16)  # n_chan itself: out of range -> OFF
+    for xr, eg in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        typ, mt = trx.expected_corr_type(dev(fn.astype(np.int32)), dev(tn), dev(ct), dev(ho), chan=dev(chan), ext_rach=xr, egprs=eg,
+                                         max_toa_nb=4, max_toa_ab=63)
+        torch.cuda.synchronize()
+        typ, mt = typ.cpu().numpy(), mt.cpu().numpy()
+        want = np.zeros(n, np.uint8)
+        for c in range(n_chan):
+            m = chan == c
+            want[m] = checker.expected_corr_type(ct[c], ho, xr, eg, fn[m], tn[m])
+        assert np.array_equal(typ, want), (xr, eg)
+        assert np.array_equal(mt, np.where((want == RACH) | (want == EXT_RACH), 63, 4))
+    # no channel array: everything is channel 0; empty batch
+    typ, _ = trx.expected_corr_type(dev(fn.astype(np.int32)), dev(tn), dev(ct), dev(ho))
+    assert np.array_equal(typ.cpu().numpy(), checker.expected_corr_type(ct[0], ho, 0, 0, fn, tn))
+    typ, mt = trx.expected_corr_type(dev(fn[:0].astype(np.int32)), dev(tn[:0]), dev(ct), dev(ho))
+    assert typ.numel() == 0 and mt.numel() == 0

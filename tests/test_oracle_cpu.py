@@ -165,6 +165,34 @@ def test_oracle_pull_vs_reference_live(oracle, ref):
             _pull_same(a, b, version)
 
 
+def _sched_cases():
+    fx = np.load(os.path.join(GOLD, "sched_fixture.npz"))
+    for i in range(int(fx["n"])):
+        yield (fx[f"chan_type_{i}"], fx[f"handover_{i}"], int(fx[f"flags_{i}"][0]), int(fx[f"flags_{i}"][1]), fx[f"fn_{i}"],
+               fx[f"tn_{i}"], fx[f"type_{i}"])
+
+
+def test_oracle_scheduler_vs_fixture(oracle):
+    """expectedCorrType restatement against vectors generated from the reference's own function."""
+    seen = set()
+    for ct, ho, xr, eg, fn, tn, want in _sched_cases():
+        got = oracle.expected_corr_type(ct, ho, xr, eg, fn, tn)
+        assert np.array_equal(got, want), (ct, ho, xr, eg)
+        seen |= set(want.tolist())
+    assert seen == {0, 1, 2, 3, 5, 6}
+
+
+def test_oracle_scheduler_vs_reference_live(oracle, ref):
+    rng = np.random.default_rng(9)
+    for _ in range(40):
+        ct = rng.integers(0, 16, 8).astype(np.uint8)
+        ho = rng.integers(0, 256, 8).astype(np.uint8)
+        fn = rng.integers(0, 2715648, 5000).astype(np.uint32)
+        tn = rng.integers(0, 8, 5000).astype(np.uint8)
+        xr, eg = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        assert np.array_equal(oracle.expected_corr_type(ct, ho, xr, eg, fn, tn), ref.expected_corr_type(ct, ho, xr, eg, fn, tn))
+
+
 def test_ref_build_reproduces_convolve_test_ok():
     exe = os.path.join(ROOT, "oracle", "_ref", "convolve_test")
     ok = "/root/reference/tests/Transceiver52M/convolve_test.ok"
