@@ -81,6 +81,8 @@ struct trxb200_ctx {
 		int ov_corr_bps = 1, ov_peak_bps = 1, ov_peak_warps = 8, ov_demod_bps = 1; // while overlapping: leave room for the other kernel
 	} tune;
 	std::string err;
+	// once-per-context device setup (function attributes and __constant__ tables are per device)
+	bool cfg_detect = false, cfg_demod = false, cfg_ch64 = false, cfg_sy64 = false, sched_tables = false;
 	HostStage *stage = nullptr;
 	PullScratch pull;	      // trxb200_pull_batch
 	PullStage *pull_stage = nullptr; // trxb200_pull_host
@@ -542,13 +544,12 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	const size_t psmem = peak_hdr_bytes() + peak_warp_bytes(lmax) * pw;
 	if (csmem > 227 * 1024 || psmem > 227 * 1024)
 		return fail(ctx, TRXB200_EINVAL, "detect: max_toa_bound too large for on-chip buffers");
-	static bool configured = false;
-	if (!configured) {
+	if (!ctx->cfg_detect) {
 		CK(cudaFuncSetAttribute(corr_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(corr_nb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(corr_nb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-		configured = true;
+		ctx->cfg_detect = true;
 	}
 	int cbps = (int)std::max<size_t>(1, std::min<size_t>(2, (225 * 1024) / (csmem + 1024)));
 	int pbps = (int)std::max<size_t>(1, std::min<size_t>(2, (225 * 1024) / (psmem + 1024)));
@@ -637,11 +638,10 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 	p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp; p.dnsamp_g = ctx->d_comp + ctx->ht->comp.size(); p.edge_tab = ctx->d_edge_tab; p.fix_clip = fix_clip;
 	const int wpb = 8;
 	const size_t smem = (size_t)wpb * kDemodWarpFloats * sizeof(float);
-	static bool configured = false;
-	if (!configured) {
+	if (!ctx->cfg_demod) {
 		CK(cudaFuncSetAttribute(demod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		CK(cudaFuncSetAttribute(demod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		configured = true;
+		ctx->cfg_demod = true;
 	}
 	if (bps <= 0) bps = ctx->tune.demod_bps;
 	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * std::max(1, std::min(2, bps)));
@@ -955,8 +955,7 @@ int trxb200_expected_corr_type_batch(trxb200_ctx *ctx, const trxb200_sched_cfg *
 	if (!cfg || n < 0 || cfg->n_chan < 1 || !cfg->chan_type || !cfg->handover || (n > 0 && (!fn || !tn || !type)))
 		return fail(ctx, TRXB200_EINVAL, "expected_corr_type: bad argument");
 	if (n == 0) return TRXB200_OK;
-	static bool tables = false;
-	if (!tables) {
+	if (!ctx->sched_tables) {
 		// SDCCH/4 and SDCCH/8 sub-slot per 102-multiframe position (Transceiver.cpp:517-520), as (value, run length)
 		static const unsigned char sd4_rl[] = { 3,4, 0,2, 2,4, 3,4, 0,27, 1,4, 0,2, 2,4, 3,4, 0,6, 1,4, 0,27, 1,4, 0,2, 2,4 };
 		static const unsigned char sd8_rl[] = { 5,4, 6,4, 7,4, 0,7, 1,4, 2,4, 3,4, 4,4, 5,4, 6,4, 7,4, 0,4,
@@ -970,7 +969,7 @@ int trxb200_expected_corr_type_batch(trxb200_ctx *ctx, const trxb200_sched_cfg *
 		if (k != 102) return fail(ctx, TRXB200_EINVAL, "expected_corr_type: internal table");
 		CK(cudaMemcpyToSymbol(c_sd4, t4, 102));
 		CK(cudaMemcpyToSymbol(c_sd8, t8, 102));
-		tables = true;
+		ctx->sched_tables = true;
 	}
 	SchedParams p;
 	p.n = n; p.n_chan = cfg->n_chan; p.fn = fn; p.tn = tn; p.chan = chan; p.chan_type = cfg->chan_type; p.handover = cfg->handover;

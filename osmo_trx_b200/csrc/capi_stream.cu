@@ -177,10 +177,9 @@ int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *o
 	int r;
 	if (fb->m == 64 && fb->L == 16 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
 		// 8 x 8 split transform + register sliding-window FIRs (filterbank.cu)
-		static bool configured = false;
-		if (!configured) {
+		if (!ctx->cfg_ch64) {
 			CK(cudaFuncSetAttribute(channelizer64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCh64Smem));
-			configured = true;
+			ctx->cfg_ch64 = true;
 		}
 		const int grid = (int)std::min<long>((total_t + kFbT - 1) / kFbT, (long)ctx->sm_count * 3);
 		channelizer64_kernel<<<grid, 256, kCh64Smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
@@ -212,10 +211,9 @@ int trxb200_synthesis_rotate(trxb200_filterbank *fb, const float *in, float *out
 	const long total_t = (long)n_blocks * fb->block_len;
 	int r;
 	if (fb->m == 64 && fb->L == 16) {
-		static bool configured = false;
-		if (!configured) {
+		if (!ctx->cfg_sy64) {
 			CK(cudaFuncSetAttribute(synthesis64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSy64Smem));
-			configured = true;
+			ctx->cfg_sy64 = true;
 		}
 		const long ntiles = (total_t + kFbT - 1) / kFbT;
 		const long want = std::min<long>(ntiles, (long)ctx->sm_count * 3);
