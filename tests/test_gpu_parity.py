@@ -532,3 +532,24 @@ def test_scheduler_expected_corr_type(trx, checker):
     assert np.array_equal(typ.cpu().numpy(), checker.expected_corr_type(ct[0], ho, 0, 0, fn, tn))
     typ, mt = trx.expected_corr_type(dev(fn[:0].astype(np.int32)), dev(tn[:0]), dev(ct), dev(ho))
     assert typ.numel() == 0 and mt.numel() == 0
+
+
+def test_wide_window_with_short_sequences(trx, checker):
+    """16-symbol sizing hint with search windows wider than corr_nb_kernel's (max_toa up to 17): the long-window
+    correlator runs with a 16-tap sequence and a small decimated row."""
+    rng = np.random.default_rng(43)
+    n = 3000
+    tsc = np.arange(n) % 8
+    w = checker.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng))
+    rx, _ = synth.impair(w, rng, snr_db=14.0, shift_lo=-40, shift_hi=20, noise_only_frac=0.05)
+    typ = np.choose(np.arange(n) % 3, [TSC, EDGE, IDLE]).astype(np.uint8)
+    mt = np.choose(np.arange(n) % 4, [0, 4, 9, 17]).astype(np.int16)
+    try:
+        trx.detect_config(16, 2)
+        g = run_gpu_dd(trx, rx, typ, tsc, mt, 17)
+    finally:
+        trx.detect_config(40, 3)
+    c = checker.detect_demod(rx, typ, tsc, mt)
+    rep = parity.compare_detect(g, c, g["flags"], "wide16")
+    parity.compare_soft(g["soft"], c["soft"], rep["ok_mask"] & (c["rc"] != EDGE), 156, "wide16")
+    assert rep["detected"] > 1500
