@@ -44,7 +44,7 @@ struct PullScratch {
 	int cap = 0, soft_stride = 0;
 	float *bursts = nullptr; // [cap][win] complex float: the correlator windows of the slots (extract_kernel)
 	int win = 0;
-	float *soft = nullptr;	 // [cap][soft_stride]
+	float *pw = nullptr;	 // [cap][80] terms of energyDetect (demod_kernel<true> -> header_kernel)
 	uint8_t *type2 = nullptr, *tsc_out = nullptr;
 	float *amp = nullptr, *toa = nullptr, *ci = nullptr;
 	DetectScratch ws;
@@ -629,11 +629,13 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, int stride, int n, int32_t *rc,
 			const float *amp, const float *toa, float *ci, uint8_t *flags, float *soft, int soft_stride,
 			int n_gmsk_soft, int fix_clip, const uint8_t *type = nullptr, int bps = 0, const int16_t *iq = nullptr,
-			int iq_stride = 0, const uint8_t *type_raw = nullptr, float *energy = nullptr)
+			int iq_stride = 0, const uint8_t *type_raw = nullptr, float *pw = nullptr, uint8_t *pkt = nullptr,
+			int pkt_stride = 0, int pkt_version = 1)
 {
 	DemodParams p;
 	p.type = type;
-	p.iq = iq; p.iq_stride = iq_stride; p.type_raw = type_raw; p.energy = energy;
+	p.iq = iq; p.iq_stride = iq_stride; p.type_raw = type_raw; p.pw = pw;
+	p.pkt = pkt; p.pkt_stride = pkt_stride; p.pkt_hdr = pkt_version == 1 ? 11 : 8; p.pkt_v0 = pkt_version == 0;
 	p.bursts = bursts; p.stride = stride; p.n = n; p.rc = rc; p.amp = amp; p.toa = toa; p.ci = ci; p.flags = flags;
 	p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp; p.dnsamp_g = ctx->d_comp + ctx->ht->comp.size(); p.edge_tab = ctx->d_edge_tab; p.fix_clip = fix_clip;
 	const int wpb = 8;
@@ -831,7 +833,7 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 /* ---------------- pull path: int16 slots -> TRXD uplink datagrams ---------------- */
 static void pull_scratch_free(PullScratch &w)
 {
-	cudaFree(w.bursts); cudaFree(w.soft); cudaFree(w.type2); cudaFree(w.tsc_out); cudaFree(w.amp); cudaFree(w.toa);
+	cudaFree(w.bursts); cudaFree(w.pw); cudaFree(w.type2); cudaFree(w.tsc_out); cudaFree(w.amp); cudaFree(w.toa);
 	cudaFree(w.ci); cudaFree(w.ws.corr); cudaFree(w.ws.pwr);
 	w = PullScratch();
 }
@@ -854,7 +856,7 @@ static int pull_scratch_get(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, i
 	pull_scratch_free(w);
 	w.ws = keep;
 	CK(cudaMalloc(&w.bursts, (size_t)cap * win * 8));
-	CK(cudaMalloc(&w.soft, (size_t)cap * soft_stride * 4));
+	CK(cudaMalloc(&w.pw, (size_t)cap * 80 * 4));
 	CK(cudaMalloc(&w.type2, cap)); CK(cudaMalloc(&w.tsc_out, cap));
 	CK(cudaMalloc(&w.amp, (size_t)cap * 8)); CK(cudaMalloc(&w.toa, (size_t)cap * 4)); CK(cudaMalloc(&w.ci, (size_t)cap * 4));
 	w.cap = cap; w.soft_stride = soft_stride; w.win = win;
@@ -914,18 +916,17 @@ static int pull_chunk(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, const t
 				  tsc_out, ci, flags, 0);
 	}
 	if (r) return r;
-	r = launch_demod(ctx, st, nullptr, 0, m, rc, amp, toa, ci, flags, w.soft, w.soft_stride, 148, 1, w.type2, 0, iq, a->stride, type,
-			 energy);
+	r = launch_demod(ctx, st, nullptr, 0, m, rc, amp, toa, ci, flags, nullptr, 0, 148, 1, w.type2, 0, iq, a->stride, type, w.pw, pkt,
+			 a->pkt_stride, a->trxd_version);
 	if (r) return r;
-	PackParams pp;
-	pp.n = m; pp.version = a->trxd_version; pp.type = type; pp.rc = rc; pp.toa = toa; pp.ci = ci; pp.energy = energy;
-	pp.tsc_out = tsc_out; pp.fn = fn; pp.tn = tn; pp.soft = w.soft; pp.soft_stride = w.soft_stride;
-	pp.full_scale = a->rx_full_scale; pp.rssi_offset = a->rssi_offset; pp.pkt = pkt; pp.pkt_stride = a->pkt_stride;
-	pp.pkt_len = pkt_len; pp.flags = flags;
+	HeaderParams hp;
+	hp.n = m; hp.version = a->trxd_version; hp.type = type; hp.rc = rc; hp.toa = toa; hp.ci = ci; hp.pw = w.pw; hp.energy = energy;
+	hp.tsc_out = tsc_out; hp.fn = fn; hp.tn = tn; hp.full_scale = a->rx_full_scale; hp.rssi_offset = a->rssi_offset; hp.pkt = pkt;
+	hp.pkt_stride = a->pkt_stride; hp.pkt_len = pkt_len; hp.flags = flags;
 	prof_pre(ctx, st);
-	pack_kernel<<<std::max(1, std::min((m + 255) / 256, ctx->sm_count * 8)), 256, 0, st>>>(pp);
-	prof_post(ctx, st, "pack_kernel");
-	return post_launch(ctx, "pack_kernel");
+	header_kernel<<<std::max(1, std::min((m + 32 * kHdrWarps - 1) / (32 * kHdrWarps), ctx->sm_count * 8)), kHdrWarps * 32, 0, st>>>(hp);
+	prof_post(ctx, st, "header_kernel");
+	return post_launch(ctx, "header_kernel");
 }
 
 int trxb200_pull_batch(trxb200_ctx *ctx, const trxb200_pull_args *a)

@@ -173,6 +173,30 @@ __device__ __forceinline__ float2 comp_output(const DemodParams &p, const float2
 	return d;
 }
 
+// soft values staged in shared memory -> the datagram's soft bytes (vectorSlicer + trxd_fill_burst_normalized255), written
+// to the slot's row behind the header.  bytes: scratch indexed by (packet byte - 8); rows that cannot hold the burst
+// are left untouched (header_kernel flags them).
+__device__ __forceinline__ void store_soft_bytes(const DemodParams &p, int b, const float *soft, int nbits, uint8_t *bytes, int lane)
+{
+	const int hdr = p.pkt_hdr;
+	const int len = hdr + nbits + (p.pkt_v0 ? 2 : 0);
+	if (len > p.pkt_stride) return;
+	for (int j = lane; j < nbits; j += 32) bytes[hdr - 8 + j] = (uint8_t)soft_to_u8(soft[j]);
+	if (p.pkt_v0 && lane < 2) bytes[hdr - 8 + nbits + lane] = 0;
+	if (lane < hdr - 8) bytes[lane] = 0; // v1: bytes 8..10 are header bytes (header_kernel fills them afterwards)
+	__syncwarp();
+	uint8_t *row = p.pkt + (size_t)b * p.pkt_stride;
+	if ((reinterpret_cast<uintptr_t>(row) & 3u) == 0) {
+		// whole words from byte 8 (v1: its bytes 8..10 are rewritten by header_kernel, which runs after this kernel)
+		const uint32_t *s4 = reinterpret_cast<const uint32_t *>(bytes);
+		const int nw = (len - 8) >> 2;
+		for (int k = lane; k < nw; k += 32) reinterpret_cast<uint32_t *>(row + 8)[k] = s4[k];
+		if (lane < ((len - 8) & 3)) row[8 + 4 * nw + lane] = bytes[4 * nw + lane];
+	} else {
+		for (int k = hdr + lane; k < len; k += 32) row[k] = bytes[k - 8];
+	}
+}
+
 // ---- EDGE: demodEdgeBurst :2105-2128 after the decimator: decs[2 + i], i < 156, hold the scaled complex
 //      1-sps samples (the shared FIR pass below produced them) ----
 __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2 *decs, int lane)
@@ -227,6 +251,11 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 		}
 	}
 	__syncwarp();
+	if (p.pkt) {
+		// pull chain: datagram bytes instead of the float row (scratch behind the 444 staged values)
+		store_soft_bytes(p, b, ost, 444, reinterpret_cast<uint8_t *>(ost + kYxOff), lane);
+		__syncwarp();
+	} else {
 	const int nvals = 3 * min(148, p.soft_stride / 3); // a row shorter than 444 values is never overrun
 	float *orow = p.soft + (size_t)b * p.soft_stride;
 	if ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0 && (nvals & 3) == 0) {
@@ -241,6 +270,7 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 	} else {
 		for (int j = lane; j < nvals; j += 32)
 			orow[j] = ost[j];
+	}
 	}
 #pragma unroll
 	for (int o = 16; o; o >>= 1)
@@ -356,10 +386,11 @@ __device__ __forceinline__ void stage_async16(const short2 *x, int off2, float2 
 	}
 }
 
-// energyDetect(burst, 20 * sps) of pullRadioVector (Transceiver.cpp:723-731, sigProcLib.cpp:1573-1585) on an int16 slot:
-// sequential float sum of |x[4i]|^2, i < 80, divided by 80.  The samples come from the staged window when it covers
-// them (Uw != nullptr), else from the row; scr: 80 floats of scratch.
-__device__ __forceinline__ void energy16(const short2 *xg, const short2 *Uw, int off2, int lane, float *scr, float *dst)
+// The terms of energyDetect(burst, 20 * sps) (pullRadioVector, Transceiver.cpp:723-731, sigProcLib.cpp:1573-1585) on
+// an int16 slot: |x[4i]|^2, i < 80, written to the slot's row of p.pw.  The sequential float sum over them is
+// header_kernel's (lanes = slots there: 80 dependent adds cost 2.5 instructions per slot instead of 100 here).
+// The samples come from the staged window when it covers them (Uw != nullptr), else from the row.
+__device__ __forceinline__ void energy_terms16(const short2 *xg, const short2 *Uw, int off2, int lane, float *dst)
 {
 #pragma unroll
 	for (int k = 0; k < 3; k++) {
@@ -367,20 +398,9 @@ __device__ __forceinline__ void energy16(const short2 *xg, const short2 *Uw, int
 		if (idx < 80) {
 			const unsigned v = Uw ? reinterpret_cast<const unsigned *>(Uw)[4 * idx - off2]
 					      : __ldg(reinterpret_cast<const unsigned *>(xg) + 4 * idx);
-			scr[idx] = norm2(cvt_s2(v));
+			dst[idx] = norm2(cvt_s2(v));
 		}
 	}
-	__syncwarp();
-	if (lane == 0) {
-		float e = 0.0f;
-#pragma unroll
-		for (int i = 0; i < 20; i++) {
-			const float4 q = reinterpret_cast<const float4 *>(scr)[i];
-			e = fa(fa(fa(fa(e, q.x), q.y), q.z), q.w);
-		}
-		*dst = e / 80.0f;
-	}
-	__syncwarp();
 }
 
 template <bool I16>
@@ -473,8 +493,7 @@ demod_kernel(DemodParams p)
 		bool want_energy = false;
 		if constexpr (I16) {
 			want_energy = p.type_raw[b] != 0;
-			if (!want_energy && lane == 0) p.energy[b] = 0.0f;
-			if (want_energy && rc <= 0) energy16(row_s(b), nullptr, 0, lane, reinterpret_cast<float *>(yv), &p.energy[b]);
+			if (want_energy && rc <= 0) energy_terms16(row_s(b), nullptr, 0, lane, p.pw + (size_t)b * 80);
 		}
 		if (rc <= 0) {
 			// undetected burst: only the deferred clipping report is left to do (sigProcLib.cpp:1746-1764)
@@ -524,8 +543,8 @@ demod_kernel(DemodParams p)
 		if constexpr (I16) {
 			if (want_energy) {
 				const bool in_win = bg.off2 <= 0 && 316 - bg.off2 < 4 * kSlots16;
-				energy16(row_s(b), in_win ? reinterpret_cast<const short2 *>(U) : nullptr, bg.off2, lane,
-					 reinterpret_cast<float *>(yv), &p.energy[b]);
+				energy_terms16(row_s(b), in_win ? reinterpret_cast<const short2 *>(U) : nullptr, bg.off2, lane,
+					       p.pw + (size_t)b * 80);
 			}
 		}
 
@@ -746,6 +765,12 @@ demod_kernel(DemodParams p)
 		__syncwarp();
 		if (edge) {
 			demod_edge_tail(p, b, decs, lane);
+			__syncwarp();
+			continue;
+		}
+		if constexpr (I16) {
+			// ---- pull chain: the soft values leave as datagram bytes ----
+			store_soft_bytes(p, b, ostage, nout, reinterpret_cast<uint8_t *>(yx), lane);
 			__syncwarp();
 			continue;
 		}

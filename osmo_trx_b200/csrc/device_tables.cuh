@@ -61,4 +61,29 @@ __device__ __forceinline__ float2 cmul_exact(float2 a, float2 b)
 	return make_float2(fs(fm(a.x, b.x), fm(a.y, b.y)), fa(fm(a.x, b.y), fm(a.y, b.x)));
 }
 
+
+// `(int32) = double` the way x86-64 cvttsd2si does it (the reference's implicit conversions in proto_trxd.c compile
+// to it): truncation, 0x80000000 for NaN and out-of-range values
+__device__ __forceinline__ int dbl_to_i32_x86(double v)
+{
+	if (!(v > -2147483649.0 && v < 2147483648.0)) return (int)0x80000000;
+	return (int)v; // in range: cvt.rzi
+}
+
+// vectorSlicer (sigProcLib.cpp:546-556) + trxd_fill_burst_normalized255 (proto_trxd.c:62-67):
+// (uint8_t)round(clamp(0.5 * (s + 1), 0, 1) * 255.0); round() is half away from zero and the argument is >= 0 or NaN
+__device__ __forceinline__ unsigned soft_to_u8(float s)
+{
+	float v = fm(0.5f, fa(s, 1.0f));
+	if (v > 1.0f) v = 1.0f;
+	else if (v < 0.0f) v = 0.0f;
+	// The reference evaluates round(v * 255.0) in double, where the product is exact.  The same integer in FP32: a
+	// candidate from the rounded product, then the two neighbouring half-integer boundaries are tested with a fused
+	// multiply-add, whose sign is that of the exact v * 255 - boundary (k +- 0.5 are exact floats).
+	int k = __float2int_rd(fmaf(v, 255.0f, 0.5f));
+	if (fmaf(v, 255.0f, -((float)k + 0.5f)) >= 0.0f) k++;
+	else if (fmaf(v, 255.0f, -((float)k - 0.5f)) < 0.0f) k--;
+	return (v == v) ? ((unsigned)k & 0xffu) : 0u; // NaN: cvttsd2si gives 0x80000000, whose low byte is 0
+}
+
 } // namespace trxb200

@@ -59,7 +59,9 @@ struct DemodParams {
 	const int16_t *iq;	 // [n][iq_stride] complex int16 (I,Q); replaces `bursts`
 	int iq_stride;
 	const uint8_t *type_raw; // slot types as scheduled by the caller (0 = off: no measurement)
-	float *energy;		 // energyDetect(slot, 80)
+	float *pw;		 // [n][80] |x[4i]|^2, the terms of energyDetect(slot, 80); summed in order by header_kernel
+	uint8_t *pkt;		 // [n][pkt_stride] TRXD datagram rows: the soft bytes are written here (header_kernel adds the header)
+	int pkt_stride, pkt_hdr, pkt_v0; // header length (8 / 11), v0 = two trailing zero bytes
 };
 
 // receive chain around the hot path (pull.cu)
@@ -86,16 +88,16 @@ struct SchedParams {
 	uint16_t *max_toa_out;	   // may be null
 };
 
-struct PackParams {
+struct HeaderParams {
 	int n, version;
 	const uint8_t *type; // caller's slot types (OFF emits nothing)
 	const int32_t *rc;
-	const float *toa, *ci, *energy;
+	const float *toa, *ci;
+	const float *pw;     // [n][80] terms of energyDetect, written by demod_kernel<true>
+	float *energy;	     // out: energyDetect(slot, 80)
 	const uint8_t *tsc_out;
 	const uint32_t *fn;
 	const uint8_t *tn;
-	const float *soft;
-	int soft_stride;
 	double full_scale, rssi_offset;
 	uint8_t *pkt;
 	int pkt_stride;

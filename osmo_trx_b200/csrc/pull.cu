@@ -7,9 +7,10 @@
 //   demod_kernel<true> (demod.cu) reads the int16 slot itself: conversion on the way to the FIR, plus pullRadioVector's
 //                   pre-detection power measurement energyDetect(burst, 20*sps) (Transceiver.cpp:723-731,
 //                   sigProcLib.cpp:1573-1585) from the staged slot.
-//   pack_kernel     what follows demodAnyBurst: RSSI (:742-751), vectorSlicer (:803, sigProcLib.cpp:546-556),
-//                   idle handling (:810-814) and trxd_send_burst_ind_v0/_v1's header + soft bits normalised
-//                   to 0..255 (proto_trxd.c:27-117), written as the exact datagram bytes.
+//                   It writes the soft bits straight into the datagram rows: vectorSlicer (:803,
+//                   sigProcLib.cpp:546-556) + soft bits normalised to 0..255 (proto_trxd.c:62-67).
+//   header_kernel   the slot power (ordered sum of the terms demod left), RSSI (:742-751), idle handling
+//                   (:810-814) and trxd_send_burst_ind_v0/_v1's header (proto_trxd.c:27-60).
 // Detection in between is the float path's corr/peak kernels, unchanged, on the extracted windows.
 #include "device_tables.cuh"
 #include "kernels.hpp"
@@ -104,111 +105,85 @@ sched_kernel(SchedParams p)
 	if (p.max_toa_out) p.max_toa_out[i] = (uint16_t)((r == 3 || r == 2) ? p.max_toa_ab : p.max_toa_nb);
 }
 
-namespace {
-
-// `(int32) = double` the way x86-64 cvttsd2si does it (the reference's implicit conversions in proto_trxd.c
-// compile to it): truncation, 0x80000000 for NaN and out-of-range values
-__device__ __forceinline__ int dbl_to_i32_x86(double v)
+// header_kernel: what surrounds the soft bytes demod_kernel<true> has already written into the datagram rows.  Lanes =
+// slots.  The slot power is the sequential float sum of the 80 terms demod_kernel<true> left in p.pw (a warp's 32 rows
+// are brought into shared memory coalesced and summed one row per lane); then RSSI (:742-751, in double as the
+// reference), idle handling (:810-814) and trxd_send_burst_ind_v0/_v1's header (proto_trxd.c:27-60).  Rows of slots
+// that emit nothing (OFF, v0 idle, truncated) get pkt_len 0 and are not touched.
+constexpr int kHdrWarps = 4;
+__global__ void __launch_bounds__(kHdrWarps * 32)
+header_kernel(HeaderParams p)
 {
-	if (!(v > -2147483649.0 && v < 2147483648.0)) return (int)0x80000000;
-	return (int)v; // in range: cvt.rzi
-}
-
-constexpr int kPktMax = 11 + 444 + 2;
-
-} // namespace
-
-// A warp takes 32 slots at a time.  First the headers, lanes = slots: the RSSI's double-precision log10 and the
-// scalar loads of 32 slots run side by side instead of one after the other on a single lane.  Then the warp walks
-// the 32 slots: soft bits -> bytes, the row assembled in shared memory and written with 4-byte stores where the row
-// allows it.  Rows of slots that emit nothing (OFF, v0 idle, truncated) get pkt_len 0 and are not touched.
-__global__ void __launch_bounds__(256)
-pack_kernel(PackParams p)
-{
-	__shared__ __align__(16) uint8_t spk_all[8][464];
-	__shared__ __align__(16) uint8_t hdr_all[8][32][12];
-	__shared__ int len_all[8][32];
+	__shared__ float pwt[kHdrWarps][32][81]; // odd pitch: a lane walking its row stays on its own bank
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int wpb = blockDim.x >> 5;
-	uint8_t *spk = spk_all[warp];
 	const int hdr = p.version == 1 ? 11 : 8;
 	const int ntiles = (p.n + 31) >> 5;
-	for (int tile = blockIdx.x * wpb + warp; tile < ntiles; tile += gridDim.x * wpb) {
+	for (int tile = blockIdx.x * kHdrWarps + warp; tile < ntiles; tile += gridDim.x * kHdrWarps) {
+		const int b0 = tile * 32;
+		const int nb = min(32, p.n - b0);
 		__syncwarp();
-		{
-			const int b = tile * 32 + lane;
-			int len = 0;
-			if (b < p.n) {
-				const int type = p.type[b];
-				const int rc = p.rc[b];
-				const bool idle = !(rc > 0);
-				const bool psk8 = (rc == 5);
-				const int nbits = idle ? 0 : (psk8 ? 444 : 148);
-				bool trunc = false;
-				if (type != 0 && !(p.version == 0 && idle)) {
-					len = hdr + nbits + ((p.version == 0) ? 2 : 0);
-					if (p.version == 1 && idle) len = hdr;
-					if (len > p.pkt_stride || (!idle && nbits > p.soft_stride)) { len = 0; trunc = true; }
-				}
-				if (len > 0) {
-					uint8_t *h = hdr_all[warp][lane];
-					// trxd_fill_common :27-33
-					const uint32_t fn = p.fn[b];
-					h[0] = (uint8_t)((p.tn[b] & 7) | ((p.version & 15) << 4));
-					h[1] = (uint8_t)(fn >> 24); h[2] = (uint8_t)(fn >> 16); h[3] = (uint8_t)(fn >> 8); h[4] = (uint8_t)fn;
-					// Transceiver.cpp:742,751 then trxd_fill_v0_specific :35-44
-					const float avg = __fsqrt_rn(p.energy[b]);
-					const double rssi = 20.0 * log10(p.full_scale / (double)avg) + p.rssi_offset;
-					h[5] = (uint8_t)((unsigned)dbl_to_i32_x86(rssi) & 0xffu);
-					const double toa = idle ? 0.0 : (double)p.toa[b];
-					const unsigned toa_i = (unsigned)dbl_to_i32_x86(toa * 256.0 + 0.5);
-					h[6] = (uint8_t)(toa_i >> 8); h[7] = (uint8_t)toa_i;
-					if (p.version == 1) {
-						// trxd_fill_v1_specific :46-60 (ci * 10 is a float product)
-						const float ci = idle ? 0.0f : p.ci[b];
-						const unsigned ci_cb = (unsigned)dbl_to_i32_x86((double)fm(ci, 10.0f) + 0.5);
-						const int tsc = idle ? 0 : p.tsc_out[b];
-						h[8] = (uint8_t)((tsc & 7) | ((psk8 ? 4 : 0) << 3) | ((idle ? 1 : 0) << 7));
-						h[9] = (uint8_t)(ci_cb >> 8); h[10] = (uint8_t)ci_cb;
-					}
-				}
-				p.pkt_len[b] = (uint16_t)len;
-				if (p.flags && trunc) p.flags[b] |= 8;
-			}
-			len_all[warp][lane] = len;
+		for (int j = 0; j < nb; j++) {
+			const float *row = p.pw + (size_t)(b0 + j) * 80;
+#pragma unroll
+			for (int k = 0; k < 3; k++)
+				if (lane + 32 * k < 80) pwt[warp][j][lane + 32 * k] = row[lane + 32 * k];
 		}
 		__syncwarp();
-		const int nb = min(32, p.n - tile * 32);
-		for (int j = 0; j < nb; j++) {
-			const int len = len_all[warp][j];
-			if (len == 0) continue;
-			const int b = tile * 32 + j;
-			const int nbits = len - hdr - ((p.version == 0) ? 2 : 0);
-			if (lane < 12) spk[lane] = hdr_all[warp][j][lane]; // bytes past the header are overwritten below
-			__syncwarp();
-			// vectorSlicer + trxd_fill_burst_normalized255 :62-67: (uint8_t)round(clamp(0.5*(s+1),0,1) * 255.0)
-			const float *srow = p.soft + (size_t)b * p.soft_stride;
-			for (int i = lane; i < nbits; i += 32) {
-				float v = fm(0.5f, fa(srow[i], 1.0f));
-				if (v > 1.0f) v = 1.0f;
-				else if (v < 0.0f) v = 0.0f;
-				const double x = (double)v * 255.0; // exact (24-bit x 8-bit significands)
-				// round(): half away from zero; x >= 0 or NaN here
-				spk[hdr + i] = (uint8_t)((unsigned)dbl_to_i32_x86(floor(x + 0.5)) & 0xffu);
+		const int b = b0 + lane;
+		if (b >= p.n) continue;
+		const int type = p.type[b];
+		const int rc = p.rc[b];
+		float e = 0.0f;
+		if (type != 0) {
+#pragma unroll 8
+			for (int i = 0; i < 80; i++) e = fa(e, pwt[warp][lane][i]);
+			e = e / 80.0f;
+		}
+		p.energy[b] = e;
+		const bool idle = !(rc > 0);
+		const bool psk8 = (rc == 5);
+		const int nbits = idle ? 0 : (psk8 ? 444 : 148);
+		int len = 0;
+		bool trunc = false;
+		if (type != 0 && !(p.version == 0 && idle)) {
+			len = hdr + nbits + ((p.version == 0) ? 2 : 0);
+			if (p.version == 1 && idle) len = hdr;
+			if (len > p.pkt_stride) { len = 0; trunc = true; }
+		}
+		if (len > 0) {
+			uint8_t h[11];
+			// trxd_fill_common :27-33
+			const uint32_t fn = p.fn[b];
+			h[0] = (uint8_t)((p.tn[b] & 7) | ((p.version & 15) << 4));
+			h[1] = (uint8_t)(fn >> 24); h[2] = (uint8_t)(fn >> 16); h[3] = (uint8_t)(fn >> 8); h[4] = (uint8_t)fn;
+			// Transceiver.cpp:742,751 then trxd_fill_v0_specific :35-44
+			const float avg = __fsqrt_rn(e);
+			const double rssi = 20.0 * log10(p.full_scale / (double)avg) + p.rssi_offset;
+			h[5] = (uint8_t)((unsigned)dbl_to_i32_x86(rssi) & 0xffu);
+			const double toa = idle ? 0.0 : (double)p.toa[b];
+			const unsigned toa_i = (unsigned)dbl_to_i32_x86(toa * 256.0 + 0.5);
+			h[6] = (uint8_t)(toa_i >> 8); h[7] = (uint8_t)toa_i;
+			h[8] = h[9] = h[10] = 0;
+			if (p.version == 1) {
+				// trxd_fill_v1_specific :46-60 (ci * 10 is a float product)
+				const float ci = idle ? 0.0f : p.ci[b];
+				const unsigned ci_cb = (unsigned)dbl_to_i32_x86((double)fm(ci, 10.0f) + 0.5);
+				const int tsc = idle ? 0 : p.tsc_out[b];
+				h[8] = (uint8_t)((tsc & 7) | ((psk8 ? 4 : 0) << 3) | ((idle ? 1 : 0) << 7));
+				h[9] = (uint8_t)(ci_cb >> 8); h[10] = (uint8_t)ci_cb;
 			}
-			if (p.version == 0 && lane < 2) spk[hdr + nbits + lane] = 0;
-			__syncwarp();
 			uint8_t *row = p.pkt + (size_t)b * p.pkt_stride;
 			if ((reinterpret_cast<uintptr_t>(row) & 3u) == 0) {
-				const uint32_t *s4 = reinterpret_cast<const uint32_t *>(spk);
-				const int nw = len >> 2;
-				for (int k = lane; k < nw; k += 32) reinterpret_cast<uint32_t *>(row)[k] = s4[k];
-				if (lane < (len & 3)) row[4 * nw + lane] = spk[4 * nw + lane];
+				reinterpret_cast<uint32_t *>(row)[0] = (uint32_t)h[0] | ((uint32_t)h[1] << 8) | ((uint32_t)h[2] << 16) | ((uint32_t)h[3] << 24);
+				reinterpret_cast<uint32_t *>(row)[1] = (uint32_t)h[4] | ((uint32_t)h[5] << 8) | ((uint32_t)h[6] << 16) | ((uint32_t)h[7] << 24);
 			} else {
-				for (int k = lane; k < len; k += 32) row[k] = spk[k];
+#pragma unroll
+				for (int k = 0; k < 8; k++) row[k] = h[k];
 			}
-			__syncwarp();
+			if (p.version == 1) { row[8] = h[8]; row[9] = h[9]; row[10] = h[10]; } // byte 11 is the first soft byte
 		}
+		p.pkt_len[b] = (uint16_t)len;
+		if (p.flags && trunc) p.flags[b] |= 8;
 	}
 }
 
