@@ -101,7 +101,7 @@ def main():
             po = trx.alloc_pull_results(n, 160)
             t_pull = timed(lambda: trx.pull(iq, typ, tsc, mt, fn, tn, bound, out=po))
             add("pull[nb] int16 -> TRXD v1", "burst", n, 2500 + 159 + 10, t_pull,
-                "extract (correlator windows) + detect + demod on the int16 slot + pack; issue bound in demod_kernel<true>, not HBM bound")
+                "gate + detect and demod on the int16 slot (soft bits written as datagram bytes) + header; issue bound in demod_kernel<true>, not HBM bound")
             # ---- helpers ----
             e_t = timed(lambda: trx.energy_detect(rx, 80))
             add("energy_detect_kernel", "burst", n, 80 * 32 + 4, e_t,
