@@ -305,6 +305,27 @@ def emit(line):
     out.flush()
 
 
+def bind_near_gpu(index):
+    """Run this rank on the CPU cores NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end measurement are first-touched on that NUMA node (one process per GPU: without it eight ranks share
+    whatever node the launcher started them on and the H2D streams cross the socket link)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def main():
     args = parse()
     _stdout_to_stderr()
@@ -320,6 +341,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    near = bind_near_gpu(local) if world > 1 else 0
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
@@ -437,6 +459,7 @@ def main():
         e2e = {"value": world * ne * reps / dt, "unit": "bursts/s", "h2d_bytes_per_step": ne * (2500 + 1 + 1 + 2 + 4 + 1),
                "d2h_bytes_per_step": ne * (4 + 4 + pstride + 2 + 1), "bursts_per_call": ne,
                "api": "trxb200_pull_host: int16 I/Q slots in (pinned host), TRXD v1 datagrams out (pinned host)",
+               "host_cores_bound_near_gpu": near,
                "sent_fraction": float((h_pout["pkt_len"] > 11).float().mean().item()), "gpu_launches": int(e2e_launches)}
         del h_iq, h_pout
     if not args.no_e2e:
