@@ -188,25 +188,17 @@ vitac_kernel(VitacParams p)
 				const int rb = st - p.lo; // window position of the burst's first sample (warp uniform)
 				const int e0 = rb & 3;
 				const float2 *cs = csel + (lane & 1) * kCirLen;
-				// tap ii of output nn reads window sample rb + 4 nn + ii = plane (e0 + ii) & 3, index (rb >> 2) + nn + (e0 + ii) / 4:
-				// with the phase e0 fixed by a (warp-uniform) switch every tap is a constant offset from four plane pointers
 				for (int nn = lane; nn < N; nn += 32) {
-					const float2 *xq = xs + (rb >> 2) + nn;
+					const float2 *xq = xs + (rb >> 2) + nn; // sample rb + 4 nn + ii: plane (e0 + ii) & 3, index + (e0 + ii) >> 2
 					const int lim = min(kCirLen, kOSR * (N - nn));
 					float acc = 0.0f;
 					if (lim == kCirLen) {
-#define VT_MF(E0)                                                                                                    \
-	_Pragma("unroll") for (int ii = 0; ii < kCirLen; ii++) {                                                        \
-		const float2 v = xq[(((E0) + ii) & 3) * P + (((E0) + ii) >> 2)], c = cs[ii];                                  \
-		acc = fa(acc, fa(fm(v.x, c.x), fm(v.y, c.y)));                                                              \
-	}
-						switch (e0) {
-						case 0: VT_MF(0) break;
-						case 1: VT_MF(1) break;
-						case 2: VT_MF(2) break;
-						default: VT_MF(3) break;
+#pragma unroll
+						for (int ii = 0; ii < kCirLen; ii++) {
+							const int e = e0 + ii;
+							const float2 v = xq[(e & 3) * P + (e >> 2)], c = cs[ii];
+							acc = fa(acc, fa(fm(v.x, c.x), fm(v.y, c.y)));
 						}
-#undef VT_MF
 					} else {
 						for (int ii = 0; ii < lim; ii++) {
 							const int e = e0 + ii;
@@ -264,12 +256,11 @@ vitac_kernel(VitacParams p)
 			if (s == 0) {
 				unsigned state = sF;
 #pragma unroll
-				const unsigned hs = h << 4;
 				for (int wi = 4; wi >= 0; wi--) {
-					unsigned acc = 0u; // steps run downwards and every chunk ends on bit 0: shift the decisions in
+					unsigned acc = 0u;
 					for (int k = min(N - 1, 32 * wi + 31); k >= 32 * wi; k--) {
-						const unsigned g = (words[2 * k] >> (hs + state)) & 1u;
-						acc = (acc << 1) + g;
+						const unsigned g = (words[2 * k] >> ((h << 4) + state)) & 1u;
+						acc |= g << (k & 31);
 						state = (state >> 1) + (g << 3);
 					}
 					gw[wi] = acc;
