@@ -121,6 +121,14 @@ int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int 
  * A burst that needs more than the configured sizes is reported as -SIGERR_BOUNDS, never processed wrongly. */
 int trxb200_detect_config(trxb200_ctx *ctx, int max_seq_len, int max_attempts);
 
+/* ---- detectSCHBurst(burst, thresh, 4, SCH_DETECT_FULL, &ebp) (sigProcLib.cpp:1805-1861), the single-burst search
+ *      of the MS side: 64-symbol synchronisation sequence, 156 correlation outputs (head = 105, tail = 51 symbols).
+ *      rc: 1 detected / 0 not (detectBurst's value, as the reference returns it); amp, toa (relative to the expected
+ *      position, head subtracted), ci as in estim_burst_params; flags may be NULL.  The NARROW state reads past its
+ *      8-sample decimated vector in the reference and the BUFFER state searches a 12-frame capture: neither is offered. ---- */
+int trxb200_detect_sch_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, float thresh, int32_t *rc, float *amp,
+			     float *toa, float *ci, uint8_t *flags);
+
 /* ---- demodulation: demodAnyBurst (sigProcLib.cpp:2130-2137) for every burst with rc[b] > 0
  *      (rc[b] is the CorrType returned by detection).  soft: f32[n][soft_stride]; GMSK bursts get
  *      `n_gmsk_soft` values (148 = what Transceiver.cpp:799-803 consumes, or 156 = the full

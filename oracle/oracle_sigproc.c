@@ -536,6 +536,31 @@ static int detect_general(const ocf *burst, int blen, float thresh, int sps, int
 	return 1;
 }
 
+/* detectSCHBurst :1805-1861 in its SCH_DETECT_FULL state (the single-burst search: head = target - 1 symbols,
+ * tail = 39 + 3 + 9): downsampleBurst(burst, len * 4, len) is the default 624 -> 156 decimation, the correlation
+ * starts at sample 0 of the decimated burst, so the 64-tap sequence reaches 63 samples before it - zeros (convolve's
+ * CUSTOM span prepends head-room :325-329).  Returns detectBurst's rc (1 on a hit). */
+int orc_detect_sch_burst(const ocf *burst, int blen, float thresh, int sps, orc_ebp *ebp, int *flags)
+{
+	orc_setup();
+	if (sps != 4)
+		return -1;
+	const int target = 3 + 39 + 64, head = target - 1, tail = 39 + 3 + 9;
+	const int start = (target - head) - 1, len = head + tail;
+	ocf dec[ORC_DEC_LEN];
+	orc_downsample_burst(burst, blen, dec);
+	int rc = detect_burst(dec, ORC_DEC_LEN, &T.sch, thresh, start, len, ebp, flags);
+	if (rc < 0)
+		return -1;
+	if (!rc) {
+		ebp->amp.r = ebp->amp.i = 0.0f;
+		ebp->toa = 0.0f;
+		return 0;
+	}
+	ebp->toa -= head; /* "Subtract forward search bits from delay" */
+	return rc;
+}
+
 /* detectAnyBurst :1926-1957 with analyzeTrafficBurst :1887, detectRACHBurst :1782,
  * detectEdgeBurst :1906, detectDummyBurst :1863 */
 int orc_detect_any_burst(const ocf *burst, int blen, unsigned tsc, float thresh, int sps, int type, unsigned max_toa,

@@ -78,6 +78,8 @@ typedef struct { ocf amp; float toa; uint8_t tsc; float ci; } orc_ebp; /* sigPro
 int orc_detect_any_burst(const ocf *burst, int blen, unsigned tsc, float thresh, int sps, int type, unsigned max_toa,
 			 orc_ebp *ebp, int *edge_flags);
 int orc_demod_any_burst(const ocf *burst, int blen, int type, int sps, orc_ebp *ebp, float *soft /*>=444*/);
+/* detectSCHBurst sigProcLib.cpp:1805-1861, SCH_DETECT_FULL */
+int orc_detect_sch_burst(const ocf *burst, int blen, float thresh, int sps, orc_ebp *ebp, int *edge_flags);
 int orc_detect_batch(const float *bursts, int stride, int blen, int n, const uint8_t *type, const uint8_t *tsc,
 		     const uint16_t *max_toa, float thresh, int sps, int32_t *rc, float *amp, float *toa,
 		     uint8_t *tsc_out, float *ci, uint8_t *flags, int nthreads);

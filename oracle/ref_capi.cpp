@@ -224,6 +224,21 @@ int ref_detect_batch(const float *bursts, int stride, int blen, int n, const uin
 	return n;
 }
 
+/* detectSCHBurst(burst, thresh, 4, SCH_DETECT_FULL, &ebp) sigProcLib.cpp:1805-1861 per burst */
+int ref_detect_sch_batch(const float *bursts, int stride, int blen, int n, float thresh, int32_t *rc, float *amp, float *toa,
+			 float *ci)
+{
+	for (int b = 0; b < n; b++) {
+		BurstView bv(bursts + (size_t)b * stride * 2, blen);
+		struct estim_burst_params ebp;
+		ebp.amp = 0.0f; ebp.toa = 0.0f; ebp.tsc = 0; ebp.ci = 0.0f;
+		rc[b] = detectSCHBurst(bv.v, thresh, 4, sch_detect_type::SCH_DETECT_FULL, &ebp);
+		amp[2 * b] = ebp.amp.real(); amp[2 * b + 1] = ebp.amp.imag();
+		toa[b] = ebp.toa; ci[b] = ebp.ci;
+	}
+	return n;
+}
+
 /* demodAnyBurst sigProcLib.cpp:2130-2137 for bursts with rc > 0; soft: [n][soft_stride] floats
  * (156 GMSK / 444 EDGE written; rest untouched); nsoft[b] = returned SoftVector size (0 if skipped). */
 int ref_demod_batch(const float *bursts, int stride, int blen, int n, const int32_t *rc, const float *amp,

@@ -263,6 +263,21 @@ class Trx:
         self._check(self.lib.trxb200_pull_host(self.h, C.byref(a)), "pull_host")
         return out
 
+    # -- SCH search (MS side) --
+    def detect_sch(self, bursts, thresh=BURST_THRESH):
+        """detectSCHBurst(SCH_DETECT_FULL) per burst.  bursts float32 [n, stride>=625, 2] (device)."""
+        _chk_dev(bursts)
+        n = bursts.shape[0]
+        d = bursts.device
+        r = dict(rc=torch.zeros(n, dtype=torch.int32, device=d), amp=torch.zeros((n, 2), dtype=torch.float32, device=d),
+                 toa=torch.zeros(n, dtype=torch.float32, device=d), ci=torch.zeros(n, dtype=torch.float32, device=d),
+                 flags=torch.zeros(n, dtype=torch.uint8, device=d))
+        self.use_current_stream()
+        self._check(self.lib.trxb200_detect_sch_batch(self.h, _ptr(bursts), C.c_int(bursts.stride(0) // 2), C.c_int(n),
+                                                      C.c_float(thresh), _ptr(r["rc"]), _ptr(r["amp"]), _ptr(r["toa"]),
+                                                      _ptr(r["ci"]), _ptr(r["flags"])), "detect_sch_batch")
+        return r
+
     # -- burst-type scheduler --
     def expected_corr_type(self, fn, tn, chan_type, handover, chan=None, ext_rach=False, egprs=False, max_toa_nb=4,
                            max_toa_ab=63):

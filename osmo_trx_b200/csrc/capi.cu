@@ -526,11 +526,13 @@ struct ChunkHook {
 static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, const float *bursts, int stride, int n,
 			 const uint8_t *type, const uint8_t *tsc, const uint16_t *max_toa, int bound, float thresh, int32_t *rc,
 			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags, int scan_clip,
-			 ChunkHook *after_chunk = nullptr, bool overlapped = false, const int16_t *iq = nullptr, int iq_stride = 0)
+			 ChunkHook *after_chunk = nullptr, bool overlapped = false, const int16_t *iq = nullptr, int iq_stride = 0,
+			 bool sch = false)
 {
 	const trxb200_ctx::Tune &tn = ctx->tune;
-	const int lmax = (16 + bound + 1) & ~1;		    // row pitch of the correlation vectors (even: 16-byte row loads in peak_kernel)
-	const int ndmax = ctx->max_seq_len + 16 + bound - 1; // decimated samples a correlation window needs
+	// sch: detectSCHBurst's full search (156 correlation outputs, 64-symbol sequence), one attempt, no per-burst arrays
+	const int lmax = sch ? 156 : (16 + bound + 1) & ~1;		    // row pitch of the correlation vectors (even: 16-byte row loads in peak_kernel)
+	const int ndmax = sch ? 64 + 156 - 1 : ctx->max_seq_len + 16 + bound - 1; // decimated samples a correlation window needs
 	// ---- launch geometry ----
 	const bool nb = (ndmax == 35 && lmax == 20); // 16-symbol sync, max_toa <= 4: register-blocked corr_nb_kernel
 	if (iq && !nb) return fail(ctx, TRXB200_EINVAL, "detect: int16 rows are read by corr_nb_kernel only");
@@ -581,14 +583,15 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 		CK(cudaMalloc(&ws.pwr, need_p));
 		ws.pwr_bytes = need_p;
 	}
-	const int rounds = ctx->max_attempts;
+	const int rounds = sch ? 1 : ctx->max_attempts;
 	for (long lo = 0; lo < n; lo += chunk) {
 		const int m = (int)std::min<long>(chunk, n - lo);
 		for (int r = 0; r < rounds; r++) {
 			CorrParams c;
 			c.bursts = bursts ? bursts + (size_t)lo * stride * 2 : nullptr; c.stride = stride; c.n = m;
 			c.iq = iq ? iq + (size_t)lo * iq_stride * 2 : nullptr; c.iq_stride = iq_stride;
-			c.type = type + lo; c.tsc = tsc + lo; c.max_toa = max_toa + lo; c.rc = rc + lo; c.round = r;
+			c.type = sch ? nullptr : type + lo; c.tsc = sch ? nullptr : tsc + lo; c.max_toa = sch ? nullptr : max_toa + lo; c.rc = rc + lo; c.round = r;
+			c.sch = sch ? 1 : 0;
 			c.max_toa_bound = bound; c.lmax = lmax; c.ndmax = ndmax; c.corr = ws.corr; c.pwr = ws.pwr; c.negzero = -0.0f;
 			const int ngroups = (m + cgroup - 1) / cgroup;
 			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));
@@ -600,10 +603,11 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			int e = post_launch(ctx, "corr_kernel");
 			if (e) return e;
 			PeakParams q;
-			q.n = m; q.type = type + lo; q.tsc = tsc + lo; q.max_toa = max_toa + lo; q.round = r; q.last_round = (r == rounds - 1);
+			q.n = m; q.type = sch ? nullptr : type + lo; q.tsc = sch ? nullptr : tsc + lo; q.max_toa = sch ? nullptr : max_toa + lo; q.round = r;
+			q.last_round = (r == rounds - 1); q.sch = sch ? 1 : 0;
 			q.max_toa_bound = bound; q.thresh = thresh; q.lmax = lmax; q.ndmax = ndmax; q.corr = ws.corr; q.pwr = ws.pwr;
 			q.sinc512 = ctx->d_sinc512; q.negzero = -0.0f; q.rc = rc + lo; q.amp = amp + (size_t)lo * 2; q.toa = toa + lo; q.ci = ci + lo;
-			q.tsc_out = tsc_out + lo; q.flags = flags ? flags + lo : nullptr;
+			q.tsc_out = tsc_out ? tsc_out + lo : nullptr; q.flags = flags ? flags + lo : nullptr;
 			const int ntiles = (m + 31) / 32;
 			const int pgrid = std::max(1, std::min((ntiles + pw - 1) / pw, ctx->sm_count * pbps));
 			prof_pre(ctx, st);
@@ -676,6 +680,17 @@ int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int 
 	if (n == 0) return TRXB200_OK;
 	return launch_detect(ctx, ctx->stream, ctx->ws, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp, toa,
 			     tsc_out, ci, flags, 1);
+}
+
+int trxb200_detect_sch_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, float thresh, int32_t *rc, float *amp,
+			     float *toa, float *ci, uint8_t *flags)
+{
+	if (ctx && n == 0) return TRXB200_OK;
+	int r = check_dd(ctx, bursts, stride, n, 0);
+	if (r) return r;
+	if (!rc || !amp || !toa || !ci) return fail(ctx, TRXB200_EINVAL, "detect_sch: null output");
+	return launch_detect(ctx, ctx->stream, ctx->ws, bursts, stride, n, nullptr, nullptr, nullptr, 0, thresh, rc, amp, toa, nullptr, ci,
+			     flags, 0, nullptr, false, nullptr, 0, true);
 }
 
 int trxb200_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, const int32_t *rc, const float *amp,

@@ -66,6 +66,9 @@ __device__ __forceinline__ float2 cvt_s2(unsigned word)
 	return add2(make_float2(__uint_as_float(lo), __uint_as_float(hi)), make_float2(-8421376.0f, -8421376.0f));
 }
 
+// internal burst type of the SCH search (trxb200_detect_sch_batch); never accepted from a caller's type array
+constexpr int kTypeSchFull = 7;
+
 struct Attempt {
 	int seq;   // sequence id or -1
 	int head;  // search symbols before target
@@ -96,13 +99,23 @@ __device__ __forceinline__ Attempt make_attempt(int type, int tsc, int T, int at
 	case 6:
 		if (attempt == 0) { a.seq = SEQ_DUMMY; a.head = 10; a.start = 71; a.len = 16 + T; a.rc_hit = 6; }
 		break;
+	case kTypeSchFull: // detectSCHBurst, SCH_DETECT_FULL :1805-1861: target 106, head 105, tail 51; returns detectBurst's rc
+		if (attempt == 0) { a.seq = SEQ_SCH; a.head = 105; a.start = 0; a.len = 156; a.rc_hit = 1; }
+		break;
 	default:
 		break;
 	}
 	return a;
 }
 
-__device__ __forceinline__ bool type_known(int type) { return type == 1 || type == 2 || type == 3 || type == 5 || type == 6; }
+__device__ __forceinline__ bool type_known(int type) { return type == 1 || type == 2 || type == 3 || type == 5 || type == 6 || type == kTypeSchFull; }
+// burst type as the kernels see it: the SCH search ignores the per-burst arrays; a caller's type array cannot select it
+__device__ __forceinline__ int load_type(const uint8_t *type, int b, int sch)
+{
+	if (sch) return kTypeSchFull;
+	const int t = type[b];
+	return t == kTypeSchFull ? 0x7f : t;
+}
 
 // Does burst (type, tsc, T) run attempt `round`?  Shared by both kernels so that they agree.
 // seq_len: length of the attempt's sync sequence (from the SeqInfo table the caller holds).
@@ -213,7 +226,7 @@ corr_nb_kernel(CorrParams p)
 		q.type = -1; q.tsc = 0; q.T = 0; q.rc = 0;
 		const int b = grp_ * kNbGroup + lane;
 		if (lane < kNbGroup && grp_ < ngroups && b < p.n) {
-			q.type = p.type[b]; q.tsc = p.tsc[b]; q.T = p.max_toa[b];
+			q.type = load_type(p.type, b, 0); q.tsc = p.tsc[b]; q.T = p.max_toa[b];
 			if (p.round > 0) q.rc = p.rc[b];
 		}
 		return q;
@@ -473,7 +486,8 @@ corr_long_kernel(CorrParams p)
 		Scal q;
 		q.type = -1; q.tsc = 0; q.T = 0; q.rc = 0;
 		if (b_ < p.n) {
-			q.type = p.type[b_]; q.tsc = p.tsc[b_]; q.T = p.max_toa[b_];
+			q.type = load_type(p.type, b_, p.sch);
+			if (!p.sch) { q.tsc = p.tsc[b_]; q.T = p.max_toa[b_]; }
 			if (p.round > 0) q.rc = p.rc[b_];
 		}
 		return q;
@@ -625,9 +639,8 @@ peak_kernel(PeakParams p)
 		const bool valid = b < p.n;
 		int type = 0, tsc = 0, T = 0, rc = 0;
 		if (valid) {
-			type = p.type[b];
-			tsc = p.tsc[b];
-			T = p.max_toa[b];
+			type = load_type(p.type, b, p.sch);
+			if (!p.sch) { tsc = p.tsc[b]; T = p.max_toa[b]; }
 			if (p.round > 0) rc = p.rc[b];
 		}
 		Attempt at;
@@ -798,7 +811,7 @@ peak_kernel(PeakParams p)
 				reinterpret_cast<float2 *>(p.amp)[b] = amp;
 				p.toa[b] = toa;
 				p.ci[b] = ci;
-				p.tsc_out[b] = (uint8_t)tsc_out;
+				if (p.tsc_out) p.tsc_out[b] = (uint8_t)tsc_out;
 			}
 			if (p.flags) {
 				if (p.round == 0) p.flags[b] = (uint8_t)flags;

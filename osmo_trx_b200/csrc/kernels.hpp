@@ -22,6 +22,7 @@ struct CorrParams {
 	// pull chain (corr_nb_kernel<true>): the windows are read from the int16 slots instead of `bursts`
 	const int16_t *iq; // [n][iq_stride] complex int16, or null
 	int iq_stride;
+	int sch;	   // every burst is a SCH_DETECT_FULL search (type / tsc / max_toa are not read)
 };
 
 struct PeakParams {
@@ -39,6 +40,7 @@ struct PeakParams {
 	float *amp, *toa, *ci;
 	uint8_t *tsc_out, *flags;
 	float negzero;
+	int sch; // every burst is a SCH_DETECT_FULL search (type / tsc / max_toa are not read)
 };
 
 struct DemodParams {

@@ -241,6 +241,19 @@ class _Base:
         rc = self.L[self.pfx + "synthesis_rotate"](h, _p(x), C.c_int(m), C.c_int(block_len), _p(out))
         return rc, out
 
+    # --- detectSCHBurst, SCH_DETECT_FULL ---
+    def detect_sch(self, bursts, thresh=4.0):
+        x = _f32(bursts)
+        n, stride = x.shape[0], x.shape[1]
+        r = dict(rc=np.zeros(n, np.int32), amp=np.zeros((n, 2), np.float32), toa=np.zeros(n, np.float32),
+                 ci=np.zeros(n, np.float32), flags=np.zeros(n, np.uint8))
+        args = [_p(x), C.c_int(stride), C.c_int(625), C.c_int(n), C.c_float(thresh), _p(r["rc"]), _p(r["amp"]),
+                _p(r["toa"]), _p(r["ci"])]
+        if self.has_flags:
+            args.append(_p(r["flags"]))
+        self.L[self.pfx + "detect_sch_batch"](*args)
+        return r
+
     # --- burst-type scheduler (Transceiver::expectedCorrType) ---
     def expected_corr_type(self, chan_type8, handover8, ext_rach, egprs, fn, tn):
         """chan_type8: ChannelCombination per timeslot of one channel (u8[8]); handover8: sub-slot bit mask per timeslot."""

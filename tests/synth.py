@@ -119,3 +119,15 @@ def multipath(wave, rng, taps_sigma=(0.3, 0.2, 0.1)):
     out[..., 0] = y.real
     out[..., 1] = y.imag
     return out
+
+
+SCH_SYNC_STR = "1011100101100010000001000000111100101101010001010111011000011011"
+
+
+def sch_bits(n, rng):
+    """Synchronisation bursts (3GPP TS 45.002 5.2.5): 3 tail, 39 data, 64-bit extended training sequence, 39 data, 3 tail."""
+    bits = np.zeros((n, 148), np.uint8)
+    bits[:, 3:42] = rng.integers(0, 2, (n, 39))
+    bits[:, 42:106] = [int(c) for c in SCH_SYNC_STR]
+    bits[:, 106:145] = rng.integers(0, 2, (n, 39))
+    return bits

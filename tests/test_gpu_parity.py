@@ -553,3 +553,23 @@ def test_wide_window_with_short_sequences(trx, checker):
     rep = parity.compare_detect(g, c, g["flags"], "wide16")
     parity.compare_soft(g["soft"], c["soft"], rep["ok_mask"] & (c["rc"] != EDGE), 156, "wide16")
     assert rep["detected"] > 1500
+
+
+def test_detect_sch_full(trx, checker):
+    """detectSCHBurst in its single-burst state (SCH_DETECT_FULL): 64-symbol sequence, 156 correlation outputs whose
+    window reaches before the burst (zeros).  Decisions exact, TOA / amp per the usual criteria."""
+    rng = np.random.default_rng(45)
+    n = 1200
+    w = checker.modulate_gmsk_batch(synth.sch_bits(n, rng))
+    rx, _ = synth.impair(w, rng, snr_db=np.choose(np.arange(n) % 3, [25.0, 10.0, 5.0]), noise_only_frac=0.1, shift_lo=-60, shift_hi=30)
+    c = checker.detect_sch(rx)
+    g = {k: v.cpu().numpy() for k, v in trx.detect_sch(dev(rx)).items()}
+    assert (c["rc"] > 0).sum() > 0.8 * n and (c["rc"] == 0).sum() > 50
+    c["tsc"] = np.zeros(n, np.uint8)
+    g["tsc"] = np.zeros(n, np.uint8)
+    rep = parity.compare_detect(g, c, g["flags"], "sch")
+    parity.compare_ci(g["ci"], c["ci"], rep["ok_mask"], "sch")
+    print("sch", {k: v for k, v in rep.items() if k not in ("ok_mask", "_ga")})
+    # an ordinary detect call cannot select the internal SCH type through its type array
+    r = run_gpu_dd(trx, rx[:64], 7, 0, 4, 4)
+    assert (r["rc"] <= 0).all()

@@ -165,6 +165,26 @@ def test_oracle_pull_vs_reference_live(oracle, ref):
             _pull_same(a, b, version)
 
 
+def test_oracle_sch_vs_fixture(oracle):
+    fx = np.load(os.path.join(GOLD, "sch_fixture.npz"))
+    a = oracle.detect_sch(fx["rx"].astype(np.float32))
+    assert (fx["rc"] > 0).any() and (fx["rc"] == 0).any()
+    for k in ("rc", "amp", "toa", "ci"):
+        assert eqb(a[k], fx[k]), k
+
+
+def test_oracle_sch_vs_reference_live(oracle, ref):
+    """detectSCHBurst(SCH_DETECT_FULL) restatement against the reference's own function, bit for bit."""
+    rng = np.random.default_rng(12)
+    n = 300
+    w = ref.modulate_gmsk_batch(synth.sch_bits(n, rng))
+    rx, _ = synth.impair(w, rng, snr_db=np.choose(np.arange(n) % 3, [25.0, 10.0, 5.0]), noise_only_frac=0.1, shift_lo=-60, shift_hi=30)
+    a, b = oracle.detect_sch(rx), ref.detect_sch(rx)
+    assert (b["rc"] > 0).sum() > 200 and (b["rc"] == 0).any()
+    for k in ("rc", "amp", "toa", "ci"):
+        assert eqb(a[k], b[k]), k
+
+
 def _sched_cases():
     fx = np.load(os.path.join(GOLD, "sched_fixture.npz"))
     for i in range(int(fx["n"])):
