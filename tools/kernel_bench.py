@@ -125,6 +125,13 @@ def main():
         del rx, res
     trx.detect_config(40, 3)
 
+    # ---- SCH search (8(f) row 4): 64-symbol sequence, 156 correlation outputs over the whole decimated burst ----
+    rx, typ, tsc, mt, bound = bench.make_workload(trx, "nb", n, seed=8, device=dev)
+    sch_ops = 219 * 62 + 156 * 64 * 8 + 9 * 2 * 21 * 4
+    add("detect_sch[full] corr+peak", "burst", n, 5000 + 24, timed(lambda: trx.detect_sch(rx), reps=5),
+        "detectSCHBurst(SCH_DETECT_FULL): 80 k complex taps per burst", ops=sch_ops)
+    del rx
+
     # ---- vitac (a42-a47) ----
     nv = n
     rx, typ, tsc, mt, bound = bench.make_workload(trx, "nb", nv, seed=9, device=dev)
