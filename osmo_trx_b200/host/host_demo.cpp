@@ -18,7 +18,7 @@ static void wr(FILE *f, const void *p, size_t n) { fwrite(p, 1, n, f); }
 
 int main(int argc, char **argv)
 {
-	if (argc != 4) { fprintf(stderr, "usage: host_demo dd|mod|conv|vit in out\n"); return 2; }
+	if (argc != 4) { fprintf(stderr, "usage: host_demo dd|sch|mod|conv|vit in out\n"); return 2; }
 	const std::string mode = argv[1];
 	FILE *fi = fopen(argv[2], "rb"), *fo = fopen(argv[3], "wb");
 	if (!fi || !fo) { perror("open"); return 2; }
@@ -47,6 +47,18 @@ int main(int argc, char **argv)
 			wr(fo, rec, sizeof(rec));
 			wr(fo, &nsoft, 4);
 			wr(fo, soft.data(), 444 * 4);
+		}
+	} else if (mode == "sch") {
+		// detectSCHBurst(burst, BURST_THRESH, 4, SCH_DETECT_FULL) per burst; the other states must be refused
+		for (int k = 0; k < n; k++) {
+			signalVector burst(625);
+			if (!rd(fi, burst.begin(), 625 * 8)) return 2;
+			estim_burst_params ebp;
+			ebp = estim_burst_params{ complex(0, 0), 0.0f, 0, 0.0f };
+			const int rc = detectSCHBurst(burst, BURST_THRESH, 4, sch_detect_type::SCH_DETECT_FULL, &ebp);
+			if (k == 0 && detectSCHBurst(burst, BURST_THRESH, 4, sch_detect_type::SCH_DETECT_BUFFER, &ebp) >= 0) return 5;
+			float rec[5] = { (float)rc, ebp.amp.real(), ebp.amp.imag(), ebp.toa, ebp.ci };
+			wr(fo, rec, sizeof(rec));
 		}
 	} else if (mode == "mod") {
 		for (int k = 0; k < n; k++) {

@@ -306,9 +306,27 @@ int detectAnyBurst(const signalVector &burst, unsigned tsc, float threshold, int
 	return r;
 }
 
-int detectSCHBurst(signalVector &, float, int, sch_detect_type, struct estim_burst_params *)
+// sigProcLib.cpp:1805-1861.  Only the single-burst state is built (trxb200_detect_sch_batch): the NARROW state reads past
+// its 8-sample decimated vector in the reference and the BUFFER state searches a 12-frame capture - both fail loudly here.
+int detectSCHBurst(signalVector &burst, float threshold, int sps, sch_detect_type state, struct estim_burst_params *ebp)
 {
-	return -SIGERR_UNSUPPORTED; // MS-side SCH search: SURVEY.md section 8(f) rank 4, not built yet
+	if (!ebp || sps != 4 || state != sch_detect_type::SCH_DETECT_FULL) return -1;
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g_ctx) return -1;
+	float *db = upload_burst(burst, d_in);
+	float *dres = (float *)d_b.get(64);
+	if (!db || !dres) return -1;
+	int32_t *drc = (int32_t *)dres;
+	float *damp = dres + 2, *dtoa = dres + 4, *dci = dres + 5;
+	if (!ok(trxb200_detect_sch_batch(g_ctx, db, 625, 1, threshold, drc, damp, dtoa, dci, nullptr), "detect_sch_batch")) return -1;
+	float hres[8];
+	if (!ok(trxb200_copy_to_host(g_ctx, hres, dres, 32), "copy")) return -1;
+	int32_t r;
+	memcpy(&r, &hres[0], 4);
+	ebp->amp = complex(hres[2], hres[3]);
+	ebp->toa = hres[4];
+	if (r > 0) ebp->ci = hres[5]; // the reference leaves ci untouched when nothing is found
+	return r;
 }
 
 SoftVector *demodAnyBurst(const signalVector &burst, CorrType type, int sps, struct estim_burst_params *ebp)

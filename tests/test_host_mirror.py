@@ -150,3 +150,19 @@ def test_mirror_vitac(host_build, checker, tmp_path):
     c = checker.vitac(buf, 40, tsc)
     assert np.array_equal(start, c["start"]) and np.array_equal(hard, c["bits"])
     assert np.allclose(cmax, c["corr_max"], rtol=1e-4, atol=0)
+
+
+@pytest.mark.gpu
+def test_mirror_detect_sch(host_build, checker, tmp_path):
+    """detectSCHBurst(SCH_DETECT_FULL) through the C++ mirror, per burst, against the CPU checker."""
+    rng = np.random.default_rng(79)
+    n = 64
+    w = checker.modulate_gmsk_batch(synth.sch_bits(n, rng))
+    rx, _ = synth.impair(w, rng, snr_db=12.0, noise_only_frac=0.15, shift_lo=-60, shift_hi=30)
+    pay = struct.pack("<i", n) + b"".join(rx[k].tobytes() for k in range(n))
+    rec = np.frombuffer(_run(host_build, "sch", pay, tmp_path), np.float32).reshape(n, 5)
+    c = checker.detect_sch(rx)
+    assert np.array_equal(rec[:, 0].astype(np.int32), c["rc"]) and (c["rc"] > 0).sum() > n // 2
+    assert np.array_equal(rec[:, 1:3], c["amp"]) and np.array_equal(rec[:, 3], c["toa"])
+    det = c["rc"] > 0
+    assert np.allclose(rec[det, 4], c["ci"][det], rtol=1e-4, atol=1e-3)
