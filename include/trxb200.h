@@ -250,7 +250,10 @@ int trxb200_convert_short_float(trxb200_ctx *ctx, float *out, const int16_t *in,
  *      -> clamp start to [clamp_lo, clamp_hi] (ms_upper.cpp:224-225 / Transceiver.cpp:631,635) ->
  *      detect_burst_nb / detect_burst_ab.  bufs: complex[n][stride]; the burst starts `offset`
  *      samples into each row so that negative starts stay addressable.  bits: i8[n][148 or 88]
- *      (+-127, pre-flipped, grgsm_vitac.cpp:101-102); cir may be NULL (else complex[n][20]). ---- */
+ *      (+-127, pre-flipped, grgsm_vitac.cpp:101-102); cir may be NULL (else complex[n][20]).
+ *      is_ab: 0 normal burst, 1 access burst, 2 SCH burst of a tracked cell (get_sch_chan_imp_resp :283-296 +
+ *      detect_burst_nb, ms_rx_lower.cpp:173-177; tsc unused, corr_max is the search's maximum although the reference's
+ *      function keeps it to itself). ---- */
 int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab,
 			const uint8_t *tsc, int max_delay, int clamp_lo, int clamp_hi, int8_t *bits,
 			int32_t *start, float *corr_max, float *cir);

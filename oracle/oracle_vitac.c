@@ -260,18 +260,27 @@ static void detect_burst(const ocf *in, const ocf *cir, int burst_start, int8_t 
 	free(fb); free(o);
 }
 
+/* get_sch_chan_imp_resp grgsm_vitac.cpp:283-296: the SCH burst of a tracked cell (search centre SYNC_POS + 5, ten symbols
+ * back, SYNC_SEARCH_RANGE = 30 forward, 54 of the 64 training symbols); corr_max is computed but not returned there */
+static int get_sch_cir(const ocf *in, ocf *cir, float *cm)
+{
+	const int c = (3 + 39) + TRAIN_BEGINNING; /* SYNC_POS + TRAIN_BEGINNING, constants.h:53 */
+	return get_cir(in, cir, (c - 10) * OSR, (c + 30) * OSR, &sch_seq[TRAIN_BEGINNING], N_SYNC_BITS - 2 * TRAIN_BEGINNING, cm) - c * OSR;
+}
+
 struct vjob { const float *bufs; int stride, offset, lo, hi, is_ab; const uint8_t *tsc; int max_delay, clo, chi;
 	      int8_t *bits; int32_t *start; float *cmax, *cir; };
 
 static void *vworker(void *arg)
 {
 	struct vjob *j = (struct vjob *)arg;
-	const int nbits = j->is_ab ? 88 : 148;
+	const int nbits = j->is_ab == 1 ? 88 : 148; /* is_ab: 0 normal burst, 1 access burst, 2 SCH burst (ms_rx_lower.cpp:173-177) */
 	for (int b = j->lo; b < j->hi; b++) {
 		const ocf *in = (const ocf *)(j->bufs + (size_t)b * j->stride * 2) + j->offset;
 		ocf cir[CIR_LEN * OSR];
 		float cm = 0;
-		int st = j->is_ab ? get_access_cir(in, cir, &cm, j->max_delay) : get_norm_cir(in, cir, &cm, j->tsc[b]);
+		int st = j->is_ab == 2 ? get_sch_cir(in, cir, &cm)
+				       : j->is_ab ? get_access_cir(in, cir, &cm, j->max_delay) : get_norm_cir(in, cir, &cm, j->tsc[b]);
 		if (st < j->clo) st = j->clo;
 		if (st > j->chi) st = j->chi;
 		detect_burst(in, cir, st, j->bits + (size_t)b * nbits, 3, nbits);

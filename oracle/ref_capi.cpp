@@ -530,18 +530,20 @@ int ref_vitac_batch(const float *bufs, int stride, int offset, int n, int is_ab,
 		    int clamp_lo, int clamp_hi, int8_t *bits, int32_t *start_out, float *corr_max, float *cir_out,
 		    int nthreads)
 {
-	const int nbits = is_ab ? 88 : 148;
+	const int nbits = is_ab == 1 ? 88 : 148; /* is_ab: 0 normal, 1 access, 2 SCH burst (ms_rx_lower.cpp:173-177) */
 	parallel_for(n, nthreads, [&](int b) {
 		const gr_complex *in = (const gr_complex *)(bufs + (size_t)b * stride * 2) + offset;
 		gr_complex cir[CHAN_IMP_RESP_LENGTH * 4];
 		float cmax = 0.0f;
 		int st;
-		if (is_ab)
+		if (is_ab == 2)
+			st = get_sch_chan_imp_resp(in, cir); /* keeps its corr_max to itself: reported as 0 */
+		else if (is_ab)
 			st = get_access_imp_resp(in, cir, &cmax, max_delay);
 		else
 			st = get_norm_chan_imp_resp(in, cir, &cmax, tsc[b]);
 		st = std::max(clamp_lo, std::min(clamp_hi, st));
-		if (is_ab)
+		if (is_ab == 1)
 			detect_burst_ab(in, cir, st, (sbit_t *)bits + (size_t)b * nbits);
 		else
 			detect_burst_nb(in, cir, st, (sbit_t *)bits + (size_t)b * nbits);

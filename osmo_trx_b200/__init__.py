@@ -355,9 +355,9 @@ class Trx:
 
     # -- vitac --
     def vitac(self, bufs, offset, tsc, is_ab=False, max_delay=0, clamp=(-39, 39), want_cir=False):
-        _chk_dev(bufs, tsc)
+        _chk_dev(bufs) if tsc is None else _chk_dev(bufs, tsc)
         n = bufs.shape[0]
-        nb = 88 if is_ab else 148
+        nb = 88 if int(is_ab) == 1 else 148  # is_ab: 0 normal, 1 access, 2 SCH burst (tsc unused)
         d = bufs.device
         r = dict(bits=torch.zeros((n, nb), dtype=torch.int8, device=d), start=torch.zeros(n, dtype=torch.int32, device=d),
                  corr_max=torch.zeros(n, dtype=torch.float32, device=d),

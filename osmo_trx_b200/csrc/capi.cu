@@ -188,6 +188,7 @@ void fill_const_tables(const HostTables &t, ConstTables &c)
 	for (int k = 0; k < 9; k++)
 		for (int i = 0; i < 26; i++) c.vitac_norm[k][i] = make_float2(t.vitac_norm[k][i].r, t.vitac_norm[k][i].i);
 	for (int i = 0; i < 41; i++) c.vitac_access[i] = make_float2(t.vitac_access[i].r, t.vitac_access[i].i);
+	for (int i = 0; i < 64; i++) c.vitac_sch[i] = make_float2(t.vitac_sch[i].r, t.vitac_sch[i].i);
 	for (int f = 0; f < kCompFilts; f++)
 		for (int e = 0; e < 2; e++)
 			for (int u = 0; u < 36; u++) {

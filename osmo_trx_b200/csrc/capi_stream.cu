@@ -23,12 +23,13 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 			int max_delay, int clamp_lo, int clamp_hi, int8_t *bits, int32_t *start, float *corr_max, float *cir)
 {
 	if (!ctx) return TRXB200_EINVAL;
-	if (!bufs || !bits || !start || !corr_max || n < 0 || max_delay < 0 || max_delay > 64 || (!is_ab && !tsc))
+	if (!bufs || !bits || !start || !corr_max || n < 0 || max_delay < 0 || max_delay > 64 || is_ab < 0 || is_ab > 2 || (!is_ab && !tsc))
 		return fail(ctx, TRXB200_EINVAL, "vitac: bad argument");
-	const int N = is_ab ? 88 : 148, center = is_ab ? 13 : 66;
-	const int s0 = (center - 5) * 4 + 1, s1 = (center + 10 + (is_ab ? max_delay : 0)) * 4;
+	const int N = is_ab == 1 ? 88 : 148, center = is_ab == 1 ? 13 : (is_ab == 2 ? 47 : 66);
+	const int s0 = is_ab == 2 ? (center - 10) * 4 : (center - 5) * 4 + 1;
+	const int s1 = is_ab == 2 ? (center + 30) * 4 : (center + 10 + (is_ab ? max_delay : 0)) * 4;
 	// every read must stay inside the row: [offset+clamp_lo, offset+clamp_hi+4N) and the search windows
-	const int tlen = is_ab ? 31 : 16;
+	const int tlen = is_ab == 1 ? 31 : (is_ab == 2 ? 54 : 16);
 	if (offset + clamp_lo < 0 || offset + clamp_hi + 4 * N > stride || offset + s1 - 1 + 4 * (tlen - 1) >= stride || clamp_lo > clamp_hi)
 		return fail(ctx, TRXB200_EINVAL, "vitac: row too short for the search window / clamp range");
 	if (n == 0) return TRXB200_OK;

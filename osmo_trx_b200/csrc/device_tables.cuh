@@ -37,6 +37,7 @@ struct ConstTables {
 	float delay[64][20];
 	float2 vitac_norm[9][26];
 	float2 vitac_access[41];
+	float2 vitac_sch[64];
 	float comp0[65][2][36]; // untruncated composite demod filters, shifted by e: comp0[f][e][u] = comp[f][0][u - e]
 };
 

@@ -75,12 +75,14 @@ vitac_kernel(VitacParams p)
 	unsigned *words = reinterpret_cast<unsigned *>(base + (per_warp - 8 - 320)); // [160][2]: gt, lt (16-byte aligned)
 	int *misc = reinterpret_cast<int *>(words + 320);
 
-	const int N = p.is_ab ? 88 : 148;
-	const int center = p.is_ab ? 13 : 66;
-	const int s0 = (center - 5) * kOSR + 1;
-	const int s1 = (center + 5 + 5 + (p.is_ab ? p.max_delay : 0)) * kOSR;
+	// is_ab: 0 normal burst (get_norm_chan_imp_resp), 1 access burst (get_access_imp_resp), 2 SCH burst
+	// (get_sch_chan_imp_resp :283-296: centre SYNC_POS + 5, ten symbols back, SYNC_SEARCH_RANGE forward, 54 symbols)
+	const int N = p.is_ab == 1 ? 88 : 148;
+	const int center = p.is_ab == 1 ? 13 : (p.is_ab == 2 ? 47 : 66);
+	const int s0 = p.is_ab == 2 ? (center - 10) * kOSR : (center - 5) * kOSR + 1;
+	const int s1 = p.is_ab == 2 ? (center + 30) * kOSR : (center + 5 + 5 + (p.is_ab ? p.max_delay : 0)) * kOSR;
 	const int nwin = s1 - s0;
-	const int tlen = p.is_ab ? 31 : 16;
+	const int tlen = p.is_ab == 1 ? 31 : (p.is_ab == 2 ? 54 : 16);
 	const float ftlen = (float)tlen;
 
 	const int npairs = (p.n + 1) >> 1;
@@ -94,7 +96,8 @@ vitac_kernel(VitacParams p)
 				continue;
 			}
 			const float2 *in = reinterpret_cast<const float2 *>(p.bufs) + (size_t)b * p.stride + p.offset + p.lo;
-			const float2 *tseq = p.is_ab ? &c_tab.vitac_access[5] : &c_tab.vitac_norm[p.tsc[b] > 8 ? 8 : p.tsc[b]][5];
+			const float2 *tseq = p.is_ab == 2 ? &c_tab.vitac_sch[5]
+						   : p.is_ab ? &c_tab.vitac_access[5] : &c_tab.vitac_norm[p.tsc[b] > 8 ? 8 : p.tsc[b]][5];
 			// ---- stage the row ----
 			for (int r0 = 0; r0 < p.range; r0 += 256) {
 				float2 v[8];

@@ -276,7 +276,7 @@ class _Base:
         bufs = _f32(bufs)
         n, stride = bufs.shape[0], bufs.shape[1]
         tsc = np.ascontiguousarray(np.broadcast_to(tsc, (n,)), np.uint8)
-        nb = 88 if is_ab else 148
+        nb = 88 if int(is_ab) == 1 else 148  # is_ab: 0 normal, 1 access, 2 SCH burst
         r = dict(bits=np.zeros((n, nb), np.int8), start=np.zeros(n, np.int32), corr_max=np.zeros(n, np.float32),
                  cir=np.zeros((n, 20, 2), np.float32))
         self.L[self.pfx + "vitac_batch"](_p(bufs), C.c_int(stride), C.c_int(offset), C.c_int(n), C.c_int(int(is_ab)),

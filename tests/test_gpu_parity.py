@@ -573,3 +573,24 @@ def test_detect_sch_full(trx, checker):
     # an ordinary detect call cannot select the internal SCH type through its type array
     r = run_gpu_dd(trx, rx[:64], 7, 0, 4, 4)
     assert (r["rc"] <= 0).all()
+
+
+def test_vitac_sch(trx, checker):
+    """SCH burst of a tracked cell through the MLSE: get_sch_chan_imp_resp (54-symbol search over 40 symbols) +
+    detect_burst_nb.  Start, CIR and every decision exact."""
+    rng = np.random.default_rng(47)
+    n = 1500
+    bits = synth.sch_bits(n, rng)
+    w = synth.multipath(checker.modulate_gmsk_batch(bits, nthreads=8), rng)
+    rx, _ = synth.impair(w, rng, snr_db=30.0, amp_range=(0.5, 1.0), shift_lo=-6, shift_hi=6)
+    buf = np.zeros((n, 40 + 625 + 63, 2), np.float32)
+    buf[:, 40:665] = rx
+    c = checker.vitac(buf, 40, 0, is_ab=2, nthreads=8)
+    g = trx.vitac(dev(buf), 40, None, is_ab=2, want_cir=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(g["start"].cpu().numpy(), c["start"])
+    assert np.array_equal(g["bits"].cpu().numpy(), c["bits"])
+    assert np.array_equal(g["cir"].cpu().numpy(), c["cir"])
+    ber = (((c["bits"] < 0).astype(np.uint8)) != bits).mean()
+    print("vitac SCH BER", ber, "start range", c["start"].min(), c["start"].max())
+    assert ber < 0.02

@@ -165,6 +165,20 @@ def test_oracle_pull_vs_reference_live(oracle, ref):
             _pull_same(a, b, version)
 
 
+def test_oracle_vitac_sch_vs_reference_live(oracle, ref):
+    """SCH burst through the MLSE (get_sch_chan_imp_resp + detect_burst_nb): start, CIR and all 148 decisions."""
+    rng = np.random.default_rng(13)
+    n = 200
+    bits = synth.sch_bits(n, rng)
+    w = synth.multipath(ref.modulate_gmsk_batch(bits), rng)
+    rx, _ = synth.impair(w, rng, snr_db=30.0, amp_range=(0.5, 1.0), shift_lo=-6, shift_hi=6)
+    buf = np.zeros((n, 40 + 625 + 63, 2), np.float32)
+    buf[:, 40:665] = rx
+    a, b = oracle.vitac(buf, 40, 0, is_ab=2), ref.vitac(buf, 40, 0, is_ab=2)
+    assert np.array_equal(a["start"], b["start"]) and np.array_equal(a["bits"], b["bits"]) and eqb(a["cir"], b["cir"])
+    assert (((b["bits"] < 0).astype(np.uint8)) != bits).mean() < 0.02
+
+
 def test_oracle_sch_vs_fixture(oracle):
     fx = np.load(os.path.join(GOLD, "sch_fixture.npz"))
     a = oracle.detect_sch(fx["rx"].astype(np.float32))
