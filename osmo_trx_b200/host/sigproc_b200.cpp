@@ -496,7 +496,7 @@ bool run_vitac(const gr_complex *input, int is_ab, int tsc, int max_delay, int l
 {
 	std::lock_guard<std::mutex> lk(g_mu);
 	if (!g_ctx) return false;
-	const int N = is_ab ? 88 : 148;
+	const int N = is_ab == 1 ? 88 : 148; // is_ab: 0 normal, 1 access, 2 SCH burst
 	float *drow = (float *)d_in.get((size_t)kVitRow * 8);
 	uint8_t *dt = (uint8_t *)d_a.get(16);
 	int8_t *dbits = (int8_t *)d_c.get(160);
@@ -540,10 +540,22 @@ int get_access_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp, floa
 	return start;
 }
 
+// grgsm_vitac.cpp:283-296; the reference's function keeps corr_max to itself
+int get_sch_chan_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp)
+{
+	int start = 0;
+	float cmax = 0.0f;
+	t_vit.input = input; t_vit.tsc = 0; t_vit.is_ab = 2; t_vit.max_delay = 0;
+	if (!run_vitac(input, 2, 0, 0, -kVitPad, 1 << 20, chan_imp_resp, &cmax, &start, nullptr)) return 0;
+	return start;
+}
+
 void detect_burst_nb(const gr_complex *input, gr_complex * /*chan_imp_resp: recomputed on the device*/, int burst_start, sbit_t *output_binary)
 {
-	const int tsc = t_vit.input == input && !t_vit.is_ab ? t_vit.tsc : 0;
-	if (!run_vitac(input, 0, tsc, 0, burst_start, burst_start, nullptr, nullptr, nullptr, output_binary))
+	const bool same = t_vit.input == input;
+	const int mode = same && t_vit.is_ab == 2 ? 2 : 0; // a SCH burst whose channel estimate was just asked for
+	const int tsc = same && !t_vit.is_ab ? t_vit.tsc : 0;
+	if (!run_vitac(input, mode, tsc, 0, burst_start, burst_start, nullptr, nullptr, nullptr, output_binary))
 		memset(output_binary, 0, 148);
 }
 
