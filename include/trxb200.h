@@ -258,6 +258,12 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 			const uint8_t *tsc, int max_delay, int clamp_lo, int clamp_hi, int8_t *bits,
 			int32_t *start, float *corr_max, float *cir);
 
+/* detect_burst_nb / detect_burst_ab (grgsm_vitac.cpp:105-123) on their own: the caller supplies the channel estimate
+ * (complex[n][20], e.g. from an earlier trxb200_vitac_batch) and the burst start per burst; matched filter + Viterbi
+ * only.  start_in is clamped to [clamp_lo, clamp_hi].  is_ab: 0 = 148 decisions, 1 = 88. */
+int trxb200_vitac_detect_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab,
+			       const float *cir_in, const int32_t *start_in, int clamp_lo, int clamp_hi, int8_t *bits);
+
 /* ---- Resampler (Resampler.h:31-61): rational p/q polyphase resampler, filt_len taps per path.
  *      rotate: in points at the first NEW input sample of each stream; `filt_len` samples of history
  *      precede it in memory (Resampler.cpp:131-150 reads before `in`).  n_streams independent streams

@@ -291,6 +291,18 @@ static void *vworker(void *arg)
 	return NULL;
 }
 
+/* detect_burst_nb / detect_burst_ab :105-123 with a given channel estimate and start (single-threaded helper) */
+int orc_vitac_detect_batch(const float *bufs, int stride, int offset, int n, int is_ab, const float *cir, const int32_t *start,
+			   int8_t *bits)
+{
+	vitac_setup();
+	const int nbits = is_ab ? 88 : 148;
+	for (int b = 0; b < n; b++)
+		detect_burst((const ocf *)(bufs + (size_t)b * stride * 2) + offset, (const ocf *)(cir + (size_t)b * 40), start[b],
+			     bits + (size_t)b * nbits, 3, nbits);
+	return n;
+}
+
 int orc_vitac_batch(const float *bufs, int stride, int offset, int n, int is_ab, const uint8_t *tsc, int max_delay,
 		    int clamp_lo, int clamp_hi, int8_t *bits, int32_t *start_out, float *corr_max, float *cir_out,
 		    int nthreads)

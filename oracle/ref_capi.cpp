@@ -526,6 +526,23 @@ int ref_synthesis_rotate(void *s_, const float *in, int m, int block_len, float 
 /* ---- grgsm_vitac (grgsm_vitac.h:65-82) ---- */
 /* bufs: [n][stride] complex, burst begins at sample `offset` inside each row (rows are zero padded so
  * negative starts are addressable, ms_upper.cpp:164-171). type: 0 NB (tsc per burst), 1 AB. */
+/* detect_burst_nb / detect_burst_ab grgsm_vitac.cpp:105-123 with a given channel estimate and start */
+int ref_vitac_detect_batch(const float *bufs, int stride, int offset, int n, int is_ab, const float *cir, const int32_t *start,
+			   int8_t *bits)
+{
+	const int nbits = is_ab ? 88 : 148;
+	for (int b = 0; b < n; b++) {
+		const gr_complex *in = (const gr_complex *)(bufs + (size_t)b * stride * 2) + offset;
+		gr_complex c[CHAN_IMP_RESP_LENGTH * 4];
+		memcpy(c, cir + (size_t)b * 40, sizeof(c));
+		if (is_ab)
+			detect_burst_ab(in, c, start[b], (sbit_t *)bits + (size_t)b * nbits);
+		else
+			detect_burst_nb(in, c, start[b], (sbit_t *)bits + (size_t)b * nbits);
+	}
+	return n;
+}
+
 int ref_vitac_batch(const float *bufs, int stride, int offset, int n, int is_ab, const uint8_t *tsc, int max_delay,
 		    int clamp_lo, int clamp_hi, int8_t *bits, int32_t *start_out, float *corr_max, float *cir_out,
 		    int nthreads)

@@ -370,6 +370,21 @@ class Trx:
         return r
 
 
+def _vitac_detect(self, bufs, offset, cir, start, is_ab=False, clamp=(-39, 39)):
+    """detect_burst_nb / detect_burst_ab with the caller's channel estimate: cir float32 [n, 20, 2], start int32 [n]."""
+    _chk_dev(bufs, cir, start)
+    n = bufs.shape[0]
+    bits = torch.zeros((n, 88 if is_ab else 148), dtype=torch.int8, device=bufs.device)
+    self.use_current_stream()
+    self._check(self.lib.trxb200_vitac_detect_batch(self.h, _ptr(bufs), C.c_int(bufs.stride(0) // 2), C.c_int(offset), C.c_int(n),
+                                                    C.c_int(int(is_ab)), _ptr(cir), _ptr(start), C.c_int(clamp[0]), C.c_int(clamp[1]),
+                                                    _ptr(bits)), "vitac_detect_batch")
+    return bits
+
+
+Trx.vitac_detect = _vitac_detect
+
+
 def build(force=False):
     """Compile libtrxb200.so in-tree (nvcc, sm_100a)."""
     return _build.build(force=force)

@@ -36,6 +36,7 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 	VitacParams p;
 	p.bufs = bufs; p.stride = stride; p.offset = offset; p.n = n; p.is_ab = is_ab; p.tsc = tsc; p.max_delay = max_delay;
 	p.clamp_lo = clamp_lo; p.clamp_hi = clamp_hi; p.bits = bits; p.start = start; p.corr_max = corr_max; p.cir = cir;
+	p.cir_in = nullptr; p.start_in = nullptr;
 	p.nwin_max = s1 - s0;
 	p.lo = std::min(clamp_lo, s0);
 	p.range = std::max(clamp_hi + 4 * N, s1 + 4 * (tlen - 1)) - p.lo;
@@ -43,6 +44,36 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 	const int wpb = 4;
 	const size_t smem = (size_t)wpb * vitac_warp_floats(p.nwin_max, p.pitch) * sizeof(float);
 	if (smem > 200 * 1024) return fail(ctx, TRXB200_EINVAL, "vitac: clamp range too wide for the on-chip window");
+	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int grid = std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
+	if (grid < 1) grid = 1;
+	vitac_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(p);
+	return post_launch(ctx, "vitac_kernel");
+}
+
+/* detect_burst_nb / detect_burst_ab (grgsm_vitac.cpp:105-123) with the CALLER's channel estimate and burst start: matched
+ * filter + Viterbi only.  start_in is clamped to [clamp_lo, clamp_hi], which also bounds what is read of each row. */
+int trxb200_vitac_detect_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab, const float *cir_in,
+			       const int32_t *start_in, int clamp_lo, int clamp_hi, int8_t *bits)
+{
+	if (!ctx) return TRXB200_EINVAL;
+	if (!bufs || !bits || !cir_in || !start_in || n < 0 || is_ab < 0 || is_ab > 1 || clamp_lo > clamp_hi)
+		return fail(ctx, TRXB200_EINVAL, "vitac_detect: bad argument");
+	const int N = is_ab ? 88 : 148;
+	if (offset + clamp_lo < 0 || offset + clamp_hi + 4 * N > stride)
+		return fail(ctx, TRXB200_EINVAL, "vitac_detect: row too short for the clamp range");
+	if (n == 0) return TRXB200_OK;
+	VitacParams p;
+	p.bufs = bufs; p.stride = stride; p.offset = offset; p.n = n; p.is_ab = is_ab; p.tsc = nullptr; p.max_delay = 0;
+	p.clamp_lo = clamp_lo; p.clamp_hi = clamp_hi; p.bits = bits; p.start = nullptr; p.corr_max = nullptr; p.cir = nullptr;
+	p.cir_in = cir_in; p.start_in = start_in;
+	p.nwin_max = 20; // cb only holds the 20 taps
+	p.lo = clamp_lo;
+	p.range = clamp_hi + 4 * N - clamp_lo;
+	p.pitch = vitac_pitch(p.range);
+	const int wpb = 4;
+	const size_t smem = (size_t)wpb * vitac_warp_floats(p.nwin_max, p.pitch) * sizeof(float);
+	if (smem > 200 * 1024) return fail(ctx, TRXB200_EINVAL, "vitac_detect: clamp range too wide for the on-chip window");
 	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int grid = std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
 	if (grid < 1) grid = 1;

@@ -27,6 +27,8 @@ struct VitacParams {
 	int32_t *start;
 	float *corr_max, *cir;
 	int nwin_max;
+	const float *cir_in;	  // complex[n][20] caller's channel estimates, or null: estimate here (get_*_imp_resp)
+	const int32_t *start_in; // burst start per burst when cir_in is given
 	int lo, range, pitch; // staged part of each row: samples [lo, lo + range) relative to the burst; plane pitch of the window
 };
 
@@ -97,7 +99,7 @@ vitac_kernel(VitacParams p)
 			}
 			const float2 *in = reinterpret_cast<const float2 *>(p.bufs) + (size_t)b * p.stride + p.offset + p.lo;
 			const float2 *tseq = p.is_ab == 2 ? &c_tab.vitac_sch[5]
-						   : p.is_ab ? &c_tab.vitac_access[5] : &c_tab.vitac_norm[p.tsc[b] > 8 ? 8 : p.tsc[b]][5];
+						   : p.is_ab ? &c_tab.vitac_access[5] : &c_tab.vitac_norm[p.tsc ? (p.tsc[b] > 8 ? 8 : p.tsc[b]) : 0][5];
 			// ---- stage the row ----
 			for (int r0 = 0; r0 < p.range; r0 += 256) {
 				float2 v[8];
@@ -114,6 +116,13 @@ vitac_kernel(VitacParams p)
 				}
 			}
 			__syncwarp();
+			int bi = 0, st = 0;
+			if (p.cir_in) {
+				// detect_burst_nb / detect_burst_ab with the caller's channel estimate (:105-123): no search
+				if (lane < kCirLen) cb[lane] = reinterpret_cast<const float2 *>(p.cir_in)[(size_t)b * kCirLen + lane];
+				st = max(p.clamp_lo, min(p.clamp_hi, p.start_in[b]));
+				__syncwarp();
+			} else {
 			// ---- correlation per search window (correlate_sequence :148-156) ----
 			for (int w = lane; w < nwin; w += 32) {
 				const int r = s0 + w - p.lo;
@@ -144,8 +153,8 @@ vitac_kernel(VitacParams p)
 				misc[h] = bi;
 			}
 			__syncwarp();
-			const int bi = misc[h];
-			int st = s0 + bi - center * kOSR;
+			bi = misc[h];
+			st = s0 + bi - center * kOSR;
 			st = max(p.clamp_lo, min(p.clamp_hi, st));
 			// corr_max + CIR export
 			{
@@ -155,6 +164,7 @@ vitac_kernel(VitacParams p)
 				if (lane == 0) { p.corr_max[b] = a; p.start[b] = st; }
 				if (p.cir && lane < kCirLen)
 					reinterpret_cast<float2 *>(p.cir)[(size_t)b * kCirLen + lane] = cb[bi + lane];
+			}
 			}
 			const float2 *cir = cb + bi;
 			// ---- rhh[k] = conj(autocorr(cir)[4k]) (:159-166,93-95); increments viterbi_detector.cc:93-100 ----

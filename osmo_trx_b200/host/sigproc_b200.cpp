@@ -488,7 +488,6 @@ bool Synthesis::rotate(float *out, size_t oLen)
 /* ---------------- grgsm_vitac ---------------- */
 namespace {
 constexpr int kVitPad = 40, kVitRow = kVitPad + 1024 + kVitPad, kVitAvail = 625;
-thread_local struct { const gr_complex *input = nullptr; int tsc = 0, is_ab = 0, max_delay = 0; } t_vit;
 
 // one GPU call: CIR search (+ detection with the start clamped to [lo, hi])
 bool run_vitac(const gr_complex *input, int is_ab, int tsc, int max_delay, int lo, int hi, gr_complex *cir, float *corr_max, int *start,
@@ -527,7 +526,6 @@ void initvita() {} // the reference symbol tables live in the GPU context (built
 int get_norm_chan_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp, float *corr_max, int bcc)
 {
 	int start = 0;
-	t_vit.input = input; t_vit.tsc = bcc; t_vit.is_ab = 0; t_vit.max_delay = 0;
 	if (!run_vitac(input, 0, bcc, 0, -kVitPad, 1 << 20, chan_imp_resp, corr_max, &start, nullptr)) return 0;
 	return start;
 }
@@ -535,7 +533,6 @@ int get_norm_chan_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp, f
 int get_access_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp, float *corr_max, int max_delay)
 {
 	int start = 0;
-	t_vit.input = input; t_vit.tsc = 0; t_vit.is_ab = 1; t_vit.max_delay = max_delay;
 	if (!run_vitac(input, 1, 0, max_delay, -kVitPad, 1 << 20, chan_imp_resp, corr_max, &start, nullptr)) return 0;
 	return start;
 }
@@ -545,23 +542,43 @@ int get_sch_chan_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp)
 {
 	int start = 0;
 	float cmax = 0.0f;
-	t_vit.input = input; t_vit.tsc = 0; t_vit.is_ab = 2; t_vit.max_delay = 0;
 	if (!run_vitac(input, 2, 0, 0, -kVitPad, 1 << 20, chan_imp_resp, &cmax, &start, nullptr)) return 0;
 	return start;
 }
 
-void detect_burst_nb(const gr_complex *input, gr_complex * /*chan_imp_resp: recomputed on the device*/, int burst_start, sbit_t *output_binary)
+// detect_burst_nb / detect_burst_ab (grgsm_vitac.cpp:105-123): matched filter + Viterbi with the CALLER's channel estimate
+// and start, whatever pointer arithmetic the caller did between the estimate and this call (ms_rx_lower.cpp:177 passes
+// &ss[start] with start 0)
+static bool run_vitac_detect(const gr_complex *input, int is_ab, const gr_complex *cir, int burst_start, sbit_t *bits)
 {
-	const bool same = t_vit.input == input;
-	const int mode = same && t_vit.is_ab == 2 ? 2 : 0; // a SCH burst whose channel estimate was just asked for
-	const int tsc = same && !t_vit.is_ab ? t_vit.tsc : 0;
-	if (!run_vitac(input, mode, tsc, 0, burst_start, burst_start, nullptr, nullptr, nullptr, output_binary))
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g_ctx || !cir) return false;
+	const int N = is_ab ? 88 : 148;
+	float *drow = (float *)d_in.get((size_t)kVitRow * 8);
+	float *dcir = (float *)d_b.get(8 + 20 * 8);
+	int32_t *dstart = (int32_t *)d_a.get(16);
+	int8_t *dbits = (int8_t *)d_c.get(160);
+	if (!drow || !dcir || !dstart || !dbits) return false;
+	if (trxb200_memset_device(g_ctx, drow, 0, (size_t)kVitRow * 8) != TRXB200_OK) return false;
+	if (trxb200_copy_to_device(g_ctx, drow + 2 * kVitPad, input, (size_t)kVitAvail * 8) != TRXB200_OK) return false;
+	if (trxb200_copy_to_device(g_ctx, dcir, cir, 20 * 8) != TRXB200_OK) return false;
+	int st = burst_start < -kVitPad ? -kVitPad : burst_start;
+	if (st > kVitRow - kVitPad - 4 * N) st = kVitRow - kVitPad - 4 * N;
+	const int32_t st32 = st;
+	if (trxb200_copy_to_device(g_ctx, dstart, &st32, 4) != TRXB200_OK) return false;
+	if (!ok(trxb200_vitac_detect_batch(g_ctx, drow, kVitRow, kVitPad, 1, is_ab, dcir, dstart, st, st, dbits), "vitac_detect_batch"))
+		return false;
+	return trxb200_copy_to_host(g_ctx, bits, dbits, (size_t)N) == TRXB200_OK;
+}
+
+void detect_burst_nb(const gr_complex *input, gr_complex *chan_imp_resp, int burst_start, sbit_t *output_binary)
+{
+	if (!run_vitac_detect(input, 0, chan_imp_resp, burst_start, output_binary))
 		memset(output_binary, 0, 148);
 }
 
-void detect_burst_ab(const gr_complex *input, gr_complex *, int burst_start, sbit_t *output_binary)
+void detect_burst_ab(const gr_complex *input, gr_complex *chan_imp_resp, int burst_start, sbit_t *output_binary)
 {
-	const int md = t_vit.input == input && t_vit.is_ab ? t_vit.max_delay : 0;
-	if (!run_vitac(input, 1, 0, md, burst_start, burst_start, nullptr, nullptr, nullptr, output_binary))
+	if (!run_vitac_detect(input, 1, chan_imp_resp, burst_start, output_binary))
 		memset(output_binary, 0, 88);
 }

@@ -285,6 +285,18 @@ class _Base:
                                            C.c_int(nthreads))
         return r
 
+    def vitac_detect(self, bufs, offset, cir, start, is_ab=False):
+        """detect_burst_nb / detect_burst_ab with a given channel estimate (cir [n,20,2]) and start per burst."""
+        bufs = _f32(bufs)
+        cir = _f32(cir)
+        n, stride = bufs.shape[0], bufs.shape[1]
+        start = np.ascontiguousarray(start, np.int32)
+        nb = 88 if is_ab else 148
+        bits = np.zeros((n, nb), np.int8)
+        self.L[self.pfx + "vitac_detect_batch"](_p(bufs), C.c_int(stride), C.c_int(offset), C.c_int(n), C.c_int(int(is_ab)), _p(cir),
+                                                  _p(start), _p(bits))
+        return bits
+
     def viterbi(self, x, rhh, start_state=3):
         x = _f32(x)
         rhh = _f32(rhh)

@@ -594,3 +594,32 @@ def test_vitac_sch(trx, checker):
     ber = (((c["bits"] < 0).astype(np.uint8)) != bits).mean()
     print("vitac SCH BER", ber, "start range", c["start"].min(), c["start"].max())
     assert ber < 0.02
+
+
+def test_vitac_detect_with_given_cir(trx, checker):
+    """detect_burst_nb / detect_burst_ab on their own: channel estimate and start supplied by the caller (here: the
+    estimate of one call, the start moved by a sample for half of the bursts), every decision exact."""
+    rng = np.random.default_rng(48)
+    n = 800
+    tsc = (np.arange(n) % 8).astype(np.uint8)
+    bits = synth.nb_bits(n, tsc, rng)
+    w = synth.multipath(checker.modulate_gmsk_batch(bits, nthreads=8), rng)
+    rx, _ = synth.impair(w, rng, snr_db=30.0, amp_range=(0.5, 1.0), shift_lo=-4, shift_hi=4)
+    buf = np.zeros((n, 40 + 625 + 63, 2), np.float32)
+    buf[:, 40:665] = rx
+    est = checker.vitac(buf, 40, tsc, nthreads=8)
+    start = est["start"] + (np.arange(n) % 2).astype(np.int32)
+    want = checker.vitac_detect(buf, 40, est["cir"], start)
+    got = trx.vitac_detect(dev(buf), 40, dev(est["cir"]), dev(start)).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(want[::2], est["bits"][::2])  # unchanged start: the one-call result
+    # access bursts
+    ab = synth.ab_bits(300, 5, rng, 0)
+    wa = checker.modulate_gmsk_batch(ab, nthreads=8)
+    rxa, _ = synth.impair(wa, rng, snr_db=25.0, amp_range=(0.5, 1.0), shift_lo=-2, shift_hi=2)
+    bufa = np.zeros((300, 40 + 625 + 63, 2), np.float32)
+    bufa[:, 40:665] = rxa
+    ea = checker.vitac(bufa, 40, 0, is_ab=True, max_delay=20, nthreads=8)
+    wa2 = checker.vitac_detect(bufa, 40, ea["cir"], ea["start"], is_ab=True)
+    ga2 = trx.vitac_detect(dev(bufa), 40, dev(ea["cir"]), dev(ea["start"]), is_ab=True).cpu().numpy()
+    assert np.array_equal(ga2, wa2) and np.array_equal(wa2, ea["bits"])
