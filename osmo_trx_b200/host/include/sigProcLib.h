@@ -49,7 +49,7 @@ float energyDetect(const signalVector &rxBurst, unsigned windowLength);						   
 int detectAnyBurst(const signalVector &burst, unsigned tsc, float threshold, int sps, CorrType type, unsigned max_toa,
 		   struct estim_burst_params *ebp);								     // :1926
 int detectSCHBurst(signalVector &rxBurst, float detectThreshold, int sps, sch_detect_type state,
-		   struct estim_burst_params *ebp);								     // :1805 (-SIGERR_UNSUPPORTED here)
+		   struct estim_burst_params *ebp);								     // :1805 (SCH_DETECT_FULL; other states return -1)
 SoftVector *demodAnyBurst(const signalVector &burst, CorrType type, int sps, struct estim_burst_params *ebp);	     // :2130
 
 // ---- batched helpers (this repository's extension): N bursts per call, host vectors in and out ----
