@@ -95,6 +95,7 @@ vitac_kernel(VitacParams p)
 			if (b >= p.n) {
 				for (int i = lane; i < 160; i += 32) filt[h * 160 + i] = 0.0f;
 				if (lane < 8) inc[h * 8 + lane] = 0.0f;
+				__syncwarp(); // the ACS stage reads these
 				continue;
 			}
 			const float2 *in = reinterpret_cast<const float2 *>(p.bufs) + (size_t)b * p.stride + p.offset + p.lo;
