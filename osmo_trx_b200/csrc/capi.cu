@@ -569,7 +569,10 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	else chunk *= std::max<long>(1, cap / chunk);
 	if (chunk > n) chunk = n;
 	// ---- scratch ----
-	const size_t need_c = (size_t)chunk * lmax * sizeof(float2), need_p = (size_t)chunk * ndmax * sizeof(float);
+	// a short remainder (< chunk / 4) rides along with the last full chunk instead of paying two more launches
+	const long rem = n % chunk;
+	const long max_m = (rem > 0 && rem < chunk / 4 && n > chunk) ? chunk + rem : chunk;
+	const size_t need_c = (size_t)max_m * lmax * sizeof(float2), need_p = (size_t)max_m * ndmax * sizeof(float);
 	if (ws.corr_bytes < need_c) {
 		CK(cudaStreamSynchronize(st));
 		cudaFree(ws.corr);
@@ -585,8 +588,12 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 		ws.pwr_bytes = need_p;
 	}
 	const int rounds = sch ? 1 : ctx->max_attempts;
-	for (long lo = 0; lo < n; lo += chunk) {
-		const int m = (int)std::min<long>(chunk, n - lo);
+	long step_m = 0;
+	for (long lo = 0; lo < n; lo += step_m) {
+		long mm = std::min<long>(chunk, n - lo);
+		if (n - lo - mm > 0 && n - lo - mm < chunk / 4) mm = n - lo;
+		step_m = mm;
+		const int m = (int)mm;
 		for (int r = 0; r < rounds; r++) {
 			CorrParams c;
 			c.bursts = bursts ? bursts + (size_t)lo * stride * 2 : nullptr; c.stride = stride; c.n = m;
