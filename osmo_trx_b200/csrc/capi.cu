@@ -76,6 +76,7 @@ struct trxb200_ctx {
 		// slower than the serial order (1.75-2.4 ms vs 1.71 ms per 2^20 bursts) - corr_nb_kernel and demod_kernel each
 		// need the whole register file of an SM to hide their latencies - so the pipeline is off unless asked for
 		int overlap = 0, chunk_cap = 131072;
+		int host_chunk = 16384; // slots per stage of the pinned-host pipelines (H2D | kernels | D2H on three streams)
 		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
 		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
 		int ov_corr_bps = 1, ov_peak_bps = 1, ov_peak_warps = 8, ov_demod_bps = 1; // while overlapping: leave room for the other kernel
@@ -299,6 +300,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_OVERLAP", t.overlap);
 		env_int("TRXB200_CHUNK", t.chunk_cap);
 		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
+		env_int("TRXB200_HOST_CHUNK", t.host_chunk);
 		env_int("TRXB200_CORR_BPS", t.corr_bps);
 		env_int("TRXB200_PEAK_BPS", t.peak_bps);
 		env_int("TRXB200_PEAK_WARPS", t.peak_warps);
@@ -309,6 +311,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_OV_DEMOD_BPS", t.ov_demod_bps);
 		if (t.chunk_cap < 4096) t.chunk_cap = 4096;
 		if (t.pull_chunk < 1024) t.pull_chunk = 1024;
+		if (t.host_chunk < 1024) t.host_chunk = 1024;
 	}
 	ctx->stream = ctx->own_stream;
 	*out = ctx;
@@ -780,7 +783,7 @@ static void stage_free(HostStage *s)
 
 static int stage_get(trxb200_ctx *ctx, int stride, int soft_stride, HostStage **out)
 {
-	const int chunk = 16384;
+	const int chunk = ctx->tune.host_chunk;
 	HostStage *s = ctx->stage;
 	if (s && (s->stride != stride || s->soft_stride != soft_stride)) {
 		stage_free(s);
@@ -1033,7 +1036,7 @@ int trxb200_pull_host(trxb200_ctx *ctx, const trxb200_pull_args *a)
 	int r = pull_check(ctx, a);
 	if (r || a->n == 0) return r;
 	CK(cudaSetDevice(ctx->device));
-	const int chunk = 16384;
+	const int chunk = ctx->tune.host_chunk;
 	PullStage *s = ctx->pull_stage;
 	if (s && (s->stride != a->stride || s->pkt_stride != a->pkt_stride)) {
 		pull_stage_free(s);
