@@ -122,12 +122,18 @@ header_kernel(HeaderParams p)
 		const int b0 = tile * 32;
 		const int nb = min(32, p.n - b0);
 		__syncwarp();
+		// the tile's 32 rows by asynchronous 4-byte copies: all 96 per lane are in flight together (one round trip)
 		for (int j = 0; j < nb; j++) {
 			const float *row = p.pw + (size_t)(b0 + j) * 80;
 #pragma unroll
 			for (int k = 0; k < 3; k++)
-				if (lane + 32 * k < 80) pwt[warp][j][lane + 32 * k] = row[lane + 32 * k];
+				if (lane + 32 * k < 80)
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&pwt[warp][j][lane + 32 * k])),
+						     "l"(row + lane + 32 * k)
+						     : "memory");
 		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncwarp();
 		const int b = b0 + lane;
 		if (b >= p.n) continue;
