@@ -658,6 +658,19 @@ peak_kernel(PeakParams p)
 				// vector in one round trip (rows are lmax long, so a pair that starts inside the row ends inside it)
 				for (int i0 = 0; i0 < len; i0 += 20) {
 					float4 v[10];
+					if (len > 20 && i0 + 40 <= ((len + 1) & ~1)) {
+						// long vectors (access bursts): forty samples per round trip
+						float4 u[20];
+#pragma unroll
+						for (int k = 0; k < 20; k++) u[k] = __ldg(reinterpret_cast<const float4 *>(src + i0 + 2 * k));
+#pragma unroll
+						for (int k = 0; k < 20; k++) {
+							dst[(i0 + 2 * k) * kRowPitch] = make_float2(u[k].x, u[k].y);
+							if (i0 + 2 * k + 1 < len) dst[(i0 + 2 * k + 1) * kRowPitch] = make_float2(u[k].z, u[k].w);
+						}
+						i0 += 20;
+						continue;
+					}
 #pragma unroll
 					for (int k = 0; k < 10; k++) {
 						v[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
