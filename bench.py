@@ -461,7 +461,22 @@ def main():
                "api": "trxb200_pull_host: int16 I/Q slots in (pinned host), TRXD v1 datagrams out (pinned host)",
                "host_cores_bound_near_gpu": near,
                "sent_fraction": float((h_pout["pkt_len"] > 11).float().mean().item()), "gpu_launches": int(e2e_launches)}
-        del h_iq, h_pout
+        # the same chain with the slots already resident in HBM (CUDA events): what the link, not the GPU, costs
+        d_iq = h_iq.to(device)
+        d_fn, d_tn = h_fn.to(device), h_tn.to(device)
+        d_pout = trx.alloc_pull_results(ne, pstride)
+        for _ in range(3):
+            trx.pull(d_iq, typ[:ne], tsc[:ne], max_toa[:ne], d_fn, d_tn, bound, out=d_pout, full_scale=RX_FULL_SCALE)
+        pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        pa.record()
+        for _ in range(10):
+            trx.pull(d_iq, typ[:ne], tsc[:ne], max_toa[:ne], d_fn, d_tn, bound, out=d_pout, full_scale=RX_FULL_SCALE)
+        pb.record()
+        torch.cuda.synchronize()
+        e2e["device_resident"] = {"value": ne * 10 / (pa.elapsed_time(pb) * 1e-3), "unit": "bursts/s per GPU",
+                                  "what": "trxb200_pull_batch on the same slots resident in HBM (no PCIe): the e2e figure is bound by the host link"}
+        del h_iq, h_pout, d_iq, d_pout
     if not args.no_e2e:
         # (b) the strict float boundary (signalVector in, SoftVector out), PCIe-bound at 5 KB per burst
         ne = min(args.e2e_bursts, n)
