@@ -67,7 +67,13 @@ int trxb200_abi_version(void);
 const char *trxb200_last_error(trxb200_ctx *ctx);
 /* A new context launches on its own non-blocking stream.  trxb200_set_stream() makes all subsequent
  * calls use the given cudaStream_t instead (NULL = the CUDA default stream); trxb200_use_own_stream()
- * switches back. */
+ * switches back.
+ * One context = one unit of device scratch (correlation intermediates, pull scratch, filterbank history), so the work
+ * of a context never overlaps itself: switching streams orders the new stream behind everything the context enqueued
+ * on the previous one (event record + wait, no host synchronisation).  Pipelines that want two batches in flight at
+ * once use two contexts.  A context is bound to the device it was created on; every entry point selects that device
+ * for the duration of the call and restores the caller's current device.  A context is not thread-safe: one caller
+ * thread at a time (the reference's per-channel RX/TX threads each own one, Transceiver.cpp:308-322). */
 int trxb200_set_stream(trxb200_ctx *ctx, void *cuda_stream);
 int trxb200_use_own_stream(trxb200_ctx *ctx);
 void *trxb200_get_stream(trxb200_ctx *ctx);
@@ -144,8 +150,11 @@ int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride
 			       int32_t *rc, float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags,
 			       float *soft, int soft_stride, int n_gmsk_soft);
 
-/* same, HOST buffers: chunks the batch, overlaps H2D / kernels / D2H on internal streams and pinned
- * staging, returns after everything has landed in the host outputs (this is the e2e path). */
+/* same, HOST buffers: chunks the batch and overlaps H2D / kernels / D2H on three internal streams; returns after
+ * everything has landed in the host outputs.  Per chunk one copy of the samples and one of the packed per-burst
+ * inputs go down, one copy of the soft rows and one of the packed per-burst results come back.  Page-locked caller
+ * buffers (cudaHostAlloc / cudaHostRegister) are read and written in place; pageable ones are staged through internal
+ * pinned buffers (one extra host memcpy per chunk) so that the copies stay asynchronous either way. */
 int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride, int n, const uint8_t *type,
 			      const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh,
 			      int32_t *rc, float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags,
@@ -195,7 +204,9 @@ typedef struct trxb200_pull_args {
 #define TRXB200_TRXD_V0_HDR 8
 /* DEVICE pointers; enqueues on the context's stream */
 int trxb200_pull_batch(trxb200_ctx *ctx, const trxb200_pull_args *args);
-/* HOST pointers; H2D / kernels / D2H pipelined over internal streams (pinned buffers recommended) */
+/* HOST pointers; H2D / kernels / D2H pipelined over three internal streams, two copies down and two back per chunk
+ * (slots + packed per-slot inputs; datagram rows + packed per-slot results); pageable caller memory is staged through
+ * internal pinned buffers, page-locked memory is used in place (this is the e2e path of bench.py) */
 int trxb200_pull_host(trxb200_ctx *ctx, const trxb200_pull_args *args);
 
 /* ---- burst-type scheduler: Transceiver::expectedCorrType (Transceiver.cpp:513-601) and the search window

@@ -69,6 +69,7 @@ struct trxb200_ctx {
 	// detect -> demod pipelining inside trxb200_detect_demod_batch: the demodulation of chunk i runs on a side
 	// stream while chunk i+1 is being detected (FP32-bound correlator / peak search beside the HBM-bound demod)
 	cudaStream_t side_stream = nullptr;
+	cudaEvent_t order_ev = nullptr; // orders a newly selected stream behind the work of the previous one (trxb200_set_stream)
 	cudaEvent_t pipe_ev[4] = {};
 	int pipe_ev_next = 0;
 	struct Tune { // launch geometry; environment overrides (TRXB200_*) are read once in trxb200_init
@@ -93,17 +94,19 @@ struct trxb200_ctx {
 	std::vector<ProfRec> prof_recs;
 };
 
+// Host-buffer pipelines (trxb200_detect_demod_host / trxb200_pull_host): per chunk ONE host->device copy of the samples,
+// ONE of the small per-slot inputs (packed struct-of-arrays in a pinned block), and on the way back ONE copy of the bulk
+// result rows and ONE of the small per-slot results (packed, scattered to the caller's arrays by the host once landed).
+// Caller memory that is not page-locked is staged through internal pinned buffers, so the copies stay asynchronous.
 struct HostStage {
 	static constexpr int kSlots = 3;
 	int chunk = 0, stride = 0, soft_stride = 0;
 	cudaStream_t streams[kSlots] = {};
-	cudaEvent_t done[kSlots] = {};
-	// device buffers per slot
-	float *d_bursts[kSlots] = {};
-	uint8_t *d_type[kSlots] = {}, *d_tsc[kSlots] = {}, *d_tsc_out[kSlots] = {}, *d_flags[kSlots] = {};
-	uint16_t *d_max_toa[kSlots] = {};
-	int32_t *d_rc[kSlots] = {};
-	float *d_amp[kSlots] = {}, *d_toa[kSlots] = {}, *d_ci[kSlots] = {}, *d_soft[kSlots] = {};
+	float *d_bursts[kSlots] = {}, *d_soft[kSlots] = {};
+	uint8_t *d_in[kSlots] = {}, *d_out[kSlots] = {}; // packed small arrays (device)
+	uint8_t *h_in[kSlots] = {}, *h_out[kSlots] = {}; // their pinned mirrors
+	float *h_bursts[kSlots] = {}, *h_soft[kSlots] = {}; // pinned staging, allocated only for pageable callers
+	int pend_lo[kSlots] = {}, pend_m[kSlots] = {};
 	DetectScratch ws[kSlots];
 };
 
@@ -126,6 +129,23 @@ int fail(trxb200_ctx *ctx, int code, const char *what, cudaError_t e = cudaSucce
 		cudaError_t e_ = (call);                                          \
 		if (e_ != cudaSuccess) return fail(ctx, TRXB200_ECUDA, #call, e_); \
 	} while (0)
+
+// Every entry point that launches, allocates or copies runs on the context's device whatever the caller's current
+// device is, and leaves the caller's device as it found it.
+struct DevGuard {
+	int prev = -1, dev;
+	explicit DevGuard(int d) : dev(d)
+	{
+		if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+		if (dev >= 0 && prev != dev) cudaSetDevice(dev);
+	}
+	~DevGuard()
+	{
+		if (dev >= 0 && prev >= 0 && prev != dev) cudaSetDevice(prev);
+	}
+	DevGuard(const DevGuard &) = delete;
+	DevGuard &operator=(const DevGuard &) = delete;
+};
 
 int post_launch(trxb200_ctx *ctx, const char *name)
 {
@@ -291,6 +311,10 @@ int trxb200_init(int device, trxb200_ctx **out)
 			trxb200_destroy(ctx);
 			return TRXB200_ECUDA;
 		}
+	if (cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming) != cudaSuccess) {
+		trxb200_destroy(ctx);
+		return TRXB200_ECUDA;
+	}
 	{
 		auto env_int = [](const char *name, int &v) {
 			const char *e = getenv(name);
@@ -340,27 +364,39 @@ void trxb200_destroy(trxb200_ctx *ctx)
 	if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
 	for (auto ev : ctx->pipe_ev)
 		if (ev) cudaEventDestroy(ev);
+	if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);
 	delete ctx->ht;
 	delete ctx;
 }
 
 const char *trxb200_last_error(trxb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+// The context owns ONE set of device scratch (correlation intermediates, pull scratch, filterbank history): work
+// enqueued through it must not overlap itself.  Switching streams therefore orders the new stream behind everything the
+// context enqueued on the previous one (event record + wait, no host synchronisation).
+static int switch_stream(trxb200_ctx *ctx, cudaStream_t ns)
+{
+	if (ns == ctx->stream) return TRXB200_OK;
+	DevGuard dg(ctx->device);
+	CK(cudaEventRecord(ctx->order_ev, ctx->stream));
+	CK(cudaStreamWaitEvent(ns, ctx->order_ev, 0));
+	ctx->stream = ns;
+	return TRXB200_OK;
+}
 int trxb200_set_stream(trxb200_ctx *ctx, void *s)
 {
 	if (!ctx) return TRXB200_EINVAL;
-	ctx->stream = (cudaStream_t)s; // NULL is the CUDA default stream, exactly as passed
-	return TRXB200_OK;
+	return switch_stream(ctx, (cudaStream_t)s); // NULL is the CUDA default stream, exactly as passed
 }
 int trxb200_use_own_stream(trxb200_ctx *ctx)
 {
 	if (!ctx) return TRXB200_EINVAL;
-	ctx->stream = ctx->own_stream;
-	return TRXB200_OK;
+	return switch_stream(ctx, ctx->own_stream);
 }
 void *trxb200_get_stream(trxb200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int trxb200_sync(trxb200_ctx *ctx)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx) return TRXB200_EINVAL;
 	CK(cudaStreamSynchronize(ctx->stream));
 	return TRXB200_OK;
@@ -372,6 +408,7 @@ uint64_t trxb200_launch_count(trxb200_ctx *ctx) { return ctx ? ctx->launches : 0
 /* ---------------- device memory helpers for bindings that have no CUDA runtime of their own ---------------- */
 int trxb200_dev_alloc(trxb200_ctx *ctx, size_t bytes, void **out)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !out) return TRXB200_EINVAL;
 	*out = nullptr;
 	CK(cudaSetDevice(ctx->device));
@@ -381,18 +418,21 @@ int trxb200_dev_alloc(trxb200_ctx *ctx, size_t bytes, void **out)
 }
 int trxb200_dev_free(trxb200_ctx *ctx, void *p)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx) return TRXB200_EINVAL;
 	if (p) CK(cudaFree(p));
 	return TRXB200_OK;
 }
 int trxb200_copy_to_device(trxb200_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || (bytes && (!dst || !src))) return TRXB200_EINVAL;
 	if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	return TRXB200_OK;
 }
 int trxb200_copy_to_host(trxb200_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || (bytes && (!dst || !src))) return TRXB200_EINVAL;
 	if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
@@ -400,6 +440,7 @@ int trxb200_copy_to_host(trxb200_ctx *ctx, void *dst, const void *src, size_t by
 }
 int trxb200_memset_device(trxb200_ctx *ctx, void *dst, int value, size_t bytes)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || (bytes && !dst)) return TRXB200_EINVAL;
 	if (bytes) CK(cudaMemsetAsync(dst, value, bytes, ctx->stream));
 	return TRXB200_OK;
@@ -416,6 +457,7 @@ int trxb200_profile_begin(trxb200_ctx *ctx)
 
 int trxb200_profile_end(trxb200_ctx *ctx, char *out, int cap)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !out || cap < 1) return TRXB200_EINVAL;
 	ctx->prof = false;
 	CK(cudaDeviceSynchronize());
@@ -501,6 +543,7 @@ int trxb200_get_table(trxb200_ctx *ctx, const char *name, int idx, float *out, i
 int trxb200_modulate_gmsk_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits, int bits_stride, int n, float *out,
 				int out_stride)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !bits || !out || nbits < 2 || nbits > 156 || bits_stride < nbits || out_stride < 625 || n < 0)
 		return fail(ctx, TRXB200_EINVAL, "modulate_gmsk: bad argument");
 	if (n == 0) return TRXB200_OK;
@@ -511,6 +554,7 @@ int trxb200_modulate_gmsk_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits
 int trxb200_modulate_edge_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits, int bits_stride, int n, float *out,
 				int out_stride)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !bits || !out || nbits < 3 || (nbits % 3) || bits_stride < nbits || out_stride < 625 || n < 0)
 		return fail(ctx, TRXB200_EINVAL, "modulate_edge: bad argument");
 	if (n == 0) return TRXB200_OK;
@@ -634,7 +678,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	}
 	if (scan_clip) {
 		prof_pre(ctx, st);
-		clip_kernel<<<std::max(1, std::min((n + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(bursts, stride, n, rc, flags);
+		clip_kernel<<<std::max(1, std::min((n + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(bursts, stride, n, rc, flags, sch ? nullptr : type);
 		prof_post(ctx, st, "clip_kernel");
 		return post_launch(ctx, "clip_kernel");
 	}
@@ -683,6 +727,7 @@ int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int 
 			 const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh, int32_t *rc,
 			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (ctx && n == 0) return TRXB200_OK;
 	int r = check_dd(ctx, bursts, stride, n, max_toa_bound);
 	if (r) return r;
@@ -696,6 +741,7 @@ int trxb200_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int 
 int trxb200_detect_sch_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, float thresh, int32_t *rc, float *amp,
 			     float *toa, float *ci, uint8_t *flags)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (ctx && n == 0) return TRXB200_OK;
 	int r = check_dd(ctx, bursts, stride, n, 0);
 	if (r) return r;
@@ -707,6 +753,7 @@ int trxb200_detect_sch_batch(trxb200_ctx *ctx, const float *bursts, int stride, 
 int trxb200_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, const int32_t *rc, const float *amp,
 			const float *toa, float *ci, float *soft, int soft_stride, int n_gmsk_soft)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (ctx && n == 0) return TRXB200_OK;
 	int r = check_dd(ctx, bursts, stride, n, 0);
 	if (r) return r;
@@ -722,6 +769,7 @@ int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride
 			       int32_t *rc, float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags,
 			       float *soft, int soft_stride, int n_gmsk_soft)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (ctx && n == 0) return TRXB200_OK;
 	int r = check_dd(ctx, bursts, stride, n, max_toa_bound);
 	if (r) return r;
@@ -768,43 +816,66 @@ int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride
 }
 
 /* ---------------- host-buffer pipeline ---------------- */
+static bool host_ptr_is_pinned(const void *p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+static inline int round16(int m) { return (m + 15) & ~15; }
+
 static void stage_free(HostStage *s)
 {
 	for (int k = 0; k < HostStage::kSlots; k++) {
-		cudaFree(s->d_bursts[k]); cudaFree(s->d_type[k]); cudaFree(s->d_tsc[k]); cudaFree(s->d_tsc_out[k]);
-		cudaFree(s->d_flags[k]); cudaFree(s->d_max_toa[k]); cudaFree(s->d_rc[k]); cudaFree(s->d_amp[k]);
-		cudaFree(s->d_toa[k]); cudaFree(s->d_ci[k]); cudaFree(s->d_soft[k]);
+		cudaFree(s->d_bursts[k]); cudaFree(s->d_soft[k]); cudaFree(s->d_in[k]); cudaFree(s->d_out[k]);
+		cudaFreeHost(s->h_in[k]); cudaFreeHost(s->h_out[k]); cudaFreeHost(s->h_bursts[k]); cudaFreeHost(s->h_soft[k]);
 		cudaFree(s->ws[k].corr); cudaFree(s->ws[k].pwr);
 		if (s->streams[k]) cudaStreamDestroy(s->streams[k]);
-		if (s->done[k]) cudaEventDestroy(s->done[k]);
 	}
 	delete s;
 }
 
-static int stage_get(trxb200_ctx *ctx, int stride, int soft_stride, HostStage **out)
+// packed per-burst arrays of the float pipeline, m16 = round16(bursts in the chunk):
+//   in : max_toa u16 @0 | type u8 @2 m16 | tsc u8 @3 m16                                              ( 4 B per burst)
+//   out: rc i32 @0 | amp f32x2 @4 m16 | toa f32 @12 m16 | ci f32 @16 m16 | tsc_out u8 @20 m16 | flags u8 @21 m16 (22 B per burst)
+constexpr int kDdInBytes = 4, kDdOutBytes = 22;
+
+static int stage_get(trxb200_ctx *ctx, int stride, int soft_stride, bool stage_in, bool stage_out, HostStage **out)
 {
-	const int chunk = ctx->tune.host_chunk;
+	const int chunk = round16(ctx->tune.host_chunk);
 	HostStage *s = ctx->stage;
-	if (s && (s->stride != stride || s->soft_stride != soft_stride)) {
+	if (s && (s->stride != stride || s->soft_stride != soft_stride || s->chunk != chunk)) {
 		stage_free(s);
 		ctx->stage = s = nullptr;
 	}
+	cudaError_t e = cudaSuccess;
+	auto A = [&](auto **p_, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p_, bytes); };
+	auto H = [&](auto **p_, size_t bytes) { if (e == cudaSuccess && !*p_) e = cudaMallocHost(p_, bytes); };
 	if (!s) {
+		// built locally and published only when complete: a failed allocation must not leave a half-built stage cached
 		s = new HostStage();
 		s->chunk = chunk; s->stride = stride; s->soft_stride = soft_stride;
-		ctx->stage = s;
-		for (int k = 0; k < HostStage::kSlots; k++) {
-			CK(cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking));
-			CK(cudaEventCreateWithFlags(&s->done[k], cudaEventDisableTiming));
-			CK(cudaMalloc(&s->d_bursts[k], (size_t)chunk * stride * 8));
-			CK(cudaMalloc(&s->d_type[k], chunk)); CK(cudaMalloc(&s->d_tsc[k], chunk));
-			CK(cudaMalloc(&s->d_tsc_out[k], chunk)); CK(cudaMalloc(&s->d_flags[k], chunk));
-			CK(cudaMalloc(&s->d_max_toa[k], (size_t)chunk * 2)); CK(cudaMalloc(&s->d_rc[k], (size_t)chunk * 4));
-			CK(cudaMalloc(&s->d_amp[k], (size_t)chunk * 8)); CK(cudaMalloc(&s->d_toa[k], (size_t)chunk * 4));
-			CK(cudaMalloc(&s->d_ci[k], (size_t)chunk * 4));
-			CK(cudaMalloc(&s->d_soft[k], (size_t)chunk * soft_stride * 4));
+		for (int k = 0; k < HostStage::kSlots && e == cudaSuccess; k++) {
+			e = cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking);
+			A(&s->d_bursts[k], (size_t)chunk * stride * 8);
+			A(&s->d_soft[k], (size_t)chunk * soft_stride * 4);
+			A(&s->d_in[k], (size_t)chunk * kDdInBytes); A(&s->d_out[k], (size_t)chunk * kDdOutBytes);
+			H(&s->h_in[k], (size_t)chunk * kDdInBytes); H(&s->h_out[k], (size_t)chunk * kDdOutBytes);
 		}
+		if (e != cudaSuccess) {
+			stage_free(s);
+			return fail(ctx, e == cudaErrorMemoryAllocation ? TRXB200_ENOMEM : TRXB200_ECUDA, "detect_demod_host: staging buffers", e);
+		}
+		ctx->stage = s;
 	}
+	for (int k = 0; k < HostStage::kSlots; k++) {
+		if (stage_in) H(&s->h_bursts[k], (size_t)chunk * stride * 8);
+		if (stage_out) H(&s->h_soft[k], (size_t)chunk * soft_stride * 4);
+	}
+	if (e != cudaSuccess) return fail(ctx, TRXB200_ENOMEM, "detect_demod_host: pinned staging", e);
 	*out = s;
 	return TRXB200_OK;
 }
@@ -814,6 +885,7 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 			      int32_t *rc, float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags,
 			      float *soft, int soft_stride, int n_gmsk_soft)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (ctx && n == 0) return TRXB200_OK;
 	int r = check_dd(ctx, bursts, stride, n, max_toa_bound);
 	if (r) return r;
@@ -821,38 +893,68 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 	    n_gmsk_soft > 156 || soft_stride < n_gmsk_soft)
 		return fail(ctx, TRXB200_EINVAL, "detect_demod_host: bad argument");
 	if (n == 0) return TRXB200_OK;
-	CK(cudaSetDevice(ctx->device));
+	const bool pin_in = host_ptr_is_pinned(bursts), pin_out = host_ptr_is_pinned(soft);
 	HostStage *s = nullptr;
-	r = stage_get(ctx, stride, soft_stride, &s);
+	r = stage_get(ctx, stride, soft_stride, !pin_in, !pin_out, &s);
 	if (r) return r;
+	// small results of the chunk a slot carried last: wait for its copies, scatter to the caller's arrays
+	auto finish = [&](int slot) -> int {
+		CK(cudaStreamSynchronize(s->streams[slot]));
+		const int m = s->pend_m[slot], lo = s->pend_lo[slot];
+		if (!m) return TRXB200_OK;
+		const int m16 = round16(m);
+		const uint8_t *o = s->h_out[slot];
+		std::memcpy(rc + lo, o, (size_t)m * 4);
+		std::memcpy(amp + (size_t)lo * 2, o + (size_t)4 * m16, (size_t)m * 8);
+		std::memcpy(toa + lo, o + (size_t)12 * m16, (size_t)m * 4);
+		std::memcpy(ci + lo, o + (size_t)16 * m16, (size_t)m * 4);
+		std::memcpy(tsc_out + lo, o + (size_t)20 * m16, m);
+		if (flags) std::memcpy(flags + lo, o + (size_t)21 * m16, m);
+		if (!pin_out) std::memcpy(soft + (size_t)lo * soft_stride, s->h_soft[slot], (size_t)m * soft_stride * 4);
+		s->pend_m[slot] = 0;
+		return TRXB200_OK;
+	};
 	int slot = 0;
 	for (int lo = 0; lo < n; lo += s->chunk, slot = (slot + 1) % HostStage::kSlots) {
-		const int m = std::min(s->chunk, n - lo);
+		const int m = std::min(s->chunk, n - lo), m16 = round16(m);
 		cudaStream_t st = s->streams[slot];
-		CK(cudaStreamSynchronize(st)); // slot's previous chunk (incl. its D2H) has fully landed
-		CK(cudaMemcpyAsync(s->d_bursts[slot], bursts + (size_t)lo * stride * 2, (size_t)m * stride * 8, cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(s->d_type[slot], type + lo, m, cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(s->d_tsc[slot], tsc + lo, m, cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(s->d_max_toa[slot], max_toa + lo, (size_t)m * 2, cudaMemcpyHostToDevice, st));
+		r = finish(slot); // the slot's previous chunk (incl. its D2H) has fully landed
+		if (r) return r;
+		uint8_t *hi = s->h_in[slot];
+		std::memcpy(hi, max_toa + lo, (size_t)m * 2);
+		std::memcpy(hi + (size_t)2 * m16, type + lo, m);
+		std::memcpy(hi + (size_t)3 * m16, tsc + lo, m);
+		const float *src = bursts + (size_t)lo * stride * 2;
+		if (!pin_in) {
+			std::memcpy(s->h_bursts[slot], src, (size_t)m * stride * 8);
+			src = s->h_bursts[slot];
+		}
+		CK(cudaMemcpyAsync(s->d_bursts[slot], src, (size_t)m * stride * 8, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(s->d_in[slot], hi, (size_t)m16 * kDdInBytes, cudaMemcpyHostToDevice, st));
+		uint8_t *di = s->d_in[slot], *d_o = s->d_out[slot];
+		const uint16_t *d_max_toa = reinterpret_cast<const uint16_t *>(di);
+		const uint8_t *d_type = di + (size_t)2 * m16, *d_tsc = di + (size_t)3 * m16;
+		int32_t *d_rc = reinterpret_cast<int32_t *>(d_o);
+		float *d_amp = reinterpret_cast<float *>(d_o + (size_t)4 * m16), *d_toa = reinterpret_cast<float *>(d_o + (size_t)12 * m16);
+		float *d_ci = reinterpret_cast<float *>(d_o + (size_t)16 * m16);
+		uint8_t *d_tsc_out = d_o + (size_t)20 * m16, *d_flags = d_o + (size_t)21 * m16;
 		// rows of undetected bursts are never written by the kernels: define them as zero for host callers
 		CK(cudaMemsetAsync(s->d_soft[slot], 0, (size_t)m * soft_stride * 4, st));
-		r = launch_detect(ctx, st, s->ws[slot], s->d_bursts[slot], stride, m, s->d_type[slot], s->d_tsc[slot], s->d_max_toa[slot],
-				  max_toa_bound, thresh, s->d_rc[slot], s->d_amp[slot], s->d_toa[slot], s->d_tsc_out[slot],
-				  s->d_ci[slot], s->d_flags[slot], 0);
+		r = launch_detect(ctx, st, s->ws[slot], s->d_bursts[slot], stride, m, d_type, d_tsc, d_max_toa, max_toa_bound, thresh, d_rc, d_amp,
+				  d_toa, d_tsc_out, d_ci, d_flags, 0);
 		if (r) return r;
-		r = launch_demod(ctx, st, s->d_bursts[slot], stride, m, s->d_rc[slot], s->d_amp[slot], s->d_toa[slot],
-				 s->d_ci[slot], s->d_flags[slot], s->d_soft[slot], soft_stride, n_gmsk_soft, 1, s->d_type[slot]);
+		r = launch_demod(ctx, st, s->d_bursts[slot], stride, m, d_rc, d_amp, d_toa, d_ci, d_flags, s->d_soft[slot], soft_stride,
+				 n_gmsk_soft, 1, d_type);
 		if (r) return r;
-		CK(cudaMemcpyAsync(rc + lo, s->d_rc[slot], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(amp + (size_t)lo * 2, s->d_amp[slot], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(toa + lo, s->d_toa[slot], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(ci + lo, s->d_ci[slot], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(tsc_out + lo, s->d_tsc_out[slot], m, cudaMemcpyDeviceToHost, st));
-		if (flags) CK(cudaMemcpyAsync(flags + lo, s->d_flags[slot], m, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(soft + (size_t)lo * soft_stride, s->d_soft[slot], (size_t)m * soft_stride * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(pin_out ? soft + (size_t)lo * soft_stride : s->h_soft[slot], s->d_soft[slot], (size_t)m * soft_stride * 4,
+				   cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(s->h_out[slot], d_o, (size_t)m16 * kDdOutBytes, cudaMemcpyDeviceToHost, st));
+		s->pend_lo[slot] = lo; s->pend_m[slot] = m;
 	}
-	for (int k = 0; k < HostStage::kSlots; k++)
-		CK(cudaStreamSynchronize(s->streams[k]));
+	for (int k = 0; k < HostStage::kSlots; k++) {
+		r = finish(k);
+		if (r) return r;
+	}
 	return TRXB200_OK;
 }
 
@@ -957,6 +1059,7 @@ static int pull_chunk(trxb200_ctx *ctx, cudaStream_t st, PullScratch &w, const t
 
 int trxb200_pull_batch(trxb200_ctx *ctx, const trxb200_pull_args *a)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	int r = pull_check(ctx, a);
 	if (r || a->n == 0) return r;
 	const int cap = ctx->tune.pull_chunk;
@@ -978,6 +1081,7 @@ int trxb200_pull_batch(trxb200_ctx *ctx, const trxb200_pull_args *a)
 int trxb200_expected_corr_type_batch(trxb200_ctx *ctx, const trxb200_sched_cfg *cfg, const uint32_t *fn, const uint8_t *tn,
 				     const uint16_t *chan, int n, uint8_t *type, uint16_t *max_toa)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx) return TRXB200_EINVAL;
 	if (!cfg || n < 0 || cfg->n_chan < 1 || !cfg->chan_type || !cfg->handover || (n > 0 && (!fn || !tn || !type)))
 		return fail(ctx, TRXB200_EINVAL, "expected_corr_type: bad argument");
@@ -1012,20 +1116,25 @@ struct PullStage {
 	cudaStream_t streams[kSlots] = {};
 	PullScratch w[kSlots];
 	int16_t *d_iq[kSlots] = {};
-	uint8_t *d_type[kSlots] = {}, *d_tsc[kSlots] = {}, *d_tn[kSlots] = {}, *d_flags[kSlots] = {}, *d_pkt[kSlots] = {};
-	uint16_t *d_max_toa[kSlots] = {}, *d_pkt_len[kSlots] = {};
-	uint32_t *d_fn[kSlots] = {};
-	int32_t *d_rc[kSlots] = {};
-	float *d_energy[kSlots] = {};
+	uint8_t *d_pkt[kSlots] = {};
+	uint8_t *d_in[kSlots] = {}, *d_out[kSlots] = {}; // packed small arrays (device)
+	uint8_t *h_in[kSlots] = {}, *h_out[kSlots] = {}; // their pinned mirrors
+	int16_t *h_iq[kSlots] = {};			   // pinned staging, allocated only for pageable callers
+	uint8_t *h_pkt[kSlots] = {};
+	int pend_lo[kSlots] = {}, pend_m[kSlots] = {};
 };
+// packed per-slot arrays of the pull pipeline, m16 = round16(slots in the chunk):
+//   in : fn u32 @0 | max_toa u16 @4 m16 | type u8 @6 m16 | tsc u8 @7 m16 | tn u8 @8 m16                  ( 9 B per slot)
+//   out: rc i32 @0 | energy f32 @4 m16 | pkt_len u16 @8 m16 | flags u8 @10 m16 | tsc_out u8 @11 m16     (12 B per slot)
+//        | amp f32x2 @12 m16 | toa f32 @20 m16 | ci f32 @24 m16   (copied back only when the caller asks for one of them)
+constexpr int kPullInBytes = 9, kPullOutBytes = 12, kPullOutBytesAll = 28;
 
 static void pull_stage_free(PullStage *s)
 {
 	for (int k = 0; k < PullStage::kSlots; k++) {
 		pull_scratch_free(s->w[k]);
-		cudaFree(s->d_iq[k]); cudaFree(s->d_type[k]); cudaFree(s->d_tsc[k]); cudaFree(s->d_tn[k]); cudaFree(s->d_flags[k]);
-		cudaFree(s->d_pkt[k]); cudaFree(s->d_max_toa[k]); cudaFree(s->d_pkt_len[k]); cudaFree(s->d_fn[k]); cudaFree(s->d_rc[k]);
-		cudaFree(s->d_energy[k]);
+		cudaFree(s->d_iq[k]); cudaFree(s->d_pkt[k]); cudaFree(s->d_in[k]); cudaFree(s->d_out[k]);
+		cudaFreeHost(s->h_in[k]); cudaFreeHost(s->h_out[k]); cudaFreeHost(s->h_iq[k]); cudaFreeHost(s->h_pkt[k]);
 		if (s->streams[k]) cudaStreamDestroy(s->streams[k]);
 	}
 	delete s;
@@ -1033,64 +1142,112 @@ static void pull_stage_free(PullStage *s)
 
 int trxb200_pull_host(trxb200_ctx *ctx, const trxb200_pull_args *a)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	int r = pull_check(ctx, a);
 	if (r || a->n == 0) return r;
-	CK(cudaSetDevice(ctx->device));
-	const int chunk = ctx->tune.host_chunk;
+	const int chunk = round16(ctx->tune.host_chunk);
+	const bool pin_in = host_ptr_is_pinned(a->iq), pin_out = host_ptr_is_pinned(a->pkt);
 	PullStage *s = ctx->pull_stage;
-	if (s && (s->stride != a->stride || s->pkt_stride != a->pkt_stride)) {
+	if (s && (s->stride != a->stride || s->pkt_stride != a->pkt_stride || s->chunk != chunk)) {
 		pull_stage_free(s);
 		ctx->pull_stage = s = nullptr;
 	}
-	if (!s) {
-		s = new PullStage();
-		s->chunk = chunk; s->stride = a->stride; s->pkt_stride = a->pkt_stride;
-		ctx->pull_stage = s;
-		for (int k = 0; k < PullStage::kSlots; k++) {
-			CK(cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking));
-			CK(cudaMalloc(&s->d_iq[k], (size_t)chunk * a->stride * 4));
-			CK(cudaMalloc(&s->d_type[k], chunk)); CK(cudaMalloc(&s->d_tsc[k], chunk)); CK(cudaMalloc(&s->d_tn[k], chunk));
-			CK(cudaMalloc(&s->d_flags[k], chunk)); CK(cudaMalloc(&s->d_pkt[k], (size_t)chunk * a->pkt_stride));
-			CK(cudaMalloc(&s->d_max_toa[k], (size_t)chunk * 2)); CK(cudaMalloc(&s->d_pkt_len[k], (size_t)chunk * 2));
-			CK(cudaMalloc(&s->d_fn[k], (size_t)chunk * 4)); CK(cudaMalloc(&s->d_rc[k], (size_t)chunk * 4));
-			CK(cudaMalloc(&s->d_energy[k], (size_t)chunk * 4));
+	{
+		cudaError_t e = cudaSuccess;
+		auto A = [&](auto **p_, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p_, bytes); };
+		auto H = [&](auto **p_, size_t bytes) { if (e == cudaSuccess && !*p_) e = cudaMallocHost(p_, bytes); };
+		if (!s) {
+			// built locally and published only when complete (a failed allocation leaves nothing half-built behind)
+			s = new PullStage();
+			s->chunk = chunk; s->stride = a->stride; s->pkt_stride = a->pkt_stride;
+			for (int k = 0; k < PullStage::kSlots && e == cudaSuccess; k++) {
+				e = cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking);
+				A(&s->d_iq[k], (size_t)chunk * a->stride * 4);
+				A(&s->d_pkt[k], (size_t)chunk * a->pkt_stride);
+				A(&s->d_in[k], (size_t)chunk * kPullInBytes); A(&s->d_out[k], (size_t)chunk * kPullOutBytesAll);
+				H(&s->h_in[k], (size_t)chunk * kPullInBytes); H(&s->h_out[k], (size_t)chunk * kPullOutBytesAll);
+			}
+			if (e != cudaSuccess) {
+				pull_stage_free(s);
+				return fail(ctx, e == cudaErrorMemoryAllocation ? TRXB200_ENOMEM : TRXB200_ECUDA, "pull_host: staging buffers", e);
+			}
+			ctx->pull_stage = s;
 		}
+		for (int k = 0; k < PullStage::kSlots; k++) {
+			if (!pin_in) H(&s->h_iq[k], (size_t)chunk * a->stride * 4);
+			if (!pin_out) H(&s->h_pkt[k], (size_t)chunk * a->pkt_stride);
+		}
+		if (e != cudaSuccess) return fail(ctx, TRXB200_ENOMEM, "pull_host: pinned staging", e);
 	}
+	const bool want_ebp = a->amp || a->toa || a->ci;
+	const int out_bytes = want_ebp ? kPullOutBytesAll : kPullOutBytes;
+	auto finish = [&](int slot) -> int {
+		CK(cudaStreamSynchronize(s->streams[slot]));
+		const int m = s->pend_m[slot], lo = s->pend_lo[slot];
+		if (!m) return TRXB200_OK;
+		const int m16 = round16(m);
+		const uint8_t *o = s->h_out[slot];
+		std::memcpy(a->rc + lo, o, (size_t)m * 4);
+		std::memcpy(a->energy + lo, o + (size_t)4 * m16, (size_t)m * 4);
+		std::memcpy(a->pkt_len + lo, o + (size_t)8 * m16, (size_t)m * 2);
+		if (a->flags) std::memcpy(a->flags + lo, o + (size_t)10 * m16, m);
+		if (a->tsc_out) std::memcpy(a->tsc_out + lo, o + (size_t)11 * m16, m);
+		if (a->amp) std::memcpy(a->amp + (size_t)lo * 2, o + (size_t)12 * m16, (size_t)m * 8);
+		if (a->toa) std::memcpy(a->toa + lo, o + (size_t)20 * m16, (size_t)m * 4);
+		if (a->ci) std::memcpy(a->ci + lo, o + (size_t)24 * m16, (size_t)m * 4);
+		if (!pin_out) std::memcpy(a->pkt + (size_t)lo * a->pkt_stride, s->h_pkt[slot], (size_t)m * a->pkt_stride);
+		s->pend_m[slot] = 0;
+		return TRXB200_OK;
+	};
 	const int ss = pull_soft_stride(a);
 	int s_min_, W_;
 	pull_window(ctx, a->max_toa_bound, s_min_, W_);
 	int slot = 0;
 	for (int lo = 0; lo < a->n; lo += chunk, slot = (slot + 1) % PullStage::kSlots) {
-		const int m = std::min(chunk, a->n - lo);
+		const int m = std::min(chunk, a->n - lo), m16 = round16(m);
 		cudaStream_t st = s->streams[slot];
-		CK(cudaStreamSynchronize(st)); // the slot's previous chunk (incl. its D2H) has fully landed
+		r = finish(slot); // the slot's previous chunk (incl. its D2H) has fully landed
+		if (r) return r;
 		r = pull_scratch_get(ctx, st, s->w[slot], chunk, ss, W_);
 		if (r) return r;
 		PullScratch &w = s->w[slot];
-		CK(cudaMemcpyAsync(s->d_iq[slot], a->iq + (size_t)lo * a->stride * 2, (size_t)m * a->stride * 4, cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(s->d_type[slot], a->type + lo, m, cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(s->d_tsc[slot], a->tsc + lo, m, cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(s->d_max_toa[slot], a->max_toa + lo, (size_t)m * 2, cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(s->d_fn[slot], a->fn + lo, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(s->d_tn[slot], a->tn + lo, m, cudaMemcpyHostToDevice, st));
+		uint8_t *hi = s->h_in[slot];
+		std::memcpy(hi, a->fn + lo, (size_t)m * 4);
+		std::memcpy(hi + (size_t)4 * m16, a->max_toa + lo, (size_t)m * 2);
+		std::memcpy(hi + (size_t)6 * m16, a->type + lo, m);
+		std::memcpy(hi + (size_t)7 * m16, a->tsc + lo, m);
+		std::memcpy(hi + (size_t)8 * m16, a->tn + lo, m);
+		const int16_t *src = a->iq + (size_t)lo * a->stride * 2;
+		if (!pin_in) {
+			std::memcpy(s->h_iq[slot], src, (size_t)m * a->stride * 4);
+			src = s->h_iq[slot];
+		}
+		CK(cudaMemcpyAsync(s->d_iq[slot], src, (size_t)m * a->stride * 4, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(s->d_in[slot], hi, (size_t)m16 * kPullInBytes, cudaMemcpyHostToDevice, st));
+		uint8_t *di = s->d_in[slot], *d_o = s->d_out[slot];
+		const uint32_t *d_fn = reinterpret_cast<const uint32_t *>(di);
+		const uint16_t *d_max_toa = reinterpret_cast<const uint16_t *>(di + (size_t)4 * m16);
+		const uint8_t *d_type = di + (size_t)6 * m16, *d_tsc = di + (size_t)7 * m16, *d_tn = di + (size_t)8 * m16;
+		int32_t *d_rc = reinterpret_cast<int32_t *>(d_o);
+		float *d_energy = reinterpret_cast<float *>(d_o + (size_t)4 * m16);
+		uint16_t *d_pkt_len = reinterpret_cast<uint16_t *>(d_o + (size_t)8 * m16);
+		uint8_t *d_flags = d_o + (size_t)10 * m16, *d_tsc_out = d_o + (size_t)11 * m16;
+		float *d_amp = reinterpret_cast<float *>(d_o + (size_t)12 * m16), *d_toa = reinterpret_cast<float *>(d_o + (size_t)20 * m16);
+		float *d_ci = reinterpret_cast<float *>(d_o + (size_t)24 * m16);
 		// datagram rows of slots that emit nothing are never written by the kernels: defined as zero for host callers
 		CK(cudaMemsetAsync(s->d_pkt[slot], 0, (size_t)m * a->pkt_stride, st));
-		r = pull_chunk(ctx, st, w, a, m, s->d_iq[slot], s->d_type[slot], s->d_tsc[slot], s->d_max_toa[slot], s->d_fn[slot],
-			       s->d_tn[slot], s->d_rc[slot], s->d_energy[slot], s->d_pkt[slot], s->d_pkt_len[slot], s->d_flags[slot],
-			       nullptr, nullptr, nullptr, nullptr);
+		r = pull_chunk(ctx, st, w, a, m, s->d_iq[slot], d_type, d_tsc, d_max_toa, d_fn, d_tn, d_rc, d_energy, s->d_pkt[slot], d_pkt_len,
+			       d_flags, d_amp, d_toa, d_ci, d_tsc_out);
 		if (r) return r;
-		CK(cudaMemcpyAsync(a->rc + lo, s->d_rc[slot], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(a->energy + lo, s->d_energy[slot], (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(a->pkt + (size_t)lo * a->pkt_stride, s->d_pkt[slot], (size_t)m * a->pkt_stride, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(a->pkt_len + lo, s->d_pkt_len[slot], (size_t)m * 2, cudaMemcpyDeviceToHost, st));
-		if (a->flags) CK(cudaMemcpyAsync(a->flags + lo, s->d_flags[slot], m, cudaMemcpyDeviceToHost, st));
-		if (a->amp) CK(cudaMemcpyAsync(a->amp + (size_t)lo * 2, w.amp, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
-		if (a->toa) CK(cudaMemcpyAsync(a->toa + lo, w.toa, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-		if (a->ci) CK(cudaMemcpyAsync(a->ci + lo, w.ci, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-		if (a->tsc_out) CK(cudaMemcpyAsync(a->tsc_out + lo, w.tsc_out, m, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(pin_out ? a->pkt + (size_t)lo * a->pkt_stride : s->h_pkt[slot], s->d_pkt[slot], (size_t)m * a->pkt_stride,
+				   cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(s->h_out[slot], d_o, (size_t)m16 * out_bytes, cudaMemcpyDeviceToHost, st));
+		s->pend_lo[slot] = lo; s->pend_m[slot] = m;
 	}
-	for (int k = 0; k < PullStage::kSlots; k++)
-		CK(cudaStreamSynchronize(s->streams[k]));
+	for (int k = 0; k < PullStage::kSlots; k++) {
+		r = finish(k);
+		if (r) return r;
+	}
 	return TRXB200_OK;
 }
 
@@ -1098,6 +1255,7 @@ int trxb200_pull_host(trxb200_ctx *ctx, const trxb200_pull_args *a)
 int trxb200_energy_detect_batch(trxb200_ctx *ctx, const float *bursts, int stride, int blen, int n, unsigned window,
 				float *energy)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !bursts || !energy || n < 0 || blen < 1 || stride < blen) return fail(ctx, TRXB200_EINVAL, "energy_detect: bad argument");
 	if (window > (unsigned)blen) window = blen;
 	if (window && 4 * (size_t)(window - 1) >= (size_t)stride) return fail(ctx, TRXB200_EINVAL, "energy_detect: window*4 exceeds the row");
@@ -1108,6 +1266,7 @@ int trxb200_energy_detect_batch(trxb200_ctx *ctx, const float *bursts, int strid
 
 int trxb200_vector_slicer(trxb200_ctx *ctx, float *dst, const float *src, size_t len)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !dst || !src) return fail(ctx, TRXB200_EINVAL, "vector_slicer: bad argument");
 	if (len == 0) return TRXB200_OK;
 	const int vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
@@ -1118,6 +1277,7 @@ int trxb200_vector_slicer(trxb200_ctx *ctx, float *dst, const float *src, size_t
 int trxb200_delay_vector_batch(trxb200_ctx *ctx, const float *in, int stride, int len, int n, const float *delay,
 			       float *out, int out_stride)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !in || !out || !delay || len < 1 || stride < len || out_stride < len || n < 0)
 		return fail(ctx, TRXB200_EINVAL, "delay_vector: bad argument");
 	if (n == 0) return TRXB200_OK;
@@ -1168,6 +1328,7 @@ int trxb200_convolve_complex_batch(trxb200_ctx *ctx, const float *x, int x_len, 
 
 int trxb200_convert_float_short(trxb200_ctx *ctx, int16_t *out, const float *in, float scale, size_t len)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !out || !in) return fail(ctx, TRXB200_EINVAL, "convert: bad argument");
 	if (len == 0) return TRXB200_OK;
 	const int vec = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(in)) & 15) == 0;
@@ -1177,6 +1338,7 @@ int trxb200_convert_float_short(trxb200_ctx *ctx, int16_t *out, const float *in,
 
 int trxb200_convert_short_float(trxb200_ctx *ctx, float *out, const int16_t *in, size_t len)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !out || !in) return fail(ctx, TRXB200_EINVAL, "convert: bad argument");
 	if (len == 0) return TRXB200_OK;
 	const int vec = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(in)) & 15) == 0;

@@ -22,6 +22,7 @@ extern "C" {
 int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab, const uint8_t *tsc,
 			int max_delay, int clamp_lo, int clamp_hi, int8_t *bits, int32_t *start, float *corr_max, float *cir)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx) return TRXB200_EINVAL;
 	if (!bufs || !bits || !start || !corr_max || n < 0 || max_delay < 0 || max_delay > 64 || is_ab < 0 || is_ab > 2 || (!is_ab && !tsc))
 		return fail(ctx, TRXB200_EINVAL, "vitac: bad argument");
@@ -56,6 +57,7 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 int trxb200_vitac_detect_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab, const float *cir_in,
 			       const int32_t *start_in, int clamp_lo, int clamp_hi, int8_t *bits)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx) return TRXB200_EINVAL;
 	if (!bufs || !bits || !cir_in || !start_in || n < 0 || is_ab < 0 || is_ab > 1 || clamp_lo > clamp_hi)
 		return fail(ctx, TRXB200_EINVAL, "vitac_detect: bad argument");
@@ -84,6 +86,7 @@ int trxb200_vitac_detect_batch(trxb200_ctx *ctx, const float *bufs, int stride, 
 /* ---------------- Resampler ---------------- */
 int trxb200_resampler_create(trxb200_ctx *ctx, int p, int q, int filt_len, float bw, trxb200_resampler **out)
 {
+	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx || !out) return TRXB200_EINVAL;
 	*out = nullptr;
 	if (p <= 0 || q <= 0 || filt_len <= 0 || filt_len > 32) // Resampler::init returns false for zero sizes
@@ -101,6 +104,7 @@ int trxb200_resampler_create(trxb200_ctx *ctx, int p, int q, int filt_len, float
 void trxb200_resampler_destroy(trxb200_resampler *r)
 {
 	if (!r) return;
+	DevGuard dg(r->ctx->device);
 	cudaFree(r->d_taps);
 	delete r;
 }
@@ -117,6 +121,7 @@ int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, 
 {
 	if (!r) return TRXB200_EINVAL;
 	trxb200_ctx *ctx = r->ctx;
+	DevGuard dg(ctx->device);
 	if (!in || !out || n_streams < 0 || in_len <= 0 || out_len <= 0)
 		return fail(ctx, TRXB200_EINVAL, "resampler_rotate: bad argument");
 	// check_vec_len (Resampler.cpp:98-129) + MAX_OUTPUT_LEN
@@ -144,6 +149,7 @@ int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, 
 static int fb_create(trxb200_ctx *ctx, int m, int block_len, int h_len, int synth, trxb200_filterbank **out)
 {
 	if (!ctx || !out) return TRXB200_EINVAL;
+	DevGuard dg(ctx->device);
 	*out = nullptr;
 	if (m < 1 || m > 256 || h_len < 1 || h_len > 32 || block_len < h_len)
 		return fail(ctx, TRXB200_EINVAL, "filterbank: bad m/block_len/h_len");
@@ -180,6 +186,7 @@ int trxb200_synthesis_create(trxb200_ctx *ctx, int m, int block_len, int h_len, 
 void trxb200_filterbank_destroy(trxb200_filterbank *fb)
 {
 	if (!fb) return;
+	DevGuard dg(fb->ctx->device);
 	cudaFree(fb->d_taps); cudaFree(fb->d_tw); cudaFree(fb->d_hist[0]); cudaFree(fb->d_hist[1]);
 	delete fb;
 }
@@ -188,6 +195,7 @@ int trxb200_filterbank_reset(trxb200_filterbank *fb)
 {
 	if (!fb) return TRXB200_EINVAL;
 	trxb200_ctx *ctx = fb->ctx;
+	DevGuard dg(ctx->device);
 	for (int k = 0; k < 2; k++) CK(cudaMemsetAsync(fb->d_hist[k], 0, (size_t)fb->m * fb->L * 8, ctx->stream));
 	return TRXB200_OK;
 }
@@ -203,6 +211,7 @@ int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *o
 {
 	if (!fb) return TRXB200_EINVAL;
 	trxb200_ctx *ctx = fb->ctx;
+	DevGuard dg(ctx->device);
 	if (fb->synth || !in || !out || n_blocks < 0) return fail(ctx, TRXB200_EINVAL, "channelizer_rotate: bad argument");
 	if (n_blocks == 0) return TRXB200_OK;
 	const long total_t = (long)n_blocks * fb->block_len;
@@ -238,6 +247,7 @@ int trxb200_synthesis_rotate(trxb200_filterbank *fb, const float *in, float *out
 {
 	if (!fb) return TRXB200_EINVAL;
 	trxb200_ctx *ctx = fb->ctx;
+	DevGuard dg(ctx->device);
 	if (!fb->synth || !in || !out || n_blocks < 0) return fail(ctx, TRXB200_EINVAL, "synthesis_rotate: bad argument");
 	if (n_blocks == 0) return TRXB200_OK;
 	const long total_t = (long)n_blocks * fb->block_len;

@@ -497,7 +497,7 @@ demod_kernel(DemodParams p)
 		}
 		if (rc <= 0) {
 			// undetected burst: only the deferred clipping report is left to do (sigProcLib.cpp:1746-1764)
-			if (p.fix_clip && rc == 0 && (!p.type || type_known(p.type[b]))) {
+			if (p.fix_clip && rc == 0 && (!p.type || type_known(load_type(p.type, b, 0)))) {
 				float2 v[20];
 #pragma unroll
 				for (int k = 0; k < 20; k++) {

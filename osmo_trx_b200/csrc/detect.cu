@@ -835,14 +835,17 @@ peak_kernel(PeakParams p)
 }
 
 // maxAmplitude (sigProcLib.cpp:1711-1722) for the bursts detection left at rc == 0: -SIGERR_CLIP is only
-// reported when nothing was detected (:1764).  One warp per burst.
+// reported when nothing was detected (:1764), and only for the types detectAnyBurst hands to detectGeneralBurst:
+// OFF, SCH and unknown types return 0 without a clipping check (:1949-1956).  type == nullptr: every burst is checked.
+// One warp per burst.
 __global__ void __launch_bounds__(256)
-clip_kernel(const float *bursts, int stride, int n, int32_t *rc, uint8_t *flags)
+clip_kernel(const float *bursts, int stride, int n, int32_t *rc, uint8_t *flags, const uint8_t *type)
 {
 	const int lane = threadIdx.x & 31;
 	const int wpb = blockDim.x >> 5;
 	for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n; b += gridDim.x * wpb) {
 		if (rc[b] != 0) continue;
+		if (type && !type_known(load_type(type, b, 0))) continue;
 		const float2 *x = reinterpret_cast<const float2 *>(bursts) + (size_t)b * stride;
 		float mx = 0.0f;
 		for (int i = lane; i < 625; i += 32) {

@@ -20,7 +20,7 @@ from cpulibs import TSC, RACH, EDGE
 pytestmark = pytest.mark.gpu
 
 N = 1 << 20
-SUBSET = 1500
+SUBSET = 20000  # bursts of each 2^20 batch that also go through the CPU checker
 
 
 def beq(a, b):

@@ -1,4 +1,6 @@
 """GPU parity tests proper: CUDA path (through the C ABI) vs the CPU checker on identical seeded inputs."""
+import contextlib
+
 import numpy as np
 import pytest
 import torch
@@ -28,10 +30,49 @@ def run_gpu_dd(trx, rx, typ, tsc, max_toa, bound, n_soft=156, soft_stride=444):
     return {k: v.cpu().numpy() for k, v in r.items()}
 
 
-def check_dd(trx, checker, rx, typ, tsc, max_toa, what, n_soft=156):
+# detect_config settings the detection tests are run under: the default (long-window correlator, three attempts),
+# and the two 16-symbol hints that select the register-blocked / fused normal-burst kernels (the benchmarked path)
+DETECT_CFGS = [(40, 3), (16, 1), (16, 2)]
+
+
+@contextlib.contextmanager
+def detect_cfg(trx, cfg):
+    try:
+        trx.detect_config(*cfg)
+        yield
+    finally:
+        trx.detect_config(40, 3)
+
+
+def unsupported_under(cfg, typ, ref_rc, n):
+    """Bursts the configuration hint cannot serve and that must therefore come back as -SIGERR_BOUNDS (never a silent
+    wrong answer): access bursts under the 16-symbol hint; 8-PSK bursts that the reference only finds in a later
+    attempt (EDGE -> TSC fall-through, sigProcLib.cpp:1933-1941) when fewer attempts are scheduled."""
+    typ = np.broadcast_to(np.asarray(typ, np.uint8), (n,))
+    bad = np.zeros(n, bool)
+    if cfg[0] < 40:
+        bad |= (typ == RACH) | (typ == EXT_RACH)
+    if cfg[1] < 2:
+        bad |= (typ == EDGE) & (ref_rc != EDGE) & (ref_rc != -3)
+    if cfg[1] < 3:
+        bad |= (typ == EXT_RACH)  # sequences 1, 2 are attempts 2, 3; a hit on sequence 0 is still reported (checked below)
+    return bad
+
+
+def check_dd(trx, checker, rx, typ, tsc, max_toa, what, n_soft=156, cfg=(40, 3)):
     bound = int(np.max(max_toa))
-    g = run_gpu_dd(trx, rx, typ, tsc, max_toa, bound, n_soft=n_soft)
+    n = rx.shape[0]
+    with detect_cfg(trx, cfg):
+        g = run_gpu_dd(trx, rx, typ, tsc, max_toa, bound, n_soft=n_soft)
     c = checker.detect_demod(rx, typ, tsc, max_toa)
+    bad = unsupported_under(cfg, typ, c["rc"], n)
+    if bad.any():
+        # loud failure on what the hint excludes (an EXT_RACH hit on the first sequence is a legitimate answer)
+        gb = g["rc"][bad]
+        assert ((gb == -1) | (gb == c["rc"][bad])).all(), f"{what}: unsupported bursts not reported as -SIGERR_BOUNDS"
+        keep = ~bad
+        g = {k: v[keep] for k, v in g.items()}
+        c = {k: v[keep] for k, v in c.items()}
     rep = parity.compare_detect(g, c, g["flags"], what)
     ok = rep["ok_mask"]
     gmsk = ok & (c["rc"] != EDGE)
@@ -85,7 +126,8 @@ def test_modulate_edge_exact(trx, checker):
     assert np.array_equal(out, ref)
 
 
-def test_nb_detect_demod_cfg1(trx, checker):
+@pytest.mark.parametrize("cfg", DETECT_CFGS)
+def test_nb_detect_demod_cfg1(trx, checker, cfg):
     """BASELINE configs[0]: 10k GMSK normal bursts, TSC 0-7, sps=4, AWGN + random TOA."""
     rng = np.random.default_rng(1)
     n = 10000
@@ -94,7 +136,7 @@ def test_nb_detect_demod_cfg1(trx, checker):
     w = checker.modulate_gmsk_batch(bits, nthreads=8)
     snr = np.choose(np.arange(n) % 3, [30.0, 10.0, 6.0])
     rx, _ = synth.impair(w, rng, snr_db=snr, noise_only_frac=0.05)
-    g, c, rep = check_dd(trx, checker, rx, TSC, tsc, 4, "cfg1-NB")
+    g, c, rep = check_dd(trx, checker, rx, TSC, tsc, 4, f"cfg1-NB{cfg}", cfg=cfg)
     assert rep["detected"] > 0.9 * 0.95 * n
     det = c["rc"] > 0
     hard = (g["soft"][det][:, :148] > 0).astype(np.uint8)
@@ -102,7 +144,8 @@ def test_nb_detect_demod_cfg1(trx, checker):
     print("cfg1 BER", ber)
     assert ber < 0.02
     # also with the 148-wide output the transceiver consumes
-    g2 = run_gpu_dd(trx, rx[:512], TSC, tsc[:512], 4, 4, n_soft=148, soft_stride=148)
+    with detect_cfg(trx, cfg):
+        g2 = run_gpu_dd(trx, rx[:512], TSC, tsc[:512], 4, 4, n_soft=148, soft_stride=148)
     assert np.array_equal(g2["soft"], g["soft"][:512, :148])
 
 
@@ -132,7 +175,8 @@ def test_detect_demod_pipeline_same_bits(trx, checker, monkeypatch):
         assert np.array_equal(got[k][det], ref[k][det]), k
 
 
-def test_nb_full_scale_and_clipping(trx, checker):
+@pytest.mark.parametrize("cfg", DETECT_CFGS)
+def test_nb_full_scale_and_clipping(trx, checker, cfg):
     rng = np.random.default_rng(5)
     n = 1024
     tsc = np.arange(n) % 8
@@ -140,13 +184,20 @@ def test_nb_full_scale_and_clipping(trx, checker):
     rx, _ = synth.impair(w, rng, snr_db=20.0, full_scale=20000.0, noise_only_frac=0.2)
     rx[::7] *= 3.0  # drive some bursts beyond CLIP_THRESH (still detected -> no clip report)
     rx[::5] = (rng.standard_normal((len(rx[::5]), 625, 2)) * 15000.0).astype(np.float32)  # loud noise: clip, no burst
-    g, c, rep = check_dd(trx, checker, rx, TSC, tsc, 4, "clip")
+    g, c, rep = check_dd(trx, checker, rx, TSC, tsc, 4, f"clip{cfg}", cfg=cfg)
     assert (c["rc"] == -2).any() and (c["rc"] == 1).any()
-    # standalone detect reports clipping too
+    # standalone detect reports clipping too - but only for the types detectAnyBurst handles: OFF / SCH / unknown
+    # types return 0 without a clipping check (sigProcLib.cpp:1949-1956)
     n2 = 256
-    r = trx.detect(dev(rx[:n2]), dev(np.full(n2, TSC, np.uint8)), dev(tsc[:n2].astype(np.uint8)),
-                   dev(np.full(n2, 4, np.int16)), 4)
-    assert np.array_equal(r["rc"].cpu().numpy(), c["rc"][:n2])
+    typ2 = np.full(n2, TSC, np.uint8)
+    typ2[::5] = 0      # OFF on loud-noise bursts
+    typ2[5::10] = 4    # SCH is not a detectAnyBurst type
+    typ2[10::20] = 9   # unknown
+    with detect_cfg(trx, cfg):
+        r = trx.detect(dev(rx[:n2]), dev(typ2), dev(tsc[:n2].astype(np.uint8)), dev(np.full(n2, 4, np.int16)), 4)
+    c2 = checker.detect_demod(rx[:n2], typ2, tsc[:n2], 4)
+    assert np.array_equal(r["rc"].cpu().numpy(), c2["rc"])
+    assert (c2["rc"][typ2 != TSC] == 0).all() and (c2["rc"] == -2).any()
 
 
 def test_rach(trx, checker):
@@ -163,7 +214,8 @@ def test_rach(trx, checker):
         assert rep["detected"] > 100
 
 
-def test_edge_and_fallback(trx, checker):
+@pytest.mark.parametrize("cfg", DETECT_CFGS)
+def test_edge_and_fallback(trx, checker, cfg):
     rng = np.random.default_rng(3)
     n = 2000
     tsc = np.arange(n) % 8
@@ -171,8 +223,8 @@ def test_edge_and_fallback(trx, checker):
     rx, _ = synth.impair(w, rng, snr_db=25.0, noise_only_frac=0.05)
     wn = checker.modulate_gmsk_batch(synth.nb_bits(300, tsc[:300], rng))
     rx[:300], _ = synth.impair(wn, rng, snr_db=20.0)
-    g, c, rep = check_dd(trx, checker, rx, EDGE, tsc, 4, "edge")
-    assert (c["rc"] == EDGE).sum() > 1000 and (c["rc"] == TSC).sum() > 200
+    g, c, rep = check_dd(trx, checker, rx, EDGE, tsc, 4, f"edge{cfg}", cfg=cfg)
+    assert (c["rc"] == EDGE).sum() > 1000 and (cfg[1] < 2 or (c["rc"] == TSC).sum() > 200)
 
 
 def test_idle_and_mixed_types(trx, checker):
@@ -187,6 +239,27 @@ def test_idle_and_mixed_types(trx, checker):
     mt = np.choose(np.arange(n) % 4, [0, 4, 17, 63]).astype(np.int16)
     g, c, rep = check_dd(trx, checker, rx, typ, tscv, mt, "mixed")
     assert (c["rc"] == -3).any()
+
+
+@pytest.mark.parametrize("cfg", DETECT_CFGS)
+def test_mixed_types_nb_geometry(trx, checker, cfg):
+    """Every burst type, unsupported TSCs and per-burst max_toa values inside the normal-burst kernels' geometry
+    (16-symbol sequences, max_toa <= 4): under the 16-symbol hints this is the register-blocked / fused path."""
+    rng = np.random.default_rng(14)
+    n = 4200
+    tsc = np.arange(n) % 8
+    w = checker.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng), nthreads=8)
+    eidx = np.arange(2, n, 6)[::2]  # half of the EDGE-typed slots carry real 8-PSK bursts
+    w[eidx] = checker.modulate_edge_batch(synth.edge_bits(len(eidx), tsc[eidx], rng), nthreads=8)
+    rx, _ = synth.impair(w, rng, snr_db=np.choose(np.arange(n) % 5, [30.0, 22.0, 15.0, 9.0, 5.0]), noise_only_frac=0.1,
+                         full_scale=12000.0)
+    rx[7::97] = (rng.standard_normal((len(rx[7::97]), 625, 2)) * 15000.0).astype(np.float32)  # clipping noise
+    typ = np.choose(np.arange(n) % 6, [TSC, IDLE, EDGE, RACH, 0, 4]).astype(np.uint8)
+    tscv = tsc.copy()
+    tscv[::50] = 9
+    mt = np.choose(np.arange(n) % 5, [0, 1, 2, 3, 4]).astype(np.int16)
+    g, c, rep = check_dd(trx, checker, rx, typ, tscv, mt, f"mixed-nb{cfg}", cfg=cfg)
+    assert (c["rc"] == -3).any() and (c["rc"] == -2).any() and (c["rc"] == IDLE).any() and (c["rc"] == EDGE).any()
 
 
 def test_empty_and_tiny_batches(trx, checker):
@@ -442,7 +515,8 @@ def pull_inputs(checker, n, seed, kind="nb"):
     return rng, tsc, rx, fn, tn
 
 
-def test_pull_nb_trxd_v1(trx, checker):
+@pytest.mark.parametrize("cfg", DETECT_CFGS)
+def test_pull_nb_trxd_v1(trx, checker, cfg):
     n = 6000
     rng, tsc, rx, fn, tn = pull_inputs(checker, n, 31)
     iq = to_i16(rx, 8000.0)
@@ -452,11 +526,13 @@ def test_pull_nb_trxd_v1(trx, checker):
     typ = np.full(n, TSC, np.uint8)
     typ[::37] = IDLE
     typ[5::41] = 0  # OFF
-    g, c, rep = run_pull(trx, checker, iq, typ, tsc, 4, fn, tn, "pull nb v1")
+    with detect_cfg(trx, cfg):
+        g, c, rep = run_pull(trx, checker, iq, typ, tsc, 4, fn, tn, f"pull nb v1 {cfg}")
     assert rep["sent"] > 0.9 * n and (c["rc"] == -2).any() and (c["pkt_len"] == 0).any() and (c["pkt_len"] == 11).any()
 
 
-def test_pull_trxd_v0_and_rach(trx, checker):
+@pytest.mark.parametrize("cfg", [(40, 3), (40, 1)])
+def test_pull_trxd_v0_and_rach(trx, checker, cfg):
     n = 3000
     rng = np.random.default_rng(32)
     b = synth.ab_bits(n, 20, rng, 0)
@@ -465,17 +541,23 @@ def test_pull_trxd_v0_and_rach(trx, checker):
     iq = to_i16(rx, 6000.0)
     fn = rng.integers(0, 2715648, n).astype(np.uint32)
     tn = rng.integers(0, 8, n).astype(np.uint8)
-    typ = np.choose(np.arange(n) % 3, [RACH, EXT_RACH, RACH]).astype(np.uint8)
+    typ = np.choose(np.arange(n) % 3, [RACH, EXT_RACH if cfg[1] == 3 else RACH, RACH]).astype(np.uint8)
     tsc = np.zeros(n, np.uint8)
-    g, c, rep = run_pull(trx, checker, iq, typ, tsc, 63, fn, tn, "pull rach v0", version=0, pkt_stride=158)
+    with detect_cfg(trx, cfg):
+        g, c, rep = run_pull(trx, checker, iq, typ, tsc, 63, fn, tn, f"pull rach v0 {cfg}", version=0, pkt_stride=158)
     assert set(np.unique(c["pkt_len"])) == {0, 158}
 
 
-def test_pull_edge_and_truncated_rows(trx, checker):
+@pytest.mark.parametrize("cfg", [(40, 3), (16, 2)])
+def test_pull_edge_and_truncated_rows(trx, checker, cfg):
     n = 2000
     rng, tsc, rx, fn, tn = pull_inputs(checker, n, 33, "edge")
+    wn = checker.modulate_gmsk_batch(synth.nb_bits(200, tsc[:200], rng))
+    rx[:200], _ = synth.impair(wn, rng, snr_db=20.0)  # GMSK bursts in 8-PSK slots: the EDGE -> TSC fall-through
     iq = to_i16(rx, 8000.0)
-    g, c, rep = run_pull(trx, checker, iq, EDGE, tsc, 4, fn, tn, "pull edge v1", pkt_stride=456)
+    with detect_cfg(trx, cfg):
+        g, c, rep = run_pull(trx, checker, iq, EDGE, tsc, 4, fn, tn, f"pull edge v1 {cfg}", pkt_stride=456)
+    assert (c["rc"] == TSC).sum() > 150
     assert (c["pkt_len"] == 455).any()
     # rows that cannot hold an 8-PSK burst: flagged, nothing emitted, nothing overrun
     out = trx.alloc_pull_results(n, 160)
@@ -487,7 +569,13 @@ def test_pull_edge_and_truncated_rows(trx, checker):
     assert ((fl & 8) != 0)[rc == 5].all() and (pl[rc == 5] == 0).all() and (out["pkt"].cpu().numpy()[rc == 5] == 0xAA).all()
 
 
-def test_pull_host_matches_device_path(trx, checker):
+@pytest.mark.parametrize("cfg", [(40, 3), (16, 1)])
+def test_pull_host_matches_device_path(trx, checker, cfg):
+    with detect_cfg(trx, cfg):
+        _pull_host_matches_device_path(trx, checker)
+
+
+def _pull_host_matches_device_path(trx, checker):
     n = 40000  # > 2 chunks of the host pipeline
     rng, tsc, rx, fn, tn = pull_inputs(checker, n, 34)
     iq = to_i16(rx, 8000.0)
