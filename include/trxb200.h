@@ -110,6 +110,14 @@ int trxb200_modulate_gmsk_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits
 int trxb200_modulate_edge_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits, int bits_stride, int n,
 				float *out, int out_stride);
 
+/* modulateBurst(bits, guard, sps, emptyPulse) outside the 4-sps Laurent case and modulateEdgeBurst(bits, sps, true)
+ * (sigProcLib.cpp:558-580,672-689,938-979) - the forms the reference uses to build its correlation references and to
+ * transmit at 1 sps.  mode 0: modulateBurstBasic (sps = 1: one Gaussian pulse, GSMPulse1); mode 1: rotateBurst
+ * (emptyPulse: NRZ impulses times the GMSK rotator, sps 1 or 4); mode 2: rotateEdgeBurst (Gray-mapped 8-PSK symbols
+ * times e^{j i 3pi/8} at stride sps; guard must be 0).  Writes sps * (symbols + guard) samples per burst. */
+int trxb200_modulate_basic_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits, int bits_stride, int n, int guard, int sps,
+				 int mode, float *out, int out_stride);
+
 /* ---- detection: detectAnyBurst (sigProcLib.cpp:1926-1957) at sps = 4 for every burst b:
  *      rc[b] = detectAnyBurst(bursts[b], tsc[b], thresh, 4, type[b], max_toa[b], &ebp)
  *      amp[b] (re,im), toa[b], tsc_out[b], ci[b] = ebp fields (sigProcLib.h:113-118).
@@ -255,6 +263,10 @@ int trxb200_convolve_complex_batch(trxb200_ctx *ctx, const float *x, int x_len, 
 
 /* ---- int16 <-> float (arch/common/convert.h; SSE semantics: round-to-nearest-even + saturation) ---- */
 int trxb200_convert_float_short(trxb200_ctx *ctx, int16_t *out, const float *in, float scale, size_t len);
+/* mode 0: as above; 1: exactly what convert_float_short() of an SSE3 host returns for any length (arch/x86/convert.c:63-71:
+ * SSE for whole groups of eight, the scalar loop - C truncation - for the len % 8 tail, convert_sse_3.c:38-47);
+ * 2: base_convert_float_short (arch/common/convert_base.c:20-25: truncation, low 16 bits) */
+int trxb200_convert_float_short_mode(trxb200_ctx *ctx, int16_t *out, const float *in, float scale, size_t len, int mode);
 int trxb200_convert_short_float(trxb200_ctx *ctx, float *out, const int16_t *in, size_t len);
 
 /* ---- grgsm_vitac MLSE (grgsm_vitac.h:65-82): per burst get_norm_chan_imp_resp / get_access_imp_resp
@@ -274,6 +286,11 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
  * only.  start_in is clamped to [clamp_lo, clamp_hi].  is_ab: 0 = 148 decisions, 1 = 88. */
 int trxb200_vitac_detect_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab,
 			       const float *cir_in, const int32_t *start_in, int clamp_lo, int clamp_hi, int8_t *bits);
+/* the five-argument detect_burst_nb / detect_burst_ab (grgsm_vitac.cpp:105-116): `ss` = the Viterbi detector's start state,
+ * 0..15 (the reference indexes a 16-entry metric array with it unchecked; values outside are rejected here) */
+int trxb200_vitac_detect_ss_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab,
+				  const float *cir_in, const int32_t *start_in, int clamp_lo, int clamp_hi, int start_state,
+				  int8_t *bits);
 
 /* ---- Resampler (Resampler.h:31-61): rational p/q polyphase resampler, filt_len taps per path.
  *      rotate: in points at the first NEW input sample of each stream; `filt_len` samples of history

@@ -854,6 +854,28 @@ void orc_convert_float_short(short *out, const float *in, float scale, int len)
 	}
 }
 
+/* base_convert_float_short (arch/common/convert_base.c:20-25): `short = float * scale`, which gcc compiles for x86-64 as
+ * cvttss2si (truncation; 0x80000000 for NaN / out of int32 range) followed by keeping the low 16 bits */
+void orc_base_convert_float_short(short *out, const float *in, float scale, int len)
+{
+	for (int i = 0; i < len; i++) {
+		float v = in[i] * scale;
+		int r;
+		if (!(v == v) || v >= 2147483648.0f || v < -2147483648.0f) r = (int)0x80000000;
+		else r = (int)v;
+		out[i] = (short)(r & 0xffff);
+	}
+}
+
+/* convert_float_short as an SSE3 host dispatches it (arch/x86/convert.c:63-71, convert_sse_3.c:38-47): whole groups of
+ * eight through the SSE routine, the len % 8 tail through the scalar loop */
+void orc_convert_float_short_x86(short *out, const float *in, float scale, int len)
+{
+	const int body = len / 8 * 8;
+	orc_convert_float_short(out, in, scale, body);
+	orc_base_convert_float_short(out + body, in + body, scale, len - body);
+}
+
 void orc_convert_short_float(float *out, const short *in, int len)
 {
 	for (int i = 0; i < len; i++)

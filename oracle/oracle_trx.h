@@ -94,6 +94,8 @@ int orc_delay_vector(const ocf *in, int len, float delay, ocf *out);
 void orc_vector_slicer(float *dst, const float *src, size_t len);
 int orc_downsample_burst(const ocf *in, int blen, ocf *out /*156*/);
 void orc_convert_float_short(short *out, const float *in, float scale, int len); /* SSE semantics */
+void orc_base_convert_float_short(short *out, const float *in, float scale, int len); /* scalar: truncation, low 16 bits */
+void orc_convert_float_short_x86(short *out, const float *in, float scale, int len); /* SSE body + scalar tail (len % 8) */
 void orc_convert_short_float(float *out, const short *in, int len);
 
 /* receive chain around the hot path (oracle_pull.c): int16 slot -> TRXD uplink datagram */

@@ -292,15 +292,20 @@ static void *vworker(void *arg)
 }
 
 /* detect_burst_nb / detect_burst_ab :105-123 with a given channel estimate and start (single-threaded helper) */
-int orc_vitac_detect_batch(const float *bufs, int stride, int offset, int n, int is_ab, const float *cir, const int32_t *start,
-			   int8_t *bits)
+int orc_vitac_detect_ss_batch(const float *bufs, int stride, int offset, int n, int is_ab, const float *cir, const int32_t *start,
+			      int ss, int8_t *bits)
 {
 	vitac_setup();
 	const int nbits = is_ab ? 88 : 148;
 	for (int b = 0; b < n; b++)
 		detect_burst((const ocf *)(bufs + (size_t)b * stride * 2) + offset, (const ocf *)(cir + (size_t)b * 40), start[b],
-			     bits + (size_t)b * nbits, 3, nbits);
+			     bits + (size_t)b * nbits, ss, nbits);
 	return n;
+}
+int orc_vitac_detect_batch(const float *bufs, int stride, int offset, int n, int is_ab, const float *cir, const int32_t *start,
+			   int8_t *bits)
+{
+	return orc_vitac_detect_ss_batch(bufs, stride, offset, n, is_ab, cir, start, 3, bits);
 }
 
 int orc_vitac_batch(const float *bufs, int stride, int offset, int n, int is_ab, const uint8_t *tsc, int max_delay,

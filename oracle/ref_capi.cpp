@@ -463,6 +463,9 @@ void ref_free(void *p) { free(p); }
 
 void ref_convert_float_short(short *out, const float *in, float scale, int len) { convert_float_short(out, in, scale, len); }
 void ref_convert_short_float(float *out, const short *in, int len) { convert_short_float(out, in, len); }
+void ref_base_convert_float_short(short *out, const float *in, float scale, int len) { base_convert_float_short(out, in, scale, len); }
+/* the reference's dispatcher is what an SSE3 host runs for any length */
+void ref_convert_float_short_x86(short *out, const float *in, float scale, int len) { convert_float_short(out, in, scale, len); }
 
 /* ---- Resampler (Resampler.h:31-61) ---- */
 void *ref_resampler_create(int p, int q, int filt_len, float bw)
@@ -539,6 +542,23 @@ int ref_vitac_detect_batch(const float *bufs, int stride, int offset, int n, int
 			detect_burst_ab(in, c, start[b], (sbit_t *)bits + (size_t)b * nbits);
 		else
 			detect_burst_nb(in, c, start[b], (sbit_t *)bits + (size_t)b * nbits);
+	}
+	return n;
+}
+
+/* the five-argument forms (start state `ss`, grgsm_vitac.cpp:105-116) */
+int ref_vitac_detect_ss_batch(const float *bufs, int stride, int offset, int n, int is_ab, const float *cir, const int32_t *start,
+			      int ss, int8_t *bits)
+{
+	const int nbits = is_ab ? 88 : 148;
+	for (int b = 0; b < n; b++) {
+		const gr_complex *in = (const gr_complex *)(bufs + (size_t)b * stride * 2) + offset;
+		gr_complex c[CHAN_IMP_RESP_LENGTH * 4];
+		memcpy(c, cir + (size_t)b * 40, sizeof(c));
+		if (is_ab)
+			detect_burst_ab(in, c, start[b], (sbit_t *)bits + (size_t)b * nbits, ss);
+		else
+			detect_burst_nb(in, c, start[b], (sbit_t *)bits + (size_t)b * nbits, ss);
 	}
 	return n;
 }

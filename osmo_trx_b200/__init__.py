@@ -171,6 +171,20 @@ class Trx:
         return out
 
     # -- detection / demod --
+    def modulate_basic(self, bits, guard=0, sps=1, mode=0):
+        """modulateBurst outside the 4-sps Laurent case (sigProcLib.cpp:558-580,672-689,938-979).
+        mode 0: modulateBurstBasic (sps 1); 1: rotateBurst (emptyPulse, sps 1 or 4); 2: rotateEdgeBurst.
+        bits: uint8 [n, nbits] on device -> float32 [n, sps * (symbols + guard), 2]"""
+        _chk_dev(bits)
+        n, nbits = bits.shape
+        nsym = nbits // 3 if mode == 2 else nbits
+        out = torch.empty((n, sps * (nsym + guard), 2), dtype=torch.float32, device=bits.device)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_modulate_basic_batch(self.h, _ptr(bits), C.c_int(nbits), C.c_int(bits.stride(0)), C.c_int(n),
+                                                          C.c_int(guard), C.c_int(sps), C.c_int(mode), _ptr(out),
+                                                          C.c_int(out.stride(0) // 2 if n else 1)), "modulate_basic_batch")
+        return out
+
     def alloc_results(self, n, soft_stride=148, device=None):
         d = device or self.device
         return dict(rc=torch.zeros(n, dtype=torch.int32, device=d), amp=torch.zeros((n, 2), dtype=torch.float32, device=d),
@@ -337,12 +351,14 @@ class Trx:
                 C.c_int(length), C.c_int(n), C.c_int(int(base)))
         return rc, y
 
-    def convert_float_short(self, x, scale):
+    def convert_float_short(self, x, scale, mode=0):
+        """mode 0: SSE semantics (round to nearest even, saturate); 1: the x86 dispatcher for any length (truncating
+        scalar tail of len % 8); 2: base_convert_float_short (truncation)"""
         _chk_dev(x)
         out = torch.empty(x.numel(), dtype=torch.int16, device=x.device)
         self.use_current_stream()
-        self._check(self.lib.trxb200_convert_float_short(self.h, _ptr(out), _ptr(x), C.c_float(scale),
-                                                         C.c_size_t(x.numel())), "convert_float_short")
+        self._check(self.lib.trxb200_convert_float_short_mode(self.h, _ptr(out), _ptr(x), C.c_float(scale),
+                                                              C.c_size_t(x.numel()), C.c_int(mode)), "convert_float_short")
         return out
 
     def convert_short_float(self, x):
@@ -370,15 +386,16 @@ class Trx:
         return r
 
 
-def _vitac_detect(self, bufs, offset, cir, start, is_ab=False, clamp=(-39, 39)):
-    """detect_burst_nb / detect_burst_ab with the caller's channel estimate: cir float32 [n, 20, 2], start int32 [n]."""
+def _vitac_detect(self, bufs, offset, cir, start, is_ab=False, clamp=(-39, 39), ss=3):
+    """detect_burst_nb / detect_burst_ab with the caller's channel estimate: cir float32 [n, 20, 2], start int32 [n];
+    ss: the Viterbi detector's start state (the five-argument forms of the reference)."""
     _chk_dev(bufs, cir, start)
     n = bufs.shape[0]
     bits = torch.zeros((n, 88 if is_ab else 148), dtype=torch.int8, device=bufs.device)
     self.use_current_stream()
-    self._check(self.lib.trxb200_vitac_detect_batch(self.h, _ptr(bufs), C.c_int(bufs.stride(0) // 2), C.c_int(offset), C.c_int(n),
-                                                    C.c_int(int(is_ab)), _ptr(cir), _ptr(start), C.c_int(clamp[0]), C.c_int(clamp[1]),
-                                                    _ptr(bits)), "vitac_detect_batch")
+    self._check(self.lib.trxb200_vitac_detect_ss_batch(self.h, _ptr(bufs), C.c_int(bufs.stride(0) // 2), C.c_int(offset), C.c_int(n),
+                                                       C.c_int(int(is_ab)), _ptr(cir), _ptr(start), C.c_int(clamp[0]),
+                                                       C.c_int(clamp[1]), C.c_int(ss), _ptr(bits)), "vitac_detect_ss_batch")
     return bits
 
 

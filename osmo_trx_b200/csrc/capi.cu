@@ -199,6 +199,8 @@ void fill_const_tables(const HostTables &t, ConstTables &c)
 	std::memcpy(c.c0_inv, t.c0_inv, sizeof(c.c0_inv));
 	for (int i = 0; i < 157; i++) c.rrot1[i] = make_float2(t.rrot1[i].r, t.rrot1[i].i);
 	for (int i = 0; i < 625; i++) c.rot4[i] = make_float2(t.rot4[i].r, t.rot4[i].i);
+	for (int i = 0; i < 157; i++) c.rot1[i] = make_float2(t.rot1[i].r, t.rot1[i].i);
+	std::memcpy(c.pulse1_c0, t.pulse1_c0, sizeof(c.pulse1_c0));
 	for (int i = 0; i < 8; i++) c.psk8[i] = make_float2(t.psk8[i].r, t.psk8[i].i);
 	for (int i = 0; i < 156; i++) c.edge_mod_rot[i] = make_float2(t.edge_mod_rot[i].r, t.edge_mod_rot[i].i);
 	for (int i = 0; i < 16; i++) c.edge_derot[i] = make_float2(t.edge_derot[i].r, t.edge_derot[i].i);
@@ -560,6 +562,26 @@ int trxb200_modulate_edge_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits
 	if (n == 0) return TRXB200_OK;
 	modulate_edge_kernel<<<grid_for(ctx, n, kModWarps, 8), kModWarps * 32, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride, ctx->d_mod_tab, -0.0f);
 	return post_launch(ctx, "modulate_edge_kernel");
+}
+
+// modulateBurst(bits, guard, sps, emptyPulse) outside the 4-sps Laurent case and modulateEdgeBurst(bits, sps, true)
+// (sigProcLib.cpp:558-580,672-689,938-979): mode 0 modulateBurstBasic (sps 1), 1 rotateBurst (sps 1 or 4), 2 rotateEdgeBurst
+int trxb200_modulate_basic_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits, int bits_stride, int n, int guard, int sps,
+				 int mode, float *out, int out_stride)
+{
+	DevGuard dg(ctx ? ctx->device : -1);
+	if (!ctx || !bits || !out || n < 0 || nbits < 1 || bits_stride < nbits || guard < 0 || (sps != 1 && sps != 4) || mode < 0 || mode > 2)
+		return fail(ctx, TRXB200_EINVAL, "modulate_basic: bad argument");
+	if (mode == 0 && sps != 1) return fail(ctx, TRXB200_EINVAL, "modulate_basic: the single-pulse shaper exists at 1 sps only");
+	if (mode == 2 && (nbits % 3 || guard)) return fail(ctx, TRXB200_EINVAL, "modulate_basic: 8-PSK bits come in threes, no guard period");
+	const int nsym = mode == 2 ? nbits / 3 : nbits;
+	const int olen = sps * (nsym + guard);
+	// the rotators cover 157 symbols (1 sps) / 625 samples (4 sps); the 8-PSK rotator 156 symbols
+	if (olen > out_stride || (mode != 2 && olen > (sps == 1 ? 157 : 625)) || (mode == 2 && nsym > 156))
+		return fail(ctx, TRXB200_EINVAL, "modulate_basic: burst longer than the rotation tables / output row");
+	if (n == 0) return TRXB200_OK;
+	modulate_basic_kernel<<<grid_for(ctx, (long)n * 32, 256, 8), 256, 0, ctx->stream>>>(bits, nbits, bits_stride, n, guard, sps, mode, out, out_stride);
+	return post_launch(ctx, "modulate_basic_kernel");
 }
 
 /* ---------------- detection / demodulation ---------------- */
@@ -1326,14 +1348,20 @@ int trxb200_convolve_complex_batch(trxb200_ctx *ctx, const float *x, int x_len, 
 	return conv_common(ctx, x, x_len, x_stride, h, h_len, y, y_len, y_stride, start, len, n, base ? 3 : 1, base != 0);
 }
 
-int trxb200_convert_float_short(trxb200_ctx *ctx, int16_t *out, const float *in, float scale, size_t len)
+int trxb200_convert_float_short_mode(trxb200_ctx *ctx, int16_t *out, const float *in, float scale, size_t len, int mode)
 {
 	DevGuard dg(ctx ? ctx->device : -1);
-	if (!ctx || !out || !in) return fail(ctx, TRXB200_EINVAL, "convert: bad argument");
+	if (!ctx || !out || !in || mode < 0 || mode > 2) return fail(ctx, TRXB200_EINVAL, "convert: bad argument");
 	if (len == 0) return TRXB200_OK;
+	if (mode == 1 && !(len & 7)) mode = 0;
 	const int vec = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(in)) & 15) == 0;
-	convert_float_short_kernel<<<grid_for(ctx, (long)len, 256 * 8, 8), 256, 0, ctx->stream>>>(out, in, scale, len, vec);
+	convert_float_short_kernel<<<grid_for(ctx, (long)len, 256 * 8, 8), 256, 0, ctx->stream>>>(out, in, scale, len, vec, mode);
 	return post_launch(ctx, "convert_float_short_kernel");
+}
+
+int trxb200_convert_float_short(trxb200_ctx *ctx, int16_t *out, const float *in, float scale, size_t len)
+{
+	return trxb200_convert_float_short_mode(ctx, out, in, scale, len, 0);
 }
 
 int trxb200_convert_short_float(trxb200_ctx *ctx, float *out, const int16_t *in, size_t len)

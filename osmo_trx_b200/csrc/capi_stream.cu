@@ -57,9 +57,16 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 int trxb200_vitac_detect_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab, const float *cir_in,
 			       const int32_t *start_in, int clamp_lo, int clamp_hi, int8_t *bits)
 {
+	return trxb200_vitac_detect_ss_batch(ctx, bufs, stride, offset, n, is_ab, cir_in, start_in, clamp_lo, clamp_hi, 3, bits);
+}
+
+int trxb200_vitac_detect_ss_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab, const float *cir_in,
+				  const int32_t *start_in, int clamp_lo, int clamp_hi, int start_state, int8_t *bits)
+{
 	DevGuard dg(ctx ? ctx->device : -1);
 	if (!ctx) return TRXB200_EINVAL;
-	if (!bufs || !bits || !cir_in || !start_in || n < 0 || is_ab < 0 || is_ab > 1 || clamp_lo > clamp_hi)
+	if (!bufs || !bits || !cir_in || !start_in || n < 0 || is_ab < 0 || is_ab > 1 || clamp_lo > clamp_hi || start_state < 0 ||
+	    start_state > 15)
 		return fail(ctx, TRXB200_EINVAL, "vitac_detect: bad argument");
 	const int N = is_ab ? 88 : 148;
 	if (offset + clamp_lo < 0 || offset + clamp_hi + 4 * N > stride)
@@ -68,7 +75,7 @@ int trxb200_vitac_detect_batch(trxb200_ctx *ctx, const float *bufs, int stride, 
 	VitacParams p;
 	p.bufs = bufs; p.stride = stride; p.offset = offset; p.n = n; p.is_ab = is_ab; p.tsc = nullptr; p.max_delay = 0;
 	p.clamp_lo = clamp_lo; p.clamp_hi = clamp_hi; p.bits = bits; p.start = nullptr; p.corr_max = nullptr; p.cir = nullptr;
-	p.cir_in = cir_in; p.start_in = start_in;
+	p.cir_in = cir_in; p.start_in = start_in; p.start_state = start_state;
 	p.nwin_max = 20; // cb only holds the 20 taps
 	p.lo = clamp_lo;
 	p.range = clamp_hi + 4 * N - clamp_lo;

@@ -39,6 +39,8 @@ struct ConstTables {
 	float2 vitac_access[41];
 	float2 vitac_sch[64];
 	float comp0[65][2][36]; // untruncated composite demod filters, shifted by e: comp0[f][e][u] = comp[f][0][u - e]
+	float2 rot1[160];	// e^{+j*pi*n/2}, the 1-sps GMSK rotator (GMSKRotation1, sigProcLib.cpp:191-216)
+	float pulse1_c0[4];	// GSMPulse1->c0 (:523-532)
 };
 
 // layout of the modulator table block kept in global memory (indexed per lane, so not __constant__)

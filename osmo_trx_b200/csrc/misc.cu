@@ -206,11 +206,27 @@ __device__ __forceinline__ unsigned f2s2(float a, float b, float scale)
 	return ((unsigned)f2s1(a, scale) & 0xffffu) | ((unsigned)f2s1(b, scale) << 16);
 }
 
+// base_convert_float_short (arch/common/convert_base.c:20-25): `short = float * scale` as gcc compiles it for x86-64 -
+// cvttss2si (truncation; 0x80000000 for NaN and values outside int32), low 16 bits kept
+__device__ __forceinline__ int f2s1_trunc(float x, float scale)
+{
+	const float v = fm(x, scale);
+	if (!(v == v) || v >= 2147483648.0f || v < -2147483648.0f) return 0;
+	return (int)(short)(__float2int_rz(v) & 0xffff);
+}
+
 // vec: both pointers 16-byte aligned -> eight values per work item (two 16-byte loads, one 16-byte store)
+// mode 0: SSE semantics for every element; 1: the x86 dispatcher of convert_float_short (arch/x86/convert.c:63-71,
+// convert_sse_3.c:38-47): SSE for whole groups of eight, the scalar truncating loop for the len % 8 tail; 2: scalar everywhere
 __global__ void __launch_bounds__(256)
-convert_float_short_kernel(int16_t *__restrict__ out, const float *__restrict__ in, float scale, size_t len, int vec)
+convert_float_short_kernel(int16_t *__restrict__ out, const float *__restrict__ in, float scale, size_t len, int vec, int mode)
 {
 	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+	if (mode) {
+		const size_t body = mode == 1 ? (len & ~(size_t)7) : 0;
+		for (size_t i = tid; i < len; i += nth) out[i] = (int16_t)(i < body ? f2s1(in[i], scale) : f2s1_trunc(in[i], scale));
+		return;
+	}
 	if (!vec) {
 		for (size_t i = tid; i < len; i += nth) out[i] = (int16_t)f2s1(in[i], scale);
 		return;

@@ -152,4 +152,56 @@ modulate_edge_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_strid
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// modulate_basic_kernel — the modulator forms the reference uses outside the 4-sps transmit path: building its
+// correlation references at setup (sigProcLib.cpp:1227-1465) and transmitting at 1 sps.  One warp per burst, lanes =
+// output samples; exact float32 order of the reference (no contraction).
+//   mode 0  modulateBurstBasic, sps = 1 (:938-967): NRZ bits x GMSKRotation1 (complex x real), then the 4-tap GSMPulse1
+//           through sse_conv_real4 (START_ONLY: y[i] = sum_k x[i-3+k] h[k], zero head-room; (L0+L1)+(L2+L3), L_k = one product)
+//   mode 1  rotateBurst (:558-580): NRZ impulses at stride sps x the rotator (complex x complex), through the one-tap
+//           "empty" pulse (base_convolve_real: 0 + x * 1)
+//   mode 2  rotateEdgeBurst (:672-689): Gray-mapped 8-PSK symbols x e^{j i 3 pi / 8} at stride sps, zeros between
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+modulate_basic_kernel(const uint8_t *__restrict__ bits, int nbits, int bits_stride, int n, int guard, int sps, int mode,
+		      float *__restrict__ out, int out_stride)
+{
+	const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+	const int nsym = mode == 2 ? nbits / 3 : nbits;
+	const int olen = sps * (nsym + guard);
+	for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n; b += gridDim.x * wpb) {
+		const uint8_t *bb = bits + (size_t)b * bits_stride;
+		float2 *o = reinterpret_cast<float2 *>(out) + (size_t)b * out_stride;
+		for (int i = lane; i < olen; i += 32) {
+			float2 y = make_float2(0.0f, 0.0f);
+			if (mode == 0) {
+				float lr[4], li[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const int m = i - 3 + k;
+					float2 x = make_float2(0.0f, 0.0f);
+					if (m >= 0 && m < nbits) {
+						const float sgn = (float)(2.0 * (double)(bb[m] & 1) - 1.0);
+						x = make_float2(fm(c_tab.rot1[m].x, sgn), fm(c_tab.rot1[m].y, sgn));
+					}
+					lr[k] = fm(x.x, c_tab.pulse1_c0[k]);
+					li[k] = fm(x.y, c_tab.pulse1_c0[k]);
+				}
+				y = make_float2(fa(fa(lr[0], lr[1]), fa(lr[2], lr[3])), fa(fa(li[0], li[1]), fa(li[2], li[3])));
+			} else if (i % sps == 0 && i / sps < nsym) {
+				const int m = i / sps;
+				if (mode == 1) {
+					const float2 sgn = make_float2((float)(2.0 * (double)(bb[m] & 1) - 1.0), 0.0f);
+					const float2 x = cmul_exact(sps == 1 ? c_tab.rot1[i] : c_tab.rot4[i], sgn);
+					y = make_float2(fa(0.0f, fm(x.x, 1.0f)), fa(0.0f, fm(x.y, 1.0f)));
+				} else {
+					const unsigned idx = (bb[3 * m] & 1u) | ((bb[3 * m + 1] & 1u) << 1) | ((bb[3 * m + 2] & 1u) << 2);
+					y = cmul_exact(c_tab.psk8[idx], c_tab.edge_mod_rot[m]);
+				}
+			}
+			o[i] = y;
+		}
+	}
+}
+
 } // namespace trxb200

@@ -29,6 +29,7 @@ struct VitacParams {
 	int nwin_max;
 	const float *cir_in;	  // complex[n][20] caller's channel estimates, or null: estimate here (get_*_imp_resp)
 	const int32_t *start_in; // burst start per burst when cir_in is given
+	int start_state = 3;	  // viterbi_detector's start state (detect_burst_* default 3, grgsm_vitac.cpp:114-121)
 	int lo, range, pitch; // staged part of each row: samples [lo, lo + range) relative to the burst; plane pitch of the window
 };
 
@@ -234,7 +235,7 @@ vitac_kernel(VitacParams p)
 			const float *ic = inc + h * 8;
 			const float i1I = odd ? ic[Ap] : -ic[Ap], i2I = odd ? -ic[7 - Ap] : ic[7 - Ap];
 			const float i1R = odd ? ic[7 - pp] : -ic[7 - pp], i2R = odd ? -ic[pp] : ic[pp];
-			float pm = (s == 3) ? 0.0f : (float)(-10e30);
+			float pm = (s == p.start_state) ? 0.0f : (float)(-10e30);
 			const int src1 = (h << 4) + pp, src2 = src1 + 8;
 			const float2 *f2 = reinterpret_cast<const float2 *>(filt + h * 160);
 			// two trellis steps per iteration (N is even): the imaginary step, then the real one

@@ -4,8 +4,15 @@
 //   host_demo mod  in.bin out.bin   modulateBurst / modulateEdgeBurst per bit vector
 //   host_demo conv in.bin out.bin   convolve_real / convolve_complex / base_* single calls
 //   host_demo vit  in.bin out.bin   get_norm_chan_imp_resp + detect_burst_nb per burst
+//   host_demo misc in.bin out.bin   a list of single calls: Resampler / Channelizer / Synthesis objects, scaleVector,
+//                                   delayVector, energyDetect, vectorSlicer, the filler-burst generators, modulateBurst at
+//                                   1 sps / with emptyPulse, convert_*
 #include "include/sigProcLib.h"
 #include "include/convolve.h"
+#include "include/convert.h"
+#include "include/Resampler.h"
+#include "include/Channelizer.h"
+#include "include/Synthesis.h"
 #include "include/grgsm_vitac.h"
 #include <cstdio>
 #include <cstring>
@@ -102,6 +109,134 @@ int main(int argc, char **argv)
 			wr(fo, &s32, 4);
 			wr(fo, &cmax, 4);
 			wr(fo, bits, 148);
+		}
+	} else if (mode == "misc") {
+		// n operations, each: int32 op, a, b, c, d + payload; every result is written as int32 count + payload
+		auto put_cf = [&](const float *p, size_t ncf) { int32_t c = (int32_t)ncf; wr(fo, &c, 4); wr(fo, p, ncf * 8); };
+		for (int k = 0; k < n; k++) {
+			int32_t h[5];
+			if (!rd(fi, h, 20)) return 2;
+			switch (h[0]) {
+			case 1: { // Resampler(p = a, q = b).rotate(in_len = c -> out_len = d); 16 samples of history precede `in`
+				std::vector<float> x(2 * (size_t)(16 + h[3])), y(2 * (size_t)h[4]);
+				if (!rd(fi, x.data(), x.size() * 4)) return 2;
+				Resampler r((size_t)h[1], (size_t)h[2]);
+				if (!r.init()) return 4;
+				if (r.rotate(x.data() + 32, (size_t)h[3], y.data(), (size_t)h[4]) != h[4]) return 4;
+				put_cf(y.data(), (size_t)h[4]);
+				break;
+			}
+			case 2: { // Channelizer(m = a, blockLen = b): c blocks through rotate(), outputBuffer(chan) after each
+				const size_t m = (size_t)h[1], bl = (size_t)h[2];
+				Channelizer ch(m, bl);
+				if (!ch.init() || ch.inputLen() != m * bl || ch.outputLen() != bl) return 4;
+				std::vector<float> x(2 * m * bl);
+				for (int blk = 0; blk < h[3]; blk++) {
+					if (!rd(fi, x.data(), x.size() * 4)) return 2;
+					if (!ch.rotate(x.data(), m * bl)) return 4;
+					for (size_t c = 0; c < m; c++) put_cf(ch.outputBuffer(c), bl);
+				}
+				if (ch.rotate(x.data(), m * bl - 1)) return 5; // length mismatch is refused (Channelizer.cpp:79-82)
+				break;
+			}
+			case 3: { // Synthesis(m = a, blockLen = b): c blocks; inputBuffer(chan) filled, rotate() out
+				const size_t m = (size_t)h[1], bl = (size_t)h[2];
+				Synthesis sy(m, bl);
+				if (!sy.init() || sy.inputLen() != bl || sy.outputLen() != m * bl) return 4;
+				std::vector<float> y(2 * m * bl);
+				for (int blk = 0; blk < h[3]; blk++) {
+					for (size_t c = 0; c < m; c++)
+						if (!rd(fi, sy.inputBuffer(c), bl * 8)) return 2;
+					if (blk == 1) sy.resetBuffer(0); // an inactive channel (radioInterfaceMulti.cpp:329-333)
+					if (!sy.rotate(y.data(), m * bl)) return 4;
+					put_cf(y.data(), m * bl);
+				}
+				break;
+			}
+			case 4: { // scaleVector(x[len = a], scale)
+				float sc[2];
+				signalVector x((size_t)h[1]);
+				if (!rd(fi, sc, 8) || !rd(fi, x.begin(), (size_t)h[1] * 8)) return 2;
+				scaleVector(x, complex(sc[0], sc[1]));
+				put_cf((const float *)x.begin(), x.size());
+				break;
+			}
+			case 5: { // delayVector(in[len = a], out = (b ? caller's vector : NULL), delay)
+				float d;
+				signalVector x((size_t)h[1]), own((size_t)h[1]);
+				if (!rd(fi, &d, 4) || !rd(fi, x.begin(), (size_t)h[1] * 8)) return 2;
+				signalVector *r = delayVector(&x, h[2] ? &own : nullptr, d);
+				if (!r || (h[2] && r != &own)) return 4;
+				put_cf((const float *)r->begin(), r->size());
+				if (!h[2]) delete r;
+				break;
+			}
+			case 6: { // energyDetect(x[len = a], window = b)
+				signalVector x((size_t)h[1]);
+				if (!rd(fi, x.begin(), (size_t)h[1] * 8)) return 2;
+				const float e = energyDetect(x, (unsigned)h[2]);
+				int32_t one = 1;
+				wr(fo, &one, 4);
+				wr(fo, &e, 4);
+				wr(fo, &e, 4);
+				break;
+			}
+			case 7: { // vectorSlicer(dst, src, len = a)
+				std::vector<float> x((size_t)h[1]), y((size_t)h[1] + (h[1] & 1));
+				if (!rd(fi, x.data(), x.size() * 4)) return 2;
+				vectorSlicer(y.data(), x.data(), x.size());
+				int32_t c = (int32_t)(y.size() / 2);
+				wr(fo, &c, 4);
+				wr(fo, y.data(), y.size() * 4);
+				break;
+			}
+			case 8: { // filler-burst generators: kind a (0 normal, 1 access, 2 EDGE, 3 dummy, 4 empty), arg b, tn c, sps d
+				std::unique_ptr<signalVector> w;
+				if (h[1] == 0) w.reset(genRandNormalBurst(h[2], h[4], h[3]));
+				else if (h[1] == 1) w.reset(genRandAccessBurst(h[2], h[4], h[3]));
+				else if (h[1] == 2) w.reset(generateEdgeBurst(h[2]));
+				else if (h[1] == 3) w.reset(generateDummyBurst(h[4], h[3]));
+				else w.reset(generateEmptyBurst(h[4], h[3]));
+				if (!w) { int32_t c = -1; wr(fo, &c, 4); break; }
+				put_cf((const float *)w->begin(), w->size());
+				break;
+			}
+			case 9: { // modulateBurst(bits[a], guard = b, sps = c, emptyPulse = d & 1); d & 2: modulateEdgeBurst
+				BitVector bits((size_t)h[1]);
+				if (!rd(fi, bits.begin(), (size_t)h[1])) return 2;
+				std::unique_ptr<signalVector> w((h[4] & 2) ? modulateEdgeBurst(bits, h[3], h[4] & 1)
+								       : modulateBurst(bits, h[2], h[3], h[4] & 1));
+				if (!w) { int32_t c = -1; wr(fo, &c, 4); break; }
+				put_cf((const float *)w->begin(), w->size());
+				break;
+			}
+			case 10: { // convert: a values, mode b (0 convert_float_short, 1 base_convert_float_short, 2 convert_short_float), scale
+				float sc;
+				if (!rd(fi, &sc, 4)) return 2;
+				const size_t len = (size_t)h[1];
+				if (h[2] < 2) {
+					std::vector<float> x(len);
+					std::vector<short> y(len + (len & 1) + 2, 0);
+					if (!rd(fi, x.data(), len * 4)) return 2;
+					if (h[2] == 0) convert_float_short(y.data(), x.data(), sc, (int)len);
+					else base_convert_float_short(y.data(), x.data(), sc, (int)len);
+					int32_t c = (int32_t)len;
+					wr(fo, &c, 4);
+					wr(fo, y.data(), len * 2);
+				} else {
+					std::vector<short> x(len);
+					std::vector<float> y(len);
+					if (!rd(fi, x.data(), len * 2)) return 2;
+					convert_short_float(y.data(), x.data(), (int)len);
+					int32_t c = (int32_t)len;
+					wr(fo, &c, 4);
+					wr(fo, y.data(), len * 4);
+				}
+				break;
+			}
+			default:
+				return 2;
+			}
 		}
 	} else {
 		return 2;

@@ -7,6 +7,7 @@
 // device memory goes through trxb200_dev_alloc / trxb200_copy_*.
 #include "include/sigProcLib.h"
 #include "include/convolve.h"
+#include "include/convert.h"
 #include "include/Resampler.h"
 #include "include/Channelizer.h"
 #include "include/Synthesis.h"
@@ -133,16 +134,37 @@ void vectorSlicer(float *dest, const float *src, size_t len)
 	ok(trxb200_copy_to_host(g_ctx, dest, d, len * 4), "copy");
 }
 
-signalVector *modulateBurst(const BitVector &wBurst, int /*guardPeriodLength: ignored at 4 sps, sigProcLib.cpp:977*/, int sps,
-			    bool emptyPulse)
+// modulateBurstBasic / rotateBurst / rotateEdgeBurst (sigProcLib.cpp:558-580,672-689,938-967): mode as in
+// trxb200_modulate_basic_batch; the result has sps * (symbols + guard) samples
+static signalVector *modulate_basic(const BitVector &bits, int guard, int sps, int mode)
 {
-	if (sps != 4 || emptyPulse) return nullptr; // the 1-sps / unshaped forms are setup-time helpers of the reference
-	return modulate(wBurst, false);
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g_ctx || bits.size() == 0 || guard < 0) return nullptr;
+	const int nbits = (int)bits.size();
+	const int olen = sps * ((mode == 2 ? nbits / 3 : nbits) + guard);
+	uint8_t *db = (uint8_t *)d_in.get(nbits);
+	float *dw = (float *)d_out.get((size_t)olen * 8);
+	if (!db || !dw) return nullptr;
+	if (!ok(trxb200_copy_to_device(g_ctx, db, bits.begin(), nbits), "copy")) return nullptr;
+	if (!ok(trxb200_modulate_basic_batch(g_ctx, db, nbits, nbits, 1, guard, sps, mode, dw, olen), "modulate_basic")) return nullptr;
+	signalVector *out = new signalVector(olen);
+	if (!ok(trxb200_copy_to_host(g_ctx, out->begin(), dw, (size_t)olen * 8), "copy")) { delete out; return nullptr; }
+	return out;
+}
+
+signalVector *modulateBurst(const BitVector &wBurst, int guardPeriodLength, int sps, bool emptyPulse)
+{
+	if (emptyPulse) return (sps == 1 || sps == 4) ? modulate_basic(wBurst, guardPeriodLength, sps, 1) : nullptr; // rotateBurst
+	if (sps == 4) return modulate(wBurst, false); // Laurent; the guard argument is ignored (sigProcLib.cpp:977)
+	if (sps == 1) return modulate_basic(wBurst, guardPeriodLength, 1, 0); // modulateBurstBasic
+	return nullptr;
 }
 
 signalVector *modulateEdgeBurst(const BitVector &bits, int sps, bool emptyPulse)
 {
-	if (sps != 4 || emptyPulse || bits.size() % 3) return nullptr;
+	if (bits.size() % 3) return nullptr;
+	if (emptyPulse) return (sps == 1 || sps == 4) ? modulate_basic(bits, 0, sps, 2) : nullptr; // rotateEdgeBurst
+	if (sps != 4) return nullptr; // sigProcLib.cpp:922
 	return modulate(bits, true);
 }
 
@@ -399,6 +421,39 @@ int base_convolve_complex(const float *x, int x_len, const float *h, int h_len, 
 }
 }
 
+/* ---------------- convert.h ---------------- */
+static void convert_fs(short *out, const float *in, float scale, int len, int mode)
+{
+	if (len <= 0) return;
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g_ctx) return;
+	float *di = (float *)d_in.get((size_t)len * 4);
+	int16_t *d_o = (int16_t *)d_out.get((size_t)len * 2);
+	if (!di || !d_o) return;
+	if (!ok(trxb200_copy_to_device(g_ctx, di, in, (size_t)len * 4), "copy")) return;
+	if (!ok(trxb200_convert_float_short_mode(g_ctx, d_o, di, scale, (size_t)len, mode), "convert_float_short")) return;
+	ok(trxb200_copy_to_host(g_ctx, out, d_o, (size_t)len * 2), "copy");
+}
+static void convert_sf(float *out, const short *in, int len)
+{
+	if (len <= 0) return;
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g_ctx) return;
+	int16_t *di = (int16_t *)d_in.get((size_t)len * 2);
+	float *d_o = (float *)d_out.get((size_t)len * 4);
+	if (!di || !d_o) return;
+	if (!ok(trxb200_copy_to_device(g_ctx, di, in, (size_t)len * 2), "copy")) return;
+	if (!ok(trxb200_convert_short_float(g_ctx, d_o, di, (size_t)len), "convert_short_float")) return;
+	ok(trxb200_copy_to_host(g_ctx, out, d_o, (size_t)len * 4), "copy");
+}
+extern "C" {
+void convert_init(void) {}
+void convert_float_short(short *out, const float *in, float scale, int len) { convert_fs(out, in, scale, len, 1); }
+void base_convert_float_short(short *out, const float *in, float scale, int len) { convert_fs(out, in, scale, len, 2); }
+void convert_short_float(float *out, const short *in, int len) { convert_sf(out, in, len); }
+void base_convert_short_float(float *out, const short *in, int len) { convert_sf(out, in, len); }
+}
+
 /* ---------------- Resampler ---------------- */
 Resampler::Resampler(size_t p_, size_t q_, size_t fl) : p(p_), q(q_), filt_len(fl) {}
 Resampler::~Resampler() { if (h) trxb200_resampler_destroy(h); }
@@ -486,8 +541,22 @@ bool Synthesis::rotate(float *out, size_t oLen)
 }
 
 /* ---------------- grgsm_vitac ---------------- */
+gr_complex d_acc_training_seq[N_ACCESS_BITS];
+gr_complex d_sch_training_seq[N_SYNC_BITS];
+gr_complex d_norm_training_seq[TRAIN_SEQ_NUM][N_TRAIN_BITS];
+
 namespace {
-constexpr int kVitPad = 40, kVitRow = kVitPad + 1024 + kVitPad, kVitAvail = 625;
+constexpr int kVitPad = 40, kVitRow = kVitPad + 1024 + kVitPad;
+int g_vit_head = 0, g_vit_avail = 625; // samples the caller owns before / from `input` (vitac_input_headroom)
+
+// the device row: kVitPad zeros | caller samples | zeros; input[0] sits at sample kVitPad
+bool upload_vitac_row(const gr_complex *input, float *drow)
+{
+	if (trxb200_memset_device(g_ctx, drow, 0, (size_t)kVitRow * 8) != TRXB200_OK) return false;
+	const int head = g_vit_head < kVitPad ? g_vit_head : kVitPad;
+	const int avail = g_vit_avail < kVitRow - kVitPad ? g_vit_avail : kVitRow - kVitPad;
+	return trxb200_copy_to_device(g_ctx, drow + 2 * (kVitPad - head), input - head, (size_t)(head + avail) * 8) == TRXB200_OK;
+}
 
 // one GPU call: CIR search (+ detection with the start clamped to [lo, hi])
 bool run_vitac(const gr_complex *input, int is_ab, int tsc, int max_delay, int lo, int hi, gr_complex *cir, float *corr_max, int *start,
@@ -501,8 +570,7 @@ bool run_vitac(const gr_complex *input, int is_ab, int tsc, int max_delay, int l
 	int8_t *dbits = (int8_t *)d_c.get(160);
 	float *dres = (float *)d_b.get(8 + 20 * 8);
 	if (!drow || !dt || !dbits || !dres) return false;
-	if (trxb200_memset_device(g_ctx, drow, 0, (size_t)kVitRow * 8) != TRXB200_OK) return false;
-	if (trxb200_copy_to_device(g_ctx, drow + 2 * kVitPad, input, (size_t)kVitAvail * 8) != TRXB200_OK) return false;
+	if (!upload_vitac_row(input, drow)) return false;
 	const uint8_t t8 = (uint8_t)tsc;
 	if (trxb200_copy_to_device(g_ctx, dt, &t8, 1) != TRXB200_OK) return false;
 	lo = lo < -kVitPad ? -kVitPad : lo;
@@ -521,7 +589,28 @@ bool run_vitac(const gr_complex *input, int is_ab, int tsc, int max_delay, int l
 }
 } // namespace
 
-void initvita() {} // the reference symbol tables live in the GPU context (built in sigProcLibSetup)
+void vitac_input_headroom(int samples_before, int samples_from_input)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	g_vit_head = samples_before < 0 ? 0 : samples_before;
+	g_vit_avail = samples_from_input < 1 ? 1 : samples_from_input;
+}
+
+// the reference builds its symbol tables here (grgsm_vitac.cpp:51-80); the device copies live in the GPU context
+// (sigProcLibSetup), the exported host arrays are filled from it
+void initvita()
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g_ctx) return;
+	float buf[2 * 64];
+	for (int t = 0; t < TRAIN_SEQ_NUM; t++)
+		if (trxb200_get_table(g_ctx, "vitac_norm", t, buf, 2 * N_TRAIN_BITS) == 2 * N_TRAIN_BITS)
+			memcpy((void *)d_norm_training_seq[t], buf, sizeof(d_norm_training_seq[t]));
+	if (trxb200_get_table(g_ctx, "vitac_access", 0, buf, 2 * N_ACCESS_BITS) == 2 * N_ACCESS_BITS)
+		memcpy((void *)d_acc_training_seq, buf, sizeof(d_acc_training_seq));
+	if (trxb200_get_table(g_ctx, "vitac_sch", 0, buf, 2 * N_SYNC_BITS) == 2 * N_SYNC_BITS)
+		memcpy((void *)d_sch_training_seq, buf, sizeof(d_sch_training_seq));
+}
 
 int get_norm_chan_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp, float *corr_max, int bcc)
 {
@@ -549,7 +638,7 @@ int get_sch_chan_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp)
 // detect_burst_nb / detect_burst_ab (grgsm_vitac.cpp:105-123): matched filter + Viterbi with the CALLER's channel estimate
 // and start, whatever pointer arithmetic the caller did between the estimate and this call (ms_rx_lower.cpp:177 passes
 // &ss[start] with start 0)
-static bool run_vitac_detect(const gr_complex *input, int is_ab, const gr_complex *cir, int burst_start, sbit_t *bits)
+static bool run_vitac_detect(const gr_complex *input, int is_ab, const gr_complex *cir, int burst_start, int ss, sbit_t *bits)
 {
 	std::lock_guard<std::mutex> lk(g_mu);
 	if (!g_ctx || !cir) return false;
@@ -559,26 +648,32 @@ static bool run_vitac_detect(const gr_complex *input, int is_ab, const gr_comple
 	int32_t *dstart = (int32_t *)d_a.get(16);
 	int8_t *dbits = (int8_t *)d_c.get(160);
 	if (!drow || !dcir || !dstart || !dbits) return false;
-	if (trxb200_memset_device(g_ctx, drow, 0, (size_t)kVitRow * 8) != TRXB200_OK) return false;
-	if (trxb200_copy_to_device(g_ctx, drow + 2 * kVitPad, input, (size_t)kVitAvail * 8) != TRXB200_OK) return false;
+	if (!upload_vitac_row(input, drow)) return false;
 	if (trxb200_copy_to_device(g_ctx, dcir, cir, 20 * 8) != TRXB200_OK) return false;
 	int st = burst_start < -kVitPad ? -kVitPad : burst_start;
 	if (st > kVitRow - kVitPad - 4 * N) st = kVitRow - kVitPad - 4 * N;
 	const int32_t st32 = st;
 	if (trxb200_copy_to_device(g_ctx, dstart, &st32, 4) != TRXB200_OK) return false;
-	if (!ok(trxb200_vitac_detect_batch(g_ctx, drow, kVitRow, kVitPad, 1, is_ab, dcir, dstart, st, st, dbits), "vitac_detect_batch"))
+	if (!ok(trxb200_vitac_detect_ss_batch(g_ctx, drow, kVitRow, kVitPad, 1, is_ab, dcir, dstart, st, st, ss, dbits), "vitac_detect_batch"))
 		return false;
 	return trxb200_copy_to_host(g_ctx, bits, dbits, (size_t)N) == TRXB200_OK;
 }
 
-void detect_burst_nb(const gr_complex *input, gr_complex *chan_imp_resp, int burst_start, sbit_t *output_binary)
+void detect_burst_nb(const gr_complex *input, gr_complex *chan_imp_resp, int burst_start, sbit_t *output_binary, int ss)
 {
-	if (!run_vitac_detect(input, 0, chan_imp_resp, burst_start, output_binary))
+	if (!run_vitac_detect(input, 0, chan_imp_resp, burst_start, ss, output_binary))
 		memset(output_binary, 0, 148);
 }
-
+void detect_burst_ab(const gr_complex *input, gr_complex *chan_imp_resp, int burst_start, sbit_t *output_binary, int ss)
+{
+	if (!run_vitac_detect(input, 1, chan_imp_resp, burst_start, ss, output_binary))
+		memset(output_binary, 0, 88);
+}
+void detect_burst_nb(const gr_complex *input, gr_complex *chan_imp_resp, int burst_start, sbit_t *output_binary)
+{
+	detect_burst_nb(input, chan_imp_resp, burst_start, output_binary, 3);
+}
 void detect_burst_ab(const gr_complex *input, gr_complex *chan_imp_resp, int burst_start, sbit_t *output_binary)
 {
-	if (!run_vitac_detect(input, 1, chan_imp_resp, burst_start, output_binary))
-		memset(output_binary, 0, 88);
+	detect_burst_ab(input, chan_imp_resp, burst_start, output_binary, 3);
 }

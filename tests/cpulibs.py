@@ -170,6 +170,14 @@ class _Base:
         self.L[self.pfx + "convert_float_short"](_p(out), _p(x), C.c_float(scale), C.c_int(x.size))
         return out
 
+    def convert_float_short_mode(self, x, scale, mode):
+        """mode 1: the x86 dispatcher (SSE body, truncating tail of len % 8); 2: base_convert_float_short"""
+        x = _f32(x)
+        out = np.zeros(x.size, np.int16)
+        name = {1: "convert_float_short_x86", 2: "base_convert_float_short"}[mode]
+        self.L[self.pfx + name](_p(out), _p(x), C.c_float(scale), C.c_int(x.size))
+        return out
+
     def convert_short_float(self, x):
         x = np.ascontiguousarray(x, np.int16)
         out = np.zeros(x.size, np.float32)
@@ -285,16 +293,17 @@ class _Base:
                                            C.c_int(nthreads))
         return r
 
-    def vitac_detect(self, bufs, offset, cir, start, is_ab=False):
-        """detect_burst_nb / detect_burst_ab with a given channel estimate (cir [n,20,2]) and start per burst."""
+    def vitac_detect(self, bufs, offset, cir, start, is_ab=False, ss=3):
+        """detect_burst_nb / detect_burst_ab with a given channel estimate (cir [n,20,2]) and start per burst
+        (ss: the Viterbi detector's start state, 3 in the four-argument forms)."""
         bufs = _f32(bufs)
         cir = _f32(cir)
         n, stride = bufs.shape[0], bufs.shape[1]
         start = np.ascontiguousarray(start, np.int32)
         nb = 88 if is_ab else 148
         bits = np.zeros((n, nb), np.int8)
-        self.L[self.pfx + "vitac_detect_batch"](_p(bufs), C.c_int(stride), C.c_int(offset), C.c_int(n), C.c_int(int(is_ab)), _p(cir),
-                                                  _p(start), _p(bits))
+        self.L[self.pfx + "vitac_detect_ss_batch"](_p(bufs), C.c_int(stride), C.c_int(offset), C.c_int(n), C.c_int(int(is_ab)),
+                                                     _p(cir), _p(start), C.c_int(ss), _p(bits))
         return bits
 
     def viterbi(self, x, rhh, start_state=3):

@@ -27,6 +27,9 @@ RACH_SYNC_STR = [
     "01010100111110001000011000101111001001101",
     "11101111001001110101011000001101101110111",
 ]
+# GSM::gDummyBurst (GSMCommon.cpp:56-58): the 148-bit dummy burst of 3GPP TS 45.002 5.2.6
+DUMMY_STR = ("0001111101101110110000010100100111000001001000100000001111100011100010111000101110001010111010010100011001100111001111010011111"
+             "000100101111101010000")
 RACH_HEAD = "00111010"  # first 8 bits of GSM::gRACHBurst (GSMCommon.cpp:68)
 
 

@@ -126,6 +126,31 @@ def test_modulate_edge_exact(trx, checker):
     assert np.array_equal(out, ref)
 
 
+def test_modulate_basic_forms(trx, checker):
+    """modulateBurst outside the 4-sps Laurent case: modulateBurstBasic (sps 1), rotateBurst (emptyPulse, sps 1 and 4),
+    rotateEdgeBurst (modulateEdgeBurst with emptyPulse) - the forms sigProcLibSetup builds its correlation references
+    with (sigProcLib.cpp:558-580,672-689,938-979).  Value-exact."""
+    rng = np.random.default_rng(13)
+    for nb, guard in ((148, 8), (148, 9), (88, 68), (26, 0), (41, 3), (64, 0), (1, 0)):
+        b = rng.integers(0, 2, (6, nb)).astype(np.uint8)
+        b[0] |= 0xF0  # only bit 0 counts
+        for sps, mode, empty in ((1, 0, False), (1, 1, True), (4, 1, True)):
+            if sps * (nb + guard) > (157 if sps == 1 else 625):
+                continue
+            out = trx.modulate_basic(dev(b), guard, sps, mode).cpu().numpy()
+            for i in range(len(b)):
+                ref = checker.modulate_burst(b[i] & 1, guard, sps, empty)
+                assert out[i].shape == ref.shape and np.array_equal(out[i], ref), (nb, guard, sps, mode, i)
+    eb = synth.edge_bits(5, np.arange(5), rng)
+    for sps in (1, 4):
+        out = trx.modulate_basic(dev(eb), 0, sps, 2).cpu().numpy()
+        for i in range(5):
+            ref = checker.modulate_edge(eb[i], sps, True)
+            assert out[i].shape == ref.shape and np.array_equal(out[i], ref), (sps, i)
+    with pytest.raises(Exception):
+        trx.modulate_basic(dev(rng.integers(0, 2, (2, 148)).astype(np.uint8)), 8, 4, 0)  # no single-pulse shaper at 4 sps
+
+
 @pytest.mark.parametrize("cfg", DETECT_CFGS)
 def test_nb_detect_demod_cfg1(trx, checker, cfg):
     """BASELINE configs[0]: 10k GMSK normal bursts, TSC 0-7, sps=4, AWGN + random TOA."""
@@ -332,6 +357,12 @@ def test_helpers(trx, checker):
     v = (rng.standard_normal(4096) * 20000).astype(np.float32)
     v[:6] = [0.5, 1.5, 2.5, -0.5, -1.5, 1e12]
     assert np.array_equal(trx.convert_float_short(dev(v), 1.7).cpu().numpy(), checker.convert_float_short(v, 1.7))
+    # the x86 dispatcher for lengths that are not multiples of eight (scalar truncating tail) and the scalar routine
+    v[4090:4096] = [0.5, 1.5, -0.5, -1.5, 40000.0, -40000.0]
+    for ln in (4096, 4093, 4088, 7, 1):
+        for mode in (1, 2):
+            got = trx.convert_float_short(dev(v[:ln].copy()), 1.0, mode=mode).cpu().numpy()
+            assert np.array_equal(got, checker.convert_float_short_mode(v[:ln], 1.0, mode)), (ln, mode)
     i16 = rng.integers(-32768, 32767, 4096).astype(np.int16)
     assert np.array_equal(trx.convert_short_float(dev(i16)).cpu().numpy(), checker.convert_short_float(i16))
 
@@ -701,6 +732,12 @@ def test_vitac_detect_with_given_cir(trx, checker):
     got = trx.vitac_detect(dev(buf), 40, dev(est["cir"]), dev(start)).cpu().numpy()
     assert np.array_equal(got, want)
     assert np.array_equal(want[::2], est["bits"][::2])  # unchanged start: the one-call result
+    # the five-argument forms: other start states of the Viterbi detector
+    for ss in (0, 7, 15):
+        w2 = checker.vitac_detect(buf[:200], 40, est["cir"][:200], start[:200], ss=ss)
+        g2 = trx.vitac_detect(dev(buf[:200]), 40, dev(est["cir"][:200]), dev(start[:200]), ss=ss).cpu().numpy()
+        assert np.array_equal(g2, w2), ss
+    assert not np.array_equal(checker.vitac_detect(buf[:200], 40, est["cir"][:200], start[:200], ss=12), want[:200])
     # access bursts
     ab = synth.ab_bits(300, 5, rng, 0)
     wa = checker.modulate_gmsk_batch(ab, nthreads=8)
