@@ -22,6 +22,7 @@ def host_build():
     import osmo_trx_b200.buildlib as b
     b.build()
     subprocess.run(["make", "-s", "-C", HOST], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "refcallers"], check=True)
     return os.path.join(HOST, "host_demo")
 
 
@@ -62,7 +63,7 @@ def test_reference_callers_compile_unmodified(host_build):
                 ["gcc", "-fsyntax-only", f"-I{inc}", f"{REF_TREE}/tests/Transceiver52M/convolve_test.c"]):
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
-    # and the linked binaries the GPU tests run exist (built by osmo_trx_b200/host/Makefile, target refcallers)
+    # and the linked binaries the GPU tests run exist (built by oracle/Makefile, target refcallers)
     for b in ("burst-gen.b200", "convolve_test.b200", "burst-gen.ref"):
         assert os.path.exists(os.path.join(ROOT, "oracle", "_ref", b)), b
 
