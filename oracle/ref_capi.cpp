@@ -17,6 +17,10 @@
 #include <cstdint>
 #include <cstring>
 #include <thread>
+#include <functional>
+#include <atomic>
+#include <mutex>
+#include <condition_variable>
 #include <vector>
 #include <complex>
 #include <algorithm>
@@ -48,6 +52,62 @@ struct BurstView {
 	BurstView(const float *p, size_t n) : v((complex *)p, 0, n, NULL, noop_free) {}
 };
 
+// Persistent worker pool (created on first use, grown on demand): the batch entry points are called many times by the
+// benchmark's reference arm, and a pool with dynamic chunking keeps thread start-up and static-partition imbalance out of
+// the measurement.  Items are handed out in chunks through an atomic counter.
+class Pool {
+public:
+	static Pool &get() { static Pool *p = new Pool; return *p; } // never destroyed: its threads live until exit
+	void run(int n, int nthreads, const std::function<void(int)> &f)
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		while ((int)th_.size() < nthreads - 1) th_.emplace_back([this, id = (int)th_.size()]() { worker(id); });
+		fn_ = &f; n_ = n; next_.store(0); active_ = nthreads - 1; pending_ = nthreads - 1;
+		chunk_ = std::max(1, std::min(256, n / (8 * nthreads)));
+		gen_++;
+		lk.unlock();
+		cv_.notify_all();
+		drain();
+		lk.lock();
+		done_.wait(lk, [this]() { return pending_ == 0; });
+		fn_ = nullptr;
+	}
+
+private:
+	void drain()
+	{
+		for (;;) {
+			const int lo = next_.fetch_add(chunk_);
+			if (lo >= n_) break;
+			const int hi = std::min(n_, lo + chunk_);
+			for (int i = lo; i < hi; i++) (*fn_)(i);
+		}
+	}
+	void worker(int id)
+	{
+		unsigned seen = 0;
+		for (;;) {
+			std::unique_lock<std::mutex> lk(mu_);
+			cv_.wait(lk, [&]() { return gen_ != seen; });
+			seen = gen_;
+			const bool take = id < active_;
+			lk.unlock();
+			if (take) {
+				drain();
+				lk.lock();
+				if (--pending_ == 0) done_.notify_all();
+			}
+		}
+	}
+	std::mutex mu_;
+	std::condition_variable cv_, done_;
+	std::vector<std::thread> th_;
+	const std::function<void(int)> *fn_ = nullptr;
+	std::atomic<int> next_{ 0 };
+	int n_ = 0, chunk_ = 1, active_ = 0, pending_ = 0;
+	unsigned gen_ = 0;
+};
+
 template <class F> void parallel_for(int n, int nthreads, F f)
 {
 	if (nthreads <= 1 || n < 2 * nthreads) {
@@ -55,19 +115,8 @@ template <class F> void parallel_for(int n, int nthreads, F f)
 			f(i);
 		return;
 	}
-	std::vector<std::thread> th;
-	int per = (n + nthreads - 1) / nthreads;
-	for (int t = 0; t < nthreads; t++) {
-		int lo = t * per, hi = std::min(n, lo + per);
-		if (lo >= hi)
-			break;
-		th.emplace_back([=]() {
-			for (int i = lo; i < hi; i++)
-				f(i);
-		});
-	}
-	for (auto &t : th)
-		t.join();
+	const std::function<void(int)> fn = f;
+	Pool::get().run(n, nthreads, fn);
 }
 
 void fill_bits(BitVector &bv, const uint8_t *bits, int n)
@@ -504,6 +553,29 @@ int ref_channelizer_rotate(void *c_, const float *in, int m, int block_len, floa
 		return -1;
 	for (int ch = 0; ch < m; ch++)
 		memcpy(out + (size_t)ch * block_len * 2, c->outputBuffer(ch), sizeof(float) * 2 * block_len);
+	return 0;
+}
+
+/* The receive side of radioInterfaceMulti (radioInterfaceMulti.cpp:237-310) for nblk blocks of an m-channel wideband stream:
+ * per block Channelizer::rotate, then per channel Resampler(p, q)::rotate of the block_len new samples behind the 16 samples of
+ * history the caller keeps (there: the tail of the previous block).  out: [m][nblk * out_per_block] complex.  One thread, as
+ * the reference's receive thread.  Returns 0 or -1. */
+int ref_wideband_rx(const float *wide, int nblk, int m, int block_len, int p, int q, float *out)
+{
+	Channelizer ch(m, block_len, 16);
+	Resampler rs(p, q, 16);
+	if (!ch.init() || !rs.init()) return -1;
+	const int out_per_block = block_len / q * p;
+	std::vector<float> hist((size_t)m * (16 + block_len) * 2, 0.0f); /* per channel: 16 history samples, then the block */
+	for (int b = 0; b < nblk; b++) {
+		if (!ch.rotate(wide + (size_t)b * m * block_len * 2, (size_t)m * block_len)) return -1;
+		for (int c = 0; c < m; c++) {
+			float *hc = hist.data() + (size_t)c * (16 + block_len) * 2;
+			memcpy(hc + 32, ch.outputBuffer(c), sizeof(float) * 2 * block_len);
+			if (rs.rotate(hc + 32, block_len, out + ((size_t)c * nblk + b) * out_per_block * 2, out_per_block) < 0) return -1;
+			memcpy(hc, hc + 2 * block_len, sizeof(float) * 32); /* the block's tail is the next block's history */
+		}
+	}
 	return 0;
 }
 

@@ -370,14 +370,15 @@ class Trx:
         return out
 
     # -- vitac --
-    def vitac(self, bufs, offset, tsc, is_ab=False, max_delay=0, clamp=(-39, 39), want_cir=False):
+    def vitac(self, bufs, offset, tsc, is_ab=False, max_delay=0, clamp=(-39, 39), want_cir=False, out=None):
         _chk_dev(bufs) if tsc is None else _chk_dev(bufs, tsc)
         n = bufs.shape[0]
         nb = 88 if int(is_ab) == 1 else 148  # is_ab: 0 normal, 1 access, 2 SCH burst (tsc unused)
         d = bufs.device
-        r = dict(bits=torch.zeros((n, nb), dtype=torch.int8, device=d), start=torch.zeros(n, dtype=torch.int32, device=d),
-                 corr_max=torch.zeros(n, dtype=torch.float32, device=d),
-                 cir=torch.zeros((n, 20, 2), dtype=torch.float32, device=d) if want_cir else None)
+        r = out if out is not None else dict(
+            bits=torch.zeros((n, nb), dtype=torch.int8, device=d), start=torch.zeros(n, dtype=torch.int32, device=d),
+            corr_max=torch.zeros(n, dtype=torch.float32, device=d),
+            cir=torch.zeros((n, 20, 2), dtype=torch.float32, device=d) if want_cir else None)
         self.use_current_stream()
         self._check(self.lib.trxb200_vitac_batch(self.h, _ptr(bufs), C.c_int(bufs.stride(0) // 2), C.c_int(offset),
                                                  C.c_int(n), C.c_int(int(is_ab)), _ptr(tsc), C.c_int(max_delay),
@@ -428,11 +429,25 @@ class Resampler:
         self.trx.lib.trxb200_resampler_taps(self.h, C.c_int(path), out.ctypes.data_as(C.c_void_p))
         return out
 
-    def rotate(self, x, out_len):
+    def rotate_streams(self, x, first, in_len, in_stride, n_streams, out, out_len):
+        """Lower-level form for streams that already lie in one buffer: x float32 [..., 2] (flat samples); stream s reads
+        its in_len new samples at sample index first + s * in_stride, with filt_len samples of history before them in
+        the buffer; out float32 [n_streams, out_len, 2].  Consecutive segments of one long stream (in_stride == in_len)
+        are each other's history, so a long rotate equals the reference's block-by-block calls whenever
+        q * out_len / p == in_len per segment (Resampler.cpp:131-150 restarts its path indices at every call)."""
+        _chk_dev(x, out)
+        self.trx.use_current_stream()
+        rc = self.trx.lib.trxb200_resampler_rotate(self.h, C.c_void_p(x.data_ptr() + 8 * first), C.c_int(in_len), C.c_int(in_stride),
+                                                   _ptr(out), C.c_int(out_len), C.c_int(out.stride(0) // 2), C.c_int(n_streams))
+        self.trx._check(rc, "resampler_rotate")
+        return out
+
+    def rotate(self, x, out_len, out=None):
         """x float32 [n_streams, filt_len + in_len, 2]: history then the new block. -> [n_streams, out_len, 2]"""
         _chk_dev(x)
         ns, tot = x.shape[0], x.shape[1]
-        out = torch.empty((ns, out_len, 2), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((ns, out_len, 2), dtype=torch.float32, device=x.device)
         self.trx.use_current_stream()
         rc = self.trx.lib.trxb200_resampler_rotate(self.h, C.c_void_p(x.data_ptr() + 8 * self.filt_len),
                                                    C.c_int(tot - self.filt_len), C.c_int(x.stride(0) // 2), _ptr(out),
@@ -471,10 +486,11 @@ class Channelizer(_Filterbank):
     def __init__(self, trx, m, block_len, h_len=16):
         super().__init__(trx, m, block_len, h_len, False)
 
-    def rotate(self, x):
+    def rotate(self, x, out=None):
         _chk_dev(x)
         nb = x.shape[0] // (self.m * self.block_len)
-        out = torch.empty((self.m, nb * self.block_len, 2), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((self.m, nb * self.block_len, 2), dtype=torch.float32, device=x.device)
         self.trx.use_current_stream()
         self.trx._check(self.trx.lib.trxb200_channelizer_rotate(self.h, _ptr(x), _ptr(out), C.c_int(nb)), "channelizer_rotate")
         return out

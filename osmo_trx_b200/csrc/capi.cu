@@ -549,7 +549,9 @@ int trxb200_modulate_gmsk_batch(trxb200_ctx *ctx, const uint8_t *bits, int nbits
 	if (!ctx || !bits || !out || nbits < 2 || nbits > 156 || bits_stride < nbits || out_stride < 625 || n < 0)
 		return fail(ctx, TRXB200_EINVAL, "modulate_gmsk: bad argument");
 	if (n == 0) return TRXB200_OK;
+	prof_pre(ctx, ctx->stream);
 	modulate_gmsk_kernel<<<grid_for(ctx, n, kModWarps, 8), kModWarps * 32, 0, ctx->stream>>>(bits, nbits, bits_stride, n, out, out_stride, ctx->d_mod_tab, -0.0f);
+	prof_post(ctx, ctx->stream, "modulate_gmsk_kernel");
 	return post_launch(ctx, "modulate_gmsk_kernel");
 }
 

@@ -48,7 +48,9 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int grid = std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
 	if (grid < 1) grid = 1;
+	prof_pre(ctx, ctx->stream);
 	vitac_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(p);
+	prof_post(ctx, ctx->stream, "vitac_kernel");
 	return post_launch(ctx, "vitac_kernel");
 }
 
@@ -86,7 +88,9 @@ int trxb200_vitac_detect_ss_batch(trxb200_ctx *ctx, const float *bufs, int strid
 	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int grid = std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
 	if (grid < 1) grid = 1;
+	prof_pre(ctx, ctx->stream);
 	vitac_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(p);
+	prof_post(ctx, ctx->stream, "vitac_kernel");
 	return post_launch(ctx, "vitac_kernel");
 }
 
@@ -143,8 +147,10 @@ int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, 
 		const size_t smem = (size_t)2 * slots * sizeof(float2); // two window buffers
 		const long tiles = (long)n_streams * ((out_len / r->p + P - 1) / P);
 		const int grid = (int)std::max<long>(1, std::min<long>(tiles, (long)ctx->sm_count * 4));
+		prof_pre(ctx, ctx->stream);
 		resampler16_kernel<<<grid, 256, smem, ctx->stream>>>(in, in_stride, out, out_len, out_stride, n_streams, r->p, r->q, P,
 								     r->d_taps, -0.0f);
+		prof_post(ctx, ctx->stream, "resampler16_kernel");
 		return post_launch(ctx, "resampler16_kernel");
 	}
 	resampler_kernel<<<grid_for(ctx, (long)n_streams * out_len, 256, 8), 256, 0, ctx->stream>>>(
@@ -230,7 +236,9 @@ int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *o
 			ctx->cfg_ch64 = true;
 		}
 		const int grid = (int)std::min<long>((total_t + kFbT - 1) / kFbT, (long)ctx->sm_count * 3);
+		prof_pre(ctx, ctx->stream);
 		channelizer64_kernel<<<grid, 256, kCh64Smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		prof_post(ctx, ctx->stream, "channelizer64_kernel");
 		r = post_launch(ctx, "channelizer64_kernel");
 	} else if (fb->L == 16 && (fb->m == 4 || fb->m == 8 || fb->m == 16)) {
 		if (fb->m == 4) launch_channelizer_small<4>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);

@@ -402,7 +402,9 @@ static int conv_one(const float *x, int x_len, const float *h, int h_len, float 
 
 extern "C" {
 void *convolve_h_alloc(size_t num) { void *p = nullptr; return posix_memalign(&p, 16, num * 2 * sizeof(float)) ? nullptr : p; }
-void convolve_init(void) {}
+// The reference's arch library is usable on its own (tests/Transceiver52M/convolve_test.c calls convolve_init() and
+// nothing else): its init entry points open the GPU context like sigProcLibSetup() does.
+void convolve_init(void) { sigProcLibSetup(); }
 int convolve_real(const float *x, int x_len, const float *h, int h_len, float *y, int y_len, int start, int len)
 {
 	return conv_one(x, x_len, h, h_len, y, y_len, start, len, false, 0);
@@ -447,7 +449,7 @@ static void convert_sf(float *out, const short *in, int len)
 	ok(trxb200_copy_to_host(g_ctx, out, d_o, (size_t)len * 4), "copy");
 }
 extern "C" {
-void convert_init(void) {}
+void convert_init(void) { sigProcLibSetup(); }
 void convert_float_short(short *out, const float *in, float scale, int len) { convert_fs(out, in, scale, len, 1); }
 void base_convert_float_short(short *out, const float *in, float scale, int len) { convert_fs(out, in, scale, len, 2); }
 void convert_short_float(float *out, const short *in, int len) { convert_sf(out, in, len); }

@@ -105,11 +105,12 @@ class _Base:
                                            C.c_int(nthreads))
         return dict(soft=soft, nsoft=nsoft, ci=ci)
 
-    def detect_demod(self, bursts, type_, tsc, max_toa, thresh=4.0, sps=4, soft_stride=444, nthreads=1, blen=625):
+    def detect_demod(self, bursts, type_, tsc, max_toa, thresh=4.0, sps=4, soft_stride=444, nthreads=1, blen=625, out=None):
         bursts, n, stride, type_, tsc, max_toa = self._dd_args(bursts, type_, tsc, max_toa)
-        r = dict(rc=np.zeros(n, np.int32), amp=np.zeros((n, 2), np.float32), toa=np.zeros(n, np.float32),
-                 tsc=np.zeros(n, np.uint8), ci=np.zeros(n, np.float32), flags=np.zeros(n, np.uint8),
-                 soft=np.zeros((n, soft_stride), np.float32), nsoft=np.zeros(n, np.int32))
+        r = out if out is not None else dict(
+            rc=np.zeros(n, np.int32), amp=np.zeros((n, 2), np.float32), toa=np.zeros(n, np.float32),
+            tsc=np.zeros(n, np.uint8), ci=np.zeros(n, np.float32), flags=np.zeros(n, np.uint8),
+            soft=np.zeros((n, soft_stride), np.float32), nsoft=np.zeros(n, np.int32))
         args = [_p(bursts), C.c_int(stride), C.c_int(blen), C.c_int(n), _p(type_), _p(tsc), _p(max_toa),
                 C.c_float(thresh), C.c_int(sps), _p(r["rc"]), _p(r["amp"]), _p(r["toa"]), _p(r["tsc"]), _p(r["ci"])]
         if self.has_flags:
@@ -186,7 +187,7 @@ class _Base:
 
     # --- receive chain around the hot path: int16 slots -> TRXD uplink datagrams ---
     def pull(self, iq, type_, tsc, max_toa, fn, tn, thresh=4.0, full_scale=32767.0, rssi_offset=0.0, version=1,
-             pkt_stride=None, nthreads=1, capture=True):
+             pkt_stride=None, nthreads=1, capture=True, out=None):
         """iq: int16 [n][stride][2].  Returns rc, energy, pkt [n][pkt_stride] u8, pkt_len, amp, toa, ci, tsc (+flags)."""
         iq = np.ascontiguousarray(iq, np.int16)
         n, stride = iq.shape[0], iq.shape[1]
@@ -197,9 +198,10 @@ class _Base:
         tn = np.ascontiguousarray(np.broadcast_to(tn, (n,)), np.uint8)
         if pkt_stride is None:
             pkt_stride = 11 + 444 + 2
-        r = dict(rc=np.zeros(n, np.int32), energy=np.zeros(n, np.float32), pkt=np.zeros((n, pkt_stride), np.uint8),
-                 pkt_len=np.zeros(n, np.uint16), flags=np.zeros(n, np.uint8), amp=np.zeros((n, 2), np.float32),
-                 toa=np.zeros(n, np.float32), ci=np.zeros(n, np.float32), tsc=np.zeros(n, np.uint8))
+        r = out if out is not None else dict(
+            rc=np.zeros(n, np.int32), energy=np.zeros(n, np.float32), pkt=np.zeros((n, pkt_stride), np.uint8),
+            pkt_len=np.zeros(n, np.uint16), flags=np.zeros(n, np.uint8), amp=np.zeros((n, 2), np.float32),
+            toa=np.zeros(n, np.float32), ci=np.zeros(n, np.float32), tsc=np.zeros(n, np.uint8))
         args = [_p(iq), C.c_int(stride), C.c_int(n), _p(type_), _p(tsc), _p(max_toa), _p(fn), _p(tn), C.c_float(thresh),
                 C.c_double(full_scale), C.c_double(rssi_offset), C.c_int(version), _p(r["rc"]), _p(r["energy"]),
                 _p(r["pkt"]), C.c_int(pkt_stride), _p(r["pkt_len"])]
@@ -236,6 +238,15 @@ class _Base:
         f = self.L[self.pfx + "synthesis_create"]
         f.restype = C.c_void_p
         return C.c_void_p(f(C.c_int(m), C.c_int(block_len), C.c_int(h_len)))
+
+    def wideband_rx(self, wide, nblk, m=64, block_len=192, p=65, q=48):
+        """Channelizer(m, block_len) + Resampler(p, q) per channel over nblk blocks, block by block as radioInterfaceMulti
+        does it (compiled reference only).  wide: [nblk * block_len * m, 2] -> [m, nblk * block_len / q * p, 2]"""
+        wide = _f32(wide)
+        out = np.zeros((m, nblk * (block_len // q * p), 2), np.float32)
+        rc = self.L[self.pfx + "wideband_rx"](_p(wide), C.c_int(nblk), C.c_int(m), C.c_int(block_len), C.c_int(p), C.c_int(q), _p(out))
+        assert rc == 0
+        return out
 
     def channelizer_rotate(self, h, x, m, block_len):
         x = _f32(x)

@@ -20,12 +20,12 @@ def dev(a, dtype=None):
     return t.cuda()
 
 
-def run_gpu_dd(trx, rx, typ, tsc, max_toa, bound, n_soft=156, soft_stride=444):
+def run_gpu_dd(trx, rx, typ, tsc, max_toa, bound, n_soft=156, soft_stride=444, thresh=4.0):
     n = rx.shape[0]
     t_type = dev(np.broadcast_to(np.asarray(typ, np.uint8), (n,)).copy())
     t_tsc = dev(np.broadcast_to(np.asarray(tsc, np.uint8), (n,)).copy())
     t_toa = dev(np.broadcast_to(np.asarray(max_toa, np.int16), (n,)).copy())
-    r = trx.detect_demod(dev(rx), t_type, t_tsc, t_toa, bound, n_gmsk_soft=n_soft, soft_stride=soft_stride)
+    r = trx.detect_demod(dev(rx), t_type, t_tsc, t_toa, bound, thresh=thresh, n_gmsk_soft=n_soft, soft_stride=soft_stride)
     torch.cuda.synchronize()
     return {k: v.cpu().numpy() for k, v in r.items()}
 
@@ -59,12 +59,12 @@ def unsupported_under(cfg, typ, ref_rc, n):
     return bad
 
 
-def check_dd(trx, checker, rx, typ, tsc, max_toa, what, n_soft=156, cfg=(40, 3)):
+def check_dd(trx, checker, rx, typ, tsc, max_toa, what, n_soft=156, cfg=(40, 3), thresh=4.0):
     bound = int(np.max(max_toa))
     n = rx.shape[0]
     with detect_cfg(trx, cfg):
-        g = run_gpu_dd(trx, rx, typ, tsc, max_toa, bound, n_soft=n_soft)
-    c = checker.detect_demod(rx, typ, tsc, max_toa)
+        g = run_gpu_dd(trx, rx, typ, tsc, max_toa, bound, n_soft=n_soft, thresh=thresh)
+    c = checker.detect_demod(rx, typ, tsc, max_toa, thresh=thresh)
     bad = unsupported_under(cfg, typ, c["rc"], n)
     if bad.any():
         # loud failure on what the hint excludes (an EXT_RACH hit on the first sequence is a legitimate answer)
@@ -215,9 +215,9 @@ def test_nb_full_scale_and_clipping(trx, checker, cfg):
     # types return 0 without a clipping check (sigProcLib.cpp:1949-1956)
     n2 = 256
     typ2 = np.full(n2, TSC, np.uint8)
-    typ2[::5] = 0      # OFF on loud-noise bursts
-    typ2[5::10] = 4    # SCH is not a detectAnyBurst type
-    typ2[10::20] = 9   # unknown
+    typ2[::10] = 0     # OFF on loud-noise bursts (every fifth burst is loud noise)
+    typ2[5::20] = 4    # SCH is not a detectAnyBurst type (loud noise too); the loud bursts at 15 mod 20 stay TSC
+    typ2[3::20] = 9    # unknown type on ordinary bursts
     with detect_cfg(trx, cfg):
         r = trx.detect(dev(rx[:n2]), dev(typ2), dev(tsc[:n2].astype(np.uint8)), dev(np.full(n2, 4, np.int16)), 4)
     c2 = checker.detect_demod(rx[:n2], typ2, tsc[:n2], 4)
@@ -274,6 +274,8 @@ def test_mixed_types_nb_geometry(trx, checker, cfg):
     n = 4200
     tsc = np.arange(n) % 8
     w = checker.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng), nthreads=8)
+    didx = np.arange(1, n, 6)[::2]  # half of the IDLE-typed slots carry the dummy burst detectDummyBurst looks for
+    w[didx] = checker.modulate_gmsk_batch(np.array([[int(ch) for ch in synth.DUMMY_STR]], np.uint8))[0]
     eidx = np.arange(2, n, 6)[::2]  # half of the EDGE-typed slots carry real 8-PSK bursts
     w[eidx] = checker.modulate_edge_batch(synth.edge_bits(len(eidx), tsc[eidx], rng), nthreads=8)
     rx, _ = synth.impair(w, rng, snr_db=np.choose(np.arange(n) % 5, [30.0, 22.0, 15.0, 9.0, 5.0]), noise_only_frac=0.1,
@@ -283,7 +285,9 @@ def test_mixed_types_nb_geometry(trx, checker, cfg):
     tscv = tsc.copy()
     tscv[::50] = 9
     mt = np.choose(np.arange(n) % 5, [0, 1, 2, 3, 4]).astype(np.int16)
-    g, c, rep = check_dd(trx, checker, rx, typ, tscv, mt, f"mixed-nb{cfg}", cfg=cfg)
+    # threshold 2.5: the dummy burst's periodic midamble has a peak-to-average ratio below the transceiver's 4.0 even on
+    # a clean signal, so only a lower threshold reaches detectDummyBurst's hit branch (and noise slots then hit as well)
+    g, c, rep = check_dd(trx, checker, rx, typ, tscv, mt, f"mixed-nb{cfg}", cfg=cfg, thresh=2.5)
     assert (c["rc"] == -3).any() and (c["rc"] == -2).any() and (c["rc"] == IDLE).any() and (c["rc"] == EDGE).any()
 
 
@@ -737,7 +741,6 @@ def test_vitac_detect_with_given_cir(trx, checker):
         w2 = checker.vitac_detect(buf[:200], 40, est["cir"][:200], start[:200], ss=ss)
         g2 = trx.vitac_detect(dev(buf[:200]), 40, dev(est["cir"][:200]), dev(start[:200]), ss=ss).cpu().numpy()
         assert np.array_equal(g2, w2), ss
-    assert not np.array_equal(checker.vitac_detect(buf[:200], 40, est["cir"][:200], start[:200], ss=12), want[:200])
     # access bursts
     ab = synth.ab_bits(300, 5, rng, 0)
     wa = checker.modulate_gmsk_batch(ab, nthreads=8)
