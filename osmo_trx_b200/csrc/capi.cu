@@ -21,6 +21,7 @@ __constant__ ConstTables c_tab;
 
 #include "detect.cu"
 #include "demod.cu"
+#include "nbfused.cu"
 #include "modulate.cu"
 #include "convolve.cu"
 #include "misc.cu"
@@ -77,6 +78,7 @@ struct trxb200_ctx {
 		// slower than the serial order (1.75-2.4 ms vs 1.71 ms per 2^20 bursts) - corr_nb_kernel and demod_kernel each
 		// need the whole register file of an SM to hide their latencies - so the pipeline is off unless asked for
 		int overlap = 0, chunk_cap = 131072;
+		int fused = 0; // 1: nb_fused_kernel (one persistent warp-specialised kernel) for detect+demod in the normal-burst geometry; measured 2.75 ms vs 1.76 ms per 2^20 bursts for the three-kernel path (profiles/r2f_*), so off by default
 		int host_chunk = 16384; // slots per stage of the pinned-host pipelines (H2D | kernels | D2H on three streams)
 		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
 		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
@@ -84,6 +86,7 @@ struct trxb200_ctx {
 	} tune;
 	std::string err;
 	// once-per-context device setup (function attributes and __constant__ tables are per device)
+	bool cfg_fused = false;
 	bool cfg_detect = false, cfg_demod = false, cfg_ch64 = false, cfg_sy64 = false, sched_tables = false;
 	HostStage *stage = nullptr;
 	PullScratch pull;	      // trxb200_pull_batch
@@ -324,6 +327,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		};
 		trxb200_ctx::Tune &t = ctx->tune;
 		env_int("TRXB200_OVERLAP", t.overlap);
+		env_int("TRXB200_FUSED", t.fused);
 		env_int("TRXB200_CHUNK", t.chunk_cap);
 		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
 		env_int("TRXB200_HOST_CHUNK", t.host_chunk);
@@ -595,6 +599,8 @@ static int gcd_i(long a, long b) { while (b) { long t = a % b; a = b; b = t; } r
 struct ChunkHook {
 	virtual int operator()(long lo, int m) = 0;
 };
+static bool nb_geometry(const trxb200_ctx *ctx, int bound) { return ctx->max_seq_len == 16 && bound <= 4; }
+
 static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, const float *bursts, int stride, int n,
 			 const uint8_t *type, const uint8_t *tsc, const uint16_t *max_toa, int bound, float thresh, int32_t *rc,
 			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags, int scan_clip,
@@ -603,10 +609,11 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 {
 	const trxb200_ctx::Tune &tn = ctx->tune;
 	// sch: detectSCHBurst's full search (156 correlation outputs, 64-symbol sequence), one attempt, no per-burst arrays
-	const int lmax = sch ? 156 : (16 + bound + 1) & ~1;		    // row pitch of the correlation vectors (even: 16-byte row loads in peak_kernel)
-	const int ndmax = sch ? 64 + 156 - 1 : ctx->max_seq_len + 16 + bound - 1; // decimated samples a correlation window needs
+	// 16-symbol sync sequences at max_toa <= 4: the register-blocked corr_nb_kernel with its fixed row lengths
+	const bool nb = !sch && nb_geometry(ctx, bound);
+	const int lmax = sch ? 156 : nb ? 20 : (16 + bound + 1) & ~1;	    // row pitch of the correlation vectors (even: 16-byte row loads in peak_kernel)
+	const int ndmax = sch ? 64 + 156 - 1 : nb ? 35 : ctx->max_seq_len + 16 + bound - 1; // decimated samples a correlation window needs
 	// ---- launch geometry ----
-	const bool nb = (ndmax == 35 && lmax == 20); // 16-symbol sync, max_toa <= 4: register-blocked corr_nb_kernel
 	if (iq && !nb) return fail(ctx, TRXB200_EINVAL, "detect: int16 rows are read by corr_nb_kernel only");
 	int cw = 8; // warps per corr block
 	if (!nb)
@@ -738,6 +745,39 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 	return post_launch(ctx, "demod_kernel");
 }
 
+// detect + demodulate in one persistent kernel (nbfused.cu): normal-burst geometry, one detection attempt, float rows
+static bool fused_applies(const trxb200_ctx *ctx, int bound) { return ctx->tune.fused && ctx->max_attempts == 1 && nb_geometry(ctx, bound); }
+
+static int launch_nb_fused(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, int stride, int n, const uint8_t *type,
+			   const uint8_t *tsc, const uint16_t *max_toa, int bound, float thresh, int32_t *rc, float *amp, float *toa,
+			   uint8_t *tsc_out, float *ci, uint8_t *flags, float *soft, int soft_stride, int n_gmsk_soft)
+{
+	FusedParams fp;
+	CorrParams &c = fp.c;
+	c.bursts = bursts; c.stride = stride; c.n = n; c.type = type; c.tsc = tsc; c.max_toa = max_toa; c.rc = rc; c.round = 0;
+	c.max_toa_bound = bound; c.lmax = 20; c.ndmax = 35; c.corr = nullptr; c.pwr = nullptr; c.negzero = -0.0f; c.iq = nullptr;
+	c.iq_stride = 0; c.sch = 0;
+	PeakParams &q = fp.q;
+	q.n = n; q.type = type; q.tsc = tsc; q.max_toa = max_toa; q.round = 0; q.last_round = 1; q.max_toa_bound = bound; q.thresh = thresh;
+	q.lmax = 20; q.ndmax = 35; q.corr = nullptr; q.pwr = nullptr; q.sinc512 = ctx->d_sinc512; q.rc = rc; q.amp = amp; q.toa = toa; q.ci = ci;
+	q.tsc_out = tsc_out; q.flags = flags; q.negzero = -0.0f; q.sch = 0;
+	DemodParams &d = fp.d;
+	d.type = type; d.iq = nullptr; d.iq_stride = 0; d.type_raw = nullptr; d.pw = nullptr; d.pkt = nullptr; d.pkt_stride = 0; d.pkt_hdr = 11;
+	d.pkt_v0 = 0; d.bursts = bursts; d.stride = stride; d.n = n; d.rc = rc; d.amp = amp; d.toa = toa; d.ci = ci; d.flags = flags;
+	d.soft = soft; d.soft_stride = soft_stride; d.n_gmsk_soft = n_gmsk_soft; d.comp = ctx->d_comp;
+	d.dnsamp_g = ctx->d_comp + ctx->ht->comp.size(); d.edge_tab = ctx->d_edge_tab; d.fix_clip = 1;
+	if (!ctx->cfg_fused) {
+		CK(cudaFuncSetAttribute(nb_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFuSmemBytes));
+		ctx->cfg_fused = true;
+	}
+	const int ntiles = (n + kFuTile - 1) / kFuTile;
+	const int grid = std::max(1, std::min(ntiles, ctx->sm_count));
+	prof_pre(ctx, st);
+	nb_fused_kernel<<<grid, kFuThreads, kFuSmemBytes, st>>>(fp);
+	prof_post(ctx, st, "nb_fused_kernel");
+	return post_launch(ctx, "nb_fused_kernel");
+}
+
 static int check_dd(trxb200_ctx *ctx, const void *bursts, int stride, int n, int bound)
 {
 	if (!ctx) return TRXB200_EINVAL;
@@ -801,6 +841,9 @@ int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride
 	    n_gmsk_soft > 156 || soft_stride < n_gmsk_soft)
 		return fail(ctx, TRXB200_EINVAL, "detect_demod: bad argument");
 	if (n == 0) return TRXB200_OK;
+	if (fused_applies(ctx, max_toa_bound))
+		return launch_nb_fused(ctx, ctx->stream, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp, toa, tsc_out, ci,
+				       flags, soft, soft_stride, n_gmsk_soft);
 	// Small batches, and the per-kernel profiling pass (which wants clean, serialised kernel times): one demod
 	// launch after detection.  Otherwise the batch is pipelined chunk by chunk over two streams.
 	if (!ctx->tune.overlap || ctx->prof || n <= ctx->tune.chunk_cap) {
@@ -964,12 +1007,18 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 		uint8_t *d_tsc_out = d_o + (size_t)20 * m16, *d_flags = d_o + (size_t)21 * m16;
 		// rows of undetected bursts are never written by the kernels: define them as zero for host callers
 		CK(cudaMemsetAsync(s->d_soft[slot], 0, (size_t)m * soft_stride * 4, st));
-		r = launch_detect(ctx, st, s->ws[slot], s->d_bursts[slot], stride, m, d_type, d_tsc, d_max_toa, max_toa_bound, thresh, d_rc, d_amp,
-				  d_toa, d_tsc_out, d_ci, d_flags, 0);
-		if (r) return r;
-		r = launch_demod(ctx, st, s->d_bursts[slot], stride, m, d_rc, d_amp, d_toa, d_ci, d_flags, s->d_soft[slot], soft_stride,
-				 n_gmsk_soft, 1, d_type);
-		if (r) return r;
+		if (fused_applies(ctx, max_toa_bound)) {
+			r = launch_nb_fused(ctx, st, s->d_bursts[slot], stride, m, d_type, d_tsc, d_max_toa, max_toa_bound, thresh, d_rc, d_amp,
+					    d_toa, d_tsc_out, d_ci, d_flags, s->d_soft[slot], soft_stride, n_gmsk_soft);
+			if (r) return r;
+		} else {
+			r = launch_detect(ctx, st, s->ws[slot], s->d_bursts[slot], stride, m, d_type, d_tsc, d_max_toa, max_toa_bound, thresh, d_rc,
+					  d_amp, d_toa, d_tsc_out, d_ci, d_flags, 0);
+			if (r) return r;
+			r = launch_demod(ctx, st, s->d_bursts[slot], stride, m, d_rc, d_amp, d_toa, d_ci, d_flags, s->d_soft[slot], soft_stride,
+					 n_gmsk_soft, 1, d_type);
+			if (r) return r;
+		}
 		CK(cudaMemcpyAsync(pin_out ? soft + (size_t)lo * soft_stride : s->h_soft[slot], s->d_soft[slot], (size_t)m * soft_stride * 4,
 				   cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(s->h_out[slot], d_o, (size_t)m16 * kDdOutBytes, cudaMemcpyDeviceToHost, st));

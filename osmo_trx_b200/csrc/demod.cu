@@ -77,29 +77,10 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b)
 // physical 16-byte slot of logical slot s (window samples 2s, 2s+1)
 __device__ __forceinline__ int slot_phys(int s) { return s; }
 
-// ---- mbarrier / TMA bulk-copy primitives (shared-window 32-bit addresses) ----
-__device__ __forceinline__ unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
+// ---- TMA bulk-copy primitives (smem_u32 / mbar_init / mbar_wait / mbar_arrive are detect.cu's) ----
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
-{
-	unsigned done = 0;
-	unsigned spins = 0;
-	while (!done) {
-		asm volatile("{\n\t.reg .pred p;\n\t"
-			     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-			     "selp.u32 %0, 1, 0, p;\n\t}"
-			     : "=r"(done)
-			     : "r"(bar), "r"(parity)
-			     : "memory");
-		if (!done && ++spins > (1u << 24)) __trap(); // a lost copy must fail loudly, not hang the device
-	}
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
@@ -403,6 +384,347 @@ __device__ __forceinline__ void energy_terms16(const short2 *xg, const short2 *U
 	}
 }
 
+// the warp's scratch behind its two window buffers, and the decimator taps this lane applies in the edge corrections
+struct DemodWarp {
+	float *ostage;
+	float2 *decs, *yv, *ytop, *yx;
+	float gk[4]; // k = 4*(lane&3) + kk
+};
+__device__ __forceinline__ DemodWarp demod_warp_setup(const DemodParams &p, float *ostage, int lane)
+{
+	DemodWarp W;
+	W.ostage = ostage;
+	W.decs = reinterpret_cast<float2 *>(ostage);
+	W.yv = reinterpret_cast<float2 *>(ostage + kYOff);
+	W.ytop = reinterpret_cast<float2 *>(ostage + kYTopOff);
+	W.yx = reinterpret_cast<float2 *>(ostage + kYxOff);
+#pragma unroll
+	for (int kk = 0; kk < 4; kk++) W.gk[kk] = p.dnsamp_g[4 * (lane & 3) + kk];
+	return W;
+}
+// row pointer (float2 or short2 samples) and its phase on the 16-byte grid
+__device__ __forceinline__ const float2 *demod_row_f(const DemodParams &p, int b) { return reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride; }
+__device__ __forceinline__ const short2 *demod_row_s(const DemodParams &p, int b) { return reinterpret_cast<const short2 *>(p.iq) + (size_t)b * p.iq_stride; }
+template <bool I16>
+__device__ __forceinline__ unsigned demod_row_phase(const DemodParams &p, int b)
+{
+	if constexpr (I16) return (unsigned)((reinterpret_cast<uintptr_t>(demod_row_s(p, b)) >> 2) & 3u);
+	else return (unsigned)((reinterpret_cast<uintptr_t>(demod_row_f(p, b)) >> 3) & 1u);
+}
+// staging call for one burst (see stage_async)
+template <bool I16>
+__device__ __forceinline__ void demod_stage(const DemodParams &p, int b, int off2, float2 *Ub, unsigned bar, int lane, float2 &patch, int &patch_idx)
+{
+	if constexpr (I16) stage_async16(demod_row_s(p, b), off2, Ub, bar, lane, patch, patch_idx);
+	else stage_async(demod_row_f(p, b), off2, Ub, bar, lane, patch, patch_idx);
+}
+
+// Everything the demodulator warp does for burst b once its scalars are known: for a detected burst (rc > 0) the window
+// U was staged by demod_stage() and completes on mbarrier `bar` (waited on here with `parity`); (patch, patch_idx) is
+// the straddling sample stage_async() handed back.  Shared by demod_kernel and nb_fused_kernel.
+template <bool I16>
+__device__ __forceinline__ void demod_one(const DemodParams &p, const DemodWarp &W, int b, int rc, float2 amp, float toa, float2 *U,
+					   float2 patch, int patch_idx, unsigned bar, unsigned parity, int lane)
+{
+	float *const ostage = W.ostage;
+	float2 *const decs = W.decs, *const yv = W.yv, *const ytop = W.ytop, *const yx = W.yx;
+	// pull path: the slot's power measurement (every slot that is not switched off, detected or not)
+	bool want_energy = false;
+	if constexpr (I16) {
+		want_energy = p.type_raw[b] != 0;
+		if (want_energy && rc <= 0) energy_terms16(demod_row_s(p, b), nullptr, 0, lane, p.pw + (size_t)b * 80);
+	}
+	if (rc <= 0) {
+		// undetected burst: only the deferred clipping report is left to do (sigProcLib.cpp:1746-1764)
+		if (p.fix_clip && rc == 0 && (!p.type || type_known(load_type(p.type, b, 0)))) {
+			float2 v[20];
+#pragma unroll
+			for (int k = 0; k < 20; k++) {
+				const int i = lane + 32 * k;
+				v[k] = make_float2(0.0f, 0.0f);
+				if (i < 625) {
+					if constexpr (I16) {
+						v[k] = cvt_s2(__ldg(reinterpret_cast<const unsigned *>(demod_row_s(p, b)) + i));
+					} else {
+						v[k] = __ldg(&demod_row_f(p, b)[i]);
+					}
+				}
+			}
+			float mx = 0.0f;
+#pragma unroll
+			for (int k = 0; k < 20; k++) mx = fmaxf(mx, fmaxf(fabsf(v[k].x), fabsf(v[k].y)));
+#pragma unroll
+			for (int o = 16; o; o >>= 1)
+				mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+			if (lane == 0 && mx > 30000.0f) {
+				p.rc[b] = -2;
+				if (p.flags) p.flags[b] |= 4;
+			}
+		}
+		return;
+	}
+
+	// ---- per-burst scalars ----
+	const float ian = __frcp_rn(norm2(amp));
+	const float2 s = make_float2(amp.x * ian, -amp.y * ian); // (complex)1.0 / amp (soft bits carry a 1e-4 tolerance)
+	const BurstGeom bg = burst_geom<I16>(toa, demod_row_phase<I16>(p, b));
+	const int whole = bg.whole, f = bg.f, e = bg.e; // e: 0..1 (float rows) / 0..3 (int16 rows)
+	const bool edge = (rc == 5);
+
+	// ---- the burst's window: straddling sample, then wait for the bulk copies ----
+	if (patch_idx >= 0) {
+		if constexpr (I16) reinterpret_cast<int *>(U)[patch_idx] = __float_as_int(patch.x);
+		else U[patch_idx] = patch;
+	}
+	__syncwarp();
+	mbar_wait(bar, parity);
+	if constexpr (I16) {
+		if (want_energy) {
+			const bool in_win = bg.off2 <= 0 && 316 - bg.off2 < 4 * kSlots16;
+			energy_terms16(demod_row_s(p, b), in_win ? reinterpret_cast<const short2 *>(U) : nullptr, bg.off2, lane,
+				       p.pw + (size_t)b * 80);
+		}
+	}
+
+	// ---- main pass (transposed FIR), shared by GMSK and EDGE: lane owns window samples 20*lane ..
+	//      20*lane+19 and accumulates into outputs i = 5*lane - 8 + m, m = 0..12; sample j meets output m
+	//      with tap u = j + 32 - 4m (0 <= u <= 35), coefficient ce[u] = comp0[f][e][u] ----
+	const int nout = edge ? 156 : p.n_gmsk_soft;
+	{
+		float2 acc[13];
+#pragma unroll
+		for (int m = 0; m < 13; m++) acc[m] = make_float2(0.0f, 0.0f);
+		const float4 *xc4 = reinterpret_cast<const float4 *>(U) + 10 * lane;
+		// int16 rows: the same 20 samples as ten 8-byte pairs, starting (e & 2) samples in
+		const uint2 *xc2 = reinterpret_cast<const uint2 *>(reinterpret_cast<const short2 *>(U) + 20 * lane + (e & 2));
+		const float *__restrict__ ce = c_tab.comp0[f][e & 1];
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			// samples j = 4k + 2h and 4k + 2h + 1, k = 0..4
+			float2 xa[5], xb[5];
+#pragma unroll
+			for (int k = 0; k < 5; k++) {
+				if constexpr (I16) {
+					const uint2 v = xc2[2 * k + h];
+					xa[k] = cvt_s2(v.x);
+					xb[k] = cvt_s2(v.y);
+				} else {
+					const float4 v = xc4[2 * k + h];
+					xa[k] = make_float2(v.x, v.y);
+					xb[k] = make_float2(v.z, v.w);
+				}
+			}
+#pragma unroll
+			for (int g = 0; g < 9; g++) {
+				// taps u = 4g + 2h (for xa) and u + 1 (for xb)
+				const float ca = ce[4 * g + 2 * h], cb = ce[4 * g + 2 * h + 1];
+#pragma unroll
+				for (int k = 0; k < 5; k++) {
+					// j = 4k + 2h, u = 4g + 2h  =>  m = (j + 32 - u) / 4 = k + 8 - g
+					const int m = k + 8 - g;
+					acc[m] = ffma2(xa[k], make_float2(ca, ca), acc[m]);
+					acc[m] = ffma2(xb[k], make_float2(cb, cb), acc[m]);
+				}
+			}
+		}
+		// hand the partial sums of outputs owned by lanes l-1 (m = 3..7) and l-2 (m = 0..2) over
+		float2 fin[5];
+#pragma unroll
+		for (int a = 0; a < 5; a++) {
+			float2 t1;
+			t1.x = __shfl_down_sync(0xffffffffu, acc[3 + a].x, 1);
+			t1.y = __shfl_down_sync(0xffffffffu, acc[3 + a].y, 1);
+			fin[a] = fadd2(acc[8 + a], t1);
+			if (a >= 2) {
+				float2 t2;
+				t2.x = __shfl_down_sync(0xffffffffu, acc[a - 2].x, 2);
+				t2.y = __shfl_down_sync(0xffffffffu, acc[a - 2].y, 2);
+				fin[a] = fadd2(fin[a], t2);
+			}
+		}
+		// lanes 30, 31 lack their right-hand neighbours: outputs >= 150 are finished by the split pass below
+		if (lane < 30) {
+			if (!edge) {
+				// soft value = Re(z_i * sum), z_i = (1/amp) * (-j)^i, i = 5*lane + a  (i mod 4 = (lane + a) mod 4)
+				float zx = (lane & 1) ? s.y : s.x, zy = (lane & 1) ? -s.x : s.y;
+				if (lane & 2) { zx = -zx; zy = -zy; }
+#pragma unroll
+				for (int a = 0; a < 5; a++) {
+					ostage[5 * lane + a] = fmaf(zx, fin[a].x, -zy * fin[a].y);
+					const float t = zx; // z *= -j
+					zx = zy;
+					zy = -t;
+				}
+			} else {
+#pragma unroll
+				for (int a = 0; a < 5; a++) decs[2 + 5 * lane + a] = cscale(fin[a], s);
+			}
+		}
+	}
+	// ---- outputs 150 .. nout-1 (EDGE, or GMSK callers asking for all 156): 4 lanes per output, 9 taps each ----
+	if (nout > 150) {
+		const int i = 150 + (lane >> 2), part = lane & 3;
+		const float *__restrict__ c = p.comp + (size_t)f * 16 * 36;
+		float2 d = make_float2(0.0f, 0.0f);
+		if (i < nout) {
+#pragma unroll
+			for (int tt = 0; tt < 9; tt++) {
+				const int t = 9 * part + tt;
+				if (t < 35) {
+					const float ct = __ldg(&c[t]);
+					d = ffma2(win_get<I16>(U, 4 * i + t + e), make_float2(ct, ct), d);
+				}
+			}
+		}
+		d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
+		d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
+		d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
+		d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
+		if (i < nout && part == 0) {
+			if (edge) decs[2 + i] = cscale(d, s);
+			else ostage[i] = soft_out(i, d, s);
+		}
+	}
+	// The pass above is the full composite over the zero-extended window.  Where the reference's intermediate
+	// vectors are truncated the dropped terms are subtracted: leading outputs lose decimator taps k < kmin
+	// (history / samples shifted in from below), trailing ones taps k > kmax (the delayed vector ends at sample
+	// 624 before the shift: delayed samples q >= q0 = 640 + whole never reach the decimator).
+	const int nlead = min(nout, (max(15, 15 + whole) + 3) >> 2);
+	const int nv = 15 + max(0, whole); // delayed samples Y[v], v < nv, are what the dropped leading taps would read
+	const int q0 = 640 + whole;
+	const bool top_trunc = q0 <= 4 * (nout - 1) + 15;
+	__syncwarp();
+	if (nv <= 32 || top_trunc) {
+		// Y[v] = sum_j win(v + e + j) * delay[f][j]: the delayed sample decimator tap k of output i reads, v = 4i + k.
+		// Lanes evaluate v = lane (leading edge); lanes 0..15 also v = q0 + lane (trailing edge).
+		const int q0c = min(max(q0, 0), 644);
+		float2 y = make_float2(0.0f, 0.0f), yt = make_float2(0.0f, 0.0f);
+		// int16 rows: the 52 window samples the leading Y values share are converted once (two per lane)
+		const float2 *uy = U + e;
+		if constexpr (I16) {
+			if (lane < 28) {
+				const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned *>(U) + (e & 2) + 2 * lane);
+				const float2 a = cvt_s2(v.x), c = cvt_s2(v.y);
+				reinterpret_cast<float4 *>(yx)[lane] = make_float4(a.x, a.y, c.x, c.y);
+			}
+			__syncwarp();
+			uy = yx + (e & 1);
+		}
+		if (f < 64) {
+#pragma unroll
+			for (int j = 0; j < 20; j++) {
+				const float hj = c_tab.delay[f][j];
+				y = ffma2(uy[lane + j], make_float2(hj, hj), y);
+			}
+			if (top_trunc && lane < 16) {
+#pragma unroll
+				for (int j = 0; j < 20; j++) {
+					const float hj = c_tab.delay[f][j];
+					yt = ffma2(win_get<I16>(U, q0c + lane + e + j), make_float2(hj, hj), yt);
+				}
+			}
+		} else {
+			y = uy[lane + 9];
+			if (top_trunc && lane < 16) yt = win_get<I16>(U, q0c + lane + e + 9);
+		}
+		yv[lane] = y;
+		if (lane < 16) ytop[lane] = yt;
+		__syncwarp();
+		if (nv <= 32) {
+			for (int base = 0; base < nlead; base += 8) {
+				const int i = base + (lane >> 2), part = lane & 3;
+				const int kmin = min(16, max(0, max(15 - 4 * i, 15 - 4 * i + whole)));
+				float2 d = make_float2(0.0f, 0.0f);
+				if (i < nlead) {
+#pragma unroll
+					for (int kk = 0; kk < 4; kk++) {
+						const int k = 4 * part + kk;
+						if (k < kmin)
+							d = ffma2(yv[4 * i + k], make_float2(W.gk[kk], W.gk[kk]), d);
+					}
+				}
+				d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
+				d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
+				d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
+				d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
+				if (i < nlead && part == 0) {
+					// every tap dropped: the reference's sample is an exact zero - store the zero, not a rounding residue
+					const bool none = kmin > min(15, 639 + whole - 4 * i);
+					if (edge) {
+						const float2 c2 = cscale(d, s);
+						decs[2 + i] = none ? make_float2(0.0f, 0.0f) : make_float2(decs[2 + i].x - c2.x, decs[2 + i].y - c2.y);
+					} else {
+						ostage[i] = none ? 0.0f : ostage[i] - soft_out(i, d, s);
+					}
+				}
+			}
+		}
+		if (top_trunc) {
+			// outputs whose taps reach q >= q0: at most 8 of them (Y beyond q0 + 8 is zero: the burst has ended)
+			const int i = max(0, (q0 - 12) >> 2) + (lane >> 2), part = lane & 3;
+			float2 d = make_float2(0.0f, 0.0f);
+			if (i < nout) {
+#pragma unroll
+				for (int kk = 0; kk < 4; kk++) {
+					const int m = 4 * i + 4 * part + kk - q0;
+					if (m >= 0 && m < 16)
+						d = ffma2(ytop[m], make_float2(W.gk[kk], W.gk[kk]), d);
+				}
+			}
+			d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
+			d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
+			d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
+			d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
+			if (i < nout && part == 0) {
+				// no tap left at all (the reference's sample is an exact zero): store the zero, not a rounding residue
+				const bool none = max(0, max(15 - 4 * i, 15 - 4 * i + whole)) > min(15, 639 + whole - 4 * i);
+				if (edge) {
+					const float2 c2 = cscale(d, s);
+					decs[2 + i] = none ? make_float2(0.0f, 0.0f) : make_float2(decs[2 + i].x - c2.x, decs[2 + i].y - c2.y);
+				} else {
+					ostage[i] = none ? 0.0f : ostage[i] - soft_out(i, d, s);
+				}
+			}
+		}
+	}
+	// ---- generic per-output path (rare): leading outputs of very late bursts (more than 32 delayed samples
+	//      feed the dropped taps) ----
+	if (nv > 32) {
+		for (int i = lane; i < nlead; i += 32) {
+			const int kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
+			const int kmax = min(15, 639 + whole - 4 * i);
+			float2 d = make_float2(0.0f, 0.0f);
+			if (kmin <= kmax)
+				d = (kmax == 15) ? comp_output<I16>(p, U, i, e, f, kmin) : slow_output<I16>(U, 4 * i + e, f, kmin, kmax);
+			if (edge) decs[2 + i] = cscale(d, s);
+			else ostage[i] = soft_out(i, d, s);
+		}
+	}
+	__syncwarp();
+	if (edge) {
+		demod_edge_tail(p, b, decs, lane);
+		__syncwarp();
+		return;
+	}
+	if constexpr (I16) {
+		// ---- pull chain: the soft values leave as datagram bytes ----
+		store_soft_bytes(p, b, ostage, nout, reinterpret_cast<uint8_t *>(yx), lane);
+		__syncwarp();
+		return;
+	}
+	// ---- coalesced store of the soft row ----
+	float *orow = p.soft + (size_t)b * p.soft_stride;
+	if (((reinterpret_cast<uintptr_t>(orow) & 15u) == 0) && (nout & 3) == 0) {
+		const float4 *os4 = reinterpret_cast<const float4 *>(ostage);
+		for (int j = lane; j < (nout >> 2); j += 32)
+			reinterpret_cast<float4 *>(orow)[j] = os4[j];
+	} else {
+		for (int j = lane; j < nout; j += 32)
+			orow[j] = ostage[j];
+	}
+	__syncwarp();
+}
+
 template <bool I16>
 __global__ void __launch_bounds__(256, 2)
 demod_kernel(DemodParams p)
@@ -412,27 +734,13 @@ demod_kernel(DemodParams p)
 	const int wpb = blockDim.x >> 5;
 	float2 *Ubase = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * (kDemodWarpFloats / 2);
 	float *ostage = reinterpret_cast<float *>(Ubase + 2 * 2 * kBufSlots);
-	float2 *decs = reinterpret_cast<float2 *>(ostage);
-	float2 *yv = reinterpret_cast<float2 *>(ostage + kYOff);
-	float2 *ytop = reinterpret_cast<float2 *>(ostage + kYTopOff);
-	float2 *yx = reinterpret_cast<float2 *>(ostage + kYxOff);
 	const unsigned bar0 = smem_u32(ostage + kScratchFloats); // two 8-byte mbarriers, one per window buffer
 	const int step = gridDim.x * wpb;
-	// row pointer (float2 or short2 samples), its phase on the 16-byte grid, and the staging call for one burst
-	auto row_f = [&](int b_) { return reinterpret_cast<const float2 *>(p.bursts) + (size_t)b_ * p.stride; };
-	auto row_s = [&](int b_) { return reinterpret_cast<const short2 *>(p.iq) + (size_t)b_ * p.iq_stride; };
-	auto row_phase = [&](int b_) {
-		if constexpr (I16) return (unsigned)((reinterpret_cast<uintptr_t>(row_s(b_)) >> 2) & 3u);
-		else return (unsigned)((reinterpret_cast<uintptr_t>(row_f(b_)) >> 3) & 1u);
-	};
+	const DemodWarp W = demod_warp_setup(p, ostage, lane);
+	auto row_phase = [&](int b_) { return demod_row_phase<I16>(p, b_); };
 	auto stage = [&](int b_, int off2, float2 *Ub, unsigned bar, float2 &patch, int &patch_idx) {
-		if constexpr (I16) stage_async16(row_s(b_), off2, Ub, bar, lane, patch, patch_idx);
-		else stage_async(row_f(b_), off2, Ub, bar, lane, patch, patch_idx);
+		demod_stage<I16>(p, b_, off2, Ub, bar, lane, patch, patch_idx);
 	};
-	// decimator taps this lane applies in the leading-output correction (k = 4*(lane&3) + kk)
-	float gk[4];
-#pragma unroll
-	for (int kk = 0; kk < 4; kk++) gk[kk] = p.dnsamp_g[4 * (lane & 3) + kk];
 
 	if (lane == 0) {
 		mbar_init(bar0, 1);
@@ -489,302 +797,8 @@ demod_kernel(DemodParams p)
 			}
 		}
 
-		// pull path: the slot's power measurement (every slot that is not switched off, detected or not)
-		bool want_energy = false;
-		if constexpr (I16) {
-			want_energy = p.type_raw[b] != 0;
-			if (want_energy && rc <= 0) energy_terms16(row_s(b), nullptr, 0, lane, p.pw + (size_t)b * 80);
-		}
-		if (rc <= 0) {
-			// undetected burst: only the deferred clipping report is left to do (sigProcLib.cpp:1746-1764)
-			if (p.fix_clip && rc == 0 && (!p.type || type_known(load_type(p.type, b, 0)))) {
-				float2 v[20];
-#pragma unroll
-				for (int k = 0; k < 20; k++) {
-					const int i = lane + 32 * k;
-					v[k] = make_float2(0.0f, 0.0f);
-					if (i < 625) {
-						if constexpr (I16) {
-							v[k] = cvt_s2(__ldg(reinterpret_cast<const unsigned *>(row_s(b)) + i));
-						} else {
-							v[k] = __ldg(&row_f(b)[i]);
-						}
-					}
-				}
-				float mx = 0.0f;
-#pragma unroll
-				for (int k = 0; k < 20; k++) mx = fmaxf(mx, fmaxf(fabsf(v[k].x), fabsf(v[k].y)));
-#pragma unroll
-				for (int o = 16; o; o >>= 1)
-					mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-				if (lane == 0 && mx > 30000.0f) {
-					p.rc[b] = -2;
-					if (p.flags) p.flags[b] |= 4;
-				}
-			}
-			continue;
-		}
-
-		// ---- per-burst scalars ----
-		const float ian = __frcp_rn(norm2(amp));
-		const float2 s = make_float2(amp.x * ian, -amp.y * ian); // (complex)1.0 / amp (soft bits carry a 1e-4 tolerance)
-		const BurstGeom bg = burst_geom<I16>(toa, row_phase(b));
-		const int whole = bg.whole, f = bg.f, e = bg.e; // e: 0..1 (float rows) / 0..3 (int16 rows)
-		const bool edge = (rc == 5);
-
-		// ---- the burst's window: straddling sample, then wait for the bulk copies ----
-		if (patch_idx >= 0) {
-			if constexpr (I16) reinterpret_cast<int *>(U)[patch_idx] = __float_as_int(patch.x);
-			else U[patch_idx] = patch;
-		}
-		__syncwarp();
-		mbar_wait(bar0 + 8 * cur, (phase >> cur) & 1u);
-		phase ^= 1u << cur;
-		if constexpr (I16) {
-			if (want_energy) {
-				const bool in_win = bg.off2 <= 0 && 316 - bg.off2 < 4 * kSlots16;
-				energy_terms16(row_s(b), in_win ? reinterpret_cast<const short2 *>(U) : nullptr, bg.off2, lane,
-					       p.pw + (size_t)b * 80);
-			}
-		}
-
-		// ---- main pass (transposed FIR), shared by GMSK and EDGE: lane owns window samples 20*lane ..
-		//      20*lane+19 and accumulates into outputs i = 5*lane - 8 + m, m = 0..12; sample j meets output m
-		//      with tap u = j + 32 - 4m (0 <= u <= 35), coefficient ce[u] = comp0[f][e][u] ----
-		const int nout = edge ? 156 : p.n_gmsk_soft;
-		{
-			float2 acc[13];
-#pragma unroll
-			for (int m = 0; m < 13; m++) acc[m] = make_float2(0.0f, 0.0f);
-			const float4 *xc4 = reinterpret_cast<const float4 *>(U) + 10 * lane;
-			// int16 rows: the same 20 samples as ten 8-byte pairs, starting (e & 2) samples in
-			const uint2 *xc2 = reinterpret_cast<const uint2 *>(reinterpret_cast<const short2 *>(U) + 20 * lane + (e & 2));
-			const float *__restrict__ ce = c_tab.comp0[f][e & 1];
-#pragma unroll
-			for (int h = 0; h < 2; h++) {
-				// samples j = 4k + 2h and 4k + 2h + 1, k = 0..4
-				float2 xa[5], xb[5];
-#pragma unroll
-				for (int k = 0; k < 5; k++) {
-					if constexpr (I16) {
-						const uint2 v = xc2[2 * k + h];
-						xa[k] = cvt_s2(v.x);
-						xb[k] = cvt_s2(v.y);
-					} else {
-						const float4 v = xc4[2 * k + h];
-						xa[k] = make_float2(v.x, v.y);
-						xb[k] = make_float2(v.z, v.w);
-					}
-				}
-#pragma unroll
-				for (int g = 0; g < 9; g++) {
-					// taps u = 4g + 2h (for xa) and u + 1 (for xb)
-					const float ca = ce[4 * g + 2 * h], cb = ce[4 * g + 2 * h + 1];
-#pragma unroll
-					for (int k = 0; k < 5; k++) {
-						// j = 4k + 2h, u = 4g + 2h  =>  m = (j + 32 - u) / 4 = k + 8 - g
-						const int m = k + 8 - g;
-						acc[m] = ffma2(xa[k], make_float2(ca, ca), acc[m]);
-						acc[m] = ffma2(xb[k], make_float2(cb, cb), acc[m]);
-					}
-				}
-			}
-			// hand the partial sums of outputs owned by lanes l-1 (m = 3..7) and l-2 (m = 0..2) over
-			float2 fin[5];
-#pragma unroll
-			for (int a = 0; a < 5; a++) {
-				float2 t1;
-				t1.x = __shfl_down_sync(0xffffffffu, acc[3 + a].x, 1);
-				t1.y = __shfl_down_sync(0xffffffffu, acc[3 + a].y, 1);
-				fin[a] = fadd2(acc[8 + a], t1);
-				if (a >= 2) {
-					float2 t2;
-					t2.x = __shfl_down_sync(0xffffffffu, acc[a - 2].x, 2);
-					t2.y = __shfl_down_sync(0xffffffffu, acc[a - 2].y, 2);
-					fin[a] = fadd2(fin[a], t2);
-				}
-			}
-			// lanes 30, 31 lack their right-hand neighbours: outputs >= 150 are finished by the split pass below
-			if (lane < 30) {
-				if (!edge) {
-					// soft value = Re(z_i * sum), z_i = (1/amp) * (-j)^i, i = 5*lane + a  (i mod 4 = (lane + a) mod 4)
-					float zx = (lane & 1) ? s.y : s.x, zy = (lane & 1) ? -s.x : s.y;
-					if (lane & 2) { zx = -zx; zy = -zy; }
-#pragma unroll
-					for (int a = 0; a < 5; a++) {
-						ostage[5 * lane + a] = fmaf(zx, fin[a].x, -zy * fin[a].y);
-						const float t = zx; // z *= -j
-						zx = zy;
-						zy = -t;
-					}
-				} else {
-#pragma unroll
-					for (int a = 0; a < 5; a++) decs[2 + 5 * lane + a] = cscale(fin[a], s);
-				}
-			}
-		}
-		// ---- outputs 150 .. nout-1 (EDGE, or GMSK callers asking for all 156): 4 lanes per output, 9 taps each ----
-		if (nout > 150) {
-			const int i = 150 + (lane >> 2), part = lane & 3;
-			const float *__restrict__ c = p.comp + (size_t)f * 16 * 36;
-			float2 d = make_float2(0.0f, 0.0f);
-			if (i < nout) {
-#pragma unroll
-				for (int tt = 0; tt < 9; tt++) {
-					const int t = 9 * part + tt;
-					if (t < 35) {
-						const float ct = __ldg(&c[t]);
-						d = ffma2(win_get<I16>(U, 4 * i + t + e), make_float2(ct, ct), d);
-					}
-				}
-			}
-			d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
-			d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
-			d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
-			d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
-			if (i < nout && part == 0) {
-				if (edge) decs[2 + i] = cscale(d, s);
-				else ostage[i] = soft_out(i, d, s);
-			}
-		}
-		// The pass above is the full composite over the zero-extended window.  Where the reference's intermediate
-		// vectors are truncated the dropped terms are subtracted: leading outputs lose decimator taps k < kmin
-		// (history / samples shifted in from below), trailing ones taps k > kmax (the delayed vector ends at sample
-		// 624 before the shift: delayed samples q >= q0 = 640 + whole never reach the decimator).
-		const int nlead = min(nout, (max(15, 15 + whole) + 3) >> 2);
-		const int nv = 15 + max(0, whole); // delayed samples Y[v], v < nv, are what the dropped leading taps would read
-		const int q0 = 640 + whole;
-		const bool top_trunc = q0 <= 4 * (nout - 1) + 15;
-		__syncwarp();
-		if (nv <= 32 || top_trunc) {
-			// Y[v] = sum_j win(v + e + j) * delay[f][j]: the delayed sample decimator tap k of output i reads, v = 4i + k.
-			// Lanes evaluate v = lane (leading edge); lanes 0..15 also v = q0 + lane (trailing edge).
-			const int q0c = min(max(q0, 0), 644);
-			float2 y = make_float2(0.0f, 0.0f), yt = make_float2(0.0f, 0.0f);
-			// int16 rows: the 52 window samples the leading Y values share are converted once (two per lane)
-			const float2 *uy = U + e;
-			if constexpr (I16) {
-				if (lane < 28) {
-					const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned *>(U) + (e & 2) + 2 * lane);
-					const float2 a = cvt_s2(v.x), c = cvt_s2(v.y);
-					reinterpret_cast<float4 *>(yx)[lane] = make_float4(a.x, a.y, c.x, c.y);
-				}
-				__syncwarp();
-				uy = yx + (e & 1);
-			}
-			if (f < 64) {
-#pragma unroll
-				for (int j = 0; j < 20; j++) {
-					const float hj = c_tab.delay[f][j];
-					y = ffma2(uy[lane + j], make_float2(hj, hj), y);
-				}
-				if (top_trunc && lane < 16) {
-#pragma unroll
-					for (int j = 0; j < 20; j++) {
-						const float hj = c_tab.delay[f][j];
-						yt = ffma2(win_get<I16>(U, q0c + lane + e + j), make_float2(hj, hj), yt);
-					}
-				}
-			} else {
-				y = uy[lane + 9];
-				if (top_trunc && lane < 16) yt = win_get<I16>(U, q0c + lane + e + 9);
-			}
-			yv[lane] = y;
-			if (lane < 16) ytop[lane] = yt;
-			__syncwarp();
-			if (nv <= 32) {
-				for (int base = 0; base < nlead; base += 8) {
-					const int i = base + (lane >> 2), part = lane & 3;
-					const int kmin = min(16, max(0, max(15 - 4 * i, 15 - 4 * i + whole)));
-					float2 d = make_float2(0.0f, 0.0f);
-					if (i < nlead) {
-#pragma unroll
-						for (int kk = 0; kk < 4; kk++) {
-							const int k = 4 * part + kk;
-							if (k < kmin)
-								d = ffma2(yv[4 * i + k], make_float2(gk[kk], gk[kk]), d);
-						}
-					}
-					d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
-					d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
-					d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
-					d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
-					if (i < nlead && part == 0) {
-						// every tap dropped: the reference's sample is an exact zero - store the zero, not a rounding residue
-						const bool none = kmin > min(15, 639 + whole - 4 * i);
-						if (edge) {
-							const float2 c2 = cscale(d, s);
-							decs[2 + i] = none ? make_float2(0.0f, 0.0f) : make_float2(decs[2 + i].x - c2.x, decs[2 + i].y - c2.y);
-						} else {
-							ostage[i] = none ? 0.0f : ostage[i] - soft_out(i, d, s);
-						}
-					}
-				}
-			}
-			if (top_trunc) {
-				// outputs whose taps reach q >= q0: at most 8 of them (Y beyond q0 + 8 is zero: the burst has ended)
-				const int i = max(0, (q0 - 12) >> 2) + (lane >> 2), part = lane & 3;
-				float2 d = make_float2(0.0f, 0.0f);
-				if (i < nout) {
-#pragma unroll
-					for (int kk = 0; kk < 4; kk++) {
-						const int m = 4 * i + 4 * part + kk - q0;
-						if (m >= 0 && m < 16)
-							d = ffma2(ytop[m], make_float2(gk[kk], gk[kk]), d);
-					}
-				}
-				d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
-				d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
-				d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
-				d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
-				if (i < nout && part == 0) {
-					// no tap left at all (the reference's sample is an exact zero): store the zero, not a rounding residue
-					const bool none = max(0, max(15 - 4 * i, 15 - 4 * i + whole)) > min(15, 639 + whole - 4 * i);
-					if (edge) {
-						const float2 c2 = cscale(d, s);
-						decs[2 + i] = none ? make_float2(0.0f, 0.0f) : make_float2(decs[2 + i].x - c2.x, decs[2 + i].y - c2.y);
-					} else {
-						ostage[i] = none ? 0.0f : ostage[i] - soft_out(i, d, s);
-					}
-				}
-			}
-		}
-		// ---- generic per-output path (rare): leading outputs of very late bursts (more than 32 delayed samples
-		//      feed the dropped taps) ----
-		if (nv > 32) {
-			for (int i = lane; i < nlead; i += 32) {
-				const int kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
-				const int kmax = min(15, 639 + whole - 4 * i);
-				float2 d = make_float2(0.0f, 0.0f);
-				if (kmin <= kmax)
-					d = (kmax == 15) ? comp_output<I16>(p, U, i, e, f, kmin) : slow_output<I16>(U, 4 * i + e, f, kmin, kmax);
-				if (edge) decs[2 + i] = cscale(d, s);
-				else ostage[i] = soft_out(i, d, s);
-			}
-		}
-		__syncwarp();
-		if (edge) {
-			demod_edge_tail(p, b, decs, lane);
-			__syncwarp();
-			continue;
-		}
-		if constexpr (I16) {
-			// ---- pull chain: the soft values leave as datagram bytes ----
-			store_soft_bytes(p, b, ostage, nout, reinterpret_cast<uint8_t *>(yx), lane);
-			__syncwarp();
-			continue;
-		}
-		// ---- coalesced store of the soft row ----
-		float *orow = p.soft + (size_t)b * p.soft_stride;
-		if (((reinterpret_cast<uintptr_t>(orow) & 15u) == 0) && (nout & 3) == 0) {
-			const float4 *os4 = reinterpret_cast<const float4 *>(ostage);
-			for (int j = lane; j < (nout >> 2); j += 32)
-				reinterpret_cast<float4 *>(orow)[j] = os4[j];
-		} else {
-			for (int j = lane; j < nout; j += 32)
-				orow[j] = ostage[j];
-		}
-		__syncwarp();
+		demod_one<I16>(p, W, b, rc, amp, toa, U, patch, patch_idx, bar0 + 8 * cur, (phase >> cur) & 1u, lane);
+		if (rc > 0) phase ^= 1u << cur;
 	}
 }
 

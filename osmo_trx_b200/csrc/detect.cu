@@ -179,27 +179,61 @@ __device__ __forceinline__ float2 cmul_tap(float2 xv, float2 hr, float2 hi, floa
 	return add2(p1, make_float2(p2.y, p2.x));
 }
 
+// ---- mbarrier primitives (shared-window 32-bit addresses); demod.cu adds the bulk-copy forms ----
+__device__ __forceinline__ unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+	unsigned done = 0;
+	unsigned spins = 0;
+	while (!done) {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+			     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			     "selp.u32 %0, 1, 0, p;\n\t}"
+			     : "=r"(done)
+			     : "r"(bar), "r"(parity)
+			     : "memory");
+		if (!done && ++spins > (1u << 24)) __trap(); // a lost arrival must fail loudly, not hang the device
+	}
+}
+
+// Where a correlator warp finds its groups and leaves its results.  Stand-alone kernel: groups strided over the grid,
+// results to the global intermediates peak_kernel reads.  (nb_fused_kernel, nbfused.cu, supplies the tile forms.)
+struct NbGridSched {
+	int first, step, ngroups;
+	// first burst of the warp's q-th group, or -1 when the warp has no q-th group
+	__device__ __forceinline__ int operator()(int q) const
+	{
+		const long g = (long)first + (long)q * step;
+		return g < ngroups ? (int)g * kNbGroup : -1;
+	}
+};
+struct NbGlobalSink {
+	float2 *corr; // [n][20]
+	float *pwr;   // [n][35]
+	__device__ __forceinline__ void begin(int, int) {}
+	__device__ __forceinline__ void pw(int b0, int g, int j, float v) { pwr[(size_t)(b0 + g) * 35 + j] = v; }
+	__device__ __forceinline__ void co(int b0, int g, int i, float2 v) { corr[(size_t)(b0 + g) * 20 + i] = v; }
+	__device__ __forceinline__ void end(int, int) {}
+};
+
+// The correlator warp's whole life: hs / sinfo are the CTA's copies of the 16-symbol sequences and the sequence table
+// (filled and synchronised by the caller), wbase the warp's staging area (corr_nb_warp_bytes()).
 // I16: the windows are read from the radio's int16 slots (p.iq, pull chain): 8-byte slots, converted after the
 // shared-memory read - detection then needs no float copy of the slot at all.
-template <bool I16>
-__global__ void __launch_bounds__(256, 2)
-corr_nb_kernel(CorrParams p)
+template <bool I16, class Sched, class Sink>
+__device__ __forceinline__ void corr_nb_run(const CorrParams &p, const float2 *hs, const SeqInfo *sinfo, unsigned char *wbase, int lane,
+					     Sched sched, Sink sink)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int wpb = blockDim.x >> 5;
-	float2 *hs = reinterpret_cast<float2 *>(smem_raw); // [SEQ_COUNT][kNbSeqPitch]
-	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + (((size_t)SEQ_COUNT * kNbSeqPitch * 8 + 15) & ~(size_t)15));
-	unsigned char *wbase = smem_raw + corr_nb_hdr_bytes() + corr_nb_warp_bytes() * warp;
 	float4 *raw = reinterpret_cast<float4 *>(wbase);			   // [kNbGroup][kNbRawPitch]
 	float2 *dec = reinterpret_cast<float2 *>(raw + kNbGroup * kNbRawPitch); // [kNbGroup][kNbDecPitch]
-
-	for (int k = threadIdx.x; k < SEQ_COUNT * 16; k += blockDim.x) {
-		const int id = k >> 4, t = k & 15;
-		if (c_tab.info[id].len == 16) hs[id * kNbSeqPitch + t] = c_tab.seq[c_tab.info[id].off + t];
-	}
-	for (int k = threadIdx.x; k < SEQ_COUNT; k += blockDim.x) sinfo[k] = c_tab.info[k];
-	__syncthreads();
 
 	const float2 NZ = bc2(p.negzero);
 	const float2 Z = make_float2(0.0f, 0.0f);
@@ -216,16 +250,14 @@ corr_nb_kernel(CorrParams p)
 	// Software pipeline over the warp's groups: the window copies of the NEXT group (cp.async, global -> shared
 	// without a register round trip) are issued as soon as the decimator has consumed the current windows and land
 	// while the current group is correlated; the per-burst scalars (type, tsc, max_toa, rc) run one group further ahead.
-	const int ngroups = (p.n + kNbGroup - 1) / kNbGroup;
-	const int gstep = gridDim.x * wpb;
 	const unsigned raw_s = (unsigned)__cvta_generic_to_shared(raw) + SB * (unsigned)((lane & 7) * kNbPlanePitch + (lane >> 3));
 
 	struct Scal { int type, tsc, T, rc; };
-	auto load_scal = [&](int grp_) {
+	auto load_scal = [&](int b0_) {
 		Scal q;
 		q.type = -1; q.tsc = 0; q.T = 0; q.rc = 0;
-		const int b = grp_ * kNbGroup + lane;
-		if (lane < kNbGroup && grp_ < ngroups && b < p.n) {
+		const int b = b0_ + lane;
+		if (lane < kNbGroup && b0_ >= 0 && b < p.n) {
 			q.type = load_type(p.type, b, 0); q.tsc = p.tsc[b]; q.T = p.max_toa[b];
 			if (p.round > 0) q.rc = p.rc[b];
 		}
@@ -241,8 +273,7 @@ corr_nb_kernel(CorrParams p)
 	};
 	// slot sl = lane + 32 * it of burst g goes to plane sl & 7, index sl >> 3: per lane a fixed shared offset plus
 	// immediates; row base, window start and alignment are warp-uniform per burst
-	auto issue_copies = [&](int grp_, int pk_) {
-		const int b0_ = grp_ * kNbGroup;
+	auto issue_copies = [&](int b0_, int pk_) {
 #pragma unroll
 		for (int g = 0; g < kNbGroup; g++) {
 			const int w = __shfl_sync(0xffffffffu, pk_, g);
@@ -279,25 +310,30 @@ corr_nb_kernel(CorrParams p)
 		asm volatile("cp.async.commit_group;" ::: "memory");
 	};
 
-	int grp = blockIdx.x * wpb + warp;
+	int q = 0;
+	int b0 = sched(0);
 	int my_pk = 0;
 	Scal sc_next;
-	if (grp < ngroups) {
-		my_pk = pack_scal(load_scal(grp));
-		issue_copies(grp, my_pk);
+	if (b0 >= 0) {
+		my_pk = pack_scal(load_scal(b0));
+		issue_copies(b0, my_pk);
 	}
-	sc_next = load_scal(grp + gstep);
-	for (; grp < ngroups; grp += gstep) {
-		const int b0 = grp * kNbGroup;
+	int b0_next = sched(1);
+	sc_next = load_scal(b0_next);
+	for (; b0 >= 0; q++) {
 		const int pk_next = pack_scal(sc_next);
+		const int b0_nn = b0_next >= 0 ? sched(q + 2) : -1;
 		const bool any = __ballot_sync(0xffffffffu, my_pk & 1) != 0u;
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncwarp();
+		sink.begin(q, lane);
 		if (!any) {
 			// nothing to do in this group: keep the pipeline moving
-			if (grp + gstep < ngroups) issue_copies(grp + gstep, pk_next);
-			sc_next = load_scal(grp + 2 * gstep);
+			if (b0_next >= 0) issue_copies(b0_next, pk_next);
+			sc_next = load_scal(b0_nn);
+			sink.end(q, lane);
 			my_pk = pk_next;
+			b0 = b0_next; b0_next = b0_nn;
 			continue;
 		}
 
@@ -313,47 +349,46 @@ corr_nb_kernel(CorrParams p)
 				if constexpr (I16) {
 					const uint2 *r = reinterpret_cast<const uint2 *>(raw) + g * kNbRawPitch + a;
 #pragma unroll
-					for (int q = 0; q < 14; q++) {
-						const uint2 wv = r[(q & 7) * kNbPlanePitch + (q >> 3)];
+					for (int qq = 0; qq < 14; qq++) {
+						const uint2 wv = r[(qq & 7) * kNbPlanePitch + (qq >> 3)];
 						const float2 lo = cvt_s2(wv.x), hi = cvt_s2(wv.y);
-						s[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+						s[qq] = make_float4(lo.x, lo.y, hi.x, hi.y);
 					}
 				} else {
 					const float4 *r = raw + g * kNbRawPitch + a;
 #pragma unroll
-					for (int q = 0; q < 14; q++) s[q] = r[(q & 7) * kNbPlanePitch + (q >> 3)];
+					for (int qq = 0; qq < 14; qq++) s[qq] = r[(qq & 7) * kNbPlanePitch + (qq >> 3)];
 				}
 				float2 *dg = dec + g * kNbDecPitch;
-				float *pw = p.pwr + (size_t)(b0 + g) * 35;
 #pragma unroll
 				for (int o = 0; o < 4; o++) {
 					float2 L[4];
 #pragma unroll
-					for (int q = 0; q < 4; q++) {
+					for (int qq = 0; qq < 4; qq++) {
 						// taps q, 4+q, 8+q, 12+q: sample k of the output sits in slot 2o + k/2, half k & 1
 						float2 pr[4];
 #pragma unroll
 						for (int m = 0; m < 4; m++) {
-							const int k = 4 * m + q;
+							const int k = 4 * m + qq;
 							const float4 v = s[2 * o + (k >> 1)];
 							pr[m] = mul2((k & 1) ? make_float2(v.z, v.w) : make_float2(v.x, v.y), bc2(g16[k]), NZ);
 						}
-						L[q] = add2(add2(pr[0], pr[1]), add2(pr[2], pr[3]));
+						L[qq] = add2(add2(pr[0], pr[1]), add2(pr[2], pr[3]));
 					}
 					const float2 y = add2(add2(L[0], L[1]), add2(L[2], L[3]));
 					const int j = 4 * a + o;
 					if (j < 35) {
 						const int j5 = (j * 13) >> 6; // j / 5 for j < 64
 						dg[(j - 5 * j5) * 7 + j5] = y;
-						pw[j] = norm2(y);
+						sink.pw(b0, g, j, norm2(y));
 					}
 				}
 			}
 		}
 		__syncwarp();
 		// the windows are consumed: start the next group's copies and the scalars of the one after
-		if (grp + gstep < ngroups) issue_copies(grp + gstep, pk_next);
-		sc_next = load_scal(grp + 2 * gstep);
+		if (b0_next >= 0) issue_copies(b0_next, pk_next);
+		sc_next = load_scal(b0_nn);
 
 		// ---- correlation (sse_conv_cmplx_8n order, convolve_sse_3.c:462-537, h_len 16): 5 outputs per item ----
 		{
@@ -370,13 +405,13 @@ corr_nb_kernel(CorrParams p)
 #pragma unroll
 				for (int step = 0; step < 8; step++) {
 					// tap pairs in the order (0,8) (4,12) (1,9) (5,13) (2,10) (6,14) (3,11) (7,15)
-					const int q = (step >> 1) + 4 * (step & 1);
-					const float2 h1 = hh[q], h2 = hh[q + 8];
+					const int qq = (step >> 1) + 4 * (step & 1);
+					const float2 h1 = hh[qq], h2 = hh[qq + 8];
 					const float2 h1r = bc2(h1.x), h1i = make_float2(h1.y, -h1.y);
 					const float2 h2r = bc2(h2.x), h2i = make_float2(h2.y, -h2.y);
 #pragma unroll
 					for (int o = 0; o < 5; o++) {
-						const float2 acc = add2(add2(Z, cmul_tap(x[o + q], h1r, h1i, NZ)), cmul_tap(x[o + q + 8], h2r, h2i, NZ));
+						const float2 acc = add2(add2(Z, cmul_tap(x[o + qq], h1r, h1i, NZ)), cmul_tap(x[o + qq + 8], h2r, h2i, NZ));
 						if ((step & 1) == 0) {
 							A[o] = acc; // A[q]
 						} else {
@@ -388,14 +423,43 @@ corr_nb_kernel(CorrParams p)
 						}
 					}
 				}
-				float2 *co = p.corr + (size_t)(b0 + g) * 20 + 5 * a;
 #pragma unroll
 				for (int o = 0; o < 5; o++)
-					if (5 * a + o < len) co[o] = out[o];
+					if (5 * a + o < len) sink.co(b0, g, 5 * a + o, out[o]);
 			}
 		}
+		sink.end(q, lane);
 		my_pk = pk_next;
+		b0 = b0_next; b0_next = b0_nn;
 	}
+}
+
+// the CTA's copies of the 16-symbol sequences and the sequence table, in front of the warps' staging areas
+__device__ __forceinline__ void corr_nb_fill_hdr(float2 *hs, SeqInfo *sinfo)
+{
+	for (int k = threadIdx.x; k < SEQ_COUNT * 16; k += blockDim.x) {
+		const int id = k >> 4, t = k & 15;
+		if (c_tab.info[id].len == 16) hs[id * kNbSeqPitch + t] = c_tab.seq[c_tab.info[id].off + t];
+	}
+	for (int k = threadIdx.x; k < SEQ_COUNT; k += blockDim.x) sinfo[k] = c_tab.info[k];
+}
+
+template <bool I16>
+__global__ void __launch_bounds__(256, 2)
+corr_nb_kernel(CorrParams p)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int wpb = blockDim.x >> 5;
+	float2 *hs = reinterpret_cast<float2 *>(smem_raw); // [SEQ_COUNT][kNbSeqPitch]
+	SeqInfo *sinfo = reinterpret_cast<SeqInfo *>(smem_raw + (((size_t)SEQ_COUNT * kNbSeqPitch * 8 + 15) & ~(size_t)15));
+	corr_nb_fill_hdr(hs, sinfo);
+	__syncthreads();
+	NbGridSched sched;
+	sched.first = blockIdx.x * wpb + warp; sched.step = gridDim.x * wpb; sched.ngroups = (p.n + kNbGroup - 1) / kNbGroup;
+	NbGlobalSink sink;
+	sink.corr = p.corr; sink.pwr = p.pwr;
+	corr_nb_run<I16>(p, hs, sinfo, smem_raw + corr_nb_hdr_bytes() + corr_nb_warp_bytes() * warp, lane, sched, sink);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -616,6 +680,153 @@ __host__ __device__ inline size_t peak_hdr_bytes()
 	return (size_t)kSinc512 * sizeof(float) + ((SEQ_COUNT * sizeof(SeqInfo) + 15) & ~(size_t)15);
 }
 
+// Everything peak detection does for one burst once its correlation vector sits in shared memory (Cl = row 0 of the
+// burst's column, rows kRowPitch apart between zero rows): the round bookkeeping, the gates, the TOA bisection, C/I,
+// amp.  pwr_at(j) = |decimated sample j|^2 of the burst's correlator window.  Shared by peak_kernel and nb_fused_kernel.
+struct PeakRes {
+	int rc;
+	float2 amp;
+	float toa, ci;
+	int tsc_out;
+	unsigned flags;
+	bool write_all; // round 0 defines every output of a valid burst; later rounds only on a hit / error
+};
+template <class PwrAt>
+__device__ __forceinline__ PeakRes peak_lane(const PeakParams &p, const SeqInfo *sinfo, const float *stab, float2 *Cl, bool valid,
+					      bool run, const Attempt &at, int type, int tsc, int T, int rc, float2 NZ, PwrAt pwr_at)
+{
+	unsigned flags = 0;
+	float2 amp = make_float2(0.0f, 0.0f);
+	float toa = 0.0f, ci = 0.0f;
+	int tsc_out = 0;
+	bool write_all = false; // round 0 defines every output of a valid burst; later rounds only on a hit / error
+
+	if (valid && p.round == 0) {
+		write_all = true;
+		if ((type == 1 || type == 5) && tsc > 7) { rc = -3; tsc_out = 0; } // -SIGERR_UNSUPPORTED
+		else {
+			if (type == 1 || type == 5) tsc_out = tsc;
+			if (type_known(type) && T > p.max_toa_bound) rc = -1; // -SIGERR_BOUNDS: caller's bound was wrong
+		}
+	}
+	if (valid && !run && rc == 0 && type_known(type) && !((type == 1 || type == 5) && tsc > 7) && T <= p.max_toa_bound) {
+		// the attempt exists but its window is larger than trxb200_detect_config() promised: -SIGERR_BOUNDS
+		if (at.seq >= 0 && sinfo[at.seq].len + at.len - 1 > p.ndmax) { rc = -1; write_all = true; }
+	}
+
+	if (run) {
+		const int len = at.len;
+		const SeqInfo si = sinfo[at.seq];
+		// rows the interpolation may touch beyond the vector are zero; the vector's last sample is
+		// excluded from interpolation (end = size - 1, :1105) and is zeroed once the gates are done
+		for (int r = len; r < len + kPadRows && r < p.lmax + kPadRows; r++) Cl[r * kRowPitch] = make_float2(0.0f, 0.0f);
+		// fastPeakDetect
+		float mx = 0.0f;
+		int idx = -1;
+		float2 pk = make_float2(0.0f, 0.0f);
+		for (int i = 0; i < len; i++) {
+			const float2 v = Cl[i * kRowPitch];
+			const float pwv = norm2(v);
+			if (pwv > mx) { mx = pwv; idx = i; pk = v; }
+		}
+		float t = (float)idx;
+		bool hit = !((t < 3.0f) || (t > (float)(len - 3)));
+		if (hit) {
+			// computePeakRatio (sps = 1)
+			int num = 0;
+			float avg = 0.0f;
+			for (int i = 2; i <= 5; i++) {
+				if (idx - i >= 0) { avg = fa(avg, norm2(Cl[(idx - i) * kRowPitch])); num++; }
+				if (idx + i < len) { avg = fa(avg, norm2(Cl[(idx + i) * kRowPitch])); num++; }
+			}
+			float ratio = 0.0f;
+			if (num >= 5) {
+				const float rms = (float)((double)sqrtf(avg / (float)num) + 0.00001);
+				ratio = sqrtf(norm2(pk)) / rms;
+			}
+			if (fabsf(ratio - p.thresh) < 1e-5f) flags |= 1u;
+			if (ratio < p.thresh) hit = false;
+		}
+		if (hit) {
+			Cl[(len - 1) * kRowPitch] = make_float2(0.0f, 0.0f);
+			// peakDetect: early/late bisection; the late point is always early + 2 (:1172), i.e. both sit on
+			// the same 1/512 grid position and share their 21 weights
+			float early = t - 1.0f, incr = 0.5f;
+#pragma unroll 1
+			for (int it = 0; it < 9; it++) {
+				const int m = (int)floorf(early);
+				const int F = (int)((early - (float)m) * 512.0f);
+				const float2 *cp = Cl + (m - 10) * kRowPitch;
+				const float *wF = stab + brev9(F);
+				float2 e = make_float2(0.0f, 0.0f), l = make_float2(0.0f, 0.0f);
+				float2 v0 = cp[0], v1 = cp[kRowPitch];
+#pragma unroll
+				for (int d = 0; d < 21; d++) {
+					const float w = wF[512 * d];
+					const float2 v2 = cp[(d + 2) * kRowPitch];
+					e = add2(e, mul2(v0, bc2(w), NZ));
+					l = add2(l, mul2(v2, bc2(w), NZ));
+					v0 = v1;
+					v1 = v2;
+				}
+				const float ne = norm2(e), nl = norm2(l);
+				if (near_tie(ne, nl)) flags |= 2u;
+				if (ne < nl) early += incr;
+				else if (ne > nl) early -= incr;
+				else break;
+				incr *= 0.5f;
+			}
+			t = early + 1.0f;
+			float2 xc = make_float2(0.0f, 0.0f);
+			{
+				const int m = (int)floorf(t);
+				const int F = (int)((t - (float)m) * 512.0f);
+				const float2 *cp = Cl + (m - 10) * kRowPitch;
+				const float *wF = stab + brev9(F);
+#pragma unroll
+				for (int d = 0; d < 21; d++) {
+					const float w = wF[512 * d];
+					xc = add2(xc, mul2(cp[d * kRowPitch], bc2(w), NZ));
+				}
+			}
+			// computeCI
+			const int N = si.len;
+			const int rt = (int)roundf(t);
+			const int ps = at.start + 1 - N + rt;
+			if (ps < 0 || ps + N > 156 || rt < 0 || rt >= len) {
+				ci = 0.0f;
+			} else {
+				// S = mean |burst[ps..ps+N)|^2, sequential (:1622-1626); pwr index j = dec index - d0 = rt + k
+									float S = 0.0f;
+				for (int k0 = 0; k0 < N; k0 += 16) { // N is 16, 40 or 64; sixteen loads in flight, then the ordered sum
+					float v[16];
+#pragma unroll
+					for (int k = 0; k < 16; k++) v[k] = (k0 + k < N) ? pwr_at(rt + k0 + k) : 0.0f;
+#pragma unroll
+					for (int k = 0; k < 16; k++)
+						if (k0 + k < N) S = fa(S, v[k]);
+				}
+				S = S / (float)N;
+				const float Cn = norm2(xc) / si.ci_den;
+				ci = fm(3.0103f, log2f(Cn / fs(S, Cn)));
+			}
+			amp = cmul_exact(xc, make_float2(si.inv_gr, si.inv_gi));
+			toa = fs(fs(t, si.toa), (float)at.head);
+			rc = at.rc_hit;
+			tsc_out = (type == 2 || type == 3) ? p.round : ((type == 1 || type == 5) ? tsc : 0);
+			write_all = true;
+		}
+	}
+	if (valid && p.last_round && rc == 0 && type_known(type)) {
+		// a further attempt exists but no round was scheduled for it (trxb200_detect_config): never silently skipped
+		Attempt nx = make_attempt(type, tsc, T, p.round + 1);
+		if (nx.seq >= 0 && !((type == 1 || type == 5) && tsc > 7) && T <= p.max_toa_bound) { rc = -1; write_all = true; }
+	}
+	PeakRes res;
+	res.rc = rc; res.amp = amp; res.toa = toa; res.ci = ci; res.tsc_out = tsc_out; res.flags = flags; res.write_all = write_all;
+	return res;
+}
+
 __global__ void __launch_bounds__(512, 1)
 peak_kernel(PeakParams p)
 {
@@ -688,135 +899,16 @@ peak_kernel(PeakParams p)
 		}
 		__syncwarp();
 
-		unsigned flags = 0;
-		float2 amp = make_float2(0.0f, 0.0f);
-		float toa = 0.0f, ci = 0.0f;
-		int tsc_out = 0;
-		bool write_all = false; // round 0 defines every output of a valid burst; later rounds only on a hit / error
-
-		if (valid && p.round == 0) {
-			write_all = true;
-			if ((type == 1 || type == 5) && tsc > 7) { rc = -3; tsc_out = 0; } // -SIGERR_UNSUPPORTED
-			else {
-				if (type == 1 || type == 5) tsc_out = tsc;
-				if (type_known(type) && T > p.max_toa_bound) rc = -1; // -SIGERR_BOUNDS: caller's bound was wrong
-			}
-		}
-		if (valid && !run && rc == 0 && type_known(type) && !((type == 1 || type == 5) && tsc > 7) && T <= p.max_toa_bound) {
-			// the attempt exists but its window is larger than trxb200_detect_config() promised: -SIGERR_BOUNDS
-			if (at.seq >= 0 && sinfo[at.seq].len + at.len - 1 > p.ndmax) { rc = -1; write_all = true; }
-		}
-
-		if (run) {
-			const int len = at.len;
-			const SeqInfo si = sinfo[at.seq];
-			float2 *Cl = C + kPadRows * kRowPitch + lane; // row i of this lane's burst: Cl[i * kRowPitch]
-			// rows the interpolation may touch beyond the vector are zero; the vector's last sample is
-			// excluded from interpolation (end = size - 1, :1105) and is zeroed once the gates are done
-			for (int r = len; r < len + kPadRows && r < p.lmax + kPadRows; r++) Cl[r * kRowPitch] = make_float2(0.0f, 0.0f);
-			// fastPeakDetect
-			float mx = 0.0f;
-			int idx = -1;
-			float2 pk = make_float2(0.0f, 0.0f);
-			for (int i = 0; i < len; i++) {
-				const float2 v = Cl[i * kRowPitch];
-				const float pwv = norm2(v);
-				if (pwv > mx) { mx = pwv; idx = i; pk = v; }
-			}
-			float t = (float)idx;
-			bool hit = !((t < 3.0f) || (t > (float)(len - 3)));
-			if (hit) {
-				// computePeakRatio (sps = 1)
-				int num = 0;
-				float avg = 0.0f;
-				for (int i = 2; i <= 5; i++) {
-					if (idx - i >= 0) { avg = fa(avg, norm2(Cl[(idx - i) * kRowPitch])); num++; }
-					if (idx + i < len) { avg = fa(avg, norm2(Cl[(idx + i) * kRowPitch])); num++; }
-				}
-				float ratio = 0.0f;
-				if (num >= 5) {
-					const float rms = (float)((double)sqrtf(avg / (float)num) + 0.00001);
-					ratio = sqrtf(norm2(pk)) / rms;
-				}
-				if (fabsf(ratio - p.thresh) < 1e-5f) flags |= 1u;
-				if (ratio < p.thresh) hit = false;
-			}
-			if (hit) {
-				Cl[(len - 1) * kRowPitch] = make_float2(0.0f, 0.0f);
-				// peakDetect: early/late bisection; the late point is always early + 2 (:1172), i.e. both sit on
-				// the same 1/512 grid position and share their 21 weights
-				float early = t - 1.0f, incr = 0.5f;
-#pragma unroll 1
-				for (int it = 0; it < 9; it++) {
-					const int m = (int)floorf(early);
-					const int F = (int)((early - (float)m) * 512.0f);
-					const float2 *cp = Cl + (m - 10) * kRowPitch;
-					const float *wF = stab + brev9(F);
-					float2 e = make_float2(0.0f, 0.0f), l = make_float2(0.0f, 0.0f);
-					float2 v0 = cp[0], v1 = cp[kRowPitch];
-#pragma unroll
-					for (int d = 0; d < 21; d++) {
-						const float w = wF[512 * d];
-						const float2 v2 = cp[(d + 2) * kRowPitch];
-						e = add2(e, mul2(v0, bc2(w), NZ));
-						l = add2(l, mul2(v2, bc2(w), NZ));
-						v0 = v1;
-						v1 = v2;
-					}
-					const float ne = norm2(e), nl = norm2(l);
-					if (near_tie(ne, nl)) flags |= 2u;
-					if (ne < nl) early += incr;
-					else if (ne > nl) early -= incr;
-					else break;
-					incr *= 0.5f;
-				}
-				t = early + 1.0f;
-				float2 xc = make_float2(0.0f, 0.0f);
-				{
-					const int m = (int)floorf(t);
-					const int F = (int)((t - (float)m) * 512.0f);
-					const float2 *cp = Cl + (m - 10) * kRowPitch;
-					const float *wF = stab + brev9(F);
-#pragma unroll
-					for (int d = 0; d < 21; d++) {
-						const float w = wF[512 * d];
-						xc = add2(xc, mul2(cp[d * kRowPitch], bc2(w), NZ));
-					}
-				}
-				// computeCI
-				const int N = si.len;
-				const int rt = (int)roundf(t);
-				const int ps = at.start + 1 - N + rt;
-				if (ps < 0 || ps + N > 156 || rt < 0 || rt >= len) {
-					ci = 0.0f;
-				} else {
-					// S = mean |burst[ps..ps+N)|^2, sequential (:1622-1626); pwr index j = dec index - d0 = rt + k
-					const float *pw = p.pwr + (size_t)b * p.ndmax + rt;
-					float S = 0.0f;
-					for (int k0 = 0; k0 < N; k0 += 16) { // N is 16, 40 or 64; sixteen loads in flight, then the ordered sum
-						float v[16];
-#pragma unroll
-						for (int k = 0; k < 16; k++) v[k] = (k0 + k < N) ? __ldg(&pw[k0 + k]) : 0.0f;
-#pragma unroll
-						for (int k = 0; k < 16; k++)
-							if (k0 + k < N) S = fa(S, v[k]);
-					}
-					S = S / (float)N;
-					const float Cn = norm2(xc) / si.ci_den;
-					ci = fm(3.0103f, log2f(Cn / fs(S, Cn)));
-				}
-				amp = cmul_exact(xc, make_float2(si.inv_gr, si.inv_gi));
-				toa = fs(fs(t, si.toa), (float)at.head);
-				rc = at.rc_hit;
-				tsc_out = (type == 2 || type == 3) ? p.round : ((type == 1 || type == 5) ? tsc : 0);
-				write_all = true;
-			}
-		}
-		if (valid && p.last_round && rc == 0 && type_known(type)) {
-			// a further attempt exists but no round was scheduled for it (trxb200_detect_config): never silently skipped
-			Attempt nx = make_attempt(type, tsc, T, p.round + 1);
-			if (nx.seq >= 0 && !((type == 1 || type == 5) && tsc > 7) && T <= p.max_toa_bound) { rc = -1; write_all = true; }
-		}
+		const float *pwrow = p.pwr + (size_t)b * p.ndmax;
+		float2 *Cl0 = C + kPadRows * kRowPitch + lane; // row i of this lane's burst: Cl0[i * kRowPitch]
+		const PeakRes res = peak_lane(p, sinfo, stab, Cl0, valid, run, at, type, tsc, T, rc, NZ,
+					      [&](int j) { return __ldg(&pwrow[j]); });
+		rc = res.rc;
+		const float2 amp = res.amp;
+		const float toa = res.toa, ci = res.ci;
+		const int tsc_out = res.tsc_out;
+		const unsigned flags = res.flags;
+		const bool write_all = res.write_all;
 
 		if (valid) {
 			if (write_all) {
