@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="nb", choices=["nb", "rach", "edge"])
+    ap.add_argument("--workload", default="nb", choices=["nb", "rach", "edge", "vitac", "wideband", "modulate"])
     ap.add_argument("--bursts", type=int, default=1 << 20, help="bursts per GPU per step")
     ap.add_argument("--e2e-bursts", type=int, default=1 << 18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -115,6 +115,9 @@ def make_workload(trx, kind, n, seed, device):
     g.manual_seed(seed)
     rx = torch.empty((n, 625, 2), dtype=torch.float32, device=device)
     tsc = (torch.arange(n, device=device) % 8).to(torch.uint8)
+    multipath = kind == "vitac"  # cfg 4: normal bursts through a random 4-tap (symbol spaced) multipath channel
+    if multipath:
+        kind = "nb"
     if kind == "nb":
         typ = torch.full((n,), 1, dtype=torch.uint8, device=device)
         max_toa = torch.full((n,), 4, dtype=torch.int16, device=device)
@@ -161,6 +164,15 @@ def make_workload(trx, kind, n, seed, device):
         x = torch.zeros((m, 1024), dtype=torch.complex64, device=device)
         x[:, 128:753] = torch.view_as_complex(tx)
         X = torch.fft.fft(x, dim=1) * torch.exp(-2j * torch.pi * f[None, :] * shift[:, None])
+        if multipath:
+            # taps 1, a1, a2, a3 at 0..3 symbols (4 samples apart), |a_k| falling off: a frequency-domain product
+            mag = torch.tensor([1.0, 0.5, 0.3, 0.2], device=device) * torch.empty((m, 4), device=device).uniform_(0.3, 1.0, generator=g)
+            mag[:, 0] = 1.0
+            pha = torch.empty((m, 4), device=device).uniform_(0, 6.2831853, generator=g)
+            pha[:, 0] = 0.0
+            taps = mag * torch.exp(1j * pha)
+            H = sum(taps[:, k:k + 1] * torch.exp(-2j * torch.pi * f[None, :] * (4.0 * k)) for k in range(4))
+            X = X * H
         y = torch.fft.ifft(X, dim=1)[:, 128:753]
         amp = torch.empty(m, device=device).uniform_(0.1, 1.0, generator=g)
         ph = torch.empty(m, device=device).uniform_(0, 6.2831853, generator=g)
@@ -230,6 +242,9 @@ def run_reference(args):
     lib, kind = (cpulibs.Ref(), "reference") if cpulibs.Ref.available() else (cpulibs.Oracle(), "port")
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(1)
+    if args.workload in AUX:
+        run_reference_aux(args, lib, kind, cores, rng)
+        return
     n = 8192 * max(1, cores // 2)
     tsc = (np.arange(n) % 8).astype(np.uint8)
     if args.workload == "edge":
@@ -280,6 +295,80 @@ def run_reference(args):
     emit(line)
 
 
+def run_reference_aux(args, lib, kind, cores, rng):
+    """--impl reference for cfg 4 / cfg 5 / the modulators: the reference's own functions on all host cores."""
+    import numpy as np
+    import synth
+    import concurrent.futures as cf
+    if args.workload == "modulate":
+        n = 8192 * max(1, cores // 2)
+        bits = synth.nb_bits(n, (np.arange(n) % 8).astype(np.uint8), rng)
+        one = lambda: lib.modulate_gmsk_batch(bits, nthreads=cores)  # noqa: E731
+        metric, chain = "GSM bursts/sec modulated (Laurent GMSK, sps=4)", "modulateBurst(bits, 0, 4)"
+        wname = "modulateBurst: 148-bit normal bursts, Laurent C0+C1 pulse shaping, sps=4"
+    elif args.workload == "vitac":
+        n = 1024 * cores
+        tsc = (np.arange(n) % 8).astype(np.uint8)
+        w = lib.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng), nthreads=cores)
+        rx, _ = synth.impair(synth.multipath(w, rng), rng, snr_db=np.choose(np.arange(n) % 3, [30.0, 10.0, 6.0]), noise_only_frac=0.05)
+        hb = np.zeros((n, 40 + 625 + 63, 2), np.float32)
+        hb[:, 40:665] = rx
+        one = lambda: lib.vitac(hb, 40, tsc, nthreads=cores)  # noqa: E731
+        metric, chain = "GSM bursts/sec equalised by the grgsm_vitac MLSE (sps=4)", "get_norm_chan_imp_resp + detect_burst_nb"
+        wname = "cfg4: grgsm_vitac MLSE of GMSK normal bursts through a random 4-tap symbol-spaced multipath channel"
+    else:
+        if kind != "reference":
+            emit({"impl": "reference", "unavailable": "the wideband chain needs the compiled reference (oracle/_ref)"})
+            return
+        M, BL, K = 64, 192, 52
+        nblk = K * 625 // 260
+        tsc = (np.arange(M * K) % 8).astype(np.uint8)
+        w = lib.modulate_gmsk_batch(synth.nb_bits(M * K, tsc, rng), nthreads=cores) * rng.uniform(0.3, 1.0, (M * K, 1, 1)).astype(np.float32)
+        streams = w.reshape(M, K * 625, 2)
+        hr = lib.resampler(48, 65)
+
+        def down(c):
+            xx = np.concatenate([np.zeros((16, 2), np.float32), streams[c]])
+            return np.concatenate([lib.resampler_rotate(hr, xx[k * 260:k * 260 + 276], 16, BL)[1] for k in range(nblk)])
+        with cf.ThreadPoolExecutor(cores) as ex:
+            chan = np.stack(list(ex.map(down, range(M))))
+        sy = lib.synthesis(M, BL)
+        wide = np.concatenate([lib.synthesis_rotate(sy, np.ascontiguousarray(chan[:, k * BL:(k + 1) * BL]), M, BL)[1] for k in range(nblk)])
+        wide += rng.standard_normal(wide.shape).astype(np.float32) * 1e-3
+        st = lib.wideband_rx(wide, nblk, M, BL, 65, 48)
+        ref0 = streams[0, :20000, 0] + 1j * streams[0, :20000, 1]
+        got0 = st[0, :, 0] + 1j * st[0, :, 1]
+        lag = int(np.argmax([np.abs(np.vdot(ref0, got0[l:l + 20000])) for l in range(200)]))
+        nsl = K - 1
+        t_h = np.ascontiguousarray(tsc.reshape(M, K)[:, :nsl].reshape(-1))
+        n = cores * M * nsl
+        pool = cf.ThreadPoolExecutor(cores)
+
+        def one():
+            # `cores` radios side by side, one receive thread each (the reference's threading), then their slots on all cores
+            outs = list(pool.map(lambda _: lib.wideband_rx(wide, nblk, M, BL, 65, 48), range(cores)))
+            sl = np.ascontiguousarray(outs[0][:, lag:lag + nsl * 625].reshape(M * nsl, 625, 2))
+            for _ in range(cores):
+                lib.detect_demod(sl, 1, t_h, 4, nthreads=cores)
+        metric, chain = "GSM bursts/sec detected+demodulated (sps=4)", ("Channelizer::rotate + Resampler::rotate block by block (one "
+                                                                        "thread per radio) -> slots -> detectAnyBurst + demodAnyBurst")
+        wname = "cfg5: 64-ARFCN wideband stream -> Channelizer(64,192) -> Resampler(65,48) -> slots -> detectAnyBurst(TSC,max_toa=4)+demodAnyBurst"
+    for _ in range(max(1, min(args.warmup, 2))):
+        one()
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    v = n * steps / dt
+    emit({"impl": "reference", "metric": metric, "value": v, "unit": "bursts/s", "arfcn_equivalents": v / ARFCN_BURSTS_PER_S,
+          "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * dt / steps,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": wname, "bursts_per_step": n, "sps": 4, "chain": chain},
+          "cpu_baseline": {"value": v, "unit": "bursts/s", "cores": cores, "kind": kind, "sample": f"{n} bursts per step, {cores} threads"},
+          "e2e": {"value": v, "unit": "bursts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
 def workload_name(kind):
     return {"nb": "cfg1 recipe at GPU scale: GMSK normal bursts, TSC 0-7, AWGN 30/10/6 dB + random TOA, 5% noise-only; "
                   "detectAnyBurst(TSC,max_toa=4)+demodAnyBurst",
@@ -326,6 +415,478 @@ def bind_near_gpu(index):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs beyond the headline: cfg 4 (grgsm_vitac MLSE), cfg 5 (wideband channelizer chain), modulators.
+# Same contract and JSON line; each has its own step, algorithmic bytes, CPU baseline and end-to-end pipeline.
+# ---------------------------------------------------------------------------------------------------------
+def timed_steps(step, steps, warmup, world, rank, local, device, dist):
+    """W untimed steps, then K steps between CUDA events on the launching stream, barrier + synchronize on both sides,
+    max over ranks; SM clock / throttle reasons sampled during the timed region on rank 0."""
+    import torch
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    return ms / steps, clocks
+
+
+def host_pipeline(nchunks, h2d, compute, d2h, streams):
+    """H2D | kernels | D2H on three streams over chunks with double-buffered device staging (slot = chunk & 1):
+    h2d(k, slot) / compute(k, slot) / d2h(k, slot) only enqueue; events order the three stages per slot."""
+    import torch
+    s_in, s_c, s_out = streams
+    ev_in, ev_c, ev_out = [None, None], [None, None], [None, None]
+    for k in range(nchunks):
+        slot = k & 1
+        with torch.cuda.stream(s_in):
+            if ev_c[slot] is not None:
+                s_in.wait_event(ev_c[slot])       # the staging input of chunk k-2 has been consumed
+            h2d(k, slot)
+            ev_in[slot] = torch.cuda.Event()
+            ev_in[slot].record(s_in)
+        with torch.cuda.stream(s_c):
+            s_c.wait_event(ev_in[slot])
+            if ev_out[slot] is not None:
+                s_c.wait_event(ev_out[slot])      # the staging output of chunk k-2 has left the device
+            compute(k, slot)
+            ev_c[slot] = torch.cuda.Event()
+            ev_c[slot].record(s_c)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_c[slot])
+            d2h(k, slot)
+            ev_out[slot] = torch.cuda.Event()
+            ev_out[slot].record(s_out)
+
+
+def time_e2e(call, units_per_call, reps, world, device, dist):
+    """wall clock around `reps` public-API calls on host buffers (copies inside), max over ranks"""
+    import torch
+    for _ in range(2):
+        call()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        call()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return world * units_per_call * reps / dt
+
+
+def med3(f, units):
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        f()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    return units / times[1]
+
+
+def link_ceiling(h_in, h_out, units, world, device, dist, e2e_value):
+    """Bare concurrent H2D (h_in) + D2H (h_out) copies of one e2e call's pinned buffers on two streams, all ranks at once:
+    the ceiling the host link sets for the end-to-end figure, whatever the kernels do."""
+    import torch
+    d_in = torch.empty(h_in.shape, dtype=h_in.dtype, device=device)
+    d_out = torch.empty(h_out.shape, dtype=h_out.dtype, device=device)
+    s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+    def once():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+
+    for _ in range(2):
+        once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    bi, bo = h_in.numel() * h_in.element_size(), h_out.numel() * h_out.element_size()
+    ceiling = world * units * reps / dt
+    return {"h2d_gbs_per_gpu": bi * reps / dt / 1e9, "d2h_gbs_per_gpu": bo * reps / dt / 1e9,
+            "slots_per_s_ceiling": ceiling, "frac_of_link": e2e_value / ceiling,
+            "what": "bare pinned cudaMemcpyAsync H2D + D2H of the same buffers, two streams, all ranks concurrently"}
+
+
+def cpu_lib():
+    import cpulibs
+    return (cpulibs.Ref(), "reference") if cpulibs.Ref.available() else (cpulibs.Oracle(), "port")
+
+
+def aux_vitac(args, trx, device, rank, world, dist):
+    """cfg 4: grgsm_vitac - channel estimate (get_norm_chan_imp_resp) + matched filter + 16-state Viterbi per burst."""
+    import numpy as np
+    import torch
+    n = args.bursts
+    rx, typ, tsc, mt, bound = make_workload(trx, "vitac", n, seed=2000 + rank, device=device)
+    off, pitch = 40, 40 + 625 + 63   # head-room as ms_upper.cpp:164-171 leaves it around the burst
+    buf = torch.zeros((n, pitch, 2), dtype=torch.float32, device=device)
+    buf[:, off:off + 625] = rx
+    ns = min(n, 1 << 17)
+    rx_s = rx[:ns].cpu()
+    del rx
+    out = trx.vitac(buf, off, tsc)
+
+    def step():
+        trx.vitac(buf, off, tsc, out=out)
+
+    def cpu():
+        lib, kind = cpu_lib()
+        cores = os.cpu_count() or 1
+        hb = np.zeros((ns, pitch, 2), np.float32)
+        hb[:, off:off + 625] = rx_s.numpy()
+        ht = tsc[:ns].cpu().numpy()
+        n0 = min(ns, 512 * cores)
+        t0 = time.perf_counter()
+        lib.vitac(hb[:n0], off, ht[:n0], nthreads=cores)
+        rate = n0 / (time.perf_counter() - t0)
+        n1 = int(min(ns, max(n0, rate * 3.0)))
+        v = med3(lambda: lib.vitac(hb[:n1], off, ht[:n1], nthreads=cores), n1)
+        return {"value": v, "unit": "bursts/s", "cores": cores, "kind": kind, "per_core": v / cores,
+                "sample": f"{n1} bursts of the same workload x 3 passes (median), {cores} threads: get_norm_chan_imp_resp + detect_burst_nb"}
+
+    def e2e():
+        ne = min(args.e2e_bursts, n)
+        chunk = 16384
+        h_rx = torch.empty((ne, 625, 2), dtype=torch.float32).pin_memory()
+        h_rx.copy_(buf[:ne, off:off + 625])
+        h_tsc = tsc[:ne].cpu().pin_memory()
+        h_bits = torch.empty((ne, 148), dtype=torch.int8).pin_memory()
+        d_buf = [torch.zeros((chunk, pitch, 2), dtype=torch.float32, device=device) for _ in range(2)]
+        d_tsc = [torch.zeros(chunk, dtype=torch.uint8, device=device) for _ in range(2)]
+        d_out = [trx.vitac(d_buf[i], off, d_tsc[i]) for i in range(2)]
+        streams = [torch.cuda.Stream(device=device) for _ in range(3)]
+        nch = (ne + chunk - 1) // chunk
+
+        def h2d(k, s):
+            lo, hi = k * chunk, min(ne, (k + 1) * chunk)
+            d_buf[s][:hi - lo, off:off + 625].copy_(h_rx[lo:hi], non_blocking=True)
+            d_tsc[s][:hi - lo].copy_(h_tsc[lo:hi], non_blocking=True)
+
+        def comp(k, s):
+            trx.vitac(d_buf[s], off, d_tsc[s], out=d_out[s])
+
+        def d2h(k, s):
+            lo, hi = k * chunk, min(ne, (k + 1) * chunk)
+            h_bits[lo:hi].copy_(d_out[s]["bits"][:hi - lo], non_blocking=True)
+
+        v = time_e2e(lambda: host_pipeline(nch, h2d, comp, d2h, streams), ne, max(3, min(args.steps, 10)), world, device, dist)
+        return {"value": v, "unit": "bursts/s", "h2d_bytes_per_step": ne * (5000 + 1), "d2h_bytes_per_step": ne * 148,
+                "bursts_per_call": ne, "api": "Trx.vitac on pinned host bursts: H2D | vitac_kernel | D2H of the 148 decisions, "
+                                              "three streams, 16k-burst stages"}
+
+    return dict(step=step, units=n, unit="bursts/s", metric="GSM bursts/sec equalised by the grgsm_vitac MLSE (sps=4)",
+                alg_step=5000 + 148 + 8, alg_kernel={"vitac_kernel": 5000 + 148 + 8}, cpu=cpu, e2e=e2e,
+                config={"workload": "cfg4: grgsm_vitac MLSE of GMSK normal bursts through a random 4-tap symbol-spaced multipath "
+                                    "channel (get_norm_chan_imp_resp + detect_burst_nb), AWGN 30/10/6 dB",
+                        "bursts_per_gpu_per_step": n, "sps": 4,
+                        "l2": "inputs (6.1 GB/GPU) far exceed the 126 MB L2; no flush needed",
+                        "sharding": "independent bursts, no data-path collective"})
+
+
+def aux_modulate(args, trx, device, rank, world, dist):
+    """TX side: modulateBurst (Laurent GMSK, sps=4) of 148-bit normal bursts."""
+    import numpy as np
+    import torch
+    n = args.bursts
+    g = torch.Generator(device=device)
+    g.manual_seed(3000 + rank)
+    bits = torch.randint(0, 2, (n, 148), generator=g, device=device, dtype=torch.uint8)
+    out = torch.empty((n, 625, 2), dtype=torch.float32, device=device)
+
+    def step():
+        trx.modulate_gmsk(bits, out=out)
+
+    def cpu():
+        lib, kind = cpu_lib()
+        cores = os.cpu_count() or 1
+        hb = bits[:1 << 18].cpu().numpy()
+        n0 = min(len(hb), 2048 * cores)
+        t0 = time.perf_counter()
+        lib.modulate_gmsk_batch(hb[:n0], nthreads=cores)
+        rate = n0 / (time.perf_counter() - t0)
+        n1 = int(min(len(hb), max(n0, rate * 3.0)))
+        v = med3(lambda: lib.modulate_gmsk_batch(hb[:n1], nthreads=cores), n1)
+        return {"value": v, "unit": "bursts/s", "cores": cores, "kind": kind, "per_core": v / cores,
+                "sample": f"{n1} bursts x 3 passes (median), {cores} threads: modulateBurst(bits, 0, 4)"}
+
+    def e2e():
+        # the transmit chain of Transceiver::addRadioVector -> RadioInterface::pushBuffer: bits in, int16 I/Q out
+        ne = min(args.e2e_bursts, n)
+        chunk = 16384
+        h_bits = bits[:ne].cpu().pin_memory()
+        h_iq = torch.empty((ne, 1250), dtype=torch.int16).pin_memory()
+        d_bits = [torch.zeros((chunk, 148), dtype=torch.uint8, device=device) for _ in range(2)]
+        d_tx = [torch.empty((chunk, 625, 2), dtype=torch.float32, device=device) for _ in range(2)]
+        d_iq = [torch.empty(chunk * 1250, dtype=torch.int16, device=device) for _ in range(2)]
+        streams = [torch.cuda.Stream(device=device) for _ in range(3)]
+        nch = (ne + chunk - 1) // chunk
+
+        def h2d(k, s):
+            lo, hi = k * chunk, min(ne, (k + 1) * chunk)
+            d_bits[s][:hi - lo].copy_(h_bits[lo:hi], non_blocking=True)
+
+        def comp(k, s):
+            trx.modulate_gmsk(d_bits[s], out=d_tx[s])
+            trx.convert_float_short(d_tx[s].reshape(-1), IQ_SCALE, out=d_iq[s])
+
+        def d2h(k, s):
+            lo, hi = k * chunk, min(ne, (k + 1) * chunk)
+            h_iq[lo:hi].copy_(d_iq[s].view(chunk, 1250)[:hi - lo], non_blocking=True)
+
+        v = time_e2e(lambda: host_pipeline(nch, h2d, comp, d2h, streams), ne, max(3, min(args.steps, 10)), world, device, dist)
+        return {"value": v, "unit": "bursts/s", "h2d_bytes_per_step": ne * 148, "d2h_bytes_per_step": ne * 2500,
+                "bursts_per_call": ne, "api": "Trx.modulate_gmsk + convert_float_short on pinned host bits: bits in, int16 I/Q out"}
+
+    return dict(step=step, units=n, unit="bursts/s", metric="GSM bursts/sec modulated (Laurent GMSK, sps=4)",
+                alg_step=148 + 5000, alg_kernel={"modulate_gmsk_kernel": 148 + 5000}, cpu=cpu, e2e=e2e,
+                config={"workload": "modulateBurst: 148-bit normal bursts, Laurent C0+C1 pulse shaping, sps=4",
+                        "bursts_per_gpu_per_step": n, "sps": 4,
+                        "l2": "outputs (5.2 GB/GPU) far exceed the 126 MB L2; no flush needed",
+                        "sharding": "independent bursts, no data-path collective"})
+
+
+def aux_wideband(args, trx, device, rank, world, dist):
+    """cfg 5: 64-ARFCN wideband stream -> Channelizer(64,192) -> Resampler(65,48) per channel -> 625-sample slots ->
+    detectAnyBurst + demodAnyBurst.  The stream is generated by this repo's own TX mirror (modulate -> Resampler(48,65)
+    -> Synthesis) on the device.  N > 1: the stream is sharded by time blocks (quantum 125 blocks = 52 slots per channel);
+    a rank that starts mid-stream re-reads its 32-row halo from the source (WidebandRx.prime)."""
+    import numpy as np
+    import torch
+    import osmo_trx_b200
+    M, BL, Q = 64, 192, 125
+    K = max(52, (args.bursts // M) // 52 * 52)        # slots per channel per GPU (whole 125-block quanta)
+    nblk = K * 625 // 260
+    n = M * K
+    g = torch.Generator(device=device)
+    g.manual_seed(4000 + rank)
+    tsc = (torch.arange(n, device=device) % 8).to(torch.uint8)
+    import synth
+    tsc_bits = torch.tensor([[int(c) for c in s_] for s_ in synth.TSC_STR], dtype=torch.uint8, device=device)
+    # ---- TX mirror on the device: per channel K bursts back to back at 4 sps, down to the channel rate, synthesised ----
+    rs_tx = osmo_trx_b200.Resampler(trx, 48, 65)
+    sy = osmo_trx_b200.Synthesis(trx, M, BL)
+    chan = torch.zeros((M, 16 + K * 625, 2), dtype=torch.float32, device=device)
+    cb = 4096
+    for lo in range(0, n, cb):
+        m_ = min(cb, n - lo)
+        bits = torch.zeros((m_, 148), dtype=torch.uint8, device=device)
+        bits[:, 3:60] = torch.randint(0, 2, (m_, 57), generator=g, device=device, dtype=torch.uint8)
+        bits[:, 88:145] = torch.randint(0, 2, (m_, 57), generator=g, device=device, dtype=torch.uint8)
+        bits[:, 61:87] = tsc_bits[tsc[lo:lo + m_].long()]
+        tx = trx.modulate_gmsk(bits) * torch.empty((m_, 1, 1), device=device).uniform_(0.3, 1.0, generator=g)
+        # burst b = c * K + k goes to channel c, slot k
+        idx = torch.arange(lo, lo + m_, device=device)
+        chan[:, 16:].reshape(M, K, 625, 2)[idx // K, idx % K] = tx
+    down = torch.empty((M, nblk * BL, 2), dtype=torch.float32, device=device)
+    rs_tx.rotate_streams(chan, 16, K * 625, chan.stride(0) // 2, M, down, nblk * BL)
+    wide = sy.rotate(down)
+    wide += torch.randn(wide.shape, generator=g, device=device) * 1e-3
+    ref0 = torch.view_as_complex(chan[0, 16:16 + 20000].contiguous())
+    del chan, down, sy, rs_tx
+    torch.cuda.synchronize()
+    rx = osmo_trx_b200.WidebandRx(trx, M, BL)
+    streams_out = torch.empty((M, nblk * 260, 2), dtype=torch.float32, device=device)
+    typ = torch.full((n,), 1, dtype=torch.uint8, device=device)
+    mt = torch.full((n,), 4, dtype=torch.int16, device=device)
+    tsc_cm = tsc   # burst order is channel-major, exactly the slot order of WidebandRx.slots
+    trx.detect_config(16, 1)
+    # The filterbank chain delays every channel by a whole number of samples; the slot grid is shifted by that lag, as a
+    # receiver's timing alignment does (found once by correlating channel 0 with what was sent, like
+    # tests/test_gpu_fullsize.py::test_cfg5_wideband_chain).
+    rx.rotate(wide, out=streams_out)
+    got0 = torch.view_as_complex(streams_out[0, :20000 + 256].contiguous())
+    corr = torch.stack([(ref0.conj() * got0[l:l + 20000]).sum().abs() for l in range(200)])
+    lag = int(corr.argmax().item())
+    del ref0, got0
+    # Slot slicing without a copy: with K * 625 samples per channel row, slot k of channel c starts at sample
+    # lag + (c * K + k) * 625 of the flat stream buffer - one uniform row pitch, which is all detectAnyBurst needs.  The
+    # last slot of every channel runs `lag` samples into the next row (into the padding for the last channel): those
+    # M rows are processed but not counted.
+    nsl = K - 1
+    n_eff = M * nsl
+    del streams_out
+    flat = torch.zeros((M * K * 625 + 256, 2), dtype=torch.float32, device=device)
+    streams_out = flat[: M * K * 625].view(M, K * 625, 2)
+    slot_rows = torch.as_strided(flat, (n, 625, 2), (1250, 2, 1), storage_offset=2 * lag)
+    res = trx.alloc_results(n, 148)
+
+    # N > 1: the ranks' streams are consecutive time blocks of one long stream; each rank gets the 32 wideband rows in
+    # front of its range from its predecessor (NCCL, once - the source data does not change between steps) and rebuilds
+    # the filter histories from that halo every step instead of carrying state
+    halo = None
+    if world > 1:
+        tail = wide[-osmo_trx_b200.wideband.HALO_ROWS * M:].contiguous()
+        tails = [torch.empty_like(tail) for _ in range(world)]
+        dist.all_gather(tails, tail)
+        if rank > 0:
+            halo = tails[rank - 1]
+        del tails
+
+    def step():
+        if halo is None:
+            rx.reset()
+        else:
+            rx.prime(halo)
+        rx.rotate(wide, out=streams_out)
+        trx.detect_demod(slot_rows, typ, tsc_cm, mt, 4, n_gmsk_soft=148, out=res)
+
+    def cpu():
+        lib, kind = cpu_lib()
+        if kind != "reference":
+            return None
+        import concurrent.futures as cf
+        cores = os.cpu_count() or 1
+        nb_s = 125                                        # one quantum: 52 slots per channel, 3,328 bursts
+        w_h = wide[: nb_s * BL * M].cpu().numpy()
+        # the receive chain is one thread per radio in the reference; `cores` independent radios run side by side
+        with cf.ThreadPoolExecutor(cores) as ex:
+            t0 = time.perf_counter()
+            outs = list(ex.map(lambda _: lib.wideband_rx(w_h, nb_s, M, BL, 65, 48), range(cores)))
+            t_fb = time.perf_counter() - t0
+        st = outs[0]
+        sl = np.ascontiguousarray(st[:, lag:lag + 51 * 625].reshape(M * 51, 625, 2))
+        t_h = np.ascontiguousarray(tsc_cm.view(M, K)[:, :51].cpu().numpy().reshape(-1))
+        reps = max(1, cores // 2)
+        big = np.concatenate([sl] * reps)
+        t0 = time.perf_counter()
+        lib.detect_demod(big, 1, np.concatenate([t_h] * reps), 4, nthreads=cores)
+        t_dd = (time.perf_counter() - t0) / reps * cores     # time for `cores` radios' worth of slots
+        nb_total = cores * M * 51
+        v = nb_total / (t_fb + t_dd)
+        return {"value": v, "unit": "bursts/s", "cores": cores, "kind": kind, "per_core": v / cores,
+                "sample": f"{cores} radios x 125 blocks (64 ch x 51 slots each): Channelizer::rotate + Resampler::rotate block by "
+                          f"block, one thread per radio ({t_fb:.2f} s), then detectAnyBurst + demodAnyBurst on {cores} threads "
+                          f"({t_dd:.2f} s)"}
+
+    def e2e():
+        # wideband float stream in pinned host memory in, soft bits + per-burst records out
+        nq = max(1, min(nblk // Q, 8))
+        nb_e = nq * Q
+        ne = M * (nb_e * 260 // 625 - 1)
+        h_w = torch.empty((nb_e * BL * M, 2), dtype=torch.float32).pin_memory()
+        h_w.copy_(wide[: nb_e * BL * M])
+        nsl_e = nb_e * 260 // 625 - 1
+        h_soft = torch.empty((ne, 148), dtype=torch.float32).pin_memory()
+        h_rc = torch.empty(ne, dtype=torch.int32).pin_memory()
+        h_toa = torch.empty(ne, dtype=torch.float32).pin_memory()
+        d_w = torch.empty((nb_e * BL * M, 2), dtype=torch.float32, device=device)
+        rx_e = osmo_trx_b200.WidebandRx(trx, M, BL)
+        so = torch.empty((M, nb_e * 260, 2), dtype=torch.float32, device=device)
+        sb = torch.empty((ne, 625, 2), dtype=torch.float32, device=device)
+        r_e = trx.alloc_results(ne, 148)
+        t_e = tsc_cm.view(M, K)[:, :nsl_e].contiguous().view(-1)
+
+        def call():
+            d_w.copy_(h_w, non_blocking=True)
+            rx_e.reset()
+            rx_e.rotate(d_w, out=so)
+            sb.view(M, nsl_e, 625, 2).copy_(so[:, lag:lag + nsl_e * 625].view(M, nsl_e, 625, 2))
+            trx.detect_demod(sb, typ[:ne], t_e, mt[:ne], 4, n_gmsk_soft=148, out=r_e)
+            h_soft.copy_(r_e["soft"], non_blocking=True)
+            h_rc.copy_(r_e["rc"], non_blocking=True)
+            h_toa.copy_(r_e["toa"], non_blocking=True)
+
+        v = time_e2e(call, ne, max(3, min(args.steps, 10)), world, device, dist)
+        return {"value": v, "unit": "bursts/s", "h2d_bytes_per_step": int(h_w.numel() * 4), "d2h_bytes_per_step": ne * (592 + 8),
+                "bursts_per_call": ne, "api": "WidebandRx.rotate + Trx.detect_demod on a pinned host wideband stream: "
+                                              "wideband float I/Q in, soft bits + rc + TOA out"}
+
+    in_b = 625 * 48 / 65 * 8      # wideband bytes per slot of one channel
+    return dict(step=step, units=n_eff, unit="bursts/s", metric="GSM bursts/sec detected+demodulated (sps=4)",
+                alg_step=in_b + 592 + 24,
+                alg_kernel={"channelizer64_kernel": 2 * in_b, "resampler16_kernel": in_b + 5000, "demod_kernel": 5000 + 592 + 16,
+                            "corr_kernel": 1216 + 300, "peak_kernel": 300 + 24},
+                cpu=cpu, e2e=e2e, det=lambda: float((res["rc"].view(M, K)[:, :nsl] > 0).float().mean().item()),
+                config={"workload": "cfg5: 64-ARFCN wideband stream -> Channelizer(64,192) -> Resampler(65,48) -> slots -> "
+                                    "detectAnyBurst(TSC,max_toa=4)+demodAnyBurst",
+                        "bursts_per_gpu_per_step": n_eff, "channels": M, "blocks_per_gpu_per_step": nblk, "slot_lag_samples": lag,
+                        "sps": 4, "l2": f"wideband input {wide.numel() * 4 / 1e9:.2f} GB/GPU plus two intermediates of the same size exceed the 126 MB L2",
+                        "sharding": "time blocks of the stream (quantum 125 blocks = 52 slots per channel), 32-row halo re-read "
+                                    "from the source; no data-path collective"})
+
+
+AUX = {"vitac": aux_vitac, "modulate": aux_modulate, "wideband": aux_wideband}
+
+
+def run_aux(args, trx, world, rank, local, device, dist):
+    import torch
+    w = AUX[args.workload](args, trx, device, rank, world, dist)
+    step, n = w["step"], w["units"]
+    l0 = trx.launch_count
+    ms_per_step, clocks = timed_steps(step, args.steps, args.warmup, world, rank, local, device, dist)
+    launches = (trx.launch_count - l0) * args.steps // (args.steps + max(args.warmup, 3))
+    value = world * n / (ms_per_step * 1e-3)
+    trx.profile_begin()
+    for _ in range(args.steps):
+        step()
+    prof = trx.profile_end()
+    peak, peak_src = peaks()
+    kern_ms = {k: v[0] / v[1] for k, v in prof.items()}
+    kern_step_ms = {k: v[0] / args.steps for k, v in prof.items()}
+    launches_per_step = {k: v[1] / args.steps for k, v in prof.items()}
+    roofline = None
+    if kern_step_ms:
+        dom = max(kern_step_ms, key=kern_step_ms.get)
+        dom_alg = w["alg_kernel"].get(dom, w["alg_step"])
+        achieved = dom_alg * n / (kern_step_ms[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_burst": dom_alg,
+                    "bursts_per_launch": n / launches_per_step[dom], "launch_ms": kern_ms[dom], "kernel_ms_per_step": kern_step_ms,
+                    "kernel_launches_per_step": launches_per_step,
+                    "kernel_share_of_step": {k: v / sum(kern_step_ms.values()) for k, v in kern_step_ms.items()},
+                    "step_algorithmic_bytes_per_burst": w["alg_step"],
+                    "step_achieved": w["alg_step"] * n / (ms_per_step * 1e-3) / 1e9,
+                    "step_frac": w["alg_step"] * n / (ms_per_step * 1e-3) / 1e9 / peak}
+    e2e = None if args.no_e2e else w["e2e"]()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = w["cpu"]()
+    if "det" in w:
+        w["config"]["detected_fraction"] = w["det"]()
+    if rank == 0:
+        line = {"metric": w["metric"], "value": value, "unit": w["unit"], "arfcn_equivalents": value / ARFCN_BURSTS_PER_S,
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": w["config"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks}
+        emit(line)
+
+
 def main():
     args = parse()
     _stdout_to_stderr()
@@ -346,6 +907,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     trx = osmo_trx_b200.Trx(local)
+    if args.workload in AUX:
+        run_aux(args, trx, world, rank, local, device, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     n = args.bursts
     rx, typ, tsc, max_toa, bound = make_workload(trx, args.workload, n, seed=1000 + rank, device=device)
@@ -383,6 +949,88 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
+
+    # ---- N > 1: the north star's collective on hardware.  Every step's per-burst records (rc, amp, toa, tsc, ci, flags:
+    #      22 B per burst) are all-gathered and the counters all-reduced over NCCL on a side stream while the next step
+    #      runs (results double buffered); the soft-bit rows stay with the rank that made them, as the datagrams of a
+    #      carrier leave through that rank's host.  `value_with_gather` is the throughput of that loop; the collective
+    #      alone, and the all-gather of the full rows (614 B per burst), are timed beside it. ----
+    gather = None
+    if world > 1:
+        from osmo_trx_b200 import sharding
+        rec_keys = ("rc", "amp", "toa", "tsc", "ci", "flags")
+        outs = [out, trx.alloc_results(n, 148)]
+        gbuf = {k: torch.empty((world,) + tuple(out[k].shape), dtype=out[k].dtype, device=device) for k in rec_keys}
+        side = torch.cuda.Stream(device=device)
+        main = torch.cuda.current_stream()
+        ev_done = [None, None]
+        cnt_box = [None]
+
+        def collect(o):
+            for k in rec_keys:
+                dist.all_gather_into_tensor(gbuf[k], o[k])
+            c = sharding.counters_device(o)
+            dist.all_reduce(c)
+            cnt_box[0] = c
+
+        def step_gather(i):
+            o = outs[i & 1]
+            if ev_done[i & 1] is not None:
+                main.wait_event(ev_done[i & 1])      # the collective that read this result set two steps ago is done
+            trx.detect_demod(rx, typ, tsc, max_toa, bound, n_gmsk_soft=148, out=o)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                collect(o)
+                ev_done[i & 1] = torch.cuda.Event()
+                ev_done[i & 1].record(side)
+
+        for i in range(4):
+            step_gather(i)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ga.record()
+        for i in range(args.steps):
+            step_gather(i)
+        main.wait_stream(side)
+        gb.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ga.elapsed_time(gb)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_g = float(t.item()) / args.steps
+
+        def timed_coll(fn, reps=10):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([a.elapsed_time(b) / reps], device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        ms_rec = timed_coll(lambda: collect(out))
+        gsoft = torch.empty((world,) + tuple(out["soft"].shape), dtype=torch.float32, device=device)
+        ms_soft = timed_coll(lambda: dist.all_gather_into_tensor(gsoft, out["soft"]), reps=5)
+        del gsoft
+        rec_b = sum(out[k].element_size() * out[k][0].numel() for k in rec_keys)
+        gather = {"value_with_gather": world * n / (ms_g * 1e-3), "ms_per_step_with_gather": ms_g,
+                  "record_bytes_per_burst": rec_b, "allgather_bytes_received_per_rank_per_step": (world - 1) * n * rec_b,
+                  "records_collective_alone_ms": ms_rec,
+                  "records_busbw_gbs": (world - 1) * n * rec_b / (ms_rec * 1e-3) / 1e9,
+                  "soft_rows_allgather_alone_ms": ms_soft,
+                  "soft_rows_busbw_gbs": (world - 1) * n * 592 / (ms_soft * 1e-3) / 1e9,
+                  "counters": [int(v) for v in cnt_box[0].tolist()], "counter_names": list(sharding.COUNTER_NAMES),
+                  "what": "NCCL all_gather of the per-burst records + all_reduce of the counters on a side stream, overlapped "
+                          "with the next step; soft rows (592 B per burst) all-gathered alone for the bandwidth figure"}
+        del outs[1], gbuf
 
     # ---- per-kernel device time for the roofline: the same K steps once more with CUDA events around every
     #      kernel on the launching stream (trxb200_profile_begin/end); the headline value above is un-instrumented ----
@@ -461,6 +1109,9 @@ def main():
                "api": "trxb200_pull_host: int16 I/Q slots in (pinned host), TRXD v1 datagrams out (pinned host)",
                "host_cores_bound_near_gpu": near,
                "sent_fraction": float((h_pout["pkt_len"] > 11).float().mean().item()), "gpu_launches": int(e2e_launches)}
+        # the host link's own ceiling for this traffic: bare pinned cudaMemcpyAsync of the same input (2,509 B per slot)
+        # and output (171 B per slot) blocks on two streams at once, no kernels, every rank at the same time
+        e2e["link"] = link_ceiling(h_iq, h_pout["pkt"], ne, world, device, dist, e2e["value"])
         # the same chain with the slots already resident in HBM (CUDA events): what the link, not the GPU, costs
         d_iq = h_iq.to(device)
         d_fn, d_tn = h_fn.to(device), h_tn.to(device)
@@ -522,6 +1173,10 @@ def main():
                            "l2": "inputs (5.2 GB/GPU) far exceed the 126 MB L2; no flush needed",
                            "detected_fraction": det_frac, "sharding": "independent bursts, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_f32": e2e_f32, "gpu_launches": int(launches), "clocks": clocks}
+        if gather is not None:
+            line["gather"] = gather
+            line["config"]["sharding"] = ("independent bursts, no data-path collective; per-burst records all-gathered and "
+                                          "counters all-reduced over NCCL (see gather)")
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -143,6 +143,14 @@ int trxb200_detect_config(trxb200_ctx *ctx, int max_seq_len, int max_attempts);
 int trxb200_detect_sch_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, float thresh, int32_t *rc, float *amp,
 			     float *toa, float *ci, uint8_t *flags);
 
+/* detectSCHBurst(burst, thresh, 4, SCH_DETECT_BUFFER, &ebp) (sigProcLib.cpp:1805-1861): the first SCH acquisition over a
+ * capture of in_len samples per row (12 frames = 60000 in ms/ms_rx_lower.cpp:213-219; in_len a multiple of 4, at most
+ * 4 * 16384 as Resampler::rotate allows).  The capture is decimated, correlated with the 64-symbol sequence at every
+ * symbol position from 0, and detectBurst's peak logic runs over the whole vector; toa[b] is the burst's first symbol
+ * inside the capture (peak - (3 + 39 + 64)).  rc 1 / 0 / -1 as the reference; amp and toa are 0 when nothing is found. */
+int trxb200_detect_sch_buffer_batch(trxb200_ctx *ctx, const float *bufs, int stride, int in_len, int n, float thresh,
+				    int32_t *rc, float *amp, float *toa, float *ci, uint8_t *flags);
+
 /* ---- demodulation: demodAnyBurst (sigProcLib.cpp:2130-2137) for every burst with rc[b] > 0
  *      (rc[b] is the CorrType returned by detection).  soft: f32[n][soft_stride]; GMSK bursts get
  *      `n_gmsk_soft` values (148 = what Transceiver.cpp:799-803 consumes, or 156 = the full
@@ -292,6 +300,16 @@ int trxb200_vitac_detect_ss_batch(trxb200_ctx *ctx, const float *bufs, int strid
 				  const float *cir_in, const int32_t *start_in, int clamp_lo, int clamp_hi, int start_state,
 				  int8_t *bits);
 
+/* First SCH acquisition of the MS side: get_sch_buffer_chan_imp_resp (grgsm_vitac/grgsm_vitac.cpp:298-309) over a capture of
+ * `len` samples per row (12 frames in ms/ms_rx_lower.cpp:160-177: the 54 inner symbols of the extended training sequence are
+ * correlated at every sample position 0 .. len - 512, the strongest 20-window wins) followed, when `bits` is given, by
+ * detect_burst_nb at the position found (ms_rx_lower.cpp:173-177).  Row b holds its capture at bufs + 2*(b*stride + offset);
+ * start[b] is the burst's first sample relative to that (position - 47 symbols; may be negative), cir complex[n][20],
+ * corr_max[n].  The demodulated position is start limited to the row ([-offset, stride - offset - 592]), where the reference
+ * reads outside its buffer. ---- */
+int trxb200_vitac_sch_buffer_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int len, int n,
+				   int8_t *bits, int32_t *start, float *corr_max, float *cir);
+
 /* ---- Resampler (Resampler.h:31-61): rational p/q polyphase resampler, filt_len taps per path.
  *      rotate: in points at the first NEW input sample of each stream; `filt_len` samples of history
  *      precede it in memory (Resampler.cpp:131-150 reads before `in`).  n_streams independent streams
@@ -301,6 +319,11 @@ int trxb200_resampler_create(trxb200_ctx *ctx, int p, int q, int filt_len, float
 void trxb200_resampler_destroy(trxb200_resampler *r);
 int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out,
 			     int out_len, int out_stride, int n_streams);
+/* The same for streams of any length (no MAX_OUTPUT_LEN): because the path indices of Resampler.cpp:131-150 repeat every
+ * p outputs / q inputs, one long call equals the reference's consecutive block calls whenever the blocks are whole periods,
+ * each block's history being the tail of the one before - which is how radioInterfaceMulti.cpp:283-309 calls it. */
+int trxb200_resampler_rotate_stream(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out,
+				    int out_len, int out_stride, int n_streams);
 int trxb200_resampler_taps(trxb200_resampler *r, int path, float *out_host);
 
 /* ---- Channelizer / Synthesis (Channelizer.h:13-31, Synthesis.h:13-32, ChannelizerBase.cpp):
@@ -315,6 +338,15 @@ void trxb200_filterbank_destroy(trxb200_filterbank *fb);
 int trxb200_filterbank_reset(trxb200_filterbank *fb);
 int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *out, int n_blocks);
 int trxb200_synthesis_rotate(trxb200_filterbank *fb, const float *in, float *out, int n_blocks);
+/* The same channelizer step for any number of time samples (total_t >= h_len wideband rows of m samples; block_len only
+ * names the reference's call size) with an output row pitch: channel c's samples land at out[c * out_stride + t], so the
+ * caller can leave room in front of each row for the 16 samples of history Resampler::rotate reads before its input
+ * (radioInterfaceMulti.cpp:283-309 keeps them in the channel's ring buffer).
+ * trxb200_channelizer_prime sets the carried history from the last h_len rows of `prev_in` ([n_prev_t][m]) without
+ * producing output: a rank that processes a time block in the middle of a stream re-reads that halo from the source
+ * (Channelizer.cpp:87-88 is the state it replaces). */
+int trxb200_channelizer_rotate_strided(trxb200_filterbank *fb, const float *in, long total_t, float *out, long out_stride);
+int trxb200_channelizer_prime(trxb200_filterbank *fb, const float *prev_in, long n_prev_t);
 int trxb200_filterbank_taps(trxb200_filterbank *fb, int branch, float *out_host);
 
 #ifdef __cplusplus

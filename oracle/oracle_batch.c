@@ -110,6 +110,23 @@ int orc_detect_sch_batch(const float *bursts, int stride, int blen, int n, float
 	return n;
 }
 
+/* detectSCHBurst(SCH_DETECT_BUFFER) per capture of in_len samples */
+int orc_detect_sch_buffer_batch(const float *bursts, int stride, int in_len, int n, float thresh, int32_t *rc, float *amp, float *toa,
+				float *ci, uint8_t *flags)
+{
+	orc_setup();
+	for (int b = 0; b < n; b++) {
+		orc_ebp ebp;
+		int fl = 0;
+		memset(&ebp, 0, sizeof(ebp));
+		rc[b] = orc_detect_sch_buffer((const ocf *)(bursts + (size_t)b * stride * 2), in_len, thresh, &ebp, &fl);
+		amp[2 * b] = ebp.amp.r; amp[2 * b + 1] = ebp.amp.i;
+		toa[b] = ebp.toa; ci[b] = ebp.ci;
+		if (flags) flags[b] = (uint8_t)fl;
+	}
+	return n;
+}
+
 int orc_demod_batch(const float *bursts, int stride, int blen, int n, const int32_t *rc, const float *amp,
 		    const float *toa, float *ci, int sps, float *soft, int soft_stride, int32_t *nsoft, int nthreads)
 {

@@ -561,6 +561,35 @@ int orc_detect_sch_burst(const ocf *burst, int blen, float thresh, int sps, orc_
 	return rc;
 }
 
+/* detectSCHBurst in its SCH_DETECT_BUFFER state :1805-1861 (first acquisition over a 12-frame capture): the whole capture is
+ * decimated (downsampleBurst(burst, len * 4, len), len = 12 * 8 * 625 / 4 = 15000) and correlated with the 64-symbol sequence
+ * from start 0 (the head of the correlation reads the zero prefix convolve() prepends, :312-334); toa is reported relative to
+ * the burst start (-(3 + 39 + 64)).  in_len: samples of the capture (60000 in the reference). */
+int orc_detect_sch_buffer(const ocf *burst, int in_len, float thresh, orc_ebp *ebp, int *flags)
+{
+	orc_setup();
+	const int len = in_len / 4;
+	if (len < 64 || len > 4096 * 4) return -1;
+	ocf *buf = (ocf *)calloc(16 + (size_t)in_len, sizeof(ocf));
+	ocf *dec = (ocf *)calloc(len, sizeof(ocf));
+	float h[32];
+	memcpy(buf + 16, burst, sizeof(ocf) * (size_t)in_len);
+	taps_cx(T.dnsamp, 16, h);
+	for (int i = 0; i < len; i++)
+		orc_convolve_real((const float *)(buf + 16), in_len, h, 16, (float *)&dec[i], len - i, 4 * i, 1);
+	int rc = detect_burst(dec, len, &T.sch, thresh, 0, len, ebp, flags);
+	free(buf); free(dec);
+	if (rc < 0)
+		return -1;
+	if (!rc) {
+		ebp->amp.r = ebp->amp.i = 0.0f;
+		ebp->toa = 0.0f;
+		return 0;
+	}
+	ebp->toa = ebp->toa - (3 + 39 + 64);
+	return rc;
+}
+
 /* detectAnyBurst :1926-1957 with analyzeTrafficBurst :1887, detectRACHBurst :1782,
  * detectEdgeBurst :1906, detectDummyBurst :1863 */
 int orc_detect_any_burst(const ocf *burst, int blen, unsigned tsc, float thresh, int sps, int type, unsigned max_toa,

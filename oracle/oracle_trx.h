@@ -79,6 +79,7 @@ int orc_detect_any_burst(const ocf *burst, int blen, unsigned tsc, float thresh,
 			 orc_ebp *ebp, int *edge_flags);
 int orc_demod_any_burst(const ocf *burst, int blen, int type, int sps, orc_ebp *ebp, float *soft /*>=444*/);
 /* detectSCHBurst sigProcLib.cpp:1805-1861, SCH_DETECT_FULL */
+int orc_detect_sch_buffer(const ocf *burst, int in_len, float thresh, orc_ebp *ebp, int *edge_flags);
 int orc_detect_sch_burst(const ocf *burst, int blen, float thresh, int sps, orc_ebp *ebp, int *edge_flags);
 int orc_detect_batch(const float *bursts, int stride, int blen, int n, const uint8_t *type, const uint8_t *tsc,
 		     const uint16_t *max_toa, float thresh, int sps, int32_t *rc, float *amp, float *toa,
@@ -133,6 +134,8 @@ int orc_chan_taps(orc_chan *, int branch, float *out /*h_len*/);
 
 /* grgsm_vitac */
 int orc_get_vitac_table(int which, int idx, float *out);
+int orc_vitac_sch_buffer_batch(const float *bufs, int stride, int offset, int len, int n, int8_t *bits, int32_t *start_out,
+			       float *corr_max, float *cir_out);
 int orc_vitac_batch(const float *bufs, int stride, int offset, int n, int is_ab, const uint8_t *tsc, int max_delay,
 		    int clamp_lo, int clamp_hi, int8_t *bits, int32_t *start_out, float *corr_max, float *cir_out,
 		    int nthreads);

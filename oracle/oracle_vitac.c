@@ -332,3 +332,30 @@ int orc_vitac_batch(const float *bufs, int stride, int offset, int n, int is_ab,
 		for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
 	return n;
 }
+
+/* get_sch_buffer_chan_imp_resp grgsm_vitac.cpp:298-309 + detect_burst_nb at the position found (ms_rx_lower.cpp:168-177): the
+ * first SCH acquisition over a capture of `len` samples (12 frames there).  Search windows 0 .. len - 8 * N_SYNC_BITS;
+ * the returned start is relative to the burst's first sample (window - (SYNC_POS + 5) * OSR) and may be negative: rows
+ * carry `offset` samples of head-room, the start is limited to what the row holds. */
+int orc_vitac_sch_buffer_batch(const float *bufs, int stride, int offset, int len, int n, int8_t *bits, int32_t *start_out,
+			       float *corr_max, float *cir_out)
+{
+	vitac_setup();
+	const int c = (3 + 39) + TRAIN_BEGINNING;
+	if (len - N_SYNC_BITS * 8 < CIR_LEN * OSR) return -1;
+	for (int b = 0; b < n; b++) {
+		const ocf *in = (const ocf *)(bufs + (size_t)b * stride * 2) + offset;
+		ocf cir[CIR_LEN * OSR];
+		float cm = 0;
+		int st = get_cir(in, cir, 0, len - N_SYNC_BITS * 8, &sch_seq[TRAIN_BEGINNING], N_SYNC_BITS - 2 * TRAIN_BEGINNING, &cm) - c * OSR;
+		start_out[b] = st;
+		corr_max[b] = cm;
+		if (cir_out) memcpy(cir_out + (size_t)b * 40, cir, sizeof(cir));
+		if (bits) {
+			int lo = -offset, hi = stride - offset - 148 * OSR;
+			int sd = st < lo ? lo : (st > hi ? hi : st);
+			detect_burst(in + sd, cir, 0, bits + (size_t)b * 148, 3, 148);
+		}
+	}
+	return n;
+}

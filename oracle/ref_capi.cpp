@@ -288,6 +288,21 @@ int ref_detect_sch_batch(const float *bursts, int stride, int blen, int n, float
 	return n;
 }
 
+/* detectSCHBurst(burst, thresh, 4, SCH_DETECT_BUFFER, &ebp) sigProcLib.cpp:1805-1861 per capture (in_len = 60000 samples) */
+int ref_detect_sch_buffer_batch(const float *bursts, int stride, int in_len, int n, float thresh, int32_t *rc, float *amp, float *toa,
+				float *ci)
+{
+	for (int b = 0; b < n; b++) {
+		BurstView bv(bursts + (size_t)b * stride * 2, in_len);
+		struct estim_burst_params ebp;
+		ebp.amp = 0.0f; ebp.toa = 0.0f; ebp.tsc = 0; ebp.ci = 0.0f;
+		rc[b] = detectSCHBurst(bv.v, thresh, 4, sch_detect_type::SCH_DETECT_BUFFER, &ebp);
+		amp[2 * b] = ebp.amp.real(); amp[2 * b + 1] = ebp.amp.imag();
+		toa[b] = ebp.toa; ci[b] = ebp.ci;
+	}
+	return n;
+}
+
 /* demodAnyBurst sigProcLib.cpp:2130-2137 for bursts with rc > 0; soft: [n][soft_stride] floats
  * (156 GMSK / 444 EDGE written; rest untouched); nsoft[b] = returned SoftVector size (0 if skipped). */
 int ref_demod_batch(const float *bursts, int stride, int blen, int n, const int32_t *rc, const float *amp,
@@ -661,6 +676,30 @@ int ref_vitac_batch(const float *bufs, int stride, int offset, int n, int is_ab,
 		if (cir_out)
 			memcpy(cir_out + (size_t)b * 40, cir, sizeof(float) * 40);
 	});
+	return n;
+}
+
+/* get_sch_buffer_chan_imp_resp (grgsm_vitac.cpp:298-309) + detect_burst_nb on the position found, as ms_rx_lower.cpp:168-177
+ * does for the first SCH acquisition.  The start may be negative (window - 47 symbols): the demodulated position is limited
+ * to the row, which carries `offset` samples of head-room. */
+int ref_vitac_sch_buffer_batch(const float *bufs, int stride, int offset, int len, int n, int8_t *bits, int32_t *start_out,
+			       float *corr_max, float *cir_out)
+{
+	for (int b = 0; b < n; b++) {
+		const gr_complex *in = (const gr_complex *)(bufs + (size_t)b * stride * 2) + offset;
+		gr_complex cir[CHAN_IMP_RESP_LENGTH * 4];
+		float cmax = 0.0f;
+		int st = get_sch_buffer_chan_imp_resp(in, cir, (unsigned)len, &cmax);
+		start_out[b] = st;
+		corr_max[b] = cmax;
+		if (cir_out)
+			memcpy(cir_out + (size_t)b * 40, cir, sizeof(float) * 40);
+		if (bits) {
+			const int lo = -offset, hi = stride - offset - 148 * 4;
+			const int sd = std::max(lo, std::min(hi, st));
+			detect_burst_nb(in + sd, cir, 0, (sbit_t *)bits + (size_t)b * 148);
+		}
+	}
 	return n;
 }
 

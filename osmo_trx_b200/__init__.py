@@ -293,6 +293,19 @@ class Trx:
         return r
 
     # -- burst-type scheduler --
+    def detect_sch_buffer(self, bufs, in_len=60000, thresh=BURST_THRESH):
+        """detectSCHBurst(SCH_DETECT_BUFFER): bufs float32 [n, stride >= in_len, 2] captures -> rc, amp, toa, ci, flags"""
+        _chk_dev(bufs)
+        n, d = bufs.shape[0], bufs.device
+        r = dict(rc=torch.zeros(n, dtype=torch.int32, device=d), amp=torch.zeros((n, 2), dtype=torch.float32, device=d),
+                 toa=torch.zeros(n, dtype=torch.float32, device=d), ci=torch.zeros(n, dtype=torch.float32, device=d),
+                 flags=torch.zeros(n, dtype=torch.uint8, device=d))
+        self.use_current_stream()
+        self._check(self.lib.trxb200_detect_sch_buffer_batch(self.h, _ptr(bufs), C.c_int(bufs.stride(0) // 2), C.c_int(in_len),
+                                                             C.c_int(n), C.c_float(thresh), _ptr(r["rc"]), _ptr(r["amp"]),
+                                                             _ptr(r["toa"]), _ptr(r["ci"]), _ptr(r["flags"])), "detect_sch_buffer_batch")
+        return r
+
     def expected_corr_type(self, fn, tn, chan_type, handover, chan=None, ext_rach=False, egprs=False, max_toa_nb=4,
                            max_toa_ab=63):
         """Transceiver::expectedCorrType per slot.  fn int32/uint32 [n], tn uint8 [n], chan_type uint8 [n_chan, 8]
@@ -351,11 +364,12 @@ class Trx:
                 C.c_int(length), C.c_int(n), C.c_int(int(base)))
         return rc, y
 
-    def convert_float_short(self, x, scale, mode=0):
+    def convert_float_short(self, x, scale, mode=0, out=None):
         """mode 0: SSE semantics (round to nearest even, saturate); 1: the x86 dispatcher for any length (truncating
         scalar tail of len % 8); 2: base_convert_float_short (truncation)"""
-        _chk_dev(x)
-        out = torch.empty(x.numel(), dtype=torch.int16, device=x.device)
+        _chk_dev(x, out)
+        if out is None:
+            out = torch.empty(x.numel(), dtype=torch.int16, device=x.device)
         self.use_current_stream()
         self._check(self.lib.trxb200_convert_float_short_mode(self.h, _ptr(out), _ptr(x), C.c_float(scale),
                                                               C.c_size_t(x.numel()), C.c_int(mode)), "convert_float_short")
@@ -385,6 +399,24 @@ class Trx:
                                                  C.c_int(clamp[0]), C.c_int(clamp[1]), _ptr(r["bits"]), _ptr(r["start"]),
                                                  _ptr(r["corr_max"]), _ptr(r["cir"])), "vitac_batch")
         return r
+
+
+def _vitac_sch_buffer(self, bufs, offset, length, want_bits=True):
+    """First SCH acquisition (get_sch_buffer_chan_imp_resp + detect_burst_nb): bufs float32 [n, stride, 2], the capture of
+    `length` samples starts at sample `offset` of every row.  -> dict(bits int8 [n,148], start, corr_max, cir [n,20,2])"""
+    _chk_dev(bufs)
+    n, d = bufs.shape[0], bufs.device
+    r = dict(bits=torch.zeros((n, 148), dtype=torch.int8, device=d) if want_bits else None,
+             start=torch.zeros(n, dtype=torch.int32, device=d), corr_max=torch.zeros(n, dtype=torch.float32, device=d),
+             cir=torch.zeros((n, 20, 2), dtype=torch.float32, device=d))
+    self.use_current_stream()
+    self._check(self.lib.trxb200_vitac_sch_buffer_batch(self.h, _ptr(bufs), C.c_int(bufs.stride(0) // 2), C.c_int(offset),
+                                                        C.c_int(length), C.c_int(n), _ptr(r["bits"]), _ptr(r["start"]),
+                                                        _ptr(r["corr_max"]), _ptr(r["cir"])), "vitac_sch_buffer_batch")
+    return r
+
+
+Trx.vitac_sch_buffer = _vitac_sch_buffer
 
 
 def _vitac_detect(self, bufs, offset, cir, start, is_ab=False, clamp=(-39, 39), ss=3):
@@ -437,8 +469,9 @@ class Resampler:
         q * out_len / p == in_len per segment (Resampler.cpp:131-150 restarts its path indices at every call)."""
         _chk_dev(x, out)
         self.trx.use_current_stream()
-        rc = self.trx.lib.trxb200_resampler_rotate(self.h, C.c_void_p(x.data_ptr() + 8 * first), C.c_int(in_len), C.c_int(in_stride),
-                                                   _ptr(out), C.c_int(out_len), C.c_int(out.stride(0) // 2), C.c_int(n_streams))
+        fn = self.trx.lib.trxb200_resampler_rotate_stream if out_len > 4096 else self.trx.lib.trxb200_resampler_rotate
+        rc = fn(self.h, C.c_void_p(x.data_ptr() + 8 * first), C.c_int(in_len), C.c_int(in_stride),
+                _ptr(out), C.c_int(out_len), C.c_int(out.stride(0) // 2), C.c_int(n_streams))
         self.trx._check(rc, "resampler_rotate")
         return out
 
@@ -495,6 +528,26 @@ class Channelizer(_Filterbank):
         self.trx._check(self.trx.lib.trxb200_channelizer_rotate(self.h, _ptr(x), _ptr(out), C.c_int(nb)), "channelizer_rotate")
         return out
 
+    def rotate_into(self, x, out, col0=0):
+        """x [total_t * m, 2] (any total_t >= h_len), out [m, pitch, 2]: channel c's samples go to out[c, col0:col0 + total_t]
+        (room in front of each row for the resampler's history)."""
+        _chk_dev(x, out)
+        total_t = x.shape[0] // self.m
+        assert out.shape[0] == self.m and out.stride(1) == 2 and col0 + total_t <= out.shape[1]
+        self.trx.use_current_stream()
+        rc = self.trx.lib.trxb200_channelizer_rotate_strided(self.h, _ptr(x), C.c_long(total_t), C.c_void_p(out.data_ptr() + 8 * col0),
+                                                            C.c_long(out.stride(0) // 2))
+        self.trx._check(rc, "channelizer_rotate_strided")
+        return out
+
+    def prime(self, prev_in):
+        """Set the carried history from the last h_len rows of prev_in [n_prev_t * m, 2] (time-block sharding: the halo
+        is re-read from the source instead of carried from the previous call)."""
+        _chk_dev(prev_in)
+        self.trx.use_current_stream()
+        self.trx._check(self.trx.lib.trxb200_channelizer_prime(self.h, _ptr(prev_in), C.c_long(prev_in.shape[0] // self.m)),
+                        "channelizer_prime")
+
 
 class Synthesis(_Filterbank):
     """M-channel synthesis filterbank (Synthesis.h:13-32). rotate(): [m, n_blocks*block_len, 2] -> [n_blocks*block_len*m, 2]"""
@@ -509,3 +562,6 @@ class Synthesis(_Filterbank):
         self.trx.use_current_stream()
         self.trx._check(self.trx.lib.trxb200_synthesis_rotate(self.h, _ptr(x), _ptr(out), C.c_int(nb)), "synthesis_rotate")
         return out
+
+
+from .wideband import WidebandRx  # noqa: E402,F401  (after Channelizer / Resampler are defined)

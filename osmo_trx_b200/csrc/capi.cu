@@ -78,6 +78,7 @@ struct trxb200_ctx {
 		// slower than the serial order (1.75-2.4 ms vs 1.71 ms per 2^20 bursts) - corr_nb_kernel and demod_kernel each
 		// need the whole register file of an SM to hide their latencies - so the pipeline is off unless asked for
 		int overlap = 0, chunk_cap = 131072;
+		int resamp_up = 0; // 1: resampler_up_kernel (three outputs per thread from a register window) for interpolating ratios; measured 4.4 ms vs 3.2 ms of resampler16_kernel on the cfg-5 stream (profiles/r2k_*), so off by default
 		int fused = 0; // 1: nb_fused_kernel (one persistent warp-specialised kernel) for detect+demod in the normal-burst geometry; measured 2.75 ms vs 1.76 ms per 2^20 bursts for the three-kernel path (profiles/r2f_*), so off by default
 		int host_chunk = 16384; // slots per stage of the pinned-host pipelines (H2D | kernels | D2H on three streams)
 		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
@@ -328,6 +329,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		trxb200_ctx::Tune &t = ctx->tune;
 		env_int("TRXB200_OVERLAP", t.overlap);
 		env_int("TRXB200_FUSED", t.fused);
+		env_int("TRXB200_RESAMP_UP", t.resamp_up);
 		env_int("TRXB200_CHUNK", t.chunk_cap);
 		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
 		env_int("TRXB200_HOST_CHUNK", t.host_chunk);
@@ -812,6 +814,43 @@ int trxb200_detect_sch_batch(trxb200_ctx *ctx, const float *bursts, int stride, 
 	if (!rc || !amp || !toa || !ci) return fail(ctx, TRXB200_EINVAL, "detect_sch: null output");
 	return launch_detect(ctx, ctx->stream, ctx->ws, bursts, stride, n, nullptr, nullptr, nullptr, 0, thresh, rc, amp, toa, nullptr, ci,
 			     flags, 0, nullptr, false, nullptr, 0, true);
+}
+
+int trxb200_detect_sch_buffer_batch(trxb200_ctx *ctx, const float *bufs, int stride, int in_len, int n, float thresh, int32_t *rc,
+				    float *amp, float *toa, float *ci, uint8_t *flags)
+{
+	DevGuard dg(ctx ? ctx->device : -1);
+	if (!ctx) return TRXB200_EINVAL;
+	const int len = in_len / 4;
+	// len: Resampler::rotate's MAX_OUTPUT_LEN (Resampler.cpp:35) bounds what the reference can decimate in one call
+	if (!bufs || !rc || !amp || !toa || !ci || n < 0 || in_len < 4 * 64 || (in_len & 3) || in_len > stride || len > 4096 * 4)
+		return fail(ctx, TRXB200_EINVAL, "detect_sch_buffer: bad argument");
+	if (n == 0) return TRXB200_OK;
+	cudaStream_t st = ctx->stream;
+	const int tiles = (n + 31) / 32;
+	const size_t dec_b = (size_t)n * (len + kSchBufDecPad) * sizeof(float2);
+	const size_t tile_b = (size_t)tiles * (len + 2 * kPadRows) * kRowPitch * sizeof(float2);
+	SchBufDetParams q;
+	q.bursts = bufs; q.stride = stride; q.in_len = in_len; q.len = len; q.n = n; q.thresh = thresh; q.sinc512 = ctx->d_sinc512;
+	q.rc = rc; q.amp = amp; q.toa = toa; q.ci = ci; q.flags = flags; q.negzero = -0.0f;
+	CK(cudaMallocAsync(&q.dec, dec_b, st));
+	CK(cudaMallocAsync(&q.ctile, tile_b, st));
+	CK(cudaMemsetAsync(q.dec, 0, dec_b, st));
+	CK(cudaMemsetAsync(q.ctile, 0, tile_b, st));
+	const dim3 grid((len + 255) / 256, n);
+	sch_buf_decim_kernel<<<grid, 256, 0, st>>>(q);
+	int r = post_launch(ctx, "sch_buf_decim_kernel");
+	if (!r) {
+		sch_buf_corr_kernel<<<grid, 256, 0, st>>>(q);
+		r = post_launch(ctx, "sch_buf_corr_kernel");
+	}
+	if (!r) {
+		sch_buf_peak_kernel<<<tiles, 32, 0, st>>>(q);
+		r = post_launch(ctx, "sch_buf_peak_kernel");
+	}
+	cudaFreeAsync(q.dec, st);
+	cudaFreeAsync(q.ctile, st);
+	return r;
 }
 
 int trxb200_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, const int32_t *rc, const float *amp,

@@ -94,6 +94,56 @@ int trxb200_vitac_detect_ss_batch(trxb200_ctx *ctx, const float *bufs, int strid
 	return post_launch(ctx, "vitac_kernel");
 }
 
+/* get_sch_buffer_chan_imp_resp (grgsm_vitac.cpp:298-309) over `len` samples of every row + detect_burst_nb at the position
+ * found (ms_rx_lower.cpp:168-177): the first SCH acquisition of a cell. */
+int trxb200_vitac_sch_buffer_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int len, int n, int8_t *bits,
+				   int32_t *start, float *corr_max, float *cir)
+{
+	DevGuard dg(ctx ? ctx->device : -1);
+	if (!ctx) return TRXB200_EINVAL;
+	const int nwin = len - 64 * 8; // search_stop_pos = len - N_SYNC_BITS * 8
+	if (!bufs || !start || !corr_max || !cir || n < 0 || offset < 0 || len <= 0 || offset + len > stride || nwin < 20)
+		return fail(ctx, TRXB200_EINVAL, "vitac_sch_buffer: bad argument");
+	if (stride - offset < 148 * 4) return fail(ctx, TRXB200_EINVAL, "vitac_sch_buffer: row shorter than a burst");
+	if (n == 0) return TRXB200_OK;
+	cudaStream_t st = ctx->stream;
+	float2 *d_corr = nullptr;
+	float *d_pw = nullptr;
+	int32_t *d_shift = nullptr;
+	CK(cudaMallocAsync(&d_corr, (size_t)n * nwin * sizeof(float2), st));
+	CK(cudaMallocAsync(&d_pw, (size_t)n * nwin * sizeof(float), st));
+	CK(cudaMallocAsync(&d_shift, (size_t)n * sizeof(int32_t), st));
+	SchBufParams q;
+	q.bufs = bufs; q.stride = stride; q.offset = offset; q.n = n; q.nwin = nwin; q.corr = d_corr; q.pw = d_pw; q.start = start;
+	q.shift = d_shift; q.shift_lo = -offset; q.shift_hi = stride - offset - 148 * 4; q.corr_max = corr_max; q.cir = cir;
+	sch_buffer_corr_kernel<<<dim3((nwin + 255) / 256, n), 256, 0, st>>>(q);
+	int r = post_launch(ctx, "sch_buffer_corr_kernel");
+	if (!r) {
+		sch_buffer_window_kernel<<<n, 256, 0, st>>>(q);
+		r = post_launch(ctx, "sch_buffer_window_kernel");
+	}
+	if (!r && bits) {
+		VitacParams p;
+		p.bufs = bufs; p.stride = stride; p.offset = offset; p.n = n; p.is_ab = 0; p.tsc = nullptr; p.max_delay = 0;
+		p.clamp_lo = 0; p.clamp_hi = 0; p.bits = bits; p.start = nullptr; p.corr_max = nullptr; p.cir = nullptr;
+		p.cir_in = cir; p.start_in = nullptr; p.row_shift = d_shift; p.start_state = 3;
+		p.nwin_max = 20;
+		p.lo = 0;
+		p.range = 4 * 148;
+		p.pitch = vitac_pitch(p.range);
+		const int wpb = 4;
+		const size_t smem = (size_t)wpb * vitac_warp_floats(p.nwin_max, p.pitch) * sizeof(float);
+		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		int grid = std::max(1, std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8));
+		vitac_kernel<<<grid, wpb * 32, smem, st>>>(p);
+		r = post_launch(ctx, "vitac_kernel");
+	}
+	cudaFreeAsync(d_corr, st);
+	cudaFreeAsync(d_pw, st);
+	cudaFreeAsync(d_shift, st);
+	return r;
+}
+
 /* ---------------- Resampler ---------------- */
 int trxb200_resampler_create(trxb200_ctx *ctx, int p, int q, int filt_len, float bw, trxb200_resampler **out)
 {
@@ -127,18 +177,46 @@ int trxb200_resampler_taps(trxb200_resampler *r, int path, float *out_host)
 	return r->L;
 }
 
+static int resampler_rotate_impl(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out, int out_len,
+				 int out_stride, int n_streams, bool capped);
 int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out, int out_len,
 			     int out_stride, int n_streams)
+{
+	return resampler_rotate_impl(r, in, in_len, in_stride, out, out_len, out_stride, n_streams, true);
+}
+int trxb200_resampler_rotate_stream(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out, int out_len,
+				    int out_stride, int n_streams)
+{
+	return resampler_rotate_impl(r, in, in_len, in_stride, out, out_len, out_stride, n_streams, false);
+}
+static int resampler_rotate_impl(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out, int out_len,
+				 int out_stride, int n_streams, bool capped)
 {
 	if (!r) return TRXB200_EINVAL;
 	trxb200_ctx *ctx = r->ctx;
 	DevGuard dg(ctx->device);
 	if (!in || !out || n_streams < 0 || in_len <= 0 || out_len <= 0)
 		return fail(ctx, TRXB200_EINVAL, "resampler_rotate: bad argument");
-	// check_vec_len (Resampler.cpp:98-129) + MAX_OUTPUT_LEN
-	if (in_len % r->q || out_len % r->p || in_len / r->q != out_len / r->p || out_len > 4096 * 4)
+	// check_vec_len (Resampler.cpp:98-129) + MAX_OUTPUT_LEN; the stream form only keeps the whole-period condition
+	if (in_len % r->q || out_len % r->p || in_len / r->q != out_len / r->p || (capped && out_len > 4096 * 4))
 		return fail(ctx, TRXB200_EINVAL, "resampler_rotate: block length mismatch");
 	if (n_streams == 0) return TRXB200_OK;
+	if (r->L == 16 && r->q <= r->p && r->p <= kRsMaxP && ctx->tune.resamp_up) {
+		// interpolating ratio: three outputs per thread from one register window (filterbank.cu, resampler_up_kernel)
+		static_assert(sizeof(ResampUpParams) <= 32764, "kernel parameter block");
+		ResampUpParams P;
+		P.in = in; P.out = out; P.in_stride = in_stride; P.out_len = out_len; P.out_stride = out_stride; P.n_streams = n_streams;
+		P.p = r->p; P.q = r->q; P.negzero = -0.0f;
+		std::memcpy(P.taps, r->taps.data(), sizeof(float) * (size_t)r->p * 16);
+		const size_t smem = rs_up_smem(r->p, r->q);
+		CK(cudaFuncSetAttribute(resampler_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		const long tiles = (long)n_streams * ((out_len / r->p + kRsTile - 1) / kRsTile);
+		const int grid = (int)std::max<long>(1, std::min<long>(tiles, (long)ctx->sm_count * 2));
+		prof_pre(ctx, ctx->stream);
+		resampler_up_kernel<<<grid, 256, smem, ctx->stream>>>(P);
+		prof_post(ctx, ctx->stream, "resampler_up_kernel");
+		return post_launch(ctx, "resampler_up_kernel");
+	}
 	if (r->L == 16 && r->p <= 256 && r->q < 2 * r->p) {
 		// shared-memory staged, taps-in-registers kernel: P polyphase periods of one stream per tile (about 3,000
 		// input samples, so that a tile's compute phase is long against the latency of its staging loads)
@@ -223,11 +301,30 @@ int trxb200_filterbank_taps(trxb200_filterbank *fb, int branch, float *out_host)
 int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *out, int n_blocks)
 {
 	if (!fb) return TRXB200_EINVAL;
+	if (n_blocks < 0) return fail(fb->ctx, TRXB200_EINVAL, "channelizer_rotate: bad argument");
+	const long total_t = (long)n_blocks * fb->block_len;
+	return trxb200_channelizer_rotate_strided(fb, in, total_t, out, total_t);
+}
+
+int trxb200_channelizer_prime(trxb200_filterbank *fb, const float *prev_in, long n_prev_t)
+{
+	if (!fb) return TRXB200_EINVAL;
 	trxb200_ctx *ctx = fb->ctx;
 	DevGuard dg(ctx->device);
-	if (fb->synth || !in || !out || n_blocks < 0) return fail(ctx, TRXB200_EINVAL, "channelizer_rotate: bad argument");
-	if (n_blocks == 0) return TRXB200_OK;
-	const long total_t = (long)n_blocks * fb->block_len;
+	if (fb->synth || !prev_in || n_prev_t < fb->L) return fail(ctx, TRXB200_EINVAL, "channelizer_prime: bad argument");
+	channelizer_hist_kernel<<<(fb->m * fb->L + 127) / 128, 128, 0, ctx->stream>>>(prev_in, fb->d_hist[fb->cur ^ 1], fb->m, fb->L, n_prev_t);
+	fb->cur ^= 1;
+	return post_launch(ctx, "channelizer_hist_kernel");
+}
+
+int trxb200_channelizer_rotate_strided(trxb200_filterbank *fb, const float *in, long total_t, float *out, long out_stride)
+{
+	if (!fb) return TRXB200_EINVAL;
+	trxb200_ctx *ctx = fb->ctx;
+	DevGuard dg(ctx->device);
+	if (fb->synth || !in || !out || total_t < 0 || out_stride < total_t || (total_t > 0 && total_t < fb->L))
+		return fail(ctx, TRXB200_EINVAL, "channelizer_rotate: bad argument");
+	if (total_t == 0) return TRXB200_OK;
 	int r;
 	if (fb->m == 64 && fb->L == 16 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
 		// 8 x 8 split transform + register sliding-window FIRs (filterbank.cu)
@@ -237,19 +334,19 @@ int trxb200_channelizer_rotate(trxb200_filterbank *fb, const float *in, float *o
 		}
 		const int grid = (int)std::min<long>((total_t + kFbT - 1) / kFbT, (long)ctx->sm_count * 3);
 		prof_pre(ctx, ctx->stream);
-		channelizer64_kernel<<<grid, 256, kCh64Smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		channelizer64_kernel<<<grid, 256, kCh64Smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, out_stride, total_t, fb->d_taps, fb->d_tw);
 		prof_post(ctx, ctx->stream, "channelizer64_kernel");
 		r = post_launch(ctx, "channelizer64_kernel");
 	} else if (fb->L == 16 && (fb->m == 4 || fb->m == 8 || fb->m == 16)) {
-		if (fb->m == 4) launch_channelizer_small<4>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
-		else if (fb->m == 8) launch_channelizer_small<8>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
-		else launch_channelizer_small<16>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, total_t, fb->d_taps, fb->d_tw);
+		if (fb->m == 4) launch_channelizer_small<4>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, out_stride, total_t, fb->d_taps, fb->d_tw);
+		else if (fb->m == 8) launch_channelizer_small<8>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, out_stride, total_t, fb->d_taps, fb->d_tw);
+		else launch_channelizer_small<16>(ctx->sm_count, ctx->stream, in, fb->d_hist[fb->cur], out, out_stride, total_t, fb->d_taps, fb->d_tw);
 		r = post_launch(ctx, "channelizer_small_kernel");
 	} else {
 		const size_t smem = ((size_t)fb->m * 33 + fb->m) * sizeof(float2);
 		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(channelizer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		const int grid = (int)std::min<long>((total_t + 31) / 32, (long)ctx->sm_count * 4);
-		channelizer_kernel<<<grid, 256, smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, fb->m, fb->L, total_t, fb->d_taps, fb->d_tw);
+		channelizer_kernel<<<grid, 256, smem, ctx->stream>>>(in, fb->d_hist[fb->cur], out, out_stride, fb->m, fb->L, total_t, fb->d_taps, fb->d_tw);
 		r = post_launch(ctx, "channelizer_kernel");
 	}
 	if (r) return r;

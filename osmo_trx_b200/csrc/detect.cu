@@ -750,50 +750,75 @@ __device__ __forceinline__ PeakRes peak_lane(const PeakParams &p, const SeqInfo 
 		if (hit) {
 			Cl[(len - 1) * kRowPitch] = make_float2(0.0f, 0.0f);
 			// peakDetect: early/late bisection; the late point is always early + 2 (:1172), i.e. both sit on
-			// the same 1/512 grid position and share their 21 weights
+			// the same 1/512 grid position and share their 21 weights.  The bisection starts at t - 1 and moves by
+			// 1/2, 1/4, ...: after its first step floor(early) is t - 2 or t - 1 for good, so every interpolation of
+			// this burst reads rows t - 12 .. t + 11 only.  They are loaded ONCE into registers (the kernel is bound
+			// by shared-memory wavefronts: 23 row loads per step were 60 % of them) and shifted by one row, once,
+			// for the lanes whose floor is t - 1.
 			float early = t - 1.0f, incr = 0.5f;
+			float2 V[24]; // V[k] = row floor(early) - 10 + k once the first step has fixed the floor
+			{
+				const float2 *cp = Cl + (idx - 12) * kRowPitch;
+#pragma unroll
+				for (int k = 0; k < 24; k++) V[k] = cp[k * kRowPitch];
+			}
+			bool first = true, tie_exit = false;
 #pragma unroll 1
 			for (int it = 0; it < 9; it++) {
 				const int m = (int)floorf(early);
 				const int F = (int)((early - (float)m) * 512.0f);
-				const float2 *cp = Cl + (m - 10) * kRowPitch;
 				const float *wF = stab + brev9(F);
 				float2 e = make_float2(0.0f, 0.0f), l = make_float2(0.0f, 0.0f);
-				float2 v0 = cp[0], v1 = cp[kRowPitch];
+				if (first) {
+					// floor = t - 1: rows t - 11 + d are V[d + 1]
 #pragma unroll
-				for (int d = 0; d < 21; d++) {
-					const float w = wF[512 * d];
-					const float2 v2 = cp[(d + 2) * kRowPitch];
-					e = add2(e, mul2(v0, bc2(w), NZ));
-					l = add2(l, mul2(v2, bc2(w), NZ));
-					v0 = v1;
-					v1 = v2;
+					for (int d = 0; d < 21; d++) {
+						const float w = wF[512 * d];
+						e = add2(e, mul2(V[d + 1], bc2(w), NZ));
+						l = add2(l, mul2(V[d + 3], bc2(w), NZ));
+					}
+				} else {
+#pragma unroll
+					for (int d = 0; d < 21; d++) {
+						const float w = wF[512 * d];
+						e = add2(e, mul2(V[d], bc2(w), NZ));
+						l = add2(l, mul2(V[d + 2], bc2(w), NZ));
+					}
 				}
 				const float ne = norm2(e), nl = norm2(l);
 				if (near_tie(ne, nl)) flags |= 2u;
 				if (ne < nl) early += incr;
 				else if (ne > nl) early -= incr;
-				else break;
+				else { tie_exit = true; }
+				if (first) {
+					first = false;
+					// from here on floor(early) is t - 1 (moved up, or stopped on a tie) or t - 2 (moved down)
+					if (!(ne > nl)) {
+#pragma unroll
+						for (int k = 0; k < 23; k++) V[k] = V[k + 1];
+					}
+				}
+				if (tie_exit) break;
 				incr *= 0.5f;
 			}
 			t = early + 1.0f;
 			float2 xc = make_float2(0.0f, 0.0f);
 			{
+				// floor(t) = floor(early) + 1: rows floor(early) - 9 + d are V[d + 1]
 				const int m = (int)floorf(t);
 				const int F = (int)((t - (float)m) * 512.0f);
-				const float2 *cp = Cl + (m - 10) * kRowPitch;
 				const float *wF = stab + brev9(F);
 #pragma unroll
 				for (int d = 0; d < 21; d++) {
 					const float w = wF[512 * d];
-					xc = add2(xc, mul2(cp[d * kRowPitch], bc2(w), NZ));
+					xc = add2(xc, mul2(V[d + 1], bc2(w), NZ));
 				}
 			}
 			// computeCI
 			const int N = si.len;
 			const int rt = (int)roundf(t);
 			const int ps = at.start + 1 - N + rt;
-			if (ps < 0 || ps + N > 156 || rt < 0 || rt >= len) {
+			if (ps < 0 || ps + N > p.dec_size || rt < 0 || rt >= len) {
 				ci = 0.0f;
 			} else {
 				// S = mean |burst[ps..ps+N)|^2, sequential (:1622-1626); pwr index j = dec index - d0 = rt + k
@@ -951,6 +976,109 @@ clip_kernel(const float *bursts, int stride, int n, int32_t *rc, uint8_t *flags,
 			rc[b] = -2;
 			if (flags) flags[b] |= 4;
 		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// detectSCHBurst in its SCH_DETECT_BUFFER state (sigProcLib.cpp:1805-1861): the first acquisition searches a whole
+// 12-frame capture.  The capture is decimated 4:1 (15,000 samples), correlated with the 64-symbol sequence at every
+// decimated position from start 0 - 960 k complex taps - and the peak logic of detectBurst runs over the 15,000-long
+// vector.  Too long for the per-warp shared-memory tiles above, and rare (once per cell acquisition), so it runs from
+// global memory (L2 resident: 120 KB per capture) with one thread per output:
+//   sch_buf_decim_kernel   out j = sse_conv_real16 order over samples 4j-15 .. 4j (16 zero history samples), stored behind
+//                          the 63 zeros convolve() prepends for a CUSTOM span starting at 0 (:312-334)
+//   sch_buf_corr_kernel    out i = sse_conv_cmplx_8n order over decimated samples i-63 .. i, stored as column (capture & 31)
+//                          of a [kPadRows + len + kPadRows][32] tile: exactly the layout peak_lane() walks
+//   sch_buf_peak_kernel    warp = tile, lanes = captures: peak_lane() (argmax, gates, ratio, bisection, C/I, amp)
+// ---------------------------------------------------------------------------------------------
+struct SchBufDetParams {
+	const float *bursts;
+	int stride, in_len, len, n;
+	float thresh;
+	float2 *dec;   // [n][len + 72]: 63 zeros, len samples, 9 zeros
+	float2 *ctile; // [tiles][len + 2 * kPadRows][32]
+	const float *sinc512;
+	int32_t *rc;
+	float *amp, *toa, *ci;
+	uint8_t *flags;
+	float negzero;
+};
+constexpr int kSchBufDecPad = 72;
+
+__global__ void __launch_bounds__(256)
+sch_buf_decim_kernel(SchBufDetParams p)
+{
+	const int b = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+	if (j >= p.len) return;
+	const float2 NZ = bc2(p.negzero);
+	const float2 *x = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
+	float2 L[4];
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		float2 pr[4];
+#pragma unroll
+		for (int m = 0; m < 4; m++) {
+			const int k = 4 * m + q, idx = 4 * j - 15 + k;
+			const float2 v = idx >= 0 ? __ldg(&x[idx]) : make_float2(0.0f, 0.0f);
+			pr[m] = mul2(v, bc2(c_tab.dnsamp[k]), NZ);
+		}
+		L[q] = add2(add2(pr[0], pr[1]), add2(pr[2], pr[3]));
+	}
+	p.dec[(size_t)b * (p.len + kSchBufDecPad) + 63 + j] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+}
+
+__global__ void __launch_bounds__(256)
+sch_buf_corr_kernel(SchBufDetParams p)
+{
+	const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= p.len) return;
+	const float2 NZ = bc2(p.negzero);
+	const float2 *dx = p.dec + (size_t)b * (p.len + kSchBufDecPad) + i; // decimated sample i - 63 + k sits at dx[k]
+	const float2 *hh = c_tab.seq + c_tab.info[SEQ_SCH].off;
+	float2 A[4], B[4];
+#pragma unroll
+	for (int q = 0; q < 4; q++) { A[q] = make_float2(0.0f, 0.0f); B[q] = make_float2(0.0f, 0.0f); }
+#pragma unroll 2
+	for (int t0 = 0; t0 < 64; t0 += 8) {
+		float2 xw[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) xw[k] = dx[t0 + k];
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const float2 h1 = hh[t0 + q], h2 = hh[t0 + 4 + q];
+			A[q] = add2(A[q], cmul_tap(xw[q], bc2(h1.x), make_float2(h1.y, -h1.y), NZ));
+			B[q] = add2(B[q], cmul_tap(xw[4 + q], bc2(h2.x), make_float2(h2.y, -h2.y), NZ));
+		}
+	}
+	float2 L[4];
+#pragma unroll
+	for (int q = 0; q < 4; q++) L[q] = add2(A[q], B[q]);
+	float2 *tile = p.ctile + (size_t)(b >> 5) * (p.len + 2 * kPadRows) * kRowPitch;
+	tile[(size_t)(kPadRows + i) * kRowPitch + (b & 31)] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+}
+
+__global__ void __launch_bounds__(32)
+sch_buf_peak_kernel(SchBufDetParams q)
+{
+	const int lane = threadIdx.x, b = blockIdx.x * 32 + lane;
+	const bool valid = b < q.n;
+	PeakParams p;
+	p.n = q.n; p.type = nullptr; p.tsc = nullptr; p.max_toa = nullptr; p.round = 0; p.last_round = 1; p.max_toa_bound = 0;
+	p.thresh = q.thresh; p.lmax = q.len; p.ndmax = 1 << 30; p.corr = nullptr; p.pwr = nullptr; p.sinc512 = q.sinc512; p.rc = q.rc;
+	p.amp = q.amp; p.toa = q.toa; p.ci = q.ci; p.tsc_out = nullptr; p.flags = q.flags; p.negzero = q.negzero; p.sch = 1;
+	p.dec_size = q.len;
+	Attempt at;
+	at.seq = SEQ_SCH; at.head = 3 + 39 + 64; at.start = 0; at.len = q.len; at.rc_hit = 1; // toa - (3 + 39 + 64), :1853-1854
+	float2 *Cl = q.ctile + ((size_t)blockIdx.x * (q.len + 2 * kPadRows) + kPadRows) * kRowPitch + lane;
+	const float2 *dec = q.dec + (size_t)(valid ? b : 0) * (q.len + kSchBufDecPad);
+	const PeakRes res = peak_lane(p, c_tab.info, q.sinc512, Cl, valid, valid, at, kTypeSchFull, 0, 0, 0, bc2(q.negzero),
+				      [&](int j) { return norm2(dec[j]); });
+	if (valid) {
+		q.rc[b] = res.rc < 0 ? -1 : res.rc;
+		reinterpret_cast<float2 *>(q.amp)[b] = res.rc > 0 ? res.amp : make_float2(0.0f, 0.0f);
+		q.toa[b] = res.rc > 0 ? res.toa : 0.0f;
+		q.ci[b] = res.ci;
+		if (q.flags) q.flags[b] = (uint8_t)res.flags;
 	}
 }
 

@@ -141,11 +141,137 @@ resampler16_kernel(const float *__restrict__ in, int in_stride, float *__restric
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// resampler_up_kernel — interpolating ratios (q <= p <= kRsMaxP, 16 taps), e.g. the 65/48 of the multi-ARFCN receive path.
+// resampler16_kernel above reads a private 16-sample window per output from shared memory (one data-pipe wavefront per
+// output: 76 % of the LSU peak at a third of the HBM roofline).  Consecutive outputs of an interpolator look at windows
+// that move by 0 or 1 sample, so here a thread produces THREE consecutive outputs of one polyphase period from one
+// 18-sample window held in registers (6 loads per output instead of 16):
+//   rows      a CTA stages a tile of periods; period P's row holds input samples P*q - 15 .. P*q + q - 1 (the 15-sample
+//             halo is stored again per row) at an odd pitch, so that lanes = consecutive periods read any row offset
+//             without bank conflicts
+//   items     (residue group g = outputs 3g .. 3g+2 of the period, block of 32 periods): lanes = periods.  The window
+//             offsets and the three tap sets depend only on g, i.e. they are warp uniform: offsets are immediates after a
+//             uniform branch, taps come from the kernel's parameter block (constant bank), nothing per lane
+//   outputs   go to a [period][p] tile in shared memory (odd pitch: conflict free) and leave as one contiguous,
+//             coalesced run of the stream
+// Same sse_conv_real16 tree per output on the packed pipe as resampler16_kernel: bit-identical to Resampler::rotate.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRsMaxP = 96;
+constexpr int kRsTile = 64; // periods per tile
+struct ResampUpParams {
+	const float *in;
+	float *out;
+	int in_stride, out_len, out_stride, n_streams, p, q;
+	float negzero;
+	float taps[kRsMaxP * 16];
+};
+__host__ __device__ inline int rs_up_in_pitch(int q) { return (q + 15) | 1; }
+__host__ __device__ inline int rs_up_out_pitch(int p) { return p | 1; }
+__host__ __device__ inline size_t rs_up_smem(int p, int q) { return (size_t)kRsTile * (2 * rs_up_in_pitch(q) + rs_up_out_pitch(p)) * sizeof(float2); }
+
+template <int D>
+__device__ __forceinline__ float2 rs_tree(const float2 (&x)[18], const float (&h)[16], float2 nz)
+{
+	float2 L[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const float2 p0 = mul2(x[D + j], bc2(h[j]), nz);
+		const float2 p1 = mul2(x[D + 4 + j], bc2(h[4 + j]), nz);
+		const float2 p2 = mul2(x[D + 8 + j], bc2(h[8 + j]), nz);
+		const float2 p3 = mul2(x[D + 12 + j], bc2(h[12 + j]), nz);
+		L[j] = add2(add2(p0, p1), add2(p2, p3));
+	}
+	return add2(add2(L[0], L[1]), add2(L[2], L[3]));
+}
+
+__global__ void __launch_bounds__(256, 2)
+resampler_up_kernel(const __grid_constant__ ResampUpParams P)
+{
+	extern __shared__ __align__(16) float2 rsu[];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int p = P.p, q = P.q;
+	const int ipitch = rs_up_in_pitch(q), opitch = rs_up_out_pitch(p);
+	float2 *rout = rsu + (size_t)2 * kRsTile * ipitch; // [kRsTile][opitch] behind the two input buffers [kRsTile][ipitch]
+	const float2 nz = make_float2(P.negzero, P.negzero);
+	const int periods_total = P.out_len / p;
+	const int tiles_per_stream = (periods_total + kRsTile - 1) / kRsTile;
+	const long total_tiles = (long)P.n_streams * tiles_per_stream;
+	const int ngroups = (p + 2) / 3;
+	const int rowlen = q + 15;
+	const unsigned rin_s = (unsigned)__cvta_generic_to_shared(rsu);
+	// stage: row r <- input samples (per0 + r) * q - 15 .. + q - 1; warps walk rows, lanes walk a row (coalesced 8-byte
+	// asynchronous copies, no index arithmetic beyond adds)
+	auto issue = [&](long tile_, int buf_) {
+		const int s_ = (int)(tile_ / tiles_per_stream), per0_ = (int)(tile_ % tiles_per_stream) * kRsTile;
+		const int np_ = min(kRsTile, periods_total - per0_);
+		const float2 *src = reinterpret_cast<const float2 *>(P.in) + (size_t)s_ * P.in_stride + ((long)per0_ * q - 15);
+		const unsigned dst = rin_s + 8u * (unsigned)(buf_ * kRsTile * ipitch);
+		for (int r = warp; r < np_; r += 8)
+			for (int c = lane; c < rowlen; c += 32)
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (unsigned)(r * ipitch + c)), "l"(src + (long)r * q + c)
+					     : "memory");
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	int buf = 0;
+	if ((long)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+	for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
+		const int s = (int)(tile / tiles_per_stream), per0 = (int)(tile % tiles_per_stream) * kRsTile;
+		const int np = min(kRsTile, periods_total - per0);
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads(); // this tile's rows have landed; the other input buffer and the output tile are free
+		if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x, buf ^ 1);
+		const float2 *rin = rsu + (size_t)buf * kRsTile * ipitch;
+		// ---- items: residue group g (warp uniform) x block of 32 periods (lanes) ----
+		const int nblk = (np + 31) >> 5;
+		for (int g = warp; g < ngroups; g += 8) {
+			const int rho0 = 3 * g;
+			const int r1 = rho0 + 1 < p ? rho0 + 1 : rho0, r2 = rho0 + 2 < p ? rho0 + 2 : rho0;
+			const int off0 = (q * rho0) / p;
+			const int d1 = (q * r1) / p - off0, d2 = (q * r2) / p - off0;
+			float h0[16], h1[16], h2[16];
+			{
+				const float *t0 = P.taps + ((q * rho0) % p) * 16, *t1 = P.taps + ((q * r1) % p) * 16, *t2 = P.taps + ((q * r2) % p) * 16;
+#pragma unroll
+				for (int k = 0; k < 16; k++) { h0[k] = t0[k]; h1[k] = t1[k]; h2[k] = t2[k]; }
+			}
+			const bool full = off0 + 18 <= rowlen;
+			for (int blk = 0; blk < nblk; blk++) {
+				const int r = blk * 32 + lane;
+				if (r < np) {
+					const float2 *row = rin + (size_t)r * ipitch + off0;
+					float2 x[18];
+					if (full) {
+#pragma unroll
+						for (int k = 0; k < 18; k++) x[k] = row[k];
+					} else {
+#pragma unroll
+						for (int k = 0; k < 18; k++) x[k] = (off0 + k < rowlen) ? row[k] : make_float2(0.0f, 0.0f);
+					}
+					float2 *orow = rout + (size_t)r * opitch + rho0;
+					orow[0] = rs_tree<0>(x, h0, nz);
+					if (rho0 + 1 < p) orow[1] = d1 ? rs_tree<1>(x, h1, nz) : rs_tree<0>(x, h1, nz);
+					if (rho0 + 2 < p) orow[2] = d2 == 2 ? rs_tree<2>(x, h2, nz) : (d2 == 1 ? rs_tree<1>(x, h2, nz) : rs_tree<0>(x, h2, nz));
+				}
+			}
+		}
+		__syncthreads();
+		// ---- the tile's outputs are one contiguous run of the stream ----
+		float2 *dst = reinterpret_cast<float2 *>(P.out) + (size_t)s * P.out_stride + (size_t)per0 * p;
+		if (opitch == p) {
+			for (int idx = tid; idx < np * p; idx += 256) dst[idx] = rout[idx];
+		} else {
+			for (int r = warp; r < np; r += 8)
+				for (int c = lane; c < p; c += 32) dst[r * p + c] = rout[(size_t)r * opitch + c];
+		}
+	}
+}
+
 // ---- channelizer ----
 // in: [n_blocks*block_len][m] wideband samples (time-major), hist_in: [m][L] previous tail per branch,
 // out: [m][n_blocks*block_len].  grid.x tiles time by T = 32.
 __global__ void __launch_bounds__(256)
-channelizer_kernel(const float *__restrict__ in, const float *__restrict__ hist_in, float *__restrict__ out,
+channelizer_kernel(const float *__restrict__ in, const float *__restrict__ hist_in, float *__restrict__ out, long out_stride,
 		   int m, int L, long total_t, const float *__restrict__ sub, const float2 *__restrict__ tw)
 {
 	extern __shared__ __align__(16) float2 csm[];
@@ -187,7 +313,7 @@ channelizer_kernel(const float *__restrict__ in, const float *__restrict__ hist_
 				idx += c; if (idx >= m) idx -= m;
 			}
 			if (t < total_t)
-				reinterpret_cast<float2 *>(out)[(size_t)c * total_t + t] = make_float2(ar, ai);
+				reinterpret_cast<float2 *>(out)[(size_t)c * out_stride + t] = make_float2(ar, ai);
 		}
 	}
 }
@@ -300,9 +426,9 @@ __device__ __forceinline__ void fb_pass_a(float2 (&a)[8], const float2 (&twa)[8]
 }
 
 // in: [total_t][64] wideband samples (time-major), hist_in: [64][16] previous tail per branch,
-// out: [64][total_t]
+// out: [64][out_stride] (total_t samples written per row)
 __global__ void __launch_bounds__(256, 3)
-channelizer64_kernel(const float *__restrict__ in, const float *__restrict__ hist_in, float *__restrict__ out, long total_t,
+channelizer64_kernel(const float *__restrict__ in, const float *__restrict__ hist_in, float *__restrict__ out, long out_stride, long total_t,
 		     const float *__restrict__ sub, const float2 *__restrict__ tw)
 {
 	extern __shared__ __align__(16) float2 fsm[];
@@ -394,7 +520,7 @@ channelizer64_kernel(const float *__restrict__ in, const float *__restrict__ his
 			if (t < total_t) {
 #pragma unroll
 				for (int k2 = 0; k2 < 8; k2++)
-					reinterpret_cast<float2 *>(out)[(size_t)(w + 8 * k2) * total_t + t] = c[k2];
+					reinterpret_cast<float2 *>(out)[(size_t)(w + 8 * k2) * out_stride + t] = c[k2];
 			}
 		}
 	}
@@ -509,7 +635,7 @@ template <int M> struct FbSmall {
 
 template <int M>
 __global__ void __launch_bounds__(256)
-channelizer_small_kernel(const float *__restrict__ in, const float *__restrict__ hist_in, float *__restrict__ out, long total_t,
+channelizer_small_kernel(const float *__restrict__ in, const float *__restrict__ hist_in, float *__restrict__ out, long out_stride, long total_t,
 			 const float *__restrict__ sub, const float2 *__restrict__ tw)
 {
 	using C = FbSmall<M>;
@@ -596,7 +722,7 @@ channelizer_small_kernel(const float *__restrict__ in, const float *__restrict__
 						ar = fmaf(yv[q].x, ww.x, ar); ar = fmaf(-yv[q].y, ww.y, ar);
 						ai = fmaf(yv[q].x, ww.y, ai); ai = fmaf(yv[q].y, ww.x, ai);
 					}
-					reinterpret_cast<float2 *>(out)[(size_t)c * total_t + t] = make_float2(ar, ai);
+					reinterpret_cast<float2 *>(out)[(size_t)c * out_stride + t] = make_float2(ar, ai);
 				}
 			}
 		}
@@ -671,13 +797,13 @@ synthesis_small_kernel(const float *__restrict__ in, const float *__restrict__ t
 }
 
 template <int M>
-static void launch_channelizer_small(int sm_count, cudaStream_t st, const float *in, const float *hist, float *out, long total_t,
-				     const float *sub, const float2 *tw)
+static void launch_channelizer_small(int sm_count, cudaStream_t st, const float *in, const float *hist, float *out, long out_stride,
+				     long total_t, const float *sub, const float2 *tw)
 {
 	using C = FbSmall<M>;
 	const long ntiles = (total_t + C::T - 1) / C::T;
 	const int grid = (int)std::max<long>(1, std::min<long>(ntiles, (long)sm_count * 4));
-	channelizer_small_kernel<M><<<grid, 256, C::kChSmem, st>>>(in, hist, out, total_t, sub, tw);
+	channelizer_small_kernel<M><<<grid, 256, C::kChSmem, st>>>(in, hist, out, out_stride, total_t, sub, tw);
 }
 template <int M>
 static void launch_synthesis_small(int sm_count, cudaStream_t st, const float *in, const float *tail, float *out, long total_t,

@@ -41,6 +41,7 @@ struct PeakParams {
 	uint8_t *tsc_out, *flags;
 	float negzero;
 	int sch; // every burst is a SCH_DETECT_FULL search (type / tsc / max_toa are not read)
+	int dec_size = 156; // samples of the decimated burst computeCI may read (15000 for the SCH buffer search)
 };
 
 struct DemodParams {

@@ -29,6 +29,7 @@ struct VitacParams {
 	int nwin_max;
 	const float *cir_in;	  // complex[n][20] caller's channel estimates, or null: estimate here (get_*_imp_resp)
 	const int32_t *start_in; // burst start per burst when cir_in is given
+	const int32_t *row_shift = nullptr; // cir_in mode: per-burst sample offset added to the row base (the burst found by a long search); start is 0 then
 	int start_state = 3;	  // viterbi_detector's start state (detect_burst_* default 3, grgsm_vitac.cpp:114-121)
 	int lo, range, pitch; // staged part of each row: samples [lo, lo + range) relative to the burst; plane pitch of the window
 };
@@ -91,6 +92,22 @@ vitac_kernel(VitacParams p)
 	const int npairs = (p.n + 1) >> 1;
 	for (int pair = blockIdx.x * wpb + warp; pair < npairs; pair += gridDim.x * wpb) {
 		__syncwarp();
+		// the rows of the warp's NEXT pair are requested into L2 now: the staging loads below otherwise wait on HBM with
+		// nothing else for this warp to do (21 % of the kernel's stall samples sat on them, profiles/r1x_vitac_summary.txt)
+		{
+			const int np_ = pair + gridDim.x * wpb;
+			if (np_ < npairs) {
+				for (int h = 0; h < 2; h++) {
+					const int b = 2 * np_ + h;
+					if (b < p.n) {
+						const char *row = reinterpret_cast<const char *>(reinterpret_cast<const float2 *>(p.bufs) + (size_t)b * p.stride + p.offset + p.lo +
+											       (p.row_shift ? p.row_shift[b] : 0));
+						for (int o = lane * 128; o < p.range * 8; o += 32 * 128)
+							asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+					}
+				}
+			}
+		}
 		for (int h = 0; h < 2; h++) {
 			const int b = 2 * pair + h;
 			if (b >= p.n) {
@@ -99,7 +116,7 @@ vitac_kernel(VitacParams p)
 				__syncwarp(); // the ACS stage reads these
 				continue;
 			}
-			const float2 *in = reinterpret_cast<const float2 *>(p.bufs) + (size_t)b * p.stride + p.offset + p.lo;
+			const float2 *in = reinterpret_cast<const float2 *>(p.bufs) + (size_t)b * p.stride + p.offset + p.lo + (p.row_shift ? p.row_shift[b] : 0);
 			const float2 *tseq = p.is_ab == 2 ? &c_tab.vitac_sch[5]
 						   : p.is_ab ? &c_tab.vitac_access[5] : &c_tab.vitac_norm[p.tsc ? (p.tsc[b] > 8 ? 8 : p.tsc[b]) : 0][5];
 			// ---- stage the row ----
@@ -122,7 +139,7 @@ vitac_kernel(VitacParams p)
 			if (p.cir_in) {
 				// detect_burst_nb / detect_burst_ab with the caller's channel estimate (:105-123): no search
 				if (lane < kCirLen) cb[lane] = reinterpret_cast<const float2 *>(p.cir_in)[(size_t)b * kCirLen + lane];
-				st = max(p.clamp_lo, min(p.clamp_hi, p.start_in[b]));
+				st = p.start_in ? max(p.clamp_lo, min(p.clamp_hi, p.start_in[b])) : 0;
 				__syncwarp();
 			} else {
 			// ---- correlation per search window (correlate_sequence :148-156) ----
@@ -321,6 +338,102 @@ vitac_kernel(VitacParams p)
 					}
 				}
 			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// First SCH acquisition: get_sch_buffer_chan_imp_resp (grgsm_vitac.cpp:298-309) over a capture of `len` samples
+// (12 frames in ms_rx_lower.cpp:160-177).  get_chan_imp_resp's three loops (:183-235) become
+//   sch_buffer_corr_kernel    one thread per search window: correlate_sequence over the 54 inner training symbols,
+//                             4 samples apart (lanes = consecutive windows: coalesced), the reference's sequential
+//                             float order, |c|^2 through double as std::pow(abs(c), 2) evaluates it;
+//   sch_buffer_window_kernel  one CTA per capture: the 20-window energy is a RUNNING float sum in the reference
+//                             (windowSum += p[i] - p[i-20]) and its first maximum decides the burst position, so the
+//                             sum stays serial: the CTA stages 2,048 differences at a time in shared memory, thread 0
+//                             adds them in order; then the 20 channel taps, corr_max and the start are written.
+// detect_burst_nb at the position found is vitac_kernel with the taps just estimated (row_shift).
+// ---------------------------------------------------------------------------------------------
+struct SchBufParams {
+	const float *bufs;
+	int stride, offset, n, nwin;
+	float2 *corr;   // [n][nwin]
+	float *pw;	// [n][nwin]
+	int32_t *start, *shift;
+	int shift_lo, shift_hi;
+	float *corr_max, *cir;
+};
+
+__global__ void __launch_bounds__(256)
+sch_buffer_corr_kernel(SchBufParams p)
+{
+	const int b = blockIdx.y, w = blockIdx.x * 256 + threadIdx.x;
+	if (w >= p.nwin) return;
+	const float2 *x = reinterpret_cast<const float2 *>(p.bufs) + (size_t)b * p.stride + p.offset + w;
+	const float2 *tseq = &c_tab.vitac_sch[5];
+	float rr = 0.0f, ri = 0.0f;
+#pragma unroll 6
+	for (int ii = 0; ii < 54; ii++) {
+		const float2 s = tseq[ii], v = __ldg(&x[ii * kOSR]);
+		rr = fa(rr, fs(fm(s.x, v.x), fm(s.y, v.y)));
+		ri = fa(ri, fa(fm(s.x, v.y), fm(s.y, v.x)));
+	}
+	const float2 c = make_float2(rr / 54.0f, -ri / 54.0f);
+	p.corr[(size_t)b * p.nwin + w] = c;
+	const float a = cabs_ref(c);
+	p.pw[(size_t)b * p.nwin + w] = (float)((double)a * (double)a);
+}
+
+__global__ void __launch_bounds__(256)
+sch_buffer_window_kernel(SchBufParams p)
+{
+	__shared__ float d[2048];
+	__shared__ int s_best;
+	const int b = blockIdx.x, tid = threadIdx.x;
+	const float *pw = p.pw + (size_t)b * p.nwin;
+	float ws = 0.0f, best = 0.0f;
+	int bi = 0;
+	if (tid == 0) {
+		for (int i = 0; i < kCirLen; i++) ws = fa(ws, pw[i]);
+		best = ws;
+	}
+	for (int i0 = kCirLen; i0 < p.nwin; i0 += 2048) {
+		const int cnt = min(2048, p.nwin - i0);
+		__syncthreads();
+		for (int k = tid; k < cnt; k += 256) d[k] = fs(pw[i0 + k], pw[i0 + k - kCirLen]);
+		__syncthreads();
+		if (tid == 0) {
+			int k = 0;
+			for (; k + 8 <= cnt; k += 8) {
+				float v[8];
+#pragma unroll
+				for (int u = 0; u < 8; u++) v[u] = d[k + u];
+#pragma unroll
+				for (int u = 0; u < 8; u++) {
+					ws = fa(ws, v[u]);
+					if (best < ws) { best = ws; bi = i0 + k + u - kCirLen + 1; }
+				}
+			}
+			for (; k < cnt; k++) {
+				ws = fa(ws, d[k]);
+				if (best < ws) { best = ws; bi = i0 + k - kCirLen + 1; }
+			}
+		}
+	}
+	if (tid == 0) s_best = bi;
+	__syncthreads();
+	bi = s_best;
+	if (tid < 32) {
+		const float2 c = tid < kCirLen ? p.corr[(size_t)b * p.nwin + bi + tid] : make_float2(0.0f, 0.0f);
+		float a = tid < kCirLen ? cabs_ref(c) : 0.0f;
+#pragma unroll
+		for (int o = 16; o; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+		if (tid < kCirLen) reinterpret_cast<float2 *>(p.cir)[(size_t)b * kCirLen + tid] = c;
+		if (tid == 0) {
+			const int st = bi - 47 * kOSR; // search_start_pos 0, search centre SYNC_POS + TRAIN_BEGINNING = 47 symbols
+			p.corr_max[b] = a;
+			p.start[b] = st;
+			p.shift[b] = max(p.shift_lo, min(p.shift_hi, st));
 		}
 	}
 }

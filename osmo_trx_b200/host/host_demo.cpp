@@ -25,7 +25,7 @@ static void wr(FILE *f, const void *p, size_t n) { fwrite(p, 1, n, f); }
 
 int main(int argc, char **argv)
 {
-	if (argc != 4) { fprintf(stderr, "usage: host_demo dd|sch|mod|conv|vit in out\n"); return 2; }
+	if (argc != 4) { fprintf(stderr, "usage: host_demo dd|sch|acq|mod|conv|vit in out\n"); return 2; }
 	const std::string mode = argv[1];
 	FILE *fi = fopen(argv[2], "rb"), *fo = fopen(argv[3], "wb");
 	if (!fi || !fo) { perror("open"); return 2; }
@@ -56,7 +56,8 @@ int main(int argc, char **argv)
 			wr(fo, soft.data(), 444 * 4);
 		}
 	} else if (mode == "sch") {
-		// detectSCHBurst(burst, BURST_THRESH, 4, SCH_DETECT_FULL) per burst; the other states must be refused
+		// detectSCHBurst(burst, BURST_THRESH, 4, SCH_DETECT_FULL) per burst; the BUFFER state needs its 12-frame capture and
+		// the NARROW state is refused
 		for (int k = 0; k < n; k++) {
 			signalVector burst(625);
 			if (!rd(fi, burst.begin(), 625 * 8)) return 2;
@@ -64,8 +65,35 @@ int main(int argc, char **argv)
 			ebp = estim_burst_params{ complex(0, 0), 0.0f, 0, 0.0f };
 			const int rc = detectSCHBurst(burst, BURST_THRESH, 4, sch_detect_type::SCH_DETECT_FULL, &ebp);
 			if (k == 0 && detectSCHBurst(burst, BURST_THRESH, 4, sch_detect_type::SCH_DETECT_BUFFER, &ebp) >= 0) return 5;
+			if (k == 0 && detectSCHBurst(burst, BURST_THRESH, 4, sch_detect_type::SCH_DETECT_NARROW, &ebp) >= 0) return 5;
 			float rec[5] = { (float)rc, ebp.amp.real(), ebp.amp.imag(), ebp.toa, ebp.ci };
 			wr(fo, rec, sizeof(rec));
+		}
+	} else if (mode == "acq") {
+		// first SCH acquisition over 12-frame captures (ms_rx_lower.cpp:160-219): detectSCHBurst(SCH_DETECT_BUFFER), and
+		// get_sch_buffer_chan_imp_resp + detect_burst_nb at the position found
+		const int L = 60000;
+		initvita();
+		for (int k = 0; k < n; k++) {
+			signalVector cap(L);
+			if (!rd(fi, cap.begin(), (size_t)L * 8)) return 2;
+			estim_burst_params ebp;
+			ebp = estim_burst_params{ complex(0, 0), 0.0f, 0, 0.0f };
+			const int rc = detectSCHBurst(cap, BURST_THRESH, 4, sch_detect_type::SCH_DETECT_BUFFER, &ebp);
+			float rec[5] = { (float)rc, ebp.amp.real(), ebp.amp.imag(), ebp.toa, ebp.ci };
+			wr(fo, rec, sizeof(rec));
+			gr_complex cir[CHAN_IMP_RESP_LENGTH * 4];
+			float cmax = 0.0f;
+			const gr_complex *ss = reinterpret_cast<const gr_complex *>(cap.begin());
+			int32_t start = get_sch_buffer_chan_imp_resp(ss, cir, L, &cmax);
+			sbit_t bits[148];
+			const int sd = start < 0 ? 0 : (start > L - 592 ? L - 592 : start);
+			vitac_input_headroom(0, 592 + 64 > L - sd ? L - sd : 592 + 64);
+			detect_burst_nb(&ss[sd], cir, 0, bits);
+			wr(fo, &start, 4);
+			wr(fo, &cmax, 4);
+			wr(fo, cir, sizeof(cir));
+			wr(fo, bits, 148);
 		}
 	} else if (mode == "mod") {
 		for (int k = 0; k < n; k++) {

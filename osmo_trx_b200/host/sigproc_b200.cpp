@@ -328,19 +328,30 @@ int detectAnyBurst(const signalVector &burst, unsigned tsc, float threshold, int
 	return r;
 }
 
-// sigProcLib.cpp:1805-1861.  Only the single-burst state is built (trxb200_detect_sch_batch): the NARROW state reads past
-// its 8-sample decimated vector in the reference and the BUFFER state searches a 12-frame capture - both fail loudly here.
+// sigProcLib.cpp:1805-1861.  SCH_DETECT_FULL (one burst, trxb200_detect_sch_batch) and SCH_DETECT_BUFFER (the 12-frame
+// capture of the first acquisition, trxb200_detect_sch_buffer_batch) are built; the NARROW state reads past its 8-sample
+// decimated vector in the reference and fails loudly here.
 int detectSCHBurst(signalVector &burst, float threshold, int sps, sch_detect_type state, struct estim_burst_params *ebp)
 {
-	if (!ebp || sps != 4 || state != sch_detect_type::SCH_DETECT_FULL) return -1;
+	if (!ebp || sps != 4 || (state != sch_detect_type::SCH_DETECT_FULL && state != sch_detect_type::SCH_DETECT_BUFFER)) return -1;
 	std::lock_guard<std::mutex> lk(g_mu);
 	if (!g_ctx) return -1;
-	float *db = upload_burst(burst, d_in);
 	float *dres = (float *)d_b.get(64);
-	if (!db || !dres) return -1;
+	if (!dres) return -1;
 	int32_t *drc = (int32_t *)dres;
 	float *damp = dres + 2, *dtoa = dres + 4, *dci = dres + 5;
+	if (state == sch_detect_type::SCH_DETECT_BUFFER) {
+		const int in_len = (12 * 8 * 625 / 4) * 4; // downsampleBurst(burst, len * 4, len), len = 15000 (:1827,1841)
+		if (burst.size() < (size_t)in_len) return -1; // the reference would copy past the end of the vector
+		float *db = (float *)d_in.get((size_t)in_len * 8);
+		if (!db || trxb200_copy_to_device(g_ctx, db, burst.begin(), (size_t)in_len * 8) != TRXB200_OK) return -1;
+		if (!ok(trxb200_detect_sch_buffer_batch(g_ctx, db, in_len, in_len, 1, threshold, drc, damp, dtoa, dci, nullptr), "detect_sch_buffer_batch"))
+			return -1;
+	} else {
+	float *db = upload_burst(burst, d_in);
+	if (!db) return -1;
 	if (!ok(trxb200_detect_sch_batch(g_ctx, db, 625, 1, threshold, drc, damp, dtoa, dci, nullptr), "detect_sch_batch")) return -1;
+	}
 	float hres[8];
 	if (!ok(trxb200_copy_to_host(g_ctx, hres, dres, 32), "copy")) return -1;
 	int32_t r;
@@ -635,6 +646,28 @@ int get_sch_chan_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp)
 	float cmax = 0.0f;
 	if (!run_vitac(input, 2, 0, 0, -kVitPad, 1 << 20, chan_imp_resp, &cmax, &start, nullptr)) return 0;
 	return start;
+}
+
+// grgsm_vitac.cpp:298-309: the first SCH acquisition over a capture of `len` samples starting at `input`
+int get_sch_buffer_chan_imp_resp(const gr_complex *input, gr_complex *chan_imp_resp, unsigned int len, float *corr_max)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g_ctx || !input || !chan_imp_resp || len < 64 * 8 + 20) return 0;
+	float *drow = (float *)d_in.get((size_t)len * 8);
+	float *dres = (float *)d_b.get(16 + 20 * 8);
+	if (!drow || !dres) return 0;
+	if (trxb200_copy_to_device(g_ctx, drow, input, (size_t)len * 8) != TRXB200_OK) return 0;
+	int32_t *dstart = (int32_t *)dres;
+	float *dcmax = dres + 1, *dcir = dres + 4;
+	if (!ok(trxb200_vitac_sch_buffer_batch(g_ctx, drow, (int)len, 0, (int)len, 1, nullptr, dstart, dcmax, dcir), "vitac_sch_buffer_batch"))
+		return 0;
+	float h[4 + 40];
+	if (trxb200_copy_to_host(g_ctx, h, dres, sizeof(h)) != TRXB200_OK) return 0;
+	int32_t st;
+	memcpy(&st, &h[0], 4);
+	if (corr_max) *corr_max = h[1];
+	memcpy((void *)chan_imp_resp, &h[4], 20 * 8);
+	return st;
 }
 
 // detect_burst_nb / detect_burst_ab (grgsm_vitac.cpp:105-123): matched filter + Viterbi with the CALLER's channel estimate

@@ -25,6 +25,20 @@ def shard_by_arfcn(n_arfcn, rank, world):
     return shard_range(n_arfcn, rank, world)
 
 
+def shard_time_blocks(n_blocks, rank, world, quantum=1):
+    """Time-block partition of one wideband stream (cfg 5): contiguous block range [b0, b1) for
+    `rank`, every boundary a multiple of `quantum` blocks (125 blocks of 192 wideband rows are exactly 52 slots of 625
+    samples per channel at 65/48, so whole bursts stay on one rank).  Returns (b0, b1, halo_rows): the number of wideband
+    rows in front of b0 the rank re-reads from the source to rebuild the channelizer and resampler histories (0 for the
+    rank that starts the stream)."""
+    q_total = n_blocks // quantum
+    lo, hi = shard_range(q_total, rank, world)
+    b0, b1 = lo * quantum, hi * quantum
+    if rank == world - 1:
+        b1 = n_blocks
+    return b0, b1, (32 if b0 > 0 else 0)
+
+
 def counters(res):
     """Per-shard statistics tensor (int64[6]) from a result dict (rc int32[n], flags uint8[n])."""
     rc, fl = res["rc"], res["flags"]

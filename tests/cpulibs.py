@@ -273,6 +273,19 @@ class _Base:
         self.L[self.pfx + "detect_sch_batch"](*args)
         return r
 
+    def detect_sch_buffer(self, bufs, in_len=60000, thresh=4.0):
+        """detectSCHBurst(SCH_DETECT_BUFFER): bufs [n, >= in_len, 2] captures (12 frames = 60000 samples in the reference)"""
+        x = _f32(bufs)
+        n, stride = x.shape[0], x.shape[1]
+        r = dict(rc=np.zeros(n, np.int32), amp=np.zeros((n, 2), np.float32), toa=np.zeros(n, np.float32),
+                 ci=np.zeros(n, np.float32), flags=np.zeros(n, np.uint8))
+        args = [_p(x), C.c_int(stride), C.c_int(in_len), C.c_int(n), C.c_float(thresh), _p(r["rc"]), _p(r["amp"]),
+                _p(r["toa"]), _p(r["ci"])]
+        if self.has_flags:
+            args.append(_p(r["flags"]))
+        self.L[self.pfx + "detect_sch_buffer_batch"](*args)
+        return r
+
     # --- burst-type scheduler (Transceiver::expectedCorrType) ---
     def expected_corr_type(self, chan_type8, handover8, ext_rach, egprs, fn, tn):
         """chan_type8: ChannelCombination per timeslot of one channel (u8[8]); handover8: sub-slot bit mask per timeslot."""
@@ -302,6 +315,17 @@ class _Base:
                                            _p(tsc), C.c_int(max_delay), C.c_int(clamp[0]), C.c_int(clamp[1]),
                                            _p(r["bits"]), _p(r["start"]), _p(r["corr_max"]), _p(r["cir"]),
                                            C.c_int(nthreads))
+        return r
+
+    def vitac_sch_buffer(self, bufs, offset, length, want_bits=True):
+        """get_sch_buffer_chan_imp_resp over `length` samples from `offset` of every row + detect_burst_nb at the position found"""
+        bufs = _f32(bufs)
+        n, stride = bufs.shape[0], bufs.shape[1]
+        r = dict(bits=np.zeros((n, 148), np.int8), start=np.zeros(n, np.int32), corr_max=np.zeros(n, np.float32),
+                 cir=np.zeros((n, 20, 2), np.float32))
+        rc = self.L[self.pfx + "vitac_sch_buffer_batch"](_p(bufs), C.c_int(stride), C.c_int(offset), C.c_int(length), C.c_int(n),
+                                                         _p(r["bits"]) if want_bits else None, _p(r["start"]), _p(r["corr_max"]), _p(r["cir"]))
+        assert rc == n, rc
         return r
 
     def vitac_detect(self, bufs, offset, cir, start, is_ab=False, ss=3):

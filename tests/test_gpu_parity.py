@@ -1,5 +1,6 @@
 """GPU parity tests proper: CUDA path (through the C ABI) vs the CPU checker on identical seeded inputs."""
 import contextlib
+import sys
 
 import numpy as np
 import pytest
@@ -696,6 +697,50 @@ def test_detect_sch_full(trx, checker):
     # an ordinary detect call cannot select the internal SCH type through its type array
     r = run_gpu_dd(trx, rx[:64], 7, 0, 4, 4)
     assert (r["rc"] <= 0).all()
+
+
+def test_sch_first_acquisition(trx, checker):
+    """The MS side's first SCH acquisition over a 12-frame capture: detectSCHBurst(SCH_DETECT_BUFFER)
+    - 15,000 decimated positions x 64 taps - and get_sch_buffer_chan_imp_resp (59,488 windows x 54 symbols, running window
+    energy) + detect_burst_nb.  rc / TOA / amp / C/I per the usual criteria; start, taps, corr_max and all decisions exact.
+    A short capture and the committed fixture as well."""
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_sch_buffer_fixture as mk
+    rng = np.random.default_rng(49)
+    for n, length, head in ((40, 60000, 192), (7, 2500, 192)):
+        buf, pos = mk.captures(checker, rng, n, length, head)
+        cap = np.ascontiguousarray(buf[:, head:head + length])
+        if length == 60000:
+            c = checker.detect_sch_buffer(cap, length)  # the reference's BUFFER state always reads 12 frames
+        else:
+            if checker.pfx != "orc_":
+                checker_d = cpulibs.Oracle()           # length-generic restatement (pinned to the reference at 60,000)
+            else:
+                checker_d = checker
+            c = checker_d.detect_sch_buffer(cap, length)
+        g = {k: v.cpu().numpy() for k, v in trx.detect_sch_buffer(dev(cap), length).items()}
+        assert np.array_equal(g["rc"], c["rc"]), (g["rc"], c["rc"])
+        hit = c["rc"] > 0
+        assert hit.sum() >= n // 2
+        assert np.abs(g["toa"][hit].astype(np.float64) - c["toa"][hit]).max() <= 1e-3
+        assert np.abs(g["amp"][hit] - c["amp"][hit]).max() <= 1e-4 * np.abs(c["amp"][hit]).max()
+        assert np.abs(g["ci"][hit] - c["ci"][hit]).max() <= 1e-2
+        assert np.all(g["toa"][~hit] == 0) and np.all(g["amp"][~hit] == 0)
+        exact = np.array_equal(g["toa"], c["toa"]) and np.array_equal(g["amp"], c["amp"])
+        cv = checker.vitac_sch_buffer(buf, head, length)
+        gv = trx.vitac_sch_buffer(dev(buf), head, length)
+        torch.cuda.synchronize()
+        for k in ("start", "corr_max", "cir", "bits"):
+            assert np.array_equal(gv[k].cpu().numpy().view(np.uint8), cv[k].view(np.uint8)), (k, length)
+        print("sch acquisition", length, "detected", int(hit.sum()), "of", n, "toa/amp bit-identical:", exact)
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sch_buffer_fixture.npz"))
+    x, head, length = fx["buf"].astype(np.float32), int(fx["head"]), int(fx["length"])
+    g = {k: v.cpu().numpy() for k, v in trx.detect_sch_buffer(dev(fx["cap"].astype(np.float32)), 60000).items()}
+    assert np.array_equal(g["rc"], fx["d_rc"]) and np.abs(g["toa"] - fx["d_toa"]).max() <= 1e-3
+    gv = trx.vitac_sch_buffer(dev(x), head, length)
+    for k in ("start", "corr_max", "cir", "bits"):
+        assert np.array_equal(gv[k].cpu().numpy().view(np.uint8), fx["v_" + k].view(np.uint8)), k
 
 
 def test_vitac_sch(trx, checker):

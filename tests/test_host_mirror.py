@@ -4,6 +4,7 @@ Transceiver.cpp / burst-gen.cpp drive sigProcLib (GPU)."""
 import os
 import struct
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -189,6 +190,38 @@ def test_mirror_detect_sch(host_build, checker, tmp_path):
     assert np.array_equal(rec[:, 1:3], c["amp"]) and np.array_equal(rec[:, 3], c["toa"])
     det = c["rc"] > 0
     assert np.allclose(rec[det, 4], c["ci"][det], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_mirror_sch_first_acquisition(host_build, checker, tmp_path):
+    """detectSCHBurst(SCH_DETECT_BUFFER) and get_sch_buffer_chan_imp_resp + detect_burst_nb through the C++ mirror on
+    12-frame captures, as ms_rx_lower.cpp:160-219 calls them, against the CPU checker."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_sch_buffer_fixture as mk
+    rng = np.random.default_rng(80)
+    n, L = 5, 60000
+    buf, pos = mk.captures(checker, rng, n, L, 0)
+    pos_ok = pos.copy()
+    cap = np.ascontiguousarray(buf[:, :L])
+    pay = struct.pack("<i", n) + b"".join(cap[k].tobytes() for k in range(n))
+    raw = _run(host_build, "acq", pay, tmp_path)
+    rsz = 20 + 4 + 4 + 160 + 148
+    assert len(raw) == n * rsz
+    c = checker.detect_sch_buffer(cap, L)
+    cv = checker.vitac_sch_buffer(cap, 0, L)
+    for k in range(n):
+        r = raw[k * rsz:(k + 1) * rsz]
+        rec = np.frombuffer(r[:20], np.float32)
+        assert int(rec[0]) == c["rc"][k]
+        assert np.array_equal(rec[1:3], c["amp"][k]) and rec[3] == c["toa"][k]
+        start = np.frombuffer(r[20:24], np.int32)[0]
+        cmax = np.frombuffer(r[24:28], np.float32)[0]
+        cir = np.frombuffer(r[28:188], np.float32).reshape(20, 2)
+        bits = np.frombuffer(r[188:336], np.int8)
+        assert start == cv["start"][k] and cmax == cv["corr_max"][k] and np.array_equal(cir, cv["cir"][k])
+        if 0 <= start <= L - 592 - 64:
+            assert np.array_equal(bits, cv["bits"][k]), k
+    assert (c["rc"] > 0).sum() >= 3
 
 
 REFBIN = os.path.join(ROOT, "oracle", "_ref")

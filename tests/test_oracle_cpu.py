@@ -199,6 +199,39 @@ def test_oracle_sch_vs_reference_live(oracle, ref):
         assert eqb(a[k], b[k]), k
 
 
+def test_oracle_sch_buffer_vs_fixture(oracle):
+    """first SCH acquisition (detectSCHBurst SCH_DETECT_BUFFER; get_sch_buffer_chan_imp_resp + detect_burst_nb) against vectors
+    generated from the reference's own functions"""
+    fx = np.load(os.path.join(GOLD, "sch_buffer_fixture.npz"))
+    x, head, length = fx["buf"].astype(np.float32), int(fx["head"]), int(fx["length"])
+    d = oracle.detect_sch_buffer(fx["cap"].astype(np.float32), 60000)
+    assert (fx["d_rc"] > 0).any()
+    for k in ("rc", "amp", "toa", "ci"):
+        assert eqb(d[k], fx["d_" + k]), k
+    v = oracle.vitac_sch_buffer(x, head, length)
+    for k in ("bits", "start", "corr_max", "cir"):
+        assert eqb(v[k], fx["v_" + k]), k
+
+
+def test_oracle_sch_buffer_vs_reference_live(oracle, ref):
+    """the same at the reference's own size: a 12-frame capture (60,000 samples)"""
+    sys.path.insert(0, GOLD)
+    import make_sch_buffer_fixture as mk
+    rng = np.random.default_rng(13)
+    buf, pos = mk.captures(ref, rng, 6, 60000, 192)
+    a, b = oracle.detect_sch_buffer(np.ascontiguousarray(buf[:, 192:192 + 60000])), ref.detect_sch_buffer(np.ascontiguousarray(buf[:, 192:192 + 60000]))
+    assert (b["rc"] > 0).sum() >= 4
+    for k in ("rc", "amp", "toa", "ci"):
+        assert eqb(a[k], b[k]), k
+    # the burst starts where it was put: toa is in symbols from the capture's first sample (modulator delay ~ 4 symbols)
+    hit = (b["rc"] > 0) & (np.arange(6) % 5 != 4) & (np.arange(6) != 1)
+    assert np.all(np.abs(b["toa"][hit] - pos[hit] / 4.0) < 8)
+    va, vb = oracle.vitac_sch_buffer(buf, 192, 60000), ref.vitac_sch_buffer(buf, 192, 60000)
+    for k in ("bits", "start", "corr_max", "cir"):
+        assert eqb(va[k], vb[k]), k
+    assert np.all(np.abs(vb["start"][hit] - pos[hit]) < 24)
+
+
 def _sched_cases():
     fx = np.load(os.path.join(GOLD, "sched_fixture.npz"))
     for i in range(int(fx["n"])):
@@ -306,6 +339,20 @@ def test_shard_ranges():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_time_blocks():
+    """cfg 5 time-block partition: contiguous, quantum-aligned (whole slots per rank), halo only past the stream start"""
+    from osmo_trx_b200.sharding import shard_time_blocks
+    for nblk in (125, 1000, 1125, 10000, 10007):
+        for w in (1, 2, 3, 8):
+            spans = [shard_time_blocks(nblk, r, w, 125) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == nblk
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            for r, (b0, b1, halo) in enumerate(spans):
+                assert b0 % 125 == 0 and (b1 % 125 == 0 or r == w - 1)
+                assert halo == (32 if b0 > 0 else 0)
+                assert (b1 - b0) * 260 % 625 == 0 or r == w - 1
 
 
 GLOO_WORKER = r"""
