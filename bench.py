@@ -958,18 +958,19 @@ def main():
     gather = None
     if world > 1:
         from osmo_trx_b200 import sharding
-        rec_keys = ("rc", "amp", "toa", "tsc", "ci", "flags")
-        outs = [out, trx.alloc_results(n, 148)]
-        gbuf = {k: torch.empty((world,) + tuple(out[k].shape), dtype=out[k].dtype, device=device) for k in rec_keys}
+        pk = [sharding.alloc_packed_results(n, 148, device) for _ in range(2)]
+        outs = [pk[0][0], pk[1][0]]
+        recs = [pk[0][1], pk[1][1]]
+        gbuf = torch.empty((world, recs[0].numel()), dtype=torch.uint8, device=device)
         side = torch.cuda.Stream(device=device)
         main = torch.cuda.current_stream()
         ev_done = [None, None]
         cnt_box = [None]
 
-        def collect(o):
-            for k in rec_keys:
-                dist.all_gather_into_tensor(gbuf[k], o[k])
-            c = sharding.counters_device(o)
+        def collect(i):
+            # one all_gather of the rank's packed 22-byte records, one all_reduce of its six counters
+            dist.all_gather_into_tensor(gbuf.view(-1), recs[i])
+            c = sharding.counters_device(outs[i])
             dist.all_reduce(c)
             cnt_box[0] = c
 
@@ -982,7 +983,7 @@ def main():
             ev.record(main)
             side.wait_event(ev)
             with torch.cuda.stream(side):
-                collect(o)
+                collect(i & 1)
                 ev_done[i & 1] = torch.cuda.Event()
                 ev_done[i & 1].record(side)
 
@@ -1016,11 +1017,14 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt.item())
 
-        ms_rec = timed_coll(lambda: collect(out))
+        ms_rec = timed_coll(lambda: collect(0))
+        # the gathered block unpacks to the single-batch arrays: rank r's bursts are rows r * n .. (r + 1) * n - 1
+        allr = sharding.unpack_records(gbuf, n, world)
+        gather_ok = bool(torch.equal(allr["rc"][rank * n:(rank + 1) * n], outs[0]["rc"]))
         gsoft = torch.empty((world,) + tuple(out["soft"].shape), dtype=torch.float32, device=device)
         ms_soft = timed_coll(lambda: dist.all_gather_into_tensor(gsoft, out["soft"]), reps=5)
         del gsoft
-        rec_b = sum(out[k].element_size() * out[k][0].numel() for k in rec_keys)
+        rec_b = sharding.RECORD_BYTES
         gather = {"value_with_gather": world * n / (ms_g * 1e-3), "ms_per_step_with_gather": ms_g,
                   "record_bytes_per_burst": rec_b, "allgather_bytes_received_per_rank_per_step": (world - 1) * n * rec_b,
                   "records_collective_alone_ms": ms_rec,
@@ -1028,9 +1032,10 @@ def main():
                   "soft_rows_allgather_alone_ms": ms_soft,
                   "soft_rows_busbw_gbs": (world - 1) * n * 592 / (ms_soft * 1e-3) / 1e9,
                   "counters": [int(v) for v in cnt_box[0].tolist()], "counter_names": list(sharding.COUNTER_NAMES),
+                  "gathered_block_matches_local": gather_ok,
                   "what": "NCCL all_gather of the per-burst records + all_reduce of the counters on a side stream, overlapped "
                           "with the next step; soft rows (592 B per burst) all-gathered alone for the bandwidth figure"}
-        del outs[1], gbuf
+        del outs, recs, pk, gbuf
 
     # ---- per-kernel device time for the roofline: the same K steps once more with CUDA events around every
     #      kernel on the launching stream (trxb200_profile_begin/end); the headline value above is un-instrumented ----

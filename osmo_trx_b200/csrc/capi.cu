@@ -78,11 +78,15 @@ struct trxb200_ctx {
 		// slower than the serial order (1.75-2.4 ms vs 1.71 ms per 2^20 bursts) - corr_nb_kernel and demod_kernel each
 		// need the whole register file of an SM to hide their latencies - so the pipeline is off unless asked for
 		int overlap = 0, chunk_cap = 131072;
+		int detect_chunk = 1 << 30; // bursts per corr/peak launch pair.  Measured (profiles/r2l_detect_chunk_sweep.txt): one pair for the whole batch beats 262,144-burst chunks (corr 0.454 -> 0.403 ms, peak 0.220 -> 0.178 ms per 2^20 bursts); keeping the intermediates L2 resident with small chunks does not pay for the extra launches and tails
 		int resamp_up = 0; // 1: resampler_up_kernel (three outputs per thread from a register window) for interpolating ratios; measured 4.4 ms vs 3.2 ms of resampler16_kernel on the cfg-5 stream (profiles/r2k_*), so off by default
 		int fused = 0; // 1: nb_fused_kernel (one persistent warp-specialised kernel) for detect+demod in the normal-burst geometry; measured 2.75 ms vs 1.76 ms per 2^20 bursts for the three-kernel path (profiles/r2f_*), so off by default
 		int host_chunk = 16384; // slots per stage of the pinned-host pipelines (H2D | kernels | D2H on three streams)
 		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
 		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
+		int corr_wpb = 18; // corr_nb_kernel as one CTA of 18 warps per SM (96 registers) instead of two of 8 (118): 0.383 -> 0.373 ms per 2^20 bursts
+		int demod_wpb = 8; // warps per demod CTA (two CTAs per SM); 17 = one CTA of 17 warps.  Measured per 2^20 bursts (profiles/r2o_demod_warps.txt):
+				   // 10 warps 1.52 ms, 12: 1.28, 14: 1.24, 16: 1.10, 17: 1.13 - latency bound up to 12 warps, HBM bound from 16
 		int ov_corr_bps = 1, ov_peak_bps = 1, ov_peak_warps = 8, ov_demod_bps = 1; // while overlapping: leave room for the other kernel
 	} tune;
 	std::string err;
@@ -331,6 +335,9 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_FUSED", t.fused);
 		env_int("TRXB200_RESAMP_UP", t.resamp_up);
 		env_int("TRXB200_CHUNK", t.chunk_cap);
+		env_int("TRXB200_DETECT_CHUNK", t.detect_chunk);
+		env_int("TRXB200_DEMOD_WPB", t.demod_wpb);
+		env_int("TRXB200_CORR_WPB", t.corr_wpb);
 		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
 		env_int("TRXB200_HOST_CHUNK", t.host_chunk);
 		env_int("TRXB200_CORR_BPS", t.corr_bps);
@@ -618,6 +625,8 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	// ---- launch geometry ----
 	if (iq && !nb) return fail(ctx, TRXB200_EINVAL, "detect: int16 rows are read by corr_nb_kernel only");
 	int cw = 8; // warps per corr block
+	const bool cwide = nb && !iq && !overlapped && tn.corr_wpb == 18; // corr_nb_kernel as one CTA of 18 warps per SM
+	if (cwide) cw = 18;
 	if (!nb)
 		while (cw > 1 && corr_lg_warp_bytes(ndmax) * cw > 100 * 1024) cw >>= 1;
 	const size_t csmem = nb ? corr_nb_hdr_bytes() + corr_nb_warp_bytes() * cw : corr_lg_warp_bytes(ndmax) * cw;
@@ -631,6 +640,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 		CK(cudaFuncSetAttribute(corr_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(corr_nb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(corr_nb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		CK(cudaFuncSetAttribute(corr_nb_kernel<false, 18, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		CK(cudaFuncSetAttribute(peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		ctx->cfg_detect = true;
 	}
@@ -644,7 +654,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	// chunk: a whole number of sweeps of both kernels (no tail quantisation), small enough that the
 	// intermediates (lmax*8 + ndmax*4 bytes per burst) stay L2 resident
 	long chunk = corr_sweep / gcd_i(corr_sweep, peak_sweep) * peak_sweep;
-	const long cap = after_chunk ? tn.chunk_cap : 262144;
+	const long cap = after_chunk ? tn.chunk_cap : tn.detect_chunk;
 	if (chunk > cap) chunk = std::max<long>(1, cap / peak_sweep) * peak_sweep;
 	else chunk *= std::max<long>(1, cap / chunk);
 	if (chunk > n) chunk = n;
@@ -685,6 +695,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));
 			prof_pre(ctx, st);
 			if (nb && iq) corr_nb_kernel<true><<<cgrid, cw * 32, csmem, st>>>(c);
+			else if (cwide) corr_nb_kernel<false, 18, 1><<<cgrid, cw * 32, csmem, st>>>(c);
 			else if (nb) corr_nb_kernel<false><<<cgrid, cw * 32, csmem, st>>>(c);
 			else corr_long_kernel<<<cgrid, cw * 32, csmem, st>>>(c);
 			prof_post(ctx, st, "corr_kernel");
@@ -730,18 +741,21 @@ static int launch_demod(trxb200_ctx *ctx, cudaStream_t st, const float *bursts, 
 	p.pkt = pkt; p.pkt_stride = pkt_stride; p.pkt_hdr = pkt_version == 1 ? 11 : 8; p.pkt_v0 = pkt_version == 0;
 	p.bursts = bursts; p.stride = stride; p.n = n; p.rc = rc; p.amp = amp; p.toa = toa; p.ci = ci; p.flags = flags;
 	p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp; p.dnsamp_g = ctx->d_comp + ctx->ht->comp.size(); p.edge_tab = ctx->d_edge_tab; p.fix_clip = fix_clip;
-	const int wpb = 8;
+	const bool wide = !iq && bps <= 0 && ctx->tune.demod_wpb == 17; // one CTA of 17 warps per SM (float rows, not while overlapping)
+	const int wpb = wide ? 17 : ((!iq && bps <= 0 && ctx->tune.demod_wpb >= 1 && ctx->tune.demod_wpb < 8) ? ctx->tune.demod_wpb : 8);
 	const size_t smem = (size_t)wpb * kDemodWarpFloats * sizeof(float);
 	if (!ctx->cfg_demod) {
-		CK(cudaFuncSetAttribute(demod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(demod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(demod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kDemodWarpFloats * sizeof(float))));
+		CK(cudaFuncSetAttribute(demod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kDemodWarpFloats * sizeof(float))));
+		CK(cudaFuncSetAttribute(demod_kernel<false, 17, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(17 * kDemodWarpFloats * sizeof(float))));
 		ctx->cfg_demod = true;
 	}
 	if (bps <= 0) bps = ctx->tune.demod_bps;
-	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * std::max(1, std::min(2, bps)));
+	int grid = std::min((n + wpb - 1) / wpb, ctx->sm_count * (wide ? 1 : std::max(1, std::min(2, bps))));
 	if (grid < 1) grid = 1;
 	prof_pre(ctx, st);
 	if (iq) demod_kernel<true><<<grid, wpb * 32, smem, st>>>(p);
+	else if (wide) demod_kernel<false, 17, 1><<<grid, wpb * 32, smem, st>>>(p);
 	else demod_kernel<false><<<grid, wpb * 32, smem, st>>>(p);
 	prof_post(ctx, st, "demod_kernel");
 	return post_launch(ctx, "demod_kernel");

@@ -207,10 +207,11 @@ static int resampler_rotate_impl(trxb200_resampler *r, const float *in, int in_l
 		ResampUpParams P;
 		P.in = in; P.out = out; P.in_stride = in_stride; P.out_len = out_len; P.out_stride = out_stride; P.n_streams = n_streams;
 		P.p = r->p; P.q = r->q; P.negzero = -0.0f;
-		std::memcpy(P.taps, r->taps.data(), sizeof(float) * (size_t)r->p * 16);
+		rs_up_fill(P, r->taps.data());
 		const size_t smem = rs_up_smem(r->p, r->q);
 		CK(cudaFuncSetAttribute(resampler_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		const long tiles = (long)n_streams * ((out_len / r->p + kRsTile - 1) / kRsTile);
+		if (tiles > 0x7fffffffL) return fail(ctx, TRXB200_EINVAL, "resampler_rotate: too many tiles");
 		const int grid = (int)std::max<long>(1, std::min<long>(tiles, (long)ctx->sm_count * 2));
 		prof_pre(ctx, ctx->stream);
 		resampler_up_kernel<<<grid, 256, smem, ctx->stream>>>(P);

@@ -725,8 +725,10 @@ __device__ __forceinline__ void demod_one(const DemodParams &p, const DemodWarp 
 	__syncwarp();
 }
 
-template <bool I16>
-__global__ void __launch_bounds__(256, 2)
+// WPB warps per CTA, BPS CTAs per SM: 8 x 2, or 17 x 1 (one CTA of 17 warps fits the register file at 120 registers per
+// thread and 223 KB of shared memory: one more resident warp per SM than two CTAs of 8)
+template <bool I16, int WPB = 8, int BPS = 2>
+__global__ void __launch_bounds__(WPB * 32, BPS)
 demod_kernel(DemodParams p)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -444,8 +444,9 @@ __device__ __forceinline__ void corr_nb_fill_hdr(float2 *hs, SeqInfo *sinfo)
 	for (int k = threadIdx.x; k < SEQ_COUNT; k += blockDim.x) sinfo[k] = c_tab.info[k];
 }
 
-template <bool I16>
-__global__ void __launch_bounds__(256, 2)
+// WPB warps per CTA, BPS CTAs per SM: 8 x 2, or one CTA of 18 warps (216 KB of staging, 112 registers per thread)
+template <bool I16, int WPB = 8, int BPS = 2>
+__global__ void __launch_bounds__(WPB * 32, BPS)
 corr_nb_kernel(CorrParams p)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -158,20 +158,35 @@ resampler16_kernel(const float *__restrict__ in, int in_stride, float *__restric
 // Same sse_conv_real16 tree per output on the packed pipe as resampler16_kernel: bit-identical to Resampler::rotate.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRsMaxP = 96;
+constexpr int kRsMaxGroups = (kRsMaxP + 2) / 3;
 constexpr int kRsTile = 64; // periods per tile
 struct ResampUpParams {
 	const float *in;
 	float *out;
 	int in_stride, out_len, out_stride, n_streams, p, q;
 	float negzero;
-	float taps[kRsMaxP * 16];
+	int goff[kRsMaxGroups];	      // per residue group: off0 | d1 << 8 | d2 << 16 (window offsets, see above)
+	float gtaps[kRsMaxGroups][48]; // the three tap sets of the group (a missing residue repeats the first)
 };
 __host__ __device__ inline int rs_up_in_pitch(int q) { return (q + 15) | 1; }
 __host__ __device__ inline int rs_up_out_pitch(int p) { return p | 1; }
 __host__ __device__ inline size_t rs_up_smem(int p, int q) { return (size_t)kRsTile * (2 * rs_up_in_pitch(q) + rs_up_out_pitch(p)) * sizeof(float2); }
+// host: fills goff / gtaps from the resampler's partition filters taps[p][16]
+inline void rs_up_fill(ResampUpParams &P, const float *taps)
+{
+	const int p = P.p, q = P.q, ng = (p + 2) / 3;
+	for (int g = 0; g < ng; g++) {
+		const int rho0 = 3 * g, r1 = rho0 + 1 < p ? rho0 + 1 : rho0, r2 = rho0 + 2 < p ? rho0 + 2 : rho0;
+		const int off0 = (q * rho0) / p;
+		P.goff[g] = off0 | (((q * r1) / p - off0) << 8) | (((q * r2) / p - off0) << 16);
+		const int rr[3] = { rho0, r1, r2 };
+		for (int o = 0; o < 3; o++)
+			for (int k = 0; k < 16; k++) P.gtaps[g][16 * o + k] = taps[(size_t)((q * rr[o]) % p) * 16 + k];
+	}
+}
 
 template <int D>
-__device__ __forceinline__ float2 rs_tree(const float2 (&x)[18], const float (&h)[16], float2 nz)
+__device__ __forceinline__ float2 rs_tree(const float2 (&x)[18], const float *h, float2 nz)
 {
 	float2 L[4];
 #pragma unroll
@@ -196,45 +211,41 @@ resampler_up_kernel(const __grid_constant__ ResampUpParams P)
 	const float2 nz = make_float2(P.negzero, P.negzero);
 	const int periods_total = P.out_len / p;
 	const int tiles_per_stream = (periods_total + kRsTile - 1) / kRsTile;
-	const long total_tiles = (long)P.n_streams * tiles_per_stream;
+	const int total_tiles = P.n_streams * tiles_per_stream;
 	const int ngroups = (p + 2) / 3;
 	const int rowlen = q + 15;
 	const unsigned rin_s = (unsigned)__cvta_generic_to_shared(rsu);
-	// stage: row r <- input samples (per0 + r) * q - 15 .. + q - 1; warps walk rows, lanes walk a row (coalesced 8-byte
-	// asynchronous copies, no index arithmetic beyond adds)
-	auto issue = [&](long tile_, int buf_) {
-		const int s_ = (int)(tile_ / tiles_per_stream), per0_ = (int)(tile_ % tiles_per_stream) * kRsTile;
+	// stage: row r <- input samples (per0 + r) * q - 15 .. + q - 1; warps walk rows, a lane keeps its columns (coalesced
+	// 8-byte asynchronous copies; per copy one shared and one global address increment)
+	auto issue = [&](int tile_, int buf_) {
+		const int s_ = tile_ / tiles_per_stream, per0_ = (tile_ - s_ * tiles_per_stream) * kRsTile;
 		const int np_ = min(kRsTile, periods_total - per0_);
-		const float2 *src = reinterpret_cast<const float2 *>(P.in) + (size_t)s_ * P.in_stride + ((long)per0_ * q - 15);
-		const unsigned dst = rin_s + 8u * (unsigned)(buf_ * kRsTile * ipitch);
-		for (int r = warp; r < np_; r += 8)
-			for (int c = lane; c < rowlen; c += 32)
-				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (unsigned)(r * ipitch + c)), "l"(src + (long)r * q + c)
-					     : "memory");
+		const float2 *src = reinterpret_cast<const float2 *>(P.in) + (size_t)s_ * P.in_stride + ((long)per0_ * q - 15) + (long)warp * q + lane;
+		unsigned dst = rin_s + 8u * (unsigned)(buf_ * kRsTile * ipitch + warp * ipitch + lane);
+		for (int r = warp; r < np_; r += 8, src += 8 * q, dst += 64u * (unsigned)ipitch) {
+			for (int c = 0; c + lane < rowlen; c += 32)
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (unsigned)c), "l"(src + c) : "memory");
+		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
 	};
 	int buf = 0;
-	if ((long)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
-	for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
-		const int s = (int)(tile / tiles_per_stream), per0 = (int)(tile % tiles_per_stream) * kRsTile;
+	if ((int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+	for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
+		const int s = tile / tiles_per_stream, per0 = (tile - s * tiles_per_stream) * kRsTile;
 		const int np = min(kRsTile, periods_total - per0);
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncthreads(); // this tile's rows have landed; the other input buffer and the output tile are free
-		if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x, buf ^ 1);
+		if (tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, buf ^ 1);
 		const float2 *rin = rsu + (size_t)buf * kRsTile * ipitch;
 		// ---- items: residue group g (warp uniform) x block of 32 periods (lanes) ----
 		const int nblk = (np + 31) >> 5;
 		for (int g = warp; g < ngroups; g += 8) {
+			const int go = P.goff[g];
+			const int off0 = go & 255, d1 = (go >> 8) & 255, d2 = (go >> 16) & 255;
 			const int rho0 = 3 * g;
-			const int r1 = rho0 + 1 < p ? rho0 + 1 : rho0, r2 = rho0 + 2 < p ? rho0 + 2 : rho0;
-			const int off0 = (q * rho0) / p;
-			const int d1 = (q * r1) / p - off0, d2 = (q * r2) / p - off0;
-			float h0[16], h1[16], h2[16];
-			{
-				const float *t0 = P.taps + ((q * rho0) % p) * 16, *t1 = P.taps + ((q * r1) % p) * 16, *t2 = P.taps + ((q * r2) % p) * 16;
+			float h[48];
 #pragma unroll
-				for (int k = 0; k < 16; k++) { h0[k] = t0[k]; h1[k] = t1[k]; h2[k] = t2[k]; }
-			}
+			for (int k = 0; k < 48; k++) h[k] = P.gtaps[g][k];
 			const bool full = off0 + 18 <= rowlen;
 			for (int blk = 0; blk < nblk; blk++) {
 				const int r = blk * 32 + lane;
@@ -249,16 +260,20 @@ resampler_up_kernel(const __grid_constant__ ResampUpParams P)
 						for (int k = 0; k < 18; k++) x[k] = (off0 + k < rowlen) ? row[k] : make_float2(0.0f, 0.0f);
 					}
 					float2 *orow = rout + (size_t)r * opitch + rho0;
-					orow[0] = rs_tree<0>(x, h0, nz);
-					if (rho0 + 1 < p) orow[1] = d1 ? rs_tree<1>(x, h1, nz) : rs_tree<0>(x, h1, nz);
-					if (rho0 + 2 < p) orow[2] = d2 == 2 ? rs_tree<2>(x, h2, nz) : (d2 == 1 ? rs_tree<1>(x, h2, nz) : rs_tree<0>(x, h2, nz));
+					orow[0] = rs_tree<0>(x, h, nz);
+					if (rho0 + 1 < p) orow[1] = d1 ? rs_tree<1>(x, h + 16, nz) : rs_tree<0>(x, h + 16, nz);
+					if (rho0 + 2 < p) orow[2] = d2 == 2 ? rs_tree<2>(x, h + 32, nz) : (d2 == 1 ? rs_tree<1>(x, h + 32, nz) : rs_tree<0>(x, h + 32, nz));
 				}
 			}
 		}
 		__syncthreads();
 		// ---- the tile's outputs are one contiguous run of the stream ----
 		float2 *dst = reinterpret_cast<float2 *>(P.out) + (size_t)s * P.out_stride + (size_t)per0 * p;
-		if (opitch == p) {
+		if (opitch == p && ((np * p) & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+			const float4 *r4 = reinterpret_cast<const float4 *>(rout);
+			float4 *d4 = reinterpret_cast<float4 *>(dst);
+			for (int idx = tid; idx < (np * p) >> 1; idx += 256) d4[idx] = r4[idx];
+		} else if (opitch == p) {
 			for (int idx = tid; idx < np * p; idx += 256) dst[idx] = rout[idx];
 		} else {
 			for (int r = warp; r < np; r += 8)

@@ -82,3 +82,42 @@ def gather_results(res, n_total, group=None, keys=("rc", "amp", "toa", "tsc", "c
         dist.all_gather(parts, buf, group=group)
         out[k] = torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
     return out
+
+
+RECORD_BYTES = 22  # rc i32 | amp f32 x 2 | toa f32 | ci f32 | tsc u8 | flags u8
+
+
+def alloc_packed_results(n, soft_stride=148, device="cuda"):
+    """Result arrays for Trx.detect_demod(out=...) carved out of ONE contiguous buffer (SoA blocks back to back:
+    rc[n] | amp[n][2] | toa[n] | ci[n] | tsc[n] | flags[n], 22 bytes per burst), so that a rank's per-burst records
+    travel in a single collective (`records`, uint8[22 n]).  n must be a multiple of 4 (alignment of the float blocks).
+    The soft-bit rows are a separate tensor: they stay with the rank that produced them."""
+    assert n % 4 == 0
+    rec = torch.zeros(RECORD_BYTES * n, dtype=torch.uint8, device=device)
+    out = dict(rc=rec[0:4 * n].view(torch.int32), amp=rec[4 * n:12 * n].view(torch.float32).view(n, 2),
+               toa=rec[12 * n:16 * n].view(torch.float32), ci=rec[16 * n:20 * n].view(torch.float32),
+               tsc=rec[20 * n:21 * n], flags=rec[21 * n:22 * n],
+               soft=torch.zeros((n, soft_stride), dtype=torch.float32, device=device))
+    return out, rec
+
+
+def unpack_records(rec_all, n, world):
+    """[world, 22 n] gathered record blocks -> dict of [world * n, ...] arrays in global burst order"""
+    r = rec_all.view(world, RECORD_BYTES * n)
+    return dict(rc=r[:, 0:4 * n].contiguous().view(torch.int32).view(-1),
+                amp=r[:, 4 * n:12 * n].contiguous().view(torch.float32).view(-1, 2),
+                toa=r[:, 12 * n:16 * n].contiguous().view(torch.float32).view(-1),
+                ci=r[:, 16 * n:20 * n].contiguous().view(torch.float32).view(-1),
+                tsc=r[:, 20 * n:21 * n].contiguous().view(-1), flags=r[:, 21 * n:22 * n].contiguous().view(-1))
+
+
+def gather_records(rec, group=None):
+    """One all_gather of a rank's packed record block (ncclAllGather on GPUs): uint8[22 n] -> uint8[world, 22 n]"""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    out = torch.empty((world, rec.numel()), dtype=torch.uint8, device=rec.device)
+    if world == 1:
+        out[0] = rec
+    else:
+        dist.all_gather_into_tensor(out.view(-1), rec, group=group)
+    return out
+

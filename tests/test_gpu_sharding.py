@@ -98,6 +98,19 @@ for k in ("rc", "amp", "toa", "tsc", "ci", "flags", "soft"):
     ok = ok and bool(torch.equal(a, b))
 want = sharding.counters(whole)
 ok = ok and bool(torch.equal(cnt.cpu(), want.cpu()))
+# the packed form: results written straight into one record block per rank, gathered by a single ncclAllGather
+m = (n // world) // 4 * 4
+outp, rec = sharding.alloc_packed_results(m, 148, dev)
+s0 = rank * m
+trx.detect_demod(rx[s0:s0 + m].contiguous(), typ[s0:s0 + m].contiguous(), tsc[s0:s0 + m].contiguous(), mt[s0:s0 + m].contiguous(), bound,
+                 n_gmsk_soft=148, out=outp)
+allp = sharding.unpack_records(sharding.gather_records(rec), m, world)
+torch.cuda.synchronize()
+for k in ("rc", "amp", "toa", "tsc", "ci", "flags"):
+    a, b = allp[k], whole[k][:world * m]
+    if a.dtype == torch.float32:
+        a, b = a.contiguous().view(torch.int32), b.contiguous().view(torch.int32)
+    ok = ok and bool(torch.equal(a, b))
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

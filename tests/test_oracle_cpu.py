@@ -378,6 +378,14 @@ c = sharding.reduce_counters(sharding.counters(res))
 assert int(c[0]) == n and int(c[1]) == int((full["rc"] > 0).sum())
 c2 = sharding.reduce_counters(sharding.counters_device(res))
 assert torch.equal(c, c2)
+# packed records: one buffer per rank, one collective (equal shard sizes: the first 296 bursts, 148 per rank)
+m = 148
+outp, rec = sharding.alloc_packed_results(m, 148, "cpu")
+for k in ("rc", "amp", "toa", "tsc", "ci", "flags"):
+    outp[k].copy_(torch.from_numpy(full[k][rank * m:(rank + 1) * m]))
+allp = sharding.unpack_records(sharding.gather_records(rec), m, world)
+for k in allp:
+    assert np.array_equal(allp[k].numpy(), full[k][:world * m]), k
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
