@@ -31,7 +31,7 @@ ALG_BYTES = {"nb": 5000 + 592 + 24, "rach": 5000 + 592 + 24, "edge": 5000 + 1776
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="nb", choices=["nb", "rach", "edge", "vitac", "wideband", "modulate"])

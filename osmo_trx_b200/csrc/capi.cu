@@ -632,7 +632,8 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	const size_t csmem = nb ? corr_nb_hdr_bytes() + corr_nb_warp_bytes() * cw : corr_lg_warp_bytes(ndmax) * cw;
 	const int cgroup = nb ? kNbGroup : 1;
 	int pw = std::max(1, std::min(32, overlapped ? tn.ov_peak_warps : tn.peak_warps)); // warps per peak block
-	while (pw > 1 && peak_hdr_bytes() + peak_warp_bytes(lmax) * pw > 200 * 1024) pw >>= 1;
+	// as many warps as the shared memory of one SM holds (long correlation vectors: 7 warps at lmax 80, not a power of two)
+	pw = std::max(1, std::min(pw, (int)((225 * 1024 - peak_hdr_bytes()) / peak_warp_bytes(lmax))));
 	const size_t psmem = peak_hdr_bytes() + peak_warp_bytes(lmax) * pw;
 	if (csmem > 227 * 1024 || psmem > 227 * 1024)
 		return fail(ctx, TRXB200_EINVAL, "detect: max_toa_bound too large for on-chip buffers");

@@ -51,7 +51,8 @@ constexpr int kYOff = 320;		 // float offset of the leading-edge Y scratch (floa
 constexpr int kYTopOff = kYOff + 64;	 // float offset of the trailing-edge Y scratch (float2[16])
 constexpr int kYxOff = kYTopOff + 64;	 // float offset of the converted head of an int16 window (float2[56]); >= 444: the EDGE soft
 					 // row is staged over the area below
-constexpr int kScratchFloats = kYxOff + 112;
+constexpr int kIdealOff = kYxOff + 112;	 // float offset of the warp's copy of the 9 ideal 8-PSK points (float2[9], padded to 32 floats)
+constexpr int kScratchFloats = kIdealOff + 32;
 constexpr int kDemodWarpFloats = 2 * 4 * kBufSlots + kScratchFloats + 4; // 2 window buffers + scratch + 2 mbarriers
 
 // ---- packed FP32 (sm_100 FFMA2): both halves are IEEE fma.rn ----
@@ -180,7 +181,9 @@ __device__ __forceinline__ void store_soft_bytes(const DemodParams &p, int b, co
 
 // ---- EDGE: demodEdgeBurst :2105-2128 after the decimator: decs[2 + i], i < 156, hold the scaled complex
 //      1-sps samples (the shared FIR pass below produced them) ----
-__device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2 *decs, int lane)
+// rot_lane: the lane's derotation factor edge_tab[lane & 15] (symbol i = lane + 32 r has i & 15 = lane & 15); ideal: the warp's
+// shared-memory copy of the nine ideal points - neither is fetched from global memory per burst
+__device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2 *decs, int lane, float2 rot_lane, const float2 *ideal_s)
 {
 	if (lane < 2) { decs[lane] = make_float2(0.0f, 0.0f); decs[158 + lane] = make_float2(0.0f, 0.0f); }
 	__syncwarp();
@@ -199,7 +202,7 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 			float2 eq = make_float2(0.0f, 0.0f);
 #pragma unroll
 			for (int k = 0; k < 5; k++) eq = ffma2(decs[i + k], make_float2(c0[k], c0[k]), eq);
-			rot[r] = cmul_fast(eq, p.edge_tab[i & 15]); // derotateEdgeBurst :691-711
+			rot[r] = cmul_fast(eq, rot_lane); // derotateEdgeBurst :691-711
 			if (i >= 8) {
 				// computeEdgeCI :2074-2093: distance to the nearest ideal 8-PSK point.  The reference picks it as
 				// round(atan2(y, x) / (pi/4)); the octant test below picks the same point except within rounding
@@ -210,7 +213,7 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 				// k + 4 per (diagonal, vertical, x < 0, y < 0): axis points 0, +-4, +-2; diagonal points +-1, +-3
 				const unsigned long long lut = 0x1735173526260844ull;
 				const int k4 = (int)((lut >> (4 * sel)) & 15u);
-				const float2 ideal = p.edge_tab[16 + k4];
+				const float2 ideal = ideal_s[k4];
 				const float ex = ideal.x - rot[r].x, ey = ideal.y - rot[r].y;
 				err = fmaf(ex, ex, fmaf(ey, ey, err));
 			}
@@ -389,6 +392,8 @@ struct DemodWarp {
 	float *ostage;
 	float2 *decs, *yv, *ytop, *yx;
 	float gk[4]; // k = 4*(lane&3) + kk
+	float2 rot_lane;     // edge_tab[lane & 15]
+	const float2 *ideal; // shared-memory copy of edge_tab[16 .. 24]
 };
 __device__ __forceinline__ DemodWarp demod_warp_setup(const DemodParams &p, float *ostage, int lane)
 {
@@ -400,6 +405,11 @@ __device__ __forceinline__ DemodWarp demod_warp_setup(const DemodParams &p, floa
 	W.yx = reinterpret_cast<float2 *>(ostage + kYxOff);
 #pragma unroll
 	for (int kk = 0; kk < 4; kk++) W.gk[kk] = p.dnsamp_g[4 * (lane & 3) + kk];
+	W.rot_lane = p.edge_tab[lane & 15];
+	float2 *ideal = reinterpret_cast<float2 *>(ostage + kIdealOff);
+	if (lane < 9) ideal[lane] = p.edge_tab[16 + lane];
+	__syncwarp();
+	W.ideal = ideal;
 	return W;
 }
 // row pointer (float2 or short2 samples) and its phase on the 16-byte grid
@@ -702,7 +712,7 @@ __device__ __forceinline__ void demod_one(const DemodParams &p, const DemodWarp 
 	}
 	__syncwarp();
 	if (edge) {
-		demod_edge_tail(p, b, decs, lane);
+		demod_edge_tail(p, b, decs, lane, W.rot_lane, W.ideal);
 		__syncwarp();
 		return;
 	}

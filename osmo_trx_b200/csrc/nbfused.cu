@@ -27,7 +27,7 @@
 namespace trxb200 {
 
 constexpr int kFuTile = 28;   // bursts per tile: 4 correlator groups of 7 = the lanes of one peak pass
-constexpr int kFuRing = 8;    // result slots (tiles) between the peak warp and the demodulator warps
+constexpr int kFuRing = 4;    // result slots (tiles) between the peak warp and the demodulator warps
 constexpr int kFuNC = 2;      // correlator warps
 constexpr int kFuNP = 1;      // peak warps
 constexpr int kFuND = 10;     // demodulator warps
