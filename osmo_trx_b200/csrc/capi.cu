@@ -26,6 +26,7 @@ __constant__ ConstTables c_tab;
 #include "convolve.cu"
 #include "misc.cu"
 #include "vitac.cu"
+#include "vitac_lane.cu"
 #include "filterbank.cu"
 #include "pull.cu"
 
@@ -84,6 +85,7 @@ struct trxb200_ctx {
 		int host_chunk = 16384; // slots per stage of the pinned-host pipelines (H2D | kernels | D2H on three streams)
 		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
 		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
+		int vitac_lane = 1; // 1: vitac_lane_kernel (lane = burst), 0: vitac_kernel (warp = burst pair)
 		int corr_wpb = 18; // corr_nb_kernel as one CTA of 18 warps per SM (96 registers) instead of two of 8 (118): 0.383 -> 0.373 ms per 2^20 bursts
 		int demod_wpb = 8; // warps per demod CTA (two CTAs per SM); 17 = one CTA of 17 warps.  Measured per 2^20 bursts (profiles/r2o_demod_warps.txt):
 				   // 10 warps 1.52 ms, 12: 1.28, 14: 1.24, 16: 1.10, 17: 1.13 - latency bound up to 12 warps, HBM bound from 16
@@ -338,6 +340,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_DETECT_CHUNK", t.detect_chunk);
 		env_int("TRXB200_DEMOD_WPB", t.demod_wpb);
 		env_int("TRXB200_CORR_WPB", t.corr_wpb);
+		env_int("TRXB200_VITAC_LANE", t.vitac_lane);
 		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
 		env_int("TRXB200_HOST_CHUNK", t.host_chunk);
 		env_int("TRXB200_CORR_BPS", t.corr_bps);

@@ -17,6 +17,44 @@ struct trxb200_filterbank {
 	int cur = 0;
 };
 
+// one launch of the MLSE: vitac_lane_kernel (lane = burst) unless switched off; nwin = search windows (0 with a caller's estimate)
+static int launch_vitac(trxb200_ctx *ctx, VitacParams &p, int nwin)
+{
+	cudaStream_t st = ctx->stream;
+	if (ctx->tune.vitac_lane) {
+		const int N = p.is_ab == 1 ? 88 : 148;
+		const size_t smem = (size_t)kVlWarps * vl_warp_bytes(p.cir_in ? 0 : nwin, N);
+		if (smem <= 200 * 1024) {
+			const int ntiles = (p.n + 31) / 32;
+			const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / smem));
+			const int grid = std::max(1, std::min((ntiles + kVlWarps - 1) / kVlWarps, ctx->sm_count * per_sm));
+			auto go = [&](auto kern) {
+				if (smem > 48 * 1024) {
+					cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+					if (e != cudaSuccess) return fail(ctx, TRXB200_ECUDA, "vitac_lane_kernel attribute", e);
+				}
+				prof_pre(ctx, st);
+				kern<<<grid, kVlWarps * 32, smem, st>>>(p);
+				prof_post(ctx, st, "vitac_kernel");
+				return post_launch(ctx, "vitac_lane_kernel");
+			};
+			if (p.cir_in || p.is_ab == 0) return go(vitac_lane_kernel<16, true>);
+			if (p.is_ab == 1) return go(vitac_lane_kernel<31, false>);
+			return go(vitac_lane_kernel<54, false>);
+		}
+	}
+	const int wpb = 4;
+	const size_t smem = (size_t)wpb * vitac_warp_floats(p.nwin_max, p.pitch) * sizeof(float);
+	if (smem > 200 * 1024) return fail(ctx, TRXB200_EINVAL, "vitac: clamp range too wide for the on-chip window");
+	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int grid = std::min(((p.n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
+	if (grid < 1) grid = 1;
+	prof_pre(ctx, st);
+	vitac_kernel<<<grid, wpb * 32, smem, st>>>(p);
+	prof_post(ctx, st, "vitac_kernel");
+	return post_launch(ctx, "vitac_kernel");
+}
+
 extern "C" {
 
 int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int offset, int n, int is_ab, const uint8_t *tsc,
@@ -42,16 +80,7 @@ int trxb200_vitac_batch(trxb200_ctx *ctx, const float *bufs, int stride, int off
 	p.lo = std::min(clamp_lo, s0);
 	p.range = std::max(clamp_hi + 4 * N, s1 + 4 * (tlen - 1)) - p.lo;
 	p.pitch = vitac_pitch(p.range);
-	const int wpb = 4;
-	const size_t smem = (size_t)wpb * vitac_warp_floats(p.nwin_max, p.pitch) * sizeof(float);
-	if (smem > 200 * 1024) return fail(ctx, TRXB200_EINVAL, "vitac: clamp range too wide for the on-chip window");
-	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int grid = std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
-	if (grid < 1) grid = 1;
-	prof_pre(ctx, ctx->stream);
-	vitac_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(p);
-	prof_post(ctx, ctx->stream, "vitac_kernel");
-	return post_launch(ctx, "vitac_kernel");
+	return launch_vitac(ctx, p, s1 - s0);
 }
 
 /* detect_burst_nb / detect_burst_ab (grgsm_vitac.cpp:105-123) with the CALLER's channel estimate and burst start: matched
@@ -82,16 +111,7 @@ int trxb200_vitac_detect_ss_batch(trxb200_ctx *ctx, const float *bufs, int strid
 	p.lo = clamp_lo;
 	p.range = clamp_hi + 4 * N - clamp_lo;
 	p.pitch = vitac_pitch(p.range);
-	const int wpb = 4;
-	const size_t smem = (size_t)wpb * vitac_warp_floats(p.nwin_max, p.pitch) * sizeof(float);
-	if (smem > 200 * 1024) return fail(ctx, TRXB200_EINVAL, "vitac_detect: clamp range too wide for the on-chip window");
-	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int grid = std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8);
-	if (grid < 1) grid = 1;
-	prof_pre(ctx, ctx->stream);
-	vitac_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(p);
-	prof_post(ctx, ctx->stream, "vitac_kernel");
-	return post_launch(ctx, "vitac_kernel");
+	return launch_vitac(ctx, p, 0);
 }
 
 /* get_sch_buffer_chan_imp_resp (grgsm_vitac.cpp:298-309) over `len` samples of every row + detect_burst_nb at the position
@@ -131,12 +151,7 @@ int trxb200_vitac_sch_buffer_batch(trxb200_ctx *ctx, const float *bufs, int stri
 		p.lo = 0;
 		p.range = 4 * 148;
 		p.pitch = vitac_pitch(p.range);
-		const int wpb = 4;
-		const size_t smem = (size_t)wpb * vitac_warp_floats(p.nwin_max, p.pitch) * sizeof(float);
-		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(vitac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		int grid = std::max(1, std::min(((n + 1) / 2 + wpb - 1) / wpb, ctx->sm_count * 8));
-		vitac_kernel<<<grid, wpb * 32, smem, st>>>(p);
-		r = post_launch(ctx, "vitac_kernel");
+		r = launch_vitac(ctx, p, 0);
 	}
 	cudaFreeAsync(d_corr, st);
 	cudaFreeAsync(d_pw, st);
