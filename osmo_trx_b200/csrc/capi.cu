@@ -20,6 +20,7 @@ __constant__ ConstTables c_tab;
 }
 
 #include "detect.cu"
+#include "detect_lane.cu"
 #include "demod.cu"
 #include "nbfused.cu"
 #include "modulate.cu"
@@ -85,6 +86,7 @@ struct trxb200_ctx {
 		int host_chunk = 16384; // slots per stage of the pinned-host pipelines (H2D | kernels | D2H on three streams)
 		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
 		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
+		int detect_lane = 1; // 1: detect_lane_kernel (lane = burst, one launch) for the normal-burst geometry; 0: corr_nb_kernel + peak_kernel
 		int vitac_lane = 1; // 1: vitac_lane_kernel (lane = burst), 0: vitac_kernel (warp = burst pair)
 		int corr_wpb = 18; // corr_nb_kernel as one CTA of 18 warps per SM (96 registers) instead of two of 8 (118): 0.383 -> 0.373 ms per 2^20 bursts
 		int demod_wpb = 8; // warps per demod CTA (two CTAs per SM); 17 = one CTA of 17 warps.  Measured per 2^20 bursts (profiles/r2o_demod_warps.txt):
@@ -93,7 +95,7 @@ struct trxb200_ctx {
 	} tune;
 	std::string err;
 	// once-per-context device setup (function attributes and __constant__ tables are per device)
-	bool cfg_fused = false;
+	bool cfg_fused = false, cfg_detlane = false;
 	bool cfg_detect = false, cfg_demod = false, cfg_ch64 = false, cfg_sy64 = false, sched_tables = false;
 	HostStage *stage = nullptr;
 	PullScratch pull;	      // trxb200_pull_batch
@@ -341,6 +343,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_DEMOD_WPB", t.demod_wpb);
 		env_int("TRXB200_CORR_WPB", t.corr_wpb);
 		env_int("TRXB200_VITAC_LANE", t.vitac_lane);
+		env_int("TRXB200_DETECT_LANE", t.detect_lane);
 		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
 		env_int("TRXB200_HOST_CHUNK", t.host_chunk);
 		env_int("TRXB200_CORR_BPS", t.corr_bps);
@@ -662,6 +665,41 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	if (chunk > cap) chunk = std::max<long>(1, cap / peak_sweep) * peak_sweep;
 	else chunk *= std::max<long>(1, cap / chunk);
 	if (chunk > n) chunk = n;
+	if (nb && tn.detect_lane && !overlapped && !after_chunk) {
+		// lane = burst: decimate + correlate + peak logic per thread, one launch per round, no intermediates
+		if (!ctx->cfg_detlane) {
+			CK(cudaFuncSetAttribute(detect_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_lane_smem()));
+			CK(cudaFuncSetAttribute(detect_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_lane_smem()));
+			ctx->cfg_detlane = true;
+		}
+		const int nrounds = ctx->max_attempts;
+		for (int r = 0; r < nrounds; r++) {
+			DetLaneParams dp;
+			CorrParams &c = dp.c;
+			c.bursts = bursts; c.stride = stride; c.n = n; c.iq = iq; c.iq_stride = iq_stride; c.type = type; c.tsc = tsc; c.max_toa = max_toa;
+			c.rc = rc; c.round = r; c.sch = 0; c.max_toa_bound = bound; c.lmax = lmax; c.ndmax = ndmax; c.corr = nullptr; c.pwr = nullptr;
+			c.negzero = -0.0f;
+			PeakParams &q = dp.q;
+			q.n = n; q.type = type; q.tsc = tsc; q.max_toa = max_toa; q.round = r; q.last_round = (r == nrounds - 1); q.sch = 0;
+			q.max_toa_bound = bound; q.thresh = thresh; q.lmax = lmax; q.ndmax = ndmax; q.corr = nullptr; q.pwr = nullptr;
+			q.sinc512 = ctx->d_sinc512; q.negzero = -0.0f; q.rc = rc; q.amp = amp; q.toa = toa; q.ci = ci; q.tsc_out = tsc_out; q.flags = flags;
+			const int ntiles = (n + 31) / 32;
+			const int grid = std::max(1, std::min((ntiles + kDlWarps - 1) / kDlWarps, ctx->sm_count));
+			prof_pre(ctx, st);
+			if (iq) detect_lane_kernel<true><<<grid, kDlWarps * 32, det_lane_smem(), st>>>(dp);
+			else detect_lane_kernel<false><<<grid, kDlWarps * 32, det_lane_smem(), st>>>(dp);
+			prof_post(ctx, st, "detect_lane_kernel");
+			const int e = post_launch(ctx, "detect_lane_kernel");
+			if (e) return e;
+		}
+		if (scan_clip) {
+			prof_pre(ctx, st);
+			clip_kernel<<<std::max(1, std::min((n + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(bursts, stride, n, rc, flags, type);
+			prof_post(ctx, st, "clip_kernel");
+			return post_launch(ctx, "clip_kernel");
+		}
+		return TRXB200_OK;
+	}
 	// ---- scratch ----
 	// a short remainder (< chunk / 4) rides along with the last full chunk instead of paying two more launches
 	const long rem = n % chunk;

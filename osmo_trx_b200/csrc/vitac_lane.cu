@@ -48,10 +48,12 @@ __device__ __forceinline__ void vl_search(const float2 *__restrict__ x0, const f
 		float2 win[TLEN];
 #pragma unroll
 		for (int ii = 1; ii < TLEN; ii++) win[ii] = __ldg(&x[4 * (ii - 1)]);
+		float2 nxt = __ldg(&x[4 * (TLEN - 1)]); // the one new sample of the next window, requested a whole window ahead
 		for (int w = r, m = 0; w < nwin; w += 4, m++) {
 #pragma unroll
 			for (int ii = 0; ii < TLEN - 1; ii++) win[ii] = win[ii + 1];
-			win[TLEN - 1] = __ldg(&x[4 * (m + TLEN - 1)]);
+			win[TLEN - 1] = nxt;
+			if (w + 4 < nwin) nxt = __ldg(&x[4 * (m + TLEN)]);
 			float rr = 0.0f, ri = 0.0f;
 #pragma unroll
 			for (int ii = 0; ii < TLEN; ii++) {
@@ -203,17 +205,28 @@ vitac_lane_kernel(VitacParams p)
 		for (int t = 4; t < 20; t++) win[t] = __ldg(&x[t - 4]);
 		// steps n <= N - 5 see all 20 taps (4 (N - n) >= 20); N is even, so whole pairs up to n = N - 6
 		int n = 0;
+		// the eight samples of a step pair are requested one pair (about 450 instructions) before they are used
+		float2 nx[8];
+#pragma unroll
+		for (int t = 0; t < 8; t++) nx[t] = __ldg(&x[16 + t]);
 #pragma unroll 1
 		for (; n + 1 <= N - 5; n += 2) {
 #pragma unroll
 			for (int t = 0; t < 16; t++) win[t] = win[t + 4];
 #pragma unroll
-			for (int t = 0; t < 4; t++) win[16 + t] = __ldg(&x[4 * n + 16 + t]);
+			for (int t = 0; t < 4; t++) win[16 + t] = nx[t];
+			float2 hi4[4];
+#pragma unroll
+			for (int t = 0; t < 4; t++) hi4[t] = nx[4 + t];
+			if (n + 3 <= N - 5) {
+#pragma unroll
+				for (int t = 0; t < 8; t++) nx[t] = __ldg(&x[4 * n + 24 + t]);
+			}
 			words[n * 32] = vl_acs<true>(pa, pb, vl_mf<true, 20>(win, cir), inc);
 #pragma unroll
 			for (int t = 0; t < 16; t++) win[t] = win[t + 4];
 #pragma unroll
-			for (int t = 0; t < 4; t++) win[16 + t] = __ldg(&x[4 * n + 20 + t]);
+			for (int t = 0; t < 4; t++) win[16 + t] = hi4[t];
 			words[(n + 1) * 32] = vl_acs<false>(pb, pa, vl_mf<false, 20>(win, cir), inc);
 		}
 		// the last four steps (n = N - 4 .. N - 1): the filter runs off the end of the burst (mafi's break), 16, 12, 8, 4 taps
