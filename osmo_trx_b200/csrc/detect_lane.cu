@@ -5,28 +5,38 @@
 // the correlator, write the correlation vectors and powers to global memory, and read them back lanes = bursts for the
 // peak logic: two launches, 300 B of intermediates per burst, cross-lane staging, shuffles and 12 KB of shared memory
 // per warp for the raw windows.  Here every thread runs the whole chain for its own burst:
-//   decimate   35 outputs from the 152 samples of the correlator window, read straight from the thread's row in global
-//              memory (a 32-byte sector serves four consecutive samples out of L1); a 16-sample register window slides
-//              by four per output; sse_conv_real16 order on the packed pipe
+//   windows    the 152-sample correlator windows (read as 160) arrive in sixteen-sample chunks: the warp copies the chunk
+//              of all its 32 rows into shared memory with coalesced asynchronous copies, every lane takes its own row's
+//              sixteen samples into registers, and the next chunk is in flight while four decimator outputs are evaluated
+//   decimate   35 outputs, a 28-sample register window; sse_conv_real16 order on the packed pipe
 //   correlate  20 outputs x 16 taps from the decimated samples in registers, sse_conv_cmplx_8n order, written to the
 //              thread's column of the warp's [row][lane] tile
 //   peak       peak_lane() of detect.cu on that column - the same function the two-kernel path runs
-// Arithmetic per output is the two-kernel path's, bit for bit.  No lane idles (7-burst groups filled 28 or 31 of 32),
-// nothing is staged, and the only shared memory is the correlation tile the peak logic indexes dynamically.
+// Arithmetic per output is the two-kernel path's, bit for bit (the GPU parity suites run green on it), and the chain
+// itself needs about 130 warp instructions per burst against 263.  What it cannot get cheaply is its input: 32 rows of
+// 1,216 bytes, 5,000 bytes apart, per warp.  Measured per 2^20 bursts (corr_nb_kernel + peak_kernel: 0.53 ms): every thread
+// loading its own row 1.58 ms (32 sector requests per load: lg_throttle); 8-byte cp.async chunks 0.68 ms (sixteen copies per
+// chunk sit in the load/store queue until their data is back: mio_throttle); one TMA bulk copy per row and chunk 0.55 ms
+// (the bulk copies are serialised through the uniform datapath: half of the kernel's instructions).  At parity, not ahead:
+// opt-in (TRXB200_DETECT_LANE=1).  The same mapping is a 2.4x win where the per-thread work per byte is high
+// (vitac_lane_kernel).
 #include "device_tables.cuh"
 #include "kernels.hpp"
 
 namespace trxb200 {
 
-constexpr int kDlWarps = 9;	 // warps per CTA, one CTA per SM
+constexpr int kDlWarps = 12;	 // warps per CTA, one CTA per SM
 constexpr int kDlStagePitch = 17; // samples per row of the staging chunk (16 + 1: lanes = rows read conflict free)
+constexpr int kDlBulkPitch = 18;  // float rows, bulk copies: 16 samples + the 2 a row that starts off the 16-byte grid needs (144 B)
 struct DetLaneParams {
 	CorrParams c;
 	PeakParams q;
 };
 __host__ __device__ constexpr size_t det_lane_warp_bytes()
 {
-	return (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float) + (size_t)32 * kDlStagePitch * sizeof(float2);
+	// correlation tile [kPadRows + 20 + kPadRows][32] + decimated powers [35][32]; the two staging chunks of the decimator
+	// (2 x [32][kDlStagePitch] samples) lie over the tile, which is not in use while the windows are read
+	return (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float) + 16; // + two mbarriers
 }
 __host__ __device__ constexpr size_t det_lane_hdr_bytes() { return (size_t)kSinc512 * sizeof(float) + corr_nb_hdr_bytes(); }
 __host__ __device__ constexpr size_t det_lane_smem() { return det_lane_hdr_bytes() + kDlWarps * det_lane_warp_bytes(); }
@@ -45,11 +55,19 @@ detect_lane_kernel(DetLaneParams P)
 	unsigned char *wb = dl_raw + det_lane_hdr_bytes() + (size_t)warp * det_lane_warp_bytes();
 	float2 *C = reinterpret_cast<float2 *>(wb);					      // [kPadRows + 20 + kPadRows][32]
 	float *Pw = reinterpret_cast<float *>(wb + (size_t)(20 + 2 * kPadRows) * kRowPitch * 8) + lane; // [35][32]
-	const float2 *stg = reinterpret_cast<const float2 *>(wb + (size_t)(20 + 2 * kPadRows) * kRowPitch * 8 + (size_t)35 * 32 * 4); // [32][kDlStagePitch]
+	const float2 *stg = reinterpret_cast<const float2 *>(wb); // [2][32][kDlStagePitch], over the tile
+	static_assert((size_t)2 * 32 * kDlBulkPitch * sizeof(float2) <= (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2), "staging chunks fit the tile");
+	const unsigned bar_s = (unsigned)__cvta_generic_to_shared(wb + (size_t)(20 + 2 * kPadRows) * kRowPitch * 8 + (size_t)35 * 32 * 4);
+	if (lane == 0) {
+		mbar_init(bar_s, 1);
+		mbar_init(bar_s + 8, 1);
+	}
+	unsigned phase = 0; // bit k: parity of the next wait on staging buffer k
 	const unsigned stg_s = (unsigned)__cvta_generic_to_shared(stg);
 	for (int k = threadIdx.x; k < kSinc512; k += blockDim.x) stab[k] = p.sinc512[k];
 	corr_nb_fill_hdr(hs, sinfo);
 	for (int k = lane; k < (20 + 2 * kPadRows) * kRowPitch; k += 32) C[k] = make_float2(0.0f, 0.0f);
+	fence_proxy_async(); // the mbarriers are visible to the bulk copies
 	__syncthreads();
 
 	const float2 NZ = bc2(p.negzero);
@@ -87,33 +105,87 @@ detect_lane_kernel(DetLaneParams P)
 		if (any) {
 			constexpr unsigned SB = I16 ? 4u : 8u; // bytes per sample
 			const int sub = lane & 15, half = lane >> 4;
+			// Rows of one tile usually share the window start (one burst type): then row r's window is rp0 + r * rowbytes and
+			// no lane has to ask another for its pointer (the shuffles of the general form were a third of all stall samples)
+			const unsigned runmask = __ballot_sync(0xffffffffu, run);
+			const int lead = __ffs(runmask) - 1;
+			const int s_lo0 = __shfl_sync(0xffffffffu, s_lo, lead);
+			const bool uniform = __ballot_sync(0xffffffffu, run && s_lo != s_lo0) == 0u;
+			const unsigned long long rowbytes = (unsigned long long)SB * (unsigned long long)(I16 ? cp.iq_stride : cp.stride);
+			const unsigned long long rp0 = __shfl_sync(0xffffffffu, rowp, lead) - (unsigned long long)lead * rowbytes; // row 0 of the tile
 			auto issue = [&](int c) {
+				const unsigned buf = stg_s + SB * (unsigned)((c & 1) * 32 * kDlStagePitch);
+				if (uniform) {
+					unsigned dst = buf + SB * (unsigned)(half * kDlStagePitch + sub);
+					unsigned long long src = rp0 + (unsigned long long)half * rowbytes + SB * (unsigned)(16 * c + sub);
 #pragma unroll
-				for (int i = 0; i < 16; i++) {
-					const int r = 2 * i + half;
-					const unsigned long long rp = __shfl_sync(0xffffffffu, rowp, r);
-					if (rp) {
-						const unsigned dst = stg_s + SB * (unsigned)(r * kDlStagePitch + sub);
-						const unsigned long long src = rp + SB * (unsigned)(16 * c + sub);
-						if constexpr (I16) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-						else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+					for (int i = 0; i < 16; i++) {
+						if ((runmask >> (2 * i + half)) & 1u) {
+							if constexpr (I16) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+							else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+						}
+						dst += SB * (unsigned)(2 * kDlStagePitch);
+						src += 2 * rowbytes;
+					}
+				} else {
+#pragma unroll
+					for (int i = 0; i < 16; i++) {
+						const int r = 2 * i + half;
+						const unsigned long long rp = __shfl_sync(0xffffffffu, rowp, r);
+						if (rp) {
+							const unsigned dst = buf + SB * (unsigned)(r * kDlStagePitch + sub);
+							const unsigned long long src = rp + SB * (unsigned)(16 * c + sub);
+							if constexpr (I16) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+							else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+						}
 					}
 				}
 				asm volatile("cp.async.commit_group;" ::: "memory");
 			};
+			// float rows: ONE bulk copy (TMA) per row and chunk, issued by the row's own lane - 144 bytes from the 16-byte
+			// grid at or below the window start (e = 0 or 1 samples in front), completion on the buffer's mbarrier.  The
+			// 8-byte cp.async form needs sixteen instructions per chunk, all of which sit in the load/store queue until
+			// their data is back (37 % of the stall samples were mio_throttle).
+			const int e = (int)((rowp >> 3) & 1ull);
+			const unsigned long long rowa = rowp & ~15ull;
+			const unsigned nact = __popc(runmask);
+			auto issue_bulk = [&](int c) {
+				const unsigned bar = bar_s + 8u * (unsigned)(c & 1);
+				fence_proxy_async(); // the buffer's earlier generic accesses are ordered before the asynchronous writes
+				__syncwarp();
+				if (lane == 0) mbar_arrive_expect_tx(bar, nact * (unsigned)(kDlBulkPitch * 8));
+				__syncwarp();
+				// (one lane walking the rows instead - a bulk copy is a uniform-datapath instruction, 32 lanes issuing one each are
+				// serialised at about twenty instructions apiece - was measured slower: 0.65 against 0.55 ms per 2^20 bursts)
+				if (run) {
+					bulk_g2s(stg_s + (unsigned)(((c & 1) * 32 + lane) * kDlBulkPitch * 8), reinterpret_cast<const void *>(rowa + (unsigned long long)(128 * c)),
+						 (unsigned)(kDlBulkPitch * 8), bar);
+				}
+			};
 			float2 X[28];
-			issue(0);
+			__syncwarp(); // the previous tile's peak logic is done with the tile the chunks overlay
+			if constexpr (I16) { issue(0); issue(1); }
+			else { issue_bulk(0); issue_bulk(1); }
 #pragma unroll
 			for (int c = 0; c < 10; c++) {
-				asm volatile("cp.async.wait_group 0;" ::: "memory");
-				__syncwarp();
+				if constexpr (I16) {
+					if (c < 9) asm volatile("cp.async.wait_group 1;" ::: "memory");
+					else asm volatile("cp.async.wait_group 0;" ::: "memory");
+					__syncwarp();
 #pragma unroll
-				for (int t = 0; t < 16; t++) {
-					if constexpr (I16) X[12 + t] = cvt_s2(reinterpret_cast<const unsigned *>(stg)[lane * kDlStagePitch + t]);
-					else X[12 + t] = stg[lane * kDlStagePitch + t];
+					for (int t = 0; t < 16; t++) X[12 + t] = cvt_s2(reinterpret_cast<const unsigned *>(stg)[((c & 1) * 32 + lane) * kDlStagePitch + t]);
+				} else {
+					mbar_wait(bar_s + 8u * (unsigned)(c & 1), (phase >> (c & 1)) & 1u);
+					phase ^= 1u << (c & 1);
+					const float2 *row = stg + ((c & 1) * 32 + lane) * kDlBulkPitch + e;
+#pragma unroll
+					for (int t = 0; t < 16; t++) X[12 + t] = row[t];
 				}
 				__syncwarp();
-				if (c < 9) issue(c + 1);
+				if (c + 2 < 10) {
+					if constexpr (I16) issue(c + 2);
+					else issue_bulk(c + 2);
+				}
 				// outputs 4c - 3 .. 4c: output j reads window samples 4j .. 4j + 15 = X[4j - 16c + 12 ..]
 #pragma unroll
 				for (int o = 0; o < 4; o++) {
@@ -133,6 +205,17 @@ detect_lane_kernel(DetLaneParams P)
 #pragma unroll
 				for (int t = 0; t < 12; t++) X[t] = X[t + 16];
 			}
+			// the chunks lay over the tile: its zero rows in front of and behind the correlation vector are restored (a lane
+			// clears its own column of every pad row; the 20 vector rows are rewritten or cleared by the code below)
+			__syncwarp();
+#pragma unroll
+			for (int r = 0; r < kPadRows; r++) {
+				C[r * kRowPitch + lane] = make_float2(0.0f, 0.0f);
+				C[(kPadRows + 20 + r) * kRowPitch + lane] = make_float2(0.0f, 0.0f);
+			}
+#pragma unroll
+			for (int r = 0; r < 20; r++) Cl0[r * kRowPitch] = make_float2(0.0f, 0.0f);
+			__syncwarp();
 		}
 		if (run) {
 #pragma unroll
