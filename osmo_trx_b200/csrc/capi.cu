@@ -2,6 +2,7 @@
 // the host-buffer pipeline.  This translation unit includes the kernel sources so that all kernels
 // share one __constant__ table block (no relocatable device code needed).
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -64,6 +65,7 @@ struct trxb200_ctx {
 	float *d_sinc512 = nullptr;
 	float *d_comp = nullptr;
 	float2 *d_edge_tab = nullptr; // derotation + ideal-symbol tables for the EDGE demodulator
+	void *d_tmap = nullptr;	      // TMA descriptors of detect_lane_kernel (four slots)
 	float *d_mod_tab = nullptr;   // modulator tables in global memory (per-lane indexed): rot4 | c0 | c1 | edge_rot | psk8
 	uint64_t launches = 0;
 	int max_seq_len = 40; // longest sync sequence detect batches may need (sizes on-chip buffers)
@@ -86,7 +88,8 @@ struct trxb200_ctx {
 		int host_chunk = 16384; // slots per stage of the pinned-host pipelines (H2D | kernels | D2H on three streams)
 		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
 		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
-		int detect_lane = 0; // 1: detect_lane_kernel (lane = burst, one launch) for the normal-burst geometry; 0: corr_nb_kernel + peak_kernel
+		int detect_tma = 1; // detect_lane_kernel: window chunks as TMA tiles (two per chunk) instead of one bulk copy per row
+		int detect_lane = 1; // 1: detect_lane_kernel (lane = burst, one launch) for the normal-burst geometry; 0: corr_nb_kernel + peak_kernel
 		int vitac_lane = 1; // 1: vitac_lane_kernel (lane = burst), 0: vitac_kernel (warp = burst pair)
 		int corr_wpb = 18; // corr_nb_kernel as one CTA of 18 warps per SM (96 registers) instead of two of 8 (118): 0.383 -> 0.373 ms per 2^20 bursts
 		int demod_wpb = 8; // warps per demod CTA (two CTAs per SM); 17 = one CTA of 17 warps.  Measured per 2^20 bursts (profiles/r2o_demod_warps.txt):
@@ -344,6 +347,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_CORR_WPB", t.corr_wpb);
 		env_int("TRXB200_VITAC_LANE", t.vitac_lane);
 		env_int("TRXB200_DETECT_LANE", t.detect_lane);
+		env_int("TRXB200_DETECT_TMA", t.detect_tma);
 		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
 		env_int("TRXB200_HOST_CHUNK", t.host_chunk);
 		env_int("TRXB200_CORR_BPS", t.corr_bps);
@@ -380,6 +384,7 @@ void trxb200_destroy(trxb200_ctx *ctx)
 	cudaFree(ctx->ws.pwr);
 	if (ctx->d_comp) cudaFree(ctx->d_comp);
 	if (ctx->d_edge_tab) cudaFree(ctx->d_edge_tab);
+	if (ctx->d_tmap) cudaFree(ctx->d_tmap);
 	if (ctx->d_mod_tab) cudaFree(ctx->d_mod_tab);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
@@ -683,6 +688,45 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			q.n = n; q.type = type; q.tsc = tsc; q.max_toa = max_toa; q.round = r; q.last_round = (r == nrounds - 1); q.sch = 0;
 			q.max_toa_bound = bound; q.thresh = thresh; q.lmax = lmax; q.ndmax = ndmax; q.corr = nullptr; q.pwr = nullptr;
 			q.sinc512 = ctx->d_sinc512; q.negzero = -0.0f; q.rc = rc; q.amp = amp; q.toa = toa; q.ci = ci; q.tsc_out = tsc_out; q.flags = flags;
+			dp.tma_on = 0;
+			dp.tmap = nullptr;
+			if (!iq && tn.detect_tma && n >= 2 && (reinterpret_cast<uintptr_t>(bursts) & 15u) == 0) {
+				// the rows taken two at a time are a legal TMA tensor: [n / 2][4 * stride] floats, row pitch 16 * stride bytes
+				typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+							     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+							     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+				static EncodeFn encode = nullptr;
+				if (!encode) {
+					void *fn = nullptr;
+					cudaDriverEntryPointQueryResult qr;
+					if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+						encode = (EncodeFn)fn;
+					else
+						cudaGetLastError();
+				}
+				if (encode && !ctx->d_tmap) {
+					if (cudaMalloc(&ctx->d_tmap, 4 * sizeof(CUtensorMap)) != cudaSuccess) { ctx->d_tmap = nullptr; cudaGetLastError(); }
+				}
+				if (encode && ctx->d_tmap) {
+					alignas(64) CUtensorMap tm;
+					const cuuint64_t gdim[2] = { (cuuint64_t)4 * (cuuint64_t)stride, (cuuint64_t)(n / 2) };
+					const cuuint64_t gstr[1] = { (cuuint64_t)16 * (cuuint64_t)stride };
+					const cuuint32_t box[2] = { 2u * kDlBulkPitch, 16u }, est[2] = { 1u, 1u }; // 18 samples x 16 row pairs
+					if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(bursts), gdim, gstr, box, est,
+						   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+						   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+						// the descriptor lives in global memory (one slot per round; stream order keeps a slot intact while a
+						// kernel that reads it is still running)
+						unsigned char *slot = reinterpret_cast<unsigned char *>(ctx->d_tmap) + (size_t)(r & 3) * sizeof(CUtensorMap);
+						if (cudaMemcpyAsync(slot, &tm, sizeof(CUtensorMap), cudaMemcpyHostToDevice, st) == cudaSuccess) {
+							dp.tmap = slot;
+							dp.tma_on = 1;
+						} else {
+							cudaGetLastError();
+						}
+					}
+				}
+			}
 			const int ntiles = (n + 31) / 32;
 			const int grid = std::max(1, std::min((ntiles + kDlWarps - 1) / kDlWarps, ctx->sm_count));
 			prof_pre(ctx, st);

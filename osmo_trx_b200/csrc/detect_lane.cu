@@ -13,13 +13,13 @@
 //              thread's column of the warp's [row][lane] tile
 //   peak       peak_lane() of detect.cu on that column - the same function the two-kernel path runs
 // Arithmetic per output is the two-kernel path's, bit for bit (the GPU parity suites run green on it), and the chain
-// itself needs about 130 warp instructions per burst against 263.  What it cannot get cheaply is its input: 32 rows of
-// 1,216 bytes, 5,000 bytes apart, per warp.  Measured per 2^20 bursts (corr_nb_kernel + peak_kernel: 0.53 ms): every thread
-// loading its own row 1.58 ms (32 sector requests per load: lg_throttle); 8-byte cp.async chunks 0.68 ms (sixteen copies per
-// chunk sit in the load/store queue until their data is back: mio_throttle); one TMA bulk copy per row and chunk 0.55 ms
-// (the bulk copies are serialised through the uniform datapath: half of the kernel's instructions).  At parity, not ahead:
-// opt-in (TRXB200_DETECT_LANE=1).  The same mapping is a 2.4x win where the per-thread work per byte is high
-// (vitac_lane_kernel).
+// itself needs about 130 warp instructions per burst against 263.  The hard part is its input: 32 rows of 1,216 bytes,
+// 5,000 bytes apart, per warp.  Measured per 2^20 bursts (corr_nb_kernel + peak_kernel: 0.53 ms): every thread loading its
+// own row 1.58 ms (32 sector requests per load: lg_throttle); 8-byte cp.async chunks 0.68 ms (sixteen copies per chunk sit
+// in the load/store queue until their data is back: mio_throttle); one TMA bulk copy per row and chunk 0.55 ms (the bulk
+// copies are serialised through the uniform datapath: half of the kernel's instructions); TMA TILE copies over the rows
+// taken two at a time (below) 0.42 ms - the default.  Rows that are not on the 16-byte grid, int16 rows and tiles with mixed
+// window starts keep the per-row forms.
 #include "device_tables.cuh"
 #include "kernels.hpp"
 
@@ -29,23 +29,37 @@ constexpr int kDlWarps = 12;	 // warps per CTA, one CTA per SM
 constexpr int kDlStagePitch = 17; // samples per row of the staging chunk (16 + 1: lanes = rows read conflict free)
 constexpr int kDlBulkPitch = 18;  // float rows, bulk copies: 16 samples + the 2 a row that starts off the 16-byte grid needs (144 B)
 struct DetLaneParams {
+	const void *tmap; // CUtensorMap (in global memory, 64-byte aligned) over the burst rows taken two at a time (below); used when tma_on
 	CorrParams c;
 	PeakParams q;
+	int tma_on; // float rows on the 16-byte grid: window chunks arrive as TMA tiles
 };
 __host__ __device__ constexpr size_t det_lane_warp_bytes()
 {
-	// correlation tile [kPadRows + 20 + kPadRows][32] + decimated powers [35][32]; the two staging chunks of the decimator
-	// (2 x [32][kDlStagePitch] samples) lie over the tile, which is not in use while the windows are read
-	return (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float) + 16; // + two mbarriers
+	// correlation tile [kPadRows + 20 + kPadRows][32] + decimated powers [35][32] + two mbarriers, rounded to 1 KB (the
+	// TMA swizzle pattern is a function of the shared address); the staging chunks of the decimator lie over the tile,
+	// which is not in use while the windows are read
+	return (((size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float) + 16) + 1023) & ~(size_t)1023;
 }
-__host__ __device__ constexpr size_t det_lane_hdr_bytes() { return (size_t)kSinc512 * sizeof(float) + corr_nb_hdr_bytes(); }
+__host__ __device__ constexpr size_t det_lane_hdr_bytes() { return ((size_t)kSinc512 * sizeof(float) + corr_nb_hdr_bytes() + 1023) & ~(size_t)1023; }
 __host__ __device__ constexpr size_t det_lane_smem() { return det_lane_hdr_bytes() + kDlWarps * det_lane_warp_bytes(); }
+
+// A row stride of 625 samples (5,000 bytes) is not a legal TMA stride, but TWO rows are (16 * stride bytes): the burst array
+// is described to the TMA as [n / 2][4 * stride] floats.  One tile copy then brings the same 16 window samples of the 16 even
+// rows of a warp's 32 bursts, a second one (inner coordinate + 2 * stride floats) those of the 16 odd rows: two instructions
+// per chunk instead of one per row.  Boxes of 16 rows x 18 samples (144 bytes: the row pitch in shared memory skews the banks).
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int c0, int c1, unsigned bar)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+		     "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+		     : "memory");
+}
 
 template <bool I16>
 __global__ void __launch_bounds__(kDlWarps * 32, 1)
-detect_lane_kernel(DetLaneParams P)
+detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 {
-	extern __shared__ __align__(16) unsigned char dl_raw[];
+	extern __shared__ __align__(1024) unsigned char dl_raw[];
 	const CorrParams &cp = P.c;
 	const PeakParams &p = P.q;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,9 +176,31 @@ detect_lane_kernel(DetLaneParams P)
 						 (unsigned)(kDlBulkPitch * 8), bar);
 				}
 			};
+			// float rows on the 16-byte grid, one window start for the whole tile, rows inside the TMA's view: two tile copies
+			bool tma = false;
+			if constexpr (!I16) tma = P.tma_on && uniform && (((p.n & 1) == 0) || tile * 32 + 32 <= (p.n & ~1));
+			// (the TMA wants the start of a box on the 16-byte grid: a row's chunk starts at the even sample at or below the window
+			// sample and is 18 samples long; e_even / e_odd = the sample in front for the even and the odd rows of the tile)
+			const int e_even = s_lo0 & 1, e_odd = (cp.stride + s_lo0) & 1;
+			auto issue_tma = [&](int c) {
+				const unsigned bar = bar_s + 8u * (unsigned)(c & 1);
+				fence_proxy_async();
+				__syncwarp();
+				if (lane == 0) {
+					mbar_arrive_expect_tx(bar, 2u * 16u * (unsigned)(kDlBulkPitch * 8));
+					const unsigned dst = stg_s + (unsigned)((c & 1) * 2 * 16 * kDlBulkPitch * 8);
+					const int c1 = tile * 16;
+					tma_load_2d(dst, P.tmap, 2 * (s_lo0 + 16 * c - e_even), c1, bar);
+					tma_load_2d(dst + (unsigned)(16 * kDlBulkPitch * 8), P.tmap, 2 * (cp.stride + s_lo0 + 16 * c - e_odd), c1, bar);
+				}
+			};
+			// the lane's row in a staged chunk: box lane & 1 (even / odd rows), row lane >> 1, 18 samples per row, its window
+			// sample t at t + e; rows 144 bytes apart and the two boxes one sample out of step: conflict-free 8-byte reads
+			const int trow = (lane & 1) * 16 * kDlBulkPitch + (lane >> 1) * kDlBulkPitch + ((lane & 1) ? e_odd : e_even);
 			float2 X[28];
 			__syncwarp(); // the previous tile's peak logic is done with the tile the chunks overlay
 			if constexpr (I16) { issue(0); issue(1); }
+			else if (tma) { issue_tma(0); issue_tma(1); }
 			else { issue_bulk(0); issue_bulk(1); }
 #pragma unroll
 			for (int c = 0; c < 10; c++) {
@@ -177,13 +213,20 @@ detect_lane_kernel(DetLaneParams P)
 				} else {
 					mbar_wait(bar_s + 8u * (unsigned)(c & 1), (phase >> (c & 1)) & 1u);
 					phase ^= 1u << (c & 1);
-					const float2 *row = stg + ((c & 1) * 32 + lane) * kDlBulkPitch + e;
+					if (tma) {
+						const float2 *row = stg + (c & 1) * 2 * 16 * kDlBulkPitch + trow;
 #pragma unroll
-					for (int t = 0; t < 16; t++) X[12 + t] = row[t];
+						for (int t = 0; t < 16; t++) X[12 + t] = row[t];
+					} else {
+						const float2 *row = stg + ((c & 1) * 32 + lane) * kDlBulkPitch + e;
+#pragma unroll
+						for (int t = 0; t < 16; t++) X[12 + t] = row[t];
+					}
 				}
 				__syncwarp();
 				if (c + 2 < 10) {
 					if constexpr (I16) issue(c + 2);
+					else if (tma) issue_tma(c + 2);
 					else issue_bulk(c + 2);
 				}
 				// outputs 4c - 3 .. 4c: output j reads window samples 4j .. 4j + 15 = X[4j - 16c + 12 ..]
