@@ -41,6 +41,8 @@ struct DetectScratch {
 	float2 *corr = nullptr; // [cap][lmax]
 	float *pwr = nullptr;	// [cap][ndmax]
 	size_t corr_bytes = 0, pwr_bytes = 0;
+	int *list = nullptr; // detect_lane_kernel's retry lists: two counters (32 bytes apart), then two lists of list_cap bursts
+	size_t list_cap = 0;
 };
 
 // device scratch of the pull path (int16 slots -> TRXD datagrams) for one chunk of slots
@@ -89,6 +91,7 @@ struct trxb200_ctx {
 		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
 		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
 		int detect_tma = 1; // detect_lane_kernel: window chunks as TMA tiles (two per chunk) instead of one bulk copy per row
+		int detect_lists = 1; // detect_lane_kernel: rounds after the first walk a list of the bursts left for them
 		int detect_lane = 1; // 1: detect_lane_kernel (lane = burst, one launch) for the normal-burst geometry; 0: corr_nb_kernel + peak_kernel
 		int vitac_lane = 1; // 1: vitac_lane_kernel (lane = burst), 0: vitac_kernel (warp = burst pair)
 		int corr_wpb = 18; // corr_nb_kernel as one CTA of 18 warps per SM (96 registers) instead of two of 8 (118): 0.383 -> 0.373 ms per 2^20 bursts
@@ -347,6 +350,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_CORR_WPB", t.corr_wpb);
 		env_int("TRXB200_VITAC_LANE", t.vitac_lane);
 		env_int("TRXB200_DETECT_LANE", t.detect_lane);
+		env_int("TRXB200_DETECT_LISTS", t.detect_lists);
 		env_int("TRXB200_DETECT_TMA", t.detect_tma);
 		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
 		env_int("TRXB200_HOST_CHUNK", t.host_chunk);
@@ -382,6 +386,7 @@ void trxb200_destroy(trxb200_ctx *ctx)
 	if (ctx->d_sinc512) cudaFree(ctx->d_sinc512);
 	cudaFree(ctx->ws.corr);
 	cudaFree(ctx->ws.pwr);
+	cudaFree(ctx->ws.list);
 	if (ctx->d_comp) cudaFree(ctx->d_comp);
 	if (ctx->d_edge_tab) cudaFree(ctx->d_edge_tab);
 	if (ctx->d_tmap) cudaFree(ctx->d_tmap);
@@ -675,11 +680,33 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 		if (!ctx->cfg_detlane) {
 			CK(cudaFuncSetAttribute(detect_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_lane_smem()));
 			CK(cudaFuncSetAttribute(detect_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_lane_smem()));
+			CK(cudaFuncSetAttribute(detect_lane_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_lane_smem()));
+			CK(cudaFuncSetAttribute(detect_lane_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_lane_smem()));
 			ctx->cfg_detlane = true;
 		}
 		const int nrounds = ctx->max_attempts;
+		// later rounds walk the list of bursts the round before left for them (detect_lane.cu); lists ping-pong
+		const bool lists = nrounds > 1 && tn.detect_lists;
+		if (lists) {
+			if (ws.list_cap < (size_t)n) {
+				CK(cudaStreamSynchronize(st));
+				cudaFree(ws.list);
+				ws.list = nullptr; ws.list_cap = 0;
+				const size_t cap = ((size_t)n + 1023) & ~(size_t)1023;
+				CK(cudaMalloc(&ws.list, (16 + 2 * cap) * sizeof(int)));
+				ws.list_cap = cap;
+			}
+			CK(cudaMemsetAsync(ws.list, 0, 16 * sizeof(int), st));
+		}
 		for (int r = 0; r < nrounds; r++) {
 			DetLaneParams dp;
+			dp.list_in = dp.list_n_in = nullptr;
+			dp.list_out = dp.list_n_out = nullptr;
+			if (lists) {
+				// round r appends to list r & 1 and counts in ws.list[4 * r] (a counter of its own per round); lists start at ws.list + 16
+				if (r > 0) { dp.list_in = ws.list + 16 + (size_t)((r - 1) & 1) * ws.list_cap; dp.list_n_in = ws.list + 4 * (r - 1); }
+				if (r + 1 < nrounds) { dp.list_out = ws.list + 16 + (size_t)(r & 1) * ws.list_cap; dp.list_n_out = ws.list + 4 * r; }
+			}
 			CorrParams &c = dp.c;
 			c.bursts = bursts; c.stride = stride; c.n = n; c.iq = iq; c.iq_stride = iq_stride; c.type = type; c.tsc = tsc; c.max_toa = max_toa;
 			c.rc = rc; c.round = r; c.sch = 0; c.max_toa_bound = bound; c.lmax = lmax; c.ndmax = ndmax; c.corr = nullptr; c.pwr = nullptr;
@@ -690,7 +717,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			q.sinc512 = ctx->d_sinc512; q.negzero = -0.0f; q.rc = rc; q.amp = amp; q.toa = toa; q.ci = ci; q.tsc_out = tsc_out; q.flags = flags;
 			dp.tma_on = 0;
 			dp.tmap = nullptr;
-			if (!iq && tn.detect_tma && n >= 2 && (reinterpret_cast<uintptr_t>(bursts) & 15u) == 0) {
+			if (!iq && !dp.list_in && tn.detect_tma && n >= 2 && (reinterpret_cast<uintptr_t>(bursts) & 15u) == 0) {
 				// the rows taken two at a time are a legal TMA tensor: [n / 2][4 * stride] floats, row pitch 16 * stride bytes
 				typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
 							     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -730,8 +757,13 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			const int ntiles = (n + 31) / 32;
 			const int grid = std::max(1, std::min((ntiles + kDlWarps - 1) / kDlWarps, ctx->sm_count));
 			prof_pre(ctx, st);
-			if (iq) detect_lane_kernel<true><<<grid, kDlWarps * 32, det_lane_smem(), st>>>(dp);
-			else detect_lane_kernel<false><<<grid, kDlWarps * 32, det_lane_smem(), st>>>(dp);
+			if (dp.list_in) {
+				if (iq) detect_lane_kernel<true, true><<<grid, kDlWarps * 32, det_lane_smem(), st>>>(dp);
+				else detect_lane_kernel<false, true><<<grid, kDlWarps * 32, det_lane_smem(), st>>>(dp);
+			} else {
+				if (iq) detect_lane_kernel<true><<<grid, kDlWarps * 32, det_lane_smem(), st>>>(dp);
+				else detect_lane_kernel<false><<<grid, kDlWarps * 32, det_lane_smem(), st>>>(dp);
+			}
 			prof_post(ctx, st, "detect_lane_kernel");
 			const int e = post_launch(ctx, "detect_lane_kernel");
 			if (e) return e;
@@ -1038,7 +1070,7 @@ static void stage_free(HostStage *s)
 	for (int k = 0; k < HostStage::kSlots; k++) {
 		cudaFree(s->d_bursts[k]); cudaFree(s->d_soft[k]); cudaFree(s->d_in[k]); cudaFree(s->d_out[k]);
 		cudaFreeHost(s->h_in[k]); cudaFreeHost(s->h_out[k]); cudaFreeHost(s->h_bursts[k]); cudaFreeHost(s->h_soft[k]);
-		cudaFree(s->ws[k].corr); cudaFree(s->ws[k].pwr);
+		cudaFree(s->ws[k].corr); cudaFree(s->ws[k].pwr); cudaFree(s->ws[k].list);
 		if (s->streams[k]) cudaStreamDestroy(s->streams[k]);
 	}
 	delete s;
@@ -1174,7 +1206,7 @@ int trxb200_detect_demod_host(trxb200_ctx *ctx, const float *bursts, int stride,
 static void pull_scratch_free(PullScratch &w)
 {
 	cudaFree(w.bursts); cudaFree(w.pw); cudaFree(w.type2); cudaFree(w.tsc_out); cudaFree(w.amp); cudaFree(w.toa);
-	cudaFree(w.ci); cudaFree(w.ws.corr); cudaFree(w.ws.pwr);
+	cudaFree(w.ci); cudaFree(w.ws.corr); cudaFree(w.ws.pwr); cudaFree(w.ws.list);
 	w = PullScratch();
 }
 

@@ -33,6 +33,11 @@ struct DetLaneParams {
 	CorrParams c;
 	PeakParams q;
 	int tma_on; // float rows on the 16-byte grid: window chunks arrive as TMA tiles
+	// Rounds after the first visit only the bursts the round before left undetected WITH a further attempt to make (EDGE ->
+	// TSC fall-through): round r appends them to list_out (count in *list_n_out), round r + 1 walks list_in.  Without the
+	// list a later round finds one or two such bursts in nearly every tile of 32 and pays a whole tile for each.
+	const int *list_in, *list_n_in; // null: the tile's bursts are 32 consecutive rows
+	int *list_out, *list_n_out;	 // null: no further round
 };
 __host__ __device__ constexpr size_t det_lane_warp_bytes()
 {
@@ -55,7 +60,7 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int 
 		     : "memory");
 }
 
-template <bool I16>
+template <bool I16, bool LISTED = false>
 __global__ void __launch_bounds__(kDlWarps * 32, 1)
 detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 {
@@ -91,10 +96,12 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 	for (int k = 0; k < 16; k++) g16[k] = c_tab.dnsamp[k];
 	float2 *Cl0 = C + kPadRows * kRowPitch + lane; // row i of this lane's burst: Cl0[i * kRowPitch]
 
-	const int ntiles = (p.n + 31) >> 5;
+	constexpr bool listed = LISTED; // (a variant of its own: the indirection costs the int16 kernel its last free registers)
+	const int n_eff = listed ? *P.list_n_in : p.n;
+	const int ntiles = (n_eff + 31) >> 5;
 	for (int tile = blockIdx.x * kDlWarps + warp; tile < ntiles; tile += gridDim.x * kDlWarps) {
-		const int b = tile * 32 + lane;
-		const bool valid = b < p.n;
+		const bool valid = tile * 32 + lane < n_eff;
+		const int b = listed ? (valid ? P.list_in[tile * 32 + lane] : 0) : tile * 32 + lane;
 		int type = 0, tsc = 0, T = 0, rc = 0;
 		if (valid) {
 			type = load_type(p.type, b, 0);
@@ -124,7 +131,7 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 			const unsigned runmask = __ballot_sync(0xffffffffu, run);
 			const int lead = __ffs(runmask) - 1;
 			const int s_lo0 = __shfl_sync(0xffffffffu, s_lo, lead);
-			const bool uniform = __ballot_sync(0xffffffffu, run && s_lo != s_lo0) == 0u;
+			const bool uniform = !listed && __ballot_sync(0xffffffffu, run && s_lo != s_lo0) == 0u;
 			const unsigned long long rowbytes = (unsigned long long)SB * (unsigned long long)(I16 ? cp.iq_stride : cp.stride);
 			const unsigned long long rp0 = __shfl_sync(0xffffffffu, rowp, lead) - (unsigned long long)lead * rowbytes; // row 0 of the tile
 			auto issue = [&](int c) {
@@ -299,6 +306,19 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 			if (p.flags) {
 				if (p.round == 0) p.flags[b] = (uint8_t)res.flags;
 				else if (res.flags) p.flags[b] |= (uint8_t)res.flags;
+			}
+		}
+		if (P.list_out) {
+			// every burst the next round can touch: still undetected and a further attempt exists (peak_lane's own conditions)
+			bool again = false;
+			if (valid && (res.write_all ? res.rc : rc) == 0 && type_known(type) && !((type == 1 || type == 5) && tsc > 7) && T <= p.max_toa_bound)
+				again = make_attempt(type, tsc, T, p.round + 1).seq >= 0;
+			const unsigned am = __ballot_sync(0xffffffffu, again);
+			if (am) {
+				int base = 0;
+				if (lane == 0) base = atomicAdd(P.list_n_out, __popc(am));
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (again) P.list_out[base + __popc(am & ((1u << lane) - 1u))] = b;
 			}
 		}
 	}
