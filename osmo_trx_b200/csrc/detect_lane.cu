@@ -19,7 +19,10 @@
 // in the load/store queue until their data is back: mio_throttle); one TMA bulk copy per row and chunk 0.55 ms (the bulk
 // copies are serialised through the uniform datapath: half of the kernel's instructions); TMA TILE copies over the rows
 // taken two at a time (below) 0.42 ms - the default.  Rows that are not on the 16-byte grid, int16 rows and tiles with mixed
-// window starts keep the per-row forms.
+// window starts keep the per-row forms.  With the tile copies 36 % of the stall samples are waits for a chunk (ncu, profiles/
+// r3a_detect_lane_summary.txt); asking for the rest of a tile's window ahead of time with four wide
+// cp.async.bulk.prefetch.tensor boxes made it slower (0.475 against 0.44 ms): the limit is the rate at which the copy engine
+// turns boxes of 144-byte rows into requests, not the latency of one of them.
 #include "device_tables.cuh"
 #include "kernels.hpp"
 
