@@ -30,6 +30,7 @@ __constant__ ConstTables c_tab;
 #include "vitac.cu"
 #include "vitac_lane.cu"
 #include "filterbank.cu"
+#include "resampler_pq.cu"
 #include "pull.cu"
 
 using namespace trxb200;
@@ -85,6 +86,7 @@ struct trxb200_ctx {
 		// need the whole register file of an SM to hide their latencies - so the pipeline is off unless asked for
 		int overlap = 0, chunk_cap = 131072;
 		int detect_chunk = 1 << 30; // bursts per corr/peak launch pair.  Measured (profiles/r2l_detect_chunk_sweep.txt): one pair for the whole batch beats 262,144-burst chunks (corr 0.454 -> 0.403 ms, peak 0.220 -> 0.178 ms per 2^20 bursts); keeping the intermediates L2 resident with small chunks does not pay for the extra launches and tails
+		int resamp_pq = 1; // 1: resampler_pq_kernel for the 65/48 and 48/65 ratios of the multi-ARFCN interface
 		int resamp_up = 0; // 1: resampler_up_kernel (three outputs per thread from a register window) for interpolating ratios; measured 4.4 ms vs 3.2 ms of resampler16_kernel on the cfg-5 stream (profiles/r2k_*), so off by default
 		int fused = 0; // 1: nb_fused_kernel (one persistent warp-specialised kernel) for detect+demod in the normal-burst geometry; measured 2.75 ms vs 1.76 ms per 2^20 bursts for the three-kernel path (profiles/r2f_*), so off by default
 		int host_chunk = 16384; // slots per stage of the pinned-host pipelines (H2D | kernels | D2H on three streams)
@@ -344,6 +346,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_OVERLAP", t.overlap);
 		env_int("TRXB200_FUSED", t.fused);
 		env_int("TRXB200_RESAMP_UP", t.resamp_up);
+		env_int("TRXB200_RESAMP_PQ", t.resamp_pq);
 		env_int("TRXB200_CHUNK", t.chunk_cap);
 		env_int("TRXB200_DETECT_CHUNK", t.detect_chunk);
 		env_int("TRXB200_DEMOD_WPB", t.demod_wpb);

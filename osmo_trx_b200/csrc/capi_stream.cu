@@ -194,6 +194,34 @@ int trxb200_resampler_taps(trxb200_resampler *r, int path, float *out_host)
 
 static int resampler_rotate_impl(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out, int out_len,
 				 int out_stride, int n_streams, bool capped);
+// resampler_pq_kernel (resampler_pq.cu): the ratio is a template parameter
+extern "C++" {
+template <int P, int Q, int R, int NCH>
+static int launch_resampler_pq(trxb200_resampler *r, const float *in, int in_stride, float *out, int out_len, int out_stride, int n_streams)
+{
+	trxb200_ctx *ctx = r->ctx;
+	using G = RsPqGeom<P, Q, R, NCH>;
+	static_assert(sizeof(RsPqParams<P, Q>) <= 32764, "kernel parameter block");
+	RsPqParams<P, Q> M;
+	M.in = in; M.out = out; M.in_stride = in_stride; M.out_len = out_len; M.out_stride = out_stride; M.n_streams = n_streams;
+	M.negzero = -0.0f;
+	for (int rho = 0; rho < P; rho++)
+		std::memcpy(M.tp[rho], r->taps.data() + (size_t)((Q * rho) % P) * 16, 16 * sizeof(float));
+	const int warps = (int)std::max<size_t>(1, std::min<size_t>(12, (size_t)(225 * 1024 - G::hdr_bytes) / G::warp_bytes));
+	const size_t smem = G::hdr_bytes + (size_t)warps * G::warp_bytes;
+	static bool cfg = false;
+	if (!cfg) {
+		CK(cudaFuncSetAttribute(resampler_pq_kernel<P, Q, R, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		cfg = true;
+	}
+	const long tiles = (long)n_streams * ((out_len / P + 31) / 32);
+	const int grid = (int)std::max<long>(1, std::min<long>((tiles + warps - 1) / warps, (long)ctx->sm_count));
+	prof_pre(ctx, ctx->stream);
+	resampler_pq_kernel<P, Q, R, NCH><<<grid, warps * 32, smem, ctx->stream>>>(M);
+	prof_post(ctx, ctx->stream, "resampler_pq_kernel");
+	return post_launch(ctx, "resampler_pq_kernel");
+}
+} // extern "C++"
 int trxb200_resampler_rotate(trxb200_resampler *r, const float *in, int in_len, int in_stride, float *out, int out_len,
 			     int out_stride, int n_streams)
 {
@@ -216,6 +244,11 @@ static int resampler_rotate_impl(trxb200_resampler *r, const float *in, int in_l
 	if (in_len % r->q || out_len % r->p || in_len / r->q != out_len / r->p || (capped && out_len > 4096 * 4))
 		return fail(ctx, TRXB200_EINVAL, "resampler_rotate: block length mismatch");
 	if (n_streams == 0) return TRXB200_OK;
+	if (r->L == 16 && ctx->tune.resamp_pq) {
+		// the multi-ARFCN interface's own ratios: R outputs per thread from one register window, everything compile-time
+		if (r->p == 65 && r->q == 48) return launch_resampler_pq<65, 48, 5, 3>(r, in, in_stride, out, out_len, out_stride, n_streams);
+		if (r->p == 48 && r->q == 65) return launch_resampler_pq<48, 65, 4, 2>(r, in, in_stride, out, out_len, out_stride, n_streams);
+	}
 	if (r->L == 16 && r->q <= r->p && r->p <= kRsMaxP && ctx->tune.resamp_up) {
 		// interpolating ratio: three outputs per thread from one register window (filterbank.cu, resampler_up_kernel)
 		static_assert(sizeof(ResampUpParams) <= 32764, "kernel parameter block");
