@@ -720,7 +720,11 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			q.sinc512 = ctx->d_sinc512; q.negzero = -0.0f; q.rc = rc; q.amp = amp; q.toa = toa; q.ci = ci; q.tsc_out = tsc_out; q.flags = flags;
 			dp.tma_on = 0;
 			dp.tmap = nullptr;
-			if (!iq && !dp.list_in && tn.detect_tma && n >= 2 && (reinterpret_cast<uintptr_t>(bursts) & 15u) == 0) {
+			dp.tma_shift = 0;
+			if (!iq && !dp.list_in && tn.detect_tma && n >= 2 && (reinterpret_cast<uintptr_t>(bursts) & 7u) == 0) {
+				// (an array that starts 8 bytes off the 16-byte grid is described from one sample in front of it; no box reaches that sample)
+				dp.tma_shift = (int)((reinterpret_cast<uintptr_t>(bursts) >> 3) & 1u);
+				const float *tbase = bursts - 2 * dp.tma_shift;
 				// the rows taken two at a time are a legal TMA tensor: [n / 2][4 * stride] floats, row pitch 16 * stride bytes
 				typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
 							     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -742,7 +746,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 					const cuuint64_t gdim[2] = { (cuuint64_t)4 * (cuuint64_t)stride, (cuuint64_t)(n / 2) };
 					const cuuint64_t gstr[1] = { (cuuint64_t)16 * (cuuint64_t)stride };
 					const cuuint32_t box[2] = { 2u * kDlBulkPitch, 16u }, est[2] = { 1u, 1u }; // 18 samples x 16 row pairs
-					if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(bursts), gdim, gstr, box, est,
+					if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(tbase), gdim, gstr, box, est,
 						   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 						   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
 						// the descriptor lives in global memory (one slot per round; stream order keeps a slot intact while a

@@ -35,7 +35,9 @@ struct DetLaneParams {
 	const void *tmap; // CUtensorMap (in global memory, 64-byte aligned) over the burst rows taken two at a time (below); used when tma_on
 	CorrParams c;
 	PeakParams q;
-	int tma_on; // float rows on the 16-byte grid: window chunks arrive as TMA tiles
+	int tma_on; // float rows: window chunks arrive as TMA tiles
+	int tma_shift; // 1: the burst array starts on an odd sample (8 bytes off the 16-byte grid, e.g. slots addressed in place in a
+		       // resampled stream): the tensor starts one sample in front of it and every sample index moves up by one
 	// Rounds after the first visit only the bursts the round before left undetected WITH a further attempt to make (EDGE ->
 	// TSC fall-through): round r appends them to list_out (count in *list_n_out), round r + 1 walks list_in.  Without the
 	// list a later round finds one or two such bursts in nearly every tile of 32 and pays a whole tile for each.
@@ -191,7 +193,8 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 			if constexpr (!I16) tma = P.tma_on && uniform && (((p.n & 1) == 0) || tile * 32 + 32 <= (p.n & ~1));
 			// (the TMA wants the start of a box on the 16-byte grid: a row's chunk starts at the even sample at or below the window
 			// sample and is 18 samples long; e_even / e_odd = the sample in front for the even and the odd rows of the tile)
-			const int e_even = s_lo0 & 1, e_odd = (cp.stride + s_lo0) & 1;
+			const int s_t = s_lo0 + P.tma_shift; // window start as a sample index of the tensor's rows
+			const int e_even = s_t & 1, e_odd = (cp.stride + s_t) & 1;
 			auto issue_tma = [&](int c) {
 				const unsigned bar = bar_s + 8u * (unsigned)(c & 1);
 				fence_proxy_async();
@@ -200,8 +203,8 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 					mbar_arrive_expect_tx(bar, 2u * 16u * (unsigned)(kDlBulkPitch * 8));
 					const unsigned dst = stg_s + (unsigned)((c & 1) * 2 * 16 * kDlBulkPitch * 8);
 					const int c1 = tile * 16;
-					tma_load_2d(dst, P.tmap, 2 * (s_lo0 + 16 * c - e_even), c1, bar);
-					tma_load_2d(dst + (unsigned)(16 * kDlBulkPitch * 8), P.tmap, 2 * (cp.stride + s_lo0 + 16 * c - e_odd), c1, bar);
+					tma_load_2d(dst, P.tmap, 2 * (s_t + 16 * c - e_even), c1, bar);
+					tma_load_2d(dst + (unsigned)(16 * kDlBulkPitch * 8), P.tmap, 2 * (cp.stride + s_t + 16 * c - e_odd), c1, bar);
 				}
 			};
 			// the lane's row in a staged chunk: box lane & 1 (even / odd rows), row lane >> 1, 18 samples per row, its window

@@ -679,6 +679,40 @@ def test_wide_window_with_short_sequences(trx, checker):
     assert rep["detected"] > 1500
 
 
+def test_detect_rows_off_the_16_byte_grid(trx):
+    """A burst array that starts on an odd sample (8 bytes off the 16-byte grid: slots addressed in place in a resampled stream)
+    takes detect_lane_kernel's TMA path through a tensor that starts one sample in front of it; an odd row count leaves the last
+    tile to the per-row copies.  Every detection output must equal the aligned run's, bit for bit."""
+    rng = np.random.default_rng(77)
+    ref = cpulibs.Ref() if cpulibs.Ref.available() else cpulibs.Oracle()
+    for n in (2048, 2049 + 32):
+        tsc = np.arange(n) % 8
+        w = ref.modulate_gmsk_batch(synth.nb_bits(n, tsc, rng))
+        rx, _ = synth.impair(w, rng, snr_db=12.0, noise_only_frac=0.1)
+        typ = np.choose(np.arange(n) % 2, [TSC, EDGE]).astype(np.uint8)
+        args = [dev(typ), dev(tsc.astype(np.uint8)), dev(np.full(n, 4, np.int16)), 4]
+        try:
+            trx.detect_config(16, 2)
+            a = {k: v.cpu().numpy() for k, v in trx.detect_demod(dev(rx), *args).items()}
+            flat = torch.zeros((n * 625 + 3, 2), dtype=torch.float32, device="cuda")
+            for off in (1, 3):
+                view = flat[off:off + n * 625].view(n, 625, 2)
+                view.copy_(dev(rx))
+                assert (view.data_ptr() >> 3) & 1 == 1
+                b = {k: v.cpu().numpy() for k, v in trx.detect_demod(view, *args).items()}
+                for k in a:
+                    if k == "soft":
+                        # the demodulator folds the row's phase on the 16-byte grid into its tap index (another summation
+                        # order): soft values carry the 1e-4 tolerance, detection outputs are exact
+                        det = a["rc"] > 0
+                        assert np.abs(a[k][det] - b[k][det]).max() <= 1e-5 * np.abs(a[k][det]).max(), (n, off, k)
+                    else:
+                        assert np.array_equal(a[k], b[k], equal_nan=True), (n, off, k)
+        finally:
+            trx.detect_config(40, 3)
+        assert (a["rc"] > 0).sum() > 0.8 * n
+
+
 def test_detect_sch_full(trx, checker):
     """detectSCHBurst in its single-burst state (SCH_DETECT_FULL): 64-symbol sequence, 156 correlation outputs whose
     window reaches before the burst (zeros).  Decisions exact, TOA / amp per the usual criteria."""
