@@ -160,6 +160,18 @@ int trxb200_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n
 			const float *amp, const float *toa, float *ci, float *soft, int soft_stride,
 			int n_gmsk_soft);
 
+/* ---- the receive path at ONE sample per symbol (rx_sps = 1): detectAnyBurst / demodAnyBurst called with sps == 1
+ *      (sigProcLib.cpp:1659-1662: the correlator reads the burst itself, no decimation; :2038-2042: the burst delayed by
+ *      -toa and scaled by 1 / amp is the demodulator's 1-sps vector).  bursts: complex[n][stride], blen samples per
+ *      burst (a slot is 156 or 157 symbols; 148 <= blen <= 160).  Outputs as the 4-sps calls; GMSK bursts yield blen
+ *      soft values (n_gmsk_soft <= blen of them are written), 8-PSK bursts 444, and computeEdgeCI runs over blen - 16
+ *      symbols.  Outside every BASELINE configuration: built for coverage of the reference's interface, not tuned. ---- */
+int trxb200_detect_sps1_batch(trxb200_ctx *ctx, const float *bursts, int stride, int blen, int n, const uint8_t *type,
+			      const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh, int32_t *rc,
+			      float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags);
+int trxb200_demod_sps1_batch(trxb200_ctx *ctx, const float *bursts, int stride, int blen, int n, const int32_t *rc,
+			     const float *amp, const float *toa, float *ci, float *soft, int soft_stride, int n_gmsk_soft);
+
 /* ---- fused detect + demod, the Transceiver::pullRadioVector sequence (Transceiver.cpp:768,786) ---- */
 int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, const uint8_t *type,
 			       const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh,

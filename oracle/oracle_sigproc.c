@@ -687,39 +687,48 @@ void orc_vector_slicer(float *dst, const float *src, size_t len)
 	}
 }
 
-/* demodCommon :2030-2048 (sps 4) */
-static void demod_common(const ocf *burst, int blen, const orc_ebp *ebp, ocf *dec)
+/* demodCommon :2030-2048: timing recovery and one-tap channel correction; at 4 sps the result is decimated to 1 sps
+ * (156 samples), at 1 sps the delayed and scaled burst is the result (blen samples).  Returns the length of dec. */
+#define ORC_DEMOD_MAX 160
+static int demod_common(const ocf *burst, int blen, int sps, const orc_ebp *ebp, ocf *dec)
 {
 	ocf *d = (ocf *)malloc(sizeof(ocf) * blen);
-	orc_delay_vector(burst, blen, -ebp->toa * (float)4, d);
+	orc_delay_vector(burst, blen, -ebp->toa * (float)sps, d);
 	ocf one = { 1.0f, 0.0f };
 	ocf scale = cdiv(one, ebp->amp);
 	for (int i = 0; i < blen; i++)
 		d[i] = cmul(d[i], scale);
-	orc_downsample_burst(d, blen, dec);
+	int n = ORC_DEC_LEN;
+	if (sps == 1) {
+		n = blen;
+		memcpy(dec, d, sizeof(ocf) * blen);
+	} else {
+		orc_downsample_burst(d, blen, dec);
+	}
 	free(d);
+	return n;
 }
 
 /* demodGmskBurst :2055-2072 */
-static int demod_gmsk(const ocf *burst, int blen, const orc_ebp *ebp, float *soft)
+static int demod_gmsk(const ocf *burst, int blen, int sps, const orc_ebp *ebp, float *soft)
 {
-	ocf dec[ORC_DEC_LEN];
-	demod_common(burst, blen, ebp, dec);
-	for (int i = 0; i < ORC_DEC_LEN; i++)
+	ocf dec[ORC_DEMOD_MAX];
+	const int n = demod_common(burst, blen, sps, ebp, dec);
+	for (int i = 0; i < n; i++)
 		soft[i] = cmul(T.rrot1[i], dec[i]).r;
-	return ORC_DEC_LEN;
+	return n;
 }
 
 /* demodEdgeBurst :2105-2128 with derotateEdgeBurst :691-711, computeEdgeCI :2074-2093,
  * softSliceEdgeBurst :1962-2006, rotateBurst2 :582-588 */
-static int demod_edge(const ocf *burst, int blen, orc_ebp *ebp, float *soft)
+static int demod_edge(const ocf *burst, int blen, int sps, orc_ebp *ebp, float *soft)
 {
-	ocf dec[ORC_DEC_LEN], eq[ORC_DEC_LEN], rot[ORC_DEC_LEN];
-	demod_common(burst, blen, ebp, dec);
+	ocf dec[ORC_DEMOD_MAX], eq[ORC_DEMOD_MAX], rot[ORC_DEMOD_MAX];
+	const int dlen = demod_common(burst, blen, sps, ebp, dec); /* 156 at 4 sps, the burst's own length at 1 sps */
 	float h[10];
 	taps_cx(T.c0_inv, 5, h);
-	orc_convolve_sv(dec, ORC_DEC_LEN, 64, h, 5, 1, 0, 1, 0, 0, eq);
-	for (int i = 0; i < ORC_DEC_LEN; i++) {
+	orc_convolve_sv(dec, dlen, 64, h, 5, 1, 0, 1, 0, 0, eq);
+	for (int i = 0; i < dlen; i++) {
 		float phase = (float)(i % 16) * 3.0f * M_PI / 8.0f;
 		ocf r = { cosf(phase), -sinf(phase) };
 		rot[i] = cmul(eq[i], r);
@@ -727,22 +736,22 @@ static int demod_edge(const ocf *burst, int blen, orc_ebp *ebp, float *soft)
 	/* computeEdgeCI */
 	float err_pwr = 0.0f;
 	float step = 2.0f * M_PI_F / 8.0f;
-	for (int i = 8; i < ORC_DEC_LEN - 8; i++) {
+	for (int i = 8; i < dlen - 8; i++) {
 		ocf sym = rot[i];
 		float phase = step * roundf(atan2f(sym.i, sym.r) / step);
 		ocf ideal = { cosf(phase), sinf(phase) };
 		ocf err = { ideal.r - sym.r, ideal.i - sym.i };
 		err_pwr += norm2(err);
 	}
-	ebp->ci = 3.0103f * log2f(1.0f * (ORC_DEC_LEN - 16) / err_pwr);
+	ebp->ci = 3.0103f * log2f(1.0f * (dlen - 16) / err_pwr);
 	/* softSliceEdgeBurst */
 	const int nsyms = 148;
 	ocf r1 = { (float)cos(-M_PI / 8.0), (float)sin(-M_PI / 8.0) };
-	for (int i = 0; i < ORC_DEC_LEN; i++) rot[i] = cmul(rot[i], r1);
+	for (int i = 0; i < dlen; i++) rot[i] = cmul(rot[i], r1);
 	for (int i = 0; i < nsyms; i++) { soft[3 * i] = -rot[i].i; soft[3 * i + 1] = rot[i].r; }
-	for (int i = 0; i < ORC_DEC_LEN; i++) { rot[i].r = fabsf(rot[i].r); rot[i].i = fabsf(rot[i].i); }
+	for (int i = 0; i < dlen; i++) { rot[i].r = fabsf(rot[i].r); rot[i].i = fabsf(rot[i].i); }
 	ocf r2 = { (float)cos(-M_PI / 4.0), (float)sin(-M_PI / 4.0) };
-	for (int i = 0; i < ORC_DEC_LEN; i++) rot[i] = cmul(rot[i], r2);
+	for (int i = 0; i < dlen; i++) rot[i] = cmul(rot[i], r2);
 	for (int i = 0; i < nsyms; i++) soft[3 * i + 2] = -rot[i].i;
 	return nsyms * 3;
 }
@@ -751,11 +760,11 @@ static int demod_edge(const ocf *burst, int blen, orc_ebp *ebp, float *soft)
 int orc_demod_any_burst(const ocf *burst, int blen, int type, int sps, orc_ebp *ebp, float *soft)
 {
 	orc_setup();
-	if (sps != 4)
-		return -1; /* oracle restates the 4 sps path only (BASELINE configs) */
+	if ((sps != 1 && sps != 4) || (sps == 1 && (blen > ORC_DEMOD_MAX || blen < 148)))
+		return -1;
 	if (type == ORC_EDGE)
-		return demod_edge(burst, blen, ebp, soft);
-	return demod_gmsk(burst, blen, ebp, soft);
+		return demod_edge(burst, blen, sps, ebp, soft);
+	return demod_gmsk(burst, blen, sps, ebp, soft);
 }
 
 /* ---- correlation sequence generation (sigProcLib.cpp:1227-1527) ---- */

@@ -228,6 +228,24 @@ class Trx:
             "detect_demod_batch")
         return r
 
+    def detect_demod_sps1(self, bursts, type_, tsc, max_toa, max_toa_bound, thresh=BURST_THRESH, n_gmsk_soft=148,
+                          soft_stride=None, out=None):
+        """detectAnyBurst + demodAnyBurst at ONE sample per symbol (rx_sps = 1): bursts float32 [n, blen, 2] with
+        148 <= blen <= 160 (a slot is 156 or 157 symbols); results as detect_demod."""
+        _chk_dev(bursts, type_, tsc, max_toa)
+        n, blen = bursts.shape[0], bursts.shape[1]
+        r = out or self.alloc_results(n, soft_stride or n_gmsk_soft)
+        self.use_current_stream()
+        self._check(self.lib.trxb200_detect_sps1_batch(
+            self.h, _ptr(bursts), C.c_int(bursts.stride(0) // 2), C.c_int(blen), C.c_int(n), _ptr(type_), _ptr(tsc),
+            _ptr(max_toa), C.c_int(max_toa_bound), C.c_float(thresh), _ptr(r["rc"]), _ptr(r["amp"]), _ptr(r["toa"]),
+            _ptr(r["tsc"]), _ptr(r["ci"]), _ptr(r["flags"])), "detect_sps1_batch")
+        self._check(self.lib.trxb200_demod_sps1_batch(
+            self.h, _ptr(bursts), C.c_int(bursts.stride(0) // 2), C.c_int(blen), C.c_int(n), _ptr(r["rc"]), _ptr(r["amp"]),
+            _ptr(r["toa"]), _ptr(r["ci"]), _ptr(r["soft"]), C.c_int(r["soft"].stride(0)), C.c_int(n_gmsk_soft)),
+            "demod_sps1_batch")
+        return r
+
     def detect_demod_host(self, bursts, type_, tsc, max_toa, max_toa_bound, out, thresh=BURST_THRESH, n_gmsk_soft=148):
         """Same with HOST tensors (ideally pinned); copies are inside the call.  `out` from alloc_results(device='cpu')."""
         n = bursts.shape[0]

@@ -633,12 +633,13 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			 const uint8_t *type, const uint8_t *tsc, const uint16_t *max_toa, int bound, float thresh, int32_t *rc,
 			 float *amp, float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags, int scan_clip,
 			 ChunkHook *after_chunk = nullptr, bool overlapped = false, const int16_t *iq = nullptr, int iq_stride = 0,
-			 bool sch = false)
+			 bool sch = false, int sps1_len = 0)
 {
 	const trxb200_ctx::Tune &tn = ctx->tune;
 	// sch: detectSCHBurst's full search (156 correlation outputs, 64-symbol sequence), one attempt, no per-burst arrays
 	// 16-symbol sync sequences at max_toa <= 4: the register-blocked corr_nb_kernel with its fixed row lengths
-	const bool nb = !sch && nb_geometry(ctx, bound);
+	// sps1_len: bursts of that many samples at one sample per symbol - no decimator, hence the long-window correlator
+	const bool nb = !sch && !sps1_len && nb_geometry(ctx, bound);
 	const int lmax = sch ? 156 : nb ? 20 : (16 + bound + 1) & ~1;	    // row pitch of the correlation vectors (even: 16-byte row loads in peak_kernel)
 	const int ndmax = sch ? 64 + 156 - 1 : nb ? 35 : ctx->max_seq_len + 16 + bound - 1; // decimated samples a correlation window needs
 	// ---- launch geometry ----
@@ -815,6 +816,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			c.iq = iq ? iq + (size_t)lo * iq_stride * 2 : nullptr; c.iq_stride = iq_stride;
 			c.type = sch ? nullptr : type + lo; c.tsc = sch ? nullptr : tsc + lo; c.max_toa = sch ? nullptr : max_toa + lo; c.rc = rc + lo; c.round = r;
 			c.sch = sch ? 1 : 0;
+			c.sps1_len = sps1_len;
 			c.max_toa_bound = bound; c.lmax = lmax; c.ndmax = ndmax; c.corr = ws.corr; c.pwr = ws.pwr; c.negzero = -0.0f;
 			const int ngroups = (m + cgroup - 1) / cgroup;
 			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));
@@ -832,6 +834,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			q.max_toa_bound = bound; q.thresh = thresh; q.lmax = lmax; q.ndmax = ndmax; q.corr = ws.corr; q.pwr = ws.pwr;
 			q.sinc512 = ctx->d_sinc512; q.negzero = -0.0f; q.rc = rc + lo; q.amp = amp + (size_t)lo * 2; q.toa = toa + lo; q.ci = ci + lo;
 			q.tsc_out = tsc_out ? tsc_out + lo : nullptr; q.flags = flags ? flags + lo : nullptr;
+			if (sps1_len) q.dec_size = sps1_len; // computeCI's bound is the correlator input's own length (:1617)
 			const int ntiles = (m + 31) / 32;
 			const int pgrid = std::max(1, std::min((ntiles + pw - 1) / pw, ctx->sm_count * pbps));
 			prof_pre(ctx, st);
@@ -847,7 +850,8 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	}
 	if (scan_clip) {
 		prof_pre(ctx, st);
-		clip_kernel<<<std::max(1, std::min((n + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(bursts, stride, n, rc, flags, sch ? nullptr : type);
+		clip_kernel<<<std::max(1, std::min((n + 7) / 8, ctx->sm_count * 8)), 256, 0, st>>>(bursts, stride, n, rc, flags, sch ? nullptr : type,
+												      sps1_len ? sps1_len : 625);
 		prof_post(ctx, st, "clip_kernel");
 		return post_launch(ctx, "clip_kernel");
 	}
@@ -1004,6 +1008,59 @@ int trxb200_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n
 	if (n == 0) return TRXB200_OK;
 	return launch_demod(ctx, ctx->stream, bursts, stride, n, const_cast<int32_t *>(rc), amp, toa, ci, nullptr, soft,
 			    soft_stride, n_gmsk_soft, 0);
+}
+
+/* ---- the 1-sample-per-symbol receive path (rx_sps = 1): detectAnyBurst / demodAnyBurst with sps == 1 ---- */
+static int check_sps1(trxb200_ctx *ctx, const void *bursts, int stride, int blen, int n, int bound)
+{
+	if (!ctx) return TRXB200_EINVAL;
+	if (n == 0) return TRXB200_OK;
+	// a slot is 156 or 157 symbols (radioInterface.cpp:257-258 at one sample per symbol); 148 is the burst itself
+	if (!bursts || blen < 148 || blen > 160 || stride < blen || n < 0 || bound < 0 || bound > 1024)
+		return fail(ctx, TRXB200_EINVAL, "detect/demod (1 sps): bad argument");
+	return TRXB200_OK;
+}
+
+int trxb200_detect_sps1_batch(trxb200_ctx *ctx, const float *bursts, int stride, int blen, int n, const uint8_t *type,
+			      const uint8_t *tsc, const uint16_t *max_toa, int max_toa_bound, float thresh, int32_t *rc, float *amp,
+			      float *toa, uint8_t *tsc_out, float *ci, uint8_t *flags)
+{
+	DevGuard dg(ctx ? ctx->device : -1);
+	if (ctx && n == 0) return TRXB200_OK;
+	int r = check_sps1(ctx, bursts, stride, blen, n, max_toa_bound);
+	if (r) return r;
+	if (!type || !tsc || !max_toa || !rc || !amp || !toa || !tsc_out || !ci)
+		return fail(ctx, TRXB200_EINVAL, "detect (1 sps): null output");
+	return launch_detect(ctx, ctx->stream, ctx->ws, bursts, stride, n, type, tsc, max_toa, max_toa_bound, thresh, rc, amp, toa,
+			     tsc_out, ci, flags, 1, nullptr, false, nullptr, 0, false, blen);
+}
+
+int trxb200_demod_sps1_batch(trxb200_ctx *ctx, const float *bursts, int stride, int blen, int n, const int32_t *rc, const float *amp,
+			     const float *toa, float *ci, float *soft, int soft_stride, int n_gmsk_soft)
+{
+	DevGuard dg(ctx ? ctx->device : -1);
+	if (ctx && n == 0) return TRXB200_OK;
+	int r = check_sps1(ctx, bursts, stride, blen, n, 0);
+	if (r) return r;
+	if (!rc || !amp || !toa || !ci || !soft || n_gmsk_soft < 1 || n_gmsk_soft > blen || soft_stride < n_gmsk_soft)
+		return fail(ctx, TRXB200_EINVAL, "demod (1 sps): bad argument");
+	cudaStream_t st = ctx->stream;
+	// delayVector(burst, -toa * sps) (:2038) into a scratch row per burst, then scale / derotate / slice
+	float *d = nullptr;
+	CK(cudaMallocAsync(&d, (size_t)n * blen * sizeof(float2), st));
+	const long tiles = (long)n * ((blen + kCvTile - 1) / kCvTile);
+	delay_vector_blk_kernel<<<grid_for(ctx, tiles * 32, 256, 8), 256, 0, st>>>(bursts, stride, blen, n, toa, d, blen, -0.0f, -1.0f);
+	r = post_launch(ctx, "delay_vector_blk_kernel");
+	if (!r) {
+		DemodParams p = DemodParams();
+		p.bursts = d; p.stride = blen; p.n = n; p.rc = const_cast<int32_t *>(rc); p.amp = amp; p.toa = toa; p.ci = ci;
+		p.soft = soft; p.soft_stride = soft_stride; p.n_gmsk_soft = n_gmsk_soft; p.comp = ctx->d_comp;
+		p.dnsamp_g = ctx->d_comp + ctx->ht->comp.size(); p.edge_tab = ctx->d_edge_tab; p.pkt_hdr = 11; p.sps1_len = blen;
+		demod1_kernel<<<std::max(1, std::min((n + 7) / 8, ctx->sm_count * 8)), 256, 8 * kScratchFloats * sizeof(float), st>>>(p);
+		r = post_launch(ctx, "demod1_kernel");
+	}
+	cudaFreeAsync(d, st);
+	return r;
 }
 
 int trxb200_detect_demod_batch(trxb200_ctx *ctx, const float *bursts, int stride, int n, const uint8_t *type,

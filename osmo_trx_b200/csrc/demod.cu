@@ -183,9 +183,11 @@ __device__ __forceinline__ void store_soft_bytes(const DemodParams &p, int b, co
 //      1-sps samples (the shared FIR pass below produced them) ----
 // rot_lane: the lane's derotation factor edge_tab[lane & 15] (symbol i = lane + 32 r has i & 15 = lane & 15); ideal: the warp's
 // shared-memory copy of the nine ideal points - neither is fetched from global memory per burst
-__device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2 *decs, int lane, float2 rot_lane, const float2 *ideal_s)
+// size: length of the 1-sps vector (156 after the 4:1 decimator; the burst's own length, 156 or 157, on the 1-sps path):
+// computeEdgeCI walks symbols 8 .. size - 9 and divides by size - 16
+__device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2 *decs, int lane, float2 rot_lane, const float2 *ideal_s, int size = 156)
 {
-	if (lane < 2) { decs[lane] = make_float2(0.0f, 0.0f); decs[158 + lane] = make_float2(0.0f, 0.0f); }
+	if (lane < 2) { decs[lane] = make_float2(0.0f, 0.0f); decs[2 + size + lane] = make_float2(0.0f, 0.0f); }
 	__syncwarp();
 	float err = 0.0f;
 	float2 rot[5];
@@ -197,13 +199,13 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 	for (int r = 0; r < 5; r++) {
 		const int i = lane + 32 * r;
 		rot[r] = make_float2(0.0f, 0.0f);
-		if (i < 148) { // softSliceEdgeBurst consumes symbols 0..147 only, computeEdgeCI 8..147
+		if (i < max(148, size - 8)) { // softSliceEdgeBurst consumes symbols 0..147 only, computeEdgeCI 8 .. size - 9
 			// 5-tap static equaliser, NO_DELAY span (convolve_base.c:27-60)
 			float2 eq = make_float2(0.0f, 0.0f);
 #pragma unroll
 			for (int k = 0; k < 5; k++) eq = ffma2(decs[i + k], make_float2(c0[k], c0[k]), eq);
 			rot[r] = cmul_fast(eq, rot_lane); // derotateEdgeBurst :691-711
-			if (i >= 8) {
+			if (i >= 8 && i < size - 8) {
 				// computeEdgeCI :2074-2093: distance to the nearest ideal 8-PSK point.  The reference picks it as
 				// round(atan2(y, x) / (pi/4)); the octant test below picks the same point except within rounding
 				// of an octant boundary, where both neighbours are equally far.
@@ -260,7 +262,7 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 	for (int o = 16; o; o >>= 1)
 		err += __shfl_xor_sync(0xffffffffu, err, o);
 	if (lane == 0)
-		p.ci[b] = 3.0103f * __log2f(__fdividef(140.0f, err));
+		p.ci[b] = 3.0103f * __log2f(__fdividef((float)(size - 16), err));
 }
 
 } // namespace
@@ -811,6 +813,40 @@ demod_kernel(DemodParams p)
 
 		demod_one<I16>(p, W, b, rc, amp, toa, U, patch, patch_idx, bar0 + 8 * cur, (phase >> cur) & 1u, lane);
 		if (rc > 0) phase ^= 1u << cur;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// demod1_kernel — demodAnyBurst at ONE sample per symbol (rx_sps = 1, sigProcLib.cpp:2030-2048 with sps == 1): the burst
+// delayed by -toa (delay_vector_blk_kernel, the exact two-stage delayVector) is the 1-sps vector; what is left is the
+// scaling by 1 / amp, GMSKReverseRotate + real part, or the 8-PSK tail shared with demod_kernel.  Outside every BASELINE
+// configuration (those run at 4 sps): written for coverage, one warp per burst, not tuned.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+demod1_kernel(DemodParams p)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+	float *ostage = reinterpret_cast<float *>(smem_raw) + (size_t)warp * kScratchFloats;
+	const DemodWarp W = demod_warp_setup(p, ostage, lane);
+	const int len = p.sps1_len;
+	for (int b = blockIdx.x * wpb + warp; b < p.n; b += gridDim.x * wpb) {
+		const int rc = p.rc[b];
+		if (rc <= 0) continue;
+		const float2 amp = reinterpret_cast<const float2 *>(p.amp)[b];
+		const float ian = __frcp_rn(norm2(amp));
+		const float2 s = make_float2(amp.x * ian, -amp.y * ian);
+		const float2 *row = reinterpret_cast<const float2 *>(p.bursts) + (size_t)b * p.stride;
+		if (rc == 5) {
+			for (int i = lane; i < len; i += 32) W.decs[2 + i] = cscale(row[i], s);
+			__syncwarp();
+			demod_edge_tail(p, b, W.decs, lane, W.rot_lane, W.ideal, len);
+			__syncwarp();
+		} else {
+			const int nout = min(p.n_gmsk_soft, len);
+			float *orow = p.soft + (size_t)b * p.soft_stride;
+			for (int i = lane; i < nout; i += 32) orow[i] = soft_out(i, row[i], s);
+		}
 	}
 }
 

@@ -604,7 +604,8 @@ corr_long_kernel(CorrParams p)
 
 	int b = blockIdx.x * wpb + warp;
 	int2 pk0 = plan(load_scal(b));
-	if (b < p.n) issue_copies(b, pk0.x, 0);
+	const bool sps1 = p.sps1_len > 0;
+	if (b < p.n && !sps1) issue_copies(b, pk0.x, 0);
 	Scal s1 = load_scal(b + step);
 	int cur = 0;
 	for (; b < p.n; b += step, cur ^= 1) {
@@ -613,14 +614,25 @@ corr_long_kernel(CorrParams p)
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncwarp();
 		// the other buffer was consumed by the previous burst's decimation: refill it with the next window
-		if (b + step < p.n) issue_copies(b + step, pk1.x, cur ^ 1);
+		if (b + step < p.n && !sps1) issue_copies(b + step, pk1.x, cur ^ 1);
 		if (pk_active(pk0.x)) {
 			const int hlen = pk_hlen(pk0.x), len = pk_len(pk0.x);
 			const int nd = hlen + len - 1;
 			const int dstart = pk_start(pk0.x) - (hlen - 1);
 			const float4 *raw = raw0 + (size_t)cur * 8 * PP;
+			if (sps1) {
+				// one sample per symbol: the "decimated" burst is the burst (zeros outside it: convolve()'s head-room, :312-334)
+				const float2 *x = xall + (size_t)b * (size_t)p.stride;
+				float *pw = p.pwr + (size_t)b * ndmax;
+				for (int j = lane; j < nd; j += 32) {
+					const int d = dstart + j;
+					const float2 y = (d >= 0 && d < p.sps1_len) ? __ldg(&x[d]) : make_float2(0.0f, 0.0f);
+					dec[j] = y;
+					pw[j] = norm2(y);
+				}
+			}
 			// ---- decimation (sse_conv_real16 order, convolve_sse_3.c:188-264): 4 outputs per item ----
-			for (int a = lane; 4 * a < nd; a += 32) {
+			for (int a = lane; !sps1 && 4 * a < nd; a += 32) {
 				float4 s[14];
 #pragma unroll
 				for (int q = 0; q < 14; q++) s[q] = raw[(q & 7) * PP + a + (q >> 3)];
@@ -957,7 +969,7 @@ peak_kernel(PeakParams p)
 // OFF, SCH and unknown types return 0 without a clipping check (:1949-1956).  type == nullptr: every burst is checked.
 // One warp per burst.
 __global__ void __launch_bounds__(256)
-clip_kernel(const float *bursts, int stride, int n, int32_t *rc, uint8_t *flags, const uint8_t *type)
+clip_kernel(const float *bursts, int stride, int n, int32_t *rc, uint8_t *flags, const uint8_t *type, int len = 625)
 {
 	const int lane = threadIdx.x & 31;
 	const int wpb = blockDim.x >> 5;
@@ -966,7 +978,7 @@ clip_kernel(const float *bursts, int stride, int n, int32_t *rc, uint8_t *flags,
 		if (type && !type_known(load_type(type, b, 0))) continue;
 		const float2 *x = reinterpret_cast<const float2 *>(bursts) + (size_t)b * stride;
 		float mx = 0.0f;
-		for (int i = lane; i < 625; i += 32) {
+		for (int i = lane; i < len; i += 32) {
 			const float2 v = __ldg(&x[i]);
 			mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
 		}

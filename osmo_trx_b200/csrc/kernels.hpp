@@ -23,6 +23,8 @@ struct CorrParams {
 	const int16_t *iq; // [n][iq_stride] complex int16, or null
 	int iq_stride;
 	int sch;	   // every burst is a SCH_DETECT_FULL search (type / tsc / max_toa are not read)
+	int sps1_len = 0;  // > 0: the rows are bursts of this many samples at ONE sample per symbol - no decimation, the correlator reads
+			   // the burst itself (detectBurst, sigProcLib.cpp:1659-1662); corr_long_kernel only
 };
 
 struct PeakParams {
@@ -65,6 +67,7 @@ struct DemodParams {
 	float *pw;		 // [n][80] |x[4i]|^2, the terms of energyDetect(slot, 80); summed in order by header_kernel
 	uint8_t *pkt;		 // [n][pkt_stride] TRXD datagram rows: the soft bytes are written here (header_kernel adds the header)
 	int pkt_stride, pkt_hdr, pkt_v0; // header length (8 / 11), v0 = two trailing zero bytes
+	int sps1_len = 0; // demod1_kernel: `bursts` holds the delayed bursts of this many samples at one sample per symbol
 };
 
 // receive chain around the hot path (pull.cu)

@@ -66,10 +66,10 @@ vector_slicer_kernel(float *dst, const float *src, size_t len, int vec)
 // sse_conv_real20 order (NO_DELAY span: zero padding both sides), then integer shift with zero fill.
 __global__ void __launch_bounds__(256)
 delay_vector_kernel(const float *__restrict__ in, int stride, int len, int n, const float *__restrict__ delay,
-		    float *__restrict__ out, int out_stride)
+		    float *__restrict__ out, int out_stride, float delay_scale = 1.0f)
 {
 	for (int b = blockIdx.x; b < n; b += gridDim.x) {
-		const float dly = delay[b];
+		const float dly = fm(delay[b], delay_scale); // (1.0 or -1.0 / -sps: exact)
 		const int whole = (int)floorf(dly);
 		const float frac = fs(dly, (float)whole);
 		const bool use_f = (double)fabsf(frac) > 1e-2;
@@ -113,7 +113,7 @@ delay_vector_kernel(const float *__restrict__ in, int stride, int len, int n, co
 // burst's 20 taps read warp-uniformly from __constant__.  The integer shift only moves the window.
 __global__ void __launch_bounds__(256)
 delay_vector_blk_kernel(const float *__restrict__ in, int stride, int len, int n, const float *__restrict__ delay,
-			float *__restrict__ out, int out_stride, float negzero)
+			float *__restrict__ out, int out_stride, float negzero, float delay_scale = 1.0f)
 {
 	constexpr int NW = kCvTile + 19, KL = (NW + 31) / 32;
 	__shared__ __align__(16) float2 win_all[8][4 * kCvPitch];
@@ -126,7 +126,7 @@ delay_vector_blk_kernel(const float *__restrict__ in, int stride, int len, int n
 	int whole_n = 0, f_n = -1;
 	auto fetch = [&](int t_) {
 		const int b_ = t_ / tpr, i0_ = (t_ - b_ * tpr) * kCvTile;
-		const float dly = delay[b_];
+		const float dly = fm(delay[b_], delay_scale); // (1.0 or -1.0 / -sps: exact)
 		whole_n = (int)floorf(dly);
 		const float frac = fs(dly, (float)whole_n);
 		f_n = -1;

@@ -25,7 +25,7 @@ static void wr(FILE *f, const void *p, size_t n) { fwrite(p, 1, n, f); }
 
 int main(int argc, char **argv)
 {
-	if (argc != 4) { fprintf(stderr, "usage: host_demo dd|sch|acq|mod|conv|vit in out\n"); return 2; }
+	if (argc != 4) { fprintf(stderr, "usage: host_demo dd|dd1|sch|acq|mod|conv|vit in out\n"); return 2; }
 	const std::string mode = argv[1];
 	FILE *fi = fopen(argv[2], "rb"), *fo = fopen(argv[3], "wb");
 	if (!fi || !fo) { perror("open"); return 2; }
@@ -33,19 +33,22 @@ int main(int argc, char **argv)
 	initvita();
 	int32_t n = 0;
 	if (!rd(fi, &n, 4)) return 2;
-	if (mode == "dd") {
+	if (mode == "dd" || mode == "dd1") {
+		// dd: 625-sample bursts at 4 samples per symbol; dd1: a fourth header word gives the length of a burst at ONE sample per symbol
+		const int sps = mode == "dd1" ? 1 : 4;
 		for (int k = 0; k < n; k++) {
-			int32_t hdr[3];
-			signalVector burst(625);
-			if (!rd(fi, hdr, 12) || !rd(fi, burst.begin(), 625 * 8)) return 2;
+			int32_t hdr[4] = { 0, 0, 0, 625 };
+			if (!rd(fi, hdr, sps == 1 ? 16 : 12) || hdr[3] < 1 || hdr[3] > 625) return 2;
+			signalVector burst(hdr[3]);
+			if (!rd(fi, burst.begin(), (size_t)hdr[3] * 8)) return 2;
 			estim_burst_params ebp;
 			ebp = estim_burst_params{ complex(0, 0), 0.0f, 0, 0.0f };
-			const int rc = detectAnyBurst(burst, (unsigned)hdr[1], BURST_THRESH, 4, (CorrType)hdr[0], (unsigned)hdr[2], &ebp);
+			const int rc = detectAnyBurst(burst, (unsigned)hdr[1], BURST_THRESH, sps, (CorrType)hdr[0], (unsigned)hdr[2], &ebp);
 			float rec[6] = { (float)rc, ebp.amp.real(), ebp.amp.imag(), ebp.toa, (float)ebp.tsc, ebp.ci };
 			std::vector<float> soft(444, 0.0f);
 			int32_t nsoft = 0;
 			if (rc > 0) {
-				std::unique_ptr<SoftVector> sv(demodAnyBurst(burst, (CorrType)rc, 4, &ebp));
+				std::unique_ptr<SoftVector> sv(demodAnyBurst(burst, (CorrType)rc, sps, &ebp));
 				if (!sv) return 4;
 				nsoft = (int32_t)sv->size();
 				memcpy(soft.data(), sv->begin(), sv->size() * 4);

@@ -296,7 +296,10 @@ int detectAnyBurst(const signalVector &burst, unsigned tsc, float threshold, int
 		   struct estim_burst_params *ebp)
 {
 	if (!ebp) return -SIGERR_INTERNAL;
-	if (sps != 4) return -SIGERR_UNSUPPORTED; // sigProcLib.cpp:1740 allows 1 or 4; the GPU path is built for 4 sps
+	if (sps != 4 && sps != 1) return -SIGERR_UNSUPPORTED; // sigProcLib.cpp:1740
+	// one sample per symbol: the vector is one slot (156 / 157 symbols, radioInterface.cpp:257-258); other lengths are refused
+	const int blen1 = (int)burst.size();
+	if (sps == 1 && (blen1 < 148 || blen1 > 160)) return -SIGERR_UNSUPPORTED;
 	std::lock_guard<std::mutex> lk(g_mu);
 	if (!g_ctx) return -SIGERR_INTERNAL;
 	float *db = upload_burst(burst, d_in);
@@ -312,8 +315,10 @@ int detectAnyBurst(const signalVector &burst, unsigned tsc, float threshold, int
 	if (!ok(trxb200_copy_to_device(g_ctx, dt, par, 16), "copy")) return -SIGERR_INTERNAL;
 	int32_t *drc = (int32_t *)dres;
 	float *damp = dres + 2, *dtoa = dres + 4, *dci = dres + 5;
-	const int rc = trxb200_detect_batch(g_ctx, db, 625, 1, dt, dt + 1, (const uint16_t *)(dt + 2), mt > 1024 ? 1024 : mt, threshold, drc,
-					    damp, dtoa, dt + 8, dci, dt + 9);
+	const int rc = sps == 1 ? trxb200_detect_sps1_batch(g_ctx, db, 625, blen1, 1, dt, dt + 1, (const uint16_t *)(dt + 2), mt > 1024 ? 1024 : mt,
+							    threshold, drc, damp, dtoa, dt + 8, dci, dt + 9)
+				: trxb200_detect_batch(g_ctx, db, 625, 1, dt, dt + 1, (const uint16_t *)(dt + 2), mt > 1024 ? 1024 : mt, threshold, drc,
+						       damp, dtoa, dt + 8, dci, dt + 9);
 	if (!ok(rc, "detect_batch")) return -SIGERR_INTERNAL;
 	float hres[8];
 	uint8_t hpar[16];
@@ -364,12 +369,14 @@ int detectSCHBurst(signalVector &burst, float threshold, int sps, sch_detect_typ
 
 SoftVector *demodAnyBurst(const signalVector &burst, CorrType type, int sps, struct estim_burst_params *ebp)
 {
-	if (!ebp || sps != 4) return nullptr;
+	if (!ebp || (sps != 4 && sps != 1)) return nullptr;
+	const int blen1 = (int)burst.size();
+	if (sps == 1 && (blen1 < 148 || blen1 > 160)) return nullptr;
 	std::lock_guard<std::mutex> lk(g_mu);
 	if (!g_ctx) return nullptr;
 	float *db = upload_burst(burst, d_in);
 	float *dpar = (float *)d_b.get(64);
-	const int nsoft = type == EDGE ? 444 : 156;
+	const int nsoft = type == EDGE ? 444 : (sps == 1 ? blen1 : 156); // demodGmskBurst returns the 1-sps vector's length
 	float *dsoft = (float *)d_out.get((size_t)nsoft * 4);
 	if (!db || !dpar || !dsoft) return nullptr;
 	float hpar[8] = { 0 };
@@ -380,7 +387,11 @@ SoftVector *demodAnyBurst(const signalVector &burst, CorrType type, int sps, str
 	hpar[4] = ebp->toa;
 	hpar[5] = ebp->ci;
 	if (!ok(trxb200_copy_to_device(g_ctx, dpar, hpar, 32), "copy")) return nullptr;
-	if (!ok(trxb200_demod_batch(g_ctx, db, 625, 1, (const int32_t *)dpar, dpar + 2, dpar + 4, dpar + 5, dsoft, nsoft, 156), "demod_batch"))
+	if (sps == 1) {
+		if (!ok(trxb200_demod_sps1_batch(g_ctx, db, 625, blen1, 1, (const int32_t *)dpar, dpar + 2, dpar + 4, dpar + 5, dsoft, nsoft, blen1),
+			"demod_sps1_batch"))
+			return nullptr;
+	} else if (!ok(trxb200_demod_batch(g_ctx, db, 625, 1, (const int32_t *)dpar, dpar + 2, dpar + 4, dpar + 5, dsoft, nsoft, 156), "demod_batch"))
 		return nullptr;
 	SoftVector *out = new SoftVector(nsoft);
 	if (!ok(trxb200_copy_to_host(g_ctx, out->begin(), dsoft, (size_t)nsoft * 4), "copy")) { delete out; return nullptr; }

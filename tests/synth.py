@@ -85,12 +85,12 @@ def frac_shift(wave, shift):
 
 def impair(wave, rng, snr_db=30.0, amp_range=(0.1, 1.0), full_scale=1.0, shift_lo=-26.0, shift_hi=-9.0,
            noise_only_frac=0.0):
-    """wave: float32 [n,625,2] clean TX bursts -> float32 [n,625,2] received bursts.
+    """wave: float32 [n,L,2] clean TX bursts (L = 625 at 4 sps, 156 / 157 at 1 sps) -> float32 [n,L,2] received bursts.
 
     shift ~ U[shift_lo, shift_hi) samples (the modulator output peaks ~18.5 samples late),
     gain A e^{j phi}, A ~ U[amp_range]*full_scale, AWGN at `snr_db` relative to the burst's mean power.
     """
-    n = wave.shape[0]
+    n, L = wave.shape[0], wave.shape[1]
     w = wave[..., 0].astype(np.float64) + 1j * wave[..., 1].astype(np.float64)
     shift = rng.uniform(shift_lo, shift_hi, n)
     y = frac_shift(w, shift)
@@ -99,12 +99,12 @@ def impair(wave, rng, snr_db=30.0, amp_range=(0.1, 1.0), full_scale=1.0, shift_l
     y = y * (A * np.exp(1j * phi))[:, None]
     snr = np.broadcast_to(np.asarray(snr_db, np.float64), (n,))
     sigma = A * 10.0 ** (-snr / 20.0) / np.sqrt(2.0)
-    noise = (rng.standard_normal((n, 625)) + 1j * rng.standard_normal((n, 625))) * sigma[:, None]
+    noise = (rng.standard_normal((n, L)) + 1j * rng.standard_normal((n, L))) * sigma[:, None]
     if noise_only_frac > 0:
         kill = rng.uniform(0, 1, n) < noise_only_frac
         y[kill] = 0
     y = y + noise
-    out = np.empty((n, 625, 2), np.float32)
+    out = np.empty((n, L, 2), np.float32)
     out[..., 0] = y.real
     out[..., 1] = y.imag
     return out, shift
@@ -134,3 +134,25 @@ def sch_bits(n, rng):
     bits[:, 42:106] = [int(c) for c in SCH_SYNC_STR]
     bits[:, 106:145] = rng.integers(0, 2, (n, 39))
     return bits
+
+
+def sps1_bursts(mod, n, rng, blen=157, edge_every=0, snr_db=20.0, noise_only_frac=0.05):
+    """Received bursts at ONE sample per symbol (the reference's rx_sps = 1 path): `mod` is a checker whose
+    modulate_burst(bits, guard, sps=1) is the reference's 1-sps modulator (modulateBurstBasic, sigProcLib.cpp:938-968).
+    Normal bursts with TSC b % 8; every `edge_every`-th burst 8-PSK (rotateEdgeBurst at 1 sps, no pulse shaping: the
+    reference itself notes that 8-PSK is nearly unrecoverable at 1 sps - the point is equal arithmetic, not sensitivity).
+    Returns (rx [n, blen, 2], tsc [n], is_edge [n])."""
+    tsc = (np.arange(n) % 8).astype(np.uint8)
+    bits = nb_bits(n, tsc, rng)
+    ebits = edge_bits(n, tsc, rng)
+    tx = np.zeros((n, blen, 2), np.float32)
+    is_edge = np.zeros(n, bool)
+    for b in range(n):
+        if edge_every and b % edge_every == edge_every - 1:
+            w = mod.modulate_edge(ebits[b], sps=1, empty=True)
+            is_edge[b] = True
+        else:
+            w = mod.modulate_burst(bits[b], guard=blen - 148, sps=1)
+        tx[b, :min(blen, len(w))] = w[:blen]
+    rx, _ = impair(tx, rng, snr_db=snr_db, shift_lo=-2.0, shift_hi=1.5, noise_only_frac=noise_only_frac)
+    return rx, tsc, is_edge

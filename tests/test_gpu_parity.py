@@ -713,6 +713,34 @@ def test_detect_rows_off_the_16_byte_grid(trx):
         assert (a["rc"] > 0).sum() > 0.8 * n
 
 
+@pytest.mark.parametrize("blen", [157, 156])
+def test_one_sample_per_symbol(trx, checker, blen):
+    """The rx_sps = 1 path (detectAnyBurst / demodAnyBurst with sps = 1, sigProcLib.cpp:1659-1662, 2038-2042): normal,
+    8-PSK (with its TSC fall-through), access and idle slots of 156 / 157 symbols; decisions exact, TOA / amp / soft bits
+    per the usual criteria; computeEdgeCI over blen - 16 symbols."""
+    rng = np.random.default_rng(80 + blen)
+    n = 3000
+    rx, tsc, is_edge = synth.sps1_bursts(checker, n, rng, blen=blen, edge_every=4, snr_db=np.choose(np.arange(n) % 3, [25.0, 12.0, 7.0]))
+    typ = np.where(is_edge, EDGE, TSC).astype(np.uint8)
+    typ[::7] = np.choose(np.arange(len(typ[::7])) % 3, [IDLE, RACH, EXT_RACH])
+    typ[5::50] = 0
+    k = len(rx[11::100])  # slots that clip and hold no burst: -SIGERR_CLIP
+    rx[11::100] = (rng.standard_normal((k, blen, 2)) * 9000.0).astype(np.float32)
+    rx[11::100, 60, 0] = 31000.0
+    mt = np.choose(np.arange(n) % 3, [4, 0, 9]).astype(np.int16)
+    c = checker.detect_demod(rx, typ, tsc, mt.astype(np.uint16), sps=1, blen=blen, nthreads=8)
+    r = trx.detect_demod_sps1(dev(rx), dev(typ), dev(tsc), dev(mt), 9, n_gmsk_soft=blen, soft_stride=444)
+    torch.cuda.synchronize()
+    g = {k: v.cpu().numpy() for k, v in r.items()}
+    rep = parity.compare_detect(g, c, g["flags"], f"sps1/{blen}")
+    ok = rep["ok_mask"]
+    parity.compare_ci(g["ci"], c["ci"], ok, f"sps1/{blen}")
+    parity.compare_soft(g["soft"], c["soft"], ok & (c["rc"] != EDGE), blen, f"sps1/{blen} gmsk")
+    parity.compare_soft(g["soft"], c["soft"], ok & (c["rc"] == EDGE), 444, f"sps1/{blen} edge")
+    assert (c["rc"] == TSC).sum() > 1200 and (c["rc"] == EDGE).sum() > 100 and (c["rc"] == -2).sum() > 5 and (c["rc"] == 0).sum() > 50
+    print(f"sps1/{blen}", {k: v for k, v in rep.items() if k not in ("ok_mask", "_ga")}, np.bincount(c["rc"] + 4))
+
+
 def test_detect_sch_full(trx, checker):
     """detectSCHBurst in its single-burst state (SCH_DETECT_FULL): 64-symbol sequence, 156 correlation outputs whose
     window reaches before the burst (zeros).  Decisions exact, TOA / amp per the usual criteria."""

@@ -128,6 +128,30 @@ def test_mirror_modulate_detect_demod(host_build, checker, tmp_path):
 
 
 @pytest.mark.gpu
+def test_mirror_detect_demod_one_sample_per_symbol(host_build, checker, tmp_path):
+    """detectAnyBurst / demodAnyBurst called with sps = 1 (rx_sps = 1) through the C++ mirror, against the reference."""
+    rng = np.random.default_rng(79)
+    n, blen = 120, 157
+    rx, tsc, is_edge = synth.sps1_bursts(checker, n, rng, blen=blen, edge_every=5)
+    typ = np.where(is_edge, EDGE, TSC).astype(np.uint8)
+    mt = np.full(n, 4, np.uint16)
+    pay = struct.pack("<i", n)
+    for k in range(n):
+        pay += struct.pack("<iiii", int(typ[k]), int(tsc[k]), int(mt[k]), blen) + rx[k].tobytes()
+    rec = np.frombuffer(_run(host_build, "dd1", pay, tmp_path), np.float32).reshape(n, 6 + 1 + 444)
+    g = dict(rc=rec[:, 0].astype(np.int32), amp=rec[:, 1:3].copy(), toa=rec[:, 3].copy(), tsc=rec[:, 4].astype(np.uint8),
+             ci=rec[:, 5].copy(), soft=rec[:, 7:].copy())
+    c = checker.detect_demod(rx, typ, tsc, mt, sps=1, blen=blen)
+    rep = parity.compare_detect(g, c, None, "host mirror 1 sps")
+    ok = rep["ok_mask"]
+    parity.compare_soft(g["soft"], c["soft"], ok & (c["rc"] != EDGE), blen, "host mirror 1 sps gmsk")
+    parity.compare_soft(g["soft"], c["soft"], ok & (c["rc"] == EDGE), 444, "host mirror 1 sps edge")
+    nsoft = rec[:, 6].view(np.int32)
+    assert (nsoft[c["rc"] == EDGE] == 444).all() and (nsoft[(c["rc"] > 0) & (c["rc"] != EDGE)] == blen).all()
+    assert rep["detected"] > 0.7 * n
+
+
+@pytest.mark.gpu
 def test_mirror_convolve_golden(host_build, tmp_path):
     """The reference's own KAT (tests/Transceiver52M/convolve_test_golden.h) through the C symbols of convolve.h."""
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "convolve_golden.npz"))

@@ -125,6 +125,22 @@ def test_oracle_vs_reference_live(oracle, ref):
         assert eqb(a[k], b[k]), k
 
 
+def test_oracle_sps1_vs_reference_live(oracle, ref):
+    """The 1-sample-per-symbol receive path (sigProcLib.cpp:1659-1662 no decimation before the correlator, :2041-2042 the
+    delayed burst is the demodulator's 1-sps vector): oracle against the compiled reference, every output bit for bit."""
+    rng = np.random.default_rng(78)
+    for blen in (157, 156):
+        rx, tsc, is_edge = synth.sps1_bursts(ref, 600, rng, blen=blen, edge_every=4)
+        typ = np.where(is_edge, EDGE, TSC).astype(np.uint8)
+        typ[::7] = np.choose(np.arange(len(typ[::7])) % 3, [IDLE, RACH, EXT_RACH])
+        mt = np.choose(np.arange(600) % 3, [4, 0, 9]).astype(np.uint16)
+        a = oracle.detect_demod(rx, typ, tsc, mt, sps=1, blen=blen, nthreads=4)
+        b = ref.detect_demod(rx, typ, tsc, mt, sps=1, blen=blen, nthreads=4)
+        for k in ("rc", "amp", "toa", "tsc", "ci", "soft", "nsoft"):
+            assert eqb(a[k], b[k]), (blen, k)
+        assert (b["rc"] == TSC).sum() > 300 and (b["rc"] == EDGE).sum() > 20 and (b["rc"] == 0).sum() > 10, np.bincount(b["rc"] + 4)
+
+
 def _pull_same(a, b, version):
     for k in ("rc", "energy", "pkt_len", "amp", "toa", "ci", "tsc"):
         assert eqb(a[k], b[k]), k
