@@ -170,7 +170,7 @@ signalVector *modulateEdgeBurst(const BitVector &bits, int sps, bool emptyPulse)
 
 signalVector *genRandNormalBurst(int tsc, int sps, int tn)
 {
-	if (tsc < 0 || tsc > 7 || tn < 0 || tn > 7 || sps != 4) return nullptr;
+	if (tsc < 0 || tsc > 7 || tn < 0 || tn > 7 || (sps != 1 && sps != 4)) return nullptr; // :772
 	BitVector bits(148); // 3 tail, 57 data, stealing, 26 TSC, stealing, 57 data, 3 tail
 	for (int i = 3; i < 60; i++) bits[i] = (char)(rand() % 2);
 	for (int i = 0; i < 26; i++) bits[61 + i] = (char)(kTsc[tsc][i] == '1');
@@ -180,7 +180,7 @@ signalVector *genRandNormalBurst(int tsc, int sps, int tn)
 
 signalVector *genRandAccessBurst(int delay, int sps, int tn)
 {
-	if (tn < 0 || tn > 7 || sps != 4 || delay < 0 || delay > 68) return nullptr;
+	if (tn < 0 || tn > 7 || (sps != 1 && sps != 4) || delay < 0 || delay > 68) return nullptr; // :815
 	BitVector bits(88 + delay); // delay zeros, 49 head+sync bits, 36 random, 3 tail
 	for (int i = 0; i < 49; i++) bits[delay + i] = (char)(kRachBurst[i] == '1');
 	for (int i = 49; i < 85; i++) bits[delay + i] = (char)(rand() % 2);
@@ -189,7 +189,7 @@ signalVector *genRandAccessBurst(int delay, int sps, int tn)
 
 signalVector *generateDummyBurst(int sps, int tn)
 {
-	if (sps != 4 || tn < 0 || tn > 7) return nullptr;
+	if ((sps != 1 && sps != 4) || tn < 0 || tn > 7) return nullptr; // :858
 	return modulateBurst(BitVector(kDummyBurst), 8 + !(tn % 4), sps);
 }
 

@@ -377,7 +377,8 @@ def test_mirror_objects_and_helpers(host_build, checker, tmp_path):
     ops.append(struct.pack("<5i", 10, 1250, 2, 0, 0) + struct.pack("<f", 0.0) + i16.tobytes())
     checks.append(("convert-back", checker.convert_short_float(i16), None))
     # filler bursts: normal (tsc 5, tn 0 and 3), access (delay 11), EDGE (tsc 2), dummy, empty
-    gens = [(0, 5, 0, 4), (0, 2, 3, 4), (1, 11, 1, 4), (2, 2, 0, 4), (3, 0, 0, 4), (4, 0, 2, 4), (4, 0, 0, 1), (0, 9, 0, 4)]
+    gens = [(0, 5, 0, 4), (0, 2, 3, 4), (1, 11, 1, 4), (2, 2, 0, 4), (3, 0, 0, 4), (4, 0, 2, 4), (4, 0, 0, 1), (0, 9, 0, 4),
+            (0, 6, 0, 1), (3, 0, 1, 1), (1, 5, 2, 1)]  # the same generators at one sample per symbol
     for kind, arg, tn, sps in gens:
         ops.append(struct.pack("<5i", 8, kind, arg, tn, sps))
     out = _run(host_build, "misc", struct.pack("<i", len(ops)) + b"".join(ops), tmp_path)
@@ -434,3 +435,10 @@ def test_mirror_objects_and_helpers(host_build, checker, tmp_path):
     assert bursts[5].shape == (625, 2) and not bursts[5].any()
     assert bursts[6].shape == (148 + 8 + 1, 2) and not bursts[6].any()  # tn % 4 == 0: one more guard symbol
     assert bursts[7] is None  # tsc 9
+    # one sample per symbol (modulateBurstBasic): 157 / 156 symbols, received by the reference's own 1-sps path
+    assert bursts[8].shape == (157, 2) and bursts[9].shape == (156, 2) and bursts[10].shape == (156, 2)
+    r = checker.detect_demod(bursts[8][None], TSC, 6, 4, sps=1, blen=157)
+    assert r["rc"][0] == TSC and list((r["soft"][0, 61:87] > 0).astype(int)) == TSCS[6]
+    assert np.array_equal(bursts[9], checker.modulate_burst(np.array([int(ch) for ch in synth.DUMMY_STR], np.uint8), guard=8, sps=1))
+    r = checker.detect_demod(bursts[10][None], RACH, 0, 63, sps=1, blen=156)
+    assert r["rc"][0] == RACH and abs(r["toa"][0] - 5) < 3
