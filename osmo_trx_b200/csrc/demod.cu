@@ -10,7 +10,7 @@
 // burst.  Where the reference's intermediate vectors are truncated (samples shifted in from outside
 // the 625-sample burst are zero, the decimator's history before sample 0 is zero) the affected
 // leading outputs use the composite truncated to the surviving decimator taps (comp[f][kmin]); outputs
-// truncated from above take a generic two-stage path.  This chain feeds no decisions, so FMA is used.
+// truncated from above get the dropped terms subtracted.  This chain feeds no decisions, so FMA is used.
 //
 // The FIR runs on the RAW complex samples with Blackwell's packed FP32 pipe: one FFMA2
 // (fma.rn.f32x2) advances the (re,im) pair of an output by one real tap, so the complex sum costs the
@@ -34,9 +34,10 @@
 //           the 13 outputs 5l-8..5l+4 it can reach (180 FFMA2 with the tap as scalar-broadcast operand,
 //           taps fetched warp-uniformly from __constant__ comp0[f][e]); the 8 partial sums that belong to
 //           lanes l-1 and l-2 are handed over with shuffles once per burst.
-//   edges   the few leading outputs whose decimator taps are truncated get the dropped terms subtracted:
-//           the (at most 31) delayed samples Y[v] those taps would have read are evaluated one per lane
-//           (20-tap fractional filter from __constant__), then 4 lanes per output sum g[k]*Y[4i+k], k < kmin.
+//   edges   the few leading outputs whose decimator taps are truncated are evaluated again, directly, with the composite
+//           truncated to the surviving taps (comp[f][kmin], global memory / L2): 4 lanes per output, 9 taps each.  Trailing
+//           outputs of very late bursts get the dropped terms subtracted instead: the (at most 16) delayed samples those
+//           taps would have read are evaluated one per lane (20-tap fractional filter from __constant__).
 //   store   outputs are staged in shared memory and written with 16-byte coalesced stores.
 #include "device_tables.cuh"
 #include "kernels.hpp"
@@ -139,20 +140,6 @@ __device__ __forceinline__ float soft_out(int i, float2 a, float2 s)
 {
 	const float v = (i & 1) ? fmaf(a.x, s.y, a.y * s.x) : fmaf(a.x, s.x, -a.y * s.y);
 	return (i & 2) ? -v : v;
-}
-
-// one output with a (possibly truncated) composite: kmin..15 decimator taps present, 35 composite taps
-template <bool I16>
-__device__ __forceinline__ float2 comp_output(const DemodParams &p, const float2 *U, int i, int e, int f, int kmin)
-{
-	const float *__restrict__ c = p.comp + ((size_t)f * 16 + kmin) * 36;
-	float2 d = make_float2(0.0f, 0.0f);
-#pragma unroll 5
-	for (int t = 0; t < 35; t++) {
-		const float ct = __ldg(&c[t]);
-		d = ffma2(win_get<I16>(U, 4 * i + t + e), make_float2(ct, ct), d);
-	}
-	return d;
 }
 
 // soft values staged in shared memory -> the datagram's soft bytes (vectorSlicer + trxd_fill_burst_normalized255), written
@@ -602,76 +589,58 @@ __device__ __forceinline__ void demod_one(const DemodParams &p, const DemodWarp 
 	// (history / samples shifted in from below), trailing ones taps k > kmax (the delayed vector ends at sample
 	// 624 before the shift: delayed samples q >= q0 = 640 + whole never reach the decimator).
 	const int nlead = min(nout, (max(15, 15 + whole) + 3) >> 2);
-	const int nv = 15 + max(0, whole); // delayed samples Y[v], v < nv, are what the dropped leading taps would read
 	const int q0 = 640 + whole;
 	const bool top_trunc = q0 <= 4 * (nout - 1) + 15;
 	__syncwarp();
-	if (nv <= 32 || top_trunc) {
-		// Y[v] = sum_j win(v + e + j) * delay[f][j]: the delayed sample decimator tap k of output i reads, v = 4i + k.
-		// Lanes evaluate v = lane (leading edge); lanes 0..15 also v = q0 + lane (trailing edge).
-		const int q0c = min(max(q0, 0), 644);
-		float2 y = make_float2(0.0f, 0.0f), yt = make_float2(0.0f, 0.0f);
-		// int16 rows: the 52 window samples the leading Y values share are converted once (two per lane)
-		const float2 *uy = U + e;
-		if constexpr (I16) {
-			if (lane < 28) {
-				const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned *>(U) + (e & 2) + 2 * lane);
-				const float2 a = cvt_s2(v.x), c = cvt_s2(v.y);
-				reinterpret_cast<float4 *>(yx)[lane] = make_float4(a.x, a.y, c.x, c.y);
-			}
-			__syncwarp();
-			uy = yx + (e & 1);
-		}
-		if (f < 64) {
+	// ---- leading outputs: evaluated again, directly, with the composite truncated to the surviving decimator taps
+	//      (comp[f][kmin], built on the host): 4 lanes per output, 9 taps each.  (The first form of this correction
+	//      evaluated the delayed samples the dropped taps would have read - 20 taps on every lane - and subtracted their
+	//      contribution: 110 of the kernel's 560 instructions per burst for four or five outputs.) ----
+	for (int base = 0; base < nlead; base += 8) {
+		const int i = base + (lane >> 2), part = lane & 3;
+		const int kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
+		const int kmax = min(15, 639 + whole - 4 * i);
+		const bool direct = i < nlead && kmin <= kmax && kmax == 15;
+		float2 d = make_float2(0.0f, 0.0f);
+		if (direct) {
+			const float *__restrict__ c = p.comp + ((size_t)f * 16 + kmin) * 36 + 9 * part;
+			float ct[9];
 #pragma unroll
-			for (int j = 0; j < 20; j++) {
-				const float hj = c_tab.delay[f][j];
-				y = ffma2(uy[lane + j], make_float2(hj, hj), y);
-			}
-			if (top_trunc && lane < 16) {
+			for (int tt = 0; tt < 9; tt++) ct[tt] = (9 * part + tt < 35) ? __ldg(&c[tt]) : 0.0f;
+#pragma unroll
+			for (int tt = 0; tt < 9; tt++) d = ffma2(win_get<I16>(U, 4 * i + 9 * part + tt + e), make_float2(ct[tt], ct[tt]), d);
+		}
+		d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
+		d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
+		d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
+		d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
+		if (i < nlead && part == 0) {
+			// no tap left at all: the reference's sample is an exact zero; a tail-truncated leading output (kmax < 15, a burst
+			// hundreds of samples late) takes the generic two-stage path
+			if (kmin <= kmax && kmax < 15) d = slow_output<I16>(U, 4 * i + e, f, kmin, kmax);
+			if (edge) decs[2 + i] = cscale(d, s);
+			else ostage[i] = soft_out(i, d, s);
+		}
+	}
+	if (top_trunc) {
+		// trailing outputs lose decimator taps k > kmax (the delayed vector ends at sample 624 before the shift: delayed samples
+		// q >= q0 never reach the decimator): Y[q0 + m], m < 16, one per lane, then 4 lanes per output subtract g[k] * Y
+		const int q0c = min(max(q0, 0), 644);
+		float2 yt = make_float2(0.0f, 0.0f);
+		if (lane < 16) {
+			if (f < 64) {
 #pragma unroll
 				for (int j = 0; j < 20; j++) {
 					const float hj = c_tab.delay[f][j];
 					yt = ffma2(win_get<I16>(U, q0c + lane + e + j), make_float2(hj, hj), yt);
 				}
+			} else {
+				yt = win_get<I16>(U, q0c + lane + e + 9);
 			}
-		} else {
-			y = uy[lane + 9];
-			if (top_trunc && lane < 16) yt = win_get<I16>(U, q0c + lane + e + 9);
+			ytop[lane] = yt;
 		}
-		yv[lane] = y;
-		if (lane < 16) ytop[lane] = yt;
 		__syncwarp();
-		if (nv <= 32) {
-			for (int base = 0; base < nlead; base += 8) {
-				const int i = base + (lane >> 2), part = lane & 3;
-				const int kmin = min(16, max(0, max(15 - 4 * i, 15 - 4 * i + whole)));
-				float2 d = make_float2(0.0f, 0.0f);
-				if (i < nlead) {
-#pragma unroll
-					for (int kk = 0; kk < 4; kk++) {
-						const int k = 4 * part + kk;
-						if (k < kmin)
-							d = ffma2(yv[4 * i + k], make_float2(W.gk[kk], W.gk[kk]), d);
-					}
-				}
-				d.x += __shfl_xor_sync(0xffffffffu, d.x, 1);
-				d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
-				d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
-				d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
-				if (i < nlead && part == 0) {
-					// every tap dropped: the reference's sample is an exact zero - store the zero, not a rounding residue
-					const bool none = kmin > min(15, 639 + whole - 4 * i);
-					if (edge) {
-						const float2 c2 = cscale(d, s);
-						decs[2 + i] = none ? make_float2(0.0f, 0.0f) : make_float2(decs[2 + i].x - c2.x, decs[2 + i].y - c2.y);
-					} else {
-						ostage[i] = none ? 0.0f : ostage[i] - soft_out(i, d, s);
-					}
-				}
-			}
-		}
-		if (top_trunc) {
+		{
 			// outputs whose taps reach q >= q0: at most 8 of them (Y beyond q0 + 8 is zero: the burst has ended)
 			const int i = max(0, (q0 - 12) >> 2) + (lane >> 2), part = lane & 3;
 			float2 d = make_float2(0.0f, 0.0f);
@@ -687,7 +656,7 @@ __device__ __forceinline__ void demod_one(const DemodParams &p, const DemodWarp 
 			d.y += __shfl_xor_sync(0xffffffffu, d.y, 1);
 			d.x += __shfl_xor_sync(0xffffffffu, d.x, 2);
 			d.y += __shfl_xor_sync(0xffffffffu, d.y, 2);
-			if (i < nout && part == 0) {
+			if (i < nout && i >= nlead && part == 0) {
 				// no tap left at all (the reference's sample is an exact zero): store the zero, not a rounding residue
 				const bool none = max(0, max(15 - 4 * i, 15 - 4 * i + whole)) > min(15, 639 + whole - 4 * i);
 				if (edge) {
@@ -697,19 +666,6 @@ __device__ __forceinline__ void demod_one(const DemodParams &p, const DemodWarp 
 					ostage[i] = none ? 0.0f : ostage[i] - soft_out(i, d, s);
 				}
 			}
-		}
-	}
-	// ---- generic per-output path (rare): leading outputs of very late bursts (more than 32 delayed samples
-	//      feed the dropped taps) ----
-	if (nv > 32) {
-		for (int i = lane; i < nlead; i += 32) {
-			const int kmin = max(0, max(15 - 4 * i, 15 - 4 * i + whole));
-			const int kmax = min(15, 639 + whole - 4 * i);
-			float2 d = make_float2(0.0f, 0.0f);
-			if (kmin <= kmax)
-				d = (kmax == 15) ? comp_output<I16>(p, U, i, e, f, kmin) : slow_output<I16>(U, 4 * i + e, f, kmin, kmax);
-			if (edge) decs[2 + i] = cscale(d, s);
-			else ostage[i] = soft_out(i, d, s);
 		}
 	}
 	__syncwarp();
