@@ -30,7 +30,8 @@ namespace trxb200 {
 
 constexpr int kDlWarps = 12;	 // warps per CTA, one CTA per SM
 constexpr int kDlStagePitch = 17; // samples per row of the staging chunk (16 + 1: lanes = rows read conflict free)
-constexpr int kDlBulkPitch = 18;  // float rows, bulk copies: 16 samples + the 2 a row that starts off the 16-byte grid needs (144 B)
+constexpr int kDlChunk = 24;	  // float rows: window samples per chunk (seven chunks cover the 152-sample window; int16 rows: sixteen)
+constexpr int kDlBulkPitch = kDlChunk + 2; // float rows, bulk copies: a chunk + the 2 samples a row that starts off the 16-byte grid needs (208 B)
 struct DetLaneParams {
 	const void *tmap; // CUtensorMap (in global memory, 64-byte aligned) over the burst rows taken two at a time (below); used when tma_on
 	CorrParams c;
@@ -57,7 +58,8 @@ __host__ __device__ constexpr size_t det_lane_smem() { return det_lane_hdr_bytes
 // A row stride of 625 samples (5,000 bytes) is not a legal TMA stride, but TWO rows are (16 * stride bytes): the burst array
 // is described to the TMA as [n / 2][4 * stride] floats.  One tile copy then brings the same 16 window samples of the 16 even
 // rows of a warp's 32 bursts, a second one (inner coordinate + 2 * stride floats) those of the 16 odd rows: two instructions
-// per chunk instead of one per row.  Boxes of 16 rows x 18 samples (144 bytes: the row pitch in shared memory skews the banks).
+// per chunk instead of one per row.  Boxes of 16 rows x 26 samples (208 bytes: the row pitch in shared memory skews the banks).
+// The copy engine's cost is per box row rather than per byte: chunks of 24 samples (14 boxes per tile) instead of 16 (20 boxes).
 __device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int c0, int c1, unsigned bar)
 {
 	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
@@ -80,7 +82,8 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 	float2 *C = reinterpret_cast<float2 *>(wb);					      // [kPadRows + 20 + kPadRows][32]
 	float *Pw = reinterpret_cast<float *>(wb + (size_t)(20 + 2 * kPadRows) * kRowPitch * 8) + lane; // [35][32]
 	const float2 *stg = reinterpret_cast<const float2 *>(wb); // [2][32][kDlStagePitch], over the tile
-	static_assert((size_t)2 * 32 * kDlBulkPitch * sizeof(float2) <= (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2), "staging chunks fit the tile");
+	static_assert((size_t)2 * 32 * kDlBulkPitch * sizeof(float2) <= (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float),
+		      "staging chunks fit the tile and the powers behind it (neither is in use while the windows are read)");
 	const unsigned bar_s = (unsigned)__cvta_generic_to_shared(wb + (size_t)(20 + 2 * kPadRows) * kRowPitch * 8 + (size_t)35 * 32 * 4);
 	if (lane == 0) {
 		mbar_init(bar_s, 1);
@@ -184,7 +187,7 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 				// (one lane walking the rows instead - a bulk copy is a uniform-datapath instruction, 32 lanes issuing one each are
 				// serialised at about twenty instructions apiece - was measured slower: 0.65 against 0.55 ms per 2^20 bursts)
 				if (run) {
-					bulk_g2s(stg_s + (unsigned)(((c & 1) * 32 + lane) * kDlBulkPitch * 8), reinterpret_cast<const void *>(rowa + (unsigned long long)(128 * c)),
+					bulk_g2s(stg_s + (unsigned)(((c & 1) * 32 + lane) * kDlBulkPitch * 8), reinterpret_cast<const void *>(rowa + (unsigned long long)(8 * kDlChunk * c)),
 						 (unsigned)(kDlBulkPitch * 8), bar);
 				}
 			};
@@ -192,7 +195,7 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 			bool tma = false;
 			if constexpr (!I16) tma = P.tma_on && uniform && (((p.n & 1) == 0) || tile * 32 + 32 <= (p.n & ~1));
 			// (the TMA wants the start of a box on the 16-byte grid: a row's chunk starts at the even sample at or below the window
-			// sample and is 18 samples long; e_even / e_odd = the sample in front for the even and the odd rows of the tile)
+			// sample and is kDlBulkPitch samples long; e_even / e_odd = the sample in front for the even and the odd rows of the tile)
 			const int s_t = s_lo0 + P.tma_shift; // window start as a sample index of the tensor's rows
 			const int e_even = s_t & 1, e_odd = (cp.stride + s_t) & 1;
 			auto issue_tma = [&](int c) {
@@ -203,63 +206,71 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 					mbar_arrive_expect_tx(bar, 2u * 16u * (unsigned)(kDlBulkPitch * 8));
 					const unsigned dst = stg_s + (unsigned)((c & 1) * 2 * 16 * kDlBulkPitch * 8);
 					const int c1 = tile * 16;
-					tma_load_2d(dst, P.tmap, 2 * (s_t + 16 * c - e_even), c1, bar);
-					tma_load_2d(dst + (unsigned)(16 * kDlBulkPitch * 8), P.tmap, 2 * (cp.stride + s_t + 16 * c - e_odd), c1, bar);
+					tma_load_2d(dst, P.tmap, 2 * (s_t + kDlChunk * c - e_even), c1, bar);
+					tma_load_2d(dst + (unsigned)(16 * kDlBulkPitch * 8), P.tmap, 2 * (cp.stride + s_t + kDlChunk * c - e_odd), c1, bar);
 				}
 			};
-			// the lane's row in a staged chunk: box lane & 1 (even / odd rows), row lane >> 1, 18 samples per row, its window
-			// sample t at t + e; rows 144 bytes apart and the two boxes one sample out of step: conflict-free 8-byte reads
+			// the lane's row in a staged chunk: box lane & 1 (even / odd rows), row lane >> 1, kDlBulkPitch samples per row, its window
+			// sample t at t + e; rows 208 bytes apart and the two boxes one sample out of step: conflict-free 8-byte reads
 			const int trow = (lane & 1) * 16 * kDlBulkPitch + (lane >> 1) * kDlBulkPitch + ((lane & 1) ? e_odd : e_even);
-			float2 X[28];
+			// The decimator consumes a chunk eight samples at a time: sub-step g brings window samples 8g .. 8g + 7 and completes the
+			// outputs 2g - 3 and 2g - 2 (output j reads window samples 4j .. 4j + 15), from a register window of 12 + 8 samples.
+			constexpr int CS = I16 ? 16 : kDlChunk, NCH = (152 + CS - 1) / CS, SUB = CS / 8;
+			float2 X[20];
 			__syncwarp(); // the previous tile's peak logic is done with the tile the chunks overlay
 			if constexpr (I16) { issue(0); issue(1); }
 			else if (tma) { issue_tma(0); issue_tma(1); }
 			else { issue_bulk(0); issue_bulk(1); }
 #pragma unroll
-			for (int c = 0; c < 10; c++) {
+			for (int c = 0; c < NCH; c++) {
+				const float2 *row;
 				if constexpr (I16) {
-					if (c < 9) asm volatile("cp.async.wait_group 1;" ::: "memory");
+					if (c < NCH - 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
 					else asm volatile("cp.async.wait_group 0;" ::: "memory");
 					__syncwarp();
-#pragma unroll
-					for (int t = 0; t < 16; t++) X[12 + t] = cvt_s2(reinterpret_cast<const unsigned *>(stg)[((c & 1) * 32 + lane) * kDlStagePitch + t]);
+					row = stg; // (int16 rows are addressed as words below)
 				} else {
 					mbar_wait(bar_s + 8u * (unsigned)(c & 1), (phase >> (c & 1)) & 1u);
 					phase ^= 1u << (c & 1);
-					if (tma) {
-						const float2 *row = stg + (c & 1) * 2 * 16 * kDlBulkPitch + trow;
+					row = tma ? stg + (c & 1) * 2 * 16 * kDlBulkPitch + trow : stg + ((c & 1) * 32 + lane) * kDlBulkPitch + e;
+				}
 #pragma unroll
-						for (int t = 0; t < 16; t++) X[12 + t] = row[t];
+				for (int u = 0; u < SUB; u++) {
+					if constexpr (I16) {
+#pragma unroll
+						for (int t = 0; t < 8; t++) X[12 + t] = cvt_s2(reinterpret_cast<const unsigned *>(stg)[((c & 1) * 32 + lane) * kDlStagePitch + 8 * u + t]);
 					} else {
-						const float2 *row = stg + ((c & 1) * 32 + lane) * kDlBulkPitch + e;
 #pragma unroll
-						for (int t = 0; t < 16; t++) X[12 + t] = row[t];
+						for (int t = 0; t < 8; t++) X[12 + t] = row[8 * u + t];
 					}
-				}
-				__syncwarp();
-				if (c + 2 < 10) {
-					if constexpr (I16) issue(c + 2);
-					else if (tma) issue_tma(c + 2);
-					else issue_bulk(c + 2);
-				}
-				// outputs 4c - 3 .. 4c: output j reads window samples 4j .. 4j + 15 = X[4j - 16c + 12 ..]
-#pragma unroll
-				for (int o = 0; o < 4; o++) {
-					const int j = 4 * c - 3 + o;
-					if (j >= 0 && j < 35) {
-						const int x0 = 4 * o; // 4j - 16c + 12
-						float2 L[4];
-#pragma unroll
-						for (int q = 0; q < 4; q++) {
-							const float2 p0 = mul2(X[x0 + q], bc2(g16[q]), NZ), p1 = mul2(X[x0 + 4 + q], bc2(g16[4 + q]), NZ);
-							const float2 p2 = mul2(X[x0 + 8 + q], bc2(g16[8 + q]), NZ), p3 = mul2(X[x0 + 12 + q], bc2(g16[12 + q]), NZ);
-							L[q] = add2(add2(p0, p1), add2(p2, p3));
+					if (u == SUB - 1) {
+						// every lane holds the rest of the chunk: its buffer takes the chunk after next
+						__syncwarp();
+						if (c + 2 < NCH) {
+							if constexpr (I16) issue(c + 2);
+							else if (tma) issue_tma(c + 2);
+							else issue_bulk(c + 2);
 						}
-						dec[j] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
 					}
-				}
+					const int g = c * SUB + u;
 #pragma unroll
-				for (int t = 0; t < 12; t++) X[t] = X[t + 16];
+					for (int o = 0; o < 2; o++) {
+						const int j = 2 * g - 3 + o;
+						if (j >= 0 && j < 35) {
+							const int x0 = 4 * o; // window sample 4j = 8g - 12 + 4o
+							float2 L[4];
+#pragma unroll
+							for (int q = 0; q < 4; q++) {
+								const float2 p0 = mul2(X[x0 + q], bc2(g16[q]), NZ), p1 = mul2(X[x0 + 4 + q], bc2(g16[4 + q]), NZ);
+								const float2 p2 = mul2(X[x0 + 8 + q], bc2(g16[8 + q]), NZ), p3 = mul2(X[x0 + 12 + q], bc2(g16[12 + q]), NZ);
+								L[q] = add2(add2(p0, p1), add2(p2, p3));
+							}
+							dec[j] = add2(add2(L[0], L[1]), add2(L[2], L[3]));
+						}
+					}
+#pragma unroll
+					for (int t = 0; t < 12; t++) X[t] = X[t + 8];
+				}
 			}
 			// the chunks lay over the tile: its zero rows in front of and behind the correlation vector are restored (a lane
 			// clears its own column of every pad row; the 20 vector rows are rewritten or cleared by the code below)
