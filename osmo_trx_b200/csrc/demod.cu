@@ -193,18 +193,15 @@ __device__ __noinline__ void demod_edge_tail(const DemodParams &p, int b, float2
 			for (int k = 0; k < 5; k++) eq = ffma2(decs[i + k], make_float2(c0[k], c0[k]), eq);
 			rot[r] = cmul_fast(eq, rot_lane); // derotateEdgeBurst :691-711
 			if (i >= 8 && i < size - 8) {
-				// computeEdgeCI :2074-2093: distance to the nearest ideal 8-PSK point.  The reference picks it as
-				// round(atan2(y, x) / (pi/4)); the octant test below picks the same point except within rounding
-				// of an octant boundary, where both neighbours are equally far.
+				// computeEdgeCI :2074-2093: squared distance to the nearest ideal 8-PSK point.  The reference picks the point as
+				// round(atan2(y, x) / (pi/4)); on a circle the point nearest in angle is the point nearest in distance, and
+				// the constellation is symmetric under |x|, |y| and their exchange: with hi = max(|x|, |y|), lo = min(|x|, |y|)
+				// the candidates are (1, 0) and (c, c), c = cos(pi/4).  (The table's points carry cosf's 4e-8 leakage, far
+				// below the 1e-4 tolerance of this chain.)
 				const float ax = fabsf(rot[r].x), ay = fabsf(rot[r].y);
-				const unsigned sel = (fminf(ax, ay) > 0.41421357f * fmaxf(ax, ay) ? 8u : 0u) | (ay > ax ? 4u : 0u) |
-						     (rot[r].x < 0.0f ? 2u : 0u) | (rot[r].y < 0.0f ? 1u : 0u);
-				// k + 4 per (diagonal, vertical, x < 0, y < 0): axis points 0, +-4, +-2; diagonal points +-1, +-3
-				const unsigned long long lut = 0x1735173526260844ull;
-				const int k4 = (int)((lut >> (4 * sel)) & 15u);
-				const float2 ideal = ideal_s[k4];
-				const float ex = ideal.x - rot[r].x, ey = ideal.y - rot[r].y;
-				err = fmaf(ex, ex, fmaf(ey, ey, err));
+				const float hi = fmaxf(ax, ay), lo = fminf(ax, ay);
+				const float a1 = hi - 1.0f, b1 = hi - 0.70710678f, b2 = lo - 0.70710678f;
+				err += fminf(fmaf(a1, a1, lo * lo), fmaf(b1, b1, b2 * b2));
 			}
 		}
 	}
@@ -488,7 +485,8 @@ __device__ __forceinline__ void demod_one(const DemodParams &p, const DemodWarp 
 	// ---- main pass (transposed FIR), shared by GMSK and EDGE: lane owns window samples 20*lane ..
 	//      20*lane+19 and accumulates into outputs i = 5*lane - 8 + m, m = 0..12; sample j meets output m
 	//      with tap u = j + 32 - 4m (0 <= u <= 35), coefficient ce[u] = comp0[f][e][u] ----
-	const int nout = edge ? 156 : p.n_gmsk_soft;
+	// 8-PSK: the equaliser's last output (symbol 147) reads the decimated samples up to 149 - the last six are never used
+	const int nout = edge ? 150 : p.n_gmsk_soft;
 	{
 		float2 acc[13];
 #pragma unroll
