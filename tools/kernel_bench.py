@@ -83,8 +83,11 @@ def main():
         t_det = timed(lambda: trx.detect(rx, typ, tsc, mt, bound, out=res))
         nd = hl + 16 + bound - 1
         det_ops = nd * 62 + (16 + bound) * hl * 8 + 9 * 2 * 21 * 4  # decimate + correlate + early/late interpolation
-        add(f"detect[{kind}] corr+peak(+clip)", "burst", n, 5000 + 24, t_det,
-            f"standalone detectAnyBurst incl. the 625-sample clip scan; correlator window alone is {win} B", ops=det_ops)
+        # the clip scan (all 625 samples) only visits the bursts detection left at rc == 0
+        undet = float((res["rc"] == 0).float().mean().item())
+        add(f"detect[{kind}] (+clip scan)", "burst", n, win + 24 + undet * 5000, t_det,
+            f"standalone detectAnyBurst: correlator window {win} B + results + the 625-sample clip scan of the {100 * undet:.0f} % of "
+            "bursts left undetected", ops=det_ops)
         t_dem = timed(lambda: trx.demod(rx, res["rc"], res["amp"], res["toa"], res["ci"], soft=res["soft"], n_gmsk_soft=148))
         add(f"demod_kernel[{kind}]", "burst", n, 5000 + soft * 4 + 16, t_dem, ops=156 * 35 * 2 + 32 * 20 * 2 + (148 * 40 if kind == "edge" else 0))
         t_dd = timed(lambda: trx.detect_demod(rx, typ, tsc, mt, bound, n_gmsk_soft=148, out=res))
