@@ -67,6 +67,7 @@ struct trxb200_ctx {
 	HostTables *ht = nullptr;
 	float *d_sinc512 = nullptr;
 	float *d_comp = nullptr;
+	uint4 *d_seq_pm1 = nullptr; // per tap of every sequence: sign masks of the +-1 component, the tiny component (corr_long_items_pm1)
 	float2 *d_edge_tab = nullptr; // derotation + ideal-symbol tables for the EDGE demodulator
 	void *d_tmap = nullptr;	      // TMA descriptors of detect_lane_kernel (four slots)
 	float *d_mod_tab = nullptr;   // modulator tables in global memory (per-lane indexed): rot4 | c0 | c1 | edge_rot | psk8
@@ -86,6 +87,8 @@ struct trxb200_ctx {
 		// need the whole register file of an SM to hide their latencies - so the pipeline is off unless asked for
 		int overlap = 0, chunk_cap = 131072;
 		int detect_chunk = 1 << 30; // bursts per corr/peak launch pair.  Measured (profiles/r2l_detect_chunk_sweep.txt): one pair for the whole batch beats 262,144-burst chunks (corr 0.454 -> 0.403 ms, peak 0.220 -> 0.178 ms per 2^20 bursts); keeping the intermediates L2 resident with small chunks does not pay for the extra launches and tails
+		int corr_long_wpb = 10; // warps per corr_long_kernel CTA (two CTAs per SM)
+		int corr_pm1 = 1; // corr_long_kernel: sign flips instead of products for the +-1 components of the rotated GMSK sequences
 		int resamp_pq = 1; // 1: resampler_pq_kernel for the 65/48 and 48/65 ratios of the multi-ARFCN interface
 		int resamp_up = 0; // 1: resampler_up_kernel (three outputs per thread from a register window) for interpolating ratios; measured 4.4 ms vs 3.2 ms of resampler16_kernel on the cfg-5 stream (profiles/r2k_*), so off by default
 		int fused = 0; // 1: nb_fused_kernel (one persistent warp-specialised kernel) for detect+demod in the normal-burst geometry; measured 2.75 ms vs 1.76 ms per 2^20 bursts for the three-kernel path (profiles/r2f_*), so off by default
@@ -207,6 +210,13 @@ void fill_const_tables(const HostTables &t, ConstTables &c)
 		c.info[id].inv_gi = -s.gain.i / n;
 		c.info[id].ci_den = (float)(s.len - 1) * std::sqrt(n);
 		c.info[id].toa = s.toa;
+		// the rotated GMSK sequences: even taps (+-1, tiny), odd taps (tiny, +-1), exactly
+		bool pm1 = (s.len % 8) == 0;
+		for (int i = 0; i < s.len && pm1; i++) {
+			const float dom = (i & 1) ? s.seq[i].i : s.seq[i].r, oth = (i & 1) ? s.seq[i].r : s.seq[i].i;
+			pm1 = std::fabs(dom) == 1.0f && std::fabs(oth) < 1e-6f;
+		}
+		c.info[id].pm1 = pm1 ? 1 : 0;
 	};
 	for (int k = 0; k < 8; k++) put(SEQ_MIDAMBLE + k, t.midamble[k]);
 	for (int k = 0; k < 8; k++) put(SEQ_EDGE + k, t.edge_midamble[k]);
@@ -283,7 +293,27 @@ int trxb200_init(int device, trxb200_ctx **out)
 	ConstTables *c = new ConstTables();
 	fill_const_tables(*ctx->ht, *c);
 	cudaError_t e = cudaMemcpyToSymbol(c_tab, c, sizeof(ConstTables));
+	// per tap of the +-1 sequences (corr_long_items_pm1): x * (+-1) is a sign flip (.x, .y = XOR masks for re, im), the other
+	// component keeps its multiplication (.z, .w = the operand pair of that product, as floats)
+	std::vector<uint4> pm(SEQ_STORE, make_uint4(0, 0, 0, 0));
+	for (int id = 0; id < SEQ_COUNT; id++) {
+		if (!c->info[id].pm1) continue;
+		for (int i = 0; i < c->info[id].len; i++) {
+			const float2 h = c->seq[c->info[id].off + i];
+			auto sgn = [](float v) { uint32_t u; std::memcpy(&u, &v, 4); return u & 0x80000000u; };
+			auto bits = [](float v) { uint32_t u; std::memcpy(&u, &v, 4); return u; };
+			uint4 t;
+			if ((i & 1) == 0) { // (x.re * hr, x.im * hr) = +-x;  (x.re * hi, x.im * -hi) stays a product
+				t.x = sgn(h.x); t.y = sgn(h.x); t.z = bits(h.y); t.w = bits(-h.y);
+			} else {	    // (x.re * hr, x.im * hr) stays a product;  (x.re * hi, x.im * -hi) = (+-x.re, -+x.im)
+				t.x = sgn(h.y); t.y = sgn(-h.y); t.z = bits(h.x); t.w = bits(h.x);
+			}
+			pm[c->info[id].off + i] = t;
+		}
+	}
 	delete c;
+	if (e == cudaSuccess) e = cudaMalloc(&ctx->d_seq_pm1, pm.size() * sizeof(uint4));
+	if (e == cudaSuccess) e = cudaMemcpy(ctx->d_seq_pm1, pm.data(), pm.size() * sizeof(uint4), cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
 	// interpolation weights for peak_kernel: tap-major, columns bit-reversed (detect.cu kSinc512)
 	std::vector<float> wtab((size_t)21 * 512);
@@ -347,6 +377,8 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_FUSED", t.fused);
 		env_int("TRXB200_RESAMP_UP", t.resamp_up);
 		env_int("TRXB200_RESAMP_PQ", t.resamp_pq);
+		env_int("TRXB200_CORR_PM1", t.corr_pm1);
+		env_int("TRXB200_CORR_LONG_WPB", t.corr_long_wpb);
 		env_int("TRXB200_CHUNK", t.chunk_cap);
 		env_int("TRXB200_DETECT_CHUNK", t.detect_chunk);
 		env_int("TRXB200_DEMOD_WPB", t.demod_wpb);
@@ -391,6 +423,7 @@ void trxb200_destroy(trxb200_ctx *ctx)
 	cudaFree(ctx->ws.pwr);
 	cudaFree(ctx->ws.list);
 	if (ctx->d_comp) cudaFree(ctx->d_comp);
+	if (ctx->d_seq_pm1) cudaFree(ctx->d_seq_pm1);
 	if (ctx->d_edge_tab) cudaFree(ctx->d_edge_tab);
 	if (ctx->d_tmap) cudaFree(ctx->d_tmap);
 	if (ctx->d_mod_tab) cudaFree(ctx->d_mod_tab);
@@ -647,9 +680,11 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 	int cw = 8; // warps per corr block
 	const bool cwide = nb && !iq && !overlapped && tn.corr_wpb == 18; // corr_nb_kernel as one CTA of 18 warps per SM
 	if (cwide) cw = 18;
-	if (!nb)
-		while (cw > 1 && corr_lg_warp_bytes(ndmax) * cw > 100 * 1024) cw >>= 1;
-	const size_t csmem = nb ? corr_nb_hdr_bytes() + corr_nb_warp_bytes() * cw : corr_lg_warp_bytes(ndmax) * cw;
+	if (!nb) {
+		cw = std::max(1, std::min(tn.corr_long_wpb, 10));
+		while (cw > 1 && corr_lg_warp_bytes(ndmax) * cw + corr_lg_hdr_bytes() > 110 * 1024) cw--;
+	}
+	const size_t csmem = nb ? corr_nb_hdr_bytes() + corr_nb_warp_bytes() * cw : corr_lg_warp_bytes(ndmax) * cw + corr_lg_hdr_bytes();
 	const int cgroup = nb ? kNbGroup : 1;
 	int pw = std::max(1, std::min(32, overlapped ? tn.ov_peak_warps : tn.peak_warps)); // warps per peak block
 	// as many warps as the shared memory of one SM holds (long correlation vectors: 7 warps at lmax 80, not a power of two)
@@ -817,6 +852,7 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			c.type = sch ? nullptr : type + lo; c.tsc = sch ? nullptr : tsc + lo; c.max_toa = sch ? nullptr : max_toa + lo; c.rc = rc + lo; c.round = r;
 			c.sch = sch ? 1 : 0;
 			c.sps1_len = sps1_len;
+			c.seq_pm1 = ctx->tune.corr_pm1 ? ctx->d_seq_pm1 : nullptr;
 			c.max_toa_bound = bound; c.lmax = lmax; c.ndmax = ndmax; c.corr = ws.corr; c.pwr = ws.pwr; c.negzero = -0.0f;
 			const int ngroups = (m + cgroup - 1) / cgroup;
 			const int cgrid = std::max(1, std::min((ngroups + cw - 1) / cw, ctx->sm_count * cbps));

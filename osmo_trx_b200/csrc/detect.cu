@@ -483,6 +483,69 @@ __host__ __device__ constexpr size_t corr_lg_warp_bytes(int ndmax)
 	return (size_t)2 * 8 * corr_lg_pp(ndmax) * 16 + ((((size_t)ndmax + 8) * 8 + 15) & ~(size_t)15);
 }
 
+__host__ __device__ constexpr size_t corr_lg_hdr_bytes() { return (size_t)SEQ_STORE * sizeof(uint4); } // the CTA's copy of CorrParams::seq_pm1
+
+// One tap of a rotated GMSK sequence: one of its components is +-1 exactly, the other a rounding residue of the rotator
+// (6e-17 .. 4e-15).  x * (+-1) is a sign flip - exact, on the ALU pipe - and only the product with the residue stays on the
+// FP32 pipe, which bounds this kernel: three packed operations per tap and output instead of four, same bits.
+//   even tap (REAL): (x.re * hr, x.im * hr) = x ^ (m, m);  T = (x.re * hi, x.im * -hi);  result = E + swap(T)
+//   odd tap (!REAL): T = (x.re * hr, x.im * hr);  (x.re * hi, x.im * -hi) = x ^ (m, ~m) = E;  result = T + swap(E)
+template <bool REAL>
+__device__ __forceinline__ float2 tap_pm1(float2 x, uint4 t, float2 NZ)
+{
+	const float2 E = make_float2(__uint_as_float(__float_as_uint(x.x) ^ t.x), __uint_as_float(__float_as_uint(x.y) ^ t.y));
+	const float2 T = mul2(x, make_float2(__uint_as_float(t.z), __uint_as_float(t.w)), NZ);
+	if (REAL) return add2(E, make_float2(T.y, T.x));
+	return add2(T, make_float2(E.y, E.x));
+}
+
+// corr_long_items for the +-1 sequences.  Lane = (group of five outputs, half of the accumulation chains): the eight chains
+// of an output (A[q], B[q], convolve_sse_3.c:462-537) are split q = 0, 1 / q = 2, 3 over the lanes l and l + 16, whose
+// partial sums (L0 + L1), (L2 + L3) meet in one shuffle - the reference's order - so that an access burst's 79 outputs
+// occupy all 32 lanes (16 groups x 2 halves) instead of 27 (x 3 outputs).  tp: the sequence's taps in shared memory.
+template <int HLEN>
+__device__ __forceinline__ void corr_long_items_pm1(const float2 *dec, const uint4 *tp, int len, int hlen_rt, int lane, float2 *crow, float2 NZ)
+{
+	const int hlen = HLEN ? HLEN : hlen_rt;
+	// (half = lane >> 4: the sixteen lanes of a half warp read windows 5 samples apart - 5 is coprime to the 16 bank pairs, so the
+	// 8-byte loads are conflict free; with the halves interleaved, lane = 2 g + half, a third of the wavefronts were conflicts)
+	const int hf = lane >> 4;
+	for (int g0 = 0; 5 * g0 < len; g0 += 16) {
+		const int g = g0 + (lane & 15);
+		const bool act = 5 * g < len;
+		const float2 *dx = dec + (act ? 5 * g : 0) + 2 * hf;
+		const uint4 *th = tp + 2 * hf;
+		float2 A[2][5], B[2][5];
+#pragma unroll
+		for (int qq = 0; qq < 2; qq++)
+#pragma unroll
+			for (int o = 0; o < 5; o++) { A[qq][o] = make_float2(0.0f, 0.0f); B[qq][o] = make_float2(0.0f, 0.0f); }
+#pragma unroll
+		for (int t0 = 0; t0 < hlen; t0 += 8) {
+			asm volatile("" ::: "memory"); // keeps the unrolled blocks' loads in their own block (register pressure)
+			float2 xw[10];
+#pragma unroll
+			for (int k = 0; k < 10; k++) xw[k] = dx[t0 + k];
+			const uint4 ta0 = th[t0], ta1 = th[t0 + 1], tb0 = th[t0 + 4], tb1 = th[t0 + 5];
+#pragma unroll
+			for (int o = 0; o < 5; o++) {
+				A[0][o] = add2(A[0][o], tap_pm1<true>(xw[o], ta0, NZ));
+				B[0][o] = add2(B[0][o], tap_pm1<true>(xw[4 + o], tb0, NZ));
+				A[1][o] = add2(A[1][o], tap_pm1<false>(xw[1 + o], ta1, NZ));
+				B[1][o] = add2(B[1][o], tap_pm1<false>(xw[5 + o], tb1, NZ));
+			}
+		}
+#pragma unroll
+		for (int o = 0; o < 5; o++) {
+			const float2 P = add2(add2(A[0][o], B[0][o]), add2(A[1][o], B[1][o])); // L[2 hf] + L[2 hf + 1]
+			float2 Q;
+			Q.x = __shfl_xor_sync(0xffffffffu, P.x, 16);
+			Q.y = __shfl_xor_sync(0xffffffffu, P.y, 16);
+			if (act && hf == 0 && 5 * g + o < len) crow[5 * g + o] = add2(P, Q); // (L0 + L1) + (L2 + L3)
+		}
+	}
+}
+
 // HLEN > 0: compile-time sequence length (fully unrolled, immediate offsets); 0: run-time multiple of 8
 template <int HLEN>
 __device__ __forceinline__ void corr_long_items(const float2 *dec, const float2 *hh, int len, int hlen_rt, int lane, float2 *crow,
@@ -525,7 +588,7 @@ __device__ __forceinline__ void corr_long_items(const float2 *dec, const float2 
 	}
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(320, 2)
 corr_long_kernel(CorrParams p)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -533,7 +596,13 @@ corr_long_kernel(CorrParams p)
 	const int wpb = blockDim.x >> 5;
 	const int ndmax = p.ndmax, lmax = p.lmax;
 	const int PP = corr_lg_pp(ndmax);
-	unsigned char *wbase = smem_raw + corr_lg_warp_bytes(ndmax) * warp;
+	// the +-1 taps of every sequence in front of the warps' areas
+	uint4 *pm1_s = p.seq_pm1 ? reinterpret_cast<uint4 *>(smem_raw) : nullptr;
+	if (pm1_s) {
+		for (int k = threadIdx.x; k < SEQ_STORE; k += blockDim.x) pm1_s[k] = p.seq_pm1[k];
+		__syncthreads();
+	}
+	unsigned char *wbase = smem_raw + corr_lg_hdr_bytes() + corr_lg_warp_bytes(ndmax) * warp;
 	float4 *raw0 = reinterpret_cast<float4 *>(wbase);		      // [2][8][PP]
 	float2 *dec = reinterpret_cast<float2 *>(raw0 + (size_t)2 * 8 * PP); // [ndmax + 8]
 	const unsigned raw_s = (unsigned)__cvta_generic_to_shared(raw0);
@@ -563,7 +632,7 @@ corr_long_kernel(CorrParams p)
 		Attempt at;
 		if (q.type >= 0 && attempt_runs(q.type, q.tsc, q.T, p.max_toa_bound, ndmax, p.round, q.rc, c_tab.info, at)) {
 			r.x = 1 | (c_tab.info[at.seq].len << 1) | (at.start << 8) | (at.len << 16);
-			r.y = c_tab.info[at.seq].off;
+			r.y = c_tab.info[at.seq].off | (c_tab.info[at.seq].pm1 << 30);
 		}
 		return r;
 	};
@@ -663,9 +732,15 @@ corr_long_kernel(CorrParams p)
 			}
 			__syncwarp();
 			// ---- correlation (sse_conv_cmplx_8n order, convolve_sse_3.c:462-537): 3 outputs per item ----
-			const float2 *hh = c_tab.seq + pk0.y;
+			const int soff = pk0.y & 0xffff;
+			const float2 *hh = c_tab.seq + soff;
 			float2 *crow = p.corr + (size_t)b * lmax;
-			if (hlen == 40) corr_long_items<40>(dec, hh, len, hlen, lane, crow, NZ);
+			if (pm1_s && (pk0.y >> 30)) {
+				if (hlen == 40) corr_long_items_pm1<40>(dec, pm1_s + soff, len, hlen, lane, crow, NZ);
+				else if (hlen == 16) corr_long_items_pm1<16>(dec, pm1_s + soff, len, hlen, lane, crow, NZ);
+				else if (hlen == 64) corr_long_items_pm1<64>(dec, pm1_s + soff, len, hlen, lane, crow, NZ);
+				else corr_long_items_pm1<0>(dec, pm1_s + soff, len, hlen, lane, crow, NZ);
+			} else if (hlen == 40) corr_long_items<40>(dec, hh, len, hlen, lane, crow, NZ);
 			else if (hlen == 16) corr_long_items<16>(dec, hh, len, hlen, lane, crow, NZ);
 			else if (hlen == 64) corr_long_items<64>(dec, hh, len, hlen, lane, crow, NZ);
 			else corr_long_items<0>(dec, hh, len, hlen, lane, crow, NZ);

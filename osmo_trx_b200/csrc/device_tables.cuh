@@ -19,6 +19,8 @@ struct SeqInfo {
 	float inv_gr, inv_gi; // gain.inv() (Complex.h:144-150): amp = xcorr * inv(gain)  (sigProcLib.cpp:1701)
 	float ci_den;	 // (N-1) * |gain|   (sigProcLib.cpp:1629)
 	float toa;	 // sequence time offset (sigProcLib.cpp:1704)
+	int pm1;	 // 1: every even tap is (+-1, tiny) and every odd tap (tiny, +-1) - the rotated GMSK sequences (corr_long_items_pm1)
+	int pad_;
 };
 
 struct ConstTables {

@@ -23,6 +23,7 @@ struct CorrParams {
 	const int16_t *iq; // [n][iq_stride] complex int16, or null
 	int iq_stride;
 	int sch;	   // every burst is a SCH_DETECT_FULL search (type / tsc / max_toa are not read)
+	const uint4 *seq_pm1 = nullptr; // [SEQ_STORE] per tap of the sequences flagged SeqInfo::pm1: sign masks and the tiny component (corr_long_items_pm1)
 	int sps1_len = 0;  // > 0: the rows are bursts of this many samples at ONE sample per symbol - no decimation, the correlator reads
 			   // the burst itself (detectBurst, sigProcLib.cpp:1659-1662); corr_long_kernel only
 };
