@@ -28,9 +28,9 @@
 
 namespace trxb200 {
 
-constexpr int kDlWarps = 12;	 // warps per CTA, one CTA per SM
+constexpr int kDlWarps = 10;	 // warps per CTA, one CTA per SM
 constexpr int kDlStagePitch = 17; // samples per row of the staging chunk (16 + 1: lanes = rows read conflict free)
-constexpr int kDlChunk = 24;	  // float rows: window samples per chunk (seven chunks cover the 152-sample window; int16 rows: sixteen)
+constexpr int kDlChunk = 32;	  // float rows: window samples per chunk (seven chunks cover the 152-sample window; int16 rows: sixteen)
 constexpr int kDlBulkPitch = kDlChunk + 2; // float rows, bulk copies: a chunk + the 2 samples a row that starts off the 16-byte grid needs (208 B)
 struct DetLaneParams {
 	const void *tmap; // CUtensorMap (in global memory, 64-byte aligned) over the burst rows taken two at a time (below); used when tma_on
@@ -50,7 +50,9 @@ __host__ __device__ constexpr size_t det_lane_warp_bytes()
 	// correlation tile [kPadRows + 20 + kPadRows][32] + decimated powers [35][32] + two mbarriers, rounded to 1 KB (the
 	// TMA swizzle pattern is a function of the shared address); the staging chunks of the decimator lie over the tile,
 	// which is not in use while the windows are read
-	return (((size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float) + 16) + 1023) & ~(size_t)1023;
+	const size_t tile = (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float);
+	const size_t stage = (size_t)2 * 32 * kDlBulkPitch * sizeof(float2);
+	return (((tile > stage ? tile : stage) + 16) + 1023) & ~(size_t)1023;
 }
 __host__ __device__ constexpr size_t det_lane_hdr_bytes() { return ((size_t)kSinc512 * sizeof(float) + corr_nb_hdr_bytes() + 1023) & ~(size_t)1023; }
 __host__ __device__ constexpr size_t det_lane_smem() { return det_lane_hdr_bytes() + kDlWarps * det_lane_warp_bytes(); }
@@ -82,9 +84,8 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 	float2 *C = reinterpret_cast<float2 *>(wb);					      // [kPadRows + 20 + kPadRows][32]
 	float *Pw = reinterpret_cast<float *>(wb + (size_t)(20 + 2 * kPadRows) * kRowPitch * 8) + lane; // [35][32]
 	const float2 *stg = reinterpret_cast<const float2 *>(wb); // [2][32][kDlStagePitch], over the tile
-	static_assert((size_t)2 * 32 * kDlBulkPitch * sizeof(float2) <= (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float),
-		      "staging chunks fit the tile and the powers behind it (neither is in use while the windows are read)");
-	const unsigned bar_s = (unsigned)__cvta_generic_to_shared(wb + (size_t)(20 + 2 * kPadRows) * kRowPitch * 8 + (size_t)35 * 32 * 4);
+
+	const unsigned bar_s = (unsigned)__cvta_generic_to_shared(wb + det_lane_warp_bytes() - 16);
 	if (lane == 0) {
 		mbar_init(bar_s, 1);
 		mbar_init(bar_s + 8, 1);
