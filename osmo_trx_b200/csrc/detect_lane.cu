@@ -28,9 +28,9 @@
 
 namespace trxb200 {
 
-constexpr int kDlWarps = 10;	 // warps per CTA, one CTA per SM
+constexpr int kDlWarps = 12;	 // warps per CTA, one CTA per SM
 constexpr int kDlStagePitch = 17; // samples per row of the staging chunk (16 + 1: lanes = rows read conflict free)
-constexpr int kDlChunk = 32;	  // float rows: window samples per chunk (seven chunks cover the 152-sample window; int16 rows: sixteen)
+constexpr int kDlChunk = 24;	  // float rows: window samples per chunk (seven chunks cover the 152-sample window; int16 rows: sixteen)
 constexpr int kDlBulkPitch = kDlChunk + 2; // float rows, bulk copies: a chunk + the 2 samples a row that starts off the 16-byte grid needs (208 B)
 struct DetLaneParams {
 	const void *tmap; // CUtensorMap (in global memory, 64-byte aligned) over the burst rows taken two at a time (below); used when tma_on
@@ -50,9 +50,7 @@ __host__ __device__ constexpr size_t det_lane_warp_bytes()
 	// correlation tile [kPadRows + 20 + kPadRows][32] + decimated powers [35][32] + two mbarriers, rounded to 1 KB (the
 	// TMA swizzle pattern is a function of the shared address); the staging chunks of the decimator lie over the tile,
 	// which is not in use while the windows are read
-	const size_t tile = (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float);
-	const size_t stage = (size_t)2 * 32 * kDlBulkPitch * sizeof(float2);
-	return (((tile > stage ? tile : stage) + 16) + 1023) & ~(size_t)1023;
+	return (((size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float) + 16) + 1023) & ~(size_t)1023;
 }
 __host__ __device__ constexpr size_t det_lane_hdr_bytes() { return ((size_t)kSinc512 * sizeof(float) + corr_nb_hdr_bytes() + 1023) & ~(size_t)1023; }
 __host__ __device__ constexpr size_t det_lane_smem() { return det_lane_hdr_bytes() + kDlWarps * det_lane_warp_bytes(); }
@@ -62,6 +60,7 @@ __host__ __device__ constexpr size_t det_lane_smem() { return det_lane_hdr_bytes
 // rows of a warp's 32 bursts, a second one (inner coordinate + 2 * stride floats) those of the 16 odd rows: two instructions
 // per chunk instead of one per row.  Boxes of 16 rows x 26 samples (208 bytes: the row pitch in shared memory skews the banks).
 // The copy engine's cost is per box row rather than per byte: chunks of 24 samples (14 boxes per tile) instead of 16 (20 boxes).
+// (32-sample chunks need 17 KB of staging per warp, i.e. ten warps instead of twelve: 0.42 against 0.40 ms.)
 __device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int c0, int c1, unsigned bar)
 {
 	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
@@ -84,8 +83,9 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 	float2 *C = reinterpret_cast<float2 *>(wb);					      // [kPadRows + 20 + kPadRows][32]
 	float *Pw = reinterpret_cast<float *>(wb + (size_t)(20 + 2 * kPadRows) * kRowPitch * 8) + lane; // [35][32]
 	const float2 *stg = reinterpret_cast<const float2 *>(wb); // [2][32][kDlStagePitch], over the tile
-
-	const unsigned bar_s = (unsigned)__cvta_generic_to_shared(wb + det_lane_warp_bytes() - 16);
+	static_assert((size_t)2 * 32 * kDlBulkPitch * sizeof(float2) <= (size_t)(20 + 2 * kPadRows) * kRowPitch * sizeof(float2) + (size_t)35 * 32 * sizeof(float),
+		      "staging chunks fit the tile and the powers behind it (neither is in use while the windows are read)");
+	const unsigned bar_s = (unsigned)__cvta_generic_to_shared(wb + (size_t)(20 + 2 * kPadRows) * kRowPitch * 8 + (size_t)35 * 32 * 4);
 	if (lane == 0) {
 		mbar_init(bar_s, 1);
 		mbar_init(bar_s + 8, 1);
