@@ -95,6 +95,7 @@ struct trxb200_ctx {
 		int host_chunk = 16384; // slots per stage of the pinned-host pipelines (H2D | kernels | D2H on three streams)
 		int pull_chunk = 262144; // slots per pass of the pull chain (scratch: correlator windows + soft bits, about 2 KB per slot)
 		int corr_bps = 0, peak_bps = 0, peak_warps = 16, demod_bps = 2; // 0 = derive from the on-chip footprint
+		int detect_tma16 = 1; // detect_lane_kernel<int16>: TMA tiles over the slots taken four at a time (0: 4-byte cp.async chunks)
 		int detect_tma = 1; // detect_lane_kernel: window chunks as TMA tiles (two per chunk) instead of one bulk copy per row
 		int detect_lists = 1; // detect_lane_kernel: rounds after the first walk a list of the bursts left for them
 		int detect_lane = 1; // 1: detect_lane_kernel (lane = burst, one launch) for the normal-burst geometry; 0: corr_nb_kernel + peak_kernel
@@ -386,6 +387,7 @@ int trxb200_init(int device, trxb200_ctx **out)
 		env_int("TRXB200_VITAC_LANE", t.vitac_lane);
 		env_int("TRXB200_DETECT_LANE", t.detect_lane);
 		env_int("TRXB200_DETECT_LISTS", t.detect_lists);
+		env_int("TRXB200_DETECT_TMA16", t.detect_tma16);
 		env_int("TRXB200_DETECT_TMA", t.detect_tma);
 		env_int("TRXB200_PULL_CHUNK", t.pull_chunk);
 		env_int("TRXB200_HOST_CHUNK", t.host_chunk);
@@ -757,11 +759,12 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 			dp.tma_on = 0;
 			dp.tmap = nullptr;
 			dp.tma_shift = 0;
-			if (!iq && !dp.list_in && tn.detect_tma && n >= 2 && (reinterpret_cast<uintptr_t>(bursts) & 7u) == 0) {
-				// (an array that starts 8 bytes off the 16-byte grid is described from one sample in front of it; no box reaches that sample)
-				dp.tma_shift = (int)((reinterpret_cast<uintptr_t>(bursts) >> 3) & 1u);
-				const float *tbase = bursts - 2 * dp.tma_shift;
-				// the rows taken two at a time are a legal TMA tensor: [n / 2][4 * stride] floats, row pitch 16 * stride bytes
+			// float rows taken two at a time ([n / 2][4 * stride] floats, row pitch 16 * stride bytes) and int16 rows taken four at a
+			// time ([n / 4][4 * iq_stride] I/Q pairs, row pitch 16 * iq_stride bytes) are legal TMA tensors.  An array that starts off
+			// the 16-byte grid is described from the grid point in front of it (no box reaches the samples before the array).
+			const bool tma_f = !iq && n >= 2 && (reinterpret_cast<uintptr_t>(bursts) & 7u) == 0;
+			const bool tma_i = iq && n >= 4 && (reinterpret_cast<uintptr_t>(iq) & 3u) == 0 && tn.detect_tma16;
+			if ((tma_f || tma_i) && !dp.list_in && tn.detect_tma) {
 				typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
 							     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
 							     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -779,18 +782,33 @@ static int launch_detect(trxb200_ctx *ctx, cudaStream_t st, DetectScratch &ws, c
 				}
 				if (encode && ctx->d_tmap) {
 					alignas(64) CUtensorMap tm;
-					const cuuint64_t gdim[2] = { (cuuint64_t)4 * (cuuint64_t)stride, (cuuint64_t)(n / 2) };
-					const cuuint64_t gstr[1] = { (cuuint64_t)16 * (cuuint64_t)stride };
-					const cuuint32_t box[2] = { 2u * kDlBulkPitch, 16u }, est[2] = { 1u, 1u }; // 18 samples x 16 row pairs
-					if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(tbase), gdim, gstr, box, est,
-						   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-						   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+					CUresult er;
+					int shift;
+					if (tma_f) {
+						shift = (int)((reinterpret_cast<uintptr_t>(bursts) >> 3) & 1u);
+						const cuuint64_t gdim[2] = { (cuuint64_t)4 * (cuuint64_t)stride, (cuuint64_t)(n / 2) };
+						const cuuint64_t gstr[1] = { (cuuint64_t)16 * (cuuint64_t)stride };
+						const cuuint32_t box[2] = { 2u * kDlBulkPitch, 16u }, est[2] = { 1u, 1u }; // kDlBulkPitch samples x 16 row pairs
+						er = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(bursts - 2 * shift), gdim, gstr, box, est,
+							    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+							    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+					} else {
+						shift = (int)((reinterpret_cast<uintptr_t>(iq) >> 2) & 3u);
+						const cuuint64_t gdim[2] = { (cuuint64_t)4 * (cuuint64_t)iq_stride, (cuuint64_t)(n / 4) };
+						const cuuint64_t gstr[1] = { (cuuint64_t)16 * (cuuint64_t)iq_stride };
+						const cuuint32_t box[2] = { (cuuint32_t)kDlBox16, 8u }, est[2] = { 1u, 1u }; // kDlBox16 I/Q pairs x 8 row quadruples
+						er = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<int16_t *>(iq - 2 * shift), gdim, gstr, box, est,
+							    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+							    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+					}
+					if (er == CUDA_SUCCESS) {
 						// the descriptor lives in global memory (one slot per round; stream order keeps a slot intact while a
 						// kernel that reads it is still running)
 						unsigned char *slot = reinterpret_cast<unsigned char *>(ctx->d_tmap) + (size_t)(r & 3) * sizeof(CUtensorMap);
 						if (cudaMemcpyAsync(slot, &tm, sizeof(CUtensorMap), cudaMemcpyHostToDevice, st) == cudaSuccess) {
 							dp.tmap = slot;
 							dp.tma_on = 1;
+							dp.tma_shift = shift;
 						} else {
 							cudaGetLastError();
 						}

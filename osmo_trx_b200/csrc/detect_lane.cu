@@ -29,8 +29,10 @@
 namespace trxb200 {
 
 constexpr int kDlWarps = 12;	 // warps per CTA, one CTA per SM
-constexpr int kDlStagePitch = 17; // samples per row of the staging chunk (16 + 1: lanes = rows read conflict free)
-constexpr int kDlChunk = 24;	  // float rows: window samples per chunk (seven chunks cover the 152-sample window; int16 rows: sixteen)
+constexpr int kDlChunk = 24;	  // float rows: window samples per chunk (seven chunks cover the 152-sample window)
+constexpr int kDlChunk16 = 48;	  // int16 rows: window samples per chunk (four chunks; a box row of 52 I/Q pairs is as long as a float box row)
+constexpr int kDlStagePitch = kDlChunk16 + 1; // int16 rows, cp.async form: words per row of the staging chunk (odd: lanes = rows read conflict free)
+constexpr int kDlBox16 = kDlChunk16 + 4;	  // int16 rows, TMA form: words per box row (a chunk + the up to 3 samples in front of a window that starts off the 16-byte grid)
 constexpr int kDlBulkPitch = kDlChunk + 2; // float rows, bulk copies: a chunk + the 2 samples a row that starts off the 16-byte grid needs (208 B)
 struct DetLaneParams {
 	const void *tmap; // CUtensorMap (in global memory, 64-byte aligned) over the burst rows taken two at a time (below); used when tma_on
@@ -134,7 +136,6 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 		float2 dec[35];
 		if (any) {
 			constexpr unsigned SB = I16 ? 4u : 8u; // bytes per sample
-			const int sub = lane & 15, half = lane >> 4;
 			// Rows of one tile usually share the window start (one burst type): then row r's window is rp0 + r * rowbytes and
 			// no lane has to ask another for its pointer (the shuffles of the general form were a third of all stall samples)
 			const unsigned runmask = __ballot_sync(0xffffffffu, run);
@@ -143,31 +144,22 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 			const bool uniform = !listed && __ballot_sync(0xffffffffu, run && s_lo != s_lo0) == 0u;
 			const unsigned long long rowbytes = (unsigned long long)SB * (unsigned long long)(I16 ? cp.iq_stride : cp.stride);
 			const unsigned long long rp0 = __shfl_sync(0xffffffffu, rowp, lead) - (unsigned long long)lead * rowbytes; // row 0 of the tile
+			// int16 rows without the TMA: 4-byte asynchronous copies, eight lanes per row (32 contiguous bytes), four rows per instruction
 			auto issue = [&](int c) {
-				const unsigned buf = stg_s + SB * (unsigned)((c & 1) * 32 * kDlStagePitch);
-				if (uniform) {
-					unsigned dst = buf + SB * (unsigned)(half * kDlStagePitch + sub);
-					unsigned long long src = rp0 + (unsigned long long)half * rowbytes + SB * (unsigned)(16 * c + sub);
+				const unsigned buf = stg_s + 4u * (unsigned)((c & 1) * 32 * kDlStagePitch);
+				const int rsub = lane >> 3, s8 = lane & 7;
 #pragma unroll
-					for (int i = 0; i < 16; i++) {
-						if ((runmask >> (2 * i + half)) & 1u) {
-							if constexpr (I16) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-							else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-						}
-						dst += SB * (unsigned)(2 * kDlStagePitch);
-						src += 2 * rowbytes;
-					}
-				} else {
+				for (int i = 0; i < 8; i++) {
+					const int r = 4 * i + rsub;
+					unsigned long long rp;
+					if (uniform) rp = ((runmask >> r) & 1u) ? rp0 + (unsigned long long)r * rowbytes : 0ull;
+					else rp = __shfl_sync(0xffffffffu, rowp, r);
+					if (rp) {
+						const unsigned dst = buf + 4u * (unsigned)(r * kDlStagePitch + s8);
+						const unsigned long long src = rp + 4u * (unsigned)(kDlChunk16 * c + s8);
 #pragma unroll
-					for (int i = 0; i < 16; i++) {
-						const int r = 2 * i + half;
-						const unsigned long long rp = __shfl_sync(0xffffffffu, rowp, r);
-						if (rp) {
-							const unsigned dst = buf + SB * (unsigned)(r * kDlStagePitch + sub);
-							const unsigned long long src = rp + SB * (unsigned)(16 * c + sub);
-							if constexpr (I16) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-							else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-						}
+						for (int k = 0; k < kDlChunk16 / 8; k++)
+							asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 32u * (unsigned)k), "l"(src + 32u * (unsigned)k) : "memory");
 					}
 				}
 				asm volatile("cp.async.commit_group;" ::: "memory");
@@ -195,6 +187,7 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 			// float rows on the 16-byte grid, one window start for the whole tile, rows inside the TMA's view: two tile copies
 			bool tma = false;
 			if constexpr (!I16) tma = P.tma_on && uniform && (((p.n & 1) == 0) || tile * 32 + 32 <= (p.n & ~1));
+			else tma = P.tma_on && uniform && (((p.n & 3) == 0) || tile * 32 + 32 <= (p.n & ~3));
 			// (the TMA wants the start of a box on the 16-byte grid: a row's chunk starts at the even sample at or below the window
 			// sample and is kDlBulkPitch samples long; e_even / e_odd = the sample in front for the even and the odd rows of the tile)
 			const int s_t = s_lo0 + P.tma_shift; // window start as a sample index of the tensor's rows
@@ -214,22 +207,52 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 			// the lane's row in a staged chunk: box lane & 1 (even / odd rows), row lane >> 1, kDlBulkPitch samples per row, its window
 			// sample t at t + e; rows 208 bytes apart and the two boxes one sample out of step: conflict-free 8-byte reads
 			const int trow = (lane & 1) * 16 * kDlBulkPitch + (lane >> 1) * kDlBulkPitch + ((lane & 1) ? e_odd : e_even);
+			// int16 rows: 2,500 bytes apart, so FOUR rows make a legal TMA row (16 * iq_stride bytes): the slot array is described as
+			// [n / 4][4 * iq_stride] 4-byte I/Q pairs, a chunk of the warp's 32 slots is four boxes of 8 rows x kDlBox16 pairs (row class
+			// r = slot & 3 at inner coordinate r * iq_stride + ...), each starting on the 16-byte grid at or below its window sample
+			const int s_t16 = s_lo0 + P.tma_shift;
+			const int cls = lane & 3;
+			const int e16 = (cls * cp.iq_stride + s_t16) & 3; // samples in front of this lane's window in its box row
+			auto issue_tma16 = [&](int c) {
+				const unsigned bar = bar_s + 8u * (unsigned)(c & 1);
+				fence_proxy_async();
+				__syncwarp();
+				if (lane == 0) {
+					mbar_arrive_expect_tx(bar, 4u * 8u * (unsigned)(kDlBox16 * 4));
+					const unsigned dst = stg_s + (unsigned)((c & 1) * 4 * 8 * kDlBox16 * 4);
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						const int x0 = r * cp.iq_stride + s_t16 + kDlChunk16 * c;
+						tma_load_2d(dst + (unsigned)(r * 8 * kDlBox16 * 4), P.tmap, x0 & ~3, tile * 8, bar);
+					}
+				}
+			};
+			const int trow16 = cls * 8 * kDlBox16 + (lane >> 2) * kDlBox16 + e16;
 			// The decimator consumes a chunk eight samples at a time: sub-step g brings window samples 8g .. 8g + 7 and completes the
 			// outputs 2g - 3 and 2g - 2 (output j reads window samples 4j .. 4j + 15), from a register window of 12 + 8 samples.
-			constexpr int CS = I16 ? 16 : kDlChunk, NCH = (152 + CS - 1) / CS, SUB = CS / 8;
+			constexpr int CS = I16 ? kDlChunk16 : kDlChunk, NCH = (152 + CS - 1) / CS, SUB = CS / 8;
 			float2 X[20];
 			__syncwarp(); // the previous tile's peak logic is done with the tile the chunks overlay
-			if constexpr (I16) { issue(0); issue(1); }
-			else if (tma) { issue_tma(0); issue_tma(1); }
+			if constexpr (I16) {
+				if (tma) { issue_tma16(0); issue_tma16(1); }
+				else { issue(0); issue(1); }
+			} else if (tma) { issue_tma(0); issue_tma(1); }
 			else { issue_bulk(0); issue_bulk(1); }
 #pragma unroll
 			for (int c = 0; c < NCH; c++) {
-				const float2 *row;
+				const float2 *row = stg;
+				const unsigned *row16 = reinterpret_cast<const unsigned *>(stg);
 				if constexpr (I16) {
-					if (c < NCH - 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-					else asm volatile("cp.async.wait_group 0;" ::: "memory");
-					__syncwarp();
-					row = stg; // (int16 rows are addressed as words below)
+					if (tma) {
+						mbar_wait(bar_s + 8u * (unsigned)(c & 1), (phase >> (c & 1)) & 1u);
+						phase ^= 1u << (c & 1);
+						row16 += (c & 1) * 4 * 8 * kDlBox16 + trow16;
+					} else {
+						if (c < NCH - 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+						else asm volatile("cp.async.wait_group 0;" ::: "memory");
+						__syncwarp();
+						row16 += ((c & 1) * 32 + lane) * kDlStagePitch;
+					}
 				} else {
 					mbar_wait(bar_s + 8u * (unsigned)(c & 1), (phase >> (c & 1)) & 1u);
 					phase ^= 1u << (c & 1);
@@ -239,7 +262,7 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 				for (int u = 0; u < SUB; u++) {
 					if constexpr (I16) {
 #pragma unroll
-						for (int t = 0; t < 8; t++) X[12 + t] = cvt_s2(reinterpret_cast<const unsigned *>(stg)[((c & 1) * 32 + lane) * kDlStagePitch + 8 * u + t]);
+						for (int t = 0; t < 8; t++) X[12 + t] = cvt_s2(row16[8 * u + t]);
 					} else {
 #pragma unroll
 						for (int t = 0; t < 8; t++) X[12 + t] = row[8 * u + t];
@@ -248,8 +271,10 @@ detect_lane_kernel(const __grid_constant__ DetLaneParams P)
 						// every lane holds the rest of the chunk: its buffer takes the chunk after next
 						__syncwarp();
 						if (c + 2 < NCH) {
-							if constexpr (I16) issue(c + 2);
-							else if (tma) issue_tma(c + 2);
+							if constexpr (I16) {
+								if (tma) issue_tma16(c + 2);
+								else issue(c + 2);
+							} else if (tma) issue_tma(c + 2);
 							else issue_bulk(c + 2);
 						}
 					}

@@ -629,6 +629,34 @@ def _pull_host_matches_device_path(trx, checker):
     assert trx.pull(dev(iq[:0]), dev(typ[:0]), dev(tsc[:0]), dev(mt[:0]), dev(fn[:0].astype(np.int32)), dev(tn[:0]), 4) is not None
 
 
+def test_pull_slots_off_the_16_byte_grid(trx, checker):
+    """int16 slot arrays that start 4, 8 or 12 bytes off the 16-byte grid, and slot counts that are not a multiple of four:
+    detect_lane_kernel<int16> describes the slots to the TMA four at a time from the grid point in front of the array (the last
+    partial tile takes the 4-byte copies).  Detection outputs, energies and header bytes must equal the aligned run's bit for
+    bit; the soft bytes may differ by one step where the demodulator's other summation order crosses a rounding boundary."""
+    for n in (4096, 4096 + 37):
+        rng, tsc, rx, fn, tn = pull_inputs(checker, n, 35)
+        iq = to_i16(rx, 8000.0)
+        typ = np.full(n, TSC, np.uint8)
+        typ[::31] = IDLE
+        args = [dev(typ), dev(tsc), dev(np.full(n, 4, np.int16)), dev(fn.astype(np.int32)), dev(tn), 4]
+        with detect_cfg(trx, (16, 1)):
+            a = {k: v.cpu().numpy() for k, v in trx.pull(dev(iq), *args).items()}
+            flat = torch.zeros((n * 625 + 4, 2), dtype=torch.int16, device="cuda")
+            for off in (1, 2, 3):
+                view = flat[off:off + n * 625].view(n, 625, 2)
+                view.copy_(dev(iq))
+                assert (view.data_ptr() >> 2) & 3 == off
+                b = {k: v.cpu().numpy() for k, v in trx.pull(view, *args).items()}
+                for k in a:
+                    if k == "pkt":
+                        d = np.abs(a[k].astype(np.int32) - b[k].astype(np.int32))
+                        assert d.max() <= 1 and (d[:, :11] == 0).all(), (n, off, k)
+                    else:
+                        assert np.array_equal(a[k], b[k], equal_nan=True), (n, off, k)
+        assert (a["rc"] > 0).sum() > 0.8 * n
+
+
 def test_scheduler_expected_corr_type(trx, checker):
     """Burst-type scheduler (Transceiver::expectedCorrType + the max_toa choice of pullRadioVector) on the device:
     several channels with different timeslot configurations in one batch, against the CPU checker per channel."""
