@@ -107,7 +107,7 @@ struct trxb200_ctx {
 	} tune;
 	std::string err;
 	// once-per-context device setup (function attributes and __constant__ tables are per device)
-	bool cfg_fused = false, cfg_detlane = false;
+	bool cfg_fused = false, cfg_detlane = false, cfg_rspq[2] = { false, false };
 	bool cfg_detect = false, cfg_demod = false, cfg_ch64 = false, cfg_sy64 = false, sched_tables = false;
 	HostStage *stage = nullptr;
 	PullScratch pull;	      // trxb200_pull_batch

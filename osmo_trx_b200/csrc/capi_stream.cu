@@ -209,7 +209,7 @@ static int launch_resampler_pq(trxb200_resampler *r, const float *in, int in_str
 		std::memcpy(M.tp[rho], r->taps.data() + (size_t)((Q * rho) % P) * 16, 16 * sizeof(float));
 	const int warps = (int)std::max<size_t>(1, std::min<size_t>(12, (size_t)(225 * 1024 - G::hdr_bytes) / G::warp_bytes));
 	const size_t smem = G::hdr_bytes + (size_t)warps * G::warp_bytes;
-	static bool cfg = false;
+	bool &cfg = ctx->cfg_rspq[P > Q ? 0 : 1]; // (the attribute is per device: a flag per context, not per process)
 	if (!cfg) {
 		CK(cudaFuncSetAttribute(resampler_pq_kernel<P, Q, R, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
 		cfg = true;
