@@ -111,6 +111,8 @@ __device__ __forceinline__ float vl_mf(const float2 (&win)[20], const float2 (&c
 	return acc;
 }
 
+__device__ __forceinline__ void vl_prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 template <int TLEN, bool LANE_SEQ>
 __global__ void __launch_bounds__(kVlWarps * 32, 2)
 vitac_lane_kernel(VitacParams p)
@@ -172,6 +174,20 @@ vitac_lane_kernel(VitacParams p)
 			}
 		}
 		__syncwarp(); // the search area becomes the decision words
+		// Every thread walks its own row, so a load instruction touches 32 lines and the register window only reaches one step
+		// pair ahead: 39 % of the stall samples waited for those loads (ncu, long_scoreboard).  The rows are therefore asked for
+		// in L2 well ahead of the walk: the first kilobyte of the burst now, a line every other step pair one kilobyte ahead in
+		// the loop below, and the search region of the warp's NEXT tile while this one is equalised.
+		{
+			const float2 *xh = in + st;
+#pragma unroll
+			for (int k = 0; k < 9; k++) vl_prefetch_l2(xh + 16 * k);
+			const int bn = (tile + (int)gridDim.x * kVlWarps) * 32 + lane;
+			if (!p.cir_in && bn < p.n) {
+				const float2 *inn = reinterpret_cast<const float2 *>(p.bufs) + (size_t)bn * p.stride + p.offset + (p.row_shift ? p.row_shift[bn] : 0) + s0;
+				for (int k = 0; 16 * k < nwin + 4 * TLEN; k++) vl_prefetch_l2(inn + 16 * k);
+			}
+		}
 		// ---- rhh[k] = conj(autocorr(cir)[4k]) (:159-166, 93-95); increments viterbi_detector.cc:93-100 ----
 		float inc[8];
 		{
@@ -222,6 +238,7 @@ vitac_lane_kernel(VitacParams p)
 #pragma unroll
 				for (int t = 0; t < 8; t++) nx[t] = __ldg(&x[4 * n + 24 + t]);
 			}
+			if ((n & 2) == 0) vl_prefetch_l2(&x[min(4 * n + 24 + 128, 4 * N + 12)]);
 			words[n * 32] = vl_acs<true>(pa, pb, vl_mf<true, 20>(win, cir), inc);
 #pragma unroll
 			for (int t = 0; t < 16; t++) win[t] = win[t + 4];
