@@ -45,8 +45,12 @@ def run(cfg, rx, typ, tsc, mt, bound, det_cfg, steps, ref=None):
     ms = e0.elapsed_time(e1) / steps
     same = None
     if ref is not None:
-        same = all(torch.equal(out[k], ref[k]) for k in ("rc", "toa", "amp", "ci", "tsc", "flags")) and \
-            torch.equal(out["soft"][out["rc"] > 0], ref["soft"][ref["rc"] > 0])
+        # bitwise comparison (torch.equal is false on any NaN, and C/I is NaN where its ratio is undefined: the first
+        # version of this sweep therefore printed same_as_serial = false for every geometry, profiles/r1t_overlap_sweep.txt)
+        def same_bits(a, b):
+            return a.shape == b.shape and torch.equal(a.contiguous().view(torch.uint8), b.contiguous().view(torch.uint8))
+        same = all(same_bits(out[k], ref[k]) for k in ("rc", "toa", "amp", "ci", "tsc", "flags")) and \
+            same_bits(out["soft"][out["rc"] > 0], ref["soft"][ref["rc"] > 0])
     res = {k: v.clone() for k, v in out.items()} if ref is None else None
     trx.close()
     print(json.dumps({"cfg": cfg, "ms_per_step": round(ms, 4), "bursts_per_s": round(n / ms * 1e3, 0), "same_as_serial": same}),
