@@ -970,6 +970,17 @@ peak_kernel(PeakParams p)
 		Attempt at;
 		const bool run = valid && attempt_runs(type, tsc, T, p.max_toa_bound, p.ndmax, p.round, rc, sinfo, at);
 
+		// the warp's NEXT tile is asked for in L2 now (its vectors and powers come from DRAM - the correlator wrote them a whole
+		// batch ago - and every lane walks a row of its own: 57 % of the stall samples waited on these loads)
+		{
+			const long bn = (long)(tile + gridDim.x * wpb) * 32 + lane;
+			if (bn < p.n) {
+				const char *c0 = reinterpret_cast<const char *>(p.corr + (size_t)bn * p.lmax);
+				for (int o = 0; o < p.lmax * 8; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c0 + o));
+				const char *w0 = reinterpret_cast<const char *>(p.pwr + (size_t)bn * p.ndmax);
+				for (int o = 0; o < p.ndmax * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + o));
+			}
+		}
 		// ---- bring the tile's correlation vectors in: global [burst][lmax] -> shared [kPadRows + i][lane];
 		//      each lane copies its own burst's row (16-byte loads at row stride, conflict-free 8-byte stores) ----
 		__syncwarp();
