@@ -4,8 +4,8 @@
 // resampler16_kernel (filterbank.cu) reads a private 16-sample window per output from shared memory: 32 data-pipe
 // wavefronts per output, 76 % of the LSU peak at a third of the HBM roofline.  Consecutive outputs of one polyphase
 // period look at windows that move by 0, 1 or 2 samples, so here a thread produces R CONSECUTIVE outputs of a period from
-// one window of at most 20 samples held in registers (4 loads per output instead of 16), with the ratio a template
-// parameter: window offsets are immediates and the taps are operands from the kernel's parameter block.
+// one window of at most 21 samples held in registers (4 loads per output instead of 16), with the ratio a template
+// parameter: window offsets are immediates; the taps are broadcast 16-byte loads from the CTA's copy in shared memory.
 //   warp      = a tile of 32 consecutive periods of one stream, lanes = periods.  Nothing is shared between warps: no
 //               block-wide barrier anywhere (resampler_up_kernel, the first attempt at register windows, spent its time in
 //               two of them per tile).
