@@ -829,8 +829,8 @@ def aux_wideband(args, trx, device, rank, world, dist):
     in_b = 625 * 48 / 65 * 8      # wideband bytes per slot of one channel
     return dict(step=step, units=n_eff, unit="bursts/s", metric="GSM bursts/sec detected+demodulated (sps=4)",
                 alg_step=in_b + 592 + 24,
-                alg_kernel={"channelizer64_kernel": 2 * in_b, "resampler16_kernel": in_b + 5000, "demod_kernel": 5000 + 592 + 16,
-                            "corr_kernel": 1216 + 300, "peak_kernel": 300 + 24},
+                alg_kernel={"channelizer64_kernel": 2 * in_b, "resampler16_kernel": in_b + 5000, "resampler_pq_kernel": in_b + 5000,
+                            "demod_kernel": 5000 + 592 + 16, "detect_lane_kernel": 1216 + 24, "corr_kernel": 1216 + 300, "peak_kernel": 300 + 24},
                 cpu=cpu, e2e=e2e, det=lambda: float((res["rc"].view(M, K)[:, :nsl] > 0).float().mean().item()),
                 config={"workload": "cfg5: 64-ARFCN wideband stream -> Channelizer(64,192) -> Resampler(65,48) -> slots -> "
                                     "detectAnyBurst(TSC,max_toa=4)+demodAnyBurst",
@@ -1052,7 +1052,8 @@ def main():
     # figure is SURVEY.md 8(d)'s 5,616 B per normal burst (6,800 EDGE)
     soft_b = 444 * 4 if args.workload == "edge" else 148 * 4
     alg_kernel = {"demod_kernel": 5000 + soft_b + 16, "corr_kernel": (4 * (15 + 16 + bound) + 12) * 8 + (16 + bound) * 8 + (31 + bound) * 4,
-                  "peak_kernel": (16 + bound) * 8 + 16 * 4 + 24}
+                  "peak_kernel": (16 + bound) * 8 + 16 * 4 + 24,
+                  "detect_lane_kernel": (4 * (15 + 16 + bound) + 12) * 8 + 24}  # correlator window + results, no intermediates
     launches_per_step = {k: v[1] / args.steps for k, v in prof.items()}
     alg = ALG_BYTES[args.workload]
     dom_alg = alg_kernel.get(dom, alg)
